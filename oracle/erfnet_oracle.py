@@ -1,0 +1,271 @@
+"""CPU oracle for the ERFNet hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product package
+(``erfnet_pytorch_b200``) never does and has no CPU fallback.
+
+What it is: a functional, state_dict-driven restatement of the reference's arithmetic in
+plain fp32 torch ops on the CPU (the reference's arithmetic *is* torch ops; nothing here is
+copied -- each function re-derives the dataflow from the cited reference lines and takes the
+weights from a flat ``{key: tensor}`` dict with the reference's checkpoint key names).
+
+Parity pin: the reference ships no tests or golden vectors, so this
+oracle is pinned against outputs of the reference modules themselves, executed in the build
+container by ``oracle/make_golden.py`` (which imports /root/reference by path) and committed
+under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` re-checks the oracle against
+them on every CPU run.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+StateDict = Dict[str, torch.Tensor]
+BN_EPS = 1e-3  # eval/erfnet.py:18,34,40,103
+
+
+# ----------------------------------------------------------------------------------------------
+# deterministic weights (independent of module construction order, so that the reference, the
+# oracle and the CUDA modules can all be given the same values without sharing RNG state)
+# ----------------------------------------------------------------------------------------------
+def erfnet_param_shapes(num_classes: int = 20) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape for every entry of ``eval/erfnet.py::ERFNet(num_classes).state_dict()``
+    (345 entries for 20 classes)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(p, c):
+        shapes[p + ".weight"] = (c,)
+        shapes[p + ".bias"] = (c,)
+        shapes[p + ".running_mean"] = (c,)
+        shapes[p + ".running_var"] = (c,)
+        shapes[p + ".num_batches_tracked"] = ()
+
+    def down(p, ci, co):  # eval/erfnet.py:12-18
+        shapes[p + ".conv.weight"] = (co - ci, ci, 3, 3)
+        shapes[p + ".conv.bias"] = (co - ci,)
+        bn(p + ".bn", co)
+
+    def nb(p, c):  # eval/erfnet.py:26-42
+        for name, k in (("conv3x1_1", (3, 1)), ("conv1x3_1", (1, 3))):
+            shapes[f"{p}.{name}.weight"] = (c, c) + k
+            shapes[f"{p}.{name}.bias"] = (c,)
+        bn(p + ".bn1", c)
+        for name, k in (("conv3x1_2", (3, 1)), ("conv1x3_2", (1, 3))):
+            shapes[f"{p}.{name}.weight"] = (c, c) + k
+            shapes[f"{p}.{name}.bias"] = (c,)
+        bn(p + ".bn2", c)
+
+    def up(p, ci, co):  # eval/erfnet.py:99-103
+        shapes[p + ".conv.weight"] = (ci, co, 3, 3)
+        shapes[p + ".conv.bias"] = (co,)
+        bn(p + ".bn", co)
+
+    down("encoder.initial_block", 3, 16)
+    down("encoder.layers.0", 16, 64)
+    for i in range(1, 6):
+        nb(f"encoder.layers.{i}", 64)
+    down("encoder.layers.6", 64, 128)
+    for i in range(7, 15):
+        nb(f"encoder.layers.{i}", 128)
+    shapes["encoder.output_conv.weight"] = (num_classes, 128, 1, 1)
+    shapes["encoder.output_conv.bias"] = (num_classes,)
+    up("decoder.layers.0", 128, 64)
+    nb("decoder.layers.1", 64)
+    nb("decoder.layers.2", 64)
+    up("decoder.layers.3", 64, 16)
+    nb("decoder.layers.4", 16)
+    nb("decoder.layers.5", 16)
+    shapes["decoder.output_conv.weight"] = (16, num_classes, 2, 2)
+    shapes["decoder.output_conv.bias"] = (num_classes,)
+    return shapes
+
+
+def _key_seed(seed: int, key: str) -> int:
+    h = 1469598103934665603
+    for ch in key.encode():
+        h = ((h ^ ch) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return (h ^ (seed * 0x9E3779B97F4A7C15)) & 0x7FFFFFFF
+
+
+def make_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, gain: float = 1.0) -> StateDict:
+    """Deterministic "trained-like" weights: conv weights ~ U(+-gain*sqrt(3/fan_in)) (keeps activations
+    O(1) through 70 layers), small biases, BN gamma in [0.7,1.3], beta in +-0.2, running_mean +-0.3,
+    running_var in [0.5,1.5].  Values depend only on (seed, key)."""
+    sd: StateDict = {}
+    for key, shape in shapes.items():
+        g = torch.Generator().manual_seed(_key_seed(seed, key))
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(8, dtype=torch.int64)
+        elif key.endswith("running_mean"):
+            sd[key] = (torch.rand(shape, generator=g) - 0.5) * 0.6
+        elif key.endswith("running_var"):
+            sd[key] = 0.5 + torch.rand(shape, generator=g)
+        elif ".bn" in key and key.endswith(".weight"):
+            sd[key] = 0.7 + 0.6 * torch.rand(shape, generator=g)
+        elif ".bn" in key and key.endswith(".bias"):
+            sd[key] = (torch.rand(shape, generator=g) - 0.5) * 0.4
+        elif key.endswith(".bias") or len(shape) == 1:
+            sd[key] = (torch.rand(shape, generator=g) - 0.5) * 0.2
+        else:
+            if "decoder" in key and ".conv." in key or key.startswith("decoder.output_conv"):
+                fan_in = shape[0] * shape[2] * shape[3] / 4.0  # ConvTranspose, stride 2: ~1/4 of the taps hit
+            else:
+                fan_in = shape[1] * shape[2] * shape[3]
+            bound = gain * math.sqrt(3.0 / fan_in)
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
+
+
+# ----------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------
+def _bn(x, sd, p, training, momentum=0.1):
+    """nn.BatchNorm2d(C, eps=1e-3): train = batch mean / biased var, running stats updated in place with
+    momentum 0.1 and the unbiased var; eval = running stats (eval/erfnet.py:18,22)."""
+    if training:
+        sd[p + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training, momentum, BN_EPS)
+
+
+def downsampler_block(x, sd: StateDict, p: str, training=False, use_batchnorm=True):
+    """eval/erfnet.py:20-23 (gated BN: train/erfnet_blocks.py:24-29): cat([conv3x3 s2 p1, maxpool2x2]) -> BN -> ReLU;
+    conv channels first, pooled input channels after."""
+    y = torch.cat([F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], stride=2, padding=1),
+                   F.max_pool2d(x, 2, stride=2)], 1)
+    if use_batchnorm:
+        y = _bn(y, sd, p + ".bn", training)
+    return F.relu(y)
+
+
+def non_bottleneck_1d(x, sd: StateDict, p: str, dilated: int, dropprob: float = 0.0, training=False,
+                      drop_scale: Optional[torch.Tensor] = None, use_batchnorm=True):
+    """eval/erfnet.py:45-61.  ``drop_scale`` is the Dropout2d multiplier [N,C,1,1] (0 or 1/(1-p)); when None and
+    training with dropprob != 0 it is drawn with torch RNG exactly like nn.Dropout2d (noise shape [N,C,1,1])."""
+    y = F.relu(F.conv2d(x, sd[p + ".conv3x1_1.weight"], sd[p + ".conv3x1_1.bias"], padding=(1, 0)))
+    y = F.conv2d(y, sd[p + ".conv1x3_1.weight"], sd[p + ".conv1x3_1.bias"], padding=(0, 1))
+    if use_batchnorm:
+        y = _bn(y, sd, p + ".bn1", training)
+    y = F.relu(y)
+    y = F.relu(F.conv2d(y, sd[p + ".conv3x1_2.weight"], sd[p + ".conv3x1_2.bias"], padding=(dilated, 0),
+                        dilation=(dilated, 1)))
+    y = F.conv2d(y, sd[p + ".conv1x3_2.weight"], sd[p + ".conv1x3_2.bias"], padding=(0, dilated), dilation=(1, dilated))
+    if use_batchnorm:
+        y = _bn(y, sd, p + ".bn2", training)
+    if dropprob != 0 and training:  # eval/erfnet.py:58-59
+        if drop_scale is None:
+            y = F.dropout2d(y, dropprob, True)
+        else:
+            y = y * drop_scale
+    return F.relu(y + x)
+
+
+def upsampler_block(x, sd: StateDict, p: str, training=False, use_batchnorm=True):
+    """eval/erfnet.py:105-108: ConvTranspose2d(3, s2, p1, op1) -> BN -> ReLU."""
+    y = F.conv_transpose2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], stride=2, padding=1, output_padding=1)
+    if use_batchnorm:
+        y = _bn(y, sd, p + ".bn", training)
+    return F.relu(y)
+
+
+ENC_DILATIONS = (2, 4, 8, 16, 2, 4, 8, 16)  # eval/erfnet.py:78-82
+
+
+def encoder_forward(x, sd: StateDict, predict=False, training=False, drop_scales=None, p="encoder", dropprob=0.1):
+    """eval/erfnet.py:87-96.  ``drop_scales``: optional {layer_prefix: [N,C,1,1]} of Dropout2d multipliers."""
+    ds = drop_scales or {}
+    y = downsampler_block(x, sd, p + ".initial_block", training)
+    y = downsampler_block(y, sd, p + ".layers.0", training)
+    for i in range(1, 6):
+        q = f"{p}.layers.{i}"
+        y = non_bottleneck_1d(y, sd, q, 1, dropprob, training, ds.get(q))
+    y = downsampler_block(y, sd, p + ".layers.6", training)
+    for i, d in enumerate(ENC_DILATIONS):
+        q = f"{p}.layers.{7 + i}"
+        y = non_bottleneck_1d(y, sd, q, d, dropprob, training, ds.get(q))
+    if predict:
+        y = F.conv2d(y, sd[p + ".output_conv.weight"], sd[p + ".output_conv.bias"])
+    return y
+
+
+def decoder_forward(x, sd: StateDict, training=False, p="decoder"):
+    """eval/erfnet.py:126-134."""
+    y = upsampler_block(x, sd, p + ".layers.0", training)
+    y = non_bottleneck_1d(y, sd, p + ".layers.1", 1, 0.0, training)
+    y = non_bottleneck_1d(y, sd, p + ".layers.2", 1, 0.0, training)
+    y = upsampler_block(y, sd, p + ".layers.3", training)
+    y = non_bottleneck_1d(y, sd, p + ".layers.4", 1, 0.0, training)
+    y = non_bottleneck_1d(y, sd, p + ".layers.5", 1, 0.0, training)
+    return F.conv_transpose2d(y, sd[p + ".output_conv.weight"], sd[p + ".output_conv.bias"], stride=2)
+
+
+def erfnet_forward(x, sd: StateDict, only_encode=False, training=False, drop_scales=None, dropprob=0.1):
+    """eval/erfnet.py:147-152.  ``dropprob`` = encoder Dropout2d p (0.1 in the reference, eval/erfnet.py:74,79-82)."""
+    if only_encode:
+        return encoder_forward(x, sd, predict=True, training=training, drop_scales=drop_scales, dropprob=dropprob)
+    return decoder_forward(encoder_forward(x, sd, training=training, drop_scales=drop_scales, dropprob=dropprob), sd, training)
+
+
+# ----------------------------------------------------------------------------------------------
+# loss, metric, optimiser
+# ----------------------------------------------------------------------------------------------
+def cross_entropy_2d(logits, target, weight=None, ignore_index=-1):
+    """train/evaluation_functions.py:6-14: nn.CrossEntropyLoss(ignore_index=-1) on [B,C,H,W] logits and int64
+    [B,H,W] targets = sum_valid(w[y]*nll)/sum_valid(w[y]).  The reference drops ``weight``; the extension honours
+    it (weight=None is the fork-exact behaviour)."""
+    logp = F.log_softmax(logits.float(), dim=1)
+    valid = target != ignore_index
+    t = torch.where(valid, target, torch.zeros_like(target))
+    nll = -logp.gather(1, t.unsqueeze(1)).squeeze(1)
+    w = torch.ones_like(nll) if weight is None else weight.float()[t]
+    w = w * valid
+    return (w * nll).sum() / w.sum()
+
+
+def iou_counts(pred: np.ndarray, gt: np.ndarray, n_classes: int = 20, ignore_index: int = 19):
+    """eval/iouEval.py:21-69 restated on integers.  pred, gt: integer label maps of identical shape.
+    tp[c] = #(p==c & g==c); fp[c] = #(p==c & g!=c & g!=ignore); fn[c] = #(p!=c & g==c) for the kept classes
+    (ignore channel dropped when n_classes > ignore_index, eval/iouEval.py:12,48-51)."""
+    ign = ignore_index if n_classes > ignore_index else -1
+    pred = np.asarray(pred).reshape(-1).astype(np.int64)
+    gt = np.asarray(gt).reshape(-1).astype(np.int64)
+    kept = n_classes if ign == -1 else n_classes - 1
+    tp = np.zeros(kept, np.int64)
+    fp = np.zeros(kept, np.int64)
+    fn = np.zeros(kept, np.int64)
+    for c in range(kept):
+        # the reference slices channels [:ignoreIndex], which equals "all but the last" only for ignore==n-1;
+        # keep its exact slice semantics
+        if ign != -1 and c >= ign:
+            break
+        pc = pred == c
+        gc = gt == c
+        tp[c] = np.count_nonzero(pc & gc)
+        fp[c] = np.count_nonzero(pc & ~gc & (gt != ign)) if ign != -1 else np.count_nonzero(pc & ~gc)
+        fn[c] = np.count_nonzero(~pc & gc)
+    return tp, fp, fn
+
+
+def iou_from_counts(tp, fp, fn):
+    """eval/iouEval.py:71-75 (float64 accumulators)."""
+    tp = np.asarray(tp, np.float64)
+    den = tp + np.asarray(fp, np.float64) + np.asarray(fn, np.float64) + 1e-15
+    iou = tp / den
+    return float(iou.mean()), iou
+
+
+def adam_step(p, g, m, v, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-4, weight_decay=1e-6):
+    """torch.optim.Adam as configured by train/main.py:43-46,213 (L2 folded into the gradient, not AdamW).
+    In-place on p, m, v (fp32 tensors); ``step`` is the 1-based step count."""
+    g = g + weight_decay * p
+    m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1 = 1 - betas[0] ** step
+    bc2 = 1 - betas[1] ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+    return p
