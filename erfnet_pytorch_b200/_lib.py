@@ -1,0 +1,76 @@
+"""ctypes binding of liberfnet_b200.so (include/erfnet_b200.h).  There is NO fallback: if the library is missing
+or a call fails, a RuntimeError is raised (the reference surfaces shape errors as torch RuntimeError too)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liberfnet_b200.so")
+
+ERF_F32, ERF_BF16 = 0, 1
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("N", "H", "W", "Cin", "in_ld", "Ho", "Wo", "Cout", "out_ld", "out_coff",
+                 "KH", "KW", "stride", "pad_h", "pad_w", "dil_h", "dil_w", "transposed", "w_ld")]
+
+
+class ConvEpilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p), ("relu", C.c_int), ("mask", C.c_void_p), ("mask_ld", C.c_int),
+                ("add", C.c_void_p), ("add_ld", C.c_int), ("stats", C.c_void_p), ("stats_c", C.c_int)]
+
+
+_vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_SIGNATURES = {
+    "erf_abi_version": [],
+    "erf_conv_fwd": [_vp, _vp, _vp, C.POINTER(ConvGeom), C.POINTER(ConvEpilogue), _i, _vp],
+    "erf_conv_wgrad": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _vp],
+    "erf_maxpool2x2_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp],
+    "erf_maxpool2x2_bwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp],
+    "erf_nchw_f32_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "erf_nhwc_to_nchw_f32": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "erf_affine_act": [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_relu_bwd": [_vp, _i, _vp, _i, _vp, _i, _ll, _i, _i, _vp],
+    "erf_bn_finalize": [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "erf_bn_eval_affine": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp],
+    "erf_bn_bwd_reduce": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "erf_bn_bwd_apply": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "erf_ce_weight_sum": [_vp, _ll, _vp, _i, _i, _vp, _vp],
+    "erf_ce_fwd_bwd": [_vp, _i, _i, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "erf_confusion_hist": [_vp, _vp, _i, _ll, _i, _vp, _vp],
+    "erf_iou_counts": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "erf_argmax": [_vp, _i, _i, _ll, _i, _vp, _i, _i, _vp],
+    "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
+    "erf_umma_probe": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every symbol include/erfnet_b200.h declares (used by the CPU test that checks the library exports them)."""
+    return ["erf_last_error_string"] + list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m erfnet_pytorch_b200.build` "
+                               "(there is no CPU / eager fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.erf_last_error_string.restype = C.c_char_p
+        L.erf_last_error_string.argtypes = []
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"liberfnet_b200: {lib().erf_last_error_string().decode()} (code {rc})")

@@ -1,0 +1,95 @@
+// Shared helpers for the sm_100a kernels behind include/erfnet_b200.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/erfnet_b200.h"
+
+namespace erfk {
+
+void set_error(const char* fmt, ...);
+
+#define ERF_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      erfk::set_error(__VA_ARGS__);        \
+      return ERF_ERR_INVALID_ARGUMENT;    \
+    }                                     \
+  } while (0)
+
+// Launch errors only (never synchronises): the library enqueues on the caller's stream.
+#define ERF_CHECK_LAUNCH(name)                                                    \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      erfk::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+      return ERF_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Load / store N consecutive elements (N*sizeof(T) must be 8 or 16 bytes and the address so aligned).
+template <typename T, int N> struct Vec;
+template <> struct Vec<float, 4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__nv_bfloat16, 4> {
+  float v[4];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+template <> struct Vec<float, 8> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace erfk

@@ -1,0 +1,407 @@
+// Bandwidth-bound pieces of the ERFNet path: layout conversion at the NCHW boundary, MaxPool half of the
+// downsampler, BatchNorm statistics / apply / backward, residual+ReLU, Adam.  All coalesced along the channel
+// (innermost NHWC) dimension; per-channel reductions use shared-memory partials + one atomic per block/channel.
+#include "common.cuh"
+
+namespace erfk {
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, long long HW, long long total_px, T* __restrict__ out, int ld) {
+  // one thread per pixel: reads are coalesced per channel plane, the (small) pixel vector is written contiguously
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_px) return;
+  long long n = p / HW, hw = p % HW;
+  const float* ip = in + n * C * HW + hw;
+  T* op = out + p * ld;
+  for (int c = 0; c < ld; ++c) op[c] = from_f<T>(c < C ? ip[(long long)c * HW] : 0.f);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int ld, int C, long long HW, long long total_px, float* __restrict__ out) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_px) return;
+  long long n = p / HW, hw = p % HW;
+  const T* ip = in + p * ld;
+  float* op = out + n * C * HW + hw;
+  for (int c = 0; c < C; ++c) op[(long long)c * HW] = to_f(ip[c]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ in, int N, int H, int W, int C, int in_ld, T* __restrict__ out, int out_ld,
+                                   int out_coff, const float* __restrict__ scale, const float* __restrict__ shift, int relu, double* stats,
+                                   int stats_c) {
+  extern __shared__ float s_stats[];  // [2*C]
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_stats[i] = 0.f;
+    __syncthreads();
+  }
+  const int Ho = H / 2, Wo = W / 2;
+  long long total = (long long)N * Ho * Wo * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    int oy = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    const T* ip = in + (((size_t)n * H + 2 * oy) * W + 2 * ox) * in_ld + c;
+    float m = to_f(ip[0]);
+    m = fmaxf(m, to_f(ip[in_ld]));
+    m = fmaxf(m, to_f(ip[(size_t)W * in_ld]));
+    m = fmaxf(m, to_f(ip[(size_t)W * in_ld + in_ld]));
+    float o = m;
+    if (scale) o = o * scale[c] + shift[c];
+    if (relu) o = fmaxf(o, 0.f);
+    out[(size_t)p * out_ld + out_coff + c] = from_f<T>(o);
+    if (stats) {
+      atomicAdd(&s_stats[c], m);
+      atomicAdd(&s_stats[C + c], m * m);
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) {
+      atomicAdd(&stats[out_coff + k], (double)s_stats[k]);
+      atomicAdd(&stats[stats_c + out_coff + k], (double)s_stats[C + k]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ in, int N, int H, int W, int C, int in_ld, const T* __restrict__ dout, int out_ld,
+                                   int out_coff, T* __restrict__ dx, int dx_ld) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long total = (long long)N * Ho * Wo * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long p = i / C;
+  int ox = (int)(p % Wo);
+  long long t = p / Wo;
+  int oy = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  size_t base = ((size_t)n * H + 2 * oy) * W + 2 * ox;
+  const T* ip = in + base * in_ld + c;
+  // torch keeps the FIRST maximum in (ky, kx) scan order: update only on strictly greater
+  float m = to_f(ip[0]);
+  size_t arg = 0;
+  float v = to_f(ip[in_ld]);
+  if (v > m) { m = v; arg = 1; }
+  v = to_f(ip[(size_t)W * in_ld]);
+  if (v > m) { m = v; arg = W; }
+  v = to_f(ip[(size_t)W * in_ld + in_ld]);
+  if (v > m) { m = v; arg = (size_t)W + 1; }
+  T* dp = dx + (base + arg) * dx_ld + c;
+  *dp = from_f<T>(to_f(*dp) + to_f(dout[(size_t)p * out_ld + out_coff + c]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void affine_act_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  int per_sample, const T* __restrict__ res, int res_ld, T* __restrict__ out, int out_ld, long long HW,
+                                  int C, long long total4, int relu) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over groups of 4 channels
+  if (i >= total4) return;
+  int c4 = C / 4;
+  int c = (int)(i % c4) * 4;
+  long long p = i / c4;
+  int sidx = per_sample ? (int)(p / HW) * C + c : c;
+  Vec<T, 4> v;
+  v.load(x + (size_t)p * x_ld + c);
+  Vec<T, 4> r;
+  if (res) r.load(res + (size_t)p * res_ld + c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float f = v.v[k];
+    if (scale) f = f * scale[sidx + k] + shift[sidx + k];
+    if (res) f += r.v[k];
+    if (relu) f = fmaxf(f, 0.f);
+    v.v[k] = f;
+  }
+  v.store(out + (size_t)p * out_ld + c);
+}
+
+// out = g * (mask > 0)      (ReLU backward as a standalone op)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ g, int g_ld, const T* __restrict__ mask, int mask_ld, T* __restrict__ out, int out_ld,
+                                int C, long long total4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  int c4 = C / 4;
+  int c = (int)(i % c4) * 4;
+  long long p = i / c4;
+  Vec<T, 4> v, m;
+  v.load(g + (size_t)p * g_ld + c);
+  m.load(mask + (size_t)p * mask_ld + c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v.v[k] = m.v[k] > 0.f ? v.v[k] : 0.f;
+  v.store(out + (size_t)p * out_ld + c);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(double* stats, double count, const float* gamma, const float* beta, float* rm, float* rv, float momentum,
+                                   float eps, const float* drop, int N, int C, float* mean, float* invstd, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = stats[c], sq = stats[C + c];
+  stats[c] = 0.0;
+  stats[C + c] = 0.0;
+  double mu = s / count;
+  double var = sq / count - mu * mu;
+  if (var < 0) var = 0;
+  float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  invstd[c] = is;
+  if (rm) {
+    double unb = count > 1 ? var * count / (count - 1) : var;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * (float)mu;
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unb;
+  }
+  float sc = gamma[c] * is;
+  float sh = beta[c] - (float)mu * sc;
+  if (drop) {
+    for (int n = 0; n < N; ++n) {
+      float d = drop[n * C + c];
+      scale[n * C + c] = sc * d;
+      shift[n * C + c] = sh * d;
+    }
+  } else {
+    scale[c] = sc;
+    shift[c] = sh;
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
+                                      float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+// gb = g * (mask > 0) * drop[n,c]; block-partial sums of gb and gb*xhat
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, int g_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ mask,
+                                     int mask_ld, const float* __restrict__ drop, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, long long HW, int C, long long n_px, int px_per_block,
+                                     double* __restrict__ sums) {
+  extern __shared__ float s[];  // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s[i] = 0.f;
+  __syncthreads();
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  long long p0 = (long long)blockIdx.x * px_per_block, p1 = p0 + px_per_block;
+  if (p1 > n_px) p1 = n_px;
+  if (lane < lanes) {
+    float a = 0.f, b = 0.f;
+    const float mu = mean[c], is = invstd[c];
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      float gv = to_f(g[(size_t)p * g_ld + c]);
+      if (mask && !(to_f(mask[(size_t)p * mask_ld + c]) > 0.f)) gv = 0.f;
+      if (drop) gv *= drop[(p / HW) * C + c];
+      float xh = (to_f(y[(size_t)p * y_ld + c]) - mu) * is;
+      a += gv;
+      b += gv * xh;
+    }
+    atomicAdd(&s[c], a);
+    atomicAdd(&s[C + c], b);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)s[i]);
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ mask,
+                                    int mask_ld, const float* __restrict__ drop, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
+                                    long long HW, int C, long long n_px, T* __restrict__ dy, int dy_ld, float* dgamma, float* dbeta) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    if (dbeta) dbeta[i] = (float)sums[i];
+    if (dgamma) dgamma[i] = (float)sums[C + i];
+  }
+  if (i >= n_px * C) return;
+  int c = (int)(i % C);
+  long long p = i / C;
+  float gv = to_f(g[(size_t)p * g_ld + c]);
+  if (mask && !(to_f(mask[(size_t)p * mask_ld + c]) > 0.f)) gv = 0.f;
+  if (drop) gv *= drop[(p / HW) * C + c];
+  const float is = invstd[c];
+  float xh = (to_f(y[(size_t)p * y_ld + c]) - mean[c]) * is;
+  const float inv_m = 1.f / (float)n_px;
+  float m1 = (float)sums[c] * inv_m, m2 = (float)sums[C + c] * inv_m;
+  dy[(size_t)p * dy_ld + c] = from_f<T>(gamma[c] * is * (gv - m1 - xh * m2));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                            float lr_over_bc1, float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pv = p[i];
+  float gv = g[i] * grad_scale + wd * pv;
+  float mv = beta1 * m[i] + (1.f - beta1) * gv;
+  float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+  m[i] = mv;
+  v[i] = vv;
+  p[i] = pv - lr_over_bc1 * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+#define DISPATCH(dtype, KERNEL, grid, block, smem, stream, ...)                                   \
+  do {                                                                                            \
+    if ((dtype) == ERF_F32) KERNEL<float><<<grid, block, smem, stream>>>(__VA_ARGS__);            \
+    else KERNEL<__nv_bfloat16><<<grid, block, smem, stream>>>(__VA_ARGS__);                       \
+  } while (0)
+#define CHECK_DTYPE(who) ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, who ": bad dtype %d", dtype)
+
+extern "C" int erf_nchw_f32_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_nchw_f32_to_nhwc");
+  ERF_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && out_ld >= C, "erf_nchw_f32_to_nhwc: bad arguments");
+  long long HW = (long long)H * W, total = HW * N;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == ERF_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, HW, total, (float*)out, out_ld);
+  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, HW, total, (__nv_bfloat16*)out, out_ld);
+  ERF_CHECK_LAUNCH("erf_nchw_f32_to_nhwc");
+  return ERF_OK;
+}
+
+extern "C" int erf_nhwc_to_nchw_f32(const void* in, int in_ld, int N, int C, int H, int W, float* out, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_nhwc_to_nchw_f32");
+  ERF_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_ld >= C, "erf_nhwc_to_nchw_f32: bad arguments");
+  long long HW = (long long)H * W, total = HW * N;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == ERF_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, in_ld, C, HW, total, out);
+  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, in_ld, C, HW, total, out);
+  ERF_CHECK_LAUNCH("erf_nhwc_to_nchw_f32");
+  return ERF_OK;
+}
+
+extern "C" int erf_maxpool2x2_fwd(const void* in, int N, int H, int W, int C, int in_ld, void* out, int out_ld, int out_coff, const float* scale,
+                                  const float* shift, int relu, double* stats, int stats_c, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_maxpool2x2_fwd");
+  ERF_CHECK_ARG(in && out && N > 0 && C > 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0, "erf_maxpool2x2_fwd: H (%d) and W (%d) must be even", H, W);
+  ERF_CHECK_ARG(in_ld >= C && out_ld >= out_coff + C, "erf_maxpool2x2_fwd: bad leading dimensions");
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  size_t smem = stats ? 2 * C * sizeof(float) : 0;
+  if (dtype == ERF_F32)
+    maxpool_fwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)in, N, H, W, C, in_ld, (float*)out, out_ld, out_coff, scale, shift, relu, stats, stats_c);
+  else
+    maxpool_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, H, W, C, in_ld, (__nv_bfloat16*)out, out_ld, out_coff, scale, shift, relu, stats, stats_c);
+  ERF_CHECK_LAUNCH("erf_maxpool2x2_fwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_maxpool2x2_bwd(const void* in, int N, int H, int W, int C, int in_ld, const void* dout, int out_ld, int out_coff, void* dx,
+                                  int dx_ld, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_maxpool2x2_bwd");
+  ERF_CHECK_ARG(in && dout && dx && N > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, "erf_maxpool2x2_bwd: bad arguments");
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == ERF_F32)
+    maxpool_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, N, H, W, C, in_ld, (const float*)dout, out_ld, out_coff, (float*)dx, dx_ld);
+  else
+    maxpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, N, H, W, C, in_ld, (const __nv_bfloat16*)dout, out_ld, out_coff, (__nv_bfloat16*)dx, dx_ld);
+  ERF_CHECK_LAUNCH("erf_maxpool2x2_bwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const float* shift, int sc_per_sample, const void* res, int res_ld,
+                              void* out, int out_ld, int N, int HW, int C, int relu, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_affine_act");
+  ERF_CHECK_ARG(x && out && N > 0 && HW > 0 && C > 0 && (C % 4) == 0 && (x_ld % 4) == 0 && (out_ld % 4) == 0 && (!res || (res_ld % 4) == 0),
+                "erf_affine_act: C and leading dimensions must be multiples of 4");
+  ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "erf_affine_act: scale and shift must be given together");
+  long long total4 = (long long)N * HW * (C / 4);
+  unsigned grid = (unsigned)((total4 + 255) / 256);
+  if (dtype == ERF_F32)
+    affine_act_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, x_ld, scale, shift, sc_per_sample, (const float*)res, res_ld, (float*)out, out_ld, HW, C, total4, relu);
+  else
+    affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_ld, scale, shift, sc_per_sample, (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out, out_ld, HW, C, total4, relu);
+  ERF_CHECK_LAUNCH("erf_affine_act");
+  return ERF_OK;
+}
+
+extern "C" int erf_relu_bwd(const void* g, int g_ld, const void* mask, int mask_ld, void* out, int out_ld, long long n_px, int C, int dtype,
+                            erf_stream_t stream) {
+  CHECK_DTYPE("erf_relu_bwd");
+  ERF_CHECK_ARG(g && mask && out && n_px > 0 && C > 0 && (C % 4) == 0 && (g_ld % 4) == 0 && (mask_ld % 4) == 0 && (out_ld % 4) == 0,
+                "erf_relu_bwd: C and leading dimensions must be multiples of 4");
+  long long total4 = n_px * (C / 4);
+  unsigned grid = (unsigned)((total4 + 255) / 256);
+  if (dtype == ERF_F32)
+    relu_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)mask, mask_ld, (float*)out, out_ld, C, total4);
+  else
+    relu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)mask, mask_ld, (__nv_bfloat16*)out, out_ld, C, total4);
+  ERF_CHECK_LAUNCH("erf_relu_bwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               float momentum, float eps, const float* drop, int N, int C, float* mean, float* invstd, float* scale, float* shift,
+                               erf_stream_t stream) {
+  ERF_CHECK_ARG(stats && gamma && beta && mean && invstd && scale && shift && C > 0 && count > 0, "erf_bn_finalize: bad arguments");
+  ERF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "erf_bn_finalize: running_mean/var must be given together");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, running_mean, running_var, momentum, eps, drop, N, C, mean,
+                                                                        invstd, scale, shift);
+  ERF_CHECK_LAUNCH("erf_bn_finalize");
+  return ERF_OK;
+}
+
+extern "C" int erf_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, int C,
+                                  float* scale, float* shift, erf_stream_t stream) {
+  ERF_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && C > 0, "erf_bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, C, scale, shift);
+  ERF_CHECK_LAUNCH("erf_bn_eval_affine");
+  return ERF_OK;
+}
+
+extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* drop,
+                                 const float* mean, const float* invstd, int N, int HW, int C, double* sums, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_bn_bwd_reduce");
+  ERF_CHECK_ARG(g && y && mean && invstd && sums && N > 0 && HW > 0 && C > 0 && C <= 256, "erf_bn_bwd_reduce: bad arguments");
+  long long n_px = (long long)N * HW;
+  long long want = 148 * 8;
+  long long ppb = (n_px + want - 1) / want;
+  if (ppb < 64) ppb = 64;
+  unsigned grid = (unsigned)((n_px + ppb - 1) / ppb);
+  size_t smem = 2 * C * sizeof(float);
+  if (dtype == ERF_F32)
+    bn_bwd_reduce_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, (int)ppb, sums);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, (int)ppb, sums);
+  ERF_CHECK_LAUNCH("erf_bn_bwd_reduce");
+  return ERF_OK;
+}
+
+extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* drop,
+                                const float* gamma, const float* mean, const float* invstd, const double* sums, int N, int HW, int C, void* dy,
+                                int dy_ld, float* dgamma, float* dbeta, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_bn_bwd_apply");
+  ERF_CHECK_ARG(g && y && gamma && mean && invstd && sums && dy && N > 0 && HW > 0 && C > 0, "erf_bn_bwd_apply: bad arguments");
+  long long n_px = (long long)N * HW;
+  unsigned grid = (unsigned)((n_px * C + 255) / 256);
+  if (dtype == ERF_F32)
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (float*)dy, dy_ld, dgamma, dbeta);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta);
+  ERF_CHECK_LAUNCH("erf_bn_bwd_apply");
+  return ERF_OK;
+}
+
+extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, float grad_scale, erf_stream_t stream) {
+  ERF_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "erf_adam_step: bad arguments");
+  double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  unsigned grid = (unsigned)((n + 255) / 256);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale);
+  ERF_CHECK_LAUNCH("erf_adam_step");
+  return ERF_OK;
+}

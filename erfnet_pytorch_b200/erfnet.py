@@ -1,0 +1,503 @@
+"""B200-native ERFNet with the reference's module API (eval/erfnet.py): same class names, constructor
+signatures, attribute names and fp32 state_dict layout (345 entries for 20 classes), NCHW fp32 tensors at the
+boundary -- but every arithmetic op runs in liberfnet_b200.so on NHWC bf16 (or fp32 "check mode") activations.
+
+Differences from the reference that a caller can observe:
+  * CUDA only; there is no CPU / eager fallback (RuntimeError instead).
+  * ``model.precision`` ("bf16" default, "fp32" check mode) selects activation storage; accumulation is fp32.
+  * in ``eval()`` mode no autograd graph is built (the reference builds one it never uses, eval/eval_iou.py:89);
+    in ``train()`` mode outputs carry a grad_fn whose backward runs this library's dgrad/wgrad kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ConvSpec
+
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.1
+_DEFAULT_PRECISION = "bf16"
+
+
+def set_default_precision(p: str):
+    global _DEFAULT_PRECISION
+    assert p in ("bf16", "fp32")
+    _DEFAULT_PRECISION = p
+
+
+def _act_dtype(precision):
+    return torch.bfloat16 if precision == "bf16" else torch.float32
+
+
+class _Ctx:
+    """Per-forward context handed down the module tree (precision, dropout masks, weight cache)."""
+
+    def __init__(self, precision, training, drop_scales=None):
+        self.dtype = _act_dtype(precision)
+        self.training = training
+        self.drop_scales = drop_scales  # optional {id(module) or name: [N,C] fp32} (tests inject fixed masks)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autograd glue: one Function per block; the block object supplies fwd_train()/bwd()
+# ---------------------------------------------------------------------------------------------------------------
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, block, bctx, x, *params):
+        y, saved = block._fwd_train(x.detach(), bctx)
+        # detached aliases: keeping `y` itself would create a node -> y -> grad_fn(node) reference cycle
+        ctx.block, ctx.saved = block, tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, grads = ctx.block._bwd(dy.contiguous(), ctx.saved, ctx.needs_input_grad[2])
+        ctx.saved = None
+        return (None, None, dx) + tuple(grads)
+
+
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ld, dtype):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x, ld, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nhwc_to_nchw(dy.contiguous(), ctx.c), None, None
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.ld, ctx.dtype = x.shape[-1], x.dtype
+        return ops.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nchw_to_nhwc(dy, ctx.ld, ctx.dtype), None
+
+
+class _B200Module(nn.Module):
+    """Common plumbing: NCHW<->NHWC at the public boundary, packed-weight cache for eval mode."""
+    precision: Optional[str] = None
+    _in_ld = None   # NHWC pitch of the input this block expects (None: = channels)
+    _out_c = None   # logical channels of the output
+
+    def _precision(self):
+        return self.precision or _DEFAULT_PRECISION
+
+    def _cache(self, dtype):
+        """Folded + packed eval-mode operands, rebuilt when any parameter/buffer changes (load_state_dict, optimizer)."""
+        sig = (dtype,) + _sig(self)
+        c = self.__dict__.get("_packed")
+        if c is None or c[0] != sig:
+            c = (sig, self._pack_eval(dtype))
+            self.__dict__["_packed"] = c
+        return c[1]
+
+    def _nhwc(self, x, ctx):
+        raise NotImplementedError
+
+    def forward(self, input):
+        ctx = _Ctx(self._precision(), self.training)
+        x = _ToNHWC.apply(input, self._in_ld or input.shape[1], ctx.dtype)
+        y = self._nhwc(x, ctx)
+        return _ToNCHW.apply(y, self._out_c)
+
+
+def _sig(mod):
+    return tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
+
+
+
+def _bn_fold(bn: nn.BatchNorm2d):
+    return ops.bn_eval_affine(bn.weight.detach().float(), bn.bias.detach().float(), bn.running_mean, bn.running_var, bn.eps)
+
+
+def _run(block, x, ctx):
+    """Dispatch a block on an NHWC tensor: autograd path in training, folded kernels otherwise."""
+    if ctx.training:
+        return _BlockFn.apply(block, ctx, x, *block._train_params())
+    with torch.no_grad():
+        return block._fwd_eval(x, ctx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class DownsamplerBlock(_B200Module):
+    """eval/erfnet.py:12-23 -- cat([conv3x3 s2 p1 (ninput -> noutput-ninput), maxpool2x2]) -> BN(eps 1e-3) -> ReLU.
+    One output tensor, two kernels writing its two channel slices."""
+
+    def __init__(self, ninput, noutput, use_batchnorm=True):
+        super().__init__()
+        self.use_batchnorm = use_batchnorm
+        self.conv = nn.Conv2d(ninput, noutput - ninput, (3, 3), stride=2, padding=1, bias=True)
+        self.pool = nn.MaxPool2d(2, stride=2)
+        self.bn = nn.BatchNorm2d(noutput, eps=BN_EPS)
+        self.ninput, self.noutput = ninput, noutput
+        self.spec = ConvSpec(ninput, noutput - ninput, 3, 3, 2, 1, 1)
+        self._in_ld, self._out_c = ops.round_up(ninput, 4), noutput
+
+    def _nhwc(self, x, ctx):
+        return _run(self, x, ctx)
+
+    def _check(self, x):
+        if x.shape[1] % 2 or x.shape[2] % 2:
+            # the reference fails in torch.cat here (conv gives ceil(H/2), pool floor(H/2)): SURVEY D8
+            raise RuntimeError(f"DownsamplerBlock: H and W must be even, got {x.shape[1]}x{x.shape[2]}")
+
+    def _pack_eval(self, dtype):
+        w = self.conv.weight.detach().float()
+        b = self.conv.bias.detach().float()
+        cc = self.noutput - self.ninput
+        if self.use_batchnorm:
+            scale, shift = _bn_fold(self.bn)
+            w = w * scale[:cc].view(-1, 1, 1, 1)
+            b = b * scale[:cc] + shift[:cc]
+            ps, psh = scale[cc:].contiguous(), shift[cc:].contiguous()
+        else:
+            ps = psh = None
+        return dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous(), ps=ps, psh=psh)
+
+    def _fwd_eval(self, x, ctx):
+        self._check(x)
+        pk = self._cache(ctx.dtype)
+        n, h, w, _ = x.shape
+        y = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
+        ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True, out=y)
+        ops.maxpool_fwd(x, self.ninput, y, self.noutput - self.ninput, pk["ps"], pk["psh"], relu=True)
+        return y
+
+    def _train_params(self):
+        return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
+
+    def _fwd_train(self, x, ctx):
+        self._check(x)
+        if not self.use_batchnorm:
+            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
+        n, h, w, _ = x.shape
+        cc = self.noutput - self.ninput
+        y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
+        stats = torch.zeros(2 * self.noutput, device=x.device, dtype=torch.float64)
+        ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                     out=y_raw, stats=stats)
+        ops.maxpool_fwd(x, self.ninput, y_raw, cc, stats=stats)
+        mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
+                                                     self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
+        self.bn.num_batches_tracked += 1
+        y = ops.affine_act(y_raw, scale, shift, relu=True)
+        return y, (x, y_raw, y, mean, invstd)
+
+    def _bwd(self, dy, saved, need_dx):
+        x, y_raw, y, mean, invstd = saved
+        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, self.bn.weight.detach(), mean, invstd, mask=y)
+        dwp, db = ops.conv_wgrad(x, dyr, self.spec)
+        dx = None
+        if need_dx:
+            n, h, w, _ = x.shape
+            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(self.conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=(h, w))
+            ops.maxpool_bwd(x, self.ninput, dyr, self.noutput - self.ninput, dx)
+        return dx, (ops.unpack_wgrad(dwp, self.spec), db, dgamma, dbeta)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class non_bottleneck_1d(_B200Module):
+    """eval/erfnet.py:26-61 -- 3x1 -> ReLU -> 1x3 -> BN -> ReLU -> dilated 3x1 -> ReLU -> dilated 1x3 -> BN ->
+    Dropout2d -> + input -> ReLU."""
+
+    def __init__(self, chann, dropprob, dilated, use_dropout=True, use_batchnorm=True):
+        super().__init__()
+        self.use_dropout, self.use_batchnorm = use_dropout, use_batchnorm
+        self.conv3x1_1 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1, 0), bias=True)
+        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1), bias=True)
+        self.bn1 = nn.BatchNorm2d(chann, eps=BN_EPS)
+        self.conv3x1_2 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1 * dilated, 0), bias=True, dilation=(dilated, 1))
+        self.conv1x3_2 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1 * dilated), bias=True, dilation=(1, dilated))
+        self.bn2 = nn.BatchNorm2d(chann, eps=BN_EPS)
+        self.dropout = nn.Dropout2d(dropprob)
+        self.chann, self.dilated = chann, dilated
+        d = dilated
+        self.specs = (ConvSpec(chann, chann, 3, 1, 1, 1, 0), ConvSpec(chann, chann, 1, 3, 1, 0, 1),
+                      ConvSpec(chann, chann, 3, 1, 1, d, 0, d, 1), ConvSpec(chann, chann, 1, 3, 1, 0, d, 1, d))
+        self._out_c = chann
+
+    def _convs(self):
+        return (self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)
+
+    def _nhwc(self, x, ctx):
+        return _run(self, x, ctx)
+
+    def _pack_eval(self, dtype):
+        ws = [c.weight.detach().float() for c in self._convs()]
+        bs = [c.bias.detach().float() for c in self._convs()]
+        if self.use_batchnorm:
+            for i, bn in ((1, self.bn1), (3, self.bn2)):
+                scale, shift = _bn_fold(bn)
+                ws[i] = ws[i] * scale.view(-1, 1, 1, 1)
+                bs[i] = bs[i] * scale + shift
+        return dict(w=[ops.pack_weight_fwd(w, s, dtype) for w, s in zip(ws, self.specs)], b=[b.contiguous() for b in bs])
+
+    def _fwd_eval(self, x, ctx):
+        pk = self._cache(ctx.dtype)
+        w, b, s = pk["w"], pk["b"], self.specs
+        t = ops.conv_fwd(x, w[0], s[0], b[0], relu=True)
+        t = ops.conv_fwd(t, w[1], s[1], b[1], relu=True)
+        t = ops.conv_fwd(t, w[2], s[2], b[2], relu=True)
+        return ops.conv_fwd(t, w[3], s[3], b[3], relu=True, add=x)
+
+    def _train_params(self):
+        return (self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias, self.bn1.weight, self.bn1.bias,
+                self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias, self.bn2.weight, self.bn2.bias)
+
+    def _drop_scale(self, x, ctx):
+        """Dropout2d multiplier [N,C] (0 or 1/(1-p)): same RNG consumption as nn.Dropout2d on [N,C,H,W] (noise [N,C,1,1])."""
+        p = self.dropout.p
+        if not (self.use_dropout and p != 0):  # eval/erfnet.py:58
+            return None
+        if ctx.drop_scales is not None and self in ctx.drop_scales:
+            return ctx.drop_scales[self].to(x.device, torch.float32).reshape(x.shape[0], self.chann).contiguous()
+        ones = torch.ones(x.shape[0], self.chann, 1, 1, device=x.device)
+        return F.dropout2d(ones, p, True).reshape(x.shape[0], self.chann).contiguous()
+
+    def _fwd_train(self, x, ctx):
+        if not self.use_batchnorm:
+            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
+        n, h, w, c = x.shape
+        s, dtp = self.specs, x.dtype
+        cv = self._convs()
+        wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
+        bs = [m.bias.detach().float() for m in cv]
+        count = n * h * w
+        st = torch.zeros(2, 2 * c, device=x.device, dtype=torch.float64)
+        t1 = ops.conv_fwd(x, wp[0], s[0], bs[0], relu=True)
+        y2 = ops.conv_fwd(t1, wp[1], s[1], bs[1], stats=st[0])
+        mean1, invstd1, sc1, sh1 = ops.bn_finalize(st[0], count, self.bn1.weight.detach(), self.bn1.bias.detach(), self.bn1.running_mean,
+                                                   self.bn1.running_var, BN_MOMENTUM, BN_EPS)
+        self.bn1.num_batches_tracked += 1
+        a2 = ops.affine_act(y2, sc1, sh1, relu=True)
+        t3 = ops.conv_fwd(a2, wp[2], s[2], bs[2], relu=True)
+        y4 = ops.conv_fwd(t3, wp[3], s[3], bs[3], stats=st[1])
+        drop = self._drop_scale(x, ctx)
+        mean2, invstd2, sc2, sh2 = ops.bn_finalize(st[1], count, self.bn2.weight.detach(), self.bn2.bias.detach(), self.bn2.running_mean,
+                                                   self.bn2.running_var, BN_MOMENTUM, BN_EPS, drop=drop)
+        self.bn2.num_batches_tracked += 1
+        out = ops.affine_act(y4, sc2, sh2, res=x, relu=True)
+        return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop)
+
+    def _bwd(self, dout, saved, need_dx):
+        x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop = saved
+        s, dtp = self.specs, x.dtype
+        cv = self._convs()
+        wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
+        ds = [ops.dgrad_spec(sp) for sp in s]
+        hw = x.shape[1:3]
+        dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, self.bn2.weight.detach(), mean2, invstd2, mask=out, drop=drop)
+        dw4, db4 = ops.conv_wgrad(t3, dy4, s[3])
+        dt3 = ops.conv_fwd(dy4, wd[3], ds[3], mask=t3, out_hw=hw)
+        dw3, db3 = ops.conv_wgrad(a2, dt3, s[2])
+        da2 = ops.conv_fwd(dt3, wd[2], ds[2], out_hw=hw)
+        dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, self.bn1.weight.detach(), mean1, invstd1, mask=a2)
+        dw2, db2 = ops.conv_wgrad(t1, dy2, s[1])
+        dt1 = ops.conv_fwd(dy2, wd[1], ds[1], mask=t1, out_hw=hw)
+        dw1, db1 = ops.conv_wgrad(x, dt1, s[0])
+        dx = None
+        if need_dx:
+            gres = ops.relu_bwd(dout, out)
+            dx = ops.conv_fwd(dt1, wd[0], ds[0], add=gres, out_hw=hw)
+        u = ops.unpack_wgrad
+        return dx, (u(dw1, s[0]), db1, u(dw2, s[1]), db2, dg1, dbe1, u(dw3, s[2]), db3, u(dw4, s[3]), db4, dg2, dbe2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class UpsamplerBlock(_B200Module):
+    """eval/erfnet.py:99-108 -- ConvTranspose2d(3, stride 2, padding 1, output_padding 1) -> BN -> ReLU."""
+
+    def __init__(self, ninput, noutput, use_batchnorm=True):
+        super().__init__()
+        self.use_batchnorm = use_batchnorm
+        self.conv = nn.ConvTranspose2d(ninput, noutput, 3, stride=2, padding=1, output_padding=1, bias=True)
+        self.bn = nn.BatchNorm2d(noutput, eps=BN_EPS)
+        self.spec = ConvSpec(ninput, noutput, 3, 3, 2, 1, 1, transposed=True, out_pad=1)
+        self._out_c = noutput
+
+    def _nhwc(self, x, ctx):
+        return _run(self, x, ctx)
+
+    def _pack_eval(self, dtype):
+        w, b = self.conv.weight.detach().float(), self.conv.bias.detach().float()
+        if self.use_batchnorm:
+            scale, shift = _bn_fold(self.bn)
+            w = w * scale.view(1, -1, 1, 1)
+            b = b * scale + shift
+        return dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous())
+
+    def _fwd_eval(self, x, ctx):
+        pk = self._cache(ctx.dtype)
+        return ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True)
+
+    def _train_params(self):
+        return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
+
+    def _fwd_train(self, x, ctx):
+        if not self.use_batchnorm:
+            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
+        c = self.spec.cout
+        stats = torch.zeros(2 * c, device=x.device, dtype=torch.float64)
+        y_raw = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                             stats=stats)
+        count = y_raw.shape[0] * y_raw.shape[1] * y_raw.shape[2]
+        mean, invstd, scale, shift = ops.bn_finalize(stats, count, self.bn.weight.detach(), self.bn.bias.detach(), self.bn.running_mean,
+                                                     self.bn.running_var, BN_MOMENTUM, BN_EPS)
+        self.bn.num_batches_tracked += 1
+        y = ops.affine_act(y_raw, scale, shift, relu=True)
+        return y, (x, y_raw, y, mean, invstd)
+
+    def _bwd(self, dy, saved, need_dx):
+        x, y_raw, y, mean, invstd = saved
+        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, self.bn.weight.detach(), mean, invstd, mask=y)
+        dwp, db = ops.conv_wgrad(x, dyr, self.spec)
+        dx = None
+        if need_dx:
+            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(self.conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec),
+                              out_hw=x.shape[1:3])
+        return dx, (ops.unpack_wgrad(dwp, self.spec), db, dgamma, dbeta)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _PlainConv:
+    """A bare conv / transposed conv with bias (the two output_conv heads, eval/erfnet.py:85,124).  Built per call
+    around the owner's nn.Conv2d / nn.ConvTranspose2d so that module replicas (DataParallel) stay independent."""
+
+    def __init__(self, conv: nn.Module, spec: ConvSpec):
+        self.spec = spec
+        self._conv = conv
+        self.out_ld = ops.round_up(spec.cout, 8)
+
+    def _out(self, x):
+        n, h, w, _ = x.shape
+        ho, wo = self.spec.out_hw(h, w)
+        if self.out_ld != self.spec.cout:
+            return torch.zeros(n, ho, wo, self.out_ld, device=x.device, dtype=x.dtype)
+        return torch.empty(n, ho, wo, self.out_ld, device=x.device, dtype=x.dtype)
+
+    def _fwd_eval(self, x, ctx):
+        sig = (ctx.dtype,) + _sig(self._conv)
+        c = self._conv.__dict__.get("_packed")
+        if c is None or c[0] != sig:
+            c = (sig, (ops.pack_weight_fwd(self._conv.weight.detach().float(), self.spec, ctx.dtype), self._conv.bias.detach().float().contiguous()))
+            self._conv.__dict__["_packed"] = c
+        w, b = c[1]
+        return ops.conv_fwd(x, w, self.spec, b, out=self._out(x))
+
+    def _train_params(self):
+        return (self._conv.weight, self._conv.bias)
+
+    def _fwd_train(self, x, ctx):
+        y = ops.conv_fwd(x, ops.pack_weight_fwd(self._conv.weight.detach(), self.spec, x.dtype), self.spec, self._conv.bias.detach().float(),
+                         out=self._out(x))
+        return y, (x,)
+
+    def _bwd(self, dy, saved, need_dx):
+        (x,) = saved
+        dwp, db = ops.conv_wgrad(x, dy, self.spec)
+        dx = None
+        if need_dx:
+            dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(self._conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec),
+                              out_hw=x.shape[1:3])
+        return dx, (ops.unpack_wgrad(dwp, self.spec), db)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Encoder(_B200Module):
+    """eval/erfnet.py:64-96."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.initial_block = DownsamplerBlock(3, 16)
+        self.layers = nn.ModuleList()
+        self.layers.append(DownsamplerBlock(16, 64))
+        for x in range(0, 5):
+            self.layers.append(non_bottleneck_1d(64, 0.1, 1))
+        self.layers.append(DownsamplerBlock(64, 128))
+        for x in range(0, 2):
+            self.layers.append(non_bottleneck_1d(128, 0.1, 2))
+            self.layers.append(non_bottleneck_1d(128, 0.1, 4))
+            self.layers.append(non_bottleneck_1d(128, 0.1, 8))
+            self.layers.append(non_bottleneck_1d(128, 0.1, 16))
+        # only for encoder mode:
+        self.output_conv = nn.Conv2d(128, num_classes, 1, stride=1, padding=0, bias=True)
+        self.num_classes = num_classes
+        self._in_ld = 4
+
+    def _nhwc(self, x, ctx, predict=False):
+        if x.shape[1] % 8 or x.shape[2] % 8:
+            raise RuntimeError(f"ERFNet: H and W must be multiples of 8, got {x.shape[1]}x{x.shape[2]} (SURVEY D8)")
+        y = _run(self.initial_block, x, ctx)
+        for layer in self.layers:
+            y = _run(layer, y, ctx)
+        if predict:
+            y = _run(_PlainConv(self.output_conv, ConvSpec(128, self.num_classes, 1, 1)), y, ctx)
+        return y
+
+    def forward(self, input, predict=False):
+        ctx = _Ctx(self._precision(), self.training)
+        x = _ToNHWC.apply(input, 4, ctx.dtype)
+        y = self._nhwc(x, ctx, predict)
+        return _ToNCHW.apply(y, self.num_classes if predict else 128)
+
+
+class Decoder(_B200Module):
+    """eval/erfnet.py:110-134."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.layers.append(UpsamplerBlock(128, 64))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(UpsamplerBlock(64, 16))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.output_conv = nn.ConvTranspose2d(16, num_classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+        self.num_classes = num_classes
+        self._out_c = num_classes
+
+    def _nhwc(self, x, ctx):
+        y = x
+        for layer in self.layers:
+            y = _run(layer, y, ctx)
+        return _run(_PlainConv(self.output_conv, ConvSpec(16, self.num_classes, 2, 2, 2, transposed=True)), y, ctx)
+
+
+class ERFNet(_B200Module):
+    """eval/erfnet.py:137-152.  ``ERFNet(num_classes, encoder=None).forward(input, only_encode=False)``."""
+
+    def __init__(self, num_classes, encoder=None):
+        super().__init__()
+        if encoder is None:
+            self.encoder = Encoder(num_classes)
+        else:
+            self.encoder = encoder
+        self.decoder = Decoder(num_classes)
+        self.num_classes = num_classes
+
+    def forward_nhwc(self, input, only_encode=False, drop_scales=None):
+        """NCHW fp32 in, internal NHWC logits out ([N,H,W,round8(C)], activation dtype) -- what the fused loss /
+        argmax / histogram kernels consume without the NCHW fp32 round trip."""
+        ctx = _Ctx(self._precision(), self.training, drop_scales)
+        x = _ToNHWC.apply(input, 4, ctx.dtype)
+        if only_encode:
+            return self.encoder._nhwc(x, ctx, predict=True)
+        return self.decoder._nhwc(self.encoder._nhwc(x, ctx), ctx)
+
+    def forward(self, input, only_encode=False):
+        y = self.forward_nhwc(input, only_encode)
+        return _ToNCHW.apply(y, self.num_classes)
+
+
+Net = ERFNet  # train/main.py instantiates ``model_file.Net``; the Cityscapes graph is the ERFNet above

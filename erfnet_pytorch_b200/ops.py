@@ -1,0 +1,297 @@
+"""Thin torch-tensor wrappers over the C ABI.  torch is used for device memory and streams only; every
+arithmetic op below is a kernel in liberfnet_b200.so.  Internal activations are NHWC tensors [N,H,W,C]
+(contiguous) in fp32 (check mode) or bf16 (fast path)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ERF_BF16, ERF_F32, ConvEpilogue, ConvGeom, check
+
+EMULATED = False  # set by tests/emu.py only (CPU emulation of the kernel contracts for host-logic tests)
+LAUNCHES = 0  # number of kernel-launching library calls made by this process (bench.py reports it)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return ERF_F32
+    if t.dtype == torch.bfloat16:
+        return ERF_BF16
+    raise RuntimeError(f"erfnet_pytorch_b200: unsupported activation dtype {t.dtype}")
+
+
+def _stream(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("erfnet_pytorch_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+# ----------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvSpec:
+    """Geometry of one convolution of the net in its FORWARD orientation."""
+    cin: int
+    cout: int
+    kh: int
+    kw: int
+    stride: int = 1
+    pad_h: int = 0
+    pad_w: int = 0
+    dil_h: int = 1
+    dil_w: int = 1
+    transposed: bool = False
+    out_pad: int = 0
+
+    def out_hw(self, h, w):
+        if self.transposed:
+            return ((h - 1) * self.stride - 2 * self.pad_h + self.dil_h * (self.kh - 1) + self.out_pad + 1,
+                    (w - 1) * self.stride - 2 * self.pad_w + self.dil_w * (self.kw - 1) + self.out_pad + 1)
+        return ((h + 2 * self.pad_h - self.dil_h * (self.kh - 1) - 1) // self.stride + 1,
+                (w + 2 * self.pad_w - self.dil_w * (self.kw - 1) - 1) // self.stride + 1)
+
+    @property
+    def cin_p(self):  # padded input channels the kernels see
+        return round_up(self.cin, 4)
+
+    @property
+    def w_ld(self):
+        return round_up(self.cout, 8)
+
+
+def pack_weight_fwd(w: torch.Tensor, spec: ConvSpec, dtype) -> torch.Tensor:
+    """torch layout -> [(ky*KW+kx)*cin_p + ci][w_ld] for the forward gather (Conv2d [Co,Ci,kh,kw]; ConvT [Ci,Co,kh,kw])."""
+    t = w.permute(2, 3, 0, 1) if spec.transposed else w.permute(2, 3, 1, 0)  # [kh,kw,ci,co]
+    out = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.w_ld, device=w.device, dtype=dtype)
+    out[:, :, :spec.cin, :spec.cout] = t
+    return out.reshape(-1, spec.w_ld)
+
+
+def dgrad_spec(spec: ConvSpec) -> ConvSpec:
+    """The data gradient of a conv is the transposed gather with the same (stride, pad, dilation) and vice versa."""
+    return ConvSpec(spec.cout, spec.cin_p, spec.kh, spec.kw, spec.stride, spec.pad_h, spec.pad_w, spec.dil_h, spec.dil_w,
+                    not spec.transposed, 0)
+
+
+def pack_weight_dgrad(w: torch.Tensor, spec: ConvSpec, dtype) -> torch.Tensor:
+    """[(ky*KW+kx)*round4(cout) + co][round8(cin_p)] operand of the dgrad gather."""
+    t = w.permute(2, 3, 1, 0) if spec.transposed else w.permute(2, 3, 0, 1)  # [kh,kw,co,ci]
+    d = dgrad_spec(spec)
+    out = torch.zeros(spec.kh, spec.kw, d.cin_p, d.w_ld, device=w.device, dtype=dtype)
+    out[:, :, :spec.cout, :spec.cin] = t
+    return out.reshape(-1, d.w_ld)
+
+
+def unpack_wgrad(dw: torch.Tensor, spec: ConvSpec) -> torch.Tensor:
+    t = dw.view(spec.kh, spec.kw, spec.cin_p, spec.w_ld)[:, :, :spec.cin, :spec.cout]
+    return (t.permute(2, 3, 0, 1) if spec.transposed else t.permute(3, 2, 0, 1)).contiguous()
+
+
+def _geom(spec: ConvSpec, x: torch.Tensor, out: torch.Tensor, out_coff: int, cin_used: Optional[int] = None) -> ConvGeom:
+    n, h, w, ld = x.shape
+    _, ho, wo, old = out.shape
+    return ConvGeom(n, h, w, cin_used if cin_used is not None else spec.cin_p, ld, ho, wo, spec.cout, old, out_coff,
+                    spec.kh, spec.kw, spec.stride, spec.pad_h, spec.pad_w, spec.dil_h, spec.dil_w, int(spec.transposed), spec.w_ld)
+
+
+def conv_fwd(x: torch.Tensor, wp: torch.Tensor, spec: ConvSpec, bias: Optional[torch.Tensor] = None, relu=False,
+             out: Optional[torch.Tensor] = None, out_coff=0, mask: Optional[torch.Tensor] = None,
+             add: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None):
+    """Generic gather conv (include/erfnet_b200.h erf_conv_fwd).  x: [N,H,W,ld>=cin_p]; returns/fills out [N,Ho,Wo,ldo]."""
+    n, h, w, _ = x.shape
+    if out is None:
+        ho, wo = out_hw if out_hw is not None else spec.out_hw(h, w)
+        out = torch.empty(n, ho, wo, spec.cout, device=x.device, dtype=x.dtype)
+    g = _geom(spec, x, out, out_coff)
+    e = ConvEpilogue(_p(bias), int(relu), _p(mask), 0 if mask is None else mask.shape[-1], _p(add), 0 if add is None else add.shape[-1],
+                     _p(stats), 0 if stats is None else stats.numel() // 2)
+    check(_lib.lib().erf_conv_fwd(_p(x), _p(wp), _p(out), C.byref(g), C.byref(e), dt(x), _stream(x)))
+    _count()
+    return out
+
+
+def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0, want_bias=True):
+    """Returns (dw_packed fp32 [(taps*cin_p), w_ld], db fp32 [cout] or None)."""
+    dw = torch.zeros(spec.kh * spec.kw * spec.cin_p, spec.w_ld, device=x.device, dtype=torch.float32)
+    db = torch.zeros(spec.cout, device=x.device, dtype=torch.float32) if want_bias else None
+    g = _geom(spec, x, dout, dout_coff)
+    check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
+    _count(2 if want_bias else 1)
+    return dw, db
+
+
+def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
+    n, h, w, ld = x.shape
+    check(_lib.lib().erf_maxpool2x2_fwd(_p(x), n, h, w, c, ld, _p(out), out.shape[-1], out_coff, _p(scale), _p(shift), int(relu),
+                                        _p(stats), 0 if stats is None else stats.numel() // 2, dt(x), _stream(x)))
+    _count()
+
+
+def maxpool_bwd(x, c, dout, out_coff, dx):
+    n, h, w, ld = x.shape
+    check(_lib.lib().erf_maxpool2x2_bwd(_p(x), n, h, w, c, ld, _p(dout), dout.shape[-1], out_coff, _p(dx), dx.shape[-1], dt(x), _stream(x)))
+    _count()
+
+
+def nchw_to_nhwc(x: torch.Tensor, ld: int, dtype) -> torch.Tensor:
+    n, c, h, w = x.shape
+    x = x.contiguous().float()
+    out = torch.empty(n, h, w, ld, device=x.device, dtype=dtype)
+    check(_lib.lib().erf_nchw_f32_to_nhwc(_p(x), n, c, h, w, _p(out), ld, dt(out), _stream(x)))
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
+    n, h, w, ld = x.shape
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    check(_lib.lib().erf_nhwc_to_nchw_f32(_p(x), ld, n, c, h, w, _p(out), dt(x), _stream(x)))
+    _count()
+    return out
+
+
+def affine_act(x, scale=None, shift=None, res=None, relu=True, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    per_sample = int(scale is not None and scale.dim() == 2)
+    check(_lib.lib().erf_affine_act(_p(x), c, _p(scale), _p(shift), per_sample, _p(res), 0 if res is None else res.shape[-1], _p(out),
+                                    out.shape[-1], n, h * w, c, int(relu), dt(x), _stream(x)))
+    _count()
+    return out
+
+
+def relu_bwd(g, mask):
+    n, h, w, c = g.shape
+    out = torch.empty_like(g)
+    check(_lib.lib().erf_relu_bwd(_p(g), c, _p(mask), mask.shape[-1], _p(out), c, n * h * w, c, dt(g), _stream(g)))
+    _count()
+    return out
+
+
+def bn_finalize(stats, count, gamma, beta, rm, rv, momentum, eps, drop=None):
+    c = gamma.numel()
+    n = 1 if drop is None else drop.shape[0]
+    dev = gamma.device
+    mean = torch.empty(c, device=dev, dtype=torch.float32)
+    invstd = torch.empty(c, device=dev, dtype=torch.float32)
+    shape = (c,) if drop is None else (n, c)
+    scale = torch.empty(shape, device=dev, dtype=torch.float32)
+    shift = torch.empty(shape, device=dev, dtype=torch.float32)
+    check(_lib.lib().erf_bn_finalize(_p(stats), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), float(momentum), float(eps), _p(drop), n, c,
+                                     _p(mean), _p(invstd), _p(scale), _p(shift), _stream(gamma)))
+    _count()
+    return mean, invstd, scale, shift
+
+
+def bn_eval_affine(gamma, beta, rm, rv, eps):
+    c = gamma.numel()
+    scale = torch.empty(c, device=gamma.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    check(_lib.lib().erf_bn_eval_affine(_p(gamma), _p(beta), _p(rm), _p(rv), float(eps), c, _p(scale), _p(shift), _stream(gamma)))
+    _count()
+    return scale, shift
+
+
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
+    """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c]."""
+    n, h, w, c = y.shape
+    sums = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
+    L = _lib.lib()
+    check(L.erf_bn_bwd_reduce(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(mean), _p(invstd),
+                              n, h * w, c, _p(sums), dt(y), _stream(y)))
+    dy = torch.empty_like(y)
+    dgamma = torch.empty(c, device=y.device, dtype=torch.float32)
+    dbeta = torch.empty(c, device=y.device, dtype=torch.float32)
+    check(L.erf_bn_bwd_apply(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(gamma), _p(mean),
+                             _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), dt(y), _stream(y)))
+    _count(2)
+    return dy, dgamma, dbeta
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, c: int,
+                  nchw: bool, want_grad: bool):
+    """Returns (loss_sum fp32[1], wsum fp32[1], dlogits or None); loss = loss_sum / wsum."""
+    target = target.contiguous()
+    if target.dtype != torch.int64:
+        raise RuntimeError("CrossEntropyLoss2d: target must be int64")
+    n_px = target.numel()
+    dev = logits.device
+    acc = torch.zeros(2, device=dev, dtype=torch.float32)
+    wsum, lsum = acc[0:1], acc[1:2]
+    L = _lib.lib()
+    check(L.erf_ce_weight_sum(_p(target), n_px, _p(weight), c, ignore_index, _p(wsum), _stream(logits)))
+    dlog = torch.empty_like(logits) if want_grad else None
+    if nchw:
+        hw = logits.shape[2] * logits.shape[3]
+        ld = 0
+    else:
+        hw, ld = 0, logits.shape[-1]
+        if want_grad and ld > c:
+            dlog.zero_()
+    check(L.erf_ce_fwd_bwd(_p(logits), ld, hw, _p(target), n_px, _p(weight), c, ignore_index, _p(wsum), _p(lsum), _p(dlog), dt(logits),
+                           _stream(logits)))
+    _count(2)
+    return lsum, wsum, dlog
+
+
+def confusion_hist(pred: torch.Tensor, gt: torch.Tensor, nc: int, cm: torch.Tensor):
+    if pred.dtype != gt.dtype or pred.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError("iouEval: predictions and labels must both be uint8 or both int64")
+    if pred.numel() != gt.numel():
+        raise RuntimeError(f"iouEval: size mismatch {tuple(pred.shape)} vs {tuple(gt.shape)}")
+    pred, gt = pred.contiguous(), gt.contiguous()
+    check(_lib.lib().erf_confusion_hist(_p(pred), _p(gt), pred.element_size(), pred.numel(), nc, _p(cm), _stream(pred)))
+    _count()
+
+
+def iou_counts(cm: torch.Tensor, nc: int, ignore: int, kept: int):
+    out = torch.empty(3, kept, device=cm.device, dtype=torch.float64)
+    check(_lib.lib().erf_iou_counts(_p(cm), nc, ignore, kept, _p(out[0]), _p(out[1]), _p(out[2]), _stream(cm)))
+    _count()
+    return out
+
+
+def argmax(logits: torch.Tensor, c: int, nchw: bool, out_dtype=torch.int64) -> torch.Tensor:
+    if nchw:
+        n, _, h, w = logits.shape
+        hw, ld = h * w, 0
+    else:
+        n, h, w, ld = logits.shape
+        hw = 0
+    out = torch.empty(n, h, w, device=logits.device, dtype=out_dtype)
+    check(_lib.lib().erf_argmax(_p(logits), ld, hw, n * h * w, c, _p(out), out.element_size(), dt(logits), _stream(logits)))
+    _count()
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_lib.lib().erf_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, _stream(p)))
+    _count()
+
+
+def umma_probe(a: torch.Tensor, b: torch.Tensor, row_shift: int, layout: int, iters: int = 1):
+    """a [rows,K] bf16, b [N,K] bf16 -> (D [128,N] fp32, cycles)."""
+    rows, k = a.shape
+    n = b.shape[0]
+    d = torch.empty(128, n, device=a.device, dtype=torch.float32)
+    cyc = torch.zeros(1, device=a.device, dtype=torch.int64)
+    check(_lib.lib().erf_umma_probe(_p(a), rows, _p(b), n, k // 16, row_shift, layout, _p(d), iters, _p(cyc), _stream(a)))
+    _count()
+    return d, cyc

@@ -1,0 +1,157 @@
+/*
+ * erfnet_b200.h -- C ABI of liberfnet_b200.so: hand-written sm_100a kernels for the ERFNet hot path.
+ *
+ * The reference (lorenwel/erfnet_pytorch) is pure Python on torch and has NO native interface of its own
+ * (SURVEY.md 2b); every entry point below replaces a run-time torch/cuDNN library call made by the reference
+ * at the cited file:line.  The Python host side (erfnet_pytorch_b200/) mirrors the reference's nn.Module API
+ * and reaches these symbols through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Contract:
+ *  - plain pointers and sizes only; all buffers are caller-owned DEVICE memory (torch tensors); the library
+ *    allocates nothing persistent and never frees;
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t) and never synchronises;
+ *  - re-entrant, no global mutable state except a thread-local last-error string;
+ *  - returns ERF_OK or a negative code (never throws/aborts); erf_last_error_string() describes the failure.
+ *
+ * Activations are NHWC ("pixel-major"): element (n,y,x,c) at ((n*H + y)*W + x)*ld + c with ld >= C the pixel
+ * pitch in elements.  dtype selects fp32 (check mode) or bf16 (fast path) storage; accumulation is fp32.
+ */
+#ifndef ERFNET_B200_H_
+#define ERFNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERF_OK 0
+#define ERF_ERR_INVALID_ARGUMENT (-1)
+#define ERF_ERR_CUDA (-2)
+#define ERF_ERR_UNSUPPORTED (-3)
+
+#define ERF_F32 0
+#define ERF_BF16 1
+
+typedef void* erf_stream_t; /* cudaStream_t */
+
+const char* erf_last_error_string(void);
+int erf_abi_version(void);
+
+/* ---- generic gather convolution (check path for every conv of the net, fwd and dgrad) --------------------
+ * transposed == 0 (nn.Conv2d, eval/erfnet.py:16,30-38,85):
+ *   out[n,oy,ox,co] = sum_{ky,kx,ci} in[n, oy*stride - pad_h + ky*dil_h, ox*stride - pad_w + kx*dil_w, ci] * w[ky,kx,ci,co]
+ * transposed == 1 (nn.ConvTranspose2d, eval/erfnet.py:102,124):
+ *   out[n,oy,ox,co] = sum over taps with (oy + pad_h - ky*dil_h) % stride == 0 (same in x) of
+ *                     in[n,(oy + pad_h - ky*dil_h)/stride,(ox + pad_w - kx*dil_w)/stride,ci] * w[ky,kx,ci,co]
+ * Weights are pre-packed by the host as w[(ky*KW + kx)*Cin + ci][w_ld], w_ld = Cout rounded up to 8, zero padded,
+ * in the activation dtype.  A dgrad is the same call with a differently packed weight tensor. */
+typedef struct {
+  int N, H, W, Cin, in_ld;
+  int Ho, Wo, Cout, out_ld, out_coff;
+  int KH, KW, stride, pad_h, pad_w, dil_h, dil_w, transposed;
+  int w_ld;
+} erf_conv_geom;
+
+/* epilogue, applied in this order: + bias -> statistics -> + add -> relu -> * (mask > 0) */
+typedef struct {
+  const float* bias;   /* [Cout] or NULL */
+  int relu;            /* out = max(out, 0) */
+  const void* mask;    /* NHWC, same dtype: out *= (mask > 0)   (ReLU backward), or NULL */
+  int mask_ld;
+  const void* add;     /* NHWC, same dtype: out += add (residual / gradient accumulation), or NULL */
+  int add_ld;
+  double* stats;       /* [2*stats_c]: stats[out_coff+co] += sum, stats[stats_c+out_coff+co] += sum of squares of
+                          (conv + bias), atomically accumulated (BN batch statistics, eval/erfnet.py:22,50,56), or NULL */
+  int stats_c;         /* channel count of the tensor the statistics are taken over (>= out_coff + Cout) */
+} erf_conv_epilogue;
+
+int erf_conv_fwd(const void* in, const void* w, void* out, const erf_conv_geom* g, const erf_conv_epilogue* e,
+                 int dtype, erf_stream_t stream);
+
+/* Weight / bias gradient of the convolution described by g (autograd of the above).
+ * dw: fp32 [(KH*KW)*Cin][w_ld], db: fp32 [Cout] or NULL; both are ACCUMULATED into (caller zeroes). */
+int erf_conv_wgrad(const void* in, const void* dout, float* dw, float* db, const erf_conv_geom* g, int dtype,
+                   erf_stream_t stream);
+
+/* ---- MaxPool2d(2, stride 2) half of DownsamplerBlock (eval/erfnet.py:17,21) ------------------------------ */
+/* out = relu?(max2x2(in)*scale[c] + shift[c]); scale/shift NULL = identity; stats (of the raw max) as in erf_conv_epilogue */
+int erf_maxpool2x2_fwd(const void* in, int N, int H, int W, int C, int in_ld, void* out, int out_ld, int out_coff,
+                       const float* scale, const float* shift, int relu, double* stats, int stats_c, int dtype,
+                       erf_stream_t stream);
+/* dx[n,y,x,c] += dout[n,y/2,x/2,out_coff+c] at the first maximum of each window (torch tie rule). */
+int erf_maxpool2x2_bwd(const void* in, int N, int H, int W, int C, int in_ld, const void* dout, int out_ld,
+                       int out_coff, void* dx, int dx_ld, int dtype, erf_stream_t stream);
+
+/* ---- layout conversion at the API boundary (reference tensors are NCHW fp32) ---------------------------- */
+int erf_nchw_f32_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld, int dtype,
+                         erf_stream_t stream); /* channels C..out_ld-1 are zero filled */
+int erf_nhwc_to_nchw_f32(const void* in, int in_ld, int N, int C, int H, int W, float* out, int dtype,
+                         erf_stream_t stream);
+
+/* ---- elementwise: out = relu?( x*scale[i] + shift[i] + res ), i = c (sc_per_sample==0) or n*C+c ---------
+ * BatchNorm apply (+Dropout2d scale, + residual) + ReLU of eval/erfnet.py:22-23,50-51,56-61,107-108.
+ * scale/shift may be NULL (identity), res may be NULL. */
+int erf_affine_act(const void* x, int x_ld, const float* scale, const float* shift, int sc_per_sample,
+                   const void* res, int res_ld, void* out, int out_ld, int N, int HW, int C, int relu, int dtype,
+                   erf_stream_t stream);
+
+/* out = g * (mask > 0): backward of the F.relu calls of eval/erfnet.py:23,48,51,54,61,108 when not fused */
+int erf_relu_bwd(const void* g, int g_ld, const void* mask, int mask_ld, void* out, int out_ld, long long n_px, int C,
+                 int dtype, erf_stream_t stream);
+
+/* ---- BatchNorm2d(eps=1e-3) training statistics --------------------------------------- */
+/* stats[2C] (sum, sumsq over `count` values/channel) -> mean, invstd (biased var), running stats update
+ * (momentum, unbiased var), and the fused apply vectors scale/shift: [C], or [N,C] when drop ([N,C] Dropout2d
+ * multipliers) is given.  stats is reset to zero. */
+int erf_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, const float* drop, int N, int C, float* mean,
+                    float* invstd, float* scale, float* shift, erf_stream_t stream);
+/* eval mode: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale */
+int erf_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, int C, float* scale, float* shift, erf_stream_t stream);
+/* backward: gb = g * (mask>0) * drop[n,c];  sums[c] += gb, sums[C+c] += gb*xhat,  xhat = (y-mean)*invstd */
+int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld,
+                      const float* drop, const float* mean, const float* invstd, int N, int HW, int C,
+                      double* sums, int dtype, erf_stream_t stream);
+/* dy = gamma*invstd*(gb - sums[c]/M - xhat*sums[C+c]/M); also writes dgamma = sums[C+c], dbeta = sums[c]. */
+int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld,
+                     const float* drop, const float* gamma, const float* mean, const float* invstd,
+                     const double* sums, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta,
+                     int dtype, erf_stream_t stream);
+
+/* ---- CrossEntropyLoss2d (train/evaluation_functions.py:6-14) ------------------------------------------- */
+/* logits element (p, c): NHWC -> logits[p*ld + c]; NCHW (nchw_hw > 0) -> logits[(p/hw)*C*hw + c*hw + p%hw].
+ * pass 1: wsum += sum_valid w[y];  pass 2: loss_sum += sum_valid w[y]*nll, dlogits = w[y]*(softmax-onehot)/wsum. */
+int erf_ce_weight_sum(const int64_t* target, long long n_px, const float* weight, int C, int ignore_index,
+                      float* wsum, erf_stream_t stream);
+int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int64_t* target, long long n_px,
+                   const float* weight, int C, int ignore_index, const float* wsum, float* loss_sum,
+                   void* dlogits, int dtype, erf_stream_t stream);
+
+/* ---- iouEval (eval/iouEval.py:21-69) and argmax (eval/eval_iou.py:92) ----------------------------------- */
+/* cm[g*nc + p] += #pixels with label g predicted p (u64, bit exact); labels outside [0,nc) are skipped. */
+int erf_confusion_hist(const void* pred, const void* gt, int elem_bytes, long long n, int nc,
+                       unsigned long long* cm, erf_stream_t stream);
+/* tp/fp/fn[c] for c < kept, float64 like the reference accumulators; ignore < 0 means none. */
+int erf_iou_counts(const unsigned long long* cm, int nc, int ignore, int kept, double* tp, double* fp, double* fn,
+                   erf_stream_t stream);
+int erf_argmax(const void* logits, int ld, int nchw_hw, long long n_px, int C, void* out, int out_elem_bytes,
+               int dtype, erf_stream_t stream);
+
+/* ---- Adam as configured by train/main.py:43-46,213 (L2 in the gradient), over one flat fp32 buffer ------- */
+int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, erf_stream_t stream);
+
+/* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
+/* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
+ * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle
+ * (core-matrix interleave), 2 = 128-byte swizzle.  A_rows x K and N x K bf16 row-major in, D fp32 row-major out. */
+int erf_umma_probe(const void* a, int a_rows, const void* b, int n, int ksteps, int row_shift, int layout,
+                   float* d, int iters, long long* cycles, erf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERFNET_B200_H_ */

@@ -1,0 +1,225 @@
+"""CPU emulation of the C-ABI kernels' CONTRACTS (include/erfnet_b200.h) in plain torch -- test infrastructure.
+
+It lets the `-m "not gpu"` suite exercise the host logic of erfnet_pytorch_b200 (conv specs, weight packing for
+fwd/dgrad, wgrad unpacking, BN bookkeeping, autograd wiring, DDP bucketing) against the oracle without a GPU.
+The product never imports this; on a GPU box the same Python drives the real kernels (tests marked gpu)."""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+from erfnet_pytorch_b200 import ops
+
+
+def _unpack(wp, spec):
+    return wp.float().view(spec.kh, spec.kw, spec.cin_p, spec.w_ld)[:, :, :, :spec.cout]  # [kh,kw,ci,co]
+
+
+def conv_fwd(x, wp, spec, bias=None, relu=False, out=None, out_coff=0, mask=None, add=None, stats=None, out_hw=None):
+    n, h, w, ld = x.shape
+    xi = x[..., :spec.cin_p].float().permute(0, 3, 1, 2)
+    wt = _unpack(wp, spec)
+    if out is not None:
+        ho, wo = out.shape[1:3]
+    else:
+        ho, wo = out_hw if out_hw is not None else spec.out_hw(h, w)
+    if not spec.transposed:
+        y = F.conv2d(xi, wt.permute(3, 2, 0, 1), None, spec.stride, (spec.pad_h, spec.pad_w), (spec.dil_h, spec.dil_w))
+    else:
+        base_h = (h - 1) * spec.stride - 2 * spec.pad_h + spec.dil_h * (spec.kh - 1) + 1
+        base_w = (w - 1) * spec.stride - 2 * spec.pad_w + spec.dil_w * (spec.kw - 1) + 1
+        y = F.conv_transpose2d(xi, wt.permute(2, 3, 0, 1), None, spec.stride, (spec.pad_h, spec.pad_w), (ho - base_h, wo - base_w), 1,
+                               (spec.dil_h, spec.dil_w))
+    assert y.shape[2:] == (ho, wo), (y.shape, ho, wo)
+    y = y.permute(0, 2, 3, 1)
+    if bias is not None:
+        y = y + bias
+    if stats is not None:
+        c = stats.numel() // 2
+        stats[out_coff:out_coff + spec.cout] += y.double().sum((0, 1, 2))
+        stats[c + out_coff:c + out_coff + spec.cout] += (y.double() ** 2).sum((0, 1, 2))
+    if add is not None:
+        y = y + add[..., :spec.cout].float()
+    if relu:
+        y = y.relu()
+    if mask is not None:
+        y = y * (mask[..., :spec.cout].float() > 0)
+    if out is None:
+        out = torch.empty(n, ho, wo, spec.cout, dtype=x.dtype)
+    out[..., out_coff:out_coff + spec.cout] = y.to(x.dtype)
+    return out
+
+
+@torch.enable_grad()
+def conv_wgrad(x, dout, spec, dout_coff=0, want_bias=True):
+    n, h, w, _ = x.shape
+    xi = x[..., :spec.cin_p].detach().float().permute(0, 3, 1, 2)
+    wt = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.cout, requires_grad=True)
+    dy = dout[..., dout_coff:dout_coff + spec.cout].detach().float().permute(0, 3, 1, 2)
+    ho, wo = dout.shape[1:3]
+    if not spec.transposed:
+        y = F.conv2d(xi, wt.permute(3, 2, 0, 1), None, spec.stride, (spec.pad_h, spec.pad_w), (spec.dil_h, spec.dil_w))
+    else:
+        base_h = (h - 1) * spec.stride - 2 * spec.pad_h + spec.dil_h * (spec.kh - 1) + 1
+        base_w = (w - 1) * spec.stride - 2 * spec.pad_w + spec.dil_w * (spec.kw - 1) + 1
+        y = F.conv_transpose2d(xi, wt.permute(2, 3, 0, 1), None, spec.stride, (spec.pad_h, spec.pad_w), (ho - base_h, wo - base_w), 1,
+                               (spec.dil_h, spec.dil_w))
+    (g,) = torch.autograd.grad(y, wt, dy)
+    dw = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.w_ld)
+    dw[..., :spec.cout] = g
+    return dw.reshape(-1, spec.w_ld), (dy.sum((0, 2, 3)) if want_bias else None)
+
+
+def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
+    m = F.max_pool2d(x[..., :c].float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    if stats is not None:
+        ct = stats.numel() // 2
+        stats[out_coff:out_coff + c] += m.double().sum((0, 1, 2))
+        stats[ct + out_coff:ct + out_coff + c] += (m.double() ** 2).sum((0, 1, 2))
+    if scale is not None:
+        m = m * scale + shift
+    if relu:
+        m = m.relu()
+    out[..., out_coff:out_coff + c] = m.to(out.dtype)
+
+
+@torch.enable_grad()
+def maxpool_bwd(x, c, dout, out_coff, dx):
+    xi = x[..., :c].detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    m = F.max_pool2d(xi, 2, 2)
+    (g,) = torch.autograd.grad(m, xi, dout[..., out_coff:out_coff + c].float().permute(0, 3, 1, 2))
+    dx[..., :c] += g.permute(0, 2, 3, 1).to(dx.dtype)
+
+
+def nchw_to_nhwc(x, ld, dtype):
+    n, c, h, w = x.shape
+    out = torch.zeros(n, h, w, ld, dtype=dtype)
+    out[..., :c] = x.permute(0, 2, 3, 1).to(dtype)
+    return out
+
+
+def nhwc_to_nchw(x, c):
+    return x[..., :c].float().permute(0, 3, 1, 2).contiguous()
+
+
+def affine_act(x, scale=None, shift=None, res=None, relu=True, out=None):
+    y = x.float()
+    if scale is not None:
+        if scale.dim() == 2:
+            y = y * scale[:, None, None, :] + shift[:, None, None, :]
+        else:
+            y = y * scale + shift
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = y.relu()
+    return y.to(x.dtype)
+
+
+def relu_bwd(g, mask):
+    return (g.float() * (mask.float() > 0)).to(g.dtype)
+
+
+def bn_finalize(stats, count, gamma, beta, rm, rv, momentum, eps, drop=None):
+    c = gamma.numel()
+    mu = stats[:c] / count
+    var = (stats[c:] / count - mu * mu).clamp_min(0)
+    stats.zero_()
+    invstd = (1.0 / torch.sqrt(var + eps)).float()
+    if rm is not None:
+        unb = var * count / (count - 1) if count > 1 else var
+        rm.mul_(1 - momentum).add_(momentum * mu.float())
+        rv.mul_(1 - momentum).add_(momentum * unb.float())
+    sc = gamma * invstd
+    sh = beta - mu.float() * sc
+    if drop is not None:
+        sc, sh = sc[None, :] * drop, sh[None, :] * drop
+    return mu.float(), invstd, sc.contiguous(), sh.contiguous()
+
+
+def bn_eval_affine(gamma, beta, rm, rv, eps):
+    sc = gamma / torch.sqrt(rv + eps)
+    return sc, beta - rm * sc
+
+
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
+    gb = g.float()
+    if mask is not None:
+        gb = gb * (mask.float() > 0)
+    if drop is not None:
+        gb = gb * drop[:, None, None, :]
+    xh = (y.float() - mean) * invstd
+    m = y.shape[0] * y.shape[1] * y.shape[2]
+    s1 = gb.double().sum((0, 1, 2)).float()
+    s2 = (gb * xh).double().sum((0, 1, 2)).float()
+    dy = gamma * invstd * (gb - s1 / m - xh * s2 / m)
+    return dy.to(y.dtype), s2, s1
+
+
+@torch.enable_grad()
+def cross_entropy(logits, target, weight, ignore_index, c, nchw, want_grad):
+    lg = logits.float() if nchw else logits[..., :c].float().permute(0, 3, 1, 2)
+    lg = lg.detach().requires_grad_(True)
+    valid = target != ignore_index
+    t = torch.where(valid, target, torch.zeros_like(target))
+    w = torch.ones(c) if weight is None else weight
+    wpx = w[t] * valid
+    nll = -F.log_softmax(lg, 1).gather(1, t.unsqueeze(1)).squeeze(1)
+    lsum = (wpx * nll).sum()
+    wsum = wpx.sum()
+    dlog = None
+    if want_grad:
+        (g,) = torch.autograd.grad(lsum / wsum, lg)
+        if nchw:
+            dlog = g
+        else:
+            dlog = torch.zeros_like(logits)
+            dlog[..., :c] = g.permute(0, 2, 3, 1).to(logits.dtype)
+    return lsum.detach().reshape(1), wsum.reshape(1), dlog
+
+
+def confusion_hist(pred, gt, nc, cm):
+    p, g = pred.reshape(-1).long(), gt.reshape(-1).long()
+    ok = (p >= 0) & (p < nc) & (g >= 0) & (g < nc)
+    cm += torch.bincount(g[ok] * nc + p[ok], minlength=nc * nc).view(nc, nc)
+
+
+def iou_counts(cm, nc, ignore, kept):
+    tp = cm.diag()[:kept]
+    rows = [g for g in range(nc) if g != ignore]
+    fp = cm[rows].sum(0)[:kept] - tp
+    fn = cm.sum(1)[:kept] - tp
+    return torch.stack([tp, fp, fn]).double()
+
+
+def argmax(logits, c, nchw, out_dtype=torch.int64):
+    return (logits.float().argmax(1) if nchw else logits[..., :c].float().argmax(-1)).to(out_dtype)
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    gv = g * grad_scale + weight_decay * p
+    m.mul_(beta1).add_(gv, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gv, gv, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+
+
+_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize",
+          "bn_eval_affine", "bn_bwd", "cross_entropy", "confusion_hist", "iou_counts", "argmax", "adam_step"]
+
+
+@contextlib.contextmanager
+def emulated_kernels():
+    """Swap erfnet_pytorch_b200.ops kernels for the CPU emulations above (tests only)."""
+    saved = {n: getattr(ops, n) for n in _NAMES}
+    saved["EMULATED"] = ops.EMULATED
+    try:
+        ops.EMULATED = True
+        for n in _NAMES:
+            setattr(ops, n, globals()[n])
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

@@ -1,0 +1,206 @@
+"""CPU: host logic of erfnet_pytorch_b200 (specs, packing, autograd wiring, BN bookkeeping, loss, metric) against the
+oracle, with the kernels replaced by tests/emu.py's torch emulation of their contracts.  The real kernels are
+checked by the gpu-marked tests."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from erfnet_pytorch_b200 import erfnet as E
+from erfnet_pytorch_b200 import ops
+from erfnet_pytorch_b200.evaluation_functions import CrossEntropyLoss2d
+from erfnet_pytorch_b200.iouEval import iouEval
+from oracle import erfnet_oracle as O
+from oracle.make_golden import golden_input, golden_labels
+from tests.emu import emulated_kernels
+
+
+def assert_rel(actual, desired, tol, msg=""):
+    """max|a-d| <= tol * max|d|  (the north_star's "max relative error" metric)."""
+    actual, desired = np.asarray(actual, np.float64), np.asarray(desired, np.float64)
+    err = np.abs(actual - desired).max()
+    ref = np.abs(desired).max() + 1e-30
+    assert err <= tol * ref, f"{msg}: max|diff|={err:.3e} vs tol*max|ref|={tol * ref:.3e}"
+
+
+# Whole-net gradients through 39 train-mode BNs over 64..2048-sample batches are ill-conditioned at this test size: the
+# fp32 oracle differs from its own float64 evaluation by up to 7% of max|grad| (encoder.layers.12.conv1x3_1.weight), so
+# whole-net checks use a loose bound and the per-block tests (well conditioned) carry the tight one.
+WHOLE_NET_GRAD_TOL = 0.15
+
+
+def _model(seed=0):
+    m = E.ERFNet(20)
+    m.precision = "fp32"
+    sd = O.make_state_dict(O.erfnet_param_shapes(20), seed)
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def test_eval_forward_matches_oracle():
+    m, sd = _model()
+    m.eval()
+    x = golden_input((1, 3, 64, 128), 0)
+    with emulated_kernels(), torch.no_grad():
+        y = m(x)
+        ye = m(x, only_encode=True)
+    with torch.no_grad():
+        np.testing.assert_allclose(y.numpy(), O.erfnet_forward(x, sd).numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(ye.numpy(), O.erfnet_forward(x, sd, only_encode=True).numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_eval_cache_invalidation():
+    m, sd = _model()
+    m.eval()
+    x = golden_input((1, 3, 32, 64), 1)
+    with emulated_kernels(), torch.no_grad():
+        y0 = m(x)
+        sd2 = O.make_state_dict(O.erfnet_param_shapes(20), 7)
+        m.load_state_dict(sd2)
+        y1 = m(x)
+    with torch.no_grad():
+        np.testing.assert_allclose(y1.numpy(), O.erfnet_forward(x, sd2).numpy(), rtol=1e-4, atol=1e-4)
+    assert not np.allclose(y0.numpy(), y1.numpy())
+
+
+def test_train_step_matches_oracle(golden_dir):
+    """train-mode forward (batch-stat BN, running-stat update), CE loss, backward: gradients of every parameter."""
+    g = np.load(os.path.join(golden_dir, "train_step_32x64.npz"))
+    m, sd = _model()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    x = golden_input((2, 3, 32, 64), 5)
+    y = golden_labels((2, 32, 64), 5)
+    crit = CrossEntropyLoss2d()
+    with emulated_kernels():
+        out = m(x)
+        loss = crit(out, y)
+        loss.backward()
+    # train-mode BN over 64-sample batches at this tiny size amplifies fp32 rounding: the oracle itself differs from
+    # its own float64 evaluation by 6.5e-4 here, so the logits tolerance is 3e-3 (eval mode holds 1e-4)
+    np.testing.assert_allclose(out.detach().numpy(), g["logits_step0"], rtol=1e-3, atol=3e-3)
+    np.testing.assert_allclose(float(loss), g["losses"][0], rtol=1e-4)
+    params = dict(m.named_parameters())
+    for k in g.files:
+        if k.startswith("grad0/") and np.abs(g[k]).max() > 1e-5:  # (pre-BN conv biases have a zero true gradient)
+            assert_rel(params[k[6:]].grad.numpy(), g[k], WHOLE_NET_GRAD_TOL, k)
+    assert sorted(k for k, p in params.items() if p.grad is None) == sorted(g["no_grad_keys"].tolist())
+    # oracle cross-check of ALL gradients and the BN running statistics
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    po = {k: v.requires_grad_(True) for k, v in sd_o.items() if v.is_floating_point() and "running" not in k}
+    lo = O.cross_entropy_2d(O.erfnet_forward(x, sd_o, training=True, dropprob=0.0), y)
+    lo.backward()
+    for k, p in params.items():
+        if p.grad is not None:
+            if po[k].grad.abs().max() > 1e-5:  # conv biases in front of a BN have an exactly-zero true gradient
+                assert_rel(p.grad.numpy(), po[k].grad.numpy(), WHOLE_NET_GRAD_TOL, k)
+    msd = m.state_dict()
+    for k in sd_o:
+        if "running" in k or "num_batches" in k:
+            np.testing.assert_allclose(msd[k].numpy(), sd_o[k].numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+def test_dropout_mask_injection_and_nhwc_loss():
+    m, sd = _model()
+    m.train()
+    x = golden_input((2, 3, 32, 64), 6)
+    y = golden_labels((2, 32, 64), 6)
+    gen = torch.Generator().manual_seed(3)
+    masks, masks_o = {}, {}
+    for name, mod in m.named_modules():
+        if isinstance(mod, E.non_bottleneck_1d) and mod.dropout.p != 0:
+            keep = (torch.rand(2, mod.chann, generator=gen) > 0.1).float() / 0.9
+            masks[mod] = keep
+            masks_o[name] = keep.view(2, mod.chann, 1, 1)
+    crit = CrossEntropyLoss2d(weight=torch.linspace(0.5, 1.5, 20))
+    with emulated_kernels():
+        loss = crit(m.forward_nhwc(x, drop_scales=masks), y, nhwc_classes=20)
+        loss.backward()
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    po = {k: v.requires_grad_(True) for k, v in sd_o.items() if v.is_floating_point() and "running" not in k}
+    lo = O.cross_entropy_2d(O.erfnet_forward(x, sd_o, training=True, drop_scales=masks_o), y, weight=torch.linspace(0.5, 1.5, 20))
+    lo.backward()
+    np.testing.assert_allclose(float(loss), float(lo), rtol=1e-5)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            if po[k].grad.abs().max() > 1e-5:  # conv biases in front of a BN have an exactly-zero true gradient
+                assert_rel(p.grad.numpy(), po[k].grad.numpy(), WHOLE_NET_GRAD_TOL, k)
+
+
+def test_blocks_standalone(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blocks.npz"))
+    blk = E.non_bottleneck_1d(128, 0.0, 16)
+    blk.precision = "fp32"
+    bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=3)
+    blk.load_state_dict({k[4:]: v for k, v in bsd.items()})
+    x = golden_input((2, 128, 18, 20), 26) - 0.3
+    blk.eval()
+    with emulated_kernels(), torch.no_grad():
+        np.testing.assert_allclose(blk(x).numpy(), g["nb128_d16_eval"], rtol=1e-4, atol=1e-4)
+    blk.train()
+    x.requires_grad_(True)
+    with emulated_kernels():
+        y = blk(x)
+        y.backward(golden_input(tuple(y.shape), 77) - 0.5)
+    np.testing.assert_allclose(y.detach().numpy(), g["nb128_d16_train"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(x.grad.numpy(), g["nb128_d16_train_dx"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(blk.conv1x3_2.weight.grad.numpy(), g["nb128_d16_train_dw_conv1x3_2"], rtol=2e-3, atol=2e-3)
+    up = E.UpsamplerBlock(128, 64)
+    up.precision = "fp32"
+    bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in up.state_dict().items()}, seed=5)
+    up.load_state_dict({k[4:]: v for k, v in bsd.items()})
+    xu = (golden_input((2, 128, 4, 8), 30 + 128) - 0.3).requires_grad_(True)
+    with emulated_kernels():
+        yu = up(xu)
+        yu.backward(golden_input(tuple(yu.shape), 79) - 0.5)
+    np.testing.assert_allclose(yu.detach().numpy(), g["up128_64_train"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(xu.grad.numpy(), g["up128_64_train_dx"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(up.conv.weight.grad.numpy(), g["up128_64_train_dw"], rtol=2e-3, atol=2e-3)
+    dn = E.DownsamplerBlock(16, 64)
+    dn.precision = "fp32"
+    bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in dn.state_dict().items()}, seed=4)
+    dn.load_state_dict({k[4:]: v for k, v in bsd.items()})
+    xd = (golden_input((2, 16, 8, 16), 20 + 16) - 0.3).requires_grad_(True)
+    with emulated_kernels():
+        yd = dn(xd)
+        yd.backward(golden_input(tuple(yd.shape), 78) - 0.5)
+    np.testing.assert_allclose(yd.detach().numpy(), g["down16_64_train"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(xd.grad.numpy(), g["down16_64_train_dx"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(dn.conv.weight.grad.numpy(), g["down16_64_train_dw"], rtol=2e-3, atol=2e-3)
+
+
+def test_odd_size_is_an_error():
+    m, _ = _model()
+    m.eval()
+    with emulated_kernels(), pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 60, 100))
+
+
+def test_iou_eval_kat(golden_dir):
+    g = np.load(os.path.join(golden_dir, "iou_kat.npz"))
+    for name, n in (("c20", 20), ("c20_big", 20), ("c5_noignore", 5)):
+        p, t = torch.from_numpy(g[name + "_pred"]).long(), torch.from_numpy(g[name + "_gt"]).long()
+        ev = iouEval(n)
+        with emulated_kernels():
+            ev.addBatch(p, t)
+            ev.addBatch(t.flip(0), t)
+            mean, per = ev.getIoU()
+        assert np.array_equal(ev.tp.numpy(), g[name + "_tp"]) and np.array_equal(ev.fp.numpy(), g[name + "_fp"])
+        assert np.array_equal(ev.fn.numpy(), g[name + "_fn"])
+        np.testing.assert_allclose(per.numpy(), g[name + "_iou"], rtol=1e-12)
+        np.testing.assert_allclose(float(mean), float(g[name + "_mean"]), rtol=1e-12)
+
+
+def test_no_cpu_fallback():
+    """Without the emulation (and without a GPU) the product must fail loudly, never compute on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m, _ = _model()
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 64))
+    with pytest.raises(RuntimeError):
+        iouEval(20).addBatch(torch.zeros(1, 1, 4, 4).long(), torch.zeros(1, 1, 4, 4).long())
