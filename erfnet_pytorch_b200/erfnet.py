@@ -111,8 +111,16 @@ class _B200Module(nn.Module):
         return _ToNCHW.apply(y, self._out_c)
 
 
+_WEIGHTS_EPOCH = 0  # bumped by code that updates parameters through aliases torch's version counters cannot see
+
+
+def bump_weights_epoch():
+    global _WEIGHTS_EPOCH
+    _WEIGHTS_EPOCH += 1
+
+
 def _sig(mod):
-    return tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
+    return (_WEIGHTS_EPOCH,) + tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
 
 
 

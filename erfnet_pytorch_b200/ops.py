@@ -21,6 +21,49 @@ def _count(n=1):
     LAUNCHES += n
 
 
+_TIMING = None  # list of (name, flops, start_event, end_event) while bench.py profiles one step
+
+
+def start_kernel_timing():
+    global _TIMING
+    _TIMING = []
+
+
+def stop_kernel_timing():
+    """-> {kernel name: {"ms": total, "n": launches, "flops": total algorithmic flops}} (synchronises)."""
+    global _TIMING
+    recs, _TIMING = _TIMING or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, e0, e1 in recs:
+        d = out.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+        d["flops"] += flops
+    return out
+
+
+class _timed:
+    def __init__(self, name, flops=0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _TIMING.append((self.name, self.flops, self.e0, e1))
+
+
+def conv_flops(spec, n, ho, wo):
+    taps = spec.kh * spec.kw / (spec.stride ** 2 if spec.transposed else 1)
+    return 2.0 * n * ho * wo * spec.cout * spec.cin * taps
+
+
 def dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return ERF_F32
@@ -121,7 +164,8 @@ def conv_fwd(x: torch.Tensor, wp: torch.Tensor, spec: ConvSpec, bias: Optional[t
     g = _geom(spec, x, out, out_coff)
     e = ConvEpilogue(_p(bias), int(relu), _p(mask), 0 if mask is None else mask.shape[-1], _p(add), 0 if add is None else add.shape[-1],
                      _p(stats), 0 if stats is None else stats.numel() // 2)
-    check(_lib.lib().erf_conv_fwd(_p(x), _p(wp), _p(out), C.byref(g), C.byref(e), dt(x), _stream(x)))
+    with _timed("conv_gather_kernel", conv_flops(spec, n, out.shape[1], out.shape[2])):
+        check(_lib.lib().erf_conv_fwd(_p(x), _p(wp), _p(out), C.byref(g), C.byref(e), dt(x), _stream(x)))
     _count()
     return out
 
@@ -131,7 +175,8 @@ def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0,
     dw = torch.zeros(spec.kh * spec.kw * spec.cin_p, spec.w_ld, device=x.device, dtype=torch.float32)
     db = torch.zeros(spec.cout, device=x.device, dtype=torch.float32) if want_bias else None
     g = _geom(spec, x, dout, dout_coff)
-    check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
+    with _timed("conv_wgrad_kernel", conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
+        check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
     _count(2 if want_bias else 1)
     return dw, db
 
@@ -225,29 +270,38 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
     return dy, dgamma, dbeta
 
 
-def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, c: int,
-                  nchw: bool, want_grad: bool):
-    """Returns (loss_sum fp32[1], wsum fp32[1], dlogits or None); loss = loss_sum / wsum."""
-    target = target.contiguous()
+def ce_weight_sum(target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int, wsum: torch.Tensor):
+    """wsum[0] += sum over valid pixels of weight[target] (1 when weight is None)."""
     if target.dtype != torch.int64:
         raise RuntimeError("CrossEntropyLoss2d: target must be int64")
-    n_px = target.numel()
-    dev = logits.device
-    acc = torch.zeros(2, device=dev, dtype=torch.float32)
-    wsum, lsum = acc[0:1], acc[1:2]
-    L = _lib.lib()
-    check(L.erf_ce_weight_sum(_p(target), n_px, _p(weight), c, ignore_index, _p(wsum), _stream(logits)))
+    check(_lib.lib().erf_ce_weight_sum(_p(target), target.numel(), _p(weight), c, ignore_index, _p(wsum), _stream(target)))
+    _count()
+
+
+def ce_fwd_bwd(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int,
+               wsum: torch.Tensor, lsum: torch.Tensor, nchw: bool = False, want_grad: bool = True):
+    """lsum[0] += sum_valid w[y]*nll; returns dlogits = w[y]*(softmax-onehot)/wsum (same layout/dtype as logits) or None."""
     dlog = torch.empty_like(logits) if want_grad else None
     if nchw:
-        hw = logits.shape[2] * logits.shape[3]
-        ld = 0
+        hw, ld = logits.shape[2] * logits.shape[3], 0
     else:
         hw, ld = 0, logits.shape[-1]
         if want_grad and ld > c:
             dlog.zero_()
-    check(L.erf_ce_fwd_bwd(_p(logits), ld, hw, _p(target), n_px, _p(weight), c, ignore_index, _p(wsum), _p(lsum), _p(dlog), dt(logits),
-                           _stream(logits)))
-    _count(2)
+    check(_lib.lib().erf_ce_fwd_bwd(_p(logits), ld, hw, _p(target), target.numel(), _p(weight), c, ignore_index, _p(wsum), _p(lsum), _p(dlog),
+                                    dt(logits), _stream(logits)))
+    _count()
+    return dlog
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, c: int,
+                  nchw: bool, want_grad: bool):
+    """Returns (loss_sum fp32[1], wsum fp32[1], dlogits or None); loss = loss_sum / wsum."""
+    target = target.contiguous()
+    acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+    wsum, lsum = acc[0:1], acc[1:2]
+    ce_weight_sum(target, weight, c, ignore_index, wsum)
+    dlog = ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw, want_grad)
     return lsum, wsum, dlog
 
 

@@ -1,0 +1,161 @@
+"""One-process-per-GPU data-parallel training of ERFNet (replaces nn.DataParallel).
+
+Reference behaviour being reproduced (train/main.py:297-392 under nn.DataParallel):
+  * the loss is taken over the GATHERED global batch -> here every rank normalises its cross-entropy by the
+    all-reduced sum of valid-pixel weights, and gradients are SUM-all-reduced (not averaged);
+  * BatchNorm statistics are per replica (no SyncBN); running stats survive from replica 0;
+  * Adam(lr 1e-4, betas (.9,.999), eps 1e-4, weight_decay 1e-6) with L2 in the gradient (train/main.py:43-46,213).
+
+B200 design: parameters, gradients and Adam moments live in ONE flat fp32 buffer each (2.07 M values); gradients
+are all-reduced in 3 contiguous buckets in reverse graph order (decoder, 128-ch encoder, 64-ch encoder + stem),
+each launched on a side stream from a post-accumulate-grad hook as soon as its last gradient is written, so NCCL
+over NVLink overlaps the rest of backward; the optimizer is one fused kernel over the flat buffers.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import erfnet as _erfnet
+from . import ops
+from .evaluation_functions import CrossEntropyLoss2d
+
+
+def _bucket_of(name: str) -> int:
+    if name.startswith("decoder."):
+        return 0
+    if name.startswith("encoder.layers."):
+        idx = int(name.split(".")[2])
+        return 1 if idx >= 6 else 2
+    return 2  # initial_block, encoder.output_conv
+
+
+class FlatAdamTrainer:
+    """Fused training step: forward (NHWC logits) -> CE fwd+bwd kernel -> backward -> bucketed all-reduce -> flat Adam."""
+
+    def __init__(self, model, weight=None, ignore_index=-1, lr=1e-4, betas=(0.9, 0.999), eps=1e-4, weight_decay=1e-6,
+                 process_group=None, num_classes=None):
+        self.model = model
+        self.num_classes = num_classes or model.num_classes
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.criterion = CrossEntropyLoss2d(weight, ignore_index)
+        self.step_count = 0
+        named = list(model.named_parameters())
+        # flat layout ordered by bucket so that each bucket is one contiguous slice
+        order = sorted(range(len(named)), key=lambda i: (_bucket_of(named[i][0]), i))
+        total = sum(p.numel() for _, p in named)
+        dev = named[0][1].device
+        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.bucket_slices: List[List[int]] = [[None, None] for _ in range(3)]
+        self._bucket_params = [0, 0, 0]
+        self._param_bucket = {}
+        off = 0
+        for i in order:
+            name, p = named[i]
+            n = p.numel()
+            b = _bucket_of(name)
+            self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + n].view_as(p)
+            p.grad = self.flat_g[off:off + n].view_as(p)
+            sl = self.bucket_slices[b]
+            sl[0] = off if sl[0] is None else sl[0]
+            sl[1] = off + n
+            self._bucket_params[b] += 1
+            self._param_bucket[p] = b
+            off += n
+        self._pending = list(self._bucket_params)
+        self._launched = [False, False, False]
+        self._works = []
+        self.cuda = dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
+        if self.world > 1:
+            for p in model.parameters():
+                p.register_post_accumulate_grad_hook(self._hook)
+            # every rank starts from rank 0's weights (nn.DataParallel replicates GPU0's module each forward)
+            dist.broadcast(self.flat_p, 0, group=self.pg)
+            for b in model.buffers():
+                dist.broadcast(b, 0, group=self.pg)
+
+    # ---- gradient buckets ---------------------------------------------------------------------------------
+    def _launch_bucket(self, b):
+        if self._launched[b] or self.world == 1:
+            return
+        self._launched[b] = True
+        lo, hi = self.bucket_slices[b]
+        if lo is None:
+            return
+        buf = self.flat_g[lo:hi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+        else:
+            self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _hook(self, p):
+        b = self._param_bucket[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch_bucket(b)
+
+    def _finish_buckets(self):
+        for b in range(3):  # buckets holding parameters that received no gradient (encoder.output_conv) never count down
+            self._launch_bucket(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._pending = list(self._bucket_params)
+        self._launched = [False, False, False]
+
+    # ---- one step ---------------------------------------------------------------------------------------------
+    def loss_and_backward(self, images, labels, drop_scales=None):
+        """images NCHW fp32, labels int64 [B,H,W] on the model's device.  Returns the GLOBAL-batch loss (0-dim tensor)."""
+        self.flat_g.zero_()
+        self.model.train()
+        logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
+        c = self.num_classes
+        w = self.criterion.weight
+        w = None if w is None else w.to(logits.device)
+        labels = labels.contiguous()
+        # pass 1: valid-pixel weight sum, all-reduced so that every rank normalises by the global denominator
+        acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+        wsum, lsum = acc[0:1], acc[1:2]
+        ops.ce_weight_sum(labels, w, c, self.criterion.ignore_index, wsum)
+        if self.world > 1:
+            dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=self.pg)
+        dlog = ops.ce_fwd_bwd(logits.detach(), labels, w, c, self.criterion.ignore_index, wsum, lsum)
+        logits.backward(dlog)
+        self._finish_buckets()
+        if self.world > 1:
+            dist.all_reduce(lsum, op=dist.ReduceOp.SUM, group=self.pg)
+        return (lsum / wsum).reshape(())
+
+    def optimizer_step(self):
+        self.step_count += 1
+        ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                      self.step_count)
+        _erfnet.bump_weights_epoch()  # flat_p aliases the parameters; invalidate eval-mode packed weights
+
+    def train_step(self, images, labels, drop_scales=None):
+        loss = self.loss_and_backward(images, labels, drop_scales)
+        self.optimizer_step()
+        return loss
+
+
+def allreduce_confusion(ev, process_group=None):
+    """Sum the per-rank iouEval confusion matrices (config 5: eval shards by batch; only 400 counters cross GPUs)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        cm = ev.confusion_matrix()
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=process_group)
+        ev._cm = cm
+        ev._dirty = True
+    return ev

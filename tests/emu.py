@@ -158,26 +158,32 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
     return dy.to(y.dtype), s2, s1
 
 
+def ce_weight_sum(target, weight, c, ignore_index, wsum):
+    valid = target != ignore_index
+    t = torch.where(valid, target, torch.zeros_like(target))
+    w = torch.ones(c) if weight is None else weight
+    wsum += (w[t] * valid).sum()
+
+
 @torch.enable_grad()
-def cross_entropy(logits, target, weight, ignore_index, c, nchw, want_grad):
-    lg = logits.float() if nchw else logits[..., :c].float().permute(0, 3, 1, 2)
-    lg = lg.detach().requires_grad_(True)
+def ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw=False, want_grad=True):
+    lg = logits.detach().float() if nchw else logits.detach()[..., :c].float().permute(0, 3, 1, 2)
+    lg = lg.requires_grad_(True)
     valid = target != ignore_index
     t = torch.where(valid, target, torch.zeros_like(target))
     w = torch.ones(c) if weight is None else weight
     wpx = w[t] * valid
     nll = -F.log_softmax(lg, 1).gather(1, t.unsqueeze(1)).squeeze(1)
-    lsum = (wpx * nll).sum()
-    wsum = wpx.sum()
-    dlog = None
-    if want_grad:
-        (g,) = torch.autograd.grad(lsum / wsum, lg)
-        if nchw:
-            dlog = g
-        else:
-            dlog = torch.zeros_like(logits)
-            dlog[..., :c] = g.permute(0, 2, 3, 1).to(logits.dtype)
-    return lsum.detach().reshape(1), wsum.reshape(1), dlog
+    ls = (wpx * nll).sum()
+    lsum += ls.detach()
+    if not want_grad:
+        return None
+    (g,) = torch.autograd.grad(ls / wsum[0], lg)
+    if nchw:
+        return g
+    dlog = torch.zeros_like(logits)
+    dlog[..., :c] = g.permute(0, 2, 3, 1).to(logits.dtype)
+    return dlog
 
 
 def confusion_hist(pred, gt, nc, cm):
@@ -207,7 +213,7 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
 
 
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "cross_entropy", "confusion_hist", "iou_counts", "argmax", "adam_step"]
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step"]
 
 
 @contextlib.contextmanager

@@ -1,0 +1,212 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+fp32 "check mode" must hold 1e-4 max relative error (north_star); bf16 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from erfnet_pytorch_b200 import erfnet as E
+from erfnet_pytorch_b200 import ops
+from erfnet_pytorch_b200.evaluation_functions import CrossEntropyLoss2d
+from erfnet_pytorch_b200.iouEval import iouEval
+from oracle import erfnet_oracle as O
+from oracle.make_golden import golden_input, golden_labels
+from tests.test_host_logic import WHOLE_NET_GRAD_TOL, assert_rel
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4   # north_star: logits within 1e-4 in the fp32 check mode
+BF16_TOL = 2e-2   # north_star: logits within 2e-2 max relative error in bf16
+
+
+def _model(precision, seed=0, nc=20):
+    m = E.ERFNet(nc)
+    m.precision = precision
+    sd = O.make_state_dict(O.erfnet_param_shapes(nc), seed)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda(), sd
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_whole_net_eval_vs_oracle_and_golden(precision, tol, golden_dir):
+    g = np.load(os.path.join(golden_dir, "erfnet_eval_64x128.npz"))
+    m, sd = _model(precision)
+    m.eval()
+    x = golden_input((1, 3, 64, 128), 0)
+    with torch.no_grad():
+        y = m(x.cuda()).cpu()
+        ye = m(x.cuda(), only_encode=True).cpu()
+        ref = O.erfnet_forward(x, sd)
+    assert y.shape == (1, 20, 64, 128) and y.dtype == torch.float32
+    assert_rel(y.numpy(), g["logits"], tol, "logits vs golden")
+    assert_rel(y.numpy(), ref.numpy(), tol, "logits vs oracle")
+    assert_rel(ye.numpy(), g["enc_logits"], tol, "encoder logits vs golden")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_larger_image_and_batch(precision, tol):
+    """Non-square, batch 3, all dilations active in the interior (H/8 = 24 > 16)."""
+    m, sd = _model(precision, seed=2)
+    m.eval()
+    x = golden_input((3, 3, 192, 320), 3)
+    with torch.no_grad():
+        y = m(x.cuda()).cpu()
+        ref = O.erfnet_forward(x, sd)
+    assert_rel(y.numpy(), ref.numpy(), tol)
+    if precision == "fp32":
+        assert (y.argmax(1) == ref.argmax(1)).float().mean() > 0.999
+
+
+def test_blocks_train_fwd_bwd_fp32(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blocks.npz"))
+    cases = {"nb64_d1": (64, 1, (8, 24)), "nb128_d2": (128, 2, (8, 12)), "nb128_d16": (128, 16, (18, 20)),
+             "nb16_d1": (16, 1, (16, 24)), "nb128_d4": (128, 4, (8, 16)), "nb128_d8": (128, 8, (10, 18))}
+    for name, (c, d, hw) in cases.items():
+        blk = E.non_bottleneck_1d(c, 0.0, d)
+        blk.precision = "fp32"
+        bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=3)
+        blk.load_state_dict({k[4:]: v for k, v in bsd.items()})
+        blk.cuda()
+        x = (golden_input((2, c) + hw, 10 + d) - 0.3).cuda()
+        blk.eval()
+        with torch.no_grad():
+            assert_rel(blk(x).cpu().numpy(), g[name + "_eval"], FP32_TOL, name + " eval")
+        blk.train()
+        x.requires_grad_(True)
+        y = blk(x)
+        y.backward((golden_input(tuple(y.shape), 77) - 0.5).cuda())
+        assert_rel(y.detach().cpu().numpy(), g[name + "_train"], 2e-4, name + " train")
+        assert_rel(x.grad.cpu().numpy(), g[name + "_train_dx"], 1e-3, name + " dx")
+        assert_rel(blk.conv1x3_2.weight.grad.cpu().numpy(), g[name + "_train_dw_conv1x3_2"], 1e-3, name + " dw4")
+        assert_rel(blk.conv3x1_1.weight.grad.cpu().numpy(), g[name + "_train_dw_conv3x1_1"], 1e-3, name + " dw1")
+        assert_rel(blk.bn1.weight.grad.cpu().numpy(), g[name + "_train_dgamma1"], 1e-3, name + " dgamma1")
+        assert_rel(blk.bn2.running_mean.cpu().numpy(), g[name + "_train_rm2"], 1e-4, name + " rm2")
+        assert_rel(blk.bn2.running_var.cpu().numpy(), g[name + "_train_rv2"], 1e-4, name + " rv2")
+    for name, (ci, co, hw) in {"down3_16": (3, 16, (16, 32)), "down16_64": (16, 64, (8, 16)), "down64_128": (64, 128, (8, 8))}.items():
+        blk = E.DownsamplerBlock(ci, co)
+        blk.precision = "fp32"
+        bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=4)
+        blk.load_state_dict({k[4:]: v for k, v in bsd.items()})
+        blk.cuda()
+        x = (golden_input((2, ci) + hw, 20 + ci) - 0.3).cuda()
+        blk.eval()
+        with torch.no_grad():
+            assert_rel(blk(x).cpu().numpy(), g[name + "_eval"], FP32_TOL, name + " eval")
+        blk.train()
+        x.requires_grad_(True)
+        y = blk(x)
+        y.backward((golden_input(tuple(y.shape), 78) - 0.5).cuda())
+        assert_rel(y.detach().cpu().numpy(), g[name + "_train"], 2e-4, name + " train")
+        assert_rel(x.grad.cpu().numpy(), g[name + "_train_dx"], 1e-3, name + " dx")
+        assert_rel(blk.conv.weight.grad.cpu().numpy(), g[name + "_train_dw"], 1e-3, name + " dw")
+    for name, (ci, co, hw) in {"up128_64": (128, 64, (4, 8)), "up64_16": (64, 16, (8, 8))}.items():
+        blk = E.UpsamplerBlock(ci, co)
+        blk.precision = "fp32"
+        bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=5)
+        blk.load_state_dict({k[4:]: v for k, v in bsd.items()})
+        blk.cuda()
+        x = (golden_input((2, ci) + hw, 30 + ci) - 0.3).cuda()
+        blk.eval()
+        with torch.no_grad():
+            assert_rel(blk(x).cpu().numpy(), g[name + "_eval"], FP32_TOL, name + " eval")
+        blk.train()
+        x.requires_grad_(True)
+        y = blk(x)
+        y.backward((golden_input(tuple(y.shape), 79) - 0.5).cuda())
+        assert_rel(y.detach().cpu().numpy(), g[name + "_train"], 2e-4, name + " train")
+        assert_rel(x.grad.cpu().numpy(), g[name + "_train_dx"], 1e-3, name + " dx")
+        assert_rel(blk.conv.weight.grad.cpu().numpy(), g[name + "_train_dw"], 1e-3, name + " dw")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_vs_golden(precision, golden_dir):
+    g = np.load(os.path.join(golden_dir, "train_step_32x64.npz"))
+    m, sd = _model(precision)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    x = golden_input((2, 3, 32, 64), 5).cuda()
+    y = golden_labels((2, 32, 64), 5).cuda()
+    crit = CrossEntropyLoss2d()
+    out = m(x)
+    loss = crit(out, y)
+    loss.backward()
+    tol = 3e-3 if precision == "fp32" else 5e-2
+    assert_rel(out.detach().cpu().numpy(), g["logits_step0"], tol, "train logits")
+    assert abs(float(loss) - g["losses"][0]) <= (1e-4 if precision == "fp32" else 2e-2) * g["losses"][0]
+    params = dict(m.named_parameters())
+    if precision == "fp32":
+        for k in g.files:
+            if k.startswith("grad0/") and np.abs(g[k]).max() > 1e-5:
+                assert_rel(params[k[6:]].grad.cpu().numpy(), g[k], WHOLE_NET_GRAD_TOL, k)
+    assert sorted(k for k, p in params.items() if p.grad is None) == sorted(g["no_grad_keys"].tolist())
+
+
+def test_cross_entropy_kernel(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ce_loss.npz"))
+    lg = ((golden_input((2, 20, 16, 24), 8) - 0.5) * 6).cuda().requires_grad_(True)
+    lb = golden_labels((2, 16, 24), 8).cuda()
+    l = CrossEntropyLoss2d()(lg, lb)
+    l.backward()
+    np.testing.assert_allclose(float(l), float(g["loss"]), rtol=1e-5)
+    assert_rel(lg.grad.cpu().numpy(), g["dlogits"], 1e-5)
+    lw = CrossEntropyLoss2d(weight=torch.linspace(0.5, 1.5, 20))(lg.detach(), lb)
+    np.testing.assert_allclose(float(lw), float(g["loss_weighted"]), rtol=1e-5)
+    # all pixels ignored -> nan like torch
+    assert torch.isnan(CrossEntropyLoss2d()(lg.detach(), torch.full_like(lb, -1)))
+
+
+def test_iou_eval_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "iou_kat.npz"))
+    for name, n in (("c20", 20), ("c20_big", 20), ("c5_noignore", 5)):
+        p8, t8 = torch.from_numpy(g[name + "_pred"]).cuda(), torch.from_numpy(g[name + "_gt"]).cuda()
+        for cast in (lambda t: t.long(), lambda t: t):  # int64 (reference API) and the fused u8 path
+            ev = iouEval(n)
+            ev.addBatch(cast(p8), cast(t8))
+            ev.addBatch(cast(t8.flip(0)), cast(t8))
+            mean, per = ev.getIoU()
+            assert np.array_equal(ev.tp.numpy(), g[name + "_tp"]) and np.array_equal(ev.fp.numpy(), g[name + "_fp"])
+            assert np.array_equal(ev.fn.numpy(), g[name + "_fn"])
+            np.testing.assert_allclose(per.numpy(), g[name + "_iou"], rtol=1e-12)
+    # full config-5 size: 8 x 1024 x 2048 labels, checksum properties + oracle on a slice
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    p = torch.randint(0, 20, (8, 1, 1024, 2048), device="cuda", generator=gen, dtype=torch.int64)
+    t = torch.randint(0, 20, (8, 1, 1024, 2048), device="cuda", generator=gen, dtype=torch.int64)
+    ev = iouEval(20)
+    ev.addBatch(p, t)
+    ev.getIoU()
+    cm = ev.confusion_matrix().cpu().numpy()
+    assert cm.sum() == p.numel()
+    assert np.array_equal(cm.sum(1), np.bincount(t.cpu().numpy().ravel(), minlength=20))
+    tp, fp, fn = O.iou_counts(p[:1].cpu().numpy(), t[:1].cpu().numpy(), 20)
+    ev1 = iouEval(20)
+    ev1.addBatch(p[:1], t[:1])
+    ev1.getIoU()
+    assert np.array_equal(ev1.tp.numpy(), tp) and np.array_equal(ev1.fp.numpy(), fp) and np.array_equal(ev1.fn.numpy(), fn)
+    # empty batch is a no-op
+    ev1.addBatch(p[:0], t[:0])
+
+
+def test_argmax_and_adam():
+    lg = (golden_input((2, 20, 16, 24), 9) - 0.5).cuda()
+    assert torch.equal(ops.argmax(lg, 20, True), lg.argmax(1))
+    n = 10007
+    gen = torch.Generator().manual_seed(4)
+    p, gr = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.clone().cuda(), m.clone().cuda(), v.clone().cuda()
+    for step in (1, 2, 3):
+        O.adam_step(p, gr, m, v, step)
+        ops.adam_step(pc, gr.cuda(), mc, vc, 1e-4, 0.9, 0.999, 1e-4, 1e-6, step)
+    np.testing.assert_allclose(pc.cpu().numpy(), p.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_state_dict_roundtrip_and_module_prefix():
+    m, sd = _model("fp32")
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())
+    wrapped = {"module." + k: v for k, v in out.items()}  # DataParallel-saved checkpoint (eval/eval_iou.py:54-65)
+    own = m.state_dict()
+    for name, param in wrapped.items():
+        own[name.split("module.")[-1]].copy_(param)
