@@ -248,11 +248,21 @@ class non_bottleneck_1d(_B200Module):
                 scale, shift = _bn_fold(bn)
                 ws[i] = ws[i] * scale.view(-1, 1, 1, 1)
                 bs[i] = bs[i] * scale + shift
-        return dict(w=[ops.pack_weight_fwd(w, s, dtype) for w, s in zip(ws, self.specs)], b=[b.contiguous() for b in bs])
+        pk = dict(w=[ops.pack_weight_fwd(w, s, dtype) for w, s in zip(ws, self.specs)], b=[b.contiguous() for b in bs])
+        if dtype == torch.bfloat16 and self.chann in (64, 128) and not ops.EMULATED:
+            pk["tc"] = [ops.pack_conv1d_tc(w) for w in ws]  # tcgen05 operand images (BN folded)
+        return pk
 
     def _fwd_eval(self, x, ctx):
         pk = self._cache(ctx.dtype)
         w, b, s = pk["w"], pk["b"], self.specs
+        d = self.dilated
+        if "tc" in pk and ops.conv1d_tc_supported(self.chann, x.shape[2], d, x.dtype) and ops.USE_TC:
+            tc = pk["tc"]
+            t = ops.conv1d_tc(x, tc[0], b[0], False, 1, relu=True)
+            t = ops.conv1d_tc(t, tc[1], b[1], True, 1, relu=True)
+            t = ops.conv1d_tc(t, tc[2], b[2], False, d, relu=True)
+            return ops.conv1d_tc(t, tc[3], b[3], True, d, relu=True, res=x)
         t = ops.conv_fwd(x, w[0], s[0], b[0], relu=True)
         t = ops.conv_fwd(t, w[1], s[1], b[1], relu=True)
         t = ops.conv_fwd(t, w[2], s[2], b[2], relu=True)

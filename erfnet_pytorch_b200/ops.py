@@ -12,6 +12,7 @@ import torch
 from . import _lib
 from ._lib import ERF_BF16, ERF_F32, ConvEpilogue, ConvGeom, check
 
+USE_TC = True     # tests flip this to compare the tcgen05 kernels with the generic CUDA-core path
 EMULATED = False  # set by tests/emu.py only (CPU emulation of the kernel contracts for host-logic tests)
 LAUNCHES = 0  # number of kernel-launching library calls made by this process (bench.py reports it)
 
@@ -179,6 +180,37 @@ def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0,
         check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
     _count(2 if want_bias else 1)
     return dw, db
+
+
+def conv1d_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
+    return dtype == torch.bfloat16 and not EMULATED and bool(_lib.lib().erf_conv1d_tc_supported(c, w, dil))
+
+
+def pack_conv1d_tc(w: torch.Tensor, dgrad: bool = False) -> torch.Tensor:
+    """Conv2d weight [Co,Ci,3,1] or [Co,Ci,1,3] (fp32, BN already folded) -> bf16 shared-memory image
+    [3][C/64][C][64] for erf_conv1d_tc: tile (t,kc) row n holds Wt[t][n][kc*64 .. +64] with its eight 16-byte chunks
+    XOR-swizzled by (n & 7).  dgrad=True packs the data-gradient operand (taps flipped, channels transposed)."""
+    co, ci = w.shape[:2]
+    wt = w.reshape(co, ci, 3).permute(2, 0, 1)  # [t][co][ci]
+    if dgrad:
+        wt = wt.flip(0).transpose(1, 2)         # [t'][ci][co] = W[co,ci,2-t']
+    c = wt.shape[1]
+    img = wt.reshape(3, c, c // 64, 8, 8).permute(0, 2, 1, 3, 4)  # [t][kc][n][j][e]
+    n = torch.arange(c, device=w.device)
+    perm = torch.arange(8, device=w.device)[None, :] ^ (n[:, None] & 7)  # [n][jj] -> source chunk
+    idx = perm[None, None, :, :, None].expand(3, c // 64, c, 8, 8)
+    return img.gather(3, idx).contiguous().to(torch.bfloat16)
+
+
+def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
+              res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    with _timed("conv1d_tc_kernel", 2.0 * n * h * w * c * c * 3):
+        check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu),
+                                       _stream(x)))
+    _count()
+    return out
 
 
 def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):

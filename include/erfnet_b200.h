@@ -144,6 +144,16 @@ int erf_argmax(const void* logits, int ld, int nchw_hw, long long n_px, int C, v
 int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, erf_stream_t stream);
 
+/* ---- tcgen05 implicit-GEMM 3x1 / 1x3 (dilated) convolution, C = 64 or 128, NHWC bf16 ----------
+ * out[p,co] = epilogue(sum_t sum_ci in[p + (t-1)*dil along H (horizontal=0) or W (horizontal=1), ci] * Wt[t][co][ci]),
+ * epilogue as erf_conv_fwd (bias -> + res -> relu -> * (mask>0)).  TMA-staged 128B-swizzled activation tiles (zero-filled
+ * borders = padding), tcgen05.mma with TMEM accumulators.  w_img = host-packed shared-memory image [3][C/64][C][64] bf16
+ * with the 16-byte chunks of row n XOR-swizzled by (n & 7) (erfnet_pytorch_b200.ops.pack_conv1d_tc).
+ * Returns ERF_ERR_UNSUPPORTED unless erf_conv1d_tc_supported(C, W, dil). */
+int erf_conv1d_tc_supported(int C, int W, int dil);
+int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask,
+                  int N, int H, int W, int C, int horizontal, int dil, int relu, erf_stream_t stream);
+
 /* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
 /* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
  * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle
