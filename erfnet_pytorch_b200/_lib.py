@@ -32,6 +32,7 @@ _SIGNATURES = {
     "erf_nchw_f32_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "erf_nhwc_to_nchw_f32": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "erf_affine_act": [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_channel_stats": [_vp, _i, _i, _ll, _vp, _i, _vp],
     "erf_relu_bwd": [_vp, _i, _vp, _i, _vp, _i, _ll, _i, _i, _vp],
     "erf_bn_finalize": [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "erf_bn_eval_affine": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp],

@@ -98,6 +98,34 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ in, int N, int H, int W
   *dp = from_f<T>(to_f(*dp) + to_f(dout[(size_t)p * out_ld + out_coff + c]));
 }
 
+// stats[c] += sum_p x[p][c], stats[C+c] += sum_p x[p][c]^2  (BN batch statistics of a stored activation)
+template <typename T>
+__global__ void channel_stats_kernel(const T* __restrict__ x, int ld, int C, long long n_px, int px_per_block, double* __restrict__ stats) {
+  extern __shared__ float s[];  // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s[i] = 0.f;
+  __syncthreads();
+  const int c8 = C / 8;                       // 8-channel (16-byte for bf16) groups
+  const int lanes = blockDim.x / c8;
+  const int g = threadIdx.x % c8, lane = threadIdx.x / c8;
+  long long p0 = (long long)blockIdx.x * px_per_block, p1 = p0 + px_per_block;
+  if (p1 > n_px) p1 = n_px;
+  if (lane < lanes) {
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      Vec<T, 8> v;
+      v.load(x + (size_t)p * ld + g * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] += v.v[k]; b[k] += v.v[k] * v.v[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s[g * 8 + k], a[k]); atomicAdd(&s[C + g * 8 + k], b[k]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], (double)s[i]);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void affine_act_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -326,6 +354,22 @@ extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const
   else
     affine_act_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_ld, scale, shift, sc_per_sample, (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out, out_ld, HW, C, total4, relu);
   ERF_CHECK_LAUNCH("erf_affine_act");
+  return ERF_OK;
+}
+
+extern "C" int erf_channel_stats(const void* x, int ld, int C, long long n_px, double* stats, int dtype, erf_stream_t stream) {
+  CHECK_DTYPE("erf_channel_stats");
+  ERF_CHECK_ARG(x && stats && n_px > 0 && C >= 8 && (C % 8) == 0 && C <= 2048 && (ld % 8) == 0, "erf_channel_stats: C and ld must be multiples of 8");
+  long long want = 148 * 8;
+  long long ppb = (n_px + want - 1) / want;
+  if (ppb < 128) ppb = 128;
+  unsigned grid = (unsigned)((n_px + ppb - 1) / ppb);
+  size_t smem = 2 * C * sizeof(float);
+  if (dtype == ERF_F32)
+    channel_stats_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)x, ld, C, n_px, (int)ppb, stats);
+  else
+    channel_stats_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, C, n_px, (int)ppb, stats);
+  ERF_CHECK_LAUNCH("erf_channel_stats");
   return ERF_OK;
 }
 

@@ -282,24 +282,41 @@ class non_bottleneck_1d(_B200Module):
         ones = torch.ones(x.shape[0], self.chann, 1, 1, device=x.device)
         return F.dropout2d(ones, p, True).reshape(x.shape[0], self.chann).contiguous()
 
+    def _use_tc(self, x):
+        return (self.chann in (64, 128) and ops.USE_TC and ops.conv1d_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
+                and ops.conv1d_tc_supported(self.chann, x.shape[2], 1, x.dtype))
+
+    def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None):
+        """conv i (0..3) of the block (or its data gradient when spec is a dgrad spec) on the tcgen05 or the generic kernel."""
+        if tc:
+            y = ops.conv1d_tc(x, w, bias, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, relu=relu, res=add, mask=mask)
+            if stats is not None:
+                ops.channel_stats(y, stats)
+            return y
+        return ops.conv_fwd(x, w, spec or self.specs[i], bias, relu=relu, stats=stats, mask=mask, add=add, out_hw=x.shape[1:3])
+
     def _fwd_train(self, x, ctx):
         if not self.use_batchnorm:
             raise RuntimeError("training with use_batchnorm=False is not implemented yet")
         n, h, w, c = x.shape
         s, dtp = self.specs, x.dtype
         cv = self._convs()
-        wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
+        tc = self._use_tc(x)
+        if tc:
+            wp = [ops.pack_conv1d_tc(m.weight.detach()) for m in cv]
+        else:
+            wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         bs = [m.bias.detach().float() for m in cv]
         count = n * h * w
         st = torch.zeros(2, 2 * c, device=x.device, dtype=torch.float64)
-        t1 = ops.conv_fwd(x, wp[0], s[0], bs[0], relu=True)
-        y2 = ops.conv_fwd(t1, wp[1], s[1], bs[1], stats=st[0])
+        t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
+        y2 = self._conv(1, t1, wp[1], bs[1], tc, stats=st[0])
         mean1, invstd1, sc1, sh1 = ops.bn_finalize(st[0], count, self.bn1.weight.detach(), self.bn1.bias.detach(), self.bn1.running_mean,
                                                    self.bn1.running_var, BN_MOMENTUM, BN_EPS)
         self.bn1.num_batches_tracked += 1
         a2 = ops.affine_act(y2, sc1, sh1, relu=True)
-        t3 = ops.conv_fwd(a2, wp[2], s[2], bs[2], relu=True)
-        y4 = ops.conv_fwd(t3, wp[3], s[3], bs[3], stats=st[1])
+        t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True)
+        y4 = self._conv(3, t3, wp[3], bs[3], tc, stats=st[1])
         drop = self._drop_scale(x, ctx)
         mean2, invstd2, sc2, sh2 = ops.bn_finalize(st[1], count, self.bn2.weight.detach(), self.bn2.bias.detach(), self.bn2.running_mean,
                                                    self.bn2.running_var, BN_MOMENTUM, BN_EPS, drop=drop)
@@ -311,22 +328,25 @@ class non_bottleneck_1d(_B200Module):
         x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop = saved
         s, dtp = self.specs, x.dtype
         cv = self._convs()
-        wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
+        tc = self._use_tc(x)
         ds = [ops.dgrad_spec(sp) for sp in s]
-        hw = x.shape[1:3]
+        if tc:
+            wd = [ops.pack_conv1d_tc(m.weight.detach(), dgrad=True) for m in cv]
+        else:
+            wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, self.bn2.weight.detach(), mean2, invstd2, mask=out, drop=drop)
         dw4, db4 = ops.conv_wgrad(t3, dy4, s[3])
-        dt3 = ops.conv_fwd(dy4, wd[3], ds[3], mask=t3, out_hw=hw)
+        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3])
         dw3, db3 = ops.conv_wgrad(a2, dt3, s[2])
-        da2 = ops.conv_fwd(dt3, wd[2], ds[2], out_hw=hw)
+        da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2])
         dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, self.bn1.weight.detach(), mean1, invstd1, mask=a2)
         dw2, db2 = ops.conv_wgrad(t1, dy2, s[1])
-        dt1 = ops.conv_fwd(dy2, wd[1], ds[1], mask=t1, out_hw=hw)
+        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1])
         dw1, db1 = ops.conv_wgrad(x, dt1, s[0])
         dx = None
         if need_dx:
             gres = ops.relu_bwd(dout, out)
-            dx = ops.conv_fwd(dt1, wd[0], ds[0], add=gres, out_hw=hw)
+            dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
         u = ops.unpack_wgrad
         return dx, (u(dw1, s[0]), db1, u(dw2, s[1]), db2, dg1, dbe1, u(dw3, s[2]), db3, u(dw4, s[3]), db4, dg2, dbe2)
 

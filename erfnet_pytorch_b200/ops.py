@@ -254,6 +254,12 @@ def affine_act(x, scale=None, shift=None, res=None, relu=True, out=None):
     return out
 
 
+def channel_stats(x, stats):
+    n, h, w, c = x.shape
+    check(_lib.lib().erf_channel_stats(_p(x), c, c, n * h * w, _p(stats), dt(x), _stream(x)))
+    _count()
+
+
 def relu_bwd(g, mask):
     n, h, w, c = g.shape
     out = torch.empty_like(g)
@@ -381,3 +387,19 @@ def umma_probe(a: torch.Tensor, b: torch.Tensor, row_shift: int, layout: int, it
     check(_lib.lib().erf_umma_probe(_p(a), rows, _p(b), n, k // 16, row_shift, layout, _p(d), iters, _p(cyc), _stream(a)))
     _count()
     return d, cyc
+
+
+def _wrap_timed(name):
+    fn = globals()[name]
+
+    def wrapper(*a, **k):
+        with _timed(name):
+            return fn(*a, **k)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    globals()[name] = wrapper
+
+
+for _n in ("channel_stats", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
+           "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
+           "unpack_wgrad", "pack_conv1d_tc"):
+    _wrap_timed(_n)

@@ -101,6 +101,10 @@ int erf_affine_act(const void* x, int x_ld, const float* scale, const float* shi
 int erf_relu_bwd(const void* g, int g_ld, const void* mask, int mask_ld, void* out, int out_ld, long long n_px, int C,
                  int dtype, erf_stream_t stream);
 
+/* stats[c] += sum_p x[p,c]; stats[C+c] += sum_p x[p,c]^2 over a stored NHWC activation (BN batch statistics when the
+ * producing kernel does not accumulate them itself) */
+int erf_channel_stats(const void* x, int ld, int C, long long n_px, double* stats, int dtype, erf_stream_t stream);
+
 /* ---- BatchNorm2d(eps=1e-3) training statistics --------------------------------------- */
 /* stats[2C] (sum, sumsq over `count` values/channel) -> mean, invstd (biased var), running stats update
  * (momentum, unbiased var), and the fused apply vectors scale/shift: [C], or [N,C] when drop ([N,C] Dropout2d

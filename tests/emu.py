@@ -118,6 +118,12 @@ def affine_act(x, scale=None, shift=None, res=None, relu=True, out=None):
     return y.to(x.dtype)
 
 
+def channel_stats(x, stats):
+    c = x.shape[-1]
+    stats[:c] += x.double().sum((0, 1, 2))
+    stats[c:] += (x.double() ** 2).sum((0, 1, 2))
+
+
 def relu_bwd(g, mask):
     return (g.float() * (mask.float() > 0)).to(g.dtype)
 
@@ -212,7 +218,7 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
 
-_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize",
+_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "relu_bwd", "bn_finalize",
           "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step"]
 
 
