@@ -46,6 +46,9 @@ _SIGNATURES = {
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_conv1d_wgrad_tc_workspace": [_i],
+    "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],
     "erf_umma_probe": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
 }
 
@@ -68,7 +71,7 @@ def lib():
         L.erf_last_error_string.argtypes = []
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
-            fn.restype = C.c_int
+            fn.restype = C.c_size_t if name.endswith("_workspace") else C.c_int
             fn.argtypes = args
         _lib = L
     return _lib

@@ -1,0 +1,259 @@
+// tcgen05 weight gradient of the 3x1 / 1x3 (dilated) convolutions (autograd of eval/erfnet.py:30-38):
+//
+//   dW[t][ci][co] = sum over all pixels p of  x[p + (t-1)*dil along H or W][ci] * dy[p][co]          t = 0..2
+//
+// i.e. three GEMMs with M = ci, N = co and a reduction dimension K = N*H*W pixels.  NHWC tiles are "MN-major" for this
+// product (channels contiguous, pixels = K), which tcgen05 consumes directly: both operands use the MN-major 128B-swizzled
+// canonical layout -- a K row is one 128-byte pixel line of 64 channels, 8 pixels form a swizzle atom (SBO = 1024 B),
+// and the second 64-element M/N atom sits LBO bytes away.  LBO is what makes the taps cheap:
+//   C = 128: the two atoms are the two 64-channel halves of a pixel tile (LBO = half-tile pitch), one accumulator per tap
+//   C =  64: the two M atoms are TWO TAPS of the same tile (LBO = tap pitch: d pixel rows, or the next row's tile), so one
+//            M=128 MMA produces dW[t] and dW[t+1] at full tensor-core rate; taps (0,1) and (1,2) give two accumulators.
+// Each persistent CTA walks 64-pixel units (TMA-staged x and dy tiles, out-of-image pixels zero-filled) accumulating in TMEM
+// across ALL its units, dumps its partial sums once to a workspace, and a second kernel reduces the per-CTA partials.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace erfk {
+using namespace tc;
+
+struct WgradTcParams {
+  float* ws;      // [grid][ACCS][128][C] per-CTA partial sums
+  int N, H, W;
+  int horizontal, dil;
+  int units;      // N * H * (W / 64)
+  int stages, stage_bytes;
+  int x_sub_bytes;   // pitch of one (tap, k-chunk) x sub-tile (vertical) / one k-chunk sub-tile (horizontal)
+  int dy_off;        // offset of the dy tile inside a stage
+};
+
+constexpr int kWgStages = 4;
+constexpr int PX = 64;  // pixels (K) per unit
+
+template <int C>
+__global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                                                                 const WgradTcParams p) {
+  constexpr int KC = C / 64;
+  constexpr int ACCS = C == 128 ? 3 : 2;
+  constexpr int TMEM_COLS = C == 128 ? 512 : 128;
+  // both operands MN-major (bits 15, 16), M = 128, N = C
+  constexpr uint32_t IDESC = make_idesc_bf16(128, C) | (1u << 15) | (1u << 16);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[kWgStages], empty_bar[kWgStages], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  __syncthreads();
+  if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int segs = p.W / PX;
+  const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (p.horizontal ? (uint32_t)(KC * (PX + 2 * p.dil) * 128) : (uint32_t)(3 * KC * PX * 128)) + (uint32_t)(KC * PX * 128);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], tx);
+        uint8_t* base = smem + (size_t)stage * p.stage_bytes;
+        if (p.horizontal) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * 64, xs * PX - p.dil, y, n);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc)
+              tma_load_4d(base + (t * KC + kc) * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * 64, xs * PX, y + (t - 1) * p.dil, n);
+        }
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + p.dy_off + kc * (PX * 128), &tmap_dy, &full_bar[stage], kc * 64, xs * PX, y, n);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t hi_base = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);  // SBO = 1024 (8 pixel rows), version 1, SW128
+      const uint32_t tap_pitch = p.horizontal ? (uint32_t)p.dil * 128u : (uint32_t)KC * p.x_sub_bytes;
+      // M-atom pitch of the x operand: the other 64-channel half (C=128) or the next tap (C=64)
+      const uint32_t lbo_x = C == 128 ? (uint32_t)p.x_sub_bytes : tap_pitch;
+      const uint32_t lbo_dy = PX * 128;  // N-atom pitch of dy (only used when C == 128)
+      bool first = true;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t x_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t dy_addr = x_addr + p.dy_off;
+#pragma unroll
+        for (int a = 0; a < ACCS; ++a) {
+          // C=128: accumulator a = tap a.  C=64: accumulator 0 = taps (0,1), accumulator 1 = taps (1,2).
+          const uint32_t xa = x_addr + a * tap_pitch;
+          const uint32_t x_lo = ((xa >> 4) & 0x3FFF) | (((lbo_x >> 4) & 0x3FFF) << 16);
+          const uint32_t dy_lo = ((dy_addr >> 4) & 0x3FFF) | (((lbo_dy >> 4) & 0x3FFF) << 16);
+#pragma unroll
+          for (int k = 0; k < PX / 16; ++k) {
+            // advancing K by 16 pixels = 16 rows of 128 B = 2048 B
+            const uint64_t da = ((uint64_t)hi_base << 32) | (uint64_t)(x_lo + k * 128);
+            const uint64_t db = ((uint64_t)hi_base << 32) | (uint64_t)(dy_lo + k * 128);
+            umma_bf16(tmem_base + a * C, da, db, IDESC, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    // epilogue (once): dump the accumulators of this CTA
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* wsb = p.ws + (size_t)blockIdx.x * ACCS * 128 * C;
+    if (my_units > 0) {
+      mbar_wait(&done_bar, 0);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int a = 0; a < ACCS; ++a) {
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(wsb + ((size_t)a * 128 + row) * C + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        }
+      }
+    } else {
+      for (int a = 0; a < ACCS; ++a)
+        for (int c = 0; c < C; ++c) wsb[((size_t)a * 128 + row) * C + c] = 0.f;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// dw[t][ci][co] (+)= sum over CTAs of the partial accumulators
+template <int C>
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
+  constexpr int ACCS = C == 128 ? 3 : 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*C*C
+  if (i >= 3 * C * C) return;
+  int co = i % C, ci = (i / C) % C, t = i / (C * C);
+  int acc, row;
+  if (C == 128) { acc = t; row = ci; }
+  else { acc = t == 2 ? 1 : 0; row = (t == 0 ? 0 : 64) + ci; }
+  const float* src = ws + ((size_t)acc * 128 + row) * C + co;
+  float s = 0.f;
+  for (int b = 0; b < grid_ctas; ++b) s += src[(size_t)b * ACCS * 128 * C];
+  dw[i] += s;
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int box_w) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn2)q;
+  }
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+
+extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) { return (size_t)148 * (C == 128 ? 3 : 2) * 128 * C * sizeof(float); }
+
+extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W, int C,
+                                   int horizontal, int dil, erf_stream_t stream) {
+  ERF_CHECK_ARG(x && dy && dw && workspace, "erf_conv1d_wgrad_tc: null pointer");
+  ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_wgrad_tc: empty tensor");
+  if (!((C == 64 || C == 128) && W >= 64 && (W % 64) == 0 && dil >= 1 && dil <= 32)) {
+    set_error("erf_conv1d_wgrad_tc: unsupported shape C=%d W=%d dil=%d", C, W, dil);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  ERF_CHECK_ARG(ws_bytes >= erf_conv1d_wgrad_tc_workspace(C), "erf_conv1d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes,
+                erf_conv1d_wgrad_tc_workspace(C));
+  const int KC = C / 64;
+  const int box_w = horizontal ? PX + 2 * dil : PX;
+  CUtensorMap mx, mdy;
+  if (make_map(&mx, x, N, H, W, C, box_w) != 0 || make_map(&mdy, dy, N, H, W, C, PX) != 0) {
+    set_error("erf_conv1d_wgrad_tc: cuTensorMapEncodeTiled failed");
+    return ERF_ERR_CUDA;
+  }
+  WgradTcParams p;
+  p.ws = (float*)workspace;
+  p.N = N; p.H = H; p.W = W; p.horizontal = horizontal; p.dil = dil;
+  p.units = N * H * (W / PX);
+  int x_bytes;
+  if (horizontal) {
+    p.x_sub_bytes = ((box_w + 7) / 8) * 8 * 128;
+    x_bytes = KC * p.x_sub_bytes;
+  } else {
+    p.x_sub_bytes = PX * 128;
+    x_bytes = 3 * KC * p.x_sub_bytes;
+  }
+  p.dy_off = x_bytes;
+  p.stage_bytes = x_bytes + KC * PX * 128;
+  p.stages = (220 * 1024) / p.stage_bytes;
+  if (p.stages > kWgStages) p.stages = kWgStages;
+  size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  int grid = p.units < 148 ? p.units : 148;
+  cudaError_t e;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C == 64) {
+    e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      conv1d_wgrad_tc_kernel<64><<<grid, 192, smem, s>>>(mx, mdy, p);
+      wgrad_reduce_kernel<64><<<(3 * 64 * 64 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+    }
+  } else {
+    e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      conv1d_wgrad_tc_kernel<128><<<grid, 192, smem, s>>>(mx, mdy, p);
+      wgrad_reduce_kernel<128><<<(3 * 128 * 128 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+    }
+  }
+  if (e != cudaSuccess) {
+    set_error("erf_conv1d_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return ERF_ERR_CUDA;
+  }
+  ERF_CHECK_LAUNCH("erf_conv1d_wgrad_tc");
+  return ERF_OK;
+}

@@ -312,3 +312,20 @@ extern "C" int erf_conv_wgrad(const void* in, const void* dout, float* dw, float
   }
   return ERF_OK;
 }
+
+extern "C" int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream) {
+  ERF_CHECK_ARG(x && out && n_px > 0 && C > 0 && C <= 256 && ld >= coff + C, "erf_channel_sum: bad arguments");
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_channel_sum: bad dtype %d", dtype);
+  long long cb = 148 * 4;
+  long long cppb = (n_px + cb - 1) / cb;
+  if (cppb < 256) cppb = 256;
+  unsigned cgrid = (unsigned)((n_px + cppb - 1) / cppb);
+  size_t smem = C * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == ERF_F32)
+    channel_sum_kernel<float><<<cgrid, 256, smem, s>>>((const float*)x, ld, coff, C, n_px, (int)cppb, out);
+  else
+    channel_sum_kernel<__nv_bfloat16><<<cgrid, 256, smem, s>>>((const __nv_bfloat16*)x, ld, coff, C, n_px, (int)cppb, out);
+  ERF_CHECK_LAUNCH("erf_channel_sum");
+  return ERF_OK;
+}

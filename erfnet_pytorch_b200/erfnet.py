@@ -335,20 +335,25 @@ class non_bottleneck_1d(_B200Module):
         else:
             wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, self.bn2.weight.detach(), mean2, invstd2, mask=out, drop=drop)
-        dw4, db4 = ops.conv_wgrad(t3, dy4, s[3])
+        dw4, db4 = self._wgrad(3, t3, dy4, tc)
         dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3])
-        dw3, db3 = ops.conv_wgrad(a2, dt3, s[2])
+        dw3, db3 = self._wgrad(2, a2, dt3, tc)
         da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2])
         dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, self.bn1.weight.detach(), mean1, invstd1, mask=a2)
-        dw2, db2 = ops.conv_wgrad(t1, dy2, s[1])
+        dw2, db2 = self._wgrad(1, t1, dy2, tc)
         dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1])
-        dw1, db1 = ops.conv_wgrad(x, dt1, s[0])
+        dw1, db1 = self._wgrad(0, x, dt1, tc)
         dx = None
         if need_dx:
             gres = ops.relu_bwd(dout, out)
             dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
-        u = ops.unpack_wgrad
-        return dx, (u(dw1, s[0]), db1, u(dw2, s[1]), db2, dg1, dbe1, u(dw3, s[2]), db3, u(dw4, s[3]), db4, dg2, dbe2)
+        return dx, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)
+
+    def _wgrad(self, i, x, dy, tc):
+        if tc and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype):
+            return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated)
+        dwp, db = ops.conv_wgrad(x, dy, self.specs[i])
+        return ops.unpack_wgrad(dwp, self.specs[i]), db
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -213,6 +213,35 @@ def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+_WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partial sums
+
+
+def conv1d_wgrad_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
+    return dtype == torch.bfloat16 and not EMULATED and c in (64, 128) and w % 64 == 0 and 1 <= dil <= 32
+
+
+def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, want_bias=True):
+    """Weight (torch layout [Co,Ci,3,1] / [Co,Ci,1,3], fp32) and bias gradients of a 3-tap conv on the tensor cores."""
+    n, h, w, c = x.shape
+    L = _lib.lib()
+    nbytes = L.erf_conv1d_wgrad_tc_workspace(c)
+    ws = _WS.get((x.device, nbytes))
+    if ws is None:
+        ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    dw = torch.zeros(3, c, c, device=x.device, dtype=torch.float32)
+    with _timed("conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
+        check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
+    _count(2)
+    db = None
+    if want_bias:
+        db = torch.zeros(c, device=x.device, dtype=torch.float32)
+        with _timed("channel_sum"):
+            check(L.erf_channel_sum(_p(dy), c, 0, c, n * h * w, _p(db), dt(dy), _stream(dy)))
+        _count()
+    dwt = dw.permute(2, 1, 0)  # [co][ci][t]
+    return (dwt.reshape(c, c, 1, 3) if horizontal else dwt.reshape(c, c, 3, 1)).contiguous(), db
+
+
 def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
     n, h, w, ld = x.shape
     check(_lib.lib().erf_maxpool2x2_fwd(_p(x), n, h, w, c, ld, _p(out), out.shape[-1], out_coff, _p(scale), _p(shift), int(relu),

@@ -158,6 +158,15 @@ int erf_conv1d_tc_supported(int C, int W, int dil);
 int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask,
                   int N, int H, int W, int C, int horizontal, int dil, int relu, erf_stream_t stream);
 
+/* tcgen05 weight gradient of the same convolutions: dw[t][ci][co] += sum_p x[p + (t-1)*dil][ci] * dy[p][co]  (fp32,
+ * [3][C][C]; caller zeroes).  Both NHWC operands are consumed MN-major; per-CTA TMEM accumulators are dumped to
+ * `workspace` (>= erf_conv1d_wgrad_tc_workspace(C) bytes, caller-owned) and reduced by a second kernel.  W % 64 == 0. */
+size_t erf_conv1d_wgrad_tc_workspace(int C);
+int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W,
+                        int C, int horizontal, int dil, erf_stream_t stream);
+/* out[c] += sum_p x[p*ld + coff + c]   (bias gradients) */
+int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream);
+
 /* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
 /* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
  * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle

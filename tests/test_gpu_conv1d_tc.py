@@ -123,3 +123,21 @@ def test_block_train_fwd_bwd_on_tensor_cores(c, d, hw):
     assert_rel(runs[True]["rv2"], ref["rv2"], 2e-2, "running_var2")
     for k in ("dx", "dw4", "dw1", "dg1"):
         assert l2(runs[True][k], ref[k]) < 0.2, (k, l2(runs[True][k], ref[k]))
+
+
+@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 64), (128, 192)])
+@pytest.mark.parametrize("horizontal", [False, True])
+@pytest.mark.parametrize("dil", [1, 2, 16])
+def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
+    gen = torch.Generator().manual_seed(c * 3 + w + dil)
+    n, h = 3, 37
+    x = torch.randn(n, h, w, c, generator=gen).bfloat16()
+    dy = torch.randn(n, h, w, c, generator=gen).bfloat16()
+    wt = torch.zeros(c, c, *((1, 3) if horizontal else (3, 1)), requires_grad=True)
+    pad, dl = ((0, dil), (1, dil)) if horizontal else ((dil, 0), (dil, 1))
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=pad, dilation=dl)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    dw, db = ops.conv1d_wgrad_tc(x.cuda(), dy.cuda(), horizontal, dil)
+    assert dw.shape == wt.shape
+    assert_rel(dw.cpu().numpy(), ref.numpy(), 2e-3, "dW")
+    assert_rel(db.cpu().numpy(), dy.float().sum((0, 1, 2)).numpy(), 2e-3, "db")
