@@ -46,6 +46,7 @@ _SIGNATURES = {
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_pack_conv1d_tc": [_vp, _i, _vp, _vp, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],

@@ -211,7 +211,7 @@ __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, con
   shift[c] = beta[c] - rm[c] * sc;
 }
 
-// gb = g * (mask > 0) * drop[n,c]; block-partial sums of gb and gb*xhat
+// gb = g * (mask > 0) * drop[n,c]; block-partial sums of gb and gb*xhat.  8 channels per thread (16-byte loads).
 template <typename T>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, int g_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ mask,
                                      int mask_ld, const float* __restrict__ drop, const float* __restrict__ mean,
@@ -220,23 +220,32 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, int g_ld, const T*
   extern __shared__ float s[];  // [2*C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s[i] = 0.f;
   __syncthreads();
-  const int lanes = blockDim.x / C;
-  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  const int c8 = C / 8;
+  const int lanes = blockDim.x / c8;
+  const int c0 = (threadIdx.x % c8) * 8, lane = threadIdx.x / c8;
   long long p0 = (long long)blockIdx.x * px_per_block, p1 = p0 + px_per_block;
   if (p1 > n_px) p1 = n_px;
   if (lane < lanes) {
-    float a = 0.f, b = 0.f;
-    const float mu = mean[c], is = invstd[c];
+    float a[8], b[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = b[k] = 0.f; mu[k] = mean[c0 + k]; is[k] = invstd[c0 + k]; }
     for (long long p = p0 + lane; p < p1; p += lanes) {
-      float gv = to_f(g[(size_t)p * g_ld + c]);
-      if (mask && !(to_f(mask[(size_t)p * mask_ld + c]) > 0.f)) gv = 0.f;
-      if (drop) gv *= drop[(p / HW) * C + c];
-      float xh = (to_f(y[(size_t)p * y_ld + c]) - mu) * is;
-      a += gv;
-      b += gv * xh;
+      Vec<T, 8> gv, yv, mv;
+      gv.load(g + (size_t)p * g_ld + c0);
+      yv.load(y + (size_t)p * y_ld + c0);
+      if (mask) mv.load(mask + (size_t)p * mask_ld + c0);
+      const float* dp = drop ? drop + (p / HW) * C + c0 : nullptr;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float gg = gv.v[k];
+        if (mask && !(mv.v[k] > 0.f)) gg = 0.f;
+        if (dp) gg *= dp[k];
+        a[k] += gg;
+        b[k] += gg * (yv.v[k] - mu[k]) * is[k];
+      }
     }
-    atomicAdd(&s[c], a);
-    atomicAdd(&s[C + c], b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s[c0 + k], a[k]); atomicAdd(&s[C + c0 + k], b[k]); }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)s[i]);
@@ -247,22 +256,51 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* 
                                     int mask_ld, const float* __restrict__ drop, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
                                     long long HW, int C, long long n_px, T* __restrict__ dy, int dy_ld, float* dgamma, float* dbeta) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (pixel, 8-channel group)
   if (i < C) {
     if (dbeta) dbeta[i] = (float)sums[i];
     if (dgamma) dgamma[i] = (float)sums[C + i];
   }
-  if (i >= n_px * C) return;
-  int c = (int)(i % C);
-  long long p = i / C;
-  float gv = to_f(g[(size_t)p * g_ld + c]);
-  if (mask && !(to_f(mask[(size_t)p * mask_ld + c]) > 0.f)) gv = 0.f;
-  if (drop) gv *= drop[(p / HW) * C + c];
-  const float is = invstd[c];
-  float xh = (to_f(y[(size_t)p * y_ld + c]) - mean[c]) * is;
+  const int c8 = C / 8;
+  if (i >= n_px * c8) return;
+  const int c0 = (int)(i % c8) * 8;
+  const long long p = i / c8;
+  Vec<T, 8> gv, yv, mv;
+  gv.load(g + (size_t)p * g_ld + c0);
+  yv.load(y + (size_t)p * y_ld + c0);
+  if (mask) mv.load(mask + (size_t)p * mask_ld + c0);
+  const float* dp = drop ? drop + (p / HW) * C + c0 : nullptr;
   const float inv_m = 1.f / (float)n_px;
-  float m1 = (float)sums[c] * inv_m, m2 = (float)sums[C + c] * inv_m;
-  dy[(size_t)p * dy_ld + c] = from_f<T>(gamma[c] * is * (gv - m1 - xh * m2));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float gg = gv.v[k];
+    if (mask && !(mv.v[k] > 0.f)) gg = 0.f;
+    if (dp) gg *= dp[k];
+    const float is = invstd[c0 + k];
+    const float xh = (yv.v[k] - mean[c0 + k]) * is;
+    gv.v[k] = gamma[c0 + k] * is * (gg - (float)sums[c0 + k] * inv_m - xh * (float)sums[C + c0 + k] * inv_m);
+  }
+  gv.store(dy + (size_t)p * dy_ld + c0);
+}
+
+// tcgen05 operand images of a 3-tap conv weight w[Co][Ci][3] (fp32): forward Wt[t][n=co][k=ci] and data-gradient
+// Wt'[t][n=ci][k=co] = w[co][ci][2-t]; layout [3][C/64][C][8 chunks of 8], chunk index XOR-swizzled by (n & 7).
+__global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_bfloat16* __restrict__ img_fwd, __nv_bfloat16* __restrict__ img_dgrad) {
+  const int kc_n = C / 64;
+  const int total = 3 * kc_n * C * 8;  // 16-byte chunks per image
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * total) return;
+  const bool dgrad = i >= total;
+  if (dgrad) i -= total;
+  const int jj = i & 7, n = (i >> 3) % C, kc = (i / (8 * C)) % kc_n, t = i / (8 * C * kc_n);
+  const int j = jj ^ (n & 7);
+  Vec<__nv_bfloat16, 8> v;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kc * 64 + j * 8 + e;
+    v.v[e] = dgrad ? w[((size_t)k * C + n) * 3 + (2 - t)] : w[((size_t)n * C + k) * 3 + t];
+  }
+  v.store((dgrad ? img_dgrad : img_fwd) + (size_t)i * 8);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -410,7 +448,9 @@ extern "C" int erf_bn_eval_affine(const float* gamma, const float* beta, const f
 extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* drop,
                                  const float* mean, const float* invstd, int N, int HW, int C, double* sums, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_bn_bwd_reduce");
-  ERF_CHECK_ARG(g && y && mean && invstd && sums && N > 0 && HW > 0 && C > 0 && C <= 256, "erf_bn_bwd_reduce: bad arguments");
+  ERF_CHECK_ARG(g && y && mean && invstd && sums && N > 0 && HW > 0 && C >= 8 && (C % 8) == 0 && C <= 2048 && (g_ld % 8) == 0 && (y_ld % 8) == 0 &&
+                    (!mask || (mask_ld % 8) == 0),
+                "erf_bn_bwd_reduce: C and leading dimensions must be multiples of 8");
   long long n_px = (long long)N * HW;
   long long want = 148 * 8;
   long long ppb = (n_px + want - 1) / want;
@@ -429,9 +469,13 @@ extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld
                                 const float* gamma, const float* mean, const float* invstd, const double* sums, int N, int HW, int C, void* dy,
                                 int dy_ld, float* dgamma, float* dbeta, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_bn_bwd_apply");
-  ERF_CHECK_ARG(g && y && gamma && mean && invstd && sums && dy && N > 0 && HW > 0 && C > 0, "erf_bn_bwd_apply: bad arguments");
+  ERF_CHECK_ARG(g && y && gamma && mean && invstd && sums && dy && N > 0 && HW > 0 && C >= 8 && (C % 8) == 0 && (g_ld % 8) == 0 && (y_ld % 8) == 0 &&
+                    (dy_ld % 8) == 0 && (!mask || (mask_ld % 8) == 0),
+                "erf_bn_bwd_apply: C and leading dimensions must be multiples of 8");
   long long n_px = (long long)N * HW;
-  unsigned grid = (unsigned)((n_px * C + 255) / 256);
+  long long work = n_px * (C / 8);
+  if (work < C) work = C;
+  unsigned grid = (unsigned)((work + 255) / 256);
   if (dtype == ERF_F32)
     bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (float*)dy, dy_ld, dgamma, dbeta);
   else
@@ -447,5 +491,13 @@ extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long 
   unsigned grid = (unsigned)((n + 255) / 256);
   adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale);
   ERF_CHECK_LAUNCH("erf_adam_step");
+  return ERF_OK;
+}
+
+extern "C" int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream) {
+  ERF_CHECK_ARG(w && img_fwd && img_dgrad && (C == 64 || C == 128), "erf_pack_conv1d_tc: bad arguments (C=%d)", C);
+  int total = 2 * 3 * (C / 64) * C * 8;
+  pack_conv1d_tc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, C, (__nv_bfloat16*)img_fwd, (__nv_bfloat16*)img_dgrad);
+  ERF_CHECK_LAUNCH("erf_pack_conv1d_tc");
   return ERF_OK;
 }

@@ -51,7 +51,7 @@ class _BlockFn(torch.autograd.Function):
     def forward(ctx, block, bctx, x, *params):
         y, saved = block._fwd_train(x.detach(), bctx)
         # detached aliases: keeping `y` itself would create a node -> y -> grad_fn(node) reference cycle
-        ctx.block, ctx.saved = block, tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in saved)
+        ctx.block, ctx.saved = block, tuple(t.detach() if isinstance(t, torch.Tensor) and t.requires_grad else t for t in saved)
         return y
 
     @staticmethod
@@ -303,8 +303,10 @@ class non_bottleneck_1d(_B200Module):
         cv = self._convs()
         tc = self._use_tc(x)
         if tc:
-            wp = [ops.pack_conv1d_tc(m.weight.detach()) for m in cv]
+            pairs = [ops.pack_conv1d_tc_pair(m.weight) for m in cv]  # forward + data-gradient images, one launch per conv
+            wp = [pr[0] for pr in pairs]
         else:
+            pairs = None
             wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         bs = [m.bias.detach().float() for m in cv]
         count = n * h * w
@@ -322,16 +324,16 @@ class non_bottleneck_1d(_B200Module):
                                                    self.bn2.running_var, BN_MOMENTUM, BN_EPS, drop=drop)
         self.bn2.num_batches_tracked += 1
         out = ops.affine_act(y4, sc2, sh2, res=x, relu=True)
-        return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop)
+        return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, pairs)
 
     def _bwd(self, dout, saved, need_dx):
-        x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop = saved
+        x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, pairs = saved
         s, dtp = self.specs, x.dtype
         cv = self._convs()
         tc = self._use_tc(x)
         ds = [ops.dgrad_spec(sp) for sp in s]
         if tc:
-            wd = [ops.pack_conv1d_tc(m.weight.detach(), dgrad=True) for m in cv]
+            wd = [pr[1] for pr in pairs] if pairs is not None else [ops.pack_conv1d_tc(m.weight.detach(), dgrad=True) for m in cv]
         else:
             wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, self.bn2.weight.detach(), mean2, invstd2, mask=out, drop=drop)

@@ -12,6 +12,7 @@ import torch
 from . import _lib
 from ._lib import ERF_BF16, ERF_F32, ConvEpilogue, ConvGeom, check
 
+DETAIL = False    # tools/profile_step.py: per-shape kernel names in the timing table
 USE_TC = True     # tests flip this to compare the tcgen05 kernels with the generic CUDA-core path
 EMULATED = False  # set by tests/emu.py only (CPU emulation of the kernel contracts for host-logic tests)
 LAUNCHES = 0  # number of kernel-launching library calls made by this process (bench.py reports it)
@@ -165,7 +166,8 @@ def conv_fwd(x: torch.Tensor, wp: torch.Tensor, spec: ConvSpec, bias: Optional[t
     g = _geom(spec, x, out, out_coff)
     e = ConvEpilogue(_p(bias), int(relu), _p(mask), 0 if mask is None else mask.shape[-1], _p(add), 0 if add is None else add.shape[-1],
                      _p(stats), 0 if stats is None else stats.numel() // 2)
-    with _timed("conv_gather_kernel", conv_flops(spec, n, out.shape[1], out.shape[2])):
+    with _timed(f"conv_gather_kernel[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_gather_kernel",
+                conv_flops(spec, n, out.shape[1], out.shape[2])):
         check(_lib.lib().erf_conv_fwd(_p(x), _p(wp), _p(out), C.byref(g), C.byref(e), dt(x), _stream(x)))
     _count()
     return out
@@ -176,7 +178,8 @@ def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0,
     dw = torch.zeros(spec.kh * spec.kw * spec.cin_p, spec.w_ld, device=x.device, dtype=torch.float32)
     db = torch.zeros(spec.cout, device=x.device, dtype=torch.float32) if want_bias else None
     g = _geom(spec, x, dout, dout_coff)
-    with _timed("conv_wgrad_kernel", conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
+    with _timed(f"conv_wgrad_kernel[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_kernel",
+                conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
         check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
     _count(2 if want_bias else 1)
     return dw, db
@@ -200,6 +203,16 @@ def pack_conv1d_tc(w: torch.Tensor, dgrad: bool = False) -> torch.Tensor:
     perm = torch.arange(8, device=w.device)[None, :] ^ (n[:, None] & 7)  # [n][jj] -> source chunk
     idx = perm[None, None, :, :, None].expand(3, c // 64, c, 8, 8)
     return img.gather(3, idx).contiguous().to(torch.bfloat16)
+
+
+def pack_conv1d_tc_pair(w: torch.Tensor):
+    """(forward image, data-gradient image) of a Conv2d weight [C,C,3,1]/[C,C,1,3] in one kernel launch."""
+    c = w.shape[0]
+    w = w.detach().contiguous().float()
+    imgs = torch.empty(2, 3 * c * c, device=w.device, dtype=torch.bfloat16)
+    check(_lib.lib().erf_pack_conv1d_tc(_p(w), c, _p(imgs[0]), _p(imgs[1]), _stream(w)))
+    _count()
+    return imgs[0], imgs[1]
 
 
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
@@ -377,6 +390,8 @@ def confusion_hist(pred: torch.Tensor, gt: torch.Tensor, nc: int, cm: torch.Tens
         raise RuntimeError("iouEval: predictions and labels must both be uint8 or both int64")
     if pred.numel() != gt.numel():
         raise RuntimeError(f"iouEval: size mismatch {tuple(pred.shape)} vs {tuple(gt.shape)}")
+    if pred.numel() == 0:
+        return
     pred, gt = pred.contiguous(), gt.contiguous()
     check(_lib.lib().erf_confusion_hist(_p(pred), _p(gt), pred.element_size(), pred.numel(), nc, _p(cm), _stream(pred)))
     _count()
@@ -430,5 +445,5 @@ def _wrap_timed(name):
 
 for _n in ("channel_stats", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
            "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
-           "unpack_wgrad", "pack_conv1d_tc"):
+           "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair"):
     _wrap_timed(_n)

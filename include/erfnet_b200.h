@@ -158,6 +158,10 @@ int erf_conv1d_tc_supported(int C, int W, int dil);
 int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask,
                   int N, int H, int W, int C, int horizontal, int dil, int relu, erf_stream_t stream);
 
+/* Build both operand images (forward and data-gradient) of a 3-tap conv weight w[Co][Ci][3] fp32 (= nn.Conv2d weight
+ * [Co,Ci,3,1] or [Co,Ci,1,3], contiguous) for erf_conv1d_tc; each image is 3*C*C bf16. */
+int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream);
+
 /* tcgen05 weight gradient of the same convolutions: dw[t][ci][co] += sum_p x[p + (t-1)*dil][ci] * dy[p][co]  (fp32,
  * [3][C][C]; caller zeroes).  Both NHWC operands are consumed MN-major; per-CTA TMEM accumulators are dumped to
  * `workspace` (>= erf_conv1d_wgrad_tc_workspace(C) bytes, caller-owned) and reduced by a second kernel.  W % 64 == 0. */

@@ -141,3 +141,11 @@ def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
     assert dw.shape == wt.shape
     assert_rel(dw.cpu().numpy(), ref.numpy(), 2e-3, "dW")
     assert_rel(db.cpu().numpy(), dy.float().sum((0, 1, 2)).numpy(), 2e-3, "db")
+
+
+def test_pack_kernel_matches_host_packing():
+    for c, shape in ((64, (64, 64, 3, 1)), (128, (128, 128, 1, 3))):
+        w = torch.randn(*shape, generator=torch.Generator().manual_seed(c)).cuda()
+        f, d = ops.pack_conv1d_tc_pair(w)
+        assert torch.equal(f.view(-1), ops.pack_conv1d_tc(w).view(-1))
+        assert torch.equal(d.view(-1), ops.pack_conv1d_tc(w, dgrad=True).view(-1))

@@ -12,6 +12,7 @@ from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
 from oracle import erfnet_oracle as O  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+ops.DETAIL = True
 model = E.ERFNet(NC)
 model.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), 0))
 model = model.cuda()
