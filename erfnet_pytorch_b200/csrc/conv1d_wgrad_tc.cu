@@ -29,15 +29,20 @@ struct WgradTcParams {
   int dy_off;        // offset of the dy tile inside a stage
 };
 
-constexpr int kWgStages = 4;
+constexpr int kWgStages = 8;
 constexpr int PX = 64;  // pixels (K) per unit
 
 template <int C>
 __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                                                                  const WgradTcParams p) {
-  constexpr int KC = C / 64;
-  constexpr int ACCS = C == 128 ? 3 : 2;
-  constexpr int TMEM_COLS = C == 128 ? 512 : 128;
+  constexpr int CH = C < 64 ? C : 64;      // channels per chunk = one swizzle row of RB bytes
+  constexpr int RB = CH * 2;
+  constexpr int KC = C / CH;
+  constexpr uint32_t LAYOUT = RB == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
+  // C=128: one accumulator per tap (M atoms = channel halves); C=64: accumulators (taps 0,1), (taps 1,2) (M atoms = taps);
+  // C=16: one accumulator, the eight 16-channel M atoms are taps 0,1,2 and five ignored garbage atoms
+  constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
+  constexpr int TMEM_COLS = C == 128 ? 512 : (C == 64 ? 128 : 32);
   // both operands MN-major (bits 15, 16), M = 128, N = C
   constexpr uint32_t IDESC = make_idesc_bf16(128, C) | (1u << 15) | (1u << 16);
   extern __shared__ uint8_t smem_raw[];
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (p.horizontal ? (uint32_t)(KC * (PX + 2 * p.dil) * 128) : (uint32_t)(3 * KC * PX * 128)) + (uint32_t)(KC * PX * 128);
+      const uint32_t tx = (p.horizontal ? (uint32_t)(KC * (PX + 2 * p.dil) * RB) : (uint32_t)(3 * KC * PX * RB)) + (uint32_t)(KC * PX * RB);
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -76,16 +81,16 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
         uint8_t* base = smem + (size_t)stage * p.stage_bytes;
         if (p.horizontal) {
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * 64, xs * PX - p.dil, y, n);
+          for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * CH, xs * PX - p.dil, y, n);
         } else {
 #pragma unroll
           for (int t = 0; t < 3; ++t)
 #pragma unroll
             for (int kc = 0; kc < KC; ++kc)
-              tma_load_4d(base + (t * KC + kc) * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * 64, xs * PX, y + (t - 1) * p.dil, n);
+              tma_load_4d(base + (t * KC + kc) * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * CH, xs * PX, y + (t - 1) * p.dil, n);
         }
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + p.dy_off + kc * (PX * 128), &tmap_dy, &full_bar[stage], kc * 64, xs * PX, y, n);
+        for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + p.dy_off + kc * (PX * RB), &tmap_dy, &full_bar[stage], kc * CH, xs * PX, y, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -93,11 +98,11 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t hi_base = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);  // SBO = 1024 (8 pixel rows), version 1, SW128
-      const uint32_t tap_pitch = p.horizontal ? (uint32_t)p.dil * 128u : (uint32_t)KC * p.x_sub_bytes;
+      const uint32_t hi_base = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);  // SBO = 8 pixel rows, version 1, swizzle mode
+      const uint32_t tap_pitch = p.horizontal ? (uint32_t)p.dil * RB : (uint32_t)KC * p.x_sub_bytes;
       // M-atom pitch of the x operand: the other 64-channel half (C=128) or the next tap (C=64)
       const uint32_t lbo_x = C == 128 ? (uint32_t)p.x_sub_bytes : tap_pitch;
-      const uint32_t lbo_dy = PX * 128;  // N-atom pitch of dy (only used when C == 128)
+      const uint32_t lbo_dy = PX * RB;  // N-atom pitch of dy (only used when C == 128)
       bool first = true;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         mbar_wait(&full_bar[stage], phase);
@@ -112,9 +117,9 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
           const uint32_t dy_lo = ((dy_addr >> 4) & 0x3FFF) | (((lbo_dy >> 4) & 0x3FFF) << 16);
 #pragma unroll
           for (int k = 0; k < PX / 16; ++k) {
-            // advancing K by 16 pixels = 16 rows of 128 B = 2048 B
-            const uint64_t da = ((uint64_t)hi_base << 32) | (uint64_t)(x_lo + k * 128);
-            const uint64_t db = ((uint64_t)hi_base << 32) | (uint64_t)(dy_lo + k * 128);
+            // advancing K by 16 pixels = 16 rows of RB bytes
+            const uint64_t da = ((uint64_t)hi_base << 32) | (uint64_t)(x_lo + k * RB);
+            const uint64_t db = ((uint64_t)hi_base << 32) | (uint64_t)(dy_lo + k * RB);
             umma_bf16(tmem_base + a * C, da, db, IDESC, (first && k == 0) ? 0u : 1u);
           }
         }
@@ -134,14 +139,16 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
       tcgen05_fence_after();
 #pragma unroll
       for (int a = 0; a < ACCS; ++a) {
+        constexpr int EW = C >= 32 ? 32 : 16;
 #pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
+        for (int c0 = 0; c0 < C; c0 += EW) {
+          uint32_t r[EW];
+          if (EW == 32) tmem_ld32(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
+          else tmem_ld16(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
           tmem_ld_wait();
           float4* dst = reinterpret_cast<float4*>(wsb + ((size_t)a * 128 + row) * C + c0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < EW / 4; ++q)
             dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         }
       }
@@ -161,13 +168,14 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
 // dw[t][ci][co] (+)= sum over CTAs of the partial accumulators
 template <int C>
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
-  constexpr int ACCS = C == 128 ? 3 : 2;
+  constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*C*C
   if (i >= 3 * C * C) return;
   int co = i % C, ci = (i / C) % C, t = i / (C * C);
   int acc, row;
   if (C == 128) { acc = t; row = ci; }
-  else { acc = t == 2 ? 1 : 0; row = (t == 0 ? 0 : 64) + ci; }
+  else if (C == 64) { acc = t == 2 ? 1 : 0; row = (t == 0 ? 0 : 64) + ci; }
+  else { acc = 0; row = t * 16 + ci; }
   const float* src = ws + ((size_t)acc * 128 + row) * C + co;
   float s = 0.f;
   for (int b = 0; b < grid_ctas; ++b) s += src[(size_t)b * ACCS * 128 * C];
@@ -188,29 +196,30 @@ static int make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C,
   if (!fn) return -1;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(C < 64 ? C : 64), (cuuint32_t)box_w, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                 C < 64 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace erfk
 
 using namespace erfk;
 
-extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) { return (size_t)148 * (C == 128 ? 3 : 2) * 128 * C * sizeof(float); }
+extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) { return (size_t)148 * (C == 128 ? 3 : (C == 64 ? 2 : 1)) * 128 * C * sizeof(float); }
 
 extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W, int C,
                                    int horizontal, int dil, erf_stream_t stream) {
   ERF_CHECK_ARG(x && dy && dw && workspace, "erf_conv1d_wgrad_tc: null pointer");
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_wgrad_tc: empty tensor");
-  if (!((C == 64 || C == 128) && W >= 64 && (W % 64) == 0 && dil >= 1 && dil <= 32)) {
+  if (!((C == 16 || C == 64 || C == 128) && W >= 64 && (W % 64) == 0 && dil >= 1 && dil <= 32)) {
     set_error("erf_conv1d_wgrad_tc: unsupported shape C=%d W=%d dil=%d", C, W, dil);
     return ERF_ERR_UNSUPPORTED;
   }
   ERF_CHECK_ARG(ws_bytes >= erf_conv1d_wgrad_tc_workspace(C), "erf_conv1d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes,
                 erf_conv1d_wgrad_tc_workspace(C));
-  const int KC = C / 64;
+  const int CH = C < 64 ? C : 64, RB = CH * 2, KC = C / CH;
   const int box_w = horizontal ? PX + 2 * dil : PX;
   CUtensorMap mx, mdy;
   if (make_map(&mx, x, N, H, W, C, box_w) != 0 || make_map(&mdy, dy, N, H, W, C, PX) != 0) {
@@ -223,21 +232,29 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
   p.units = N * H * (W / PX);
   int x_bytes;
   if (horizontal) {
-    p.x_sub_bytes = ((box_w + 7) / 8) * 8 * 128;
+    p.x_sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;
     x_bytes = KC * p.x_sub_bytes;
   } else {
-    p.x_sub_bytes = PX * 128;
+    p.x_sub_bytes = PX * RB;
     x_bytes = 3 * KC * p.x_sub_bytes;
   }
+  x_bytes = ((x_bytes + 1023) / 1024) * 1024;
   p.dy_off = x_bytes;
-  p.stage_bytes = x_bytes + KC * PX * 128;
-  p.stages = (220 * 1024) / p.stage_bytes;
+  p.stage_bytes = x_bytes + ((KC * PX * RB + 1023) / 1024) * 1024;
+  p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > kWgStages) p.stages = kWgStages;
-  size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  // C = 16: the five unused M atoms of the x operand read up to 7 tap pitches past the tile -- keep that inside the allocation
+  size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (C == 16 ? 16 * 1024 : 0);
   int grid = p.units < 148 ? p.units : 148;
   cudaError_t e;
   cudaStream_t s = (cudaStream_t)stream;
-  if (C == 64) {
+  if (C == 16) {
+    e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      conv1d_wgrad_tc_kernel<16><<<grid, 192, smem, s>>>(mx, mdy, p);
+      wgrad_reduce_kernel<16><<<(3 * 16 * 16 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+    }
+  } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<64><<<grid, 192, smem, s>>>(mx, mdy, p);

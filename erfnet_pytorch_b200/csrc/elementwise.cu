@@ -286,18 +286,21 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* 
 // tcgen05 operand images of a 3-tap conv weight w[Co][Ci][3] (fp32): forward Wt[t][n=co][k=ci] and data-gradient
 // Wt'[t][n=ci][k=co] = w[co][ci][2-t]; layout [3][C/64][C][8 chunks of 8], chunk index XOR-swizzled by (n & 7).
 __global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_bfloat16* __restrict__ img_fwd, __nv_bfloat16* __restrict__ img_dgrad) {
-  const int kc_n = C / 64;
-  const int total = 3 * kc_n * C * 8;  // 16-byte chunks per image
+  const int ch = C < 64 ? C : 64;   // channels per K chunk (one swizzle row)
+  const int cpr = ch / 8;           // 16-byte chunks per row: 8 (128B swizzle) or 2 (32B swizzle)
+  const int kc_n = C / ch;
+  const int total = 3 * kc_n * C * cpr;  // 16-byte chunks per image
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * total) return;
   const bool dgrad = i >= total;
   if (dgrad) i -= total;
-  const int jj = i & 7, n = (i >> 3) % C, kc = (i / (8 * C)) % kc_n, t = i / (8 * C * kc_n);
-  const int j = jj ^ (n & 7);
+  const int jj = i % cpr, n = (i / cpr) % C, kc = (i / (cpr * C)) % kc_n, t = i / (cpr * C * kc_n);
+  // swizzle: address bits [4,7) ^= bits [7,10) (128B rows) ; bit 4 ^= bit 7 (32B rows: bit 7 of n*32 is bit 2 of n)
+  const int j = cpr == 8 ? (jj ^ (n & 7)) : (jj ^ ((n >> 2) & 1));
   Vec<__nv_bfloat16, 8> v;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k = kc * 64 + j * 8 + e;
+    const int k = kc * ch + j * 8 + e;
     v.v[e] = dgrad ? w[((size_t)k * C + n) * 3 + (2 - t)] : w[((size_t)n * C + k) * 3 + t];
   }
   v.store((dgrad ? img_dgrad : img_fwd) + (size_t)i * 8);
@@ -495,8 +498,8 @@ extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long 
 }
 
 extern "C" int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream) {
-  ERF_CHECK_ARG(w && img_fwd && img_dgrad && (C == 64 || C == 128), "erf_pack_conv1d_tc: bad arguments (C=%d)", C);
-  int total = 2 * 3 * (C / 64) * C * 8;
+  ERF_CHECK_ARG(w && img_fwd && img_dgrad && (C == 16 || C == 64 || C == 128), "erf_pack_conv1d_tc: bad arguments (C=%d)", C);
+  int total = 2 * 3 * C * (C / 8);
   pack_conv1d_tc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, C, (__nv_bfloat16*)img_fwd, (__nv_bfloat16*)img_dgrad);
   ERF_CHECK_LAUNCH("erf_pack_conv1d_tc");
   return ERF_OK;

@@ -249,7 +249,7 @@ class non_bottleneck_1d(_B200Module):
                 ws[i] = ws[i] * scale.view(-1, 1, 1, 1)
                 bs[i] = bs[i] * scale + shift
         pk = dict(w=[ops.pack_weight_fwd(w, s, dtype) for w, s in zip(ws, self.specs)], b=[b.contiguous() for b in bs])
-        if dtype == torch.bfloat16 and self.chann in (64, 128) and not ops.EMULATED:
+        if dtype == torch.bfloat16 and self.chann in (16, 64, 128) and not ops.EMULATED:
             pk["tc"] = [ops.pack_conv1d_tc(w) for w in ws]  # tcgen05 operand images (BN folded)
         return pk
 
@@ -283,7 +283,7 @@ class non_bottleneck_1d(_B200Module):
         return F.dropout2d(ones, p, True).reshape(x.shape[0], self.chann).contiguous()
 
     def _use_tc(self, x):
-        return (self.chann in (64, 128) and ops.USE_TC and ops.conv1d_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
+        return (self.chann in (16, 64, 128) and ops.USE_TC and ops.conv1d_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
                 and ops.conv1d_tc_supported(self.chann, x.shape[2], 1, x.dtype))
 
     def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None):

@@ -198,10 +198,13 @@ def pack_conv1d_tc(w: torch.Tensor, dgrad: bool = False) -> torch.Tensor:
     if dgrad:
         wt = wt.flip(0).transpose(1, 2)         # [t'][ci][co] = W[co,ci,2-t']
     c = wt.shape[1]
-    img = wt.reshape(3, c, c // 64, 8, 8).permute(0, 2, 1, 3, 4)  # [t][kc][n][j][e]
+    ch = min(c, 64)          # channels per K chunk = one swizzle row (128 B, or 32 B for C = 16)
+    cpr = ch // 8            # 16-byte chunks per row
+    img = wt.reshape(3, c, c // ch, cpr, 8).permute(0, 2, 1, 3, 4)  # [t][kc][n][j][e]
     n = torch.arange(c, device=w.device)
-    perm = torch.arange(8, device=w.device)[None, :] ^ (n[:, None] & 7)  # [n][jj] -> source chunk
-    idx = perm[None, None, :, :, None].expand(3, c // 64, c, 8, 8)
+    key = (n & 7) if cpr == 8 else ((n >> 2) & 1)
+    perm = torch.arange(cpr, device=w.device)[None, :] ^ key[:, None]  # [n][jj] -> source chunk
+    idx = perm[None, None, :, :, None].expand(3, c // ch, c, cpr, 8)
     return img.gather(3, idx).contiguous().to(torch.bfloat16)
 
 
@@ -230,7 +233,7 @@ _WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partia
 
 
 def conv1d_wgrad_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
-    return dtype == torch.bfloat16 and not EMULATED and c in (64, 128) and w % 64 == 0 and 1 <= dil <= 32
+    return dtype == torch.bfloat16 and not EMULATED and c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
 
 
 def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, want_bias=True):

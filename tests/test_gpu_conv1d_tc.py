@@ -14,7 +14,7 @@ from tests.test_host_logic import assert_rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 128), (128, 384)])
+@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 128), (128, 384), (16, 512), (16, 128)])
 @pytest.mark.parametrize("horizontal", [False, True])
 @pytest.mark.parametrize("dil", [1, 2, 16])
 def test_conv1d_tc_matches_fp32_conv(c, w, horizontal, dil):
@@ -59,7 +59,7 @@ def test_whole_net_with_tensor_core_blocks():
         ops.start_kernel_timing()
         y_tc = m(x.cuda()).cpu()
         kt = ops.stop_kernel_timing()
-        assert kt.get("conv1d_tc_kernel", {}).get("n", 0) == 60, kt  # 15 blocks x 4 convs on the tensor cores
+        assert kt.get("conv1d_tc_kernel", {}).get("n", 0) == 68, kt  # all 17 blocks x 4 convs on the tensor cores
         ops.USE_TC = False
         try:
             y_gen = m(x.cuda()).cpu()
@@ -71,7 +71,7 @@ def test_whole_net_with_tensor_core_blocks():
     print(f"argmax agreement tc-vs-oracle: {agree:.5f}; max rel err {np.abs(y_tc.numpy() - ref.numpy()).max() / np.abs(ref.numpy()).max():.3e}")
 
 
-@pytest.mark.parametrize("c,d,hw", [(64, 1, (8, 256)), (128, 4, (12, 128)), (128, 16, (40, 128))])
+@pytest.mark.parametrize("c,d,hw", [(64, 1, (8, 256)), (128, 4, (12, 128)), (128, 16, (40, 128)), (16, 1, (10, 512))])
 def test_block_train_fwd_bwd_on_tensor_cores(c, d, hw):
     """Train-mode non_bottleneck_1d (batch-stat BN, fixed dropout mask): forward, dx, dW, dgamma with the tcgen05 convs."""
     blk = E.non_bottleneck_1d(c, 0.1, d)
@@ -125,7 +125,7 @@ def test_block_train_fwd_bwd_on_tensor_cores(c, d, hw):
         assert l2(runs[True][k], ref[k]) < 0.2, (k, l2(runs[True][k], ref[k]))
 
 
-@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 64), (128, 192)])
+@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 64), (128, 192), (16, 512), (16, 64)])
 @pytest.mark.parametrize("horizontal", [False, True])
 @pytest.mark.parametrize("dil", [1, 2, 16])
 def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
@@ -144,7 +144,7 @@ def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
 
 
 def test_pack_kernel_matches_host_packing():
-    for c, shape in ((64, (64, 64, 3, 1)), (128, (128, 128, 1, 3))):
+    for c, shape in ((64, (64, 64, 3, 1)), (128, (128, 128, 1, 3)), (16, (16, 16, 3, 1))):
         w = torch.randn(*shape, generator=torch.Generator().manual_seed(c)).cuda()
         f, d = ops.pack_conv1d_tc_pair(w)
         assert torch.equal(f.view(-1), ops.pack_conv1d_tc(w).view(-1))
