@@ -219,6 +219,125 @@ __global__ void conv_wgrad_kernel(const T* __restrict__ in, const T* __restrict_
       if (co0 + k < g.Cout && acc[q][k] != 0.f) atomicAdd(&dw[((size_t)tap * g.Cin + ci0 + q) * g.w_ld + co0 + k], acc[q][k]);
 }
 
+// Shared-memory tiled weight gradient (same contract as conv_wgrad_kernel): one block = one tap x one pixel chunk.
+// Pixels are staged 32 at a time as fp32 ([32][CIN_S] gathered x, [32][COUT_S] dy); a 16x16 thread grid keeps a
+// TI x TJ register tile of dW (ci = ty*TI + i, co = tx*TJ + j) and the block flushes it with one atomic per element.
+template <typename T, int TI, int TJ>
+__global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const T* __restrict__ in, const T* __restrict__ dout, float* __restrict__ dw,
+                                                               erf_conv_geom g, int px_per_block) {
+  constexpr int CIN_S = 16 * TI, COUT_S = 16 * TJ, PXT = 32;
+  __shared__ __align__(16) float xs[PXT][CIN_S];
+  __shared__ __align__(16) float ds[PXT][COUT_S];
+  const int tap = blockIdx.y;
+  const int ky = tap / g.KW, kx = tap % g.KW;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // The loop runs over the DENSE side of the gather: output pixels for a conv, INPUT pixels for a transposed conv
+  // (there every (tap, input pixel) pair is valid, whereas only 1/stride^2 of the (tap, output pixel) pairs are).
+  const int DW = g.transposed ? g.W : g.Wo, DH = g.transposed ? g.H : g.Ho;
+  const long long total = (long long)g.N * DH * DW;
+  const long long p0 = (long long)blockIdx.x * px_per_block;
+  long long p1 = p0 + px_per_block;
+  if (p1 > total) p1 = total;
+  float acc[TI][TJ];
+#pragma unroll
+  for (int i = 0; i < TI; ++i)
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
+  for (long long pb = p0; pb < p1; pb += PXT) {
+    // ---- stage 32 pixels: 4 input channels / 4 output channels per thread-iteration
+    for (int e = threadIdx.x; e < PXT * (CIN_S / 4 + COUT_S / 4); e += 256) {
+      const bool is_x = e < PXT * (CIN_S / 4);
+      const int e2 = is_x ? e : e - PXT * (CIN_S / 4);
+      const int per = is_x ? CIN_S / 4 : COUT_S / 4;
+      const int pp = e2 / per, c4 = (e2 % per) * 4;
+      const long long p = pb + pp;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int cmax = is_x ? g.Cin : g.Cout;
+      if (p < p1 && c4 < cmax) {
+        int dx = (int)(p % DW);
+        long long t = p / DW;
+        int dy_ = (int)(t % DH), n = (int)(t / DH);
+        // coordinates of this pixel on the input (iy, ix) and output (oy, ox) grids
+        int iy, ix, oy, ox;
+        bool ok = true;
+        if (!g.transposed) {
+          oy = dy_; ox = dx;
+          iy = oy * g.stride - g.pad_h + ky * g.dil_h;
+          ix = ox * g.stride - g.pad_w + kx * g.dil_w;
+          ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+        } else {
+          iy = dy_; ix = dx;
+          oy = iy * g.stride - g.pad_h + ky * g.dil_h;
+          ox = ix * g.stride - g.pad_w + kx * g.dil_w;
+          ok = oy >= 0 && oy < g.Ho && ox >= 0 && ox < g.Wo;
+        }
+        if (ok) {
+          if (is_x) {
+            Vec<T, 4> t4;
+            t4.load(in + (((size_t)n * g.H + iy) * g.W + ix) * g.in_ld + c4);
+            v = make_float4(t4.v[0], t4.v[1], t4.v[2], t4.v[3]);
+          } else {
+            const T* dp = dout + (((size_t)n * g.Ho + oy) * g.Wo + ox) * g.out_ld + g.out_coff + c4;
+            if (c4 + 4 <= g.Cout && ((g.out_ld | g.out_coff) & 3) == 0) {
+              Vec<T, 4> t4;
+              t4.load(dp);
+              v = make_float4(t4.v[0], t4.v[1], t4.v[2], t4.v[3]);
+            } else {
+              float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int k = 0; k < 4; ++k)
+                if (c4 + k < g.Cout) tmp[k] = to_f(dp[k]);
+              v = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            }
+          }
+        }
+      }
+      if (is_x) *reinterpret_cast<float4*>(&xs[pp][c4]) = v;
+      else *reinterpret_cast<float4*>(&ds[pp][c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < PXT; ++pp) {
+      float xv[TI], dv[TJ];
+#pragma unroll
+      for (int i = 0; i < TI; ++i) xv[i] = xs[pp][ty * TI + i];
+#pragma unroll
+      for (int j = 0; j < TJ; ++j) dv[j] = ds[pp][tx * TJ + j];
+#pragma unroll
+      for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j] = fmaf(xv[i], dv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TI; ++i)
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) {
+      const int ci = ty * TI + i, co = tx * TJ + j;
+      if (ci < g.Cin && co < g.Cout && acc[i][j] != 0.f) atomicAdd(&dw[((size_t)tap * g.Cin + ci) * g.w_ld + co], acc[i][j]);
+    }
+}
+
+template <typename T>
+static bool launch_wgrad_tiled(const T* in, const T* dout, float* dw, const erf_conv_geom& g, cudaStream_t s) {
+  const int ti = g.Cin <= 16 ? 1 : (g.Cin <= 32 ? 2 : (g.Cin <= 64 ? 4 : (g.Cin <= 128 ? 8 : 0)));
+  const int tj = g.Cout <= 16 ? 1 : (g.Cout <= 32 ? 2 : (g.Cout <= 64 ? 4 : (g.Cout <= 128 ? 8 : 0)));
+  if (!ti || !tj) return false;
+  const long long total = g.transposed ? (long long)g.N * g.H * g.W : (long long)g.N * g.Ho * g.Wo;
+  const int taps = g.KH * g.KW;
+  long long want_blocks = 148 * 6 / taps + 1;
+  long long ppb = (total + want_blocks - 1) / want_blocks;
+  ppb = ((ppb + 31) / 32) * 32;
+  if (ppb < 256) ppb = 256;
+  dim3 grid((unsigned)((total + ppb - 1) / ppb), taps);
+#define WG_CASE(TI_, TJ_) \
+  if (ti == TI_ && tj == TJ_) { conv_wgrad_tiled_kernel<T, TI_, TJ_><<<grid, 256, 0, s>>>(in, dout, dw, g, (int)ppb); return true; }
+  WG_CASE(1, 1) WG_CASE(1, 2) WG_CASE(1, 4) WG_CASE(1, 8) WG_CASE(2, 1) WG_CASE(2, 2) WG_CASE(2, 4) WG_CASE(2, 8)
+  WG_CASE(4, 1) WG_CASE(4, 2) WG_CASE(4, 4) WG_CASE(4, 8) WG_CASE(8, 1) WG_CASE(8, 2) WG_CASE(8, 4) WG_CASE(8, 8)
+#undef WG_CASE
+  return false;
+}
+
 // out[c] += sum_p x[p*ld + coff + c]
 template <typename T>
 __global__ void channel_sum_kernel(const T* __restrict__ x, int ld, int coff, int C, long long n_px, int px_per_block,
@@ -283,19 +402,23 @@ extern "C" int erf_conv_wgrad(const void* in, const void* dout, float* dw, float
   ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_conv_wgrad: bad dtype %d", dtype);
   const int ntile = (g->Cin / 4) * (g->w_ld / CT);
   ERF_CHECK_ARG(ntile <= 1024, "erf_conv_wgrad: Cin*Cout too large (%d x %d)", g->Cin, g->Cout);
-  int block = ntile <= 256 ? 256 : (ntile <= 512 ? 512 : 1024);
-  int lanes = block / ntile;
   long long total = (long long)g->N * g->Ho * g->Wo;
   int taps = g->KH * g->KW;
-  long long want_blocks = 148 * 4 / taps + 1;
-  long long ppb = (total + want_blocks - 1) / want_blocks;
-  if (ppb < 64 * lanes) ppb = 64 * lanes;
-  dim3 grid((unsigned)((total + ppb - 1) / ppb), taps);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == ERF_F32)
-    conv_wgrad_kernel<float><<<grid, block, 0, s>>>((const float*)in, (const float*)dout, dw, *g, (int)ppb, ntile, lanes);
-  else
-    conv_wgrad_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, dw, *g, (int)ppb, ntile, lanes);
+  bool done = dtype == ERF_F32 ? launch_wgrad_tiled<float>((const float*)in, (const float*)dout, dw, *g, s)
+                               : launch_wgrad_tiled<__nv_bfloat16>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, dw, *g, s);
+  if (!done) {
+    int block = ntile <= 256 ? 256 : (ntile <= 512 ? 512 : 1024);
+    int lanes = block / ntile;
+    long long want_blocks = 148 * 4 / taps + 1;
+    long long ppb = (total + want_blocks - 1) / want_blocks;
+    if (ppb < 64 * lanes) ppb = 64 * lanes;
+    dim3 grid((unsigned)((total + ppb - 1) / ppb), taps);
+    if (dtype == ERF_F32)
+      conv_wgrad_kernel<float><<<grid, block, 0, s>>>((const float*)in, (const float*)dout, dw, *g, (int)ppb, ntile, lanes);
+    else
+      conv_wgrad_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, dw, *g, (int)ppb, ntile, lanes);
+  }
   ERF_CHECK_LAUNCH("erf_conv_wgrad");
   if (db) {
     int cblock = 256;
