@@ -44,6 +44,7 @@ _SIGNATURES = {
     "erf_iou_counts": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "erf_argmax": [_vp, _i, _i, _ll, _i, _vp, _i, _i, _vp],
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
+    "erf_adam_step_dev": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "erf_pack_conv1d_tc": [_vp, _i, _vp, _vp, _vp],

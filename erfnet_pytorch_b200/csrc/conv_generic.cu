@@ -422,7 +422,7 @@ extern "C" int erf_conv_wgrad(const void* in, const void* dout, float* dw, float
   ERF_CHECK_LAUNCH("erf_conv_wgrad");
   if (db) {
     int cblock = 256;
-    long long cb = 148 * 4;
+    long long cb = 148 * 2;
     long long cppb = (total + cb - 1) / cb;
     if (cppb < 256) cppb = 256;
     unsigned cgrid = (unsigned)((total + cppb - 1) / cppb);
@@ -439,7 +439,7 @@ extern "C" int erf_conv_wgrad(const void* in, const void* dout, float* dw, float
 extern "C" int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream) {
   ERF_CHECK_ARG(x && out && n_px > 0 && C > 0 && C <= 256 && ld >= coff + C, "erf_channel_sum: bad arguments");
   ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_channel_sum: bad dtype %d", dtype);
-  long long cb = 148 * 4;
+  long long cb = 148 * 2;
   long long cppb = (n_px + cb - 1) / cb;
   if (cppb < 256) cppb = 256;
   unsigned cgrid = (unsigned)((n_px + cppb - 1) / cppb);

@@ -308,7 +308,13 @@ __global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_b
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                            float lr_over_bc1, float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale) {
+                            float lr_over_bc1, float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale,
+                            const int* __restrict__ step_dev, float lr) {
+  if (step_dev) {  // CUDA-graph friendly: the step count lives on the device (incremented by adam_step_inc_kernel)
+    const double st = (double)*step_dev;
+    lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, st)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, st)));
+  }
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float pv = p[i];
@@ -319,6 +325,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   v[i] = vv;
   p[i] = pv - lr_over_bc1 * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
 }
+
+__global__ void adam_step_inc_kernel(int* step_dev) { *step_dev += 1; }
 
 }  // namespace erfk
 
@@ -401,7 +409,7 @@ extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const
 extern "C" int erf_channel_stats(const void* x, int ld, int C, long long n_px, double* stats, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_channel_stats");
   ERF_CHECK_ARG(x && stats && n_px > 0 && C >= 8 && (C % 8) == 0 && C <= 2048 && (ld % 8) == 0, "erf_channel_stats: C and ld must be multiples of 8");
-  long long want = 148 * 8;
+  long long want = 148 * 2;
   long long ppb = (n_px + want - 1) / want;
   if (ppb < 128) ppb = 128;
   unsigned grid = (unsigned)((n_px + ppb - 1) / ppb);
@@ -455,7 +463,7 @@ extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_l
                     (!mask || (mask_ld % 8) == 0),
                 "erf_bn_bwd_reduce: C and leading dimensions must be multiples of 8");
   long long n_px = (long long)N * HW;
-  long long want = 148 * 8;
+  long long want = 148 * 2;
   long long ppb = (n_px + want - 1) / want;
   if (ppb < 64) ppb = 64;
   unsigned grid = (unsigned)((n_px + ppb - 1) / ppb);
@@ -492,8 +500,19 @@ extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long 
   ERF_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "erf_adam_step: bad arguments");
   double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   unsigned grid = (unsigned)((n + 255) / 256);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale,
+                                                      nullptr, lr);
   ERF_CHECK_LAUNCH("erf_adam_step");
+  return ERF_OK;
+}
+
+extern "C" int erf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, int* step_dev, float grad_scale, erf_stream_t stream) {
+  ERF_CHECK_ARG(p && g && m && v && n > 0 && step_dev, "erf_adam_step_dev: bad arguments");
+  unsigned grid = (unsigned)((n + 255) / 256);
+  adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr);
+  ERF_CHECK_LAUNCH("erf_adam_step_dev");
   return ERF_OK;
 }
 

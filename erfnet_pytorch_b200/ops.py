@@ -425,6 +425,13 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     _count()
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale=1.0):
+    """Adam with the step counter in device memory (int32[1], incremented by the call) -- CUDA-graph capturable."""
+    check(_lib.lib().erf_adam_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, _p(step_dev), grad_scale,
+                                       _stream(p)))
+    _count(2)
+
+
 def umma_probe(a: torch.Tensor, b: torch.Tensor, row_shift: int, layout: int, iters: int = 1):
     """a [rows,K] bf16, b [N,K] bf16 -> (D [128,N] fp32, cycles)."""
     rows, k = a.shape

@@ -49,6 +49,7 @@ class FlatAdamTrainer:
         order = sorted(range(len(named)), key=lambda i: (_bucket_of(named[i][0]), i))
         total = sum(p.numel() for _, p in named)
         dev = named[0][1].device
+        self.criterion = self.criterion.to(dev)
         self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -73,6 +74,7 @@ class FlatAdamTrainer:
         self._pending = list(self._bucket_params)
         self._launched = [False, False, False]
         self._works = []
+        self._graph, self._step_dev = None, None
         self.cuda = dev.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
         if self.world > 1:
@@ -124,7 +126,6 @@ class FlatAdamTrainer:
         logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
         c = self.num_classes
         w = self.criterion.weight
-        w = None if w is None else w.to(logits.device)
         labels = labels.contiguous()
         # pass 1: valid-pixel weight sum, all-reduced so that every rank normalises by the global denominator
         acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
@@ -141,14 +142,55 @@ class FlatAdamTrainer:
 
     def optimizer_step(self):
         self.step_count += 1
-        ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                      self.step_count)
+        if self._step_dev is not None:  # CUDA-graph mode: the step counter lives on the device
+            ops.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                              self._step_dev)
+        else:
+            ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                          self.step_count)
         _erfnet.bump_weights_epoch()  # flat_p aliases the parameters; invalidate eval-mode packed weights
 
     def train_step(self, images, labels, drop_scales=None):
+        if self._graph is not None and drop_scales is None:
+            self._g_images.copy_(images, non_blocking=True)
+            self._g_labels.copy_(labels, non_blocking=True)
+            self._graph.replay()
+            self.step_count += 1
+            _erfnet.bump_weights_epoch()
+            return self._g_loss
         loss = self.loss_and_backward(images, labels, drop_scales)
         self.optimizer_step()
         return loss
+
+    # ---- CUDA graph of the whole step (forward, loss, backward, all-reduce, Adam): ~700 launches -> one replay ---------
+    def capture_cuda_graph(self, images_shape, labels_shape, warmup=2):
+        """Capture one full training step for fixed shapes.  State touched by the warm-up steps is restored, so training
+        semantics are unchanged; afterwards train_step() copies the batch into static buffers and replays the graph."""
+        dev = self.flat_p.device
+        self._g_images = torch.zeros(images_shape, device=dev, dtype=torch.float32)
+        self._g_labels = torch.zeros(labels_shape, device=dev, dtype=torch.int64)
+        self._step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int32)
+        snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self._step_dev)]
+        bufs = [b.clone() for b in self.model.buffers()]
+        count = self.step_count
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.loss_and_backward(self._g_images, self._g_labels)
+                self.optimizer_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.loss_and_backward(self._g_images, self._g_labels)
+            self.optimizer_step()
+        for t, s_ in zip((self.flat_p, self.flat_m, self.flat_v, self._step_dev), snap):
+            t.copy_(s_)
+        for b, s_ in zip(self.model.buffers(), bufs):
+            b.copy_(s_)
+        self.step_count = count
+        self._g_loss, self._graph = loss, graph
+        return graph
 
 
 def allreduce_confusion(ev, process_group=None):

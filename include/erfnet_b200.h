@@ -148,6 +148,11 @@ int erf_argmax(const void* logits, int ld, int nchw_hw, long long n_px, int C, v
 int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, erf_stream_t stream);
 
+/* Same, with the step counter on the device (*step_dev is incremented, then used for the bias corrections) so that the
+ * call can be captured in a CUDA graph and replayed. */
+int erf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int* step_dev, float grad_scale, erf_stream_t stream);
+
 /* ---- tcgen05 implicit-GEMM 3x1 / 1x3 (dilated) convolution, C = 64 or 128, NHWC bf16 ----------
  * out[p,co] = epilogue(sum_t sum_ci in[p + (t-1)*dil along H (horizontal=0) or W (horizontal=1), ci] * Wt[t][co][ci]),
  * epilogue as erf_conv_fwd (bias -> + res -> relu -> * (mask>0)).  TMA-staged 128B-swizzled activation tiles (zero-filled

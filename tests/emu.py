@@ -218,8 +218,13 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale=1.0):
+    step_dev += 1
+    adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, int(step_dev), grad_scale)
+
+
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step"]
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev"]
 
 
 @contextlib.contextmanager

@@ -1,0 +1,48 @@
+"""GPU: CUDA-graph replay of the training step / inference forward gives the same numbers as eager launches."""
+import numpy as np
+import pytest
+import torch
+
+from erfnet_pytorch_b200 import erfnet as E
+from erfnet_pytorch_b200.graphs import GraphedInference
+from erfnet_pytorch_b200.parallel import FlatAdamTrainer
+from oracle import erfnet_oracle as O
+from oracle.make_golden import golden_input, golden_labels
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(precision):
+    m = E.ERFNet(20)
+    m.precision = precision
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 0))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0  # deterministic comparison
+    return FlatAdamTrainer(m.cuda(), weight=torch.linspace(0.5, 1.5, 20))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_training_matches_eager(precision):
+    x = [golden_input((2, 3, 64, 256), i).cuda() for i in range(3)]
+    y = [golden_labels((2, 64, 256), i).cuda() for i in range(3)]
+    a, b = _trainer(precision), _trainer(precision)
+    b.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
+    la = [float(a.train_step(x[i], y[i])) for i in range(3)]
+    lb = [float(b.train_step(x[i], y[i])) for i in range(3)]
+    np.testing.assert_allclose(lb, la, rtol=2e-3 if precision == "fp32" else 2e-2)
+    assert b.step_count == 3 and int(b._step_dev) == 3
+    sa, sb = a.model.state_dict(), b.model.state_dict()
+    assert int(sb["encoder.layers.3.bn1.num_batches_tracked"]) == int(sa["encoder.layers.3.bn1.num_batches_tracked"])
+    np.testing.assert_allclose(sb["decoder.layers.3.bn.running_var"].cpu().numpy(), sa["decoder.layers.3.bn.running_var"].cpu().numpy(), rtol=2e-2)
+
+
+def test_graphed_inference_matches_eager():
+    m = E.ERFNet(20)
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 0))
+    m = m.cuda().eval()
+    x0, x1 = golden_input((2, 3, 64, 1024), 1).cuda(), golden_input((2, 3, 64, 1024), 2).cuda()
+    gi = GraphedInference(m, x0)
+    with torch.no_grad():
+        assert torch.equal(gi(x1), m(x1))
+        assert torch.equal(gi(x0), m(x0))
