@@ -12,10 +12,13 @@
 //                        is shifted by t*d pixel rows (address-based swizzle makes any row shift legal; pinned by
 //                        tests/test_gpu_umma.py)
 //   * the three tap weight matrices (host pre-swizzled image) arrive once per persistent CTA with cp.async.bulk
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue: TMEM -> registers -> swizzled
-//     shared-memory staging tile -> TMA store (coalesced 128-byte lines instead of 32 scattered 16-byte stores per warp
-//     instruction); the residual / ReLU-mask operand is TMA-loaded INTO the same staging tile and combined in place
-//   * two TMEM accumulators: the epilogue of unit i overlaps the MMAs of unit i+1.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 and 6-9 = TWO epilogue groups that take
+//     alternate units (one TMEM accumulator each): TMEM -> registers -> swizzled shared-memory staging sub-tile (one
+//     64-channel k-chunk, double-buffered per group) -> TMA store (coalesced 128-byte lines instead of 32 scattered
+//     16-byte stores per warp instruction); the residual / ReLU-mask operand is TMA-PREFETCHED into the staging sub-tile
+//     one step ahead and combined in place
+//   * the A ring works at (tap, k-chunk) granularity for vertical convs and k-chunk granularity for horizontal ones, so
+//     at C = 128 (96 KB of weights) there are still 3-4 loads in flight.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -39,16 +42,17 @@ struct Conv1dTcParams {
 };
 
 constexpr int kMaxSlots = 8;
+constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 template <int C>
-__global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                            const __grid_constant__ CUtensorMap tmap_aux, const Conv1dTcParams p) {
   constexpr int CH = C < 64 ? C : 64;           // channels per K chunk (one swizzle row)
   constexpr int RB = CH * 2;                    // bytes per pixel row of a chunk: 128 (128B swizzle) or 32 (32B swizzle, C = 16)
@@ -58,8 +62,9 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
   constexpr uint32_t LAYOUT = RB == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
   constexpr int W_BYTES = 3 * KC * C * RB;      // all tap weights
   constexpr int W_PAD = ((W_BYTES + 1023) / 1024) * 1024;
-  constexpr int STG_BYTES = KC * 128 * RB;      // output / aux staging tile ([kc][128 px][RB])
+  constexpr int STG_BYTES = 128 * RB;           // one staging sub-tile: 128 px x one k-chunk
   constexpr int STG_PAD = ((STG_BYTES + 1023) / 1024) * 1024;
+  constexpr int STG_TOTAL = 4 * STG_PAD;        // 2 epilogue groups x double buffer
   constexpr int EW = C >= 32 ? 32 : 16;         // epilogue column chunk
   constexpr uint32_t TMEM_COLS = 2 * C < 32 ? 32 : 2 * C;
   constexpr uint32_t IDESC = make_idesc_bf16(128, C);
@@ -67,8 +72,8 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;
   uint8_t* s_stg = smem + W_PAD;
-  uint8_t* s_a = s_stg + STG_PAD;
-  __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar;
+  uint8_t* s_a = s_stg + STG_TOTAL;
+  __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[C];
 
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
       mbar_init(&tempty_bar[a], 4);
     }
     mbar_init(&w_bar, 1);
-    mbar_init(&aux_bar, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&aux_bar[a], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_out);
@@ -112,21 +117,23 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
         if (p.horizontal) {
-          mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(KC * (128 + 2 * p.dil) * RB));
-          uint8_t* base = s_a + (size_t)slot * p.slot_bytes;
-#pragma unroll
-          for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.sub_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128 - p.dil, y, n);
-          if (++slot == p.slots) { slot = 0; phase ^= 1; }
+#pragma unroll 1
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)((128 + 2 * p.dil) * RB));
+            tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128 - p.dil, y, n);
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
         } else {
 #pragma unroll 1
           for (int t = 0; t < 3; ++t) {
-            mbar_wait(&empty_bar[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(KC * 128 * RB));
-            uint8_t* base = s_a + (size_t)slot * p.slot_bytes;
-#pragma unroll
-            for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.sub_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128, y + (t - 1) * p.dil, n);
-            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+#pragma unroll 1
+            for (int kc = 0; kc < KC; ++kc) {
+              mbar_wait(&empty_bar[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(128 * RB));
+              tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128, y + (t - 1) * p.dil, n);
+              if (++slot == p.slots) { slot = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -143,40 +150,40 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         const uint32_t d_tmem = tmem_base + acc * C;
         if (p.horizontal) {
-          mbar_wait(&full_bar[slot], phase);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(s_a + (size_t)slot * p.slot_bytes);
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-#pragma unroll
-            for (int kc = 0; kc < KC; ++kc) {
-              const uint32_t a_lo = (((a_addr + t * p.dil * RB + kc * p.sub_bytes) >> 4) & 0x3FFF) | (1u << 16);
-              const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
-                          (t | kc | k) != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&empty_bar[slot]);
-          if (++slot == p.slots) { slot = 0; phase ^= 1; }
-        } else {
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
+          for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(&full_bar[slot], phase);
             tcgen05_fence_after();
             const uint32_t a_addr = smem_u32(s_a + (size_t)slot * p.slot_bytes);
 #pragma unroll
-            for (int kc = 0; kc < KC; ++kc) {
-              const uint32_t a_lo = (((a_addr + kc * p.sub_bytes) >> 4) & 0x3FFF) | (1u << 16);
+            for (int t = 0; t < 3; ++t) {
+              const uint32_t a_lo = (((a_addr + t * p.dil * RB) >> 4) & 0x3FFF) | (1u << 16);
               const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
                 umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
                           (t | kc | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[slot]);   // this tap's tile is reusable once its MMAs have read it
+            umma_commit(&empty_bar[slot]);
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+              mbar_wait(&full_bar[slot], phase);
+              tcgen05_fence_after();
+              const uint32_t a_addr = smem_u32(s_a + (size_t)slot * p.slot_bytes);
+              const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | (1u << 16);
+              const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                          (t | kc | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[slot]);   // this (tap, k-chunk) tile is reusable once its MMAs have read it
+              if (++slot == p.slots) { slot = 0; phase ^= 1; }
+            }
           }
         }
         umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
@@ -185,94 +192,112 @@ __global__ void __launch_bounds__(192, 1) conv1d_tc_kernel(const __grid_constant
       }
     }
   } else {
-    // ================= epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =================
+    // ================= epilogue: group 0 = warps 2..5, group 1 = warps 6..9; TMEM lane quadrant = warp % 4 =========
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;          // pixel within the unit = TMEM lane = staging row
-    const bool leader = (warp == 2 && lane == 0);
-    // swizzled position of logical 16-byte chunk j of this row inside a k-chunk sub-tile of the staging buffer
+    const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
+    // swizzled position of logical 16-byte chunk j of this row inside a staging sub-tile
     const int sw_key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
-    uint8_t* my_row = s_stg + row * RB;
-    uint32_t acc = 0, acc_phase = 0, aux_phase = 0;
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+    uint8_t* stg_g = s_stg + grp * 2 * STG_PAD;
+    uint64_t* aux_g = &aux_bar[grp * 2];
+    const uint32_t acc = grp;                  // accumulator owned by this group
+    uint32_t acc_phase = 0, aux_phase[2] = {0, 0};
+    int step = 0;                              // staging steps (unit, k-chunk) done by this group
+    // units of this CTA alternate between the two groups
+    const int u_first = blockIdx.x + grp * gridDim.x, u_stride = 2 * gridDim.x;
+    if (leader && p.aux_mode && u_first < p.units) {   // aux prefetch for the very first step
+      const int xs = u_first % segs, y = (u_first / segs) % p.H, n = u_first / (segs * p.H);
+      mbar_arrive_expect_tx(&aux_g[0], STG_BYTES);
+      tma_load_4d(stg_g, &tmap_aux, &aux_g[0], 0, xs * 128, y, n);
+    }
+    for (int u = u_first; u < p.units; u += u_stride) {
       const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
-      if (leader) {
-        tma_store_wait_read0();            // the previous unit's store has finished reading the staging tile
-        if (p.aux_mode) {
-          mbar_arrive_expect_tx(&aux_bar, STG_BYTES);
-#pragma unroll
-          for (int kc = 0; kc < KC; ++kc) tma_load_4d(s_stg + kc * (128 * RB), &tmap_aux, &aux_bar, kc * CH, xs * 128, y, n);
-        }
-      }
-      epi_bar_sync();                      // staging tile is free (and its aux load is in flight)
       mbar_wait(&tfull_bar[acc], acc_phase);
+      acc_phase ^= 1;
       tcgen05_fence_after();
-      if (p.aux_mode) {
-        mbar_wait(&aux_bar, aux_phase);
-        aux_phase ^= 1;
-      }
       const uint32_t taddr = tmem_base + acc * C + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += EW) {
-        uint32_t r[EW];
-        if (EW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        float v[EW];
-#pragma unroll
-        for (int j = 0; j < EW; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-        uint8_t* sub = my_row + (c0 / CH) * (128 * RB);   // k-chunk sub-tile holding channels c0..
-        const int j0 = (c0 % CH) / 8;                      // first logical 16-byte chunk of this column chunk
-        uint4 aux[EW / 8];
+      for (int kc = 0; kc < KC; ++kc, ++step) {
+        const int b = step & 1;
+        uint8_t* my_row = stg_g + b * STG_PAD + row * RB;
+        // both 32-column TMEM loads of this k-chunk are in flight before the first wait
+        uint32_t r[CH];
+        if (CH == 64) { tmem_ld32(taddr + kc * CH, r); tmem_ld32(taddr + kc * CH + 32, r + 32); }
+        else tmem_ld16(taddr, r);
         if (p.aux_mode) {
-#pragma unroll
-          for (int q = 0; q < EW / 8; ++q) aux[q] = *reinterpret_cast<const uint4*>(sub + (((j0 + q) ^ sw_key) * 16));
+          mbar_wait(&aux_g[b], aux_phase[b]);
+          aux_phase[b] ^= 1;
         }
-        if (p.aux_mode == 1) {
+        tmem_ld_wait();
+        if (kc == KC - 1) {                      // all TMEM reads of this unit are done: release the accumulator early
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += EW) {
+          float v[EW];
+#pragma unroll
+          for (int j = 0; j < EW; ++j) v[j] = __uint_as_float(r[c0 + j]) + s_bias[kc * CH + c0 + j];
+          const int j0 = c0 / 8;                 // first logical 16-byte chunk of this column chunk
+          uint4 aux[EW / 8];
+          if (p.aux_mode) {
+#pragma unroll
+            for (int q = 0; q < EW / 8; ++q) aux[q] = *reinterpret_cast<const uint4*>(my_row + (((j0 + q) ^ sw_key) * 16));
+          }
+          if (p.aux_mode == 1) {
+#pragma unroll
+            for (int q = 0; q < EW / 8; ++q) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aux[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[q * 8 + 2 * e] += __low2float(h[e]);
+                v[q * 8 + 2 * e + 1] += __high2float(h[e]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < EW; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.aux_mode == 2) {
+#pragma unroll
+            for (int q = 0; q < EW / 8; ++q) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aux[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (!(__low2float(h[e]) > 0.f)) v[q * 8 + 2 * e] = 0.f;
+                if (!(__high2float(h[e]) > 0.f)) v[q * 8 + 2 * e + 1] = 0.f;
+              }
+            }
+          }
 #pragma unroll
           for (int q = 0; q < EW / 8; ++q) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aux[q]);
+            uint4 t;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[q * 8 + 2 * e] += __low2float(h[e]);
-              v[q * 8 + 2 * e + 1] += __high2float(h[e]);
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(my_row + (((j0 + q) ^ sw_key) * 16)) = t;
+          }
+        }
+        fence_proxy_async_smem();              // staging writes -> visible to the TMA store
+        if (leader) tma_store_wait_read0();    // the store of step-1 (other buffer) has finished reading its sub-tile
+        epi_bar_sync(grp);
+        if (leader) {
+          tma_store_4d(&tmap_out, stg_g + b * STG_PAD, kc * CH, xs * 128, y, n);
+          tma_store_commit();
+          if (p.aux_mode) {                    // prefetch the aux sub-tile of the NEXT step into the other buffer
+            int nkc = kc + 1, nu = u;
+            if (nkc == KC) { nkc = 0; nu = u + u_stride; }
+            if (nu < p.units) {
+              const int nxs = nu % segs, ny = (nu / segs) % p.H, nn = nu / (segs * p.H);
+              mbar_arrive_expect_tx(&aux_g[b ^ 1], STG_BYTES);
+              tma_load_4d(stg_g + (b ^ 1) * STG_PAD, &tmap_aux, &aux_g[b ^ 1], nkc * CH, nxs * 128, ny, nn);
             }
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < EW; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.aux_mode == 2) {
-#pragma unroll
-          for (int q = 0; q < EW / 8; ++q) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&aux[q]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (!(__low2float(h[e]) > 0.f)) v[q * 8 + 2 * e] = 0.f;
-              if (!(__high2float(h[e]) > 0.f)) v[q * 8 + 2 * e + 1] = 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < EW / 8; ++q) {
-          uint4 t;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(sub + (((j0 + q) ^ sw_key) * 16)) = t;
-        }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator may be overwritten by the MMAs of unit i+2
-      fence_proxy_async_smem();                        // staging writes -> visible to the TMA store
-      epi_bar_sync();
-      if (leader) {
-#pragma unroll
-        for (int kc = 0; kc < KC; ++kc) tma_store_4d(&tmap_out, s_stg + kc * (128 * RB), kc * CH, xs * 128, y, n);
-        tma_store_commit();
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
     if (leader) tma_store_wait0();
   }
@@ -351,9 +376,9 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   } else {
     p.sub_bytes = ((128 * RB + 1023) / 1024) * 1024;
   }
-  p.slot_bytes = KC * p.sub_bytes;
+  p.slot_bytes = p.sub_bytes;   // one (tap, k-chunk) tile [vertical] or one k-chunk of the haloed row tile [horizontal]
   const int w_pad = ((3 * KC * C * RB + 1023) / 1024) * 1024;
-  const int stg_pad = ((KC * 128 * RB + 1023) / 1024) * 1024;
+  const int stg_pad = 4 * (((128 * RB + 1023) / 1024) * 1024);
   const int budget = 225 * 1024 - w_pad - stg_pad;
   p.slots = budget / p.slot_bytes;
   if (p.slots > kMaxSlots) p.slots = kMaxSlots;
@@ -370,13 +395,13 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<16><<<grid, 192, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) conv1d_tc_kernel<16><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<64><<<grid, 192, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) conv1d_tc_kernel<64><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
   } else {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<128><<<grid, 192, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) conv1d_tc_kernel<128><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
   }
   if (e != cudaSuccess) {
     set_error("erf_conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
