@@ -1,0 +1,75 @@
+"""GPU: north_star gate -- the bf16 training loss curve tracks an fp32 run of the same data/initialisation within 1 %
+over 200 synthetic steps (the fp32 path itself is pinned to the reference by the golden train-step test and, over a short
+horizon, to the CPU oracle below)."""
+import numpy as np
+import pytest
+import torch
+
+from erfnet_pytorch_b200 import erfnet as E
+from erfnet_pytorch_b200.parallel import FlatAdamTrainer
+from oracle import erfnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+NC = 20
+
+
+def _data(n_batches, b, h, w, seed=0):
+    """Piece-wise constant label blocks, image = class colour + noise, so the loss actually decreases."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    palette = torch.rand(NC + 1, 3, generator=g)
+    for _ in range(n_batches):
+        blocks = torch.randint(0, NC - 1, (b, h // 16, w // 16), generator=g)
+        blocks = torch.where(torch.rand(b, h // 16, w // 16, generator=g) < 0.05, torch.full_like(blocks, -1), blocks)
+        lab = blocks.repeat_interleave(16, 1).repeat_interleave(16, 2).contiguous()
+        img = palette[lab.clamp_min(0)].permute(0, 3, 1, 2) * 0.8 + 0.1 * torch.rand(b, 3, h, w, generator=g)
+        out.append((img.contiguous(), lab))
+    return out
+
+
+def _run(precision, data, steps, lr=1e-4, seed=0):
+    m = E.ERFNet(NC)
+    m.precision = precision
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), seed))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0  # dropout RNG is device-specific; the gate compares arithmetic, not RNG streams
+    tr = FlatAdamTrainer(m.cuda(), weight=torch.linspace(0.5, 1.5, NC), lr=lr)
+    dev = [(x.cuda(), y.cuda()) for x, y in data]
+    return np.array([float(tr.train_step(*dev[i % len(dev)])) for i in range(steps)])
+
+
+def test_bf16_loss_curve_tracks_fp32_within_1_percent_over_200_steps():
+    data = _data(16, 4, 128, 256)
+    ref = _run("fp32", data, 200)   # the reference's optimiser settings: Adam lr 1e-4, eps 1e-4, wd 1e-6 (train/main.py:43-46)
+    got = _run("bf16", data, 200)
+    assert ref[-20:].mean() < 0.97 * ref[:20].mean(), "the synthetic task should be learnable"
+    # compare smoothed curves (window 10): single-step losses differ by batch noise, the curve must track
+    k = np.ones(10) / 10
+    rs, gs = np.convolve(ref, k, "valid"), np.convolve(got, k, "valid")
+    rel = np.abs(gs - rs) / rs
+    print(f"loss {ref[0]:.3f} -> {ref[-1]:.3f} (fp32), {got[0]:.3f} -> {got[-1]:.3f} (bf16); max smoothed rel dev {rel.max():.4f}")
+    assert rel.max() < 0.01, rel.max()
+
+
+def test_fp32_training_tracks_cpu_oracle_10_steps():
+    data = _data(2, 2, 64, 128, seed=3)
+    got = _run("fp32", data, 10, seed=2)
+    sd = O.make_state_dict(O.erfnet_param_shapes(NC), 2)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in params.items()}
+    wv = torch.linspace(0.5, 1.5, NC)
+    ref = []
+    for i in range(10):
+        x, y = data[i % 2]
+        for p in params.values():
+            p.grad = None
+        loss = O.cross_entropy_2d(O.erfnet_forward(x, sd, training=True, dropprob=0.0), y, weight=wv)
+        loss.backward()
+        with torch.no_grad():
+            for k, p in params.items():
+                if p.grad is not None:
+                    O.adam_step(p, p.grad, m[k], v2[k], i + 1)
+        ref.append(float(loss))
+    np.testing.assert_allclose(got, np.array(ref), rtol=1e-2)
