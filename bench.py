@@ -173,7 +173,7 @@ def main():
     model.precision = args.precision
     model = model.to(dev)
     trainer = FlatAdamTrainer(model, weight=torch.linspace(0.5, 1.5, NC))
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("ERF_GRAPH_DDP", "1") == "1")
 
     # a pool of distinct batches larger than L2 (126 MB) so inputs are never L2-resident between steps
     pool = [synth_batch(torch, 100 * rank + i, B) for i in range(4)]

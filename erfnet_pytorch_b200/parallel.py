@@ -75,6 +75,7 @@ class FlatAdamTrainer:
         self._launched = [False, False, False]
         self._works = []
         self._graph, self._step_dev = None, None
+        self._hooks_enabled = True
         self.cuda = dev.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
         if self.world > 1:
@@ -102,6 +103,8 @@ class FlatAdamTrainer:
             self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def _hook(self, p):
+        if not self._hooks_enabled:
+            return
         b = self._param_bucket[p]
         self._pending[b] -= 1
         if self._pending[b] == 0:
@@ -154,7 +157,17 @@ class FlatAdamTrainer:
         if self._graph is not None and drop_scales is None:
             self._g_images.copy_(images, non_blocking=True)
             self._g_labels.copy_(labels, non_blocking=True)
-            self._graph.replay()
+            if isinstance(self._graph, tuple):
+                # N > 1: three graph segments with the (tiny) NCCL collectives launched eagerly between them
+                g1, g2, g3 = self._graph
+                g1.replay()                                                    # zero grads, forward, valid-pixel weight sum
+                dist.all_reduce(self._g_acc[0:1], op=dist.ReduceOp.SUM, group=self.pg)
+                g2.replay()                                                    # CE fwd+bwd, backward
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                dist.all_reduce(self._g_acc[1:2], op=dist.ReduceOp.SUM, group=self.pg)
+                g3.replay()                                                    # Adam, loss = lsum / wsum
+            else:
+                self._graph.replay()
             self.step_count += 1
             _erfnet.bump_weights_epoch()
             return self._g_loss
@@ -180,10 +193,32 @@ class FlatAdamTrainer:
                 self.loss_and_backward(self._g_images, self._g_labels)
                 self.optimizer_step()
         torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = self.loss_and_backward(self._g_images, self._g_labels)
-            self.optimizer_step()
+        if self.world > 1:
+            # NCCL collectives stay outside the graphs (8.27 MB of gradients + two scalars per step): capture the three
+            # compute segments between them, sharing one memory pool so that activations saved by segment 1 stay alive
+            self._hooks_enabled = False
+            c, w = self.num_classes, self.criterion.weight
+            self._g_acc = torch.zeros(2, device=dev, dtype=torch.float32)
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self.flat_g.zero_()
+                self._g_acc.zero_()
+                self.model.train()
+                logits = self.model.forward_nhwc(self._g_images)
+                ops.ce_weight_sum(self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1])
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
+                logits.backward(dlog)
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                self.optimizer_step()
+                loss = (self._g_acc[1:2] / self._g_acc[0:1]).reshape(())
+            self._hooks_enabled = True
+            graph = (g1, g2, g3)
+        else:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self.loss_and_backward(self._g_images, self._g_labels)
+                self.optimizer_step()
         for t, s_ in zip((self.flat_p, self.flat_m, self.flat_v, self._step_dev), snap):
             t.copy_(s_)
         for b, s_ in zip(self.model.buffers(), bufs):
