@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   }
 }
 
-// dw[t][ci][co] (+)= sum over CTAs of the partial accumulators
+// dw[co][ci][t] (the nn.Conv2d layout [Co,Ci,3,1] / [Co,Ci,1,3]) += sum over CTAs of the partial accumulators
 template <int C>
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
   constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
@@ -179,7 +179,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas,
   const float* src = ws + ((size_t)acc * 128 + row) * C + co;
   float s = 0.f;
   for (int b = 0; b < grid_ctas; ++b) s += src[(size_t)b * ACCS * 128 * C];
-  dw[i] += s;
+  dw[((size_t)co * C + ci) * 3 + t] += s;
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

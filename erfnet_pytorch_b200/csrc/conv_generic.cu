@@ -224,7 +224,7 @@ __global__ void conv_wgrad_kernel(const T* __restrict__ in, const T* __restrict_
 // TI x TJ register tile of dW (ci = ty*TI + i, co = tx*TJ + j) and the block flushes it with one atomic per element.
 template <typename T, int TI, int TJ>
 __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const T* __restrict__ in, const T* __restrict__ dout, float* __restrict__ dw,
-                                                               erf_conv_geom g, int px_per_block) {
+                                                               erf_conv_geom g, int px_per_block, int cin_real) {
   constexpr int CIN_S = 16 * TI, COUT_S = 16 * TJ, PXT = 32;
   __shared__ __align__(16) float xs[PXT][CIN_S];
   __shared__ __align__(16) float ds[PXT][COUT_S];
@@ -314,12 +314,19 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < TJ; ++j) {
       const int ci = ty * TI + i, co = tx * TJ + j;
-      if (ci < g.Cin && co < g.Cout && acc[i][j] != 0.f) atomicAdd(&dw[((size_t)tap * g.Cin + ci) * g.w_ld + co], acc[i][j]);
+      if (ci < g.Cin && co < g.Cout && acc[i][j] != 0.f) {
+        if (cin_real <= 0) {            // packed [(tap*Cin + ci)][w_ld]
+          atomicAdd(&dw[((size_t)tap * g.Cin + ci) * g.w_ld + co], acc[i][j]);
+        } else if (ci < cin_real) {     // torch parameter layout
+          const size_t o = g.transposed ? (((size_t)ci * g.Cout + co) * g.KH + ky) * g.KW + kx : (((size_t)co * cin_real + ci) * g.KH + ky) * g.KW + kx;
+          atomicAdd(&dw[o], acc[i][j]);
+        }
+      }
     }
 }
 
 template <typename T>
-static bool launch_wgrad_tiled(const T* in, const T* dout, float* dw, const erf_conv_geom& g, cudaStream_t s) {
+static bool launch_wgrad_tiled(const T* in, const T* dout, float* dw, const erf_conv_geom& g, cudaStream_t s, int cin_real = 0) {
   const int ti = g.Cin <= 16 ? 1 : (g.Cin <= 32 ? 2 : (g.Cin <= 64 ? 4 : (g.Cin <= 128 ? 8 : 0)));
   const int tj = g.Cout <= 16 ? 1 : (g.Cout <= 32 ? 2 : (g.Cout <= 64 ? 4 : (g.Cout <= 128 ? 8 : 0)));
   if (!ti || !tj) return false;
@@ -331,7 +338,7 @@ static bool launch_wgrad_tiled(const T* in, const T* dout, float* dw, const erf_
   if (ppb < 256) ppb = 256;
   dim3 grid((unsigned)((total + ppb - 1) / ppb), taps);
 #define WG_CASE(TI_, TJ_) \
-  if (ti == TI_ && tj == TJ_) { conv_wgrad_tiled_kernel<T, TI_, TJ_><<<grid, 256, 0, s>>>(in, dout, dw, g, (int)ppb); return true; }
+  if (ti == TI_ && tj == TJ_) { conv_wgrad_tiled_kernel<T, TI_, TJ_><<<grid, 256, 0, s>>>(in, dout, dw, g, (int)ppb, cin_real); return true; }
   WG_CASE(1, 1) WG_CASE(1, 2) WG_CASE(1, 4) WG_CASE(1, 8) WG_CASE(2, 1) WG_CASE(2, 2) WG_CASE(2, 4) WG_CASE(2, 8)
   WG_CASE(4, 1) WG_CASE(4, 2) WG_CASE(4, 4) WG_CASE(4, 8) WG_CASE(8, 1) WG_CASE(8, 2) WG_CASE(8, 4) WG_CASE(8, 8)
 #undef WG_CASE
@@ -450,5 +457,22 @@ extern "C" int erf_channel_sum(const void* x, int ld, int coff, int C, long long
   else
     channel_sum_kernel<__nv_bfloat16><<<cgrid, 256, smem, s>>>((const __nv_bfloat16*)x, ld, coff, C, n_px, (int)cppb, out);
   ERF_CHECK_LAUNCH("erf_channel_sum");
+  return ERF_OK;
+}
+
+extern "C" int erf_conv_wgrad_torch(const void* in, const void* dout, float* dw, float* db, const erf_conv_geom* g, int cin_real, int dtype,
+                                    erf_stream_t stream) {
+  if (int rc = check_geom(g, "erf_conv_wgrad_torch")) return rc;
+  ERF_CHECK_ARG(in && dout && dw && cin_real > 0 && cin_real <= g->Cin, "erf_conv_wgrad_torch: bad arguments");
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_conv_wgrad_torch: bad dtype %d", dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool done = dtype == ERF_F32 ? launch_wgrad_tiled<float>((const float*)in, (const float*)dout, dw, *g, s, cin_real)
+                               : launch_wgrad_tiled<__nv_bfloat16>((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, dw, *g, s, cin_real);
+  if (!done) {
+    set_error("erf_conv_wgrad_torch: unsupported channel counts Cin=%d Cout=%d (<= 128 each)", g->Cin, g->Cout);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  ERF_CHECK_LAUNCH("erf_conv_wgrad_torch");
+  if (db) return erf_channel_sum(dout, g->out_ld, g->out_coff, g->Cout, (long long)g->N * g->Ho * g->Wo, db, dtype, stream);
   return ERF_OK;
 }

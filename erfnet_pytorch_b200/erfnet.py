@@ -111,6 +111,39 @@ class _B200Module(nn.Module):
         return _ToNCHW.apply(y, self._out_c)
 
 
+_GRAD_SINK = None   # set by parallel.FlatAdamTrainer while it runs backward: gradients are then accumulated by the kernels
+                    # straight into the parameters' pre-assigned .grad views (no zero-fill / permute / AccumulateGrad launches)
+
+
+def _sink(p):
+    return p.grad if (_GRAD_SINK is not None and p.grad is not None) else None
+
+
+def _sunk(*params):
+    if _GRAD_SINK is not None:
+        for p in params:
+            if p.grad is not None:
+                _GRAD_SINK.ready(p)
+
+
+def _ret(p, g):
+    """What autograd gets for parameter p: nothing if the kernel already accumulated into p.grad."""
+    return None if _sink(p) is not None else g
+
+
+def _stats_buf(bn, device):
+    """Persistent zeroed fp64 [2C] statistics accumulator of a BatchNorm (erf_bn_finalize resets it after use)."""
+    b = bn.__dict__.get("_erf_stats")
+    if b is None or b.device != device:
+        b = bn.__dict__["_erf_stats"] = torch.zeros(2 * bn.num_features, device=device, dtype=torch.float64)
+    return b
+
+
+def _tick(bn):
+    if not bn.__dict__.get("_erf_nbt_managed", False):
+        bn.num_batches_tracked += 1
+
+
 _WEIGHTS_EPOCH = 0  # bumped by code that updates parameters through aliases torch's version counters cannot see
 
 
@@ -191,26 +224,29 @@ class DownsamplerBlock(_B200Module):
         n, h, w, _ = x.shape
         cc = self.noutput - self.ninput
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
-        stats = torch.zeros(2 * self.noutput, device=x.device, dtype=torch.float64)
+        stats = _stats_buf(self.bn, x.device)
         ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                      out=y_raw, stats=stats)
         ops.maxpool_fwd(x, self.ninput, y_raw, cc, stats=stats)
         mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
                                                      self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
-        self.bn.num_batches_tracked += 1
+        _tick(self.bn)
         y = ops.affine_act(y_raw, scale, shift, relu=True)
         return y, (x, y_raw, y, mean, invstd)
 
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
-        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, self.bn.weight.detach(), mean, invstd, mask=y)
-        dwp, db = ops.conv_wgrad(x, dyr, self.spec)
+        cw, cb, gw, gb = self._train_params()
+        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+        dw, db = ops.conv_wgrad(x, dyr, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
         dx = None
         if need_dx:
             n, h, w, _ = x.shape
-            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(self.conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=(h, w))
+            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=(h, w))
             ops.maxpool_bwd(x, self.ninput, dyr, self.noutput - self.ninput, dx)
-        return dx, (ops.unpack_wgrad(dwp, self.spec), db, dgamma, dbeta)
+        grads = (_ret(cw, dw), _ret(cb, db), _ret(gw, dgamma), _ret(gb, dbeta))
+        _sunk(cw, cb, gw, gb)
+        return dx, grads
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -310,19 +346,19 @@ class non_bottleneck_1d(_B200Module):
             wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         bs = [m.bias.detach().float() for m in cv]
         count = n * h * w
-        st = torch.zeros(2, 2 * c, device=x.device, dtype=torch.float64)
+        st = (_stats_buf(self.bn1, x.device), _stats_buf(self.bn2, x.device))
         t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
         y2 = self._conv(1, t1, wp[1], bs[1], tc, stats=st[0])
         mean1, invstd1, sc1, sh1 = ops.bn_finalize(st[0], count, self.bn1.weight.detach(), self.bn1.bias.detach(), self.bn1.running_mean,
                                                    self.bn1.running_var, BN_MOMENTUM, BN_EPS)
-        self.bn1.num_batches_tracked += 1
+        _tick(self.bn1)
         a2 = ops.affine_act(y2, sc1, sh1, relu=True)
         t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True)
         y4 = self._conv(3, t3, wp[3], bs[3], tc, stats=st[1])
         drop = self._drop_scale(x, ctx)
         mean2, invstd2, sc2, sh2 = ops.bn_finalize(st[1], count, self.bn2.weight.detach(), self.bn2.bias.detach(), self.bn2.running_mean,
                                                    self.bn2.running_var, BN_MOMENTUM, BN_EPS, drop=drop)
-        self.bn2.num_batches_tracked += 1
+        _tick(self.bn2)
         out = ops.affine_act(y4, sc2, sh2, res=x, relu=True)
         return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, pairs)
 
@@ -336,26 +372,28 @@ class non_bottleneck_1d(_B200Module):
             wd = [pr[1] for pr in pairs] if pairs is not None else [ops.pack_conv1d_tc(m.weight.detach(), dgrad=True) for m in cv]
         else:
             wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
-        dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, self.bn2.weight.detach(), mean2, invstd2, mask=out, drop=drop)
-        dw4, db4 = self._wgrad(3, t3, dy4, tc)
+        P = self._train_params()  # w1,b1,w2,b2,g1,be1,w3,b3,w4,b4,g2,be2
+        dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]), dbeta_out=_sink(P[11]))
+        dw4, db4 = self._wgrad(3, t3, dy4, tc, P[8], P[9])
         dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3])
-        dw3, db3 = self._wgrad(2, a2, dt3, tc)
+        dw3, db3 = self._wgrad(2, a2, dt3, tc, P[6], P[7])
         da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2])
-        dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, self.bn1.weight.detach(), mean1, invstd1, mask=a2)
-        dw2, db2 = self._wgrad(1, t1, dy2, tc)
+        dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, P[4].detach(), mean1, invstd1, mask=a2, dgamma_out=_sink(P[4]), dbeta_out=_sink(P[5]))
+        dw2, db2 = self._wgrad(1, t1, dy2, tc, P[2], P[3])
         dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1])
-        dw1, db1 = self._wgrad(0, x, dt1, tc)
+        dw1, db1 = self._wgrad(0, x, dt1, tc, P[0], P[1])
         dx = None
         if need_dx:
             gres = ops.relu_bwd(dout, out)
             dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
-        return dx, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)
+        grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)))
+        _sunk(*P)
+        return dx, grads
 
-    def _wgrad(self, i, x, dy, tc):
+    def _wgrad(self, i, x, dy, tc, wparam, bparam):
         if tc and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype):
-            return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated)
-        dwp, db = ops.conv_wgrad(x, dy, self.specs[i])
-        return ops.unpack_wgrad(dwp, self.specs[i]), db
+            return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, dw_out=_sink(wparam), db_out=_sink(bparam))
+        return ops.conv_wgrad(x, dy, self.specs[i], dw_out=_sink(wparam), db_out=_sink(bparam))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -391,26 +429,27 @@ class UpsamplerBlock(_B200Module):
     def _fwd_train(self, x, ctx):
         if not self.use_batchnorm:
             raise RuntimeError("training with use_batchnorm=False is not implemented yet")
-        c = self.spec.cout
-        stats = torch.zeros(2 * c, device=x.device, dtype=torch.float64)
+        stats = _stats_buf(self.bn, x.device)
         y_raw = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                              stats=stats)
         count = y_raw.shape[0] * y_raw.shape[1] * y_raw.shape[2]
         mean, invstd, scale, shift = ops.bn_finalize(stats, count, self.bn.weight.detach(), self.bn.bias.detach(), self.bn.running_mean,
                                                      self.bn.running_var, BN_MOMENTUM, BN_EPS)
-        self.bn.num_batches_tracked += 1
+        _tick(self.bn)
         y = ops.affine_act(y_raw, scale, shift, relu=True)
         return y, (x, y_raw, y, mean, invstd)
 
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
-        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, self.bn.weight.detach(), mean, invstd, mask=y)
-        dwp, db = ops.conv_wgrad(x, dyr, self.spec)
+        cw, cb, gw, gb = self._train_params()
+        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+        dw, db = ops.conv_wgrad(x, dyr, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
         dx = None
         if need_dx:
-            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(self.conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec),
-                              out_hw=x.shape[1:3])
-        return dx, (ops.unpack_wgrad(dwp, self.spec), db, dgamma, dbeta)
+            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
+        grads = (_ret(cw, dw), _ret(cb, db), _ret(gw, dgamma), _ret(gb, dbeta))
+        _sunk(cw, cb, gw, gb)
+        return dx, grads
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -449,12 +488,14 @@ class _PlainConv:
 
     def _bwd(self, dy, saved, need_dx):
         (x,) = saved
-        dwp, db = ops.conv_wgrad(x, dy, self.spec)
+        cw, cb = self._train_params()
+        dw, db = ops.conv_wgrad(x, dy, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
         dx = None
         if need_dx:
-            dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(self._conv.weight.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec),
-                              out_hw=x.shape[1:3])
-        return dx, (ops.unpack_wgrad(dwp, self.spec), db)
+            dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
+        grads = (_ret(cw, dw), _ret(cb, db))
+        _sunk(cw, cb)
+        return dx, grads
 
 
 # ---------------------------------------------------------------------------------------------------------------

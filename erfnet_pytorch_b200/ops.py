@@ -173,16 +173,20 @@ def conv_fwd(x: torch.Tensor, wp: torch.Tensor, spec: ConvSpec, bias: Optional[t
     return out
 
 
-def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0, want_bias=True):
-    """Returns (dw_packed fp32 [(taps*cin_p), w_ld], db fp32 [cout] or None)."""
-    dw = torch.zeros(spec.kh * spec.kw * spec.cin_p, spec.w_ld, device=x.device, dtype=torch.float32)
-    db = torch.zeros(spec.cout, device=x.device, dtype=torch.float32) if want_bias else None
+def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0, dw_out=None, db_out=None):
+    """Weight / bias gradient in the TORCH parameter layout, accumulated into dw_out / db_out (e.g. views of a flat
+    gradient buffer) or into fresh zero tensors.  Returns (dw, db)."""
+    if dw_out is None:
+        shape = (spec.cin, spec.cout, spec.kh, spec.kw) if spec.transposed else (spec.cout, spec.cin, spec.kh, spec.kw)
+        dw_out = torch.zeros(shape, device=x.device, dtype=torch.float32)
+    if db_out is None:
+        db_out = torch.zeros(spec.cout, device=x.device, dtype=torch.float32)
     g = _geom(spec, x, dout, dout_coff)
-    with _timed(f"conv_wgrad_kernel[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_kernel",
-                conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
-        check(_lib.lib().erf_conv_wgrad(_p(x), _p(dout), _p(dw), _p(db), C.byref(g), dt(x), _stream(x)))
-    _count(2 if want_bias else 1)
-    return dw, db
+    name = f"conv_wgrad_kernel[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_kernel"
+    with _timed(name, conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
+        check(_lib.lib().erf_conv_wgrad_torch(_p(x), _p(dout), _p(dw_out), _p(db_out), C.byref(g), spec.cin, dt(x), _stream(x)))
+    _count(2)
+    return dw_out, db_out
 
 
 def conv1d_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
@@ -236,26 +240,26 @@ def conv1d_wgrad_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
     return dtype == torch.bfloat16 and not EMULATED and c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
 
 
-def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, want_bias=True):
-    """Weight (torch layout [Co,Ci,3,1] / [Co,Ci,1,3], fp32) and bias gradients of a 3-tap conv on the tensor cores."""
+def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, dw_out=None, db_out=None):
+    """Weight (torch layout [Co,Ci,3,1] / [Co,Ci,1,3], fp32) and bias gradients of a 3-tap conv on the tensor cores,
+    accumulated into dw_out / db_out (e.g. the parameters' .grad views) or into fresh zero tensors."""
     n, h, w, c = x.shape
     L = _lib.lib()
     nbytes = L.erf_conv1d_wgrad_tc_workspace(c)
     ws = _WS.get((x.device, nbytes))
     if ws is None:
         ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
-    dw = torch.zeros(3, c, c, device=x.device, dtype=torch.float32)
+    if dw_out is None:
+        dw_out = torch.zeros((c, c, 1, 3) if horizontal else (c, c, 3, 1), device=x.device, dtype=torch.float32)
+    if db_out is None:
+        db_out = torch.zeros(c, device=x.device, dtype=torch.float32)
     with _timed("conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
-        check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
+        check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
     _count(2)
-    db = None
-    if want_bias:
-        db = torch.zeros(c, device=x.device, dtype=torch.float32)
-        with _timed("channel_sum"):
-            check(L.erf_channel_sum(_p(dy), c, 0, c, n * h * w, _p(db), dt(dy), _stream(dy)))
-        _count()
-    dwt = dw.permute(2, 1, 0)  # [co][ci][t]
-    return (dwt.reshape(c, c, 1, 3) if horizontal else dwt.reshape(c, c, 3, 1)).contiguous(), db
+    with _timed("channel_sum"):
+        check(L.erf_channel_sum(_p(dy), c, 0, c, n * h * w, _p(db_out), dt(dy), _stream(dy)))
+    _count()
+    return dw_out, db_out
 
 
 def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
@@ -337,16 +341,24 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
     return scale, shift
 
 
-def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
-    """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c]."""
+_BN_SUMS = {}  # (device, C) -> fp64 [2C] scratch for the BN-backward reductions
+
+
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None):
+    """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c].
+    dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step)."""
     n, h, w, c = y.shape
-    sums = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
+    sums = _BN_SUMS.get((y.device, c))
+    if sums is None:
+        sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
+    else:
+        sums.zero_()
     L = _lib.lib()
     check(L.erf_bn_bwd_reduce(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(mean), _p(invstd),
                               n, h * w, c, _p(sums), dt(y), _stream(y)))
     dy = torch.empty_like(y)
-    dgamma = torch.empty(c, device=y.device, dtype=torch.float32)
-    dbeta = torch.empty(c, device=y.device, dtype=torch.float32)
+    dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
+    dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
     check(L.erf_bn_bwd_apply(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(gamma), _p(mean),
                              _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), dt(y), _stream(y)))
     _count(2)

@@ -71,11 +71,19 @@ class FlatAdamTrainer:
             self._bucket_params[b] += 1
             self._param_bucket[p] = b
             off += n
+        # all BatchNorm step counters in one int64 tensor: one increment per step instead of 39
+        bns = [mod for mod in model.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+        self.flat_nbt = torch.zeros(len(bns), device=dev, dtype=torch.int64)
+        for i, bn in enumerate(bns):
+            self.flat_nbt[i] = bn.num_batches_tracked
+            bn.num_batches_tracked = self.flat_nbt[i]       # a 0-dim view: state_dict() keeps reporting it
+            bn.__dict__["_erf_nbt_managed"] = True
         self._pending = list(self._bucket_params)
         self._launched = [False, False, False]
         self._works = []
         self._graph, self._step_dev = None, None
         self._hooks_enabled = True
+        self._seen = set()
         self.cuda = dev.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
         if self.world > 1:
@@ -102,9 +110,15 @@ class FlatAdamTrainer:
         else:
             self._works.append(dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
+    def ready(self, p):
+        """Called by the blocks' backward once the kernels have accumulated p's gradient into p.grad (gradient sink)."""
+        self._hook(p)
+
     def _hook(self, p):
-        if not self._hooks_enabled:
+        # reached both from autograd's post-accumulate hook and from the gradient sink: count each parameter once per step
+        if not self._hooks_enabled or p in self._seen:
             return
+        self._seen.add(p)
         b = self._param_bucket[p]
         self._pending[b] -= 1
         if self._pending[b] == 0:
@@ -120,11 +134,13 @@ class FlatAdamTrainer:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self._pending = list(self._bucket_params)
         self._launched = [False, False, False]
+        self._seen = set()
 
     # ---- one step ---------------------------------------------------------------------------------------------
     def loss_and_backward(self, images, labels, drop_scales=None):
         """images NCHW fp32, labels int64 [B,H,W] on the model's device.  Returns the GLOBAL-batch loss (0-dim tensor)."""
         self.flat_g.zero_()
+        self.flat_nbt.add_(1)
         self.model.train()
         logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
         c = self.num_classes
@@ -137,11 +153,18 @@ class FlatAdamTrainer:
         if self.world > 1:
             dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=self.pg)
         dlog = ops.ce_fwd_bwd(logits.detach(), labels, w, c, self.criterion.ignore_index, wsum, lsum)
-        logits.backward(dlog)
+        self._backward(logits, dlog)
         self._finish_buckets()
         if self.world > 1:
             dist.all_reduce(lsum, op=dist.ReduceOp.SUM, group=self.pg)
         return (lsum / wsum).reshape(())
+
+    def _backward(self, logits, dlog):
+        _erfnet._GRAD_SINK = self
+        try:
+            logits.backward(dlog)
+        finally:
+            _erfnet._GRAD_SINK = None
 
     def optimizer_step(self):
         self.step_count += 1
@@ -202,13 +225,14 @@ class FlatAdamTrainer:
             g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 self.flat_g.zero_()
+                self.flat_nbt.add_(1)
                 self._g_acc.zero_()
                 self.model.train()
                 logits = self.model.forward_nhwc(self._g_images)
                 ops.ce_weight_sum(self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1])
             with torch.cuda.graph(g2, pool=g1.pool()):
                 dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
-                logits.backward(dlog)
+                self._backward(logits, dlog)
             with torch.cuda.graph(g3, pool=g1.pool()):
                 self.optimizer_step()
                 loss = (self._g_acc[1:2] / self._g_acc[0:1]).reshape(())

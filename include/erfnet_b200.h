@@ -74,6 +74,10 @@ int erf_conv_fwd(const void* in, const void* w, void* out, const erf_conv_geom* 
  * dw: fp32 [(KH*KW)*Cin][w_ld], db: fp32 [Cout] or NULL; both are ACCUMULATED into (caller zeroes). */
 int erf_conv_wgrad(const void* in, const void* dout, float* dw, float* db, const erf_conv_geom* g, int dtype,
                    erf_stream_t stream);
+/* Same, but dw is ACCUMULATED in the torch parameter layout: nn.Conv2d [Cout][cin_real][KH][KW] (g->transposed == 0) or
+ * nn.ConvTranspose2d [cin_real][Cout][KH][KW] (g->transposed == 1); input channels >= cin_real (padding) are dropped. */
+int erf_conv_wgrad_torch(const void* in, const void* dout, float* dw, float* db, const erf_conv_geom* g, int cin_real,
+                         int dtype, erf_stream_t stream);
 
 /* ---- MaxPool2d(2, stride 2) half of DownsamplerBlock (eval/erfnet.py:17,21) ------------------------------ */
 /* out = relu?(max2x2(in)*scale[c] + shift[c]); scale/shift NULL = identity; stats (of the raw max) as in erf_conv_epilogue */
@@ -167,8 +171,8 @@ int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* ou
  * [Co,Ci,3,1] or [Co,Ci,1,3], contiguous) for erf_conv1d_tc; each image is 3*C*C bf16. */
 int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream);
 
-/* tcgen05 weight gradient of the same convolutions: dw[t][ci][co] += sum_p x[p + (t-1)*dil][ci] * dy[p][co]  (fp32,
- * [3][C][C]; caller zeroes).  Both NHWC operands are consumed MN-major; per-CTA TMEM accumulators are dumped to
+/* tcgen05 weight gradient of the same convolutions: dw[co][ci][t] += sum_p x[p + (t-1)*dil][ci] * dy[p][co]  (fp32, in
+ * the nn.Conv2d weight layout [Co,Ci,3,1] == [Co,Ci,1,3]; ACCUMULATED, e.g. straight into the parameter's .grad).  Both NHWC operands are consumed MN-major; per-CTA TMEM accumulators are dumped to
  * `workspace` (>= erf_conv1d_wgrad_tc_workspace(C) bytes, caller-owned) and reduced by a second kernel.  W % 64 == 0. */
 size_t erf_conv1d_wgrad_tc_workspace(int C);
 int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W,

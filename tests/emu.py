@@ -53,7 +53,7 @@ def conv_fwd(x, wp, spec, bias=None, relu=False, out=None, out_coff=0, mask=None
 
 
 @torch.enable_grad()
-def conv_wgrad(x, dout, spec, dout_coff=0, want_bias=True):
+def conv_wgrad(x, dout, spec, dout_coff=0, dw_out=None, db_out=None):
     n, h, w, _ = x.shape
     xi = x[..., :spec.cin_p].detach().float().permute(0, 3, 1, 2)
     wt = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.cout, requires_grad=True)
@@ -66,10 +66,12 @@ def conv_wgrad(x, dout, spec, dout_coff=0, want_bias=True):
         base_w = (w - 1) * spec.stride - 2 * spec.pad_w + spec.dil_w * (spec.kw - 1) + 1
         y = F.conv_transpose2d(xi, wt.permute(2, 3, 0, 1), None, spec.stride, (spec.pad_h, spec.pad_w), (ho - base_h, wo - base_w), 1,
                                (spec.dil_h, spec.dil_w))
-    (g,) = torch.autograd.grad(y, wt, dy)
-    dw = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.w_ld)
-    dw[..., :spec.cout] = g
-    return dw.reshape(-1, spec.w_ld), (dy.sum((0, 2, 3)) if want_bias else None)
+    (g,) = torch.autograd.grad(y, wt, dy)   # [kh,kw,ci,co]
+    g = g[:, :, :spec.cin]
+    gt = g.permute(2, 3, 0, 1) if spec.transposed else g.permute(3, 2, 0, 1)
+    dw = gt.contiguous() if dw_out is None else dw_out.add_(gt)
+    db = dy.sum((0, 2, 3)) if db_out is None else db_out.add_(dy.sum((0, 2, 3)))
+    return dw, db
 
 
 def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
@@ -150,7 +152,7 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
     return sc, beta - rm * sc
 
 
-def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None):
     gb = g.float()
     if mask is not None:
         gb = gb * (mask.float() > 0)
@@ -161,6 +163,10 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None):
     s1 = gb.double().sum((0, 1, 2)).float()
     s2 = (gb * xh).double().sum((0, 1, 2)).float()
     dy = gamma * invstd * (gb - s1 / m - xh * s2 / m)
+    if dgamma_out is not None:
+        dgamma_out.copy_(s2)
+        dbeta_out.copy_(s1)
+        return dy.to(y.dtype), dgamma_out, dbeta_out
     return dy.to(y.dtype), s2, s1
 
 
