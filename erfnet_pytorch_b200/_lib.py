@@ -47,7 +47,7 @@ _SIGNATURES = {
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "erf_adam_step_dev": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
-    "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "erf_pack_conv1d_tc": [_vp, _i, _vp, _vp, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],

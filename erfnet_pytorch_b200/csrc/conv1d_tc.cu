@@ -39,7 +39,25 @@ struct Conv1dTcParams {
   int slots;                    // A ring depth
   int slot_bytes;               // bytes per ring slot (multiple of 1024)
   int sub_bytes;                // pitch of one k-chunk sub-tile inside a slot
+  double* stats;                // [2C] += per-channel sum / sum of squares of the stored output (BN batch statistics), or null
+  float* colsum;                // [C]  += per-channel sum of the stored output (bias gradient of the producing conv), or null
 };
+
+// Transposed warp reduction: every lane holds 32 values v[0..31] (one pixel, 32 channels); on return lane j holds the sum
+// over the 32 lanes of v[j].  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
 
 constexpr int kMaxSlots = 8;
 constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups
@@ -204,6 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     const uint32_t acc = grp;                  // accumulator owned by this group
     uint32_t acc_phase = 0, aux_phase[2] = {0, 0};
     int step = 0;                              // staging steps (unit, k-chunk) done by this group
+    constexpr int NCH = C >= 32 ? C / 32 : 1;  // 32-column chunks per pixel row
+    float red_sum[NCH], red_sq[NCH];           // this lane's column of each chunk, accumulated over all units of the CTA
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) red_sum[i] = red_sq[i] = 0.f;
+    const bool want_red = (p.stats != nullptr || p.colsum != nullptr) && EW == 32;
     // units of this CTA alternate between the two groups
     const int u_first = blockIdx.x + grp * gridDim.x, u_stride = 2 * gridDim.x;
     if (leader && p.aux_mode && u_first < p.units) {   // aux prefetch for the very first step
@@ -277,8 +300,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
             uint4 t;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) {
+              h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+              // statistics are taken over the values as STORED (bf16), which is what the consumer normalises
+              v[q * 8 + 2 * e] = __low2float(h[e]);
+              v[q * 8 + 2 * e + 1] = __high2float(h[e]);
+            }
             *reinterpret_cast<uint4*>(my_row + (((j0 + q) ^ sw_key) * 16)) = t;
+          }
+          if constexpr (EW == 32) {
+            if (want_red) {
+              const int ch = (kc * CH + c0) / 32;
+              if (p.stats) {
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                red_sq[ch] += warp_colsum32(sq, lane);
+              }
+              red_sum[ch] += warp_colsum32(v, lane);
+            }
           }
         }
         fence_proxy_async_smem();              // staging writes -> visible to the TMA store
@@ -300,6 +340,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait0();
+    if (want_red) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = i * 32 + lane;
+        if (p.stats) {
+          atomicAdd(&p.stats[c], (double)red_sum[i]);
+          atomicAdd(&p.stats[C + c], (double)red_sq[i]);
+        }
+        if (p.colsum) atomicAdd(&p.colsum[c], red_sum[i]);
+      }
+    }
   }
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();
@@ -347,10 +398,11 @@ extern "C" int erf_conv1d_tc_supported(int C, int W, int dil) {
 }
 
 extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask, int N, int H, int W,
-                             int C, int horizontal, int dil, int relu, erf_stream_t stream) {
+                             int C, int horizontal, int dil, int relu, double* stats, float* colsum, erf_stream_t stream) {
   ERF_CHECK_ARG(in && w_img && out, "erf_conv1d_tc: null pointer");
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_tc: empty tensor");
   ERF_CHECK_ARG(!(res && mask), "erf_conv1d_tc: res and mask are mutually exclusive");
+  ERF_CHECK_ARG(!(stats || colsum) || C >= 64, "erf_conv1d_tc: fused statistics need C >= 64 (use erf_channel_stats / erf_channel_sum for C = %d)", C);
   if (!erf_conv1d_tc_supported(C, W, dil)) {
     set_error("erf_conv1d_tc: unsupported shape C=%d W=%d dil=%d (need C in {16,64,128}, W %% 128 == 0, dil <= 32)", C, W, dil);
     return ERF_ERR_UNSUPPORTED;
@@ -370,6 +422,8 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.N = N; p.H = H; p.W = W;
   p.horizontal = horizontal; p.dil = dil; p.relu = relu;
   p.aux_mode = res ? 1 : (mask ? 2 : 0);
+  p.stats = stats;
+  p.colsum = colsum;
   p.units = N * H * (W / 128);
   if (horizontal) {
     p.sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;

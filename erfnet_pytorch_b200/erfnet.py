@@ -322,14 +322,17 @@ class non_bottleneck_1d(_B200Module):
         return (self.chann in (16, 64, 128) and ops.USE_TC and ops.conv1d_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
                 and ops.conv1d_tc_supported(self.chann, x.shape[2], 1, x.dtype))
 
-    def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None):
-        """conv i (0..3) of the block (or its data gradient when spec is a dgrad spec) on the tcgen05 or the generic kernel."""
+    def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None, colsum=None):
+        """conv i (0..3) of the block (or its data gradient when spec is a dgrad spec) on the tcgen05 or the generic kernel.
+        colsum: fp32 [C] that receives the per-channel sum of the result (= bias gradient of the conv that produced the
+        tensor this gradient belongs to)."""
         if tc:
-            y = ops.conv1d_tc(x, w, bias, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, relu=relu, res=add, mask=mask)
-            if stats is not None:
-                ops.channel_stats(y, stats)
-            return y
-        return ops.conv_fwd(x, w, spec or self.specs[i], bias, relu=relu, stats=stats, mask=mask, add=add, out_hw=x.shape[1:3])
+            return ops.conv1d_tc(x, w, bias, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, relu=relu, res=add, mask=mask,
+                                 stats=stats, colsum=colsum)
+        y = ops.conv_fwd(x, w, spec or self.specs[i], bias, relu=relu, stats=stats, mask=mask, add=add, out_hw=x.shape[1:3])
+        if colsum is not None:
+            ops.channel_sum(y, colsum)
+        return y
 
     def _fwd_train(self, x, ctx):
         if not self.use_batchnorm:
@@ -373,15 +376,25 @@ class non_bottleneck_1d(_B200Module):
         else:
             wd = [ops.pack_weight_dgrad(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         P = self._train_params()  # w1,b1,w2,b2,g1,be1,w3,b3,w4,b4,g2,be2
+        dev = x.device
+
+        def bias_dst(p):
+            d = _sink(p)
+            return d if d is not None else torch.zeros(self.chann, device=dev, dtype=torch.float32)
+
+        # The biases of conv1x3_1 / conv1x3_2 feed a train-mode BatchNorm: their gradient sum_p dy is EXACTLY zero
+        # (sum_p xhat = 0), the reference only ever sees its rounding noise (~1e-9, far below Adam's eps = 1e-4) -> no kernel.
+        db2 = db4 = None if (_sink(P[3]) is not None) else torch.zeros(self.chann, device=dev, dtype=torch.float32)
+        db1, db3 = bias_dst(P[1]), bias_dst(P[7])
         dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]), dbeta_out=_sink(P[11]))
-        dw4, db4 = self._wgrad(3, t3, dy4, tc, P[8], P[9])
-        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3])
-        dw3, db3 = self._wgrad(2, a2, dt3, tc, P[6], P[7])
+        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
+        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3)     # grad wrt conv3x1_2's output
+        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
         da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2])
         dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, P[4].detach(), mean1, invstd1, mask=a2, dgamma_out=_sink(P[4]), dbeta_out=_sink(P[5]))
-        dw2, db2 = self._wgrad(1, t1, dy2, tc, P[2], P[3])
-        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1])
-        dw1, db1 = self._wgrad(0, x, dt1, tc, P[0], P[1])
+        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
+        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1)     # grad wrt conv3x1_1's output
+        dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
         dx = None
         if need_dx:
             gres = ops.relu_bwd(dout, out)
@@ -390,10 +403,11 @@ class non_bottleneck_1d(_B200Module):
         _sunk(*P)
         return dx, grads
 
-    def _wgrad(self, i, x, dy, tc, wparam, bparam):
+    def _wgrad(self, i, x, dy, tc, wparam):
+        """Weight gradient only (the bias gradients come from the data-gradient epilogues, see _bwd)."""
         if tc and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype):
-            return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, dw_out=_sink(wparam), db_out=_sink(bparam))
-        return ops.conv_wgrad(x, dy, self.specs[i], dw_out=_sink(wparam), db_out=_sink(bparam))
+            return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, dw_out=_sink(wparam), want_bias=False)
+        return ops.conv_wgrad(x, dy, self.specs[i], dw_out=_sink(wparam), want_bias=False)
 
 
 # ---------------------------------------------------------------------------------------------------------------

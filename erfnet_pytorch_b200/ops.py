@@ -173,18 +173,18 @@ def conv_fwd(x: torch.Tensor, wp: torch.Tensor, spec: ConvSpec, bias: Optional[t
     return out
 
 
-def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0, dw_out=None, db_out=None):
+def conv_wgrad(x: torch.Tensor, dout: torch.Tensor, spec: ConvSpec, dout_coff=0, dw_out=None, db_out=None, want_bias=True):
     """Weight / bias gradient in the TORCH parameter layout, accumulated into dw_out / db_out (e.g. views of a flat
     gradient buffer) or into fresh zero tensors.  Returns (dw, db)."""
     if dw_out is None:
         shape = (spec.cin, spec.cout, spec.kh, spec.kw) if spec.transposed else (spec.cout, spec.cin, spec.kh, spec.kw)
         dw_out = torch.zeros(shape, device=x.device, dtype=torch.float32)
-    if db_out is None:
+    if db_out is None and want_bias:
         db_out = torch.zeros(spec.cout, device=x.device, dtype=torch.float32)
     g = _geom(spec, x, dout, dout_coff)
     name = f"conv_wgrad_kernel[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_kernel"
     with _timed(name, conv_flops(spec, x.shape[0], dout.shape[1], dout.shape[2])):
-        check(_lib.lib().erf_conv_wgrad_torch(_p(x), _p(dout), _p(dw_out), _p(db_out), C.byref(g), spec.cin, dt(x), _stream(x)))
+        check(_lib.lib().erf_conv_wgrad_torch(_p(x), _p(dout), _p(dw_out), _p(db_out) if want_bias else None, C.byref(g), spec.cin, dt(x), _stream(x)))
     _count(2)
     return dw_out, db_out
 
@@ -223,13 +223,22 @@ def pack_conv1d_tc_pair(w: torch.Tensor):
 
 
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
-              res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+              res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+              colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated in the kernel epilogue for C >= 64, by a follow-up
+    bandwidth kernel for C = 16."""
     n, h, w, c = x.shape
     out = torch.empty_like(x)
+    fused = c >= 64
     with _timed("conv1d_tc_kernel", 2.0 * n * h * w * c * c * 3):
         check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu),
-                                       _stream(x)))
+                                       _p(stats) if fused else None, _p(colsum) if fused else None, _stream(x)))
     _count()
+    if not fused:
+        if stats is not None:
+            channel_stats(out, stats)
+        if colsum is not None:
+            channel_sum(out, colsum)
     return out
 
 
@@ -240,7 +249,7 @@ def conv1d_wgrad_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
     return dtype == torch.bfloat16 and not EMULATED and c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
 
 
-def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, dw_out=None, db_out=None):
+def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, dw_out=None, db_out=None, want_bias=True):
     """Weight (torch layout [Co,Ci,3,1] / [Co,Ci,1,3], fp32) and bias gradients of a 3-tap conv on the tensor cores,
     accumulated into dw_out / db_out (e.g. the parameters' .grad views) or into fresh zero tensors."""
     n, h, w, c = x.shape
@@ -251,14 +260,13 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
         ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     if dw_out is None:
         dw_out = torch.zeros((c, c, 1, 3) if horizontal else (c, c, 3, 1), device=x.device, dtype=torch.float32)
-    if db_out is None:
-        db_out = torch.zeros(c, device=x.device, dtype=torch.float32)
     with _timed("conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
         check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
     _count(2)
-    with _timed("channel_sum"):
-        check(L.erf_channel_sum(_p(dy), c, 0, c, n * h * w, _p(db_out), dt(dy), _stream(dy)))
-    _count()
+    if want_bias:
+        if db_out is None:
+            db_out = torch.zeros(c, device=x.device, dtype=torch.float32)
+        channel_sum(dy, db_out)
     return dw_out, db_out
 
 
@@ -306,6 +314,13 @@ def affine_act(x, scale=None, shift=None, res=None, relu=True, out=None):
 def channel_stats(x, stats):
     n, h, w, c = x.shape
     check(_lib.lib().erf_channel_stats(_p(x), c, c, n * h * w, _p(stats), dt(x), _stream(x)))
+    _count()
+
+
+def channel_sum(x, out):
+    """out[c] += sum over pixels of x[..., c]"""
+    n, h, w, c = x.shape
+    check(_lib.lib().erf_channel_sum(_p(x), c, 0, c, n * h * w, _p(out), dt(x), _stream(x)))
     _count()
 
 
@@ -465,7 +480,7 @@ def _wrap_timed(name):
     globals()[name] = wrapper
 
 
-for _n in ("channel_stats", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
+for _n in ("channel_stats", "channel_sum", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
            "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
            "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair"):
     _wrap_timed(_n)

@@ -53,7 +53,7 @@ def conv_fwd(x, wp, spec, bias=None, relu=False, out=None, out_coff=0, mask=None
 
 
 @torch.enable_grad()
-def conv_wgrad(x, dout, spec, dout_coff=0, dw_out=None, db_out=None):
+def conv_wgrad(x, dout, spec, dout_coff=0, dw_out=None, db_out=None, want_bias=True):
     n, h, w, _ = x.shape
     xi = x[..., :spec.cin_p].detach().float().permute(0, 3, 1, 2)
     wt = torch.zeros(spec.kh, spec.kw, spec.cin_p, spec.cout, requires_grad=True)
@@ -70,7 +70,9 @@ def conv_wgrad(x, dout, spec, dout_coff=0, dw_out=None, db_out=None):
     g = g[:, :, :spec.cin]
     gt = g.permute(2, 3, 0, 1) if spec.transposed else g.permute(3, 2, 0, 1)
     dw = gt.contiguous() if dw_out is None else dw_out.add_(gt)
-    db = dy.sum((0, 2, 3)) if db_out is None else db_out.add_(dy.sum((0, 2, 3)))
+    db = None
+    if want_bias:
+        db = dy.sum((0, 2, 3)) if db_out is None else db_out.add_(dy.sum((0, 2, 3)))
     return dw, db
 
 
@@ -124,6 +126,10 @@ def channel_stats(x, stats):
     c = x.shape[-1]
     stats[:c] += x.double().sum((0, 1, 2))
     stats[c:] += (x.double() ** 2).sum((0, 1, 2))
+
+
+def channel_sum(x, out):
+    out += x.float().sum((0, 1, 2))
 
 
 def relu_bwd(g, mask):
@@ -229,7 +235,7 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, gra
     adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, int(step_dev), grad_scale)
 
 
-_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "relu_bwd", "bn_finalize",
+_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "relu_bwd", "bn_finalize",
           "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev"]
 
 

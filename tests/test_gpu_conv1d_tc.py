@@ -33,6 +33,14 @@ def test_conv1d_tc_matches_fp32_conv(c, w, horizontal, dil):
     # plain conv + bias
     y = ops.conv1d_tc(xc, img, bc, horizontal, dil)
     assert_rel(y.float().cpu().numpy(), ref.numpy(), 1e-2, "conv+bias")
+    # fused epilogue reductions: BN statistics and column sums of the tensor as stored
+    stats = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
+    colsum = torch.zeros(c, device="cuda", dtype=torch.float32)
+    y = ops.conv1d_tc(xc, img, bc, horizontal, dil, stats=stats, colsum=colsum)
+    yf = y.double().cpu()
+    np.testing.assert_allclose(stats[:c].cpu().numpy(), yf.sum((0, 1, 2)).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(stats[c:].cpu().numpy(), (yf ** 2).sum((0, 1, 2)).numpy(), rtol=1e-4)
+    np.testing.assert_allclose(colsum.cpu().numpy(), yf.sum((0, 1, 2)).numpy(), rtol=1e-4, atol=1e-2)
     # residual + relu
     y = ops.conv1d_tc(xc, img, bc, horizontal, dil, relu=True, res=res.cuda())
     assert_rel(y.float().cpu().numpy(), (ref + res.float()).relu().numpy(), 1e-2, "res+relu")
