@@ -22,6 +22,16 @@ class ConvEpilogue(C.Structure):
                 ("add", C.c_void_p), ("add_ld", C.c_int), ("stats", C.c_void_p), ("stats_c", C.c_int)]
 
 
+class Im2colDesc(C.Structure):
+    _fields_ = ([("in_", C.c_void_p)] + [(n, C.c_int) for n in ("H", "W", "in_ld", "Cin", "EN", "EH", "EW", "in_step", "ntaps")] +
+                [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p)] +
+                [(n, C.c_int) for n in ("Ho", "Wo", "out_ld", "out_c0", "out_step", "out_oy", "out_ox", "NP", "n_valid", "relu", "units")])
+
+
+class Im2colTaps(C.Structure):
+    _fields_ = [("ntaps", C.c_int), ("off", C.c_longlong * 9)]
+
+
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _SIGNATURES = {
     "erf_abi_version": [],
@@ -52,6 +62,8 @@ _SIGNATURES = {
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],
+    "erf_conv_im2col_tc": [C.POINTER(Im2colDesc), _vp],
+    "erf_pack_im2col_weights": [_vp, _ll, _ll, _i, _i, _i, C.POINTER(Im2colTaps), _i, _i, _vp, _vp],
     "erf_umma_probe": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
 }
 

@@ -1,0 +1,309 @@
+// Generic tcgen05 implicit-GEMM convolution with SOFTWARE im2col, for every conv of the net that is not a 3-tap 1-D conv:
+// the 3x3 stride-2 convs of the downsamplers (eval/erfnet.py:16), the 3x3 stride-2 transposed convs of the upsamplers
+// (l.102), the 2x2 stride-2 transposed head (l.124), the 1x1 encoder head (l.85) and all their data gradients.
+//
+// One launch covers one "class" of output pixels that share a tap list:
+//   * pixels are enumerated on a grid (EN, EH, EW); enumerated pixel (n, y, x) reads input pixel
+//     (in_step*y + tap.dy, in_step*x + tap.dx) for each tap and writes output pixel (out_step*y + out_oy, out_step*x + out_ox)
+//       strided conv      : grid = output grid,        in_step = stride, tap = (ky*dil - pad, kx*dil - pad), out_step = 1
+//       transposed stride 2: grid = output grid / 2 per parity class (a,b), in_step = 1, taps = the 1/2/2/4 taps that hit
+//                            that parity (sub-pixel form), out_step = 2, out offset = (a,b)
+//   * unit = 128 consecutive enumerated pixels = one UMMA M block; per tap the A tile [128 px][Cin] is gathered by four
+//     loader warps with 16-byte cp.async (zero-fill outside the image = padding) straight into the swizzled K-major layout
+//     (128B swizzle for 64-channel chunks, 32B swizzle for 16-channel chunks), one ring slot per tap;
+//   * the class's tap weight matrices are resident in shared memory (bulk copy of a host-packed image);
+//   * warp 4 issues the MMAs (N = padded Cout, K = Cin per tap) into one of two TMEM accumulators; warps 5-8 run the
+//     epilogue (bias, ReLU, bf16, per-pixel 16-byte stores into the NHWC output slice).
+// These layers are 6 % of the network's FLOPs; the point of this kernel is to get them off the CUDA cores, not peak MMA rate.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace erfk {
+using namespace tc;
+
+constexpr int kImMaxSlots = 8;
+constexpr int kImThreads = 288;  // warps 0-3 loaders, warp 4 MMA, warps 5-8 epilogue
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_g2s_im(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf_im2col_desc p, const int slots, const int slot_bytes,
+                                                                       const int w_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + ((w_bytes + 1023) / 1024) * 1024;
+  __shared__ uint64_t full_bar[kImMaxSlots], empty_bar[kImMaxSlots], tfull_bar[2], tempty_bar[2], w_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[NP];
+  constexpr uint32_t TMEM_COLS = 2 * NP < 32 ? 32 : 2 * NP;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, NP);
+  const int CH = (p.Cin % 64) == 0 ? 64 : 16;   // channels per K chunk
+  const int RB = CH * 2, KC = p.Cin / CH, KSTEPS = CH / 16, CPR = RB / 16;
+  const uint32_t layout = RB == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
+  const long long total = (long long)p.EN * p.EH * p.EW;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < NP; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < slots; ++s) {
+      mbar_init(&full_bar[s], 128);   // one arrival per loader thread
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    mbar_init(&w_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ================= loaders: 128 threads gather one tap tile per ring slot =================
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&w_bar, w_bytes);
+      for (int off = 0; off < w_bytes; off += 32768) {
+        const int nb = w_bytes - off < 32768 ? w_bytes - off : 32768;
+        bulk_g2s_im(s_w + off, reinterpret_cast<const uint8_t*>(p.w_img) + off, nb, &w_bar);
+      }
+    }
+    // thread t copies 16-byte chunk j = t % CPR of rows r_i = i * (128 / CPR) + t / CPR
+    const int rows_per_iter = 128 / CPR, iters = CPR;   // CPR = 8: 8 rows/thread; CPR = 2: 2 rows/thread
+    const int j = tid % CPR, r0 = tid / CPR;
+    int slot = 0;
+    uint32_t phase = 0;
+    // completion lags issue by `lag` tap tiles so that the gathers of consecutive taps overlap (needs slots > lag)
+    const int lag = slots > 2 ? 2 : 1;
+    int pend[2] = {-1, -1};
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      // decode this thread's rows once per unit
+      int ry[8], rx[8], rn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < iters) {
+          const long long q = (long long)u * 128 + i * rows_per_iter + r0;
+          if (q < total) {
+            rx[i] = (int)(q % p.EW);
+            const long long t2 = q / p.EW;
+            ry[i] = (int)(t2 % p.EH);
+            rn[i] = (int)(t2 / p.EH);
+          } else {
+            rn[i] = -1; ry[i] = rx[i] = 0;
+          }
+        }
+      }
+      for (int t = 0; t < p.ntaps; ++t) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        uint8_t* base = s_a + (size_t)slot * slot_bytes;
+        const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < iters) {
+            const int row = i * rows_per_iter + r0;
+            const int iy = p.in_step * ry[i] + dy, ix = p.in_step * rx[i] + dx;
+            const bool ok = rn[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const __nv_bfloat16* src = ok ? in + (((size_t)rn[i] * p.H + iy) * p.W + ix) * p.in_ld + j * 8 : in;
+            const int key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
+            uint8_t* dst = base + row * RB + ((j ^ key) * 16);
+            for (int kc = 0; kc < KC; ++kc) cp_async16(dst + kc * (128 * RB), src + (ok ? kc * CH : 0), ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        // retire the tile issued `lag` steps ago
+        if (lag == 2) {
+          if (pend[1] >= 0) { cp_async_wait<2>(); fence_proxy_async_smem(); mbar_arrive(&full_bar[pend[1]]); }
+          pend[1] = pend[0];
+          pend[0] = slot;
+        } else {
+          if (pend[0] >= 0) { cp_async_wait<1>(); fence_proxy_async_smem(); mbar_arrive(&full_bar[pend[0]]); }
+          pend[0] = slot;
+        }
+        if (++slot == slots) { slot = 0; phase ^= 1; }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    if (lag == 2 && pend[1] >= 0) mbar_arrive(&full_bar[pend[1]]);
+    if (pend[0] >= 0) mbar_arrive(&full_bar[pend[0]]);
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t w_addr = smem_u32(s_w);
+      const uint32_t desc_hi = ((8u * RB) >> 4) | (1u << 14) | (layout << 29);
+      mbar_wait(&w_bar, 0);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        const uint32_t d_tmem = tmem_base + acc * NP;
+        uint32_t first = 0;
+        for (int t = 0; t < p.ntaps; ++t) {
+          mbar_wait(&full_bar[slot], phase);
+          fence_proxy_async_smem();
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(s_a + (size_t)slot * slot_bytes);
+          for (int kc = 0; kc < KC; ++kc) {
+            const uint32_t a_lo = (((a_addr + kc * (128 * RB)) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t b_lo = (((w_addr + (t * KC + kc) * (NP * RB)) >> 4) & 0x3FFF) | (1u << 16);
+            for (int k = 0; k < KSTEPS; ++k) {
+              umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC, first);
+              first = 1;
+            }
+          }
+          umma_commit(&empty_bar[slot]);
+          if (++slot == slots) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue: warps 5..8 (TMEM quadrant = warp % 4) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const long long q = (long long)u * 128 + row;
+      __nv_bfloat16* dst = nullptr;
+      if (q < total) {
+        const int x = (int)(q % p.EW);
+        const long long t2 = q / p.EW;
+        const int y = (int)(t2 % p.EH), n = (int)(t2 / p.EH);
+        dst = outp + (((size_t)n * p.Ho + (p.out_step * y + p.out_oy)) * p.Wo + (p.out_step * x + p.out_ox)) * p.out_ld + p.out_c0;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * NP + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < NP; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (dst != nullptr && c0 < p.n_valid) {
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            v[e] = __uint_as_float(r[e]) + s_bias[c0 + e];
+            if (p.relu) v[e] = fmaxf(v[e], 0.f);
+          }
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (c0 + h8 * 8 < p.n_valid) {
+              uint4 t4;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[h8 * 8 + 2 * e], v[h8 * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + c0 + h8 * 8) = t4;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Weight image [ntaps][KC][NP][CH] (bf16, swizzled) from an fp32 torch weight: element (n, k, tap) = w[n*stride_n + k*stride_k + tap_off[t]]
+// for n < n_src, k < k_src (zero otherwise).
+__global__ void pack_im2col_weights_kernel(const float* __restrict__ w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
+                                           erf_im2col_taps taps, int Cin, int NP, __nv_bfloat16* __restrict__ img) {
+  const int CH = (Cin % 64) == 0 ? 64 : 16, CPR = CH / 8, KC = Cin / CH;
+  const int total = taps.ntaps * KC * NP * CPR;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int jj = i % CPR, n = (i / CPR) % NP, kc = (i / (CPR * NP)) % KC, t = i / (CPR * NP * KC);
+  const int j = CPR == 8 ? (jj ^ (n & 7)) : (jj ^ ((n >> 2) & 1));
+  Vec<__nv_bfloat16, 8> v;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kc * CH + j * 8 + e;
+    v.v[e] = (n0 + n < n_src && k < k_src) ? w[(long long)(n0 + n) * stride_n + (long long)k * stride_k + taps.off[t]] : 0.f;
+  }
+  v.store(img + (size_t)i * 8);
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+
+extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream) {
+  ERF_CHECK_ARG(d && d->in && d->out && d->w_img, "erf_conv_im2col_tc: null pointer");
+  ERF_CHECK_ARG(d->Cin >= 16 && d->Cin <= 128 && (d->Cin % 16) == 0 && (d->in_ld % 8) == 0 && d->in_ld >= d->Cin,
+                "erf_conv_im2col_tc: Cin=%d must be a multiple of 16 in [16,128] and in_ld=%d a multiple of 8", d->Cin, d->in_ld);
+  ERF_CHECK_ARG(d->NP == 16 || d->NP == 32 || d->NP == 64 || d->NP == 128, "erf_conv_im2col_tc: padded N=%d must be 16, 32, 64 or 128", d->NP);
+  ERF_CHECK_ARG(d->n_valid > 0 && d->n_valid <= d->NP && (d->n_valid % 8) == 0 && ((d->out_ld | d->out_c0) % 8) == 0,
+                "erf_conv_im2col_tc: n_valid / out_ld / out_c0 must be multiples of 8");
+  ERF_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9 && d->EN > 0 && d->EH > 0 && d->EW > 0, "erf_conv_im2col_tc: bad tap count or grid");
+  const int CH = (d->Cin % 64) == 0 ? 64 : 16, RB = CH * 2, KC = d->Cin / CH;
+  const int w_bytes = d->ntaps * KC * d->NP * RB;
+  const int w_pad = ((w_bytes + 1023) / 1024) * 1024;
+  const int slot_bytes = KC * 128 * RB;
+  int slots = (200 * 1024 - w_pad) / slot_bytes;
+  if (slots > kImMaxSlots) slots = kImMaxSlots;
+  if (slots < 2) {
+    set_error("erf_conv_im2col_tc: %d taps x N=%d x Cin=%d of weights do not fit in shared memory; split the class", d->ntaps, d->NP, d->Cin);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  const long long total = (long long)d->EN * d->EH * d->EW;
+  erf_im2col_desc p = *d;
+  p.units = (int)((total + 127) / 128);
+  size_t smem = (size_t)w_pad + (size_t)slots * slot_bytes + 1024;
+  int grid = p.units < 148 ? p.units : 148;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+#define IM_LAUNCH(NP_)                                                                                                  \
+  e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e == cudaSuccess) conv_im2col_tc_kernel<NP_><<<grid, kImThreads, smem, st>>>(p, slots, slot_bytes, w_bytes);
+  if (d->NP == 16) { IM_LAUNCH(16) }
+  else if (d->NP == 32) { IM_LAUNCH(32) }
+  else if (d->NP == 64) { IM_LAUNCH(64) }
+  else { IM_LAUNCH(128) }
+#undef IM_LAUNCH
+  if (e != cudaSuccess) {
+    set_error("erf_conv_im2col_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return ERF_ERR_CUDA;
+  }
+  ERF_CHECK_LAUNCH("erf_conv_im2col_tc");
+  return ERF_OK;
+}
+
+extern "C" int erf_pack_im2col_weights(const float* w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
+                                       const erf_im2col_taps* taps, int Cin, int NP, void* img, erf_stream_t stream) {
+  ERF_CHECK_ARG(w && taps && img && taps->ntaps >= 1 && taps->ntaps <= 9 && (Cin % 16) == 0 && Cin <= 128, "erf_pack_im2col_weights: bad arguments");
+  const int CH = (Cin % 64) == 0 ? 64 : 16;
+  const int total = taps->ntaps * (Cin / CH) * NP * (CH / 8);
+  pack_im2col_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, stride_n, stride_k, n0, n_src, k_src, *taps, Cin, NP,
+                                                                                   (__nv_bfloat16*)img);
+  ERF_CHECK_LAUNCH("erf_pack_im2col_weights");
+  return ERF_OK;
+}

@@ -161,6 +161,36 @@ def _bn_fold(bn: nn.BatchNorm2d):
     return ops.bn_eval_affine(bn.weight.detach().float(), bn.bias.detach().float(), bn.running_mean, bn.running_var, bn.eps)
 
 
+class _TcConv:
+    """tcgen05 (software-im2col) execution of one conv layer: forward and data gradient, with cached plans."""
+
+    def __init__(self, spec: ConvSpec):
+        self.spec = spec
+        self.dspec = ops.dgrad_spec(spec)
+        self._plans = None
+
+    def plans(self):
+        if self._plans is None:
+            self._plans = (ops.im2col_plan(self.spec), ops.im2col_plan(self.dspec))
+        return self._plans
+
+    def fwd_ok(self, dtype):
+        return ops.im2col_supported(self.spec, dtype)
+
+    def bwd_ok(self, dtype):
+        return ops.im2col_supported(self.dspec, dtype)
+
+    def pack_fwd(self, w):
+        return ops.im2col_pack(w, self.spec, False, self.plans()[0])
+
+    def forward(self, x, imgs, bias, relu=False, out=None, out_coff=0):
+        return ops.conv_im2col_tc(x, imgs, self.plans()[0], self.spec, bias, relu=relu, out=out, out_coff=out_coff)
+
+    def dgrad(self, dy, w, out_hw):
+        plan = self.plans()[1]
+        return ops.conv_im2col_tc(dy, ops.im2col_pack(w, self.spec, True, plan), plan, self.dspec, out_hw=out_hw)
+
+
 def _run(block, x, ctx):
     """Dispatch a block on an NHWC tensor: autograd path in training, folded kernels otherwise."""
     if ctx.training:
@@ -182,6 +212,7 @@ class DownsamplerBlock(_B200Module):
         self.bn = nn.BatchNorm2d(noutput, eps=BN_EPS)
         self.ninput, self.noutput = ninput, noutput
         self.spec = ConvSpec(ninput, noutput - ninput, 3, 3, 2, 1, 1)
+        self.__dict__["_tc"] = _TcConv(self.spec)
         self._in_ld, self._out_c = ops.round_up(ninput, 4), noutput
 
     def _nhwc(self, x, ctx):
@@ -203,14 +234,20 @@ class DownsamplerBlock(_B200Module):
             ps, psh = scale[cc:].contiguous(), shift[cc:].contiguous()
         else:
             ps = psh = None
-        return dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous(), ps=ps, psh=psh)
+        pk = dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous(), ps=ps, psh=psh)
+        if self._tc.fwd_ok(dtype):
+            pk["tc"] = self._tc.pack_fwd(w)
+        return pk
 
     def _fwd_eval(self, x, ctx):
         self._check(x)
         pk = self._cache(ctx.dtype)
         n, h, w, _ = x.shape
         y = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
-        ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True, out=y)
+        if "tc" in pk and ops.USE_TC:
+            self._tc.forward(x, pk["tc"], pk["b"], relu=True, out=y)
+        else:
+            ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True, out=y)
         ops.maxpool_fwd(x, self.ninput, y, self.noutput - self.ninput, pk["ps"], pk["psh"], relu=True)
         return y
 
@@ -225,9 +262,14 @@ class DownsamplerBlock(_B200Module):
         cc = self.noutput - self.ninput
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
         stats = _stats_buf(self.bn, x.device)
-        ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
-                     out=y_raw, stats=stats)
-        ops.maxpool_fwd(x, self.ninput, y_raw, cc, stats=stats)
+        if self._tc.fwd_ok(x.dtype):
+            self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), out=y_raw)
+            ops.maxpool_fwd(x, self.ninput, y_raw, cc)
+            ops.channel_stats(y_raw, stats)
+        else:
+            ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                         out=y_raw, stats=stats)
+            ops.maxpool_fwd(x, self.ninput, y_raw, cc, stats=stats)
         mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
                                                      self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
         _tick(self.bn)
@@ -242,7 +284,10 @@ class DownsamplerBlock(_B200Module):
         dx = None
         if need_dx:
             n, h, w, _ = x.shape
-            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=(h, w))
+            if self._tc.bwd_ok(x.dtype):
+                dx = self._tc.dgrad(dyr, cw, (h, w))
+            else:
+                dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=(h, w))
             ops.maxpool_bwd(x, self.ninput, dyr, self.noutput - self.ninput, dx)
         grads = (_ret(cw, dw), _ret(cb, db), _ret(gw, dgamma), _ret(gb, dbeta))
         _sunk(cw, cb, gw, gb)
@@ -420,6 +465,7 @@ class UpsamplerBlock(_B200Module):
         self.conv = nn.ConvTranspose2d(ninput, noutput, 3, stride=2, padding=1, output_padding=1, bias=True)
         self.bn = nn.BatchNorm2d(noutput, eps=BN_EPS)
         self.spec = ConvSpec(ninput, noutput, 3, 3, 2, 1, 1, transposed=True, out_pad=1)
+        self.__dict__["_tc"] = _TcConv(self.spec)
         self._out_c = noutput
 
     def _nhwc(self, x, ctx):
@@ -431,10 +477,15 @@ class UpsamplerBlock(_B200Module):
             scale, shift = _bn_fold(self.bn)
             w = w * scale.view(1, -1, 1, 1)
             b = b * scale + shift
-        return dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous())
+        pk = dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous())
+        if self._tc.fwd_ok(dtype):
+            pk["tc"] = self._tc.pack_fwd(w)
+        return pk
 
     def _fwd_eval(self, x, ctx):
         pk = self._cache(ctx.dtype)
+        if "tc" in pk and ops.USE_TC:
+            return self._tc.forward(x, pk["tc"], pk["b"], relu=True)
         return ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True)
 
     def _train_params(self):
@@ -444,8 +495,12 @@ class UpsamplerBlock(_B200Module):
         if not self.use_batchnorm:
             raise RuntimeError("training with use_batchnorm=False is not implemented yet")
         stats = _stats_buf(self.bn, x.device)
-        y_raw = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
-                             stats=stats)
+        if self._tc.fwd_ok(x.dtype):
+            y_raw = self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float())
+            ops.channel_stats(y_raw, stats)
+        else:
+            y_raw = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                                 stats=stats)
         count = y_raw.shape[0] * y_raw.shape[1] * y_raw.shape[2]
         mean, invstd, scale, shift = ops.bn_finalize(stats, count, self.bn.weight.detach(), self.bn.bias.detach(), self.bn.running_mean,
                                                      self.bn.running_var, BN_MOMENTUM, BN_EPS)
@@ -460,7 +515,10 @@ class UpsamplerBlock(_B200Module):
         dw, db = ops.conv_wgrad(x, dyr, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
         dx = None
         if need_dx:
-            dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
+            if self._tc.bwd_ok(x.dtype):
+                dx = self._tc.dgrad(dyr, cw, x.shape[1:3])
+            else:
+                dx = ops.conv_fwd(dyr, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
         grads = (_ret(cw, dw), _ret(cb, db), _ret(gw, dgamma), _ret(gb, dbeta))
         _sunk(cw, cb, gw, gb)
         return dx, grads
@@ -474,6 +532,7 @@ class _PlainConv:
     def __init__(self, conv: nn.Module, spec: ConvSpec):
         self.spec = spec
         self._conv = conv
+        self._tc = _TcConv(spec)
         self.out_ld = ops.round_up(spec.cout, 8)
 
     def _out(self, x):
@@ -487,17 +546,23 @@ class _PlainConv:
         sig = (ctx.dtype,) + _sig(self._conv)
         c = self._conv.__dict__.get("_packed")
         if c is None or c[0] != sig:
-            c = (sig, (ops.pack_weight_fwd(self._conv.weight.detach().float(), self.spec, ctx.dtype), self._conv.bias.detach().float().contiguous()))
+            tc = self._tc.pack_fwd(self._conv.weight) if self._tc.fwd_ok(ctx.dtype) else None
+            c = (sig, (ops.pack_weight_fwd(self._conv.weight.detach().float(), self.spec, ctx.dtype), self._conv.bias.detach().float().contiguous(), tc))
             self._conv.__dict__["_packed"] = c
-        w, b = c[1]
+        w, b, tc = c[1]
+        if tc is not None and ops.USE_TC:
+            return self._tc.forward(x, tc, b, out=self._out(x))
         return ops.conv_fwd(x, w, self.spec, b, out=self._out(x))
 
     def _train_params(self):
         return (self._conv.weight, self._conv.bias)
 
     def _fwd_train(self, x, ctx):
-        y = ops.conv_fwd(x, ops.pack_weight_fwd(self._conv.weight.detach(), self.spec, x.dtype), self.spec, self._conv.bias.detach().float(),
-                         out=self._out(x))
+        if self._tc.fwd_ok(x.dtype):
+            y = self._tc.forward(x, self._tc.pack_fwd(self._conv.weight), self._conv.bias.detach().float(), out=self._out(x))
+        else:
+            y = ops.conv_fwd(x, ops.pack_weight_fwd(self._conv.weight.detach(), self.spec, x.dtype), self.spec, self._conv.bias.detach().float(),
+                             out=self._out(x))
         return y, (x,)
 
     def _bwd(self, dy, saved, need_dx):
@@ -506,7 +571,10 @@ class _PlainConv:
         dw, db = ops.conv_wgrad(x, dy, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
         dx = None
         if need_dx:
-            dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
+            if self._tc.bwd_ok(x.dtype):
+                dx = self._tc.dgrad(dy, cw, x.shape[1:3])
+            else:
+                dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
         grads = (_ret(cw, dw), _ret(cb, db))
         _sunk(cw, cb)
         return dx, grads

@@ -242,6 +242,107 @@ def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------
+# generic tcgen05 conv (software im2col): planning, weight images, launch
+# ----------------------------------------------------------------------------------------------------------
+def im2col_supported(spec_g: ConvSpec, dtype) -> bool:
+    """spec_g: the GATHER that is executed (a forward spec, or dgrad_spec(forward spec))."""
+    return (dtype == torch.bfloat16 and not EMULATED and USE_TC and spec_g.cin % 16 == 0 and spec_g.cin <= 128 and spec_g.cout <= 128
+            and spec_g.stride in (1, 2) and spec_g.kh * spec_g.kw <= 9)
+
+
+def im2col_plan(spec_g: ConvSpec):
+    """One dict per launch (class of output pixels sharing a tap list, and an N range)."""
+    s = spec_g.stride
+    classes = []
+    if not spec_g.transposed:
+        taps = [(ky, kx, ky * spec_g.dil_h - spec_g.pad_h, kx * spec_g.dil_w - spec_g.pad_w) for ky in range(spec_g.kh) for kx in range(spec_g.kw)]
+        classes.append(dict(taps=taps, in_step=s, out_step=1, oy=0, ox=0, div=1))
+    else:
+        for a in range(s):
+            for b in range(s):
+                taps = []
+                for ky in range(spec_g.kh):
+                    ty = a + spec_g.pad_h - ky * spec_g.dil_h
+                    if ty % s:
+                        continue
+                    for kx in range(spec_g.kw):
+                        tx = b + spec_g.pad_w - kx * spec_g.dil_w
+                        if tx % s:
+                            continue
+                        taps.append((ky, kx, ty // s, tx // s))
+                if taps:
+                    classes.append(dict(taps=taps, in_step=1, out_step=s, oy=a, ox=b, div=s))
+    np_full = 16
+    while np_full < spec_g.cout:
+        np_full *= 2
+    plan = []
+    for c in classes:
+        npad = np_full
+        while len(c["taps"]) * spec_g.cin * npad * 2 > 96 * 1024 and npad > 16:
+            npad //= 2
+        for n0 in range(0, np_full, npad):
+            if n0 >= spec_g.cout:
+                break
+            plan.append(dict(c, n0=n0, NP=npad, n_valid=min(round_up(spec_g.cout, 8) - n0, npad)))
+    return plan
+
+
+def im2col_pack(w: torch.Tensor, spec_fwd: ConvSpec, dgrad: bool, plan):
+    """bf16 weight images (one per plan entry) from the fp32 torch weight of the FORWARD conv spec_fwd."""
+    w = w.detach().contiguous().float()
+    khw = spec_fwd.kh * spec_fwd.kw
+    d0, d1 = w.shape[0], w.shape[1]          # Conv2d: [Co,Ci,..]; ConvTranspose2d: [Ci,Co,..]
+    co_is_dim0 = not spec_fwd.transposed
+    n_is_co = not dgrad                       # forward: n = out channel; data gradient: n = in channel
+    n_dim0 = (n_is_co == co_is_dim0)
+    stride_n, stride_k = (d1 * khw, khw) if n_dim0 else (khw, d1 * khw)
+    n_src, k_src = (d0, d1) if n_dim0 else (d1, d0)
+    cin_g = round_up(k_src, 16)
+    L = _lib.lib()
+    imgs = []
+    for e in plan:
+        taps = _lib.Im2colTaps()
+        taps.ntaps = len(e["taps"])
+        for i, (ky, kx, _, _) in enumerate(e["taps"]):
+            taps.off[i] = ky * spec_fwd.kw + kx
+        img = torch.empty(len(e["taps"]) * cin_g * e["NP"], device=w.device, dtype=torch.bfloat16)
+        check(L.erf_pack_im2col_weights(_p(w), stride_n, stride_k, e["n0"], n_src, k_src, C.byref(taps), cin_g, e["NP"], _p(img), _stream(w)))
+        _count()
+        imgs.append(img)
+    return imgs
+
+
+def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional[torch.Tensor] = None, relu=False,
+                   out: Optional[torch.Tensor] = None, out_coff=0, out_hw: Optional[Tuple[int, int]] = None):
+    """Run the gather spec_g on the tensor cores.  x: [N,H,W,ld >= cin]; fills out[..., out_coff : out_coff + round8(cout)]."""
+    n, h, w, ld = x.shape
+    if out is None:
+        ho, wo = out_hw if out_hw is not None else spec_g.out_hw(h, w)
+        out = torch.empty(n, ho, wo, round_up(spec_g.cout, 8), device=x.device, dtype=x.dtype)
+    ho, wo = out.shape[1:3]
+    if bias is not None and bias.numel() % 8:
+        bias = torch.nn.functional.pad(bias.float(), (0, 8 - bias.numel() % 8))  # the kernel adds bias to the padded channels too
+    L = _lib.lib()
+    name = f"conv_im2col_tc[{spec_g.cin}->{spec_g.cout} {spec_g.kh}x{spec_g.kw} s{spec_g.stride}{'T' if spec_g.transposed else ''}]" if DETAIL else "conv_im2col_tc_kernel"
+    with _timed(name, conv_flops(spec_g, n, ho, wo)):
+        for e, img in zip(plan, imgs):
+            d = _lib.Im2colDesc()
+            d.in_, d.H, d.W, d.in_ld, d.Cin = x.data_ptr(), h, w, ld, round_up(spec_g.cin, 16)
+            d.EN, d.EH, d.EW, d.in_step = n, ho // e["div"], wo // e["div"], e["in_step"]
+            d.ntaps = len(e["taps"])
+            for i, (_, _, dy, dx) in enumerate(e["taps"]):
+                d.tap_dy[i], d.tap_dx[i] = dy, dx
+            d.w_img = img.data_ptr()
+            d.bias = None if bias is None else bias.data_ptr() + 4 * e["n0"]
+            d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo, out.shape[-1], out_coff + e["n0"]
+            d.out_step, d.out_oy, d.out_ox = e["out_step"], e["oy"], e["ox"]
+            d.NP, d.n_valid, d.relu = e["NP"], e["n_valid"], int(relu)
+            check(L.erf_conv_im2col_tc(C.byref(d), _stream(x)))
+            _count()
+    return out
+
+
 _WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partial sums
 
 

@@ -183,6 +183,29 @@ int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspac
 /* out[c] += sum_p x[p*ld + coff + c]   (bias gradients) */
 int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream);
 
+/* ---- generic tcgen05 implicit-GEMM convolution with software im2col ------------------------------------------------------
+ * Serves the 3x3 stride-2 convs (eval/erfnet.py:16), the stride-2 transposed convs (l.102, 124; one launch per output
+ * parity class, sub-pixel form), the 1x1 head (l.85) and all their data gradients.  One launch = one class of output
+ * pixels sharing a tap list: pixel (n,y,x) of the enumeration grid (EN,EH,EW) reads input pixel
+ * (in_step*y + tap_dy[t], in_step*x + tap_dx[t]) per tap (zero outside the image) and writes output pixel
+ * (out_step*y + out_oy, out_step*x + out_ox), channels [out_c0, out_c0 + n_valid).  NHWC bf16 in/out. */
+typedef struct {
+  const void* in; int H, W, in_ld, Cin;            /* Cin: multiple of 16, <= 128 */
+  int EN, EH, EW, in_step;
+  int ntaps; int tap_dy[9]; int tap_dx[9];
+  const void* w_img;                                /* erf_pack_im2col_weights image [ntaps][Cin/CH][NP][CH] */
+  const float* bias;                                /* [n_valid] or NULL */
+  void* out; int Ho, Wo, out_ld, out_c0, out_step, out_oy, out_ox;
+  int NP, n_valid, relu;                            /* NP = padded N (16/32/64/128); n_valid % 8 == 0 */
+  int units;                                        /* filled in by the library */
+} erf_im2col_desc;
+typedef struct { int ntaps; long long off[9]; } erf_im2col_taps;
+int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream);
+/* img[t][kc][n][..] = w[(n0+n)*stride_n + k*stride_k + taps->off[t]] (fp32 torch weight, any of the Conv2d / ConvTranspose2d
+ * forward / data-gradient orientations), zero for n0+n >= n_src or k >= k_src; bf16, swizzled for the kernel above. */
+int erf_pack_im2col_weights(const float* w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
+                            const erf_im2col_taps* taps, int Cin, int NP, void* img, erf_stream_t stream);
+
 /* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
 /* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
  * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle

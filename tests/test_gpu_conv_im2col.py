@@ -1,0 +1,59 @@
+"""GPU: the generic tcgen05 conv (software im2col) vs fp32 torch convs of the same bf16 operands, for every shape class
+it serves in ERFNet: stride-2 3x3 convs, stride-2 transposed convs (3x3 and 2x2), 1x1, and their data gradients."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from erfnet_pytorch_b200 import ops
+from erfnet_pytorch_b200.ops import ConvSpec
+from tests.test_host_logic import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("down64_128", ConvSpec(64, 64, 3, 3, 2, 1, 1), (2, 24, 40)),
+    ("down16_64", ConvSpec(16, 48, 3, 3, 2, 1, 1), (2, 20, 36)),
+    ("up128_64", ConvSpec(128, 64, 3, 3, 2, 1, 1, transposed=True, out_pad=1), (2, 9, 20)),
+    ("up64_16", ConvSpec(64, 16, 3, 3, 2, 1, 1, transposed=True, out_pad=1), (3, 10, 24)),
+    ("head16_20", ConvSpec(16, 20, 2, 2, 2, transposed=True), (2, 12, 40)),
+    ("enc_head_1x1", ConvSpec(128, 20, 1, 1), (2, 8, 24)),
+]
+
+
+def _torch_fwd(x_nchw, w, b, spec):
+    if spec.transposed:
+        return F.conv_transpose2d(x_nchw, w, b, stride=spec.stride, padding=(spec.pad_h, spec.pad_w), output_padding=spec.out_pad)
+    return F.conv2d(x_nchw, w, b, stride=spec.stride, padding=(spec.pad_h, spec.pad_w))
+
+
+@pytest.mark.parametrize("name,spec,nhw", CASES, ids=[c[0] for c in CASES])
+def test_forward_and_data_gradient(name, spec, nhw):
+    gen = torch.Generator().manual_seed(len(name))
+    n, h, w = nhw
+    wshape = (spec.cin, spec.cout, spec.kh, spec.kw) if spec.transposed else (spec.cout, spec.cin, spec.kh, spec.kw)
+    wt = torch.randn(*wshape, generator=gen) / (spec.cin * spec.kh * spec.kw) ** 0.5
+    bias = torch.randn(spec.cout, generator=gen) * 0.1
+    x = torch.randn(n, h, w, spec.cin, generator=gen).bfloat16()
+    wq = wt.bfloat16().float()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = _torch_fwd(xr, wq, bias, spec)
+    # forward (+ bias, relu) into a wider tensor at a channel offset, like the downsampler concat
+    assert ops.im2col_supported(spec, torch.bfloat16)
+    plan = ops.im2col_plan(spec)
+    imgs = ops.im2col_pack(wt.cuda(), spec, False, plan)
+    ho, wo = ref.shape[2:]
+    c8 = ops.round_up(spec.cout, 8)
+    out = torch.full((n, ho, wo, c8 + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.conv_im2col_tc(x.cuda(), imgs, plan, spec, bias.cuda(), relu=True, out=out, out_coff=0)
+    got = out[..., :spec.cout].float().cpu()
+    assert_rel(got.numpy(), ref.relu().permute(0, 2, 3, 1).detach().numpy(), 1e-2, name + " fwd")
+    assert torch.all(out[..., c8:] == 7.0), "channels outside the slice must be untouched"
+    # data gradient (only where the gather's input channels are a multiple of 16)
+    dspec = ops.dgrad_spec(spec)
+    if ops.im2col_supported(dspec, torch.bfloat16):
+        dy = torch.randn(n, ho, wo, spec.cout, generator=gen).bfloat16()
+        (gref,) = torch.autograd.grad(ref, xr, dy.float().permute(0, 3, 1, 2))
+        dplan = ops.im2col_plan(dspec)
+        dimgs = ops.im2col_pack(wt.cuda(), spec, True, dplan)
+        dx = ops.conv_im2col_tc(dy.cuda(), dimgs, dplan, dspec, out_hw=(h, w))
+        assert_rel(dx[..., :spec.cin].float().cpu().numpy(), gref.permute(0, 2, 3, 1).numpy(), 1e-2, name + " dgrad")
