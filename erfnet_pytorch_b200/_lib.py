@@ -28,6 +28,12 @@ class Im2colDesc(C.Structure):
                 [(n, C.c_int) for n in ("Ho", "Wo", "out_ld", "out_c0", "out_step", "out_oy", "out_ox", "NP", "n_valid", "relu", "units")])
 
 
+class WgradIm2colDesc(C.Structure):
+    _fields_ = ([("g", C.c_void_p)] + [(n, C.c_int) for n in ("GH", "GW", "g_ld", "Cg", "CgP", "g_copy_bytes", "g_step")] +
+                [("d", C.c_void_p)] + [(n, C.c_int) for n in ("EN", "EH", "EW", "d_ld", "d_c0", "d_c_base", "Cd", "NP", "ntaps")] +
+                [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("tap_off", C.c_int * 9), ("KHW", C.c_int), ("tail_bytes", C.c_int)])
+
+
 class Im2colTaps(C.Structure):
     _fields_ = [("ntaps", C.c_int), ("off", C.c_longlong * 9)]
 
@@ -64,6 +70,8 @@ _SIGNATURES = {
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],
     "erf_conv_im2col_tc": [C.POINTER(Im2colDesc), _vp],
     "erf_pack_im2col_weights": [_vp, _ll, _ll, _i, _i, _i, C.POINTER(Im2colTaps), _i, _i, _vp, _vp],
+    "erf_conv_wgrad_im2col_tc_workspace": [],
+    "erf_conv_wgrad_im2col_tc": [C.POINTER(WgradIm2colDesc), _vp, _vp, C.c_size_t, _vp],
     "erf_umma_probe": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
 }
 

@@ -1,0 +1,262 @@
+// Generic tcgen05 weight gradient with software gather, for the convs served by conv_im2col_tc.cu (3x3 stride-2 convs,
+// stride-2 transposed convs, the stem):
+//
+//   dW[tap][cg][cd] = sum over the DENSE-side pixels q of  G[gather(q, tap)][cg] * D[q][cd]
+//
+//   conv  (stride s): dense D = dy on the output grid, gathered G = x at (s*oy - pad + ky*dil, s*ox - pad + kx*dil)
+//   convT (stride s): dense D = x  on the input  grid, gathered G = dy at (s*iy - pad + ky,     s*ix - pad + kx)
+//   (in both cases the torch parameter index is ((cd*Cg + cg)*KH*KW + ky*KW + kx), so one reduce kernel serves both).
+//
+// Both operands are NHWC pixel tiles, i.e. MN-major for this product (channels contiguous, pixels = K).  The gathered
+// operand sits on the M side: its tap tiles are adjacent in shared memory at a uniform pitch, so the UMMA descriptor's
+// leading-byte-offset walks "M atoms" = (tap, channel sub-tile) pairs -- one M=128 MMA covers 2 taps of a 64-channel tensor
+// or 8 taps of a 16-channel one at full tensor-core width (the same trick as conv1d_wgrad_tc.cu).  Each group of 128 M rows
+// owns one TMEM accumulator [128 x NP]; a persistent CTA accumulates over all its 64-pixel units and dumps once.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace erfk {
+using namespace tc;
+
+constexpr int kWiThreads = 288;  // warps 0-3 loaders, warp 4 MMA, warps 5-8 epilogue
+constexpr int kWiPX = 64;        // pixels (K) per unit
+constexpr int kWiMaxStages = 4;
+
+__device__ __forceinline__ void wi_cp_async(void* smem_dst, const void* gsrc, int bytes, uint32_t src_bytes) {
+  if (bytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// smem stage layout: [gathered: ntaps*gsubs sub-tiles of 64 px x CHg][dense: dsubs sub-tiles of 64 px x CHd]
+__global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(const erf_wgrad_im2col_desc p, const int stages, const int stage_bytes,
+                                                                             const int dense_off, const int groups, float* __restrict__ ws) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[kWiMaxStages], empty_bar[kWiMaxStages], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_row[kWiMaxStages][kWiPX][3];   // (n, y, x) of the unit's pixels, -1 = beyond the end
+  const int CHg = (p.CgP % 64) == 0 ? 64 : 16, RBg = CHg * 2, gsubs = p.CgP / CHg;
+  const int CHd = (p.NP % 64) == 0 ? 64 : 16, RBd = CHd * 2, dsubs = p.NP / CHd;
+  const int g_sub_bytes = kWiPX * RBg, d_sub_bytes = kWiPX * RBd;
+  const long long total = (long long)p.EN * p.EH * p.EW;
+  const int units = (int)((total + kWiPX - 1) / kWiPX);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < groups * p.NP) tmem_cols <<= 1;
+
+  // zero the whole staging area once: rows shorter than their swizzle row / padded channels / garbage atoms stay finite
+  for (int i = tid; i < (stages * stage_bytes + p.tail_bytes) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 4) tmem_alloc(&tmem_base_s, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ================= loaders =================
+    const uint8_t* G = reinterpret_cast<const uint8_t*>(p.g);
+    const uint8_t* D = reinterpret_cast<const uint8_t*>(p.d);
+    const int g_row_bytes = p.g_copy_bytes;                 // bytes copied per gathered pixel (multiple of 16, or 8)
+    const int g_chunk = g_row_bytes >= 16 ? 16 : 8;
+    const int g_chunks = g_row_bytes / g_chunk;
+    const int d_chunks = p.NP / 8;                          // 16-byte chunks per dense pixel
+    int stage = 0;
+    uint32_t phase = 0;
+    int pend = -1;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* base = smem + (size_t)stage * stage_bytes;
+      // per-unit pixel table (64 rows); the loader group syncs on named barrier 1
+      if (tid < kWiPX) {
+        const long long q = (long long)u * kWiPX + tid;
+        if (q < total) {
+          s_row[stage][tid][2] = (int)(q % p.EW);
+          const long long t2 = q / p.EW;
+          s_row[stage][tid][1] = (int)(t2 % p.EH);
+          s_row[stage][tid][0] = (int)(t2 / p.EH);
+        } else {
+          s_row[stage][tid][0] = -1;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // gathered operand: items (tap, row, chunk)
+      const int g_items = p.ntaps * kWiPX * g_chunks;
+      for (int it = tid; it < g_items; it += 128) {
+        const int ch = it % g_chunks, row = (it / g_chunks) % kWiPX, t = it / (g_chunks * kWiPX);
+        const int n = s_row[stage][row][0];
+        const int gy = p.g_step * s_row[stage][row][1] + p.tap_dy[t], gx = p.g_step * s_row[stage][row][2] + p.tap_dx[t];
+        const bool ok = n >= 0 && gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
+        const uint8_t* src = ok ? G + ((((size_t)n * p.GH + gy) * p.GW + gx) * p.g_ld) * 2 + ch * g_chunk : G;
+        // destination: 16-byte chunk index c16 of the pixel row -> sub-tile c16 / (CHg/8), chunk within the sub-tile row
+        const int byte0 = ch * g_chunk, c16 = byte0 / 16, sub = c16 / (CHg / 8), cj = c16 % (CHg / 8);
+        const int key = RBg == 128 ? (row & 7) : ((row >> 2) & 1);
+        uint8_t* dst = base + (t * gsubs + sub) * g_sub_bytes + row * RBg + ((cj ^ key) * 16) + (byte0 & 15);
+        wi_cp_async(dst, src, g_chunk, ok ? (uint32_t)g_chunk : 0u);
+      }
+      // dense operand: items (row, chunk)
+      const int d_items = kWiPX * d_chunks;
+      for (int it = tid; it < d_items; it += 128) {
+        const int c16 = it % d_chunks, row = it / d_chunks;
+        const int n = s_row[stage][row][0];
+        const bool ok = n >= 0;
+        const uint8_t* src = ok ? D + ((((size_t)n * p.EH + s_row[stage][row][1]) * p.EW + s_row[stage][row][2]) * p.d_ld + p.d_c0) * 2 + c16 * 16 : D;
+        const int sub = c16 / (CHd / 8), cj = c16 % (CHd / 8);
+        const int key = RBd == 128 ? (row & 7) : ((row >> 2) & 1);
+        uint8_t* dst = base + dense_off + sub * d_sub_bytes + row * RBd + ((cj ^ key) * 16);
+        wi_cp_async(dst, src, 16, ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (pend >= 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[pend]);
+      }
+      pend = stage;
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async_smem();
+    if (pend >= 0) mbar_arrive(&full_bar[pend]);
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t lay_g = RBg == 128 ? LAYOUT_SW128 : LAYOUT_SW32, lay_d = RBd == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
+      const uint32_t hi_g = ((8u * RBg) >> 4) | (1u << 14) | (lay_g << 29);   // SBO = 8 pixel rows
+      const uint32_t hi_d = ((8u * RBd) >> 4) | (1u << 14) | (lay_d << 29);
+      const uint32_t idesc = make_idesc_bf16(128, p.NP) | (1u << 15) | (1u << 16);   // both operands MN-major
+      const int atoms_per_m = 128 / CHg;
+      bool first = true;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        fence_proxy_async_smem();
+        tcgen05_fence_after();
+        const uint32_t g_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t d_addr = g_addr + dense_off;
+        const uint32_t d_lo = ((d_addr >> 4) & 0x3FFF) | ((((uint32_t)d_sub_bytes >> 4) & 0x3FFF) << 16);   // LBO = dense sub-tile pitch
+        for (int gidx = 0; gidx < groups; ++gidx) {
+          const uint32_t ga = g_addr + gidx * atoms_per_m * g_sub_bytes;
+          const uint32_t g_lo = ((ga >> 4) & 0x3FFF) | ((((uint32_t)g_sub_bytes >> 4) & 0x3FFF) << 16);     // LBO = (tap, sub) atom pitch
+          for (int k = 0; k < kWiPX / 16; ++k)
+            umma_bf16(tmem_base + gidx * p.NP, ((uint64_t)hi_g << 32) | (uint64_t)(g_lo + k * RBg), ((uint64_t)hi_d << 32) | (uint64_t)(d_lo + k * RBd),
+                      idesc, (first && k == 0) ? 0u : 1u);
+        }
+        first = false;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    // ================= epilogue (once): dump this CTA's accumulators =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* wsb = ws + (size_t)blockIdx.x * groups * 128 * p.NP;
+    if ((int)blockIdx.x < units) {
+      mbar_wait(&done_bar, 0);
+      tcgen05_fence_after();
+      for (int gidx = 0; gidx < groups; ++gidx) {
+        for (int c0 = 0; c0 < p.NP; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + gidx * p.NP + c0 + ((uint32_t)(quad * 32) << 16), r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(wsb + ((size_t)gidx * 128 + row) * p.NP + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// dw[((n0 + col) * Cg + cg) * KHW + tap_off[tap]] += sum over CTAs; (group, row) -> atom = group*(128/CHg) + row/CHg -> (tap, sub)
+__global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int ctas, int groups, erf_wgrad_im2col_desc p, float* __restrict__ dw) {
+  const int CHg = (p.CgP % 64) == 0 ? 64 : 16, gsubs = p.CgP / CHg;
+  const int per_cta = groups * 128 * p.NP;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_cta) return;
+  const int col = i % p.NP, row = (i / p.NP) % 128, gidx = i / (p.NP * 128);
+  const int atom = gidx * (128 / CHg) + row / CHg;
+  const int tap = atom / gsubs, sub = atom % gsubs;
+  const int cg = sub * CHg + row % CHg, cd = p.d_c0 - p.d_c_base + col;
+  if (tap >= p.ntaps || cg >= p.Cg || cd >= p.Cd) return;
+  float s = 0.f;
+  for (int b = 0; b < ctas; ++b) s += ws[(size_t)b * per_cta + i];
+  dw[((size_t)cd * p.Cg + cg) * p.KHW + p.tap_off[tap]] += s;
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+
+extern "C" size_t erf_conv_wgrad_im2col_tc_workspace(void) { return (size_t)148 * 512 * 128 * sizeof(float); }
+
+extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* dw, void* workspace, size_t ws_bytes, erf_stream_t stream) {
+  ERF_CHECK_ARG(d && d->g && d->d && dw && workspace, "erf_conv_wgrad_im2col_tc: null pointer");
+  ERF_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9 && d->EN > 0 && d->EH > 0 && d->EW > 0, "erf_conv_wgrad_im2col_tc: bad tap count or grid");
+  ERF_CHECK_ARG(d->CgP >= 16 && d->CgP <= 128 && (d->CgP % 16) == 0 && d->NP >= 16 && d->NP <= 128 && (d->NP % 16) == 0,
+                "erf_conv_wgrad_im2col_tc: padded channel counts must be multiples of 16 in [16,128] (CgP=%d NP=%d)", d->CgP, d->NP);
+  ERF_CHECK_ARG(d->g_copy_bytes == 8 || (d->g_copy_bytes >= 16 && (d->g_copy_bytes % 16) == 0 && d->g_copy_bytes <= d->CgP * 2),
+                "erf_conv_wgrad_im2col_tc: bad g_copy_bytes %d", d->g_copy_bytes);
+  ERF_CHECK_ARG((d->d_ld % 8) == 0 && (d->d_c0 % 8) == 0 && d->d_c0 + d->NP <= d->d_ld,
+                "erf_conv_wgrad_im2col_tc: dense slice [%d, %d) must be 16-byte aligned and inside the pixel row of %d channels", d->d_c0,
+                d->d_c0 + d->NP, d->d_ld);
+  const int CHg = (d->CgP % 64) == 0 ? 64 : 16, gsubs = d->CgP / CHg, RBg = CHg * 2;
+  const int CHd = (d->NP % 64) == 0 ? 64 : 16, dsubs = d->NP / CHd, RBd = CHd * 2;
+  const int atoms = d->ntaps * gsubs, atoms_per_m = 128 / CHg;
+  const int groups = (atoms + atoms_per_m - 1) / atoms_per_m;
+  if (groups * d->NP > 512) {
+    set_error("erf_conv_wgrad_im2col_tc: %d accumulator groups x N=%d exceed TMEM; split N", groups, d->NP);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  const int g_bytes = ((atoms * kWiPX * RBg + 1023) / 1024) * 1024;
+  const int d_bytes = ((dsubs * kWiPX * RBd + 1023) / 1024) * 1024;
+  const int stage_bytes = g_bytes + d_bytes;
+  int stages = (190 * 1024) / stage_bytes;
+  if (stages > kWiMaxStages) stages = kWiMaxStages;
+  if (stages < 2) {
+    set_error("erf_conv_wgrad_im2col_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  erf_wgrad_im2col_desc p = *d;
+  // the last group's unused atoms read past the gathered tiles: keep those reads inside the (zeroed) allocation
+  p.tail_bytes = atoms_per_m * kWiPX * RBg;
+  const long long total = (long long)d->EN * d->EH * d->EW;
+  const int units = (int)((total + kWiPX - 1) / kWiPX);
+  const int grid = units < 148 ? units : 148;
+  ERF_CHECK_ARG(ws_bytes >= (size_t)grid * groups * 128 * d->NP * sizeof(float), "erf_conv_wgrad_im2col_tc: workspace too small");
+  size_t smem = (size_t)stages * stage_bytes + p.tail_bytes + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_im2col_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("erf_conv_wgrad_im2col_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return ERF_ERR_CUDA;
+  }
+  conv_wgrad_im2col_tc_kernel<<<grid, kWiThreads, smem, st>>>(p, stages, stage_bytes, g_bytes, groups, (float*)workspace);
+  const int per_cta = groups * 128 * d->NP;
+  wgrad_im2col_reduce_kernel<<<(per_cta + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, groups, p, dw);
+  ERF_CHECK_LAUNCH("erf_conv_wgrad_im2col_tc");
+  return ERF_OK;
+}

@@ -190,6 +190,20 @@ class _TcConv:
         plan = self.plans()[1]
         return ops.conv_im2col_tc(dy, ops.im2col_pack(w, self.spec, True, plan), plan, self.dspec, out_hw=out_hw)
 
+    def wgrad(self, x, dy, wparam, bparam, bias_is_zero):
+        """(dw, db) for autograd, accumulated in place when a gradient sink is active.  bias_is_zero: the conv feeds a
+        train-mode BatchNorm, so its bias gradient is exactly zero (see non_bottleneck_1d._bwd)."""
+        if ops.wgrad_im2col_supported(self.spec, x.dtype):
+            dw = ops.conv_wgrad_im2col_tc(x, dy, self.spec, dw_out=_sink(wparam))
+            bdst = _sink(bparam)
+            if bias_is_zero:
+                db = None if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
+            else:
+                db = bdst if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
+                ops.channel_sum_slice(dy, self.spec.cout, db)
+            return dw, db
+        return ops.conv_wgrad(x, dy, self.spec, dw_out=_sink(wparam), db_out=_sink(bparam))
+
 
 def _run(block, x, ctx):
     """Dispatch a block on an NHWC tensor: autograd path in training, folded kernels otherwise."""
@@ -280,7 +294,7 @@ class DownsamplerBlock(_B200Module):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
         dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
-        dw, db = ops.conv_wgrad(x, dyr, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
+        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=True)
         dx = None
         if need_dx:
             n, h, w, _ = x.shape
@@ -512,7 +526,7 @@ class UpsamplerBlock(_B200Module):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
         dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
-        dw, db = ops.conv_wgrad(x, dyr, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
+        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=True)
         dx = None
         if need_dx:
             if self._tc.bwd_ok(x.dtype):
@@ -568,7 +582,7 @@ class _PlainConv:
     def _bwd(self, dy, saved, need_dx):
         (x,) = saved
         cw, cb = self._train_params()
-        dw, db = ops.conv_wgrad(x, dy, self.spec, dw_out=_sink(cw), db_out=_sink(cb))
+        dw, db = self._tc.wgrad(x, dy, cw, cb, bias_is_zero=False)
         dx = None
         if need_dx:
             if self._tc.bwd_ok(x.dtype):

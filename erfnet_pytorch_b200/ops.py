@@ -343,6 +343,58 @@ def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional
     return out
 
 
+def wgrad_im2col_supported(spec: ConvSpec, dtype) -> bool:
+    """spec: the FORWARD conv.  The gathered side is x for a conv and dy for a transposed conv."""
+    return (dtype == torch.bfloat16 and not EMULATED and USE_TC and spec.cin <= 128 and spec.cout <= 128 and spec.stride in (1, 2)
+            and spec.kh * spec.kw <= 9 and spec.dil_h == 1 and spec.dil_w == 1)
+
+
+def conv_wgrad_im2col_tc(x: torch.Tensor, dy: torch.Tensor, spec: ConvSpec, dy_coff=0, dw_out=None):
+    """Weight gradient (torch parameter layout, fp32, ACCUMULATED into dw_out or a fresh zero tensor) on the tensor cores."""
+    n, h, w, xld = x.shape
+    _, ho, wo, dyld = dy.shape
+    if dw_out is None:
+        shape = (spec.cin, spec.cout, spec.kh, spec.kw) if spec.transposed else (spec.cout, spec.cin, spec.kh, spec.kw)
+        dw_out = torch.zeros(shape, device=x.device, dtype=torch.float32)
+    L = _lib.lib()
+    nbytes = L.erf_conv_wgrad_im2col_tc_workspace()
+    ws = _WS.get((x.device, nbytes))
+    if ws is None:
+        ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    if spec.transposed:   # gathered = dy (channels co), dense = x (channels ci)
+        g, gh, gw, gld, cg, goff = dy, ho, wo, dyld, spec.cout, dy_coff
+        dn, eh, ew, dld, cd, dbase = x, h, w, xld, spec.cin, 0
+    else:                 # gathered = x (channels ci), dense = dy (channels co)
+        g, gh, gw, gld, cg, goff = x, h, w, xld, spec.cin, 0
+        dn, eh, ew, dld, cd, dbase = dy, ho, wo, dyld, spec.cout, dy_coff
+    if goff:
+        raise RuntimeError("conv_wgrad_im2col_tc: the gathered operand must start at channel 0")
+    cgp = round_up(cg, 16)
+    avail = gld * 2                                   # bytes of the gathered pixel row
+    copy = 8 if avail < 16 else min(avail // 16 * 16, cgp * 2)
+    np_full = round_up(cd, 16)
+    taps = [(ky, kx) for ky in range(spec.kh) for kx in range(spec.kw)]
+    chg = 64 if cgp % 64 == 0 else 16
+    groups = -(-(len(taps) * (cgp // chg)) // (128 // chg))
+    npad = np_full
+    while groups * npad > 512 or (-(-(len(taps) * (cgp // chg) * 64 * chg * 2) // 1024) * 1024 + npad * 128) * 2 > 190 * 1024:
+        npad = round_up(npad // 2, 16)
+    name = f"conv_wgrad_im2col_tc[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_im2col_tc_kernel"
+    with _timed(name, conv_flops(spec, n, ho, wo)):
+        for n0 in range(0, np_full, npad):
+            d = _lib.WgradIm2colDesc()
+            d.g, d.GH, d.GW, d.g_ld, d.Cg, d.CgP, d.g_copy_bytes, d.g_step = g.data_ptr(), gh, gw, gld, cg, cgp, copy, spec.stride
+            d.d, d.EN, d.EH, d.EW, d.d_ld, d.d_c0, d.d_c_base, d.Cd = dn.data_ptr(), n, eh, ew, dld, dbase + n0, dbase, cd
+            d.NP = min(npad, np_full - n0)
+            d.ntaps = len(taps)
+            for i, (ky, kx) in enumerate(taps):
+                d.tap_dy[i], d.tap_dx[i], d.tap_off[i] = ky - spec.pad_h, kx - spec.pad_w, ky * spec.kw + kx
+            d.KHW = spec.kh * spec.kw
+            check(L.erf_conv_wgrad_im2col_tc(C.byref(d), _p(dw_out), _p(ws), nbytes, _stream(x)))
+            _count(2)
+    return dw_out
+
+
 _WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partial sums
 
 
@@ -422,6 +474,13 @@ def channel_sum(x, out):
     """out[c] += sum over pixels of x[..., c]"""
     n, h, w, c = x.shape
     check(_lib.lib().erf_channel_sum(_p(x), c, 0, c, n * h * w, _p(out), dt(x), _stream(x)))
+    _count()
+
+
+def channel_sum_slice(x, c, out):
+    """out[k] += sum over pixels of x[..., k] for k < c (x may be wider than c)."""
+    n, h, w, ld = x.shape
+    check(_lib.lib().erf_channel_sum(_p(x), ld, 0, c, n * h * w, _p(out), dt(x), _stream(x)))
     _count()
 
 
@@ -581,7 +640,7 @@ def _wrap_timed(name):
     globals()[name] = wrapper
 
 
-for _n in ("channel_stats", "channel_sum", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
+for _n in ("channel_stats", "channel_sum", "channel_sum_slice", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
            "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
            "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair"):
     _wrap_timed(_n)

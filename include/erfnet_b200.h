@@ -206,6 +206,19 @@ int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream);
 int erf_pack_im2col_weights(const float* w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
                             const erf_im2col_taps* taps, int Cin, int NP, void* img, erf_stream_t stream);
 
+/* Weight gradient of the same layers on the tensor cores: dw[((cd)*Cg + cg)*KHW + tap_off[t]] += sum over the dense-side
+ * pixels q of G[gather(q,t)][cg] * D[q][cd] (torch parameter layout for both nn.Conv2d -- G = x, D = dy -- and
+ * nn.ConvTranspose2d -- G = dy, D = x).  gather(q,t) = (g_step*y + tap_dy[t], g_step*x + tap_dx[t]) on G's (GH, GW) grid.
+ * The launch covers dense channels [d_c0, d_c0 + NP) of the pixel row (d_c_base = channel of the conv's channel 0). */
+typedef struct {
+  const void* g; int GH, GW, g_ld, Cg, CgP, g_copy_bytes, g_step;     /* gathered operand (M side) */
+  const void* d; int EN, EH, EW, d_ld, d_c0, d_c_base, Cd, NP;        /* dense operand (N side), its pixel grid is the loop */
+  int ntaps; int tap_dy[9]; int tap_dx[9]; int tap_off[9]; int KHW;
+  int tail_bytes;                                                     /* filled in by the library */
+} erf_wgrad_im2col_desc;
+size_t erf_conv_wgrad_im2col_tc_workspace(void);
+int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* dw, void* workspace, size_t ws_bytes, erf_stream_t stream);
+
 /* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
 /* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
  * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle

@@ -132,6 +132,10 @@ def channel_sum(x, out):
     out += x.float().sum((0, 1, 2))
 
 
+def channel_sum_slice(x, c, out):
+    out += x[..., :c].float().sum((0, 1, 2))
+
+
 def relu_bwd(g, mask):
     return (g.float() * (mask.float() > 0)).to(g.dtype)
 
@@ -235,7 +239,7 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, gra
     adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, int(step_dev), grad_scale)
 
 
-_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "relu_bwd", "bn_finalize",
+_NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "channel_sum_slice", "relu_bwd", "bn_finalize",
           "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev"]
 
 

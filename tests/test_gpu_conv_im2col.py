@@ -57,3 +57,27 @@ def test_forward_and_data_gradient(name, spec, nhw):
         dimgs = ops.im2col_pack(wt.cuda(), spec, True, dplan)
         dx = ops.conv_im2col_tc(dy.cuda(), dimgs, dplan, dspec, out_hw=(h, w))
         assert_rel(dx[..., :spec.cin].float().cpu().numpy(), gref.permute(0, 2, 3, 1).numpy(), 1e-2, name + " dgrad")
+
+
+WG_CASES = CASES[:5] + [("stem3_13", ConvSpec(3, 13, 3, 3, 2, 1, 1), (2, 20, 44))]
+
+
+@pytest.mark.parametrize("name,spec,nhw", WG_CASES, ids=[c[0] for c in WG_CASES])
+def test_weight_gradient(name, spec, nhw):
+    gen = torch.Generator().manual_seed(3 + len(name))
+    n, h, w = nhw
+    xld = ops.round_up(spec.cin, 4)
+    wshape = (spec.cin, spec.cout, spec.kh, spec.kw) if spec.transposed else (spec.cout, spec.cin, spec.kh, spec.kw)
+    x = torch.zeros(n, h, w, xld).bfloat16()
+    x[..., :spec.cin] = torch.randn(n, h, w, spec.cin, generator=gen).bfloat16()
+    wt = torch.zeros(*wshape, requires_grad=True)
+    y = _torch_fwd(x[..., :spec.cin].float().permute(0, 3, 1, 2), wt, None, spec)
+    ho, wo = y.shape[2:]
+    # dy lives in a wider tensor (the downsampler's concat gradient): extra channels hold unrelated data
+    dyld = ops.round_up(spec.cout, 8) + 8
+    dy = torch.randn(n, ho, wo, dyld, generator=gen).bfloat16()
+    (ref,) = torch.autograd.grad(y, wt, dy[..., :spec.cout].float().permute(0, 3, 1, 2))
+    assert ops.wgrad_im2col_supported(spec, torch.bfloat16)
+    dw = torch.full(wshape, 0.5, device="cuda")   # accumulates into existing contents
+    ops.conv_wgrad_im2col_tc(x.cuda(), dy.cuda(), spec, dw_out=dw)
+    assert_rel((dw.cpu() - 0.5).numpy(), ref.numpy(), 3e-3, name + " dW")
