@@ -25,6 +25,72 @@ __global__ void ce_weight_sum_kernel(const int64_t* __restrict__ target, long lo
 
 constexpr int CE_MAXC = 32;
 
+// NHWC bf16 fast path: one thread per pixel, the pixel's logits travel as LD8 16-byte vectors (LD8 = ld / 8, ld >= C)
+template <int LD8>
+__global__ void __launch_bounds__(128) ce_fwd_bwd_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+                                                                   long long n_px, const float* __restrict__ weight, int C, int ignore,
+                                                                   const float* __restrict__ wsum, float* __restrict__ loss_sum,
+                                                                   __nv_bfloat16* __restrict__ dlogits) {
+  float lsum = 0.f;
+  const float inv_w = 1.f / *wsum;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += (long long)gridDim.x * blockDim.x) {
+    float v[LD8 * 8];
+    const uint4* src = reinterpret_cast<const uint4*>(logits + (size_t)p * (LD8 * 8));
+#pragma unroll
+    for (int q = 0; q < LD8; ++q) {
+      const uint4 t4 = src[q];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[q * 8 + 2 * e] = __low2float(h[e]); v[q * 8 + 2 * e + 1] = __high2float(h[e]); }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < LD8 * 8; ++c)
+      if (c < C) mx = fmaxf(mx, v[c]);
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < LD8 * 8; ++c) {
+      v[c] = c < C ? __expf(v[c] - mx) : 0.f;
+      se += v[c];
+    }
+    const long long t = target[p];
+    const bool valid = t != ignore && t >= 0 && t < C;
+    const float w = valid ? (weight ? weight[t] : 1.f) : 0.f;
+    const float inv_se = 1.f / se;
+    if (valid) {
+      float pt = 0.f;
+#pragma unroll
+      for (int c = 0; c < LD8 * 8; ++c)
+        if (c == t) pt = v[c];
+      lsum += -w * __logf(pt * inv_se);
+    }
+    if (dlogits) {
+      const float k = w * inv_w;
+      uint4* dst = reinterpret_cast<uint4*>(dlogits + (size_t)p * (LD8 * 8));
+#pragma unroll
+      for (int q = 0; q < LD8; ++q) {
+        uint4 t4;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = q * 8 + 2 * e;
+          h[e] = __floats2bfloat162_rn(k * (v[c] * inv_se - (c == t ? 1.f : 0.f)), k * (v[c + 1] * inv_se - (c + 1 == t ? 1.f : 0.f)));
+        }
+        dst[q] = t4;   // padding channels (c >= C) get exactly 0 (v = 0, never the target)
+      }
+    }
+  }
+  lsum = warp_sum(lsum);
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lsum = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    lsum = warp_sum(lsum);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, lsum);
+  }
+}
+
 template <typename T>
 __global__ void ce_fwd_bwd_kernel(const T* __restrict__ logits, int ld, long long hw, const int64_t* __restrict__ target, long long n_px,
                                   const float* __restrict__ weight, int C, int ignore, const float* __restrict__ wsum,
@@ -148,6 +214,15 @@ extern "C" int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int
   ERF_CHECK_ARG(nchw_hw > 0 || ld >= C, "erf_ce_fwd_bwd: ld < C");
   long long blocks = (n_px + 127) / 128;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == ERF_BF16 && nchw_hw == 0 && (ld == 24 || ld == 32) &&
+      ((uintptr_t)logits % 16) == 0 && (!dlogits || ((uintptr_t)dlogits % 16) == 0)) {
+    if (ld == 24)
+      ce_fwd_bwd_nhwc_bf16_kernel<3><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+    else
+      ce_fwd_bwd_nhwc_bf16_kernel<4><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+    ERF_CHECK_LAUNCH("erf_ce_fwd_bwd");
+    return ERF_OK;
+  }
   if (dtype == ERF_F32)
     ce_fwd_bwd_kernel<float><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const float*)logits, ld, nchw_hw, target, n_px, weight, C, ignore_index, wsum, loss_sum, (float*)dlogits);
   else

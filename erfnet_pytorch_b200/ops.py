@@ -556,8 +556,8 @@ def ce_fwd_bwd(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torc
         hw, ld = logits.shape[2] * logits.shape[3], 0
     else:
         hw, ld = 0, logits.shape[-1]
-        if want_grad and ld > c:
-            dlog.zero_()
+        if want_grad and ld > c and not (logits.dtype == torch.bfloat16 and ld in (24, 32)):
+            dlog.zero_()   # (the vectorised bf16 kernel writes the padding channels itself)
     check(_lib.lib().erf_ce_fwd_bwd(_p(logits), ld, hw, _p(target), target.numel(), _p(weight), c, ignore_index, _p(wsum), _p(lsum), _p(dlog),
                                     dt(logits), _stream(logits)))
     _count()
