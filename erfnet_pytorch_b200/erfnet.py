@@ -10,6 +10,7 @@ Differences from the reference that a caller can observe:
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -144,6 +145,20 @@ def _tick(bn):
         bn.num_batches_tracked += 1
 
 
+_FIXED_DROPOUT = None  # {non_bottleneck_1d module: [N,C] Dropout2d multipliers} installed by fixed_dropout()
+
+
+@contextlib.contextmanager
+def fixed_dropout(scales):
+    """Parity runs: use the given Dropout2d multipliers (0 or 1/(1-p), [N,C] per block) instead of drawing them."""
+    global _FIXED_DROPOUT
+    prev, _FIXED_DROPOUT = _FIXED_DROPOUT, scales
+    try:
+        yield
+    finally:
+        _FIXED_DROPOUT = prev
+
+
 _WEIGHTS_EPOCH = 0  # bumped by code that updates parameters through aliases torch's version counters cannot see
 
 
@@ -270,11 +285,17 @@ class DownsamplerBlock(_B200Module):
 
     def _fwd_train(self, x, ctx):
         self._check(x)
-        if not self.use_batchnorm:
-            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
         n, h, w, _ = x.shape
         cc = self.noutput - self.ninput
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
+        if not self.use_batchnorm:  # train/erfnet_blocks.py:24-29: relu(cat(conv, pool)), both ReLUs in the producing kernels
+            if self._tc.fwd_ok(x.dtype):
+                self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), relu=True, out=y_raw)
+            else:
+                ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                             relu=True, out=y_raw)
+            ops.maxpool_fwd(x, self.ninput, y_raw, cc, relu=True)
+            return y_raw, (x, None, y_raw, None, None)
         stats = _stats_buf(self.bn, x.device)
         if self._tc.fwd_ok(x.dtype):
             self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), out=y_raw)
@@ -293,8 +314,11 @@ class DownsamplerBlock(_B200Module):
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
-        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
-        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=True)
+        if self.use_batchnorm:
+            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+        else:
+            dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
+        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=self.use_batchnorm)
         dx = None
         if need_dx:
             n, h, w, _ = x.shape
@@ -372,8 +396,9 @@ class non_bottleneck_1d(_B200Module):
         p = self.dropout.p
         if not (self.use_dropout and p != 0):  # eval/erfnet.py:58
             return None
-        if ctx.drop_scales is not None and self in ctx.drop_scales:
-            return ctx.drop_scales[self].to(x.device, torch.float32).reshape(x.shape[0], self.chann).contiguous()
+        fixed = ctx.drop_scales if ctx.drop_scales is not None else _FIXED_DROPOUT
+        if fixed is not None and self in fixed:
+            return fixed[self].to(x.device, torch.float32).reshape(x.shape[0], self.chann).contiguous()
         ones = torch.ones(x.shape[0], self.chann, 1, 1, device=x.device)
         return F.dropout2d(ones, p, True).reshape(x.shape[0], self.chann).contiguous()
 
@@ -394,8 +419,6 @@ class non_bottleneck_1d(_B200Module):
         return y
 
     def _fwd_train(self, x, ctx):
-        if not self.use_batchnorm:
-            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
         n, h, w, c = x.shape
         s, dtp = self.specs, x.dtype
         cv = self._convs()
@@ -407,6 +430,18 @@ class non_bottleneck_1d(_B200Module):
             pairs = None
             wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         bs = [m.bias.detach().float() for m in cv]
+        if not self.use_batchnorm:
+            # train/erfnet_blocks.py:55-73 without the BNs: conv+bias+ReLU chain, everything in the conv epilogues
+            t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
+            a2 = self._conv(1, t1, wp[1], bs[1], tc, relu=True)
+            t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True)
+            drop = self._drop_scale(x, ctx)
+            if drop is None:
+                out = self._conv(3, t3, wp[3], bs[3], tc, relu=True, add=x)
+            else:
+                y4 = self._conv(3, t3, wp[3], bs[3], tc)
+                out = ops.affine_act(y4, drop, torch.zeros_like(drop), res=x, relu=True)
+            return out, (x, t1, None, a2, t3, None, out, None, None, None, None, drop, pairs)
         count = n * h * w
         st = (_stats_buf(self.bn1, x.device), _stats_buf(self.bn2, x.device))
         t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
@@ -443,6 +478,8 @@ class non_bottleneck_1d(_B200Module):
 
         # The biases of conv1x3_1 / conv1x3_2 feed a train-mode BatchNorm: their gradient sum_p dy is EXACTLY zero
         # (sum_p xhat = 0), the reference only ever sees its rounding noise (~1e-9, far below Adam's eps = 1e-4) -> no kernel.
+        if not self.use_batchnorm:
+            return self._bwd_nobn(dout, saved, need_dx, tc, wd, ds, P, bias_dst)
         db2 = db4 = None if (_sink(P[3]) is not None) else torch.zeros(self.chann, device=dev, dtype=torch.float32)
         db1, db3 = bias_dst(P[1]), bias_dst(P[7])
         dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]), dbeta_out=_sink(P[11]))
@@ -460,6 +497,26 @@ class non_bottleneck_1d(_B200Module):
             dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)))
         _sunk(*P)
+        return dx, grads
+
+    def _bwd_nobn(self, dout, saved, need_dx, tc, wd, ds, P, bias_dst):
+        """Backward of the BN-free block: every ReLU mask and bias-gradient column sum rides in a data-gradient epilogue;
+        the BN parameters get no gradient (they are unused, as in the reference)."""
+        x, t1, _, a2, t3, _, out, _, _, _, _, drop, _ = saved
+        db1, db2, db3, db4 = bias_dst(P[1]), bias_dst(P[3]), bias_dst(P[7]), bias_dst(P[9])
+        gres = ops.relu_bwd(dout, out)                                                  # grad wrt (branch + x)
+        dy4 = gres if drop is None else ops.affine_act(gres, drop, torch.zeros_like(drop), relu=False)
+        ops.channel_sum(dy4, db4)
+        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
+        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3)
+        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
+        dy2 = self._conv(2, dt3, wd[2], None, tc, mask=a2, spec=ds[2], colsum=db2)
+        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
+        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1)
+        dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
+        dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0]) if need_dx else None
+        grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, None, None, dw3, db3, dw4, db4, None, None)))
+        _sunk(*P)  # the unused BN parameters count as done (their gradient stays zero)
         return dx, grads
 
     def _wgrad(self, i, x, dy, tc, wparam):
@@ -506,8 +563,13 @@ class UpsamplerBlock(_B200Module):
         return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
 
     def _fwd_train(self, x, ctx):
-        if not self.use_batchnorm:
-            raise RuntimeError("training with use_batchnorm=False is not implemented yet")
+        if not self.use_batchnorm:  # train/erfnet_blocks.py:84-88: relu(convT(x))
+            if self._tc.fwd_ok(x.dtype):
+                y = self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), relu=True)
+            else:
+                y = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
+                                 relu=True)
+            return y, (x, None, y, None, None)
         stats = _stats_buf(self.bn, x.device)
         if self._tc.fwd_ok(x.dtype):
             y_raw = self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float())
@@ -525,8 +587,11 @@ class UpsamplerBlock(_B200Module):
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
-        dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
-        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=True)
+        if self.use_batchnorm:
+            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+        else:
+            dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
+        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=self.use_batchnorm)
         dx = None
         if need_dx:
             if self._tc.bwd_ok(x.dtype):

@@ -607,6 +607,48 @@ def argmax(logits: torch.Tensor, c: int, nchw: bool, out_dtype=torch.int64) -> t
     return out
 
 
+LOSS_L1, LOSS_LOGLIK, LOSS_L1_CLASSPROB, LOSS_LOGLIK_CLASSPROB, LOSS_MSE_WEIGHTED = range(5)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"masked loss: {name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def masked_loss_fwd(kind: int, a, b, prob, target, eps: float, acc: torch.Tensor):
+    """acc (fp64 [2], caller-zeroed) += (sum of per-pixel losses, #labelled pixels); see include/erfnet_b200.h."""
+    n_px = target.numel()
+    if prob is not None:
+        hw, c = prob.shape[2] * prob.shape[3], prob.shape[1]
+    else:
+        hw, c = n_px, 0
+    check(_lib.lib().erf_masked_loss_fwd(kind, _p(a), _p(b), _p(prob), _p(target), n_px, hw, c, eps, _p(acc), _stream(target)))
+    _count()
+
+
+def masked_loss_bwd(kind: int, a, b, prob, target, eps: float, scale: float, acc, go):
+    """Gradients of scale * acc[0] / acc[1] times go: (d_a, d_b) for the per-pixel kinds, (d_prob, dclass fp64 [2C] UNSCALED)
+    for the class-probability kinds."""
+    n_px = target.numel()
+    if prob is not None:
+        hw, c = prob.shape[2] * prob.shape[3], prob.shape[1]
+        d_prob = torch.empty_like(prob)
+        dclass = torch.zeros(2 * c, device=prob.device, dtype=torch.float64)
+        d_a = d_b = None
+    else:
+        hw, c = n_px, 0
+        d_prob = dclass = None
+        d_a = torch.empty_like(a)
+        d_b = torch.empty_like(b) if kind == LOSS_LOGLIK else None
+    check(_lib.lib().erf_masked_loss_bwd(kind, _p(a), _p(b), _p(prob), _p(target), n_px, hw, c, eps, scale, _p(acc), _p(go), _p(d_a), _p(d_b),
+                                         _p(d_prob), _p(dclass), _stream(target)))
+    _count()
+    return (d_prob, dclass) if prob is not None else (d_a, d_b)
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(_lib.lib().erf_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, _stream(p)))
     _count()

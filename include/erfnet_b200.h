@@ -148,6 +148,28 @@ int erf_iou_counts(const unsigned long long* cm, int nc, int ignore, int kept, d
 int erf_argmax(const void* logits, int ld, int nchw_hw, long long n_px, int C, void* out, int out_elem_bytes,
                int dtype, erf_stream_t stream);
 
+/* ---- masked regression losses of the fork (train/evaluation_functions.py:32-131) -------------------------- */
+/* kind                      | a             | b            | prob        | per-pixel loss over labelled pixels (target != -1)
+ * ERF_LOSS_L1               | out [n_px]    | -            | -           | |a - t|                                  (L1LossMasked l.89-97)
+ * ERF_LOSS_LOGLIK           | mean [n_px]   | var [n_px]   | -           | log(2 pi (b+eps)) + (a-t)^2/(b+eps)      (LogLikelihoodLossMasked l.71-87)
+ * ERF_LOSS_L1_CLASSPROB     | cost [C]      | -            | [B,C,H,W]   | sum_c |a_c - t| prob_c                   (L1LossClassProbMasked l.32-47)
+ * ERF_LOSS_LOGLIK_CLASSPROB | cost [C]      | var [C]      | [B,C,H,W]   | sum_c (log(2 pi v_c) + (a_c-t)^2/v_c) prob_c, v_c = b_c+eps   (l.49-69)
+ * ERF_LOSS_MSE_WEIGHTED     | out [n_px]    | -            | -           | (a - t)^2 over ALL elements              (MSELossWeighted l.122-131)
+ * All operands fp32; target [n_px] float; hw = H*W (class kinds).  fwd: acc[0] += sum, acc[1] += count (fp64, caller-zeroed);
+ * loss = scale * acc[0] / acc[1].  bwd: gradients of that loss times go[0] (go may be NULL = 1): d_a/d_b [n_px] for the per-pixel
+ * kinds, d_prob [B,C,H,W] for the class kinds, whose per-class sums are ACCUMULATED UNSCALED into dclass[0..C) (cost) and
+ * dclass[C..2C) (variance) in fp64 (caller-zeroed; multiply by go*scale/acc[1]). */
+#define ERF_LOSS_L1 0
+#define ERF_LOSS_LOGLIK 1
+#define ERF_LOSS_L1_CLASSPROB 2
+#define ERF_LOSS_LOGLIK_CLASSPROB 3
+#define ERF_LOSS_MSE_WEIGHTED 4
+int erf_masked_loss_fwd(int kind, const float* a, const float* b, const float* prob, const float* target,
+                        long long n_px, long long hw, int C, float eps, double* acc, erf_stream_t stream);
+int erf_masked_loss_bwd(int kind, const float* a, const float* b, const float* prob, const float* target,
+                        long long n_px, long long hw, int C, float eps, float scale, const double* acc,
+                        const float* go, float* d_a, float* d_b, float* d_prob, double* dclass, erf_stream_t stream);
+
 /* ---- Adam as configured by train/main.py:43-46,213 (L2 in the gradient), over one flat fp32 buffer ------- */
 int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, erf_stream_t stream);

@@ -226,6 +226,50 @@ def cross_entropy_2d(logits, target, weight=None, ignore_index=-1):
     return (w * nll).sum() / w.sum()
 
 
+def _masked_mean(per_px, target):
+    """mean of per_px over the labelled pixels (target != -1): masked_select(...).mean() of the reference."""
+    m = target != -1.0
+    return (per_px * m).sum() / m.sum()
+
+
+def l1_loss_masked(outputs, targets):
+    """train/evaluation_functions.py:89-97: outputs [B,1,H,W], targets float [B,H,W]."""
+    return _masked_mean((outputs.squeeze(1) - targets).abs(), targets)
+
+
+def loglik_loss_masked(cost, var, targets, opt_eps=0.0):
+    """train/evaluation_functions.py:71-87 (the 1/2 factor of the Gaussian likelihood is dropped there too)."""
+    v = var + opt_eps
+    return _masked_mean((2 * math.pi * v).log() + (cost - targets) ** 2 / v, targets)
+
+
+def l1_loss_classprob_masked(prob, cost, targets):
+    """train/evaluation_functions.py:32-47: prob [B,C,H,W], cost [1,C,1,1], targets [B,H,W]."""
+    t = targets.unsqueeze(1)
+    return _masked_mean(((cost - t).abs() * prob).sum(1), targets)
+
+
+def loglik_loss_classprob_masked(prob, cost, var, targets, opt_eps=0.0):
+    """train/evaluation_functions.py:49-69."""
+    t = targets.unsqueeze(1)
+    v = var + opt_eps
+    return _masked_mean((((2 * math.pi * v).log() + (cost - t) ** 2 / v) * prob).sum(1), targets)
+
+
+def mse_loss_weighted(outputs, targets, scale_factor, weight):
+    """train/evaluation_functions.py:122-131."""
+    return ((outputs - targets) ** 2 * scale_factor * weight).mean()
+
+
+def accuracy_counts(prob, targets, n_classes):
+    """train/evaluation_functions.py:133-163 on integers: (n_correct, n_total, per-class correct, per-class total)."""
+    pred = prob.argmax(1)
+    correct = pred == targets
+    cc = np.array([int((correct & (targets == c)).sum()) for c in range(n_classes)], np.int64)
+    ct = np.array([int((targets == c).sum()) for c in range(n_classes)], np.int64)
+    return int(correct.sum()), int((targets >= 0).sum()), cc, ct
+
+
 def iou_counts(pred: np.ndarray, gt: np.ndarray, n_classes: int = 20, ignore_index: int = 19):
     """eval/iouEval.py:21-69 restated on integers.  pred, gt: integer label maps of identical shape.
     tp[c] = #(p==c & g==c); fp[c] = #(p==c & g!=c & g!=ignore); fn[c] = #(p!=c & g==c) for the kept classes

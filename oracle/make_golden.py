@@ -184,8 +184,108 @@ def main():
         kat[name + "_mean"], kat[name + "_iou"] = np.float64(mean), per.numpy()
         kat[name + "_pred"], kat[name + "_gt"] = p.numpy().astype(np.uint8), t.numpy().astype(np.uint8)
     np.savez_compressed(os.path.join(OUT, "iou_kat.npz"), **kat)
+    fork_losses(os.path.join(OUT, "fork_losses.npz"))
+    blocks_nobn(os.path.join(OUT, "blocks_nobn.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+NOBN_NB = {"nb64_d1_drop": (64, 1, (8, 24), 0.3, True), "nb128_d4": (128, 4, (8, 16), 0.1, False), "nb16_d1": (16, 1, (16, 24), 0.0, True),
+           "nb128_d16_drop": (128, 16, (18, 20), 0.1, True)}
+NOBN_DOWN = {"down3_16": (3, 16, (16, 32)), "down16_64": (16, 64, (8, 16)), "down64_128": (64, 128, (8, 8))}
+NOBN_UP = {"up128_64": (128, 64, (4, 8)), "up64_16": (64, 16, (8, 8))}
+
+
+def blocks_nobn(path):
+    """The fork's BN-free blocks (train/erfnet_blocks.py, use_batchnorm=False default) in train mode: output, dx, dW, db.
+    Dropout masks are drawn under a fixed seed and stored ([N,C] multipliers) so the tests can inject them."""
+    sys.path.insert(0, os.path.join(REF, "train"))
+    import erfnet_blocks as ref_blocks
+    res = {}
+
+    def load(m, seed):
+        bsd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=seed)
+        m.load_state_dict({k[4:]: v for k, v in bsd.items()}, strict=True)
+        m.train()
+
+    for name, (c, d, hw, p, use_dropout) in NOBN_NB.items():
+        m = ref_blocks.non_bottleneck_1d(c, p, d, use_dropout=use_dropout)
+        load(m, 13)
+        xb = (golden_input((2, c) + hw, 40 + d) - 0.3).requires_grad_(True)
+        torch.manual_seed(123)
+        yb = m(xb)
+        if use_dropout and p != 0:
+            torch.manual_seed(123)
+            res[name + "_drop"] = torch.nn.functional.dropout2d(torch.ones(2, c, 1, 1), p, True).reshape(2, c).numpy()
+        yb.backward(golden_input(tuple(yb.shape), 87) - 0.5)
+        res[name + "_y"], res[name + "_dx"] = yb.detach().numpy(), xb.grad.numpy()
+        for cn in ("conv3x1_1", "conv1x3_1", "conv3x1_2", "conv1x3_2"):
+            res[f"{name}_db_{cn}"] = getattr(m, cn).bias.grad.numpy()
+            if c <= 64 or cn in ("conv3x1_1", "conv1x3_2"):  # keeps the fixture small
+                res[f"{name}_dw_{cn}"] = getattr(m, cn).weight.grad.numpy()
+        assert m.bn1.weight.grad is None
+    for table, cls, seed, gseed in ((NOBN_DOWN, ref_blocks.DownsamplerBlock, 14, 88), (NOBN_UP, ref_blocks.UpsamplerBlock, 15, 89)):
+        for name, (ci, co, hw) in table.items():
+            m = cls(ci, co)
+            load(m, seed)
+            xb = (golden_input((2, ci) + hw, 50 + ci) - 0.3).requires_grad_(True)
+            yb = m(xb)
+            yb.backward(golden_input(tuple(yb.shape), gseed) - 0.5)
+            res[name + "_y"], res[name + "_dx"] = yb.detach().numpy(), xb.grad.numpy()
+            res[name + "_dw"], res[name + "_db"] = m.conv.weight.grad.numpy(), m.conv.bias.grad.numpy()
+    # DecoderBlock / DecoderBlockSmall (train/erfnet_blocks.py:114-135): upsampler + 1-2 nb1d blocks chained
+    for name, cls in (("decblock64_16", ref_blocks.DecoderBlock), ("decblocksmall64_16", ref_blocks.DecoderBlockSmall)):
+        m = cls(64, 16)
+        load(m, 16)
+        xb = (golden_input((2, 64, 6, 8), 61) - 0.3).requires_grad_(True)
+        yb = m(xb)
+        yb.backward(golden_input(tuple(yb.shape), 90) - 0.5)
+        res[name + "_y"], res[name + "_dx"] = yb.detach().numpy(), xb.grad.numpy()
+        res[name + "_dw_up"] = m.layers[0].conv.weight.grad.numpy()
+        res[name + "_db_last"] = m.layers[-1].conv1x3_2.bias.grad.numpy()
+    np.savez_compressed(path, **res)
+
+
+def fork_loss_inputs():
+    """Deterministic operands of the fork-loss KATs (regenerated by the tests, not stored)."""
+    b, c, h, w = 2, 6, 12, 20
+    tgt = golden_input((b, h, w), 21) * 2.0
+    tgt[golden_input((b, h, w), 22) < 0.6] = -1.0                      # ~60 % unlabelled pixels
+    return dict(out=golden_input((b, 1, h, w), 23) * 2.0, var=golden_input((b, h, w), 24) + 0.05, target=tgt,
+                prob=torch.softmax((golden_input((b, c, h, w), 25) - 0.5) * 4, 1), cost=golden_input((1, c, 1, 1), 26) * 2.0,
+                cvar=golden_input((1, c, 1, 1), 27) + 0.1, teacher=golden_input((b, 1, h, w), 28) * 2.0,
+                labels=golden_labels((b, h, w), 29, n_classes=c))
+
+
+def fork_losses(path):
+    """KATs of the fork's masked regression losses and accuracy metrics (train/evaluation_functions.py:32-163)."""
+    import warnings
+    sys.path.insert(0, os.path.join(REF, "train"))
+    warnings.simplefilter("ignore")
+    import evaluation_functions as ref_ev
+    d = fork_loss_inputs()
+    res = {}
+
+    def run(name, crit, args, grad_idx):
+        leaves = [a.clone().requires_grad_(i in grad_idx) for i, a in enumerate(args)]
+        loss = crit(*leaves)
+        loss.backward()
+        res[name + "_loss"] = np.float64(loss.item())
+        for i in grad_idx:
+            res[f"{name}_g{i}"] = leaves[i].grad.numpy()
+
+    run("l1", ref_ev.L1LossMasked(), (d["out"], d["target"]), (0,))
+    run("loglik", ref_ev.LogLikelihoodLossMasked(opt_eps=1e-4), (d["out"][:, 0], d["var"], d["target"]), (0, 1))
+    run("l1cp", ref_ev.L1LossClassProbMasked(), (d["prob"], d["cost"], d["target"]), (0, 1))
+    run("loglikcp", ref_ev.LogLikelihoodLossClassProbMasked(opt_eps=1e-4), (d["prob"], d["cost"], d["cvar"], d["target"]), (0, 1, 2))
+    leaves = [d["out"].clone().requires_grad_(True), d["teacher"].clone().requires_grad_(True)]
+    loss = ref_ev.MSELossWeighted(3.0)(leaves[0], leaves[1], 0.25)
+    loss.backward()
+    res["mse_loss"], res["mse_g0"], res["mse_g1"] = np.float64(loss.item()), leaves[0].grad.numpy(), leaves[1].grad.numpy()
+    acc = ref_ev.ClassificationAccuracy()(d["prob"], d["labels"])
+    macc, cacc = ref_ev.MeanAccuracy(d["prob"].shape[1])(d["prob"], d["labels"])
+    res["acc"], res["mean_acc"], res["class_acc"] = np.float64(acc.item()), np.float64(macc.item()), np.array([float(v) for v in cacc])
+    np.savez_compressed(path, **res)
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@ The product never imports this; on a GPU box the same Python drives the real ker
 from __future__ import annotations
 
 import contextlib
+import math
 
 import torch
 import torch.nn.functional as F
@@ -239,8 +240,55 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, gra
     adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, int(step_dev), grad_scale)
 
 
+def _ml_per_px(kind, a, b, prob, target, eps):
+    """per-pixel loss of erf_masked_loss_* (include/erfnet_b200.h) on flat fp32 operands, shape of target"""
+    t = target
+    if kind == ops.LOSS_L1:
+        return (a.reshape(t.shape) - t).abs()
+    if kind == ops.LOSS_LOGLIK:
+        v = b.reshape(t.shape) + eps
+        return (2 * math.pi * v).log() + (a.reshape(t.shape) - t) ** 2 / v
+    if kind == ops.LOSS_MSE_WEIGHTED:
+        return (a.reshape(t.shape) - t) ** 2
+    c = prob.shape[1]
+    tt = t.reshape(prob.shape[0], 1, prob.shape[2], prob.shape[3])
+    d = a.reshape(1, c, 1, 1) - tt
+    if kind == ops.LOSS_L1_CLASSPROB:
+        val = d.abs()
+    else:
+        v = b.reshape(1, c, 1, 1) + eps
+        val = (2 * math.pi * v).log() + d * d / v
+    return (val * prob).sum(1).reshape(t.shape)
+
+
+def masked_loss_fwd(kind, a, b, prob, target, eps, acc):
+    valid = torch.ones_like(target, dtype=torch.bool) if kind == ops.LOSS_MSE_WEIGHTED else target != -1.0
+    per = _ml_per_px(kind, a, b, prob, target, eps)
+    acc[0] += (per * valid).double().sum()
+    acc[1] += valid.double().sum()
+
+
+@torch.enable_grad()
+def masked_loss_bwd(kind, a, b, prob, target, eps, scale, acc, go):
+    target = target.detach()
+    valid = torch.ones_like(target, dtype=torch.bool) if kind == ops.LOSS_MSE_WEIGHTED else target != -1.0
+    leaves = [None if t is None else t.detach().clone().requires_grad_(True) for t in (a, b, prob)]
+    per = _ml_per_px(kind, leaves[0], leaves[1], leaves[2], target, eps)
+    g = float(go.reshape(-1)[0]) * scale / float(acc[1])
+    if prob is None:
+        ((per * valid).sum() * g).backward()
+        return leaves[0].grad.detach(), None if b is None else leaves[1].grad.detach()
+    (per * valid).sum().backward()  # class sums stay unscaled
+    c = prob.shape[1]
+    dclass = torch.zeros(2 * c, dtype=torch.float64)
+    dclass[:c] = leaves[0].grad.reshape(-1).double()
+    if b is not None:
+        dclass[c:] = leaves[1].grad.reshape(-1).double()
+    return (leaves[2].grad * g).detach(), dclass
+
+
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "channel_sum_slice", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev"]
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd"]
 
 
 @contextlib.contextmanager

@@ -194,6 +194,20 @@ def test_iou_eval_kat(golden_dir):
         np.testing.assert_allclose(float(mean), float(g[name + "_mean"]), rtol=1e-12)
 
 
+def test_blocks_without_batchnorm(golden_dir):
+    """Fork default (use_batchnorm=False): train-mode forward/backward wiring of all three blocks, kernels emulated."""
+    from tests.nobn_cases import check_blocks_nobn
+    with emulated_kernels():
+        check_blocks_nobn(golden_dir, "cpu")
+
+
+def test_fork_losses_host_logic(golden_dir):
+    """Masked regression losses / accuracy metrics: autograd wiring and shapes, kernels emulated."""
+    from tests.fork_loss_cases import check_fork_losses
+    with emulated_kernels():
+        check_fork_losses(golden_dir, "cpu")
+
+
 def test_no_cpu_fallback():
     """Without the emulation (and without a GPU) the product must fail loudly, never compute on the CPU."""
     if torch.cuda.is_available():

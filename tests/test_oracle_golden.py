@@ -144,3 +144,69 @@ def test_iou_kat(golden_dir):
         mean, per = O.iou_from_counts(tp + tp2, fp + fp2, fn + fn2)
         np.testing.assert_allclose(per, g[name + "_iou"], rtol=1e-12)
         np.testing.assert_allclose(mean, float(g[name + "_mean"]), rtol=1e-12)
+
+
+def _fork_oracle_cases(d):
+    """name -> (oracle loss fn, operands, indices of the operands that receive gradients)"""
+    return {
+        "l1": (O.l1_loss_masked, (d["out"], d["target"]), (0,)),
+        "loglik": (lambda c, v, t: O.loglik_loss_masked(c, v, t, 1e-4), (d["out"][:, 0], d["var"], d["target"]), (0, 1)),
+        "l1cp": (O.l1_loss_classprob_masked, (d["prob"], d["cost"], d["target"]), (0, 1)),
+        "loglikcp": (lambda p, c, v, t: O.loglik_loss_classprob_masked(p, c, v, t, 1e-4), (d["prob"], d["cost"], d["cvar"], d["target"]), (0, 1, 2)),
+        "mse": (lambda a, b: O.mse_loss_weighted(a, b, 3.0, 0.25), (d["out"], d["teacher"]), (0, 1)),
+    }
+
+
+def test_fork_losses(golden_dir):
+    """Masked regression losses + accuracy metrics of the fork vs the reference's own classes (fork_losses.npz)."""
+    from oracle.make_golden import fork_loss_inputs
+    z = np.load(os.path.join(golden_dir, "fork_losses.npz"))
+    d = fork_loss_inputs()
+    for name, (fn, args, gidx) in _fork_oracle_cases(d).items():
+        leaves = [a.clone().requires_grad_(i in gidx) for i, a in enumerate(args)]
+        loss = fn(*leaves)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), z[name + "_loss"], rtol=1e-5)
+        for i in gidx:
+            np.testing.assert_allclose(leaves[i].grad.numpy(), z[f"{name}_g{i}"], rtol=1e-4, atol=1e-7, err_msg=f"{name} grad {i}")
+    nc, nt, cc, ct = O.accuracy_counts(d["prob"], d["labels"], d["prob"].shape[1])
+    np.testing.assert_allclose(nc / nt, z["acc"], rtol=1e-6)
+    with np.errstate(invalid="ignore"):
+        ca = cc / ct
+    np.testing.assert_allclose(ca, z["class_acc"], rtol=1e-6)
+    np.testing.assert_allclose(np.nanmean(ca), z["mean_acc"], rtol=1e-6)
+
+
+def test_blocks_without_batchnorm(golden_dir):
+    """Oracle blocks with use_batchnorm=False vs the fork's own BN-free blocks (train/erfnet_blocks.py), train mode."""
+    from oracle.make_golden import NOBN_DOWN, NOBN_NB, NOBN_UP
+    g = np.load(os.path.join(golden_dir, "blocks_nobn.npz"))
+
+    def leaves(shapes, seed):
+        sd = _blk_sd(shapes, seed)
+        return {k: (v.clone().requires_grad_(True) if (v.dtype.is_floating_point and "running" not in k) else v) for k, v in sd.items()}
+
+    for name, (c, d, hw, p, use_dropout) in NOBN_NB.items():
+        sd = leaves(_nb_shapes(c), 13)
+        x = (golden_input((2, c) + hw, 40 + d) - 0.3).requires_grad_(True)
+        drop = torch.from_numpy(g[name + "_drop"]).view(2, c, 1, 1) if name + "_drop" in g.files else None
+        y = O.non_bottleneck_1d(x, sd, "blk", d, dropprob=p if (use_dropout and drop is not None) else 0.0, training=True, drop_scale=drop,
+                                use_batchnorm=False)
+        y.backward(golden_input(tuple(y.shape), 87) - 0.5)
+        np.testing.assert_allclose(y.detach().numpy(), g[name + "_y"], **TOL)
+        np.testing.assert_allclose(x.grad.numpy(), g[name + "_dx"], rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(sd["blk.conv1x3_1.bias"].grad.numpy(), g[name + "_db_conv1x3_1"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(sd["blk.conv3x1_1.weight"].grad.numpy(), g[name + "_dw_conv3x1_1"], rtol=1e-3, atol=1e-4)
+    full = O.erfnet_param_shapes(20)
+    for table, fn, seed, gseed, pref in ((NOBN_DOWN, O.downsampler_block, 14, 88, {3: "encoder.initial_block.", 16: "encoder.layers.0.", 64: "encoder.layers.6."}),
+                                         (NOBN_UP, O.upsampler_block, 15, 89, {128: "decoder.layers.0.", 64: "decoder.layers.3."})):
+        for name, (ci, co, hw) in table.items():
+            shapes = {k[len(pref[ci]):]: s for k, s in full.items() if k.startswith(pref[ci])}
+            sd = leaves(shapes, seed)
+            x = (golden_input((2, ci) + hw, 50 + ci) - 0.3).requires_grad_(True)
+            y = fn(x, sd, "blk", training=True, use_batchnorm=False)
+            y.backward(golden_input(tuple(y.shape), gseed) - 0.5)
+            np.testing.assert_allclose(y.detach().numpy(), g[name + "_y"], **TOL)
+            np.testing.assert_allclose(x.grad.numpy(), g[name + "_dx"], rtol=1e-3, atol=1e-5)
+            np.testing.assert_allclose(sd["blk.conv.weight"].grad.numpy(), g[name + "_dw"], rtol=1e-3, atol=1e-4)
+            np.testing.assert_allclose(sd["blk.conv.bias"].grad.numpy(), g[name + "_db"], rtol=1e-3, atol=1e-4)
