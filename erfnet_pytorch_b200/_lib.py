@@ -54,7 +54,7 @@ _SIGNATURES = {
     "erf_bn_finalize": [_vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "erf_bn_eval_affine": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "erf_bn_bwd_reduce": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
-    "erf_bn_bwd_apply": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "erf_bn_bwd_apply": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "erf_ce_weight_sum": [_vp, _ll, _vp, _i, _i, _vp, _vp],
     "erf_ce_fwd_bwd": [_vp, _i, _i, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "erf_confusion_hist": [_vp, _vp, _i, _ll, _i, _vp, _vp],
@@ -67,6 +67,7 @@ _SIGNATURES = {
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "erf_pack_conv1d_tc": [_vp, _i, _vp, _vp, _vp],
+    "erf_pack_conv1d_tc_batched": [_vp, _i, _i, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],

@@ -43,24 +43,8 @@ struct Conv1dTcParams {
   float* colsum;                // [C]  += per-channel sum of the stored output (bias gradient of the producing conv), or null
 };
 
-// Transposed warp reduction: every lane holds 32 values v[0..31] (one pixel, 32 channels); on return lane j holds the sum
-// over the 32 lanes of v[j].  31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 constexpr int kMaxSlots = 8;
-constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups
+constexpr int kThreads = 352;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warp 10 statistics MMAs
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -84,19 +68,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   constexpr int STG_PAD = ((STG_BYTES + 1023) / 1024) * 1024;
   constexpr int STG_TOTAL = 4 * STG_PAD;        // 2 epilogue groups x double buffer
   constexpr int EW = C >= 32 ? 32 : 16;         // epilogue column chunk
-  constexpr uint32_t TMEM_COLS = 2 * C < 32 ? 32 : 2 * C;
+  // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) ride on the tensor pipe: the staged output
+  // sub-tile Y [128 px][64 ch] is an MN-major operand, so  Y^T Y (Gram, diagonal = sum of squares) and  Y^T 1  (sums) are
+  // two more accumulating MMAs per sub-tile, issued by warp 10 into their own TMEM columns and read once at the end.
+  constexpr bool RED = CH == 64;
+  constexpr uint32_t GRAM_COL = 2 * C, ONES_COL = 2 * C + KC * 64;         // KC x 64 Gram columns, KC x 16 sum columns
+  constexpr uint32_t TMEM_COLS = C == 128 ? 512 : (C == 64 ? 256 : 32);
   constexpr uint32_t IDESC = make_idesc_bf16(128, C);
+  constexpr uint32_t IDESC_GRAM = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);  // both operands MN-major
+  constexpr uint32_t IDESC_ONES = make_idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;
   uint8_t* s_stg = smem + W_PAD;
   uint8_t* s_a = s_stg + STG_TOTAL;
+  uint8_t* s_ones = s_a + (size_t)p.slots * p.slot_bytes;   // 512 B of bf16 1.0 (statistics mode only)
   __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar[4];
+  __shared__ uint64_t sfull_bar[4], sdone_bar[4], sfinal_bar;   // staged sub-tile ready / statistics MMAs done (per group x buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[C];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < C; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  const bool want_red = RED && (p.stats != nullptr || p.colsum != nullptr);
+  if (want_red) {
+    for (int i = tid; i < 128; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   if (tid == 0) {
     for (int s = 0; s < p.slots; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -107,7 +105,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       mbar_init(&tempty_bar[a], 4);
     }
     mbar_init(&w_bar, 1);
-    for (int a = 0; a < 4; ++a) mbar_init(&aux_bar[a], 1);
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(&aux_bar[a], 1);
+      mbar_init(&sfull_bar[a], 1);
+      mbar_init(&sdone_bar[a], 1);
+    }
+    mbar_init(&sfinal_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_out);
@@ -209,6 +212,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (warp == 10) {
+    // ================= statistics MMAs: Y^T Y and Y^T 1 of every staged sub-tile =================
+    if (RED && want_red && lane == 0) {
+      const uint32_t hi128 = ((8u * 128u) >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);   // MN-major, 8 pixel rows of 128 B per atom
+      const uint32_t hi32 = ((8u * 32u) >> 4) | (1u << 14) | (LAYOUT_SW32 << 29);      // the ones operand: 16 "channels" = 32-byte rows
+      const uint32_t ones_addr = smem_u32(s_ones);
+      const uint64_t d_ones = ((uint64_t)hi32 << 32) | (uint64_t)((ones_addr >> 4) & 0x3FFF);
+      int cnt[2] = {0, 0};
+      uint32_t ph[4] = {0, 0, 0, 0};
+      uint32_t started = 0;   // bit kc: the accumulators of k-chunk kc hold data
+      int i = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
+        const int g = i & 1;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          const int b = cnt[g] & 1;
+          ++cnt[g];
+          mbar_wait(&sfull_bar[g * 2 + b], ph[g * 2 + b]);
+          ph[g * 2 + b] ^= 1;
+          tcgen05_fence_after();
+          const uint32_t tile = smem_u32(s_stg + (g * 2 + b) * STG_PAD);
+          // M = 128 = two 64-channel atoms: the sub-tile and (LBO away) whatever follows it in shared memory (the next staging
+          // buffer or the operand ring); rows 64..127 of D are never read and cannot influence rows 0..63
+          const uint32_t a_lo = ((tile >> 4) & 0x3FFF) | (((STG_PAD >> 4) & 0x3FFF) << 16);
+          const uint32_t b_lo = ((tile >> 4) & 0x3FFF) | (1u << 16);
+          const uint32_t acc_en = (started >> kc) & 1u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // K = 128 pixels, 16 per MMA = 16 rows of 128 B
+            const uint64_t da = ((uint64_t)hi128 << 32) | (uint64_t)(a_lo + k * 128);
+            if (p.stats)
+              umma_bf16(tmem_base + GRAM_COL + kc * 64, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * 128), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
+            umma_bf16(tmem_base + ONES_COL + kc * 16, da, d_ones, IDESC_ONES, (acc_en | k) ? 1u : 0u);
+          }
+          started |= 1u << kc;
+          umma_commit(&sdone_bar[g * 2 + b]);
+        }
+      }
+      umma_commit(&sfinal_bar);
+    }
   } else {
     // ================= epilogue: group 0 = warps 2..5, group 1 = warps 6..9; TMEM lane quadrant = warp % 4 =========
     const int grp = (warp - 2) >> 2;
@@ -222,11 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     const uint32_t acc = grp;                  // accumulator owned by this group
     uint32_t acc_phase = 0, aux_phase[2] = {0, 0};
     int step = 0;                              // staging steps (unit, k-chunk) done by this group
-    constexpr int NCH = C >= 32 ? C / 32 : 1;  // 32-column chunks per pixel row
-    float red_sum[NCH], red_sq[NCH];           // this lane's column of each chunk, accumulated over all units of the CTA
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) red_sum[i] = red_sq[i] = 0.f;
-    const bool want_red = (p.stats != nullptr || p.colsum != nullptr) && EW == 32;
+    uint32_t sdone_phase[2] = {0, 0};
     // units of this CTA alternate between the two groups
     const int u_first = blockIdx.x + grp * gridDim.x, u_stride = 2 * gridDim.x;
     if (leader && p.aux_mode && u_first < p.units) {   // aux prefetch for the very first step
@@ -300,25 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
             uint4 t;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-              // statistics are taken over the values as STORED (bf16), which is what the consumer normalises
-              v[q * 8 + 2 * e] = __low2float(h[e]);
-              v[q * 8 + 2 * e + 1] = __high2float(h[e]);
-            }
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
             *reinterpret_cast<uint4*>(my_row + (((j0 + q) ^ sw_key) * 16)) = t;
-          }
-          if constexpr (EW == 32) {
-            if (want_red) {
-              const int ch = (kc * CH + c0) / 32;
-              if (p.stats) {
-                float sq[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-                red_sq[ch] += warp_colsum32(sq, lane);
-              }
-              red_sum[ch] += warp_colsum32(v, lane);
-            }
           }
         }
         fence_proxy_async_smem();              // staging writes -> visible to the TMA store
@@ -327,6 +348,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
         if (leader) {
           tma_store_4d(&tmap_out, stg_g + b * STG_PAD, kc * CH, xs * 128, y, n);
           tma_store_commit();
+          if (want_red) mbar_arrive(&sfull_bar[grp * 2 + b]);   // statistics are taken over the values as STORED (bf16)
+        }
+        if (want_red && step >= 1) {           // the statistics MMAs of the previous step have read the other buffer
+          mbar_wait(&sdone_bar[grp * 2 + (b ^ 1)], sdone_phase[b ^ 1]);
+          sdone_phase[b ^ 1] ^= 1;
+        }
+        if (leader) {
           if (p.aux_mode) {                    // prefetch the aux sub-tile of the NEXT step into the other buffer
             int nkc = kc + 1, nu = u;
             if (nkc == KC) { nkc = 0; nu = u + u_stride; }
@@ -340,15 +368,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait0();
-    if (want_red) {
+    if constexpr (RED) {
+      if (want_red && grp == 0 && quad < 2) {   // TMEM lanes 0..63 = the 64 channels of a k-chunk: one atomic per channel and CTA
+        mbar_wait(&sfinal_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c = i * 32 + lane;
-        if (p.stats) {
-          atomicAdd(&p.stats[c], (double)red_sum[i]);
-          atomicAdd(&p.stats[C + c], (double)red_sq[i]);
+        for (int kc = 0; kc < KC; ++kc) {
+          const int c = kc * 64 + quad * 32 + lane;
+          uint32_t o[16];
+          tmem_ld16(tmem_base + ONES_COL + kc * 16 + lane_bits, o);
+          tmem_ld_wait();
+          const float sum = __uint_as_float(o[0]);
+          if (p.colsum) atomicAdd(&p.colsum[c], sum);
+          if (p.stats) {
+            uint32_t g0[32], g1[32];
+            tmem_ld32(tmem_base + GRAM_COL + kc * 64 + lane_bits, g0);
+            tmem_ld32(tmem_base + GRAM_COL + kc * 64 + 32 + lane_bits, g1);
+            tmem_ld_wait();
+            float sq = 0.f;   // the diagonal element: column (quad*32 + lane) of this thread's row
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j == lane) sq = __uint_as_float(quad == 0 ? g0[j] : g1[j]);
+            }
+            atomicAdd(&p.stats[c], (double)sum);
+            atomicAdd(&p.stats[C + c], (double)sq);
+          }
         }
-        if (p.colsum) atomicAdd(&p.colsum[c], red_sum[i]);
       }
     }
   }
@@ -433,14 +479,15 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.slot_bytes = p.sub_bytes;   // one (tap, k-chunk) tile [vertical] or one k-chunk of the haloed row tile [horizontal]
   const int w_pad = ((3 * KC * C * RB + 1023) / 1024) * 1024;
   const int stg_pad = 4 * (((128 * RB + 1023) / 1024) * 1024);
-  const int budget = 225 * 1024 - w_pad - stg_pad;
+  const int ones_bytes = ((stats || colsum) && C >= 64) ? 1024 : 0;   // bf16 ones operand of the statistics MMAs
+  const int budget = 225 * 1024 - w_pad - stg_pad - ones_bytes;
   p.slots = budget / p.slot_bytes;
   if (p.slots > kMaxSlots) p.slots = kMaxSlots;
   if (p.slots < 2) {
     set_error("erf_conv1d_tc: tile does not fit in shared memory");
     return ERF_ERR_UNSUPPORTED;
   }
-  size_t smem = (size_t)w_pad + stg_pad + (size_t)p.slots * p.slot_bytes + 1024;
+  size_t smem = (size_t)w_pad + stg_pad + (size_t)p.slots * p.slot_bytes + ones_bytes + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -165,10 +165,13 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   }
 }
 
-// dw[co][ci][t] (the nn.Conv2d layout [Co,Ci,3,1] / [Co,Ci,1,3]) += sum over CTAs of the partial accumulators
+// dw[co][ci][t] (the nn.Conv2d layout [Co,Ci,3,1] / [Co,Ci,1,3]) += sum over CTAs of the partial accumulators.
+// The CTA range is split over blockIdx.y (the partials are 10-29 MB spread over <=148 slabs: one thread per output walking all
+// slabs serially is latency-bound), four independent partial sums per thread keep loads in flight, one atomic per split.
 template <int C>
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
   constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
+  constexpr size_t SLAB = (size_t)ACCS * 128 * C;
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*C*C
   if (i >= 3 * C * C) return;
   int co = i % C, ci = (i / C) % C, t = i / (C * C);
@@ -176,10 +179,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas,
   if (C == 128) { acc = t; row = ci; }
   else if (C == 64) { acc = t == 2 ? 1 : 0; row = (t == 0 ? 0 : 64) + ci; }
   else { acc = 0; row = t * 16 + ci; }
+  const int per = (grid_ctas + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(b0 + per, grid_ctas);
   const float* src = ws + ((size_t)acc * 128 + row) * C + co;
-  float s = 0.f;
-  for (int b = 0; b < grid_ctas; ++b) s += src[(size_t)b * ACCS * 128 * C];
-  dw[((size_t)co * C + ci) * 3 + t] += s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = b0;
+  for (; b + 4 <= b1; b += 4) {
+    s0 += src[(size_t)b * SLAB];
+    s1 += src[(size_t)(b + 1) * SLAB];
+    s2 += src[(size_t)(b + 2) * SLAB];
+    s3 += src[(size_t)(b + 3) * SLAB];
+  }
+  for (; b < b1; ++b) s0 += src[(size_t)b * SLAB];
+  if (b1 > b0) atomicAdd(&dw[((size_t)co * C + ci) * 3 + t], (s0 + s1) + (s2 + s3));
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -252,19 +264,19 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<16><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<16><<<(3 * 16 * 16 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+      wgrad_reduce_kernel<16><<<dim3((3 * 16 * 16 + 255) / 256, 37), 256, 0, s>>>(p.ws, grid, dw);
     }
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<64><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<64><<<(3 * 64 * 64 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+      wgrad_reduce_kernel<64><<<dim3((3 * 64 * 64 + 255) / 256, 16), 256, 0, s>>>(p.ws, grid, dw);
     }
   } else {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<128><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<128><<<(3 * 128 * 128 + 255) / 256, 256, 0, s>>>(p.ws, grid, dw);
+      wgrad_reduce_kernel<128><<<dim3((3 * 128 * 128 + 255) / 256, 6), 256, 0, s>>>(p.ws, grid, dw);
     }
   }
   if (e != cudaSuccess) {

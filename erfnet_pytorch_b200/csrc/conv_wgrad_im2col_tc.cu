@@ -202,9 +202,18 @@ __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int cta
   const int tap = atom / gsubs, sub = atom % gsubs;
   const int cg = sub * CHg + row % CHg, cd = p.d_c0 - p.d_c_base + col;
   if (tap >= p.ntaps || cg >= p.Cg || cd >= p.Cd) return;
-  float s = 0.f;
-  for (int b = 0; b < ctas; ++b) s += ws[(size_t)b * per_cta + i];
-  dw[((size_t)cd * p.Cg + cg) * p.KHW + p.tap_off[tap]] += s;
+  const int per = (ctas + gridDim.y - 1) / gridDim.y;  // CTA range split over blockIdx.y, one atomic per split
+  const int b0 = blockIdx.y * per, b1 = min(b0 + per, ctas);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = b0;
+  for (; b + 4 <= b1; b += 4) {
+    s0 += ws[(size_t)b * per_cta + i];
+    s1 += ws[(size_t)(b + 1) * per_cta + i];
+    s2 += ws[(size_t)(b + 2) * per_cta + i];
+    s3 += ws[(size_t)(b + 3) * per_cta + i];
+  }
+  for (; b < b1; ++b) s0 += ws[(size_t)b * per_cta + i];
+  if (b1 > b0) atomicAdd(&dw[((size_t)cd * p.Cg + cg) * p.KHW + p.tap_off[tap]], (s0 + s1) + (s2 + s3));
 }
 
 }  // namespace erfk
@@ -256,7 +265,9 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   }
   conv_wgrad_im2col_tc_kernel<<<grid, kWiThreads, smem, st>>>(p, stages, stage_bytes, g_bytes, groups, (float*)workspace);
   const int per_cta = groups * 128 * d->NP;
-  wgrad_im2col_reduce_kernel<<<(per_cta + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, groups, p, dw);
+  const int rblocks = (per_cta + 255) / 256;
+  const int rsplit = rblocks >= 148 ? 4 : (rblocks >= 32 ? 12 : 37);
+  wgrad_im2col_reduce_kernel<<<dim3(rblocks, rsplit), 256, 0, st>>>((const float*)workspace, grid, groups, p, dw);
   ERF_CHECK_LAUNCH("erf_conv_wgrad_im2col_tc");
   return ERF_OK;
 }

@@ -255,7 +255,8 @@ template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ mask,
                                     int mask_ld, const float* __restrict__ drop, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
-                                    long long HW, int C, long long n_px, T* __restrict__ dy, int dy_ld, float* dgamma, float* dbeta) {
+                                    long long HW, int C, long long n_px, T* __restrict__ dy, int dy_ld, float* dgamma, float* dbeta,
+                                    T* __restrict__ gmasked, int gmasked_ld) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (pixel, 8-channel group)
   if (i < C) {
     if (dbeta) dbeta[i] = (float)sums[i];
@@ -271,6 +272,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* 
   if (mask) mv.load(mask + (size_t)p * mask_ld + c0);
   const float* dp = drop ? drop + (p / HW) * C + c0 : nullptr;
   const float inv_m = 1.f / (float)n_px;
+  if (gmasked) {  // g * (mask > 0): the ReLU backward the residual path needs, produced while g and mask are in registers
+    Vec<T, 8> gm;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gm.v[k] = (mask && !(mv.v[k] > 0.f)) ? 0.f : (float)gv.v[k];
+    gm.store(gmasked + (size_t)p * gmasked_ld + c0);
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float gg = gv.v[k];
@@ -285,12 +292,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int g_ld, const T* 
 
 // tcgen05 operand images of a 3-tap conv weight w[Co][Ci][3] (fp32): forward Wt[t][n=co][k=ci] and data-gradient
 // Wt'[t][n=ci][k=co] = w[co][ci][2-t]; layout [3][C/64][C][8 chunks of 8], chunk index XOR-swizzled by (n & 7).
-__global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_bfloat16* __restrict__ img_fwd, __nv_bfloat16* __restrict__ img_dgrad) {
+__device__ __forceinline__ void pack_conv1d_tc_body(const float* __restrict__ w, int C, __nv_bfloat16* __restrict__ img_fwd,
+                                                    __nv_bfloat16* __restrict__ img_dgrad, int i) {
   const int ch = C < 64 ? C : 64;   // channels per K chunk (one swizzle row)
   const int cpr = ch / 8;           // 16-byte chunks per row: 8 (128B swizzle) or 2 (32B swizzle)
   const int kc_n = C / ch;
   const int total = 3 * kc_n * C * cpr;  // 16-byte chunks per image
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * total) return;
   const bool dgrad = i >= total;
   if (dgrad) i -= total;
@@ -304,6 +311,16 @@ __global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_b
     v.v[e] = dgrad ? w[((size_t)k * C + n) * 3 + (2 - t)] : w[((size_t)n * C + k) * 3 + t];
   }
   v.store((dgrad ? img_dgrad : img_fwd) + (size_t)i * 8);
+}
+
+__global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_bfloat16* __restrict__ img_fwd, __nv_bfloat16* __restrict__ img_dgrad) {
+  pack_conv1d_tc_body(w, C, img_fwd, img_dgrad, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// every 3-tap conv of the net in ONE launch (blockIdx.y = table entry): the per-step weight re-pack of a training step
+__global__ void pack_conv1d_tc_batched_kernel(const erf_pack1d_entry* __restrict__ table) {
+  const erf_pack1d_entry e = table[blockIdx.y];
+  pack_conv1d_tc_body(e.w, e.C, (__nv_bfloat16*)e.img_fwd, (__nv_bfloat16*)e.img_dgrad, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -478,8 +495,9 @@ extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_l
 
 extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* drop,
                                 const float* gamma, const float* mean, const float* invstd, const double* sums, int N, int HW, int C, void* dy,
-                                int dy_ld, float* dgamma, float* dbeta, int dtype, erf_stream_t stream) {
+                                int dy_ld, float* dgamma, float* dbeta, void* gmasked, int gmasked_ld, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_bn_bwd_apply");
+  ERF_CHECK_ARG(!gmasked || (gmasked_ld % 8) == 0, "erf_bn_bwd_apply: gmasked_ld must be a multiple of 8");
   ERF_CHECK_ARG(g && y && gamma && mean && invstd && sums && dy && N > 0 && HW > 0 && C >= 8 && (C % 8) == 0 && (g_ld % 8) == 0 && (y_ld % 8) == 0 &&
                     (dy_ld % 8) == 0 && (!mask || (mask_ld % 8) == 0),
                 "erf_bn_bwd_apply: C and leading dimensions must be multiples of 8");
@@ -488,9 +506,9 @@ extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld
   if (work < C) work = C;
   unsigned grid = (unsigned)((work + 255) / 256);
   if (dtype == ERF_F32)
-    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (float*)dy, dy_ld, dgamma, dbeta);
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (float*)dy, dy_ld, dgamma, dbeta, (float*)gmasked, gmasked_ld);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta, (__nv_bfloat16*)gmasked, gmasked_ld);
   ERF_CHECK_LAUNCH("erf_bn_bwd_apply");
   return ERF_OK;
 }
@@ -513,6 +531,15 @@ extern "C" int erf_adam_step_dev(float* p, const float* g, float* m, float* v, l
   adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
   adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr);
   ERF_CHECK_LAUNCH("erf_adam_step_dev");
+  return ERF_OK;
+}
+
+extern "C" int erf_pack_conv1d_tc_batched(const erf_pack1d_entry* table_dev, int n_entries, int max_C, erf_stream_t stream) {
+  ERF_CHECK_ARG(table_dev && n_entries > 0 && n_entries <= 65535 && (max_C == 16 || max_C == 64 || max_C == 128),
+                "erf_pack_conv1d_tc_batched: bad arguments (n=%d, max_C=%d)", n_entries, max_C);
+  int total = 2 * 3 * max_C * (max_C / 8);
+  pack_conv1d_tc_batched_kernel<<<dim3((total + 255) / 256, n_entries), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  ERF_CHECK_LAUNCH("erf_pack_conv1d_tc_batched");
   return ERF_OK;
 }
 

@@ -145,6 +145,8 @@ def _tick(bn):
         bn.num_batches_tracked += 1
 
 
+_PREPACKED_FRESH = False  # True while FlatAdamTrainer runs a forward right after its batched weight re-pack
+
 _FIXED_DROPOUT = None  # {non_bottleneck_1d module: [N,C] Dropout2d multipliers} installed by fixed_dropout()
 
 
@@ -424,7 +426,8 @@ class non_bottleneck_1d(_B200Module):
         cv = self._convs()
         tc = self._use_tc(x)
         if tc:
-            pairs = [ops.pack_conv1d_tc_pair(m.weight) for m in cv]  # forward + data-gradient images, one launch per conv
+            # forward + data-gradient images: pre-packed for this step by the trainer's batched launch, else one launch per conv
+            pairs = (self.__dict__.get("_prepacked") if _PREPACKED_FRESH else None) or [ops.pack_conv1d_tc_pair(m.weight) for m in cv]
             wp = [pr[0] for pr in pairs]
         else:
             pairs = None
@@ -482,7 +485,8 @@ class non_bottleneck_1d(_B200Module):
             return self._bwd_nobn(dout, saved, need_dx, tc, wd, ds, P, bias_dst)
         db2 = db4 = None if (_sink(P[3]) is not None) else torch.zeros(self.chann, device=dev, dtype=torch.float32)
         db1, db3 = bias_dst(P[1]), bias_dst(P[7])
-        dy4, dg2, dbe2 = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]), dbeta_out=_sink(P[11]))
+        dy4, dg2, dbe2, gres = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]),
+                                          dbeta_out=_sink(P[11]), want_masked=True)  # gres = dout * (out > 0): the residual path's gradient
         dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
         dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3)     # grad wrt conv3x1_2's output
         dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
@@ -493,7 +497,6 @@ class non_bottleneck_1d(_B200Module):
         dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
         dx = None
         if need_dx:
-            gres = ops.relu_bwd(dout, out)
             dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)))
         _sunk(*P)

@@ -222,6 +222,36 @@ def pack_conv1d_tc_pair(w: torch.Tensor):
     return imgs[0], imgs[1]
 
 
+class Conv1dPackTable:
+    """Device table for erf_pack_conv1d_tc_batched: every listed Conv2d weight [C,C,3,1]/[C,C,1,3] (fp32, contiguous, fixed
+    address -- e.g. views of a flat parameter buffer) is re-packed into persistent (forward, data-gradient) images by ONE launch."""
+
+    def __init__(self, weights):
+        import struct
+        dev = weights[0].device
+        sizes = [3 * w.shape[0] * w.shape[0] for w in weights]
+        self.images = torch.empty(2 * sum(sizes), device=dev, dtype=torch.bfloat16)
+        self.pairs, rows, off = [], b"", 0
+        for w, n in zip(weights, sizes):
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                raise RuntimeError("Conv1dPackTable: weights must be contiguous fp32")
+            f, d = self.images[off:off + n], self.images[off + n:off + 2 * n]
+            off += 2 * n
+            self.pairs.append((f, d))
+            rows += struct.pack("<QQQii", w.data_ptr(), f.data_ptr(), d.data_ptr(), w.shape[0], 0)
+        self._ptrs = [w.data_ptr() for w in weights]
+        self._weights = weights
+        self.table = torch.frombuffer(bytearray(rows), dtype=torch.uint8).to(dev)
+        self.n, self.max_c = len(weights), max(w.shape[0] for w in weights)
+
+    def valid(self):
+        return all(w.data_ptr() == p for w, p in zip(self._weights, self._ptrs))
+
+    def run(self):
+        check(_lib.lib().erf_pack_conv1d_tc_batched(_p(self.table), self.n, self.max_c, _stream(self.table)))
+        _count()
+
+
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
               res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -519,9 +549,10 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
 _BN_SUMS = {}  # (device, C) -> fp64 [2C] scratch for the BN-backward reductions
 
 
-def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None):
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False):
     """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c].
-    dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step)."""
+    dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step).
+    want_masked: also return g*(mask>0) as a 4th value (written by the apply pass, saves a separate relu_bwd)."""
     n, h, w, c = y.shape
     sums = _BN_SUMS.get((y.device, c))
     if sums is None:
@@ -534,10 +565,11 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbe
     dy = torch.empty_like(y)
     dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
     dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
+    gm = torch.empty_like(y) if want_masked else None
     check(L.erf_bn_bwd_apply(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(gamma), _p(mean),
-                             _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), dt(y), _stream(y)))
+                             _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), _p(gm), c, dt(y), _stream(y)))
     _count(2)
-    return dy, dgamma, dbeta
+    return (dy, dgamma, dbeta, gm) if want_masked else (dy, dgamma, dbeta)
 
 
 def ce_weight_sum(target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int, wsum: torch.Tensor):

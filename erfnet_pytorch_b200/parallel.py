@@ -78,6 +78,14 @@ class FlatAdamTrainer:
             self.flat_nbt[i] = bn.num_batches_tracked
             bn.num_batches_tracked = self.flat_nbt[i]       # a 0-dim view: state_dict() keeps reporting it
             bn.__dict__["_erf_nbt_managed"] = True
+        # tcgen05 operand images of all 3-tap convs, re-packed from the flat parameters by one launch per step
+        self._pack_table = None
+        if dev.type == "cuda" and not ops.EMULATED:
+            blocks = [m for m in model.modules() if isinstance(m, _erfnet.non_bottleneck_1d) and m.chann in (16, 64, 128)]
+            if blocks:
+                self._pack_table = ops.Conv1dPackTable([c.weight.data for b in blocks for c in b._convs()])
+                for i, b in enumerate(blocks):
+                    b.__dict__["_prepacked"] = self._pack_table.pairs[4 * i:4 * i + 4]
         self._pending = list(self._bucket_params)
         self._launched = [False, False, False]
         self._works = []
@@ -142,7 +150,15 @@ class FlatAdamTrainer:
         self.flat_g.zero_()
         self.flat_nbt.add_(1)
         self.model.train()
-        logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
+        if self._pack_table is not None:
+            if not self._pack_table.valid():
+                raise RuntimeError("FlatAdamTrainer: a conv weight was re-allocated after the trainer took ownership of the parameters")
+            self._pack_table.run()
+            _erfnet._PREPACKED_FRESH = True
+        try:
+            logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
+        finally:
+            _erfnet._PREPACKED_FRESH = False
         c = self.num_classes
         w = self.criterion.weight
         labels = labels.contiguous()

@@ -123,11 +123,12 @@ int erf_bn_eval_affine(const float* gamma, const float* beta, const float* runni
 int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld,
                       const float* drop, const float* mean, const float* invstd, int N, int HW, int C,
                       double* sums, int dtype, erf_stream_t stream);
-/* dy = gamma*invstd*(gb - sums[c]/M - xhat*sums[C+c]/M); also writes dgamma = sums[C+c], dbeta = sums[c]. */
+/* dy = gamma*invstd*(gb - sums[c]/M - xhat*sums[C+c]/M); also writes dgamma = sums[C+c], dbeta = sums[c] and, when gmasked is
+ * given, gmasked = g * (mask>0) (the ReLU backward of the residual path, eval/erfnet.py:61). */
 int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld,
                      const float* drop, const float* gamma, const float* mean, const float* invstd,
                      const double* sums, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta,
-                     int dtype, erf_stream_t stream);
+                     void* gmasked, int gmasked_ld, int dtype, erf_stream_t stream);
 
 /* ---- CrossEntropyLoss2d (train/evaluation_functions.py:6-14) ------------------------------------------- */
 /* logits element (p, c): NHWC -> logits[p*ld + c]; NCHW (nchw_hw > 0) -> logits[(p/hw)*C*hw + c*hw + p%hw].
@@ -195,6 +196,16 @@ int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* ou
 /* Build both operand images (forward and data-gradient) of a 3-tap conv weight w[Co][Ci][3] fp32 (= nn.Conv2d weight
  * [Co,Ci,3,1] or [Co,Ci,1,3], contiguous) for erf_conv1d_tc; each image is 3*C*C bf16. */
 int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream);
+/* All 3-tap convs of a net in one launch: table (DEVICE memory) of n_entries {fp32 weight, forward image, data-gradient
+ * image, C}; max_C = largest C in the table.  Same images as erf_pack_conv1d_tc. */
+typedef struct erf_pack1d_entry {
+  const float* w;
+  void* img_fwd;
+  void* img_dgrad;
+  int C;
+  int reserved;
+} erf_pack1d_entry;
+int erf_pack_conv1d_tc_batched(const erf_pack1d_entry* table_dev, int n_entries, int max_C, erf_stream_t stream);
 
 /* tcgen05 weight gradient of the same convolutions: dw[co][ci][t] += sum_p x[p + (t-1)*dil][ci] * dy[p][co]  (fp32, in
  * the nn.Conv2d weight layout [Co,Ci,3,1] == [Co,Ci,1,3]; ACCUMULATED, e.g. straight into the parameter's .grad).  Both NHWC operands are consumed MN-major; per-CTA TMEM accumulators are dumped to
