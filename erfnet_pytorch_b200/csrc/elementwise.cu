@@ -2,6 +2,7 @@
 // downsampler, BatchNorm statistics / apply / backward, residual+ReLU, Adam.  All coalesced along the channel
 // (innermost NHWC) dimension; per-channel reductions use shared-memory partials + one atomic per block/channel.
 #include "common.cuh"
+#include "bn_stream.cuh"
 
 namespace erfk {
 
@@ -413,6 +414,17 @@ extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const
   ERF_CHECK_ARG(x && out && N > 0 && HW > 0 && C > 0 && (C % 4) == 0 && (x_ld % 4) == 0 && (out_ld % 4) == 0 && (!res || (res_ld % 4) == 0),
                 "erf_affine_act: C and leading dimensions must be multiples of 4");
   ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "erf_affine_act: scale and shift must be given together");
+  if (bs_fast_ok(C) && (x_ld % 8) == 0 && (out_ld % 8) == 0 && (!res || (res_ld % 8) == 0) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+      ((uintptr_t)res % 16) == 0) {
+    const long long n_px = (long long)N * HW;
+    const BsLaunch l = bs_launch(C, n_px, 4);
+    if (dtype == ERF_F32)
+      affine_act_v2_kernel<float><<<l.grid, BS_THREADS, 0, (cudaStream_t)stream>>>((const float*)x, x_ld, scale, shift, sc_per_sample, (const float*)res, res_ld, (float*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
+    else
+      affine_act_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_ld, scale, shift, sc_per_sample, (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
+    ERF_CHECK_LAUNCH("erf_affine_act");
+    return ERF_OK;
+  }
   long long total4 = (long long)N * HW * (C / 4);
   unsigned grid = (unsigned)((total4 + 255) / 256);
   if (dtype == ERF_F32)
@@ -426,6 +438,15 @@ extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const
 extern "C" int erf_channel_stats(const void* x, int ld, int C, long long n_px, double* stats, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_channel_stats");
   ERF_CHECK_ARG(x && stats && n_px > 0 && C >= 8 && (C % 8) == 0 && C <= 2048 && (ld % 8) == 0, "erf_channel_stats: C and ld must be multiples of 8");
+  if (bs_fast_ok(C) && ((uintptr_t)x % 16) == 0) {
+    const BsLaunch l = bs_launch(C, n_px, 2);
+    if (dtype == ERF_F32)
+      channel_reduce_v2_kernel<float, true, double><<<l.grid, BS_THREADS, l.smem(C, 2), (cudaStream_t)stream>>>((const float*)x, ld, C, n_px, l.px_per_block, stats);
+    else
+      channel_reduce_v2_kernel<__nv_bfloat16, true, double><<<l.grid, BS_THREADS, l.smem(C, 2), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, C, n_px, l.px_per_block, stats);
+    ERF_CHECK_LAUNCH("erf_channel_stats");
+    return ERF_OK;
+  }
   long long want = 148 * 2;
   long long ppb = (n_px + want - 1) / want;
   if (ppb < 128) ppb = 128;
@@ -480,7 +501,17 @@ extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_l
                     (!mask || (mask_ld % 8) == 0),
                 "erf_bn_bwd_reduce: C and leading dimensions must be multiples of 8");
   long long n_px = (long long)N * HW;
+  if (bs_fast_ok(C) && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)mask % 16) == 0) {
+    const BsLaunch l = bs_launch(C, n_px, 2);
+    if (dtype == ERF_F32)
+      bn_bwd_reduce_v2_kernel<float><<<l.grid, BS_THREADS, l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
+    else
+      bn_bwd_reduce_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
+    ERF_CHECK_LAUNCH("erf_bn_bwd_reduce");
+    return ERF_OK;
+  }
   long long want = 148 * 2;
+  const int thr = 256;
   long long ppb = (n_px + want - 1) / want;
   if (ppb < 64) ppb = 64;
   unsigned grid = (unsigned)((n_px + ppb - 1) / ppb);
@@ -488,7 +519,7 @@ extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_l
   if (dtype == ERF_F32)
     bn_bwd_reduce_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, (int)ppb, sums);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, (int)ppb, sums);
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, thr, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, (int)ppb, sums);
   ERF_CHECK_LAUNCH("erf_bn_bwd_reduce");
   return ERF_OK;
 }
@@ -502,6 +533,16 @@ extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld
                     (dy_ld % 8) == 0 && (!mask || (mask_ld % 8) == 0),
                 "erf_bn_bwd_apply: C and leading dimensions must be multiples of 8");
   long long n_px = (long long)N * HW;
+  if (bs_fast_ok(C) && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)mask % 16) == 0 && ((uintptr_t)dy % 16) == 0 &&
+      ((uintptr_t)gmasked % 16) == 0) {
+    const BsLaunch l = bs_launch(C, n_px, 4);
+    if (dtype == ERF_F32)
+      bn_bwd_apply_v2_kernel<float><<<l.grid, BS_THREADS, 4 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (float*)dy, dy_ld, dgamma, dbeta, (float*)gmasked, gmasked_ld);
+    else
+      bn_bwd_apply_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, 4 * C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta, (__nv_bfloat16*)gmasked, gmasked_ld);
+    ERF_CHECK_LAUNCH("erf_bn_bwd_apply");
+    return ERF_OK;
+  }
   long long work = n_px * (C / 8);
   if (work < C) work = C;
   unsigned grid = (unsigned)((work + 255) / 256);
