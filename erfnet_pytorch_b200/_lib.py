@@ -25,7 +25,8 @@ class ConvEpilogue(C.Structure):
 class Im2colDesc(C.Structure):
     _fields_ = ([("in_", C.c_void_p)] + [(n, C.c_int) for n in ("H", "W", "in_ld", "Cin", "EN", "EH", "EW", "in_step", "ntaps")] +
                 [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p)] +
-                [(n, C.c_int) for n in ("Ho", "Wo", "out_ld", "out_c0", "out_step", "out_oy", "out_ox", "NP", "n_valid", "relu", "units")])
+                [(n, C.c_int) for n in ("Ho", "Wo", "out_ld", "out_c0", "out_step", "out_oy", "out_ox", "NP", "n_valid", "relu", "units",
+                                        "in_step_x", "out_step_x", "bias_period")])
 
 
 class WgradIm2colDesc(C.Structure):
@@ -35,7 +36,7 @@ class WgradIm2colDesc(C.Structure):
 
 
 class Im2colTaps(C.Structure):
-    _fields_ = [("ntaps", C.c_int), ("off", C.c_longlong * 9)]
+    _fields_ = [("ntaps", C.c_int), ("off", C.c_longlong * 9), ("n_split", C.c_int), ("off2", C.c_longlong * 9)]
 
 
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double

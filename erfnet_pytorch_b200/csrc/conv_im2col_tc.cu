@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
   const long long total = (long long)p.EN * p.EH * p.EW;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < NP; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  for (int i = tid; i < NP; i += blockDim.x)
+    s_bias[i] = (p.bias && i < p.n_valid) ? (p.bias_period > 0 ? p.bias[(p.out_c0 + i) % p.bias_period] : p.bias[i]) : 0.f;
+  const int in_step_x = p.in_step_x > 0 ? p.in_step_x : p.in_step, out_step_x = p.out_step_x > 0 ? p.out_step_x : p.out_step;
   if (tid == 0) {
     for (int s = 0; s < slots; ++s) {
       mbar_init(&full_bar[s], 128);   // one arrival per loader thread
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
         for (int i = 0; i < 8; ++i) {
           if (i < iters) {
             const int row = i * rows_per_iter + r0;
-            const int iy = p.in_step * ry[i] + dy, ix = p.in_step * rx[i] + dx;
+            const int iy = p.in_step * ry[i] + dy, ix = in_step_x * rx[i] + dx;
             const bool ok = rn[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
             const __nv_bfloat16* src = ok ? in + (((size_t)rn[i] * p.H + iy) * p.W + ix) * p.in_ld + j * 8 : in;
             const int key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
         const int x = (int)(q % p.EW);
         const long long t2 = q / p.EW;
         const int y = (int)(t2 % p.EH), n = (int)(t2 / p.EH);
-        dst = outp + (((size_t)n * p.Ho + (p.out_step * y + p.out_oy)) * p.Wo + (p.out_step * x + p.out_ox)) * p.out_ld + p.out_c0;
+        dst = outp + (((size_t)n * p.Ho + (p.out_step * y + p.out_oy)) * p.Wo + (out_step_x * x + p.out_ox)) * p.out_ld + p.out_c0;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -247,7 +249,12 @@ __global__ void pack_im2col_weights_kernel(const float* __restrict__ w, long lon
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kc * CH + j * 8 + e;
-    v.v[e] = (n0 + n < n_src && k < k_src) ? w[(long long)(n0 + n) * stride_n + (long long)k * stride_k + taps.off[t]] : 0.f;
+    int nn = n0 + n;
+    long long off = taps.off[t];
+    if (taps.n_split > 0) {   // column-folded image: n = b * n_split + c
+      if (nn >= taps.n_split) { nn -= taps.n_split; off = nn < taps.n_split ? taps.off2[t] : -1; }
+    }
+    v.v[e] = (off >= 0 && nn < n_src && k < k_src) ? w[(long long)nn * stride_n + (long long)k * stride_k + off] : 0.f;
   }
   v.store(img + (size_t)i * 8);
 }

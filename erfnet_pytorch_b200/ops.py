@@ -281,10 +281,16 @@ def im2col_supported(spec_g: ConvSpec, dtype) -> bool:
             and spec_g.stride in (1, 2) and spec_g.kh * spec_g.kw <= 9)
 
 
-def im2col_plan(spec_g: ConvSpec):
-    """One dict per launch (class of output pixels sharing a tap list, and an N range)."""
+MERGE_ROW_PARITY = True   # stride-2 transposed gathers: fold the two column parities into N (whole-row writes, 2 launches not 4)
+
+
+def im2col_plan(spec_g: ConvSpec, row_parity: Optional[bool] = None):
+    """One dict per launch (class of output pixels sharing a tap list, and an N range).  row_parity (default: MERGE_ROW_PARITY)
+    selects the whole-row form of stride-2 transposed gathers, which needs a dense output tensor of round8(cout) channels."""
     s = spec_g.stride
     classes = []
+    if spec_g.transposed and s == 2 and (MERGE_ROW_PARITY if row_parity is None else row_parity):
+        return _im2col_plan_row_parity(spec_g)
     if not spec_g.transposed:
         taps = [(ky, kx, ky * spec_g.dil_h - spec_g.pad_h, kx * spec_g.dil_w - spec_g.pad_w) for ky in range(spec_g.kh) for kx in range(spec_g.kw)]
         classes.append(dict(taps=taps, in_step=s, out_step=1, oy=0, ox=0, div=1))
@@ -318,6 +324,46 @@ def im2col_plan(spec_g: ConvSpec):
     return plan
 
 
+def _im2col_plan_row_parity(spec_g: ConvSpec):
+    """Stride-2 transposed gather in row-parity form: one class per output row parity a; its N axis is (b, c) = (column parity,
+    channel), so pixel (y, x) of the input grid writes the 2*cout8 contiguous values of output row 2y+a at columns 2x, 2x+1.
+    A tap is an input offset (dy, dx) plus, per column parity, the kernel element that multiplies it (None = no contribution)."""
+    c8 = round_up(spec_g.cout, 8)
+    plan = []
+    for a in range(2):
+        taps = {}
+        for b in range(2):
+            for ky in range(spec_g.kh):
+                ty = a + spec_g.pad_h - ky * spec_g.dil_h
+                if ty % 2:
+                    continue
+                for kx in range(spec_g.kw):
+                    tx = b + spec_g.pad_w - kx * spec_g.dil_w
+                    if tx % 2:
+                        continue
+                    taps.setdefault((ty // 2, tx // 2), [None, None])[b] = (ky, kx)
+        if not taps:
+            continue
+        tl = [(k0, k1, dy, dx) for (dy, dx), (k0, k1) in sorted(taps.items())]
+        n_total = 2 * c8
+        np_full = 16
+        while np_full < n_total:
+            np_full *= 2
+        npad = min(np_full, 128)
+        while len(tl) * round_up(spec_g.cin, 16) * npad * 2 > 96 * 1024 and npad > 16:
+            npad //= 2
+        for n0 in range(0, n_total, npad):
+            # a chunk that lies inside one column parity only needs the taps feeding that parity
+            if n0 + npad <= c8:
+                tc = [t for t in tl if t[0] is not None]
+            elif n0 >= c8:
+                tc = [t for t in tl if t[1] is not None]
+            else:
+                tc = tl
+            plan.append(dict(taps=tc, in_step=1, out_step=2, oy=a, ox=0, div=2, n0=n0, NP=npad, n_valid=min(n_total - n0, npad), merged=c8))
+    return plan
+
+
 def im2col_pack(w: torch.Tensor, spec_fwd: ConvSpec, dgrad: bool, plan):
     """bf16 weight images (one per plan entry) from the fp32 torch weight of the FORWARD conv spec_fwd."""
     w = w.detach().contiguous().float()
@@ -334,8 +380,14 @@ def im2col_pack(w: torch.Tensor, spec_fwd: ConvSpec, dgrad: bool, plan):
     for e in plan:
         taps = _lib.Im2colTaps()
         taps.ntaps = len(e["taps"])
-        for i, (ky, kx, _, _) in enumerate(e["taps"]):
-            taps.off[i] = ky * spec_fwd.kw + kx
+        if e.get("merged"):
+            taps.n_split = e["merged"]
+            for i, (k0, k1, _, _) in enumerate(e["taps"]):
+                taps.off[i] = -1 if k0 is None else k0[0] * spec_fwd.kw + k0[1]
+                taps.off2[i] = -1 if k1 is None else k1[0] * spec_fwd.kw + k1[1]
+        else:
+            for i, (ky, kx, _, _) in enumerate(e["taps"]):
+                taps.off[i] = ky * spec_fwd.kw + kx
         img = torch.empty(len(e["taps"]) * cin_g * e["NP"], device=w.device, dtype=torch.bfloat16)
         check(L.erf_pack_im2col_weights(_p(w), stride_n, stride_k, e["n0"], n_src, k_src, C.byref(taps), cin_g, e["NP"], _p(img), _stream(w)))
         _count()
@@ -364,9 +416,17 @@ def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional
             for i, (_, _, dy, dx) in enumerate(e["taps"]):
                 d.tap_dy[i], d.tap_dx[i] = dy, dx
             d.w_img = img.data_ptr()
-            d.bias = None if bias is None else bias.data_ptr() + 4 * e["n0"]
-            d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo, out.shape[-1], out_coff + e["n0"]
-            d.out_step, d.out_oy, d.out_ox = e["out_step"], e["oy"], e["ox"]
+            if e.get("merged"):
+                if out.shape[-1] != e["merged"] or out_coff != 0 or wo % 2:
+                    raise RuntimeError(f"conv_im2col_tc: row-parity form needs a dense output of {e['merged']} channels (got ld {out.shape[-1]}, offset {out_coff})")
+                d.bias = None if bias is None else bias.data_ptr()
+                d.bias_period = e["merged"]
+                d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo // 2, 2 * out.shape[-1], e["n0"]
+                d.out_step, d.out_step_x, d.out_oy, d.out_ox = 2, 1, e["oy"], 0
+            else:
+                d.bias = None if bias is None else bias.data_ptr() + 4 * e["n0"]
+                d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo, out.shape[-1], out_coff + e["n0"]
+                d.out_step, d.out_oy, d.out_ox = e["out_step"], e["oy"], e["ox"]
             d.NP, d.n_valid, d.relu = e["NP"], e["n_valid"], int(relu)
             check(L.erf_conv_im2col_tc(C.byref(d), _stream(x)))
             _count()

@@ -231,10 +231,16 @@ typedef struct {
   void* out; int Ho, Wo, out_ld, out_c0, out_step, out_oy, out_ox;
   int NP, n_valid, relu;                            /* NP = padded N (16/32/64/128); n_valid % 8 == 0 */
   int units;                                        /* filled in by the library */
+  int in_step_x, out_step_x;                        /* 0: same as in_step / out_step; else the column step differs from the row step */
+  int bias_period;                                  /* 0: bias[n]; else bias[(out_c0 + n) % bias_period] (column-folded outputs) */
 } erf_im2col_desc;
-typedef struct { int ntaps; long long off[9]; } erf_im2col_taps;
+/* Row-parity form of a stride-2 transposed conv: the two column parities b of an output row are folded into N (n = b*n_split + c),
+ * the output is addressed as [N][Ho][Wo/2][2*ld] with out_step = 2 (rows) and out_step_x = 1, so each launch writes whole rows.
+ * In the weight image tap t then holds w[..off[t]] for b = 0 and w[..off2[t]] for b = 1 (offset -1 = this tap does not feed that
+ * parity: zeros). */
+typedef struct { int ntaps; long long off[9]; int n_split; long long off2[9]; } erf_im2col_taps;
 int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream);
-/* img[t][kc][n][..] = w[(n0+n)*stride_n + k*stride_k + taps->off[t]] (fp32 torch weight, any of the Conv2d / ConvTranspose2d
+/* n_split == 0: img[t][kc][n][..] = w[(n0+n)*stride_n + k*stride_k + taps->off[t]] (fp32 torch weight, any of the Conv2d / ConvTranspose2d
  * forward / data-gradient orientations), zero for n0+n >= n_src or k >= k_src; bf16, swizzled for the kernel above. */
 int erf_pack_im2col_weights(const float* w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
                             const erf_im2col_taps* taps, int Cin, int NP, void* img, erf_stream_t stream);

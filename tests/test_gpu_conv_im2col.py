@@ -39,7 +39,7 @@ def test_forward_and_data_gradient(name, spec, nhw):
     ref = _torch_fwd(xr, wq, bias, spec)
     # forward (+ bias, relu) into a wider tensor at a channel offset, like the downsampler concat
     assert ops.im2col_supported(spec, torch.bfloat16)
-    plan = ops.im2col_plan(spec)
+    plan = ops.im2col_plan(spec, row_parity=False)   # one launch per output parity class: any output pitch / channel offset
     imgs = ops.im2col_pack(wt.cuda(), spec, False, plan)
     ho, wo = ref.shape[2:]
     c8 = ops.round_up(spec.cout, 8)
@@ -48,6 +48,15 @@ def test_forward_and_data_gradient(name, spec, nhw):
     got = out[..., :spec.cout].float().cpu()
     assert_rel(got.numpy(), ref.relu().permute(0, 2, 3, 1).detach().numpy(), 1e-2, name + " fwd")
     assert torch.all(out[..., c8:] == 7.0), "channels outside the slice must be untouched"
+    if spec.transposed and spec.stride == 2:
+        # row-parity form (the default plan): column parities folded into N, whole output rows per launch, dense output
+        plan2 = ops.im2col_plan(spec)
+        assert plan2[0].get("merged") == c8 and len(plan2) < len(plan) + 1
+        out2 = ops.conv_im2col_tc(x.cuda(), ops.im2col_pack(wt.cuda(), spec, False, plan2), plan2, spec, bias.cuda(), relu=True)
+        assert_rel(out2[..., :spec.cout].float().cpu().numpy(), ref.relu().permute(0, 2, 3, 1).detach().numpy(), 1e-2, name + " fwd row-parity")
+        assert_rel(out2[..., :spec.cout].float().cpu().numpy(), got.numpy(), 4e-3, name + " row-parity vs per-class")  # tap order differs
+        with pytest.raises(RuntimeError):
+            ops.conv_im2col_tc(x.cuda(), imgs, plan2, spec, bias.cuda(), out=out)   # needs a dense output
     # data gradient (only where the gather's input channels are a multiple of 16)
     dspec = ops.dgrad_spec(spec)
     if ops.im2col_supported(dspec, torch.bfloat16):

@@ -36,6 +36,26 @@ for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
         ops.bn_bwd(g, y, gamma, mean, invstd, mask=m, drop=drop, want_masked=masked)
 
     t_bytes = b * h * w * c * 2
+    from erfnet_pytorch_b200 import _lib
+    L = _lib.lib()
+    sums = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
+    dy = torch.empty_like(sets[0][0])
+    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    st = ops._stream(dy)
+
+    def red():
+        g, y, m = sets[it[0] % 6]
+        it[0] += 1
+        ops.check(L.erf_bn_bwd_reduce(ops._p(g), c, ops._p(y), c, ops._p(m), c, ops._p(drop), ops._p(mean), ops._p(invstd), b, h * w, c, ops._p(sums), 1, st))
+
+    def app():
+        g, y, m = sets[it[0] % 6]
+        it[0] += 1
+        ops.check(L.erf_bn_bwd_apply(ops._p(g), c, ops._p(y), c, ops._p(m), c, ops._p(drop), ops._p(gamma), ops._p(mean), ops._p(invstd), ops._p(sums), b, h * w, c,
+                                     ops._p(dy), c, ops._p(dg), ops._p(db), None, c, 1, st))
+
+    ur, ua = timeit(red), timeit(app)
+    print(f"C={c:3d}: reduce {ur:6.1f} us ({3 * t_bytes / ur / 1e6:5.2f} TB/s)   apply {ua:6.1f} us ({4 * t_bytes / ua / 1e6:5.2f} TB/s)")
     us = timeit(lambda: run(False))
     us2 = timeit(lambda: run(True))
     sc, sh = torch.rand(c, device="cuda"), torch.rand(c, device="cuda")
