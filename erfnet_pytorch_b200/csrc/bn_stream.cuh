@@ -28,6 +28,7 @@ __device__ __forceinline__ PxRange px_range(int C, long long n_px, int px_per_bl
   r.p0 = (long long)blockIdx.x * px_per_block;
   r.p1 = r.p0 + px_per_block;
   if (r.p1 > n_px) r.p1 = n_px;
+  if (r.lane_px >= r.lanes) r.p1 = r.p0;   // threads beyond the last whole pixel lane (blockDim % c8 != 0) stay idle
   return r;
 }
 
@@ -36,6 +37,23 @@ template <int NV, typename F>
 __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int C, int c0, float* s_part /* [warps][NV*C] */, F&& f) {
   const int c8 = C >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  if (32 % c8 != 0) {
+    // channel groups do not tile a warp (e.g. the 24-channel padded logits): per-thread rows in shared memory [threads][NV*8],
+    // then thread i sums the rows of the threads that own channel i's group
+    const int lanes = blockDim.x / c8;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_part[(size_t)threadIdx.x * NV * 8 + v * 8 + k] = acc[v][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV * C; i += blockDim.x) {
+      const int v = i / C, c = i % C, g = c >> 3, k = c & 7;
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += s_part[(size_t)(l * c8 + g) * NV * 8 + v * 8 + k];
+      f(i, t);
+    }
+    return;
+  }
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -315,13 +333,18 @@ __global__ void __launch_bounds__(BS_THREADS, 2) affine_act_v2_kernel(const T* _
 struct BsLaunch {
   unsigned grid;
   int px_per_block;
-  size_t smem(int C, int nv) const { return (size_t)(BS_THREADS / 32) * nv * C * sizeof(float); }   // reduction rows
+  size_t smem(int C, int nv) const {   // reduction rows: one per warp, or one per thread when the groups do not tile a warp
+    const size_t per_warp = (size_t)(BS_THREADS / 32) * nv * C * sizeof(float), per_thread = (size_t)BS_THREADS * nv * 8 * sizeof(float);
+    return (32 % (C / 8)) == 0 ? per_warp : (per_thread > per_warp ? per_thread : per_warp);
+  }
 };
 
 static inline bool bs_fast_ok(int C) {
   const int c8 = C / 8;
   return C >= 8 && (C % 8) == 0 && c8 <= 32 && (32 % c8) == 0;
 }
+// reductions also take channel counts whose groups do not tile a warp (shared-memory fallback inside block_channel_reduce)
+static inline bool bs_reduce_ok(int C) { return C >= 8 && (C % 8) == 0 && C <= 256; }
 
 static inline BsLaunch bs_launch(int C, long long n_px, int blocks_per_sm) {
   BsLaunch l;

@@ -447,7 +447,7 @@ extern "C" int erf_conv_wgrad(const void* in, const void* dout, float* dw, float
 extern "C" int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream) {
   ERF_CHECK_ARG(x && out && n_px > 0 && C > 0 && C <= 256 && ld >= coff + C, "erf_channel_sum: bad arguments");
   ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_channel_sum: bad dtype %d", dtype);
-  if (bs_fast_ok(C) && (ld % 8) == 0 && (coff % 8) == 0 && ((uintptr_t)x % 16) == 0) {   // vectorised slice [coff, coff + C) of each pixel row
+  if (bs_reduce_ok(C) && (ld % 8) == 0 && (coff % 8) == 0 && ((uintptr_t)x % 16) == 0) {   // vectorised slice [coff, coff + C) of each pixel row
     const BsLaunch l = bs_launch(C, n_px, 2);
     if (dtype == ERF_F32)
       channel_reduce_v2_kernel<float, false, float><<<l.grid, BS_THREADS, l.smem(C, 1), (cudaStream_t)stream>>>((const float*)x + coff, ld, C, n_px, l.px_per_block, out);

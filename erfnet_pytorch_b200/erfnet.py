@@ -217,7 +217,13 @@ class _TcConv:
                 db = None if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
             else:
                 db = bdst if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
-                ops.channel_sum_slice(dy, self.spec.cout, db)
+                c8 = ops.round_up(self.spec.cout, 8)
+                if c8 != self.spec.cout and dy.shape[-1] >= c8:   # vectorised kernel over the padded channels, then keep the real ones
+                    tmp = torch.zeros(c8, device=x.device, dtype=torch.float32)
+                    ops.channel_sum_slice(dy, c8, tmp)
+                    db += tmp[:self.spec.cout]
+                else:
+                    ops.channel_sum_slice(dy, self.spec.cout, db)
             return dw, db
         return ops.conv_wgrad(x, dy, self.spec, dw_out=_sink(wparam), db_out=_sink(bparam))
 
@@ -617,10 +623,10 @@ class _PlainConv:
         self._tc = _TcConv(spec)
         self.out_ld = ops.round_up(spec.cout, 8)
 
-    def _out(self, x):
+    def _out(self, x, tc=False):
         n, h, w, _ = x.shape
         ho, wo = self.spec.out_hw(h, w)
-        if self.out_ld != self.spec.cout:
+        if self.out_ld != self.spec.cout and not tc:   # the tcgen05 kernel writes the pad channels itself (zeros)
             return torch.zeros(n, ho, wo, self.out_ld, device=x.device, dtype=x.dtype)
         return torch.empty(n, ho, wo, self.out_ld, device=x.device, dtype=x.dtype)
 
@@ -633,7 +639,7 @@ class _PlainConv:
             self._conv.__dict__["_packed"] = c
         w, b, tc = c[1]
         if tc is not None and ops.USE_TC:
-            return self._tc.forward(x, tc, b, out=self._out(x))
+            return self._tc.forward(x, tc, b, out=self._out(x, tc=True))
         return ops.conv_fwd(x, w, self.spec, b, out=self._out(x))
 
     def _train_params(self):
@@ -641,7 +647,7 @@ class _PlainConv:
 
     def _fwd_train(self, x, ctx):
         if self._tc.fwd_ok(x.dtype):
-            y = self._tc.forward(x, self._tc.pack_fwd(self._conv.weight), self._conv.bias.detach().float(), out=self._out(x))
+            y = self._tc.forward(x, self._tc.pack_fwd(self._conv.weight), self._conv.bias.detach().float(), out=self._out(x, tc=True))
         else:
             y = ops.conv_fwd(x, ops.pack_weight_fwd(self._conv.weight.detach(), self.spec, x.dtype), self.spec, self._conv.bias.detach().float(),
                              out=self._out(x))
@@ -655,6 +661,8 @@ class _PlainConv:
         if need_dx:
             if self._tc.bwd_ok(x.dtype):
                 dx = self._tc.dgrad(dy, cw, x.shape[1:3])
+            elif ops.convT2x2_dgrad_tc_supported(self.spec, dy):
+                dx = ops.convT2x2_dgrad_tc(dy, cw, self.spec)
             else:
                 dx = ops.conv_fwd(dy, ops.pack_weight_dgrad(cw.detach(), self.spec, x.dtype), ops.dgrad_spec(self.spec), out_hw=x.shape[1:3])
         grads = (_ret(cw, dw), _ret(cb, db))

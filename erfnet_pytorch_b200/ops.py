@@ -433,6 +433,50 @@ def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional
     return out
 
 
+def convT2x2_dgrad_tc_supported(spec: ConvSpec, dy: torch.Tensor) -> bool:
+    """Data gradient of a non-overlapping ConvTranspose2d(k=2, s=2, p=0) (the decoder head, eval/erfnet.py:124) whose output
+    channel count is not a multiple of 16: possible on the tensor cores through the row-folded view below."""
+    ld = dy.shape[-1]
+    return (dy.dtype == torch.bfloat16 and not EMULATED and USE_TC and spec.transposed and spec.kh == 2 and spec.kw == 2 and spec.stride == 2
+            and spec.pad_h == 0 and spec.pad_w == 0 and spec.cin % 8 == 0 and spec.cin <= 128 and ld == round_up(spec.cout, 8)
+            and (2 * ld) % 16 == 0 and 2 * ld <= 128 and dy.shape[2] % 2 == 0)
+
+
+def convT2x2_dgrad_tc(dy: torch.Tensor, w: torch.Tensor, spec: ConvSpec) -> torch.Tensor:
+    """dx[i,j,ci] = sum_{a,b,c} dy[2i+a, 2j+b, c] * w[ci,c,a,b].  dy [N,Ho,Wo,ld] is read as [N,Ho,Wo/2,2*ld]: the pixel pair
+    (2j, 2j+1) of a row is one pixel with channels (b, c), so the gather is a 2-tap conv (rows 2i, 2i+1; row step 2, column step 1)
+    with K = 2 * 2*ld -- a multiple of 16 even though cout (20) is not."""
+    n, ho, wo, ld = dy.shape
+    k2 = 2 * ld
+    # fp32 operand [a][(b,c)][ci], zero in the pad channels
+    wk = torch.zeros(2, 2, ld, spec.cin, device=w.device, dtype=torch.float32)
+    wk[:, :, :spec.cout] = w.detach().float().permute(2, 3, 1, 0)
+    taps = _lib.Im2colTaps()
+    taps.ntaps = 2
+    taps.off[0], taps.off[1] = 0, k2 * spec.cin
+    npad = 16
+    while npad < spec.cin:
+        npad *= 2
+    cin_g = round_up(k2, 16)
+    img = torch.empty(2 * cin_g * npad, device=w.device, dtype=torch.bfloat16)
+    L = _lib.lib()
+    check(L.erf_pack_im2col_weights(_p(wk), 1, spec.cin, 0, spec.cin, k2, C.byref(taps), cin_g, npad, _p(img), _stream(dy)))
+    dx = torch.empty(n, ho // 2, wo // 2, round_up(spec.cin, 8), device=dy.device, dtype=dy.dtype)
+    d = _lib.Im2colDesc()
+    d.in_, d.H, d.W, d.in_ld, d.Cin = dy.data_ptr(), ho, wo // 2, k2, cin_g
+    d.EN, d.EH, d.EW, d.in_step, d.in_step_x = n, ho // 2, wo // 2, 2, 1
+    d.ntaps = 2
+    d.tap_dy[0], d.tap_dx[0], d.tap_dy[1], d.tap_dx[1] = 0, 0, 1, 0
+    d.w_img, d.bias = img.data_ptr(), None
+    d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = dx.data_ptr(), ho // 2, wo // 2, dx.shape[-1], 0
+    d.out_step, d.out_oy, d.out_ox = 1, 0, 0
+    d.NP, d.n_valid, d.relu = npad, dx.shape[-1], 0
+    with _timed("conv_im2col_tc_kernel", 2.0 * n * ho * wo * spec.cout * spec.cin):
+        check(L.erf_conv_im2col_tc(C.byref(d), _stream(dy)))
+    _count(2)
+    return dx
+
+
 def wgrad_im2col_supported(spec: ConvSpec, dtype) -> bool:
     """spec: the FORWARD conv.  The gathered side is x for a conv and dy for a transposed conv."""
     return (dtype == torch.bfloat16 and not EMULATED and USE_TC and spec.cin <= 128 and spec.cout <= 128 and spec.stride in (1, 2)

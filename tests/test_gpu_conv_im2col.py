@@ -1,5 +1,6 @@
 """GPU: the generic tcgen05 conv (software im2col) vs fp32 torch convs of the same bf16 operands, for every shape class
 it serves in ERFNet: stride-2 3x3 convs, stride-2 transposed convs (3x3 and 2x2), 1x1, and their data gradients."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -90,3 +91,27 @@ def test_weight_gradient(name, spec, nhw):
     dw = torch.full(wshape, 0.5, device="cuda")   # accumulates into existing contents
     ops.conv_wgrad_im2col_tc(x.cuda(), dy.cuda(), spec, dw_out=dw)
     assert_rel((dw.cpu() - 0.5).numpy(), ref.numpy(), 3e-3, name + " dW")
+
+
+def test_head_data_gradient_row_folded():
+    """ConvTranspose2d(16, 20, 2, stride 2) data gradient through the row-folded view (K = 2 x 48) vs torch autograd."""
+    gen = torch.Generator().manual_seed(11)
+    spec = ConvSpec(16, 20, 2, 2, 2, 0, 0, transposed=True)
+    n, h, w = 2, 12, 72
+    wt = torch.randn(16, 20, 2, 2, generator=gen) * 0.2
+    x = torch.randn(n, 16, h, w, generator=gen, requires_grad=True)
+    y = torch.nn.functional.conv_transpose2d(x, wt.bfloat16().float(), stride=2)
+    dy = torch.zeros(n, 2 * h, 2 * w, 24).bfloat16()
+    dy[..., :20] = torch.randn(n, 2 * h, 2 * w, 20, generator=gen).bfloat16()
+    dy[..., 20:] = 3.0          # pad channels hold junk: the zero weight rows must cancel it
+    (gref,) = torch.autograd.grad(y, x, dy[..., :20].float().permute(0, 3, 1, 2))
+    assert ops.convT2x2_dgrad_tc_supported(spec, dy.cuda())
+    dx = ops.convT2x2_dgrad_tc(dy.cuda(), wt.cuda(), spec)
+    assert_rel(dx.float().cpu().numpy(), gref.permute(0, 2, 3, 1).numpy(), 1e-2, "head dgrad")
+
+
+def test_channel_sum_padded_24():
+    x = torch.randn(3, 16, 40, 24).bfloat16().cuda()
+    out = torch.zeros(24, device="cuda")
+    ops.channel_sum_slice(x, 24, out)
+    np.testing.assert_allclose(out.cpu().numpy(), x.float().sum((0, 1, 2)).cpu().numpy(), rtol=2e-3, atol=2e-2)
