@@ -146,15 +146,16 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
           if (EW == 32) tmem_ld32(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
           else tmem_ld16(tmem_base + a * C + c0 + ((uint32_t)(quad * 32) << 16), r);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(wsb + ((size_t)a * 128 + row) * C + c0);
+          // slab layout [acc][col/4][row][4]: the 32 lanes (rows) of a store instruction write 512 contiguous bytes
+          float4* dst = reinterpret_cast<float4*>(wsb) + ((size_t)a * (C / 4) + c0 / 4) * 128 + row;
 #pragma unroll
           for (int q = 0; q < EW / 4; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            dst[(size_t)q * 128] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         }
       }
     } else {
       for (int a = 0; a < ACCS; ++a)
-        for (int c = 0; c < C; ++c) wsb[((size_t)a * 128 + row) * C + c] = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) reinterpret_cast<float4*>(wsb)[((size_t)a * (C / 4) + c4) * 128 + row] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   tcgen05_fence_before();
@@ -172,16 +173,17 @@ template <int C>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
   constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
   constexpr size_t SLAB = (size_t)ACCS * 128 * C;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 3*C*C
-  if (i >= 3 * C * C) return;
-  int co = i % C, ci = (i / C) % C, t = i / (C * C);
-  int acc, row;
-  if (C == 128) { acc = t; row = ci; }
-  else if (C == 64) { acc = t == 2 ? 1 : 0; row = (t == 0 ? 0 : 64) + ci; }
-  else { acc = 0; row = t * 16 + ci; }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // linear index into a slab [acc][col/4][row][4]: coalesced reads
+  if (i >= (int)SLAB) return;
+  const int e = i & 3, row = (i >> 2) & 127, c4 = (i >> 9) % (C / 4), acc = (i >> 9) / (C / 4);
+  const int co = c4 * 4 + e;
+  int t, ci;
+  if (C == 128) { t = acc; ci = row; }
+  else if (C == 64) { t = acc + (row >> 6); ci = row & 63; if (acc == 1 && row < 64) return; }   // accumulator 1 repeats tap 1 in rows 0..63
+  else { t = row >> 4; ci = row & 15; if (t > 2) return; }                                        // rows 48..127 are the ignored atoms
   const int per = (grid_ctas + gridDim.y - 1) / gridDim.y;
   const int b0 = blockIdx.y * per, b1 = min(b0 + per, grid_ctas);
-  const float* src = ws + ((size_t)acc * 128 + row) * C + co;
+  const float* src = ws + i;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int b = b0;
   for (; b + 4 <= b1; b += 4) {
@@ -264,13 +266,13 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<16><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<16><<<dim3((3 * 16 * 16 + 255) / 256, 37), 256, 0, s>>>(p.ws, grid, dw);
+      wgrad_reduce_kernel<16><<<dim3((1 * 128 * 16 + 255) / 256, 37), 256, 0, s>>>(p.ws, grid, dw);
     }
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
       conv1d_wgrad_tc_kernel<64><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<64><<<dim3((3 * 64 * 64 + 255) / 256, 16), 256, 0, s>>>(p.ws, grid, dw);
+      wgrad_reduce_kernel<64><<<dim3((2 * 128 * 64 + 255) / 256, 12), 256, 0, s>>>(p.ws, grid, dw);
     }
   } else {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

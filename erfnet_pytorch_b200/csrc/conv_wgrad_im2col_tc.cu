@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
           uint32_t r[16];
           tmem_ld16(tmem_base + gidx * p.NP + c0 + ((uint32_t)(quad * 32) << 16), r);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(wsb + ((size_t)gidx * 128 + row) * p.NP + c0);
+          // slab layout [group][col/4][row][4]: the 32 lanes (rows) of a store instruction write 512 contiguous bytes
+          float4* dst = reinterpret_cast<float4*>(wsb) + ((size_t)gidx * (p.NP / 4) + c0 / 4) * 128 + row;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            dst[(size_t)q * 128] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         }
       }
     }
@@ -197,7 +198,8 @@ __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int cta
   const int per_cta = groups * 128 * p.NP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_cta) return;
-  const int col = i % p.NP, row = (i / p.NP) % 128, gidx = i / (p.NP * 128);
+  const int e4 = i & 3, row = (i >> 2) & 127, c4 = (i >> 9) % (p.NP / 4), gidx = (i >> 9) / (p.NP / 4);   // slab layout [group][col/4][row][4]
+  const int col = c4 * 4 + e4;
   const int atom = gidx * (128 / CHg) + row / CHg;
   const int tap = atom / gsubs, sub = atom % gsubs;
   const int cg = sub * CHg + row % CHg, cd = p.d_c0 - p.d_c_base + col;
