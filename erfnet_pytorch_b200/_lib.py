@@ -45,6 +45,8 @@ _SIGNATURES = {
     "erf_conv_fwd": [_vp, _vp, _vp, C.POINTER(ConvGeom), C.POINTER(ConvEpilogue), _i, _vp],
     "erf_conv_wgrad": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _vp],
     "erf_conv_wgrad_torch": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _i, _vp],
+    "erf_stem_fwd": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
+    "erf_stem_wgrad": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "erf_maxpool2x2_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp],
     "erf_maxpool2x2_bwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp],
     "erf_nchw_f32_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp],

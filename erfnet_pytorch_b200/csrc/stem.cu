@@ -1,0 +1,243 @@
+// The 3-channel stem (encoder.initial_block, eval/erfnet.py:67 + 12-23): DownsamplerBlock(3, 16) = cat([conv3x3 s2 p1 (3 -> 13),
+// maxpool2x2 (3)]) -> BN -> ReLU.  K = 27: no tensor-core shape fits, and the block is pure bandwidth (25 MB in, 25 MB out at
+// batch 6), so it gets its own CUDA-core kernels:
+//   stem_fwd_kernel    one thread per output pixel: 9 taps x 8 bytes in, 13 conv + 3 pooled channels (32 bytes) out, weights
+//                      broadcast from shared memory, optional per-channel affine + ReLU (eval: BN folded) and fused batch statistics
+//   stem_wgrad_kernel  dW[13][3][3][3] (+ db): thread = (tap, group of 4 output channels), a block walks whole output rows staged in
+//                      shared memory; 12 FMAs per 2 shared loads
+// Input x: NHWC [N][H][W][4] (channel 3 = padding), output y: NHWC [N][H/2][W/2][16], bf16 or fp32.
+#include "common.cuh"
+
+namespace erfk {
+
+constexpr int STEM_CO = 13, STEM_CI = 3, STEM_C = 16;
+
+template <typename T> struct Px4;   // one 4-channel input pixel
+template <> struct Px4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    f[0] = __low2float(a); f[1] = __high2float(a); f[2] = __low2float(b); f[3] = __high2float(b);
+  }
+};
+template <> struct Px4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int relu, T* __restrict__ y, double* __restrict__ stats) {
+  __shared__ __align__(16) float s_w[9 * STEM_CI * STEM_C];   // [tap][ci][co padded to 16]
+  __shared__ float s_b[STEM_C], s_sc[STEM_C], s_sh[STEM_C];
+  __shared__ float s_red[8][2 * STEM_C];
+  for (int i = threadIdx.x; i < 9 * STEM_CI * STEM_C; i += blockDim.x) {
+    const int co = i % STEM_C, ci = (i / STEM_C) % STEM_CI, tap = i / (STEM_C * STEM_CI);
+    s_w[i] = co < STEM_CO ? w[(co * STEM_CI + ci) * 9 + tap] : 0.f;   // torch layout [co][ci][ky][kx]
+  }
+  if (threadIdx.x < STEM_C) {
+    s_b[threadIdx.x] = (bias && threadIdx.x < STEM_CO) ? bias[threadIdx.x] : 0.f;
+    s_sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
+    s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo;
+  float st_sum[STEM_C], st_sq[STEM_C];
+#pragma unroll
+  for (int c = 0; c < STEM_C; ++c) st_sum[c] = st_sq[c] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % Wo);
+    const long long t2 = p / Wo;
+    const int oy = (int)(t2 % Ho), n = (int)(t2 / Ho);
+    float acc[STEM_C];
+#pragma unroll
+    for (int c = 0; c < STEM_C; ++c) acc[c] = s_b[c];
+    float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) Px4<T>::load(x + (((size_t)n * H + iy) * W + ix) * 4, v);
+        if (ky >= 1 && kx >= 1) {   // the 2x2 pooling window = taps (1..2, 1..2), always inside the image
+#pragma unroll
+          for (int c = 0; c < 3; ++c) mx[c] = fmaxf(mx[c], v[c]);
+        }
+        const float4* wt = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * STEM_CI * STEM_C);
+#pragma unroll
+        for (int ci = 0; ci < STEM_CI; ++ci)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = wt[ci * 4 + q];
+            acc[4 * q] += v[ci] * w4.x; acc[4 * q + 1] += v[ci] * w4.y; acc[4 * q + 2] += v[ci] * w4.z; acc[4 * q + 3] += v[ci] * w4.w;
+          }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[STEM_CO + c] = mx[c];
+    // round to the storage type first: statistics and the affine epilogue see the values as stored
+    __align__(16) T o[STEM_C];
+#pragma unroll
+    for (int c = 0; c < STEM_C; ++c) {
+      float f = acc[c] * s_sc[c] + s_sh[c];
+      if (relu) f = fmaxf(f, 0.f);
+      o[c] = from_f<T>(f);
+      const float r = to_f(o[c]);
+      st_sum[c] += r;
+      st_sq[c] += r * r;
+    }
+    T* dst = y + (size_t)p * STEM_C;
+    if (sizeof(T) == 2) {
+      reinterpret_cast<uint4*>(dst)[0] = *reinterpret_cast<const uint4*>(&o[0]);
+      reinterpret_cast<uint4*>(dst)[1] = *reinterpret_cast<const uint4*>(&o[8]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(&o[4 * q]);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int c = 0; c < STEM_C; ++c) {
+      st_sum[c] = warp_sum(st_sum[c]);
+      st_sq[c] = warp_sum(st_sq[c]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < STEM_C; ++c) { s_red[warp][c] = st_sum[c]; s_red[warp][STEM_C + c] = st_sq[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * STEM_C) {
+      float t = 0.f;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += s_red[wv][threadIdx.x];
+      atomicAdd(&stats[threadIdx.x], (double)t);
+    }
+  }
+}
+
+// dW[co][ci][ky][kx] += sum_p dy[p][co] * x[2oy-1+ky][2ox-1+kx][ci];  db[co] += sum_p dy[p][co]   (dy: first 13 channels of a 16-wide row)
+constexpr int SW_LANES = 7, SW_GROUP = 36;   // 36 threads = 9 taps x 4 output-channel quads; 7 pixel lanes -> 252 active threads
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int N, int H, int W,
+                                                         float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const int Ho = H / 2, Wo = W / 2;
+  T* s_x = reinterpret_cast<T*>(s_raw);                               // [3 rows][W][4]
+  T* s_dy = s_x + (size_t)3 * W * 4;                                  // [Wo][16]
+  float* s_acc = reinterpret_cast<float*>(s_dy + (size_t)Wo * STEM_C);  // [SW_LANES][9][16][3] partial sums + [16] bias sums
+  const int tid = threadIdx.x;
+  const int lane_px = tid / SW_GROUP, g = tid % SW_GROUP, tap = g / 4, cq = g % 4;
+  const int ky = tap / 3, kx = tap % 3;
+  const bool active = lane_px < SW_LANES;
+  float acc[4][3], bsum[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { bsum[a] = 0.f; acc[a][0] = acc[a][1] = acc[a][2] = 0.f; }
+  const int rows = N * Ho;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int n = r / Ho, oy = r % Ho;
+    __syncthreads();   // previous row fully consumed
+    // stage input rows 2oy-1 .. 2oy+1 (zero outside the image) and the dy row, 16 bytes per thread and step
+    const int x_vecs = W * 4 * (int)sizeof(T) / 16, dy_vecs = Wo * STEM_C * (int)sizeof(T) / 16;
+    for (int i = tid; i < 3 * x_vecs; i += blockDim.x) {
+      const int rr = i / x_vecs, v = i % x_vecs, iy = 2 * oy - 1 + rr;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (iy >= 0 && iy < H) val = reinterpret_cast<const uint4*>(x + ((size_t)n * H + iy) * W * 4)[v];
+      reinterpret_cast<uint4*>(s_x)[i] = val;
+    }
+    for (int i = tid; i < dy_vecs; i += blockDim.x) reinterpret_cast<uint4*>(s_dy)[i] = reinterpret_cast<const uint4*>(dy + (size_t)r * Wo * STEM_C)[i];
+    __syncthreads();
+    if (active) {
+      for (int ox = lane_px; ox < Wo; ox += SW_LANES) {
+        const int ix = 2 * ox - 1 + kx;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ix >= 0 && ix < W) Px4<T>::load(s_x + ((size_t)ky * W + ix) * 4, xv);
+        float dv[4];
+        Px4<T>::load(s_dy + (size_t)ox * STEM_C + cq * 4, dv);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          acc[a][0] += dv[a] * xv[0];
+          acc[a][1] += dv[a] * xv[1];
+          acc[a][2] += dv[a] * xv[2];
+          bsum[a] += dv[a];
+        }
+      }
+    }
+  }
+  // combine the pixel lanes of the block, then one atomic per weight and block
+  __syncthreads();
+  float* mine = s_acc + ((size_t)lane_px * SW_GROUP + g) * 16;   // 12 weights + 4 bias sums per thread
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      mine[a * 3] = acc[a][0]; mine[a * 3 + 1] = acc[a][1]; mine[a * 3 + 2] = acc[a][2];
+      mine[12 + a] = bsum[a];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < SW_GROUP * 16; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < SW_LANES; ++l) t += s_acc[(size_t)l * SW_GROUP * 16 + i];
+    const int gg = i / 16, e = i % 16, tp = gg / 4, q = gg % 4;
+    if (e < 12) {
+      const int co = q * 4 + e / 3, ci = e % 3;
+      if (co < STEM_CO) atomicAdd(&dw[(co * STEM_CI + ci) * 9 + tp], t);
+    } else if (db && tp == 4) {   // every tap thread saw the same dy: take the centre tap's bias sums
+      const int co = q * 4 + (e - 12);
+      if (co < STEM_CO) atomicAdd(&db[co], t);
+    }
+  }
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+
+extern "C" int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
+                            int relu, void* y, double* stats, int dtype, erf_stream_t stream) {
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_stem_fwd: bad dtype %d", dtype);
+  ERF_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0, "erf_stem_fwd: bad arguments (H, W must be even)");
+  ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "erf_stem_fwd: scale and shift must be given together");
+  ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "erf_stem_fwd: tensors must be 16-byte aligned");
+  const long long total = (long long)N * (H / 2) * (W / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == ERF_F32)
+    stem_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, N, H, W, w, bias, scale, shift, relu, (float*)y, stats);
+  else
+    stem_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, N, H, W, w, bias, scale, shift, relu, (__nv_bfloat16*)y, stats);
+  ERF_CHECK_LAUNCH("erf_stem_fwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W, float* dw, float* db, int dtype, erf_stream_t stream) {
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_stem_wgrad: bad dtype %d", dtype);
+  ERF_CHECK_ARG(x && dy && dw && N > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 4) == 0, "erf_stem_wgrad: bad arguments (H even, W % 4 == 0)");
+  ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0, "erf_stem_wgrad: tensors must be 16-byte aligned");
+  const size_t esz = dtype == ERF_F32 ? 4 : 2;
+  const size_t smem = (size_t)3 * W * 4 * esz + (size_t)(W / 2) * STEM_C * esz + (size_t)SW_LANES * SW_GROUP * 16 * sizeof(float);
+  ERF_CHECK_ARG(smem <= 200 * 1024, "erf_stem_wgrad: image row of %d pixels does not fit in shared memory", W);
+  const int rows = N * (H / 2);
+  int grid = rows < 148 * 2 ? rows : 148 * 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e;
+  if (dtype == ERF_F32) {
+    e = cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) stem_wgrad_kernel<float><<<grid, 256, smem, s>>>((const float*)x, (const float*)dy, N, H, W, dw, db);
+  } else {
+    e = cudaFuncSetAttribute(stem_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) stem_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
+  }
+  if (e != cudaSuccess) {
+    set_error("erf_stem_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return ERF_ERR_CUDA;
+  }
+  ERF_CHECK_LAUNCH("erf_stem_wgrad");
+  return ERF_OK;
+}

@@ -272,6 +272,11 @@ class DownsamplerBlock(_B200Module):
         else:
             ps = psh = None
         pk = dict(w=ops.pack_weight_fwd(w, self.spec, dtype), b=b.contiguous(), ps=ps, psh=psh)
+        if self.ninput == 3 and self.noutput == 16:   # stem kernel operands: folded fp32 weight, affine of the pooled channels
+            pk["stem_w"] = w.contiguous()
+            if ps is not None:
+                pk["stem_sc"] = torch.cat([torch.ones_like(b), ps]).contiguous()
+                pk["stem_sh"] = torch.cat([torch.zeros_like(b), psh]).contiguous()
         if self._tc.fwd_ok(dtype):
             pk["tc"] = self._tc.pack_fwd(w)
         return pk
@@ -280,6 +285,8 @@ class DownsamplerBlock(_B200Module):
         self._check(x)
         pk = self._cache(ctx.dtype)
         n, h, w, _ = x.shape
+        if "stem_w" in pk and ops.stem_supported(x):
+            return ops.stem_fwd(x, pk["stem_w"], pk["b"], pk.get("stem_sc"), pk.get("stem_sh"), relu=True)
         y = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
         if "tc" in pk and ops.USE_TC:
             self._tc.forward(x, pk["tc"], pk["b"], relu=True, out=y)
@@ -295,6 +302,18 @@ class DownsamplerBlock(_B200Module):
         self._check(x)
         n, h, w, _ = x.shape
         cc = self.noutput - self.ninput
+        stem = self.ninput == 3 and self.noutput == 16 and ops.stem_supported(x)
+        if stem and not self.use_batchnorm:
+            y = ops.stem_fwd(x, self.conv.weight.detach(), self.conv.bias.detach(), relu=True)
+            return y, (x, None, y, None, None)
+        if stem:
+            stats = _stats_buf(self.bn, x.device)
+            y_raw = ops.stem_fwd(x, self.conv.weight.detach(), self.conv.bias.detach(), stats=stats)
+            mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
+                                                         self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
+            _tick(self.bn)
+            y = ops.affine_act(y_raw, scale, shift, relu=True)
+            return y, (x, y_raw, y, mean, invstd)
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
         if not self.use_batchnorm:  # train/erfnet_blocks.py:24-29: relu(cat(conv, pool)), both ReLUs in the producing kernels
             if self._tc.fwd_ok(x.dtype):
@@ -326,7 +345,12 @@ class DownsamplerBlock(_B200Module):
             dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
         else:
             dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
-        dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=self.use_batchnorm)
+        if self.ninput == 3 and self.noutput == 16 and ops.stem_supported(x):
+            dw, db = ops.stem_wgrad(x, dyr, dw_out=_sink(cw), db_out=_sink(cb), want_bias=not self.use_batchnorm)
+            if db is None and _sink(cb) is None:   # conv bias feeding a train-mode BN: gradient exactly zero
+                db = torch.zeros(self.noutput - self.ninput, device=x.device, dtype=torch.float32)
+        else:
+            dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=self.use_batchnorm)
         dx = None
         if need_dx:
             n, h, w, _ = x.shape

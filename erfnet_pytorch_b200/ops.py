@@ -557,6 +557,33 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
     return dw_out, db_out
 
 
+def stem_supported(x: torch.Tensor) -> bool:
+    return not EMULATED and x.shape[-1] == 4 and x.shape[1] % 2 == 0 and x.shape[2] % 4 == 0 and x.shape[2] <= 4096
+
+
+def stem_fwd(x, w, bias, scale=None, shift=None, relu=False, stats=None):
+    """DownsamplerBlock(3, 16) forward on x NHWC [N,H,W,4]: y [N,H/2,W/2,16] = relu?((conv | maxpool) * scale + shift)."""
+    n, h, wd, _ = x.shape
+    y = torch.empty(n, h // 2, wd // 2, 16, device=x.device, dtype=x.dtype)
+    with _timed("stem_fwd", 2.0 * n * (h // 2) * (wd // 2) * 13 * 27):
+        check(_lib.lib().erf_stem_fwd(_p(x), n, h, wd, _p(w), _p(bias), _p(scale), _p(shift), int(relu), _p(y), _p(stats), dt(x), _stream(x)))
+    _count()
+    return y
+
+
+def stem_wgrad(x, dy, dw_out=None, db_out=None, want_bias=True):
+    """(dw [13,3,3,3], db [13] or None), ACCUMULATED into dw_out / db_out when given."""
+    n, h, wd, _ = x.shape
+    dw = dw_out if dw_out is not None else torch.zeros(13, 3, 3, 3, device=x.device, dtype=torch.float32)
+    db = None
+    if want_bias:
+        db = db_out if db_out is not None else torch.zeros(13, device=x.device, dtype=torch.float32)
+    with _timed("stem_wgrad", 2.0 * n * (h // 2) * (wd // 2) * 13 * 27):
+        check(_lib.lib().erf_stem_wgrad(_p(x), _p(dy), n, h, wd, _p(dw), _p(db), dt(x), _stream(x)))
+    _count()
+    return dw, db
+
+
 def maxpool_fwd(x, c, out, out_coff, scale=None, shift=None, relu=False, stats=None):
     n, h, w, ld = x.shape
     check(_lib.lib().erf_maxpool2x2_fwd(_p(x), n, h, w, c, ld, _p(out), out.shape[-1], out_coff, _p(scale), _p(shift), int(relu),

@@ -79,6 +79,17 @@ int erf_conv_wgrad(const void* in, const void* dout, float* dw, float* db, const
 int erf_conv_wgrad_torch(const void* in, const void* dout, float* dw, float* db, const erf_conv_geom* g, int cin_real,
                          int dtype, erf_stream_t stream);
 
+/* ---- the 3-channel stem: DownsamplerBlock(3, 16) = cat([Conv2d(3, 13, 3, stride 2, padding 1), MaxPool2d(2, 2)]) (eval/erfnet.py:67, 12-23)
+ * x NHWC [N][H][W][4] (channel 3 = padding), y NHWC [N][H/2][W/2][16]: channels 0..12 = conv + bias, 13..15 = pooled input.
+ * y = relu?(raw * scale[c] + shift[c]) (scale/shift [16] or NULL = identity; eval mode passes the BN affine of the pooled channels and
+ * folds the conv channels' BN into w / bias); stats (fp64 [32], optional) += per-channel sum and sum of squares of the stored y.
+ * w: torch layout [13][3][3][3] fp32.  CUDA-core kernels: K = 27 fits no tensor-core shape and the block is bandwidth-bound. */
+int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
+                 int relu, void* y, double* stats, int dtype, erf_stream_t stream);
+/* dw[13][3][3][3] += conv weight gradient from x and dy (the 16-channel gradient of y; channels 13..15 are ignored);
+ * db[13] += per-channel sum of dy (NULL to skip). */
+int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W, float* dw, float* db, int dtype, erf_stream_t stream);
+
 /* ---- MaxPool2d(2, stride 2) half of DownsamplerBlock (eval/erfnet.py:17,21) ------------------------------ */
 /* out = relu?(max2x2(in)*scale[c] + shift[c]); scale/shift NULL = identity; stats (of the raw max) as in erf_conv_epilogue */
 int erf_maxpool2x2_fwd(const void* in, int N, int H, int W, int C, int in_ld, void* out, int out_ld, int out_coff,

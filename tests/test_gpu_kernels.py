@@ -265,3 +265,35 @@ def test_cross_entropy_nhwc_bf16_fast_path():
     np.testing.assert_allclose(float(lsum / wsum), float(lo), rtol=2e-4)
     assert_rel(dlog[..., :20].float().cpu().permute(0, 3, 1, 2).numpy(), lg_ref.grad.numpy(), 1e-2)
     assert float(dlog[..., 20:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_kernels(dtype):
+    """erf_stem_fwd / erf_stem_wgrad (DownsamplerBlock(3,16), eval/erfnet.py:67) vs torch on the same stored operands."""
+    gen = torch.Generator().manual_seed(17)
+    n, h, w = 2, 24, 1024           # full-width rows: the wgrad kernel stages 3 input rows + 1 gradient row in shared memory
+    x = torch.zeros(n, h, w, 4)
+    x[..., :3] = torch.rand(n, h, w, 3, generator=gen) - 0.3
+    x = x.to(dtype)
+    wt = torch.randn(13, 3, 3, 3, generator=gen) * 0.3
+    bias = torch.randn(13, generator=gen) * 0.1
+    xr = x[..., :3].float().permute(0, 3, 1, 2).requires_grad_(False)
+    wr = wt.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    ref = torch.cat([torch.nn.functional.conv2d(xr, wr, br, stride=2, padding=1), torch.nn.functional.max_pool2d(xr, 2, 2)], 1)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    stats = torch.zeros(32, device="cuda", dtype=torch.float64)
+    y = ops.stem_fwd(x.cuda(), wt.cuda(), bias.cuda(), stats=stats)
+    assert_rel(y.float().cpu().numpy(), ref.detach().permute(0, 2, 3, 1).numpy(), tol, "stem fwd")
+    ys = y.double()
+    np.testing.assert_allclose(stats[:16].cpu().numpy(), ys.sum((0, 1, 2)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(stats[16:].cpu().numpy(), (ys * ys).sum((0, 1, 2)).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    sc, sh = torch.rand(16, generator=gen) + 0.5, torch.randn(16, generator=gen) * 0.1
+    y2 = ops.stem_fwd(x.cuda(), wt.cuda(), bias.cuda(), sc.cuda(), sh.cuda(), relu=True)
+    assert_rel(y2.float().cpu().numpy(), (ref.detach() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).relu().permute(0, 2, 3, 1).numpy(), tol, "stem affine")
+    dy = (torch.randn(n, h // 2, w // 2, 16, generator=gen) * 0.5).to(dtype)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dw0 = torch.full((13, 3, 3, 3), 0.25, device="cuda")            # accumulate semantics
+    dw, db = ops.stem_wgrad(x.cuda(), dy.cuda(), dw_out=dw0)
+    assert_rel((dw - 0.25).cpu().numpy(), wr.grad.numpy(), 1e-4 if dtype == torch.float32 else 2e-3, "stem dw")
+    assert_rel(db.cpu().numpy(), br.grad.numpy(), 1e-4 if dtype == torch.float32 else 2e-3, "stem db")
