@@ -221,7 +221,9 @@ static int make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C,
 
 using namespace erfk;
 
-extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) { return (size_t)148 * (C == 128 ? 3 : (C == 64 ? 2 : 1)) * 128 * C * sizeof(float); }
+extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) {
+  return (size_t)(C == 16 ? 296 : 148) * (C == 128 ? 3 : (C == 64 ? 2 : 1)) * 128 * C * sizeof(float);
+}
 
 extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W, int C,
                                    int horizontal, int dil, erf_stream_t stream) {
@@ -259,7 +261,8 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
   if (p.stages > kWgStages) p.stages = kWgStages;
   // C = 16: the five unused M atoms of the x operand read up to 7 tap pitches past the tile -- keep that inside the allocation
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (C == 16 ? 16 * 1024 : 0);
-  int grid = p.units < 148 ? p.units : 148;
+  const int ctas = C == 16 ? 296 : 148;   // C = 16: ~60 KB of shared memory and 32 TMEM columns per CTA -> two CTAs per SM hide the per-unit latency
+  int grid = p.units < ctas ? p.units : ctas;
   cudaError_t e;
   cudaStream_t s = (cudaStream_t)stream;
   if (C == 16) {
