@@ -259,9 +259,10 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
   p.stage_bytes = x_bytes + ((KC * PX * RB + 1023) / 1024) * 1024;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > kWgStages) p.stages = kWgStages;
+  const bool two_per_sm = C == 16;   // ~60 KB of shared memory, 32 TMEM columns: two CTAs per SM hide the per-unit latency (C = 64: measured neutral)
   // C = 16: the five unused M atoms of the x operand read up to 7 tap pitches past the tile -- keep that inside the allocation
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (C == 16 ? 16 * 1024 : 0);
-  const int ctas = C == 16 ? 296 : 148;   // C = 16: ~60 KB of shared memory and 32 TMEM columns per CTA -> two CTAs per SM hide the per-unit latency
+  const int ctas = two_per_sm ? 296 : 148;
   int grid = p.units < ctas ? p.units : ctas;
   cudaError_t e;
   cudaStream_t s = (cudaStream_t)stream;

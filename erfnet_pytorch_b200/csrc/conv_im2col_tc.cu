@@ -286,7 +286,7 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   p.units = (int)((total + 127) / 128);
   size_t smem = (size_t)w_pad + (size_t)slots * slot_bytes + 1024;
   // small classes (<= 100 KB of shared memory, <= 256 TMEM columns for two CTAs) run two CTAs per SM: their per-unit
-  // gather -> MMA -> epilogue chain is latency-bound
+  // gather -> MMA -> epilogue chain is latency-bound (shrinking the ring of the large classes to fit two CTAs measured neutral)
   const int per_sm = (smem <= 100 * 1024 && 2 * d->NP <= 128) ? 2 : 1;
   int grid = p.units < 148 * per_sm ? p.units : 148 * per_sm;
   cudaStream_t st = (cudaStream_t)stream;

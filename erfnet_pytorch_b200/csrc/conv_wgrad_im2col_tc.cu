@@ -222,7 +222,7 @@ __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int cta
 
 using namespace erfk;
 
-extern "C" size_t erf_conv_wgrad_im2col_tc_workspace(void) { return (size_t)148 * 512 * 128 * sizeof(float); }
+extern "C" size_t erf_conv_wgrad_im2col_tc_workspace(void) { return (size_t)148 * 512 * 128 * sizeof(float); }   // = 296 CTAs x 256 columns
 
 extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* dw, void* workspace, size_t ws_bytes, erf_stream_t stream) {
   ERF_CHECK_ARG(d && d->g && d->d && dw && workspace, "erf_conv_wgrad_im2col_tc: null pointer");
@@ -256,7 +256,14 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   p.tail_bytes = atoms_per_m * kWiPX * RBg;
   const long long total = (long long)d->EN * d->EH * d->EW;
   const int units = (int)((total + kWiPX - 1) / kWiPX);
-  const int grid = units < 148 ? units : 148;
+  // two CTAs per SM when two rings of >= 2 stages and two accumulator sets fit (latency-bound per-unit chain)
+  int per_sm = 1;
+  if (groups * d->NP <= 256 && (104 * 1024 - p.tail_bytes) / stage_bytes >= 2 && units > 148) {
+    per_sm = 2;
+    stages = (104 * 1024 - p.tail_bytes) / stage_bytes;
+    if (stages > kWiMaxStages) stages = kWiMaxStages;
+  }
+  const int grid = units < 148 * per_sm ? units : 148 * per_sm;
   ERF_CHECK_ARG(ws_bytes >= (size_t)grid * groups * 128 * d->NP * sizeof(float), "erf_conv_wgrad_im2col_tc: workspace too small");
   size_t smem = (size_t)stages * stage_bytes + p.tail_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
