@@ -71,11 +71,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) ride on the tensor pipe: the staged output
   // sub-tile Y [128 px][64 ch] is an MN-major operand, so  Y^T Y (Gram, diagonal = sum of squares) and  Y^T 1  (sums) are
   // two more accumulating MMAs per sub-tile, issued by warp 10 into their own TMEM columns and read once at the end.
-  constexpr bool RED = CH == 64;
-  constexpr uint32_t GRAM_COL = 2 * C, ONES_COL = 2 * C + KC * 64;         // KC x 64 Gram columns, KC x 16 sum columns
-  constexpr uint32_t TMEM_COLS = C == 128 ? 512 : (C == 64 ? 256 : 32);
+  constexpr bool RED = true;
+  constexpr int GW = CH;                                                   // Gram width = channels of a sub-tile (64, or 16 for C = 16)
+  constexpr uint32_t GRAM_COL = 2 * C, ONES_COL = 2 * C + KC * GW;         // KC x GW Gram columns, KC x 16 sum columns
+  constexpr uint32_t TMEM_COLS = C == 128 ? 512 : (C == 64 ? 256 : 64);
   constexpr uint32_t IDESC = make_idesc_bf16(128, C);
-  constexpr uint32_t IDESC_GRAM = make_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);  // both operands MN-major
+  constexpr uint32_t IDESC_GRAM = make_idesc_bf16(128, GW) | (1u << 15) | (1u << 16);  // both operands MN-major
   constexpr uint32_t IDESC_ONES = make_idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   } else if (warp == 10) {
     // ================= statistics MMAs: Y^T Y and Y^T 1 of every staged sub-tile =================
     if (RED && want_red && lane == 0) {
-      const uint32_t hi128 = ((8u * 128u) >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);   // MN-major, 8 pixel rows of 128 B per atom
+      const uint32_t hi128 = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);           // MN-major, 8 pixel rows of RB bytes per atom
       const uint32_t hi32 = ((8u * 32u) >> 4) | (1u << 14) | (LAYOUT_SW32 << 29);      // the ones operand: 16 "channels" = 32-byte rows
       const uint32_t ones_addr = smem_u32(s_ones);
       const uint64_t d_ones = ((uint64_t)hi32 << 32) | (uint64_t)((ones_addr >> 4) & 0x3FFF);
@@ -233,16 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
           ph[g * 2 + b] ^= 1;
           tcgen05_fence_after();
           const uint32_t tile = smem_u32(s_stg + (g * 2 + b) * STG_PAD);
-          // M = 128 = two 64-channel atoms: the sub-tile and (LBO away) whatever follows it in shared memory (the next staging
-          // buffer or the operand ring); rows 64..127 of D are never read and cannot influence rows 0..63
+          // M = 128 = 128/GW channel atoms: the sub-tile and (LBO away each) whatever follows it in shared memory (the next staging
+          // buffers or the operand ring); rows GW..127 of D are never read and cannot influence rows 0..GW-1
           const uint32_t a_lo = ((tile >> 4) & 0x3FFF) | (((STG_PAD >> 4) & 0x3FFF) << 16);
           const uint32_t b_lo = ((tile >> 4) & 0x3FFF) | (1u << 16);
           const uint32_t acc_en = (started >> kc) & 1u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {   // K = 128 pixels, 16 per MMA = 16 rows of 128 B
-            const uint64_t da = ((uint64_t)hi128 << 32) | (uint64_t)(a_lo + k * 128);
+          for (int k = 0; k < 8; ++k) {   // K = 128 pixels, 16 per MMA = 16 rows of RB bytes
+            const uint64_t da = ((uint64_t)hi128 << 32) | (uint64_t)(a_lo + k * RB);
             if (p.stats)
-              umma_bf16(tmem_base + GRAM_COL + kc * 64, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * 128), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
+              umma_bf16(tmem_base + GRAM_COL + kc * GW, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * RB), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
             umma_bf16(tmem_base + ONES_COL + kc * 16, da, d_ones, IDESC_ONES, (acc_en | k) ? 1u : 0u);
           }
           started |= 1u << kc;
@@ -369,30 +370,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     }
     if (leader) tma_store_wait0();
     if constexpr (RED) {
-      if (want_red && grp == 0 && quad < 2) {   // TMEM lanes 0..63 = the 64 channels of a k-chunk: one atomic per channel and CTA
+      if (want_red && grp == 0 && quad * 32 < GW) {   // whole warps (tcgen05.ld is warp-collective); TMEM lanes 0..GW-1 = the channels of a k-chunk
+        const bool mine = quad * 32 + lane < GW;         // one atomic per channel and CTA
         mbar_wait(&sfinal_bar, 0);
         tcgen05_fence_after();
         const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
-          const int c = kc * 64 + quad * 32 + lane;
+          const int c = kc * GW + quad * 32 + lane;
           uint32_t o[16];
           tmem_ld16(tmem_base + ONES_COL + kc * 16 + lane_bits, o);
           tmem_ld_wait();
           const float sum = __uint_as_float(o[0]);
-          if (p.colsum) atomicAdd(&p.colsum[c], sum);
+          if (p.colsum && mine) atomicAdd(&p.colsum[c], sum);
           if (p.stats) {
-            uint32_t g0[32], g1[32];
-            tmem_ld32(tmem_base + GRAM_COL + kc * 64 + lane_bits, g0);
-            tmem_ld32(tmem_base + GRAM_COL + kc * 64 + 32 + lane_bits, g1);
-            tmem_ld_wait();
             float sq = 0.f;   // the diagonal element: column (quad*32 + lane) of this thread's row
+            if constexpr (GW == 64) {
+              uint32_t g0[32], g1[32];
+              tmem_ld32(tmem_base + GRAM_COL + kc * GW + lane_bits, g0);
+              tmem_ld32(tmem_base + GRAM_COL + kc * GW + 32 + lane_bits, g1);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j == lane) sq = __uint_as_float(quad == 0 ? g0[j] : g1[j]);
+              for (int j = 0; j < 32; ++j) {
+                if (j == lane) sq = __uint_as_float(quad == 0 ? g0[j] : g1[j]);
+              }
+            } else {
+              uint32_t g0[16];
+              tmem_ld16(tmem_base + GRAM_COL + lane_bits, g0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j == lane) sq = __uint_as_float(g0[j]);
+              }
             }
-            atomicAdd(&p.stats[c], (double)sum);
-            atomicAdd(&p.stats[C + c], (double)sq);
+            if (mine) {
+              atomicAdd(&p.stats[c], (double)sum);
+              atomicAdd(&p.stats[C + c], (double)sq);
+            }
           }
         }
       }
@@ -448,7 +462,6 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   ERF_CHECK_ARG(in && w_img && out, "erf_conv1d_tc: null pointer");
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_tc: empty tensor");
   ERF_CHECK_ARG(!(res && mask), "erf_conv1d_tc: res and mask are mutually exclusive");
-  ERF_CHECK_ARG(!(stats || colsum) || C >= 64, "erf_conv1d_tc: fused statistics need C >= 64 (use erf_channel_stats / erf_channel_sum for C = %d)", C);
   if (!erf_conv1d_tc_supported(C, W, dil)) {
     set_error("erf_conv1d_tc: unsupported shape C=%d W=%d dil=%d (need C in {16,64,128}, W %% 128 == 0, dil <= 32)", C, W, dil);
     return ERF_ERR_UNSUPPORTED;
@@ -479,7 +492,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.slot_bytes = p.sub_bytes;   // one (tap, k-chunk) tile [vertical] or one k-chunk of the haloed row tile [horizontal]
   const int w_pad = ((3 * KC * C * RB + 1023) / 1024) * 1024;
   const int stg_pad = 4 * (((128 * RB + 1023) / 1024) * 1024);
-  const int ones_bytes = ((stats || colsum) && C >= 64) ? 1024 : 0;   // bf16 ones operand of the statistics MMAs
+  const int ones_bytes = (stats || colsum) ? 1024 : 0;   // bf16 ones operand of the statistics MMAs
   const int budget = 225 * 1024 - w_pad - stg_pad - ones_bytes;
   p.slots = budget / p.slot_bytes;
   if (p.slots > kMaxSlots) p.slots = kMaxSlots;

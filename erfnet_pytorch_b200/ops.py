@@ -255,11 +255,10 @@ class Conv1dPackTable:
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
               res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated in the kernel epilogue for C >= 64, by a follow-up
-    bandwidth kernel for C = 16."""
+    """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated by the kernel itself (Gram / ones MMAs over the staged output tile)."""
     n, h, w, c = x.shape
     out = torch.empty_like(x)
-    fused = c >= 64
+    fused = True
     with _timed("conv1d_tc_kernel", 2.0 * n * h * w * c * c * 3):
         check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu),
                                        _p(stats) if fused else None, _p(colsum) if fused else None, _stream(x)))

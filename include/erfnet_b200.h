@@ -196,8 +196,8 @@ int erf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
  * epilogue as erf_conv_fwd (bias -> + res -> relu -> * (mask>0)).  TMA-staged 128B-swizzled activation tiles (zero-filled
  * borders = padding), tcgen05.mma with TMEM accumulators.  w_img = host-packed shared-memory image [3][C/64][C][64] bf16
  * with the 16-byte chunks of row n XOR-swizzled by (n & 7) (erfnet_pytorch_b200.ops.pack_conv1d_tc).
- * stats  (fp64 [2C], C >= 64): += per-channel sum and sum of squares of the stored (bf16) output -- the BN batch statistics;
- * colsum (fp32 [C],  C >= 64): += per-channel sum of the stored output -- the bias gradient when this call is a data gradient.
+ * stats  (fp64 [2C]): += per-channel sum and sum of squares of the stored (bf16) output -- the BN batch statistics;
+ * colsum (fp32 [C]): += per-channel sum of the stored output -- the bias gradient when this call is a data gradient.
  * Returns ERF_ERR_UNSUPPORTED unless erf_conv1d_tc_supported(C, W, dil). */
 int erf_conv1d_tc_supported(int C, int W, int dil);
 int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask,
