@@ -38,12 +38,44 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (20 ms period, no start-up delay), falling
+    back to an `nvidia-smi -lms` child process when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.stop, self.t = index, [], None, False, None
+        self.max_mhz, self.reasons = 0, set()
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop:
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.t = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -55,22 +87,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([s.strip() for s in line.split(",")])
+            s = [v.strip() for v in line.split(",")]
+            if s and s[0].isdigit():
+                self.samples.append(int(s[0]))
+                if len(s) > 1 and s[1].isdigit():
+                    self.max_mhz = max(self.max_mhz, int(s[1]))
+                for n, v in zip(self.NAMES, s[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+        elif self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = max([int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()] or [0])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz or None, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def synth_batch(torch, seed, batch=BATCH, h=H, w=W):
@@ -217,13 +256,23 @@ def main():
     # ---- training end to end: pinned host buffers -> device, loss back to the host, every step
     last = {}
 
-    def train_e2e(i):
-        xh, yh = pool_pin[i % len(pool_pin)]
-        x = xh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
-        last["loss"] = float(trainer.train_step(x, y))
+    # The public call is FlatAdamTrainer.train_stream(host batches): every step copies ITS batch from pinned host memory (on a side
+    # stream, overlapping the previous step's compute) and the loop reads every step's loss back to the host.
+    def e2e_run(steps):
+        for loss in trainer.train_stream(pool_pin[i % len(pool_pin)] for i in range(steps)):
+            last["loss"] = float(loss)
 
-    e2e_ms, _ = timed(train_e2e, K, 2)
+    e2e_run(2)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    e2e_run(K)
+    ev1.record()
+    barrier()
+    e2e_t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t) / K
 
     # ---- inference forward (eval mode, BN folded), resident inputs, NCHW fp32 logits out (reference API)
     model.eval()
@@ -274,7 +323,7 @@ def main():
                            "global_batch": B * world, "parallelism": f"dp{world}", "l2": "inputs rotate over a 4-batch pool (252 MB) > L2; per-step working set >> L2",
                            "random_init": "deterministic synthetic weights (pretrained blob missing)", "cuda_graph": bool(use_graph)},
                 "clocks": clocks,
-                "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * (3 * H * W * 4 + H * W * 8), "d2h_bytes_per_step": 4,
+                "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": world * B * (3 * H * W * 4 + H * W * 8), "d2h_bytes_per_step": 4 * world,
                         "ms_per_step": e2e_ms, "loss": last.get("loss")},
                 "gpu_launches": launches,
                 "fwd": {"images_per_s": B * world / (fwd_ms * 1e-3), "ms_per_step": fwd_ms, "batch": B,

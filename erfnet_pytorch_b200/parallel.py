@@ -214,6 +214,52 @@ class FlatAdamTrainer:
         self.optimizer_step()
         return loss
 
+    # ---- host-fed training: H2D of batch i+1 overlaps the step on batch i ------------------------------------------------
+    def _stage(self, batch, k):
+        """Enqueue the host->device copy of (images, labels) (pinned CPU tensors) into staging slot k on the copy stream."""
+        images, labels = batch
+        dev = self.flat_p.device
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(device=dev)
+            self._stage_buf = [None, None]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_used = [False, False]
+        buf = self._stage_buf[k]
+        if buf is None or buf[0].shape != images.shape or buf[1].shape != labels.shape:
+            buf = self._stage_buf[k] = (torch.empty(images.shape, device=dev, dtype=torch.float32), torch.empty(labels.shape, device=dev, dtype=torch.int64))
+            self._stage_used[k] = False
+        with torch.cuda.stream(self._h2d_stream):
+            if self._stage_used[k]:
+                self._h2d_stream.wait_event(self._stage_free[k])      # the step that read this slot has been enqueued and finished
+            buf[0].copy_(images, non_blocking=True)
+            buf[1].copy_(labels, non_blocking=True)
+            self._stage_ready[k].record(self._h2d_stream)
+
+    def _step_from_stage(self, k):
+        cur = torch.cuda.current_stream(self.flat_p.device)
+        cur.wait_event(self._stage_ready[k])
+        loss = self.train_step(*self._stage_buf[k])
+        self._stage_free[k].record(cur)
+        self._stage_used[k] = True
+        return loss
+
+    def train_stream(self, batches):
+        """Generator over an iterable of HOST batches (images fp32 NCHW, labels int64; pinned memory for asynchronous copies): yields
+        the loss tensor of each step.  The copy of the next batch runs on a side stream while the current step computes, so a
+        training loop that reads the loss every step (train/main.py:392) still keeps the GPU busy."""
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        if nxt is not None:
+            self._stage(nxt, k)
+        while nxt is not None:
+            nxt2 = next(it, None)
+            if nxt2 is not None:
+                self._stage(nxt2, k ^ 1)
+            yield self._step_from_stage(k)
+            nxt, k = nxt2, k ^ 1
+
     # ---- CUDA graph of the whole step (forward, loss, backward, all-reduce, Adam): ~700 launches -> one replay ---------
     def capture_cuda_graph(self, images_shape, labels_shape, warmup=2):
         """Capture one full training step for fixed shapes.  State touched by the warm-up steps is restored, so training
