@@ -101,12 +101,13 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (i < iters) {
-          const long long q = (long long)u * 128 + i * rows_per_iter + r0;
-          if (q < total) {
-            rx[i] = (int)(q % p.EW);
-            const long long t2 = q / p.EW;
-            ry[i] = (int)(t2 % p.EH);
-            rn[i] = (int)(t2 / p.EH);
+          // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod here was the kernel's critical path
+          const unsigned q = (unsigned)u * 128u + (unsigned)(i * rows_per_iter + r0);
+          if (q < (unsigned)total) {
+            const unsigned t2 = q / (unsigned)p.EW;
+            rx[i] = (int)(q - t2 * (unsigned)p.EW);
+            rn[i] = (int)(t2 / (unsigned)p.EH);
+            ry[i] = (int)(t2 - (unsigned)rn[i] * (unsigned)p.EH);
           } else {
             rn[i] = -1; ry[i] = rx[i] = 0;
           }
@@ -185,12 +186,12 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
     uint32_t acc = 0, acc_phase = 0;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      const long long q = (long long)u * 128 + row;
+      const unsigned q = (unsigned)u * 128u + (unsigned)row;
       __nv_bfloat16* dst = nullptr;
-      if (q < total) {
-        const int x = (int)(q % p.EW);
-        const long long t2 = q / p.EW;
-        const int y = (int)(t2 % p.EH), n = (int)(t2 / p.EH);
+      if (q < (unsigned)total) {
+        const unsigned t2 = q / (unsigned)p.EW;
+        const int x = (int)(q - t2 * (unsigned)p.EW);
+        const int n = (int)(t2 / (unsigned)p.EH), y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
         dst = outp + (((size_t)n * p.Ho + (p.out_step * y + p.out_oy)) * p.Wo + (out_step_x * x + p.out_ox)) * p.out_ld + p.out_c0;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -282,6 +283,7 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
     return ERF_ERR_UNSUPPORTED;
   }
   const long long total = (long long)d->EN * d->EH * d->EW;
+  ERF_CHECK_ARG(total + 128 < 0x7fffffffLL, "erf_conv_im2col_tc: %lld output pixels exceed the 32-bit index range", total);
   erf_im2col_desc p = *d;
   p.units = (int)((total + 127) / 128);
   size_t smem = (size_t)w_pad + (size_t)slots * slot_bytes + 1024;

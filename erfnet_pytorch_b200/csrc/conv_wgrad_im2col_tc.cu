@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
       uint8_t* base = smem + (size_t)stage * stage_bytes;
       // per-unit pixel table (64 rows); the loader group syncs on named barrier 1
       if (tid < kWiPX) {
-        const long long q = (long long)u * kWiPX + tid;
-        if (q < total) {
-          s_row[stage][tid][2] = (int)(q % p.EW);
-          const long long t2 = q / p.EW;
-          s_row[stage][tid][1] = (int)(t2 % p.EH);
-          s_row[stage][tid][0] = (int)(t2 / p.EH);
+        const unsigned q = (unsigned)u * (unsigned)kWiPX + (unsigned)tid;   // 32-bit index arithmetic (host-checked range)
+        if (q < (unsigned)total) {
+          const unsigned t2 = q / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
+          s_row[stage][tid][2] = (int)(q - t2 * (unsigned)p.EW);
+          s_row[stage][tid][1] = (int)(t2 - nn * (unsigned)p.EH);
+          s_row[stage][tid][0] = (int)nn;
         } else {
           s_row[stage][tid][0] = -1;
         }
@@ -255,6 +255,7 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   // the last group's unused atoms read past the gathered tiles: keep those reads inside the (zeroed) allocation
   p.tail_bytes = atoms_per_m * kWiPX * RBg;
   const long long total = (long long)d->EN * d->EH * d->EW;
+  ERF_CHECK_ARG(total + kWiPX < 0x7fffffffLL, "erf_conv_wgrad_im2col_tc: %lld pixels exceed the 32-bit index range", total);
   const int units = (int)((total + kWiPX - 1) / kWiPX);
   // two CTAs per SM when two rings of >= 2 stages and two accumulator sets fit (latency-bound per-unit chain)
   int per_sm = 1;

@@ -1,0 +1,21 @@
+"""Eval-mode forwards only (for ncu captures of the inference kernels)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import NC, synth_batch  # noqa: E402
+from erfnet_pytorch_b200 import erfnet as E  # noqa: E402
+from oracle import erfnet_oracle as O  # noqa: E402
+
+model = E.ERFNet(NC)
+model.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), 0))
+model = model.cuda().eval()
+x, _ = synth_batch(torch, 0, 6)
+x = x.cuda()
+for _ in range(3):
+    with torch.no_grad():
+        model(x)
+torch.cuda.synchronize()
+print("ok")
