@@ -329,6 +329,77 @@ __global__ void __launch_bounds__(BS_THREADS, 2) affine_act_v2_kernel(const T* _
   }
 }
 
+// ---- MaxPool2d(2, 2) half of a DownsamplerBlock, 8 channels (16 bytes for bf16) per thread, 32-bit index arithmetic ---------------
+// forward: out[.., out_coff + c] = relu?(max2x2(in)[c] * scale[c] + shift[c])
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_v2_kernel(const T* __restrict__ in, int H, int W, int C, int in_ld, T* __restrict__ out, int out_ld,
+                                                             int out_coff, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                                             unsigned total8) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const unsigned c8 = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
+  const unsigned p = i / c8, c0 = (i - p * c8) * 8u;
+  const unsigned t = p / Wo, ox = p - t * Wo, n = t / Ho, oy = t - n * Ho;
+  const T* ip = in + (((size_t)n * H + 2 * oy) * W + 2 * ox) * in_ld + c0;
+  Raw8<T> r[4];
+  r[0].load(ip); r[1].load(ip + in_ld); r[2].load(ip + (size_t)W * in_ld); r[3].load(ip + (size_t)W * in_ld + in_ld);
+  float m[8], f[8];
+  r[0].unpack(m);
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    r[q].unpack(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (scale) m[k] = m[k] * scale[c0 + k] + shift[c0 + k];
+    if (relu) m[k] = fmaxf(m[k], 0.f);
+  }
+  Raw8<T>::store(out + (size_t)p * out_ld + out_coff + c0, m);
+}
+
+// backward: dx at the FIRST maximum of each window (torch's tie rule, scan order (0,0),(0,1),(1,0),(1,1)) += dout[.., out_coff + c]
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_v2_kernel(const T* __restrict__ in, int H, int W, int C, int in_ld, const T* __restrict__ dout,
+                                                             int out_ld, int out_coff, T* __restrict__ dx, int dx_ld, unsigned total8) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const unsigned c8 = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
+  const unsigned p = i / c8, c0 = (i - p * c8) * 8u;
+  const unsigned t = p / Wo, ox = p - t * Wo, n = t / Ho, oy = t - n * Ho;
+  const size_t base = ((size_t)n * H + 2 * oy) * W + 2 * ox;
+  const size_t offs[4] = {0, 1, (size_t)W, (size_t)W + 1};
+  float m[8], f[8], g[8];
+  int arg[8];
+  Raw8<T> r;
+  r.load(in + base * in_ld + c0);
+  r.unpack(m);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) arg[k] = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    r.load(in + (base + offs[q]) * in_ld + c0);
+    r.unpack(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (f[k] > m[k]) { m[k] = f[k]; arg[k] = q; }
+  }
+  r.load(dout + (size_t)p * out_ld + out_coff + c0);
+  r.unpack(g);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    T* dp = dx + (base + offs[q]) * dx_ld + c0;
+    r.load(dp);
+    r.unpack(f);
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (arg[k] == q) { f[k] += g[k]; any = true; }
+    if (any) Raw8<T>::store(dp, f);
+  }
+}
+
 // launch geometry shared by the kernels above
 struct BsLaunch {
   unsigned grid;

@@ -386,6 +386,19 @@ extern "C" int erf_maxpool2x2_fwd(const void* in, int N, int H, int W, int C, in
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   unsigned grid = (unsigned)((total + 255) / 256);
   size_t smem = stats ? 2 * C * sizeof(float) : 0;
+  {
+    const long long total8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    if (!stats && (C % 8) == 0 && (in_ld % 8) == 0 && (out_ld % 8) == 0 && (out_coff % 8) == 0 && total8 < 0x7fffffffLL && ((uintptr_t)in % 16) == 0 &&
+        ((uintptr_t)out % 16) == 0) {
+      const unsigned g8 = (unsigned)((total8 + 255) / 256);
+      if (dtype == ERF_F32)
+        maxpool_fwd_v2_kernel<float><<<g8, 256, 0, (cudaStream_t)stream>>>((const float*)in, H, W, C, in_ld, (float*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
+      else
+        maxpool_fwd_v2_kernel<__nv_bfloat16><<<g8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, H, W, C, in_ld, (__nv_bfloat16*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
+      ERF_CHECK_LAUNCH("erf_maxpool2x2_fwd");
+      return ERF_OK;
+    }
+  }
   if (dtype == ERF_F32)
     maxpool_fwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)in, N, H, W, C, in_ld, (float*)out, out_ld, out_coff, scale, shift, relu, stats, stats_c);
   else
@@ -398,6 +411,19 @@ extern "C" int erf_maxpool2x2_bwd(const void* in, int N, int H, int W, int C, in
                                   int dx_ld, int dtype, erf_stream_t stream) {
   CHECK_DTYPE("erf_maxpool2x2_bwd");
   ERF_CHECK_ARG(in && dout && dx && N > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, "erf_maxpool2x2_bwd: bad arguments");
+  {
+    const long long total8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    if ((C % 8) == 0 && (in_ld % 8) == 0 && (out_ld % 8) == 0 && (out_coff % 8) == 0 && (dx_ld % 8) == 0 && total8 < 0x7fffffffLL &&
+        ((uintptr_t)in % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dx % 16) == 0) {
+      const unsigned g8 = (unsigned)((total8 + 255) / 256);
+      if (dtype == ERF_F32)
+        maxpool_bwd_v2_kernel<float><<<g8, 256, 0, (cudaStream_t)stream>>>((const float*)in, H, W, C, in_ld, (const float*)dout, out_ld, out_coff, (float*)dx, dx_ld, (unsigned)total8);
+      else
+        maxpool_bwd_v2_kernel<__nv_bfloat16><<<g8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, H, W, C, in_ld, (const __nv_bfloat16*)dout, out_ld, out_coff, (__nv_bfloat16*)dx, dx_ld, (unsigned)total8);
+      ERF_CHECK_LAUNCH("erf_maxpool2x2_bwd");
+      return ERF_OK;
+    }
+  }
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   unsigned grid = (unsigned)((total + 255) / 256);
   if (dtype == ERF_F32)

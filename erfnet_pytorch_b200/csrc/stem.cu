@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, 
   }
   __syncthreads();
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo;
+  const unsigned total = (unsigned)N * (unsigned)Ho * (unsigned)Wo;   // host-checked < 2^31: 32-bit index arithmetic
   float st_sum[STEM_C], st_sq[STEM_C];
 #pragma unroll
   for (int c = 0; c < STEM_C; ++c) st_sum[c] = st_sq[c] = 0.f;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(p % Wo);
-    const long long t2 = p / Wo;
-    const int oy = (int)(t2 % Ho), n = (int)(t2 / Ho);
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+    const unsigned t2 = p / (unsigned)Wo;
+    const int ox = (int)(p - t2 * (unsigned)Wo);
+    const int n = (int)(t2 / (unsigned)Ho), oy = (int)(t2 - (unsigned)n * (unsigned)Ho);
     float acc[STEM_C];
 #pragma unroll
     for (int c = 0; c < STEM_C; ++c) acc[c] = s_b[c];
@@ -205,6 +205,7 @@ extern "C" int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, 
   ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "erf_stem_fwd: scale and shift must be given together");
   ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "erf_stem_fwd: tensors must be 16-byte aligned");
   const long long total = (long long)N * (H / 2) * (W / 2);
+  ERF_CHECK_ARG(total < 0x7fffffffLL, "erf_stem_fwd: %lld output pixels exceed the 32-bit index range", total);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 6) blocks = 148 * 6;
   cudaStream_t s = (cudaStream_t)stream;
