@@ -69,6 +69,8 @@ _SIGNATURES = {
     "erf_adam_step_dev": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "erf_conv1d_pair_tc_supported": [_i, _i, _i],
+    "erf_conv1d_pair_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "erf_pack_conv1d_tc": [_vp, _i, _vp, _vp, _vp],
     "erf_pack_conv1d_tc_batched": [_vp, _i, _i, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],

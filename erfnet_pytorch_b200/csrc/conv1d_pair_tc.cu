@@ -1,0 +1,390 @@
+// Fused pair of the factorised convolutions of non_bottleneck_1d (eval/erfnet.py:47-51 and 53-61):
+//
+//     out = act2( conv1x3_d( relu( conv3x1_d(x) + b1 ) ) + b2 [+ res] )
+//
+// in ONE kernel for C = 16 / 64.  A unit is a whole image row (W <= 512 pixels = NT <= 4 tiles of 128): the 3x1 conv of row y
+// reads rows y-d, y, y+d (TMA boxes, out-of-image rows zero-filled), its accumulators go TMEM -> registers -> (+b1, ReLU, bf16)
+// -> a swizzled K-major ROW BUFFER in shared memory with d zero pixels of halo on both sides, and the 1x3 conv then runs its
+// three taps as row-shifted UMMA descriptors over that buffer -- the intermediate tensor never leaves the SM and, because the
+// unit is a full row, the horizontal halo is free.  Two sets of TMEM accumulators per stage (and two row buffers at C = 16) let
+// stage 1 of row i+1 overlap stage 2 of row i.  Versus two conv1d_tc launches: half the launches (6 us of fixed cost each at batch 6),
+// no write + re-read of the intermediate, and the same arithmetic in the same order (bit-identical results).
+//
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 stage-1 epilogue (TMEM -> row buffer),
+// warps 6-9 stage-2 epilogue (TMEM -> staging -> TMA store, residual tile TMA-prefetched into the staging buffer).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace erfk {
+using namespace tc;
+
+struct PairParams {
+  const __nv_bfloat16* w1_img;   // [3][C][C] swizzled images as for conv1d_tc (forward orientation)
+  const __nv_bfloat16* w2_img;
+  const float* bias1;
+  const float* bias2;
+  int N, H, W, dil, relu, has_res;
+  int rows, NT, slots, t_rows, t_bytes;
+};
+
+constexpr int kPairThreads = 352, kPairMaxSlots = 8, NSTG = 4;
+
+__device__ __forceinline__ void pair_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                                                                        const __grid_constant__ CUtensorMap tmap_res, const PairParams p) {
+  constexpr int RB = C * 2;                      // bytes per pixel row (one k-chunk: C <= 64)
+  constexpr int KSTEPS = C / 16;
+  constexpr int CPR = RB / 16;
+  constexpr uint32_t LAYOUT = RB == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
+  constexpr int W_BYTES = 3 * C * RB;
+  constexpr int W_PAD = ((W_BYTES + 1023) / 1024) * 1024;
+  constexpr int TILE = 128 * RB;                 // one 128-pixel tile
+  constexpr int TILE_PAD = ((TILE + 1023) / 1024) * 1024;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, C);
+  constexpr int TB = C == 64 ? 1 : 2;            // row buffers: at C = 64 the 34 KB are worth more as two extra ring slots (loads in flight)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w1 = smem;
+  uint8_t* s_w2 = s_w1 + W_PAD;
+  uint8_t* s_t = s_w2 + W_PAD;                   // TB row buffers
+  uint8_t* s_stg = s_t + TB * p.t_bytes;         // NSTG staging tiles
+  uint8_t* s_a = s_stg + NSTG * TILE_PAD;        // operand ring
+  __shared__ uint64_t full_bar[kPairMaxSlots], empty_bar[kPairMaxSlots], w_bar;
+  __shared__ uint64_t d1_full[2], d1_empty[2], t_full[2], t_empty[2], d2_full[2], d2_empty[2], aux_bar[NSTG];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_b1[C], s_b2[C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NT = p.NT;
+  const uint32_t tmem_cols = 4u * NT * C <= 32 ? 32u : (4u * NT * C <= 64 ? 64u : (4u * NT * C <= 128 ? 128u : (4u * NT * C <= 256 ? 256u : 512u)));
+
+  for (int i = tid; i < C; i += blockDim.x) {
+    s_b1[i] = p.bias1 ? p.bias1[i] : 0.f;
+    s_b2[i] = p.bias2 ? p.bias2[i] : 0.f;
+  }
+  // zero both row buffers once: the halo pixels stay zero (= the conv padding), the interior is overwritten every row
+  for (int i = tid; i < TB * p.t_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_t)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    for (int s = 0; s < p.slots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&d1_full[a], 1);
+      mbar_init(&d1_empty[a], 1);
+      mbar_init(&t_full[a], 1);
+      mbar_init(&t_empty[a], 1);
+      mbar_init(&d2_full[a], 1);
+      mbar_init(&d2_empty[a], 4);
+    }
+    for (int a = 0; a < NSTG; ++a) mbar_init(&aux_bar[a], 1);
+    mbar_init(&w_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_out);
+    if (p.has_res) tma_prefetch_desc(&tmap_res);
+  }
+  __syncthreads();
+  if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int cnt = (int)blockIdx.x < p.rows ? (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // rows of this CTA
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, 2 * W_BYTES);
+      pair_bulk_g2s(s_w1, p.w1_img, W_BYTES, &w_bar);
+      pair_bulk_g2s(s_w2, p.w2_img, W_BYTES, &w_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const int r = blockIdx.x + i * gridDim.x, n = r / p.H, y = r % p.H;
+        for (int m = 0; m < NT; ++m) {
+#pragma unroll 1
+          for (int t = 0; t < 3; ++t) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)TILE);
+            tma_load_4d(s_a + (size_t)slot * TILE_PAD, &tmap_in, &full_bar[slot], 0, 128 * m, y + (t - 1) * p.dil, n);
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: stage 1 of row i, then stage 2 of row i-1 =================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t w1_addr = smem_u32(s_w1), w2_addr = smem_u32(s_w2), t_addr = smem_u32(s_t);
+      const uint32_t desc_hi = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);
+      mbar_wait(&w_bar, 0);
+      for (int i = 0; i <= cnt; ++i) {
+        if (i < cnt) {
+          const int par = i & 1;
+          mbar_wait(&d1_empty[par], ((i >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          for (int m = 0; m < NT; ++m) {
+            const uint32_t d_tmem = tmem_base + (par * NT + m) * C;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              mbar_wait(&full_bar[slot], phase);
+              tcgen05_fence_after();
+              const uint32_t a_lo = ((smem_u32(s_a + (size_t)slot * TILE_PAD) >> 4) & 0x3FFF) | (1u << 16);
+              const uint32_t b_lo = (((w1_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                          (t | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[slot]);
+              if (++slot == p.slots) { slot = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(&d1_full[par]);
+        }
+        if (i >= 1) {
+          const int j = i - 1, par = j & 1;
+          const int tbi = j % TB;
+          mbar_wait(&t_full[tbi], (j / TB) & 1);
+          mbar_wait(&d2_empty[par], ((j >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tb = t_addr + tbi * p.t_bytes;
+          for (int m = 0; m < NT; ++m) {
+            const uint32_t d_tmem = tmem_base + ((2 + par) * NT + m) * C;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              // pixel q - d + t*d of the row = row buffer index q + t*d (d halo pixels in front)
+              const uint32_t a_lo = (((tb + (128 * m + t * p.dil) * RB) >> 4) & 0x3FFF) | (1u << 16);
+              const uint32_t b_lo = (((w2_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                          (t | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&t_empty[tbi]);
+          umma_commit(&d2_full[par]);
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // ================= stage-1 epilogue: TMEM -> (+b1, ReLU, bf16) -> row buffer =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    for (int i = 0; i < cnt; ++i) {
+      const int par = i & 1;
+      const int tbi = i % TB;
+      mbar_wait(&d1_full[par], (i >> 1) & 1);
+      mbar_wait(&t_empty[tbi], ((i / TB) & 1) ^ 1);     // stage 2 of row i-TB has read this row buffer
+      tcgen05_fence_after();
+      uint8_t* tb = s_t + tbi * p.t_bytes;
+      for (int m = 0; m < NT; ++m) {
+        const uint32_t taddr = tmem_base + (par * NT + m) * C + ((uint32_t)(quad * 32) << 16);
+        uint32_t r[C];
+        if (C == 64) { tmem_ld32(taddr, r); tmem_ld32(taddr + 32, r + 32); }
+        else tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        const int rr = p.dil + 128 * m + row;             // row-buffer index of this pixel
+        const int key = CPR == 8 ? (rr & 7) : ((rr >> 2) & 1);
+        uint8_t* my_row = tb + (size_t)rr * RB;
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) {
+          uint4 t4;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + s_b1[q * 8 + 2 * e], 0.f);
+            const float b = fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + s_b1[q * 8 + 2 * e + 1], 0.f);
+            h[e] = __floats2bfloat162_rn(a, b);
+          }
+          *reinterpret_cast<uint4*>(my_row + ((q ^ key) * 16)) = t4;
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();                          // row-buffer writes -> visible to the UMMA (async proxy)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        mbar_arrive(&t_full[tbi]);
+        mbar_arrive(&d1_empty[par]);
+      }
+    }
+  } else if (warp >= 6 && warp < 10) {
+    // ================= stage-2 epilogue: TMEM -> (+b2, +res, ReLU, bf16) -> staging -> TMA store =================
+    // One group works through every tile, so nothing else hides a TMA round trip: NSTG staging buffers let the store of step s-1
+    // still be reading while step s is staged (wait_group.read 1) and let the residual tile of step s+2 be prefetched two steps ahead.
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool leader = (warp == 6 && lane == 0);
+    const int sw_key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
+    uint32_t aux_phase = 0;                               // bit b: phase of aux_bar[b]
+    const int total_steps = cnt * NT;
+    auto prefetch_res = [&](int s) {                      // residual tile of step s -> staging buffer s % NSTG
+      if (s >= total_steps) return;
+      const int ii = s / NT, mm = s - ii * NT, rr = blockIdx.x + ii * gridDim.x, bb = s % NSTG;
+      mbar_arrive_expect_tx(&aux_bar[bb], (uint32_t)TILE);
+      tma_load_4d(s_stg + bb * TILE_PAD, &tmap_res, &aux_bar[bb], 0, 128 * mm, rr % p.H, rr / p.H);
+    };
+    if (leader && p.has_res) {
+      prefetch_res(0);
+      prefetch_res(1);
+    }
+    int step = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int par = i & 1;
+      const int r = blockIdx.x + i * gridDim.x, n = r / p.H, y = r % p.H;
+      mbar_wait(&d2_full[par], (i >> 1) & 1);
+      tcgen05_fence_after();
+      for (int m = 0; m < NT; ++m, ++step) {
+        const int b = step % NSTG;
+        uint8_t* my_row = s_stg + b * TILE_PAD + row * RB;
+        const uint32_t taddr = tmem_base + ((2 + par) * NT + m) * C + ((uint32_t)(quad * 32) << 16);
+        uint32_t rg[C];
+        if (C == 64) { tmem_ld32(taddr, rg); tmem_ld32(taddr + 32, rg + 32); }
+        else tmem_ld16(taddr, rg);
+        if (p.has_res) {
+          mbar_wait(&aux_bar[b], (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
+        }
+        tmem_ld_wait();
+        if (m == NT - 1) {                                // all TMEM reads of this row are done
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d2_empty[par]);
+        }
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rg[q * 8 + e]) + s_b2[q * 8 + e];
+          uint8_t* cptr = my_row + ((q ^ sw_key) * 16);
+          if (p.has_res) {
+            const uint4 a4 = *reinterpret_cast<const uint4*>(cptr);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(h[e]); v[2 * e + 1] += __high2float(h[e]); }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          uint4 t4;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          *reinterpret_cast<uint4*>(cptr) = t4;
+        }
+        fence_proxy_async_smem();
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // stores up to step-2 have finished reading
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (leader) {
+          tma_store_4d(&tmap_out, s_stg + b * TILE_PAD, 0, 128 * m, y, n);
+          tma_store_commit();
+          if (p.has_res) prefetch_res(step + 2);          // into the buffer whose store (step-2) is known to be done
+        }
+      }
+    }
+    if (leader) tma_store_wait0();
+  }
+  // ---- teardown ----------------------------------------------------------------------------------------------------
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*PairEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int pair_make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C) {
+  static PairEncodeFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (PairEncodeFn)q;
+  }
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace erfk
+
+using namespace erfk;
+
+extern "C" int erf_conv1d_pair_tc_supported(int C, int W, int dil) {
+  if (!((C == 16 || C == 64) && W >= 128 && (W % 128) == 0 && dil >= 1 && dil <= 16)) return 0;
+  const int NT = W / 128;
+  return NT <= 4 && 4 * NT * C <= 512;
+}
+
+extern "C" int erf_conv1d_pair_tc(const void* in, const void* w1_img, const float* bias1, const void* w2_img, const float* bias2, void* out,
+                                  const void* res, int N, int H, int W, int C, int dil, int relu, erf_stream_t stream) {
+  ERF_CHECK_ARG(in && w1_img && w2_img && out && N > 0 && H > 0, "erf_conv1d_pair_tc: null pointer / empty tensor");
+  if (!erf_conv1d_pair_tc_supported(C, W, dil)) {
+    set_error("erf_conv1d_pair_tc: unsupported shape C=%d W=%d dil=%d (need C in {16,64}, W %% 128 == 0, W/128 * C <= 128, dil <= 16)", C, W, dil);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tin, tout, tres;
+  if (pair_make_map(&tin, in, N, H, W, C) != 0 || pair_make_map(&tout, out, N, H, W, C) != 0 || pair_make_map(&tres, res ? res : out, N, H, W, C) != 0) {
+    set_error("erf_conv1d_pair_tc: cuTensorMapEncodeTiled failed");
+    return ERF_ERR_CUDA;
+  }
+  const int RB = C * 2;
+  PairParams p;
+  p.w1_img = (const __nv_bfloat16*)w1_img;
+  p.w2_img = (const __nv_bfloat16*)w2_img;
+  p.bias1 = bias1; p.bias2 = bias2;
+  p.N = N; p.H = H; p.W = W; p.dil = dil; p.relu = relu; p.has_res = res != nullptr;
+  p.rows = N * H;
+  p.NT = W / 128;
+  p.t_rows = ((W + 2 * dil + 7) / 8) * 8 + 8;          // + one swizzle group of slack behind the last halo pixel
+  p.t_bytes = ((p.t_rows * RB + 1023) / 1024) * 1024;
+  const int w_pad = ((3 * C * RB + 1023) / 1024) * 1024;
+  const int tile_pad = ((128 * RB + 1023) / 1024) * 1024;
+  const int tbufs = C == 64 ? 1 : 2;
+  const int budget = 224 * 1024 - 2 * w_pad - tbufs * p.t_bytes - NSTG * tile_pad;
+  p.slots = budget / tile_pad;
+  if (p.slots > kPairMaxSlots) p.slots = kPairMaxSlots;
+  if (p.slots < 3) {
+    set_error("erf_conv1d_pair_tc: row of %d pixels x %d channels does not fit in shared memory", W, C);
+    return ERF_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)2 * w_pad + tbufs * p.t_bytes + NSTG * tile_pad + (size_t)p.slots * tile_pad + 1024;
+  // C = 16: ~80 KB of shared memory, 68 registers, <= 256 TMEM columns -> two CTAs per SM hide the per-row latency chain
+  const int ctas = (C == 16 && smem <= 100 * 1024 && 4 * p.NT * C <= 256) ? 296 : 148;
+  const int grid = p.rows < ctas ? p.rows : ctas;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (C == 16) {
+    e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv1d_pair_tc_kernel<16><<<grid, kPairThreads, smem, st>>>(tin, tout, tres, p);
+  } else {
+    e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) conv1d_pair_tc_kernel<64><<<grid, kPairThreads, smem, st>>>(tin, tout, tres, p);
+  }
+  if (e != cudaSuccess) {
+    set_error("erf_conv1d_pair_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return ERF_ERR_CUDA;
+  }
+  ERF_CHECK_LAUNCH("erf_conv1d_pair_tc");
+  return ERF_OK;
+}

@@ -410,6 +410,9 @@ class non_bottleneck_1d(_B200Module):
         d = self.dilated
         if "tc" in pk and ops.conv1d_tc_supported(self.chann, x.shape[2], d, x.dtype) and ops.USE_TC:
             tc = pk["tc"]
+            if ops.conv1d_pair_tc_supported(self.chann, x.shape[2], d, x.dtype) and ops.conv1d_pair_tc_supported(self.chann, x.shape[2], 1, x.dtype):
+                t = ops.conv1d_pair_tc(x, tc[0], b[0], tc[1], b[1], 1, relu=True)            # 3x1 -> ReLU -> 1x3 (+BN1 folded) -> ReLU
+                return ops.conv1d_pair_tc(t, tc[2], b[2], tc[3], b[3], d, relu=True, res=x)  # dilated pair (+BN2 folded) + x -> ReLU
             t = ops.conv1d_tc(x, tc[0], b[0], False, 1, relu=True)
             t = ops.conv1d_tc(t, tc[1], b[1], True, 1, relu=True)
             t = ops.conv1d_tc(t, tc[2], b[2], False, d, relu=True)

@@ -222,6 +222,23 @@ def pack_conv1d_tc_pair(w: torch.Tensor):
     return imgs[0], imgs[1]
 
 
+def conv1d_pair_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
+    return dtype == torch.bfloat16 and not EMULATED and USE_TC and USE_PAIR and bool(_lib.lib().erf_conv1d_pair_tc_supported(c, w, dil))
+
+
+USE_PAIR = True   # fused 3x1 -> ReLU -> 1x3 pairs in eval mode (C = 16 / 64)
+
+
+def conv1d_pair_tc(x, w1_img, b1, w2_img, b2, dil, relu=True, res=None):
+    """act(conv1x3_d(relu(conv3x1_d(x) + b1)) + b2 [+ res]) in one launch; bit-identical to two conv1d_tc calls."""
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    with _timed("conv1d_pair_tc_kernel", 2.0 * 2.0 * n * h * w * c * c * 3):
+        check(_lib.lib().erf_conv1d_pair_tc(_p(x), _p(w1_img), _p(b1), _p(w2_img), _p(b2), _p(out), _p(res), n, h, w, c, dil, int(relu), _stream(x)))
+    _count()
+    return out
+
+
 class Conv1dPackTable:
     """Device table for erf_pack_conv1d_tc_batched: every listed Conv2d weight [C,C,3,1]/[C,C,1,3] (fp32, contiguous, fixed
     address -- e.g. views of a flat parameter buffer) is re-packed into persistent (forward, data-gradient) images by ONE launch."""

@@ -204,6 +204,13 @@ int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* ou
                   int N, int H, int W, int C, int horizontal, int dil, int relu, double* stats, float* colsum,
                   erf_stream_t stream);
 
+/* Fused pair out = act(conv1x3_d(relu(conv3x1_d(in) + bias1)) + bias2 [+ res]) -- one half of a non_bottleneck_1d block in eval mode
+ * (eval/erfnet.py:47-51 / 53-61 with BN folded into w2/bias2) -- in one kernel: the intermediate row stays in shared memory.
+ * C = 16 or 64, W % 128 == 0, (W/128)*C <= 128; images as for erf_conv1d_tc; results are bit-identical to two erf_conv1d_tc calls. */
+int erf_conv1d_pair_tc_supported(int C, int W, int dil);
+int erf_conv1d_pair_tc(const void* in, const void* w1_img, const float* bias1, const void* w2_img, const float* bias2, void* out,
+                       const void* res, int N, int H, int W, int C, int dil, int relu, erf_stream_t stream);
+
 /* Build both operand images (forward and data-gradient) of a 3-tap conv weight w[Co][Ci][3] fp32 (= nn.Conv2d weight
  * [Co,Ci,3,1] or [Co,Ci,1,3], contiguous) for erf_conv1d_tc; each image is 3*C*C bf16. */
 int erf_pack_conv1d_tc(const float* w, int C, void* img_fwd, void* img_dgrad, erf_stream_t stream);
