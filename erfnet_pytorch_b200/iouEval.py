@@ -22,10 +22,26 @@ class iouEval:
         classes = self.nClasses if self.ignoreIndex == -1 else self.nClasses - 1
         self._classes = classes
         self._cm = None  # device u64 (as int64) [nClasses, nClasses], allocated on first addBatch
-        self.tp = torch.zeros(classes).double()
-        self.fp = torch.zeros(classes).double()
-        self.fn = torch.zeros(classes).double()
+        self._tp = torch.zeros(classes).double()
+        self._fp = torch.zeros(classes).double()
+        self._fn = torch.zeros(classes).double()
         self._dirty = False
+
+    # tp / fp / fn are attributes of the reference class (eval/iouEval.py:15-19): kept readable at any time, synchronised lazily
+    @property
+    def tp(self):
+        self._sync()
+        return self._tp
+
+    @property
+    def fp(self):
+        self._sync()
+        return self._fp
+
+    @property
+    def fn(self):
+        self._sync()
+        return self._fn
 
     def addBatch(self, x, y):  # x = preds, y = targets; "batch_size x 1 x H x W" label maps (or [B,H,W])
         if not (x.is_cuda and y.is_cuda) and not ops.EMULATED:
@@ -47,10 +63,10 @@ class iouEval:
         if self._dirty:
             kept = self._classes if self.ignoreIndex == -1 else min(self._classes, self.ignoreIndex)
             t = ops.iou_counts(self._cm, self.nClasses, self.ignoreIndex, kept).cpu()
-            self.tp = torch.zeros(self._classes).double()
-            self.fp = torch.zeros(self._classes).double()
-            self.fn = torch.zeros(self._classes).double()
-            self.tp[:kept], self.fp[:kept], self.fn[:kept] = t[0], t[1], t[2]
+            self._tp = torch.zeros(self._classes).double()
+            self._fp = torch.zeros(self._classes).double()
+            self._fn = torch.zeros(self._classes).double()
+            self._tp[:kept], self._fp[:kept], self._fn[:kept] = t[0], t[1], t[2]
             self._dirty = False
 
     def confusion_matrix(self):
@@ -63,7 +79,7 @@ class iouEval:
 
     def getIoU(self):
         self._sync()
-        num = self.tp
-        den = self.tp + self.fp + self.fn + 1e-15
+        num = self._tp
+        den = self._tp + self._fp + self._fn + 1e-15
         iou = num / den
         return torch.mean(iou), iou  # "iou mean", "iou per class"
