@@ -644,11 +644,12 @@ class _PlainConv:
     """A bare conv / transposed conv with bias (the two output_conv heads, eval/erfnet.py:85,124).  Built per call
     around the owner's nn.Conv2d / nn.ConvTranspose2d so that module replicas (DataParallel) stay independent."""
 
-    def __init__(self, conv: nn.Module, spec: ConvSpec):
+    def __init__(self, conv: nn.Module, spec: ConvSpec, relu: bool = False):
         self.spec = spec
         self._conv = conv
         self._tc = _TcConv(spec)
         self.out_ld = ops.round_up(spec.cout, 8)
+        self.relu = relu   # conv + bias + ReLU (the 3x3 conv of the fork's LadderBlock, train/erfnet_blocks.py:150-154)
 
     def _out(self, x, tc=False):
         n, h, w, _ = x.shape
@@ -666,22 +667,24 @@ class _PlainConv:
             self._conv.__dict__["_packed"] = c
         w, b, tc = c[1]
         if tc is not None and ops.USE_TC:
-            return self._tc.forward(x, tc, b, out=self._out(x, tc=True))
-        return ops.conv_fwd(x, w, self.spec, b, out=self._out(x))
+            return self._tc.forward(x, tc, b, relu=self.relu, out=self._out(x, tc=True))
+        return ops.conv_fwd(x, w, self.spec, b, relu=self.relu, out=self._out(x))
 
     def _train_params(self):
         return (self._conv.weight, self._conv.bias)
 
     def _fwd_train(self, x, ctx):
         if self._tc.fwd_ok(x.dtype):
-            y = self._tc.forward(x, self._tc.pack_fwd(self._conv.weight), self._conv.bias.detach().float(), out=self._out(x, tc=True))
+            y = self._tc.forward(x, self._tc.pack_fwd(self._conv.weight), self._conv.bias.detach().float(), relu=self.relu, out=self._out(x, tc=True))
         else:
             y = ops.conv_fwd(x, ops.pack_weight_fwd(self._conv.weight.detach(), self.spec, x.dtype), self.spec, self._conv.bias.detach().float(),
-                             out=self._out(x))
-        return y, (x,)
+                             relu=self.relu, out=self._out(x))
+        return y, (x, y if self.relu else None)
 
     def _bwd(self, dy, saved, need_dx):
-        (x,) = saved
+        x, y = saved
+        if self.relu:
+            dy = ops.relu_bwd(dy, y)
         cw, cb = self._train_params()
         dw, db = self._tc.wgrad(x, dy, cw, cb, bias_is_zero=False)
         dx = None

@@ -3,11 +3,14 @@ with the FORK's defaults -- BatchNorm off, dropout off unless ``use_dropout`` --
 in the fork's net_*.py files resolves to these.  The BatchNorm modules are still constructed (their parameters and
 buffers are part of the fork's checkpoints) but take no part in the arithmetic when ``use_batchnorm`` is False.
 
-Built so far: DownsamplerBlock, non_bottleneck_1d, UpsamplerBlock, DecoderBlockSmall, DecoderBlock (train + eval, all
-on the same kernels as erfnet.py).  SoftMaxConv and LadderBlock are SURVEY section 8(f) "next" items."""
+Built: DownsamplerBlock, non_bottleneck_1d, UpsamplerBlock, DecoderBlockSmall, DecoderBlock, LadderBlock (train + eval, all
+on the same kernels as erfnet.py).  SoftMaxConv is a SURVEY section 8(f) "next" item."""
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
+
+from .ops import ConvSpec
 
 from . import erfnet as _E
 
@@ -55,3 +58,30 @@ class DecoderBlock(DecoderBlockSmall):
     def __init__(self, in_channels, out_channels, use_dropout=False):
         super().__init__(in_channels, out_channels, use_dropout)
         self.layers.append(non_bottleneck_1d(out_channels, 0, 1, use_dropout=use_dropout))
+
+
+class LadderBlock(_E._B200Module):
+    """train/erfnet_blocks.py:140-154: cat(input, input_ladder) -> non_bottleneck_1d(2C, 0.03, 1) -> Conv2d(2C, C, 3, padding 1) -> ReLU.
+    The channel concat happens on the NHWC tensors (one copy), the 3x3 conv + bias + ReLU is one tcgen05 launch."""
+
+    def __init__(self, noutput, use_batchnorm=False, use_dropout=False):
+        super().__init__()
+        if use_batchnorm:
+            raise NotImplementedError("LadderBlock(use_batchnorm=True) is not used by any of the fork's nets and is not built")
+        self.use_batchnorm = use_batchnorm
+        self.layer = non_bottleneck_1d(2 * noutput, 0.03, 1, use_dropout=use_dropout)
+        self.conv = nn.Conv2d(2 * noutput, noutput, 3, stride=1, padding=1, bias=True)
+        self.bn = nn.BatchNorm2d(noutput, eps=_E.BN_EPS)
+        self.noutput = noutput
+        self._out_c = noutput
+
+    def _nhwc2(self, x, ladder, ctx):
+        y = torch.cat((x, ladder), dim=-1)                       # NHWC: channels are the last dimension
+        y = self.layer._nhwc(y, ctx)
+        return _E._run(_E._PlainConv(self.conv, ConvSpec(2 * self.noutput, self.noutput, 3, 3, 1, 1, 1), relu=True), y, ctx)
+
+    def forward(self, input, input_ladder):
+        ctx = _E._Ctx(self._precision(), self.training)
+        x = _E._ToNHWC.apply(input, input.shape[1], ctx.dtype)
+        l = _E._ToNHWC.apply(input_ladder, input_ladder.shape[1], ctx.dtype)
+        return _E._ToNCHW.apply(self._nhwc2(x, l, ctx), self.noutput)

@@ -523,25 +523,38 @@ def conv_wgrad_im2col_tc(x: torch.Tensor, dy: torch.Tensor, spec: ConvSpec, dy_c
     avail = gld * 2                                   # bytes of the gathered pixel row
     copy = 8 if avail < 16 else min(avail // 16 * 16, cgp * 2)
     np_full = round_up(cd, 16)
-    taps = [(ky, kx) for ky in range(spec.kh) for kx in range(spec.kw)]
+    all_taps = [(ky, kx) for ky in range(spec.kh) for kx in range(spec.kw)]
     chg = 64 if cgp % 64 == 0 else 16
-    groups = -(-(len(taps) * (cgp // chg)) // (128 // chg))
+
+    def fits(ntaps, npad):   # two pipeline stages in shared memory and all accumulator groups in TMEM
+        groups = -(-(ntaps * (cgp // chg)) // (128 // chg))
+        stage = -(-(ntaps * (cgp // chg) * 64 * chg * 2) // 1024) * 1024 + npad * 128
+        return groups * npad <= 512 and stage * 2 <= 190 * 1024
+
+    # taps per launch (a 3x3 conv over 128 gathered channels does not fit at once: one kernel row per launch), then the N split
+    tpl = len(all_taps)
+    while tpl > 1 and not fits(tpl, 16):
+        tpl = max(1, tpl // 2) if tpl % spec.kw else (tpl - spec.kw if tpl > spec.kw else max(1, tpl // 2))
     npad = np_full
-    while groups * npad > 512 or (-(-(len(taps) * (cgp // chg) * 64 * chg * 2) // 1024) * 1024 + npad * 128) * 2 > 190 * 1024:
+    while npad > 16 and not fits(tpl, npad):
         npad = round_up(npad // 2, 16)
+    if not fits(tpl, npad):
+        raise RuntimeError(f"conv_wgrad_im2col_tc: {cg} gathered channels do not fit the kernel even one tap at a time")
     name = f"conv_wgrad_im2col_tc[{spec.cin}->{spec.cout} {spec.kh}x{spec.kw} s{spec.stride}{'T' if spec.transposed else ''}]" if DETAIL else "conv_wgrad_im2col_tc_kernel"
     with _timed(name, conv_flops(spec, n, ho, wo)):
-        for n0 in range(0, np_full, npad):
-            d = _lib.WgradIm2colDesc()
-            d.g, d.GH, d.GW, d.g_ld, d.Cg, d.CgP, d.g_copy_bytes, d.g_step = g.data_ptr(), gh, gw, gld, cg, cgp, copy, spec.stride
-            d.d, d.EN, d.EH, d.EW, d.d_ld, d.d_c0, d.d_c_base, d.Cd = dn.data_ptr(), n, eh, ew, dld, dbase + n0, dbase, cd
-            d.NP = min(npad, np_full - n0)
-            d.ntaps = len(taps)
-            for i, (ky, kx) in enumerate(taps):
-                d.tap_dy[i], d.tap_dx[i], d.tap_off[i] = ky - spec.pad_h, kx - spec.pad_w, ky * spec.kw + kx
-            d.KHW = spec.kh * spec.kw
-            check(L.erf_conv_wgrad_im2col_tc(C.byref(d), _p(dw_out), _p(ws), nbytes, _stream(x)))
-            _count(2)
+        for t0 in range(0, len(all_taps), tpl):
+            taps = all_taps[t0:t0 + tpl]
+            for n0 in range(0, np_full, npad):
+                d = _lib.WgradIm2colDesc()
+                d.g, d.GH, d.GW, d.g_ld, d.Cg, d.CgP, d.g_copy_bytes, d.g_step = g.data_ptr(), gh, gw, gld, cg, cgp, copy, spec.stride
+                d.d, d.EN, d.EH, d.EW, d.d_ld, d.d_c0, d.d_c_base, d.Cd = dn.data_ptr(), n, eh, ew, dld, dbase + n0, dbase, cd
+                d.NP = min(npad, np_full - n0)
+                d.ntaps = len(taps)
+                for i, (ky, kx) in enumerate(taps):
+                    d.tap_dy[i], d.tap_dx[i], d.tap_off[i] = ky - spec.pad_h, kx - spec.pad_w, ky * spec.kw + kx
+                d.KHW = spec.kh * spec.kw
+                check(L.erf_conv_wgrad_im2col_tc(C.byref(d), _p(dw_out), _p(ws), nbytes, _stream(x)))
+                _count(2)
     return dw_out
 
 

@@ -211,6 +211,40 @@ def erfnet_forward(x, sd: StateDict, only_encode=False, training=False, drop_sca
 
 
 # ----------------------------------------------------------------------------------------------
+# fork: ladder regression net (train/net_regression_ladder.py; BN off, dropout off for softmax_classes = 0)
+# ----------------------------------------------------------------------------------------------
+def decoder_block(x, sd: StateDict, p: str, n_nb: int = 2):
+    """train/erfnet_blocks.py:114-135: UpsamplerBlock -> n_nb x non_bottleneck_1d(C, 0, 1), BatchNorm off."""
+    y = upsampler_block(x, sd, p + ".layers.0", use_batchnorm=False)
+    for i in range(n_nb):
+        y = non_bottleneck_1d(y, sd, f"{p}.layers.{i + 1}", 1, use_batchnorm=False)
+    return y
+
+
+def ladder_block(x, ladder, sd: StateDict, p: str):
+    """train/erfnet_blocks.py:140-154: cat -> non_bottleneck_1d(2C, 0.03, 1) (dropout off) -> conv3x3 p1 -> ReLU."""
+    y = torch.cat((x, ladder), dim=1)
+    y = non_bottleneck_1d(y, sd, p + ".layer", 1, use_batchnorm=False)
+    return F.relu(F.conv2d(y, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1))
+
+
+def regression_ladder_forward(x, sd: StateDict):
+    """train/net_regression_ladder.py:41-52, 72-80, 122-128 with softmax_classes = 0: [B, 1 or 2, H, W]."""
+    e1 = downsampler_block(x, sd, "encoder.initial_block", use_batchnorm=False)
+    e2 = downsampler_block(e1, sd, "encoder.block1.0", use_batchnorm=False)
+    for i in range(1, 6):
+        e2 = non_bottleneck_1d(e2, sd, f"encoder.block1.{i}", 1, use_batchnorm=False)
+    e3 = downsampler_block(e2, sd, "encoder.block2.0", use_batchnorm=False)
+    for i, d in enumerate(ENC_DILATIONS):
+        e3 = non_bottleneck_1d(e3, sd, f"encoder.block2.{i + 1}", d, use_batchnorm=False)
+    y = decoder_block(e3, sd, "decoder.scalar_decoder_1")
+    y = ladder_block(y, e2, sd, "decoder.ladder_block_1")
+    y = decoder_block(y, sd, "decoder.scalar_decoder_2")
+    y = ladder_block(y, e1, sd, "decoder.ladder_block_2")
+    return F.conv_transpose2d(y, sd["decoder.scalar_output_conv.weight"], sd["decoder.scalar_output_conv.bias"], stride=2)
+
+
+# ----------------------------------------------------------------------------------------------
 # loss, metric, optimiser
 # ----------------------------------------------------------------------------------------------
 def cross_entropy_2d(logits, target, weight=None, ignore_index=-1):

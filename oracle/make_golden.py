@@ -186,6 +186,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "iou_kat.npz"), **kat)
     fork_losses(os.path.join(OUT, "fork_losses.npz"))
     blocks_nobn(os.path.join(OUT, "blocks_nobn.npz"))
+    ladder_net(os.path.join(OUT, "ladder_net.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -243,6 +244,46 @@ def blocks_nobn(path):
         res[name + "_y"], res[name + "_dx"] = yb.detach().numpy(), xb.grad.numpy()
         res[name + "_dw_up"] = m.layers[0].conv.weight.grad.numpy()
         res[name + "_db_last"] = m.layers[-1].conv1x3_2.bias.grad.numpy()
+    np.savez_compressed(path, **res)
+
+
+def ladder_net(path):
+    """train/net_regression_ladder.Net (BASELINE config 4): state_dict layout, eval outputs of the 1- and 2-channel heads and one
+    training step's loss + a few gradients (L1LossMasked on a 70 %-unlabelled target) at 64 x 128."""
+    import contextlib
+    import io
+    import warnings
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(REF, "train"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import evaluation_functions as ref_ev
+        import net_regression_ladder as ref_net
+        nets = {"reg": ref_net.Net(), "lik": ref_net.Net(likelihood_loss=True)}
+    res = {}
+    x = golden_input((2, 3, 64, 128), 71)
+    tgt = golden_input((2, 64, 128), 72) * 2.0
+    tgt[golden_input((2, 64, 128), 73) < 0.7] = -1.0
+    for name, m in nets.items():
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        sd = O.make_state_dict(shapes, seed=31)
+        m.load_state_dict(sd, strict=True)
+        if name == "reg":
+            with open(os.path.join(OUT, "ladder_net_keys.txt"), "w") as f:
+                for k, sh in shapes.items():
+                    f.write(f"{k} {sh}\n")
+        m.train()   # BN is off and dropout is off for softmax_classes = 0: train == eval arithmetic
+        y = m(x)
+        res[name + "_out"] = y.detach().numpy()
+        if name == "reg":
+            loss = ref_ev.L1LossMasked()(y, tgt)
+        else:
+            loss = ref_ev.LogLikelihoodLossMasked(opt_eps=0.05)(y[:, 0], y[:, 1].pow(2), tgt)   # train/main.py:356-365; eps 0.05 (not 1e-4) keeps the KAT well conditioned
+        loss.backward()
+        res[name + "_loss"] = np.float64(loss.item())
+        for k in ("encoder.initial_block.conv.weight", "encoder.block2.5.conv3x1_2.weight", "decoder.ladder_block_1.conv.weight",
+                  "decoder.ladder_block_2.layer.conv1x3_1.bias", "decoder.scalar_output_conv.weight", "decoder.scalar_decoder_2.layers.0.conv.bias"):
+            mod, attr = k.rsplit(".", 1)
+            res[f"{name}_g_{k}"] = getattr(m.get_submodule(mod), attr).grad.numpy()
     np.savez_compressed(path, **res)
 
 

@@ -208,6 +208,14 @@ def test_fork_losses_host_logic(golden_dir):
         check_fork_losses(golden_dir, "cpu")
 
 
+def test_ladder_net_host_logic(golden_dir):
+    """train/net_regression_ladder.Net: module wiring (three-scale encoder, ladder concat, conv+ReLU block, 1/2-channel heads),
+    autograd through it and the masked losses, kernels emulated."""
+    from tests.ladder_cases import check_ladder_net
+    with emulated_kernels():
+        check_ladder_net(golden_dir, "cpu", "fp32", out_tol=1e-4, grad_tol=2e-3)
+
+
 def test_no_cpu_fallback():
     """Without the emulation (and without a GPU) the product must fail loudly, never compute on the CPU."""
     if torch.cuda.is_available():

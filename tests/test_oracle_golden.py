@@ -210,3 +210,19 @@ def test_blocks_without_batchnorm(golden_dir):
             np.testing.assert_allclose(x.grad.numpy(), g[name + "_dx"], rtol=1e-3, atol=1e-5)
             np.testing.assert_allclose(sd["blk.conv.weight"].grad.numpy(), g[name + "_dw"], rtol=1e-3, atol=1e-4)
             np.testing.assert_allclose(sd["blk.conv.bias"].grad.numpy(), g[name + "_db"], rtol=1e-3, atol=1e-4)
+
+
+def test_ladder_net(golden_dir):
+    """Oracle restatement of train/net_regression_ladder.Net (softmax_classes = 0) vs the reference's outputs."""
+    g = np.load(os.path.join(golden_dir, "ladder_net.npz"))
+    lines = open(os.path.join(golden_dir, "ladder_net_keys.txt")).read().strip().split("\n")
+    assert len(lines) == 395
+    shapes = {l.split(" ", 1)[0]: eval(l.split(" ", 1)[1]) for l in lines}
+    x = golden_input((2, 3, 64, 128), 71)
+    sd = O.make_state_dict(shapes, seed=31)
+    with torch.no_grad():
+        np.testing.assert_allclose(O.regression_ladder_forward(x, sd).numpy(), g["reg_out"], rtol=1e-4, atol=1e-4)
+    shapes["decoder.scalar_output_conv.weight"], shapes["decoder.scalar_output_conv.bias"] = (16, 2, 2, 2), (2,)
+    sd2 = O.make_state_dict(shapes, seed=31)
+    with torch.no_grad():
+        np.testing.assert_allclose(O.regression_ladder_forward(x, sd2).numpy(), g["lik_out"], rtol=1e-4, atol=1e-4)
