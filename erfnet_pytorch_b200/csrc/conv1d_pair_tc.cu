@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
     }
   } else if (warp == 1) {
     // ================= MMA issuer: stage 1 of row i, then stage 2 of row i-1 =================
-    if (lane == 0) {
+    {   // whole warp: uniform control flow, one elected lane issues (see tc.cuh elect_one)
       int slot = 0;
       uint32_t phase = 0;
       const uint32_t w1_addr = smem_u32(s_w1), w2_addr = smem_u32(s_w2), t_addr = smem_u32(s_t);
@@ -144,13 +144,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
               const uint32_t b_lo = (((w1_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                if (elect_one()) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
                           (t | k) != 0 ? 1u : 0u);
-              umma_commit(&empty_bar[slot]);
+              if (elect_one()) umma_commit(&empty_bar[slot]);
               if (++slot == p.slots) { slot = 0; phase ^= 1; }
             }
           }
-          umma_commit(&d1_full[par]);
+          if (elect_one()) umma_commit(&d1_full[par]);
         }
         if (i >= 1) {
           const int j = i - 1, par = j & 1;
@@ -168,12 +168,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
               const uint32_t b_lo = (((w2_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                if (elect_one()) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
                           (t | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&t_empty[tbi]);
-          umma_commit(&d2_full[par]);
+          if (elect_one()) umma_commit(&t_empty[tbi]);
+          if (elect_one()) umma_commit(&d2_full[par]);
         }
       }
     }
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
         }
       }
     }
-    if (leader) tma_store_wait0();
+    if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
   }
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();

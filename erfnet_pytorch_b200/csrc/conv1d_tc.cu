@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues =================
+    {
       int slot = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       const uint32_t w_addr = smem_u32(s_w);
@@ -177,16 +177,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
             mbar_wait(&full_bar[slot], phase);
             tcgen05_fence_after();
             const uint32_t a_addr = smem_u32(s_a + (size_t)slot * p.slot_bytes);
+            if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              const uint32_t a_lo = (((a_addr + t * p.dil * RB) >> 4) & 0x3FFF) | (1u << 16);
-              const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+              for (int t = 0; t < 3; ++t) {
+                const uint32_t a_lo = (((a_addr + t * p.dil * RB) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
-                          (t | kc | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                            (t | kc | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[slot]);
             }
-            umma_commit(&empty_bar[slot]);
+            __syncwarp();
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
         } else {
@@ -199,23 +202,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
               const uint32_t a_addr = smem_u32(s_a + (size_t)slot * p.slot_bytes);
               const uint32_t a_lo = ((a_addr >> 4) & 0x3FFF) | (1u << 16);
               const uint32_t b_lo = (((w_addr + (t * KC + kc) * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
-                          (t | kc | k) != 0 ? 1u : 0u);
-              umma_commit(&empty_bar[slot]);   // this (tap, k-chunk) tile is reusable once its MMAs have read it
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                            (t | kc | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[slot]);   // this (tap, k-chunk) tile is reusable once its MMAs have read it
+              }
+              __syncwarp();
               if (++slot == p.slots) { slot = 0; phase ^= 1; }
             }
           }
         }
-        umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
+        if (elect_one()) umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp == 10) {
     // ================= statistics MMAs: Y^T Y and Y^T 1 of every staged sub-tile =================
-    if (RED && want_red && lane == 0) {
+    if (RED && want_red) {   // whole warp, one elected lane issues
       const uint32_t hi128 = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);           // MN-major, 8 pixel rows of RB bytes per atom
       const uint32_t hi32 = ((8u * 32u) >> 4) | (1u << 14) | (LAYOUT_SW32 << 29);      // the ones operand: 16 "channels" = 32-byte rows
       const uint32_t ones_addr = smem_u32(s_ones);
@@ -243,14 +250,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
           for (int k = 0; k < 8; ++k) {   // K = 128 pixels, 16 per MMA = 16 rows of RB bytes
             const uint64_t da = ((uint64_t)hi128 << 32) | (uint64_t)(a_lo + k * RB);
             if (p.stats)
-              umma_bf16(tmem_base + GRAM_COL + kc * GW, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * RB), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
-            umma_bf16(tmem_base + ONES_COL + kc * 16, da, d_ones, IDESC_ONES, (acc_en | k) ? 1u : 0u);
+              if (elect_one()) umma_bf16(tmem_base + GRAM_COL + kc * GW, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * RB), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
+            if (elect_one()) umma_bf16(tmem_base + ONES_COL + kc * 16, da, d_ones, IDESC_ONES, (acc_en | k) ? 1u : 0u);
           }
           started |= 1u << kc;
-          umma_commit(&sdone_bar[g * 2 + b]);
+          if (elect_one()) umma_commit(&sdone_bar[g * 2 + b]);
         }
       }
-      umma_commit(&sfinal_bar);
+      if (elect_one()) umma_commit(&sfinal_bar);
     }
   } else {
     // ================= epilogue: group 0 = warps 2..5, group 1 = warps 6..9; TMEM lane quadrant = warp % 4 =========
@@ -368,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
         }
       }
     }
-    if (leader) tma_store_wait0();
+    if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
     if constexpr (RED) {
       if (want_red && grp == 0 && quad * 32 < GW) {   // whole warps (tcgen05.ld is warp-collective); TMEM lanes 0..GW-1 = the channels of a k-chunk
         const bool mine = quad * 32 + lane < GW;         // one atomic per channel and CTA

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp: uniform control flow, one elected lane issues (see tc.cuh elect_one)
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t hi_base = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);  // SBO = 8 pixel rows, version 1, swizzle mode
@@ -120,14 +120,14 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
             // advancing K by 16 pixels = 16 rows of RB bytes
             const uint64_t da = ((uint64_t)hi_base << 32) | (uint64_t)(x_lo + k * RB);
             const uint64_t db = ((uint64_t)hi_base << 32) | (uint64_t)(dy_lo + k * RB);
-            umma_bf16(tmem_base + a * C, da, db, IDESC, (first && k == 0) ? 0u : 1u);
+            if (elect_one()) umma_bf16(tmem_base + a * C, da, db, IDESC, (first && k == 0) ? 0u : 1u);
           }
         }
         first = false;
-        umma_commit(&empty_bar[stage]);
+        if (elect_one()) umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&done_bar);
+      if (elect_one()) umma_commit(&done_bar);
     }
   } else {
     // epilogue (once): dump the accumulators of this CTA

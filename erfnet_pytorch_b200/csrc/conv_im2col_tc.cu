@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
     if (pend[0] >= 0) mbar_arrive(&full_bar[pend[0]]);
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    {   // whole warp: uniform control flow, one elected lane issues (see tc.cuh elect_one)
       int slot = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       const uint32_t w_addr = smem_u32(s_w);
@@ -167,14 +167,14 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
             const uint32_t a_lo = (((a_addr + kc * (128 * RB)) >> 4) & 0x3FFF) | (1u << 16);
             const uint32_t b_lo = (((w_addr + (t * KC + kc) * (NP * RB)) >> 4) & 0x3FFF) | (1u << 16);
             for (int k = 0; k < KSTEPS; ++k) {
-              umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC, first);
+              if (elect_one()) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC, first);
               first = 1;
             }
           }
-          umma_commit(&empty_bar[slot]);
+          if (elect_one()) umma_commit(&empty_bar[slot]);
           if (++slot == slots) { slot = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

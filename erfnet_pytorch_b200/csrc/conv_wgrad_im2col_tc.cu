@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
     if (pend >= 0) mbar_arrive(&full_bar[pend]);
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    {   // whole warp: uniform control flow, one elected lane issues (see tc.cuh elect_one)
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t lay_g = RBg == 128 ? LAYOUT_SW128 : LAYOUT_SW32, lay_d = RBd == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
@@ -153,14 +153,14 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
           const uint32_t ga = g_addr + gidx * atoms_per_m * g_sub_bytes;
           const uint32_t g_lo = ((ga >> 4) & 0x3FFF) | ((((uint32_t)g_sub_bytes >> 4) & 0x3FFF) << 16);     // LBO = (tap, sub) atom pitch
           for (int k = 0; k < kWiPX / 16; ++k)
-            umma_bf16(tmem_base + gidx * p.NP, ((uint64_t)hi_g << 32) | (uint64_t)(g_lo + k * RBg), ((uint64_t)hi_d << 32) | (uint64_t)(d_lo + k * RBd),
+            if (elect_one()) umma_bf16(tmem_base + gidx * p.NP, ((uint64_t)hi_g << 32) | (uint64_t)(g_lo + k * RBg), ((uint64_t)hi_d << 32) | (uint64_t)(d_lo + k * RBd),
                       idesc, (first && k == 0) ? 0u : 1u);
         }
         first = false;
-        umma_commit(&empty_bar[stage]);
+        if (elect_one()) umma_commit(&empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&done_bar);
+      if (elect_one()) umma_commit(&done_bar);
     }
   } else {
     // ================= epilogue (once): dump this CTA's accumulators =================

@@ -104,6 +104,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One lane of a CONVERGED warp.  Issue loops run warp-uniformly (every lane executes the loop, descriptors live in uniform
+// registers) and only the tcgen05.mma / commit instructions are predicated on this: inside an `if (lane == 0)` region the
+// compiler wraps every UTCHMMA in a lane-serialising loop with R2UR moves, ~80 cycles per MMA for the issuing thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

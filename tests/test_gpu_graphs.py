@@ -72,5 +72,8 @@ def test_train_stream_matches_sequential_steps():
     pinned = [(x.pin_memory(), y.pin_memory()) for x, y in batches]
     got = [float(l) for l in t2.train_stream(iter(pinned))]
     assert len(got) == len(seq)
-    np.testing.assert_allclose(got, seq, rtol=2e-3)
+    # identical kernels, but their atomics make every run slightly different and 39 train-mode BNs at 64 x 128 amplify that step by step
+    # (DESIGN.md section 2): the first step pins the input path tightly, the later ones loosely
+    np.testing.assert_allclose(got[0], seq[0], rtol=1e-5)
+    np.testing.assert_allclose(got, seq, rtol=1e-2)
     assert float((t1.flat_p - t2.flat_p).abs().mean()) < 1e-4   # Adam's sign-like first steps amplify rounding noise on ~zero gradients: mean, not max
