@@ -102,10 +102,13 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&w_bar, 2 * W_BYTES);
-      pair_bulk_g2s(s_w1, p.w1_img, W_BYTES, &w_bar);
-      pair_bulk_g2s(s_w2, p.w2_img, W_BYTES, &w_bar);
+    {   // whole warp in uniform control flow, one elected lane issues
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w_bar, 2 * W_BYTES);
+        pair_bulk_g2s(s_w1, p.w1_img, W_BYTES, &w_bar);
+        pair_bulk_g2s(s_w2, p.w2_img, W_BYTES, &w_bar);
+      }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
       for (int i = 0; i < cnt; ++i) {
@@ -114,8 +117,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
 #pragma unroll 1
           for (int t = 0; t < 3; ++t) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)TILE);
-            tma_load_4d(s_a + (size_t)slot * TILE_PAD, &tmap_in, &full_bar[slot], 0, 128 * m, y + (t - 1) * p.dil, n);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)TILE);
+              tma_load_4d(s_a + (size_t)slot * TILE_PAD, &tmap_in, &full_bar[slot], 0, 128 * m, y + (t - 1) * p.dil, n);
+            }
+            __syncwarp();
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
         }

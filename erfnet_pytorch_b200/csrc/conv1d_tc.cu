@@ -126,14 +126,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   const int segs = p.W / 128;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer: whole warp in uniform control flow, one elected lane issues =================
+    {
       // weights: one bulk copy per <= 32 KB piece, completing on w_bar
-      mbar_arrive_expect_tx(&w_bar, W_BYTES);
-      for (int off = 0; off < W_BYTES; off += 32768) {
-        const int n = W_BYTES - off < 32768 ? W_BYTES - off : 32768;
-        bulk_g2s(s_w + off, reinterpret_cast<const uint8_t*>(p.w_img) + off, n, &w_bar);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w_bar, W_BYTES);
+        for (int off = 0; off < W_BYTES; off += 32768) {
+          const int n = W_BYTES - off < 32768 ? W_BYTES - off : 32768;
+          bulk_g2s(s_w + off, reinterpret_cast<const uint8_t*>(p.w_img) + off, n, &w_bar);
+        }
       }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -142,8 +145,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)((128 + 2 * p.dil) * RB));
-            tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128 - p.dil, y, n);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)((128 + 2 * p.dil) * RB));
+              tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128 - p.dil, y, n);
+            }
+            __syncwarp();
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
         } else {
@@ -152,8 +158,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
 #pragma unroll 1
             for (int kc = 0; kc < KC; ++kc) {
               mbar_wait(&empty_bar[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(128 * RB));
-              tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128, y + (t - 1) * p.dil, n);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(128 * RB));
+                tma_load_4d(s_a + (size_t)slot * p.slot_bytes, &tmap_in, &full_bar[slot], kc * CH, xs * 128, y + (t - 1) * p.dil, n);
+              }
+              __syncwarp();
               if (++slot == p.slots) { slot = 0; phase ^= 1; }
             }
           }

@@ -70,15 +70,16 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (p.horizontal ? (uint32_t)(KC * (PX + 2 * p.dil) * RB) : (uint32_t)(3 * KC * PX * RB)) + (uint32_t)(KC * PX * RB);
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], tx);
         uint8_t* base = smem + (size_t)stage * p.stage_bytes;
+        if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], tx);
         if (p.horizontal) {
 #pragma unroll
           for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + kc * p.x_sub_bytes, &tmap_x, &full_bar[stage], kc * CH, xs * PX - p.dil, y, n);
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
         }
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) tma_load_4d(base + p.dy_off + kc * (PX * RB), &tmap_dy, &full_bar[stage], kc * CH, xs * PX, y, n);
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
