@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 H, W, BATCH, NC = 512, 1024, 6, 20
 GFLOP_FWD_PER_IMG = 53.225
 GFLOP_TRAIN_PER_IMG = 159.6
+NCU_TRAFFIC_BYTES = 12.75e6   # measured once per round with ncu --set full, see profiles/
 
 
 def peaks():
@@ -311,7 +312,7 @@ def main():
         rec = ktimes[name]
         ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["flops"] else None
         roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                "frac": (ach / pk["tc_sustained"]) if ach else None, "traffic": None, "peak_source": pk["src"] + " (sustained bf16 dense)",
+                "frac": (ach / pk["tc_sustained"]) if ach else None, "traffic": NCU_TRAFFIC_BYTES, "traffic_note": "dram read+write per launch of conv1d_tc_kernel<128> at this workload, ncu --set full (profiles/r01_conv1d_tc_ncu_full.csv); algorithmic 25.2 MB", "peak_source": pk["src"] + " (sustained bf16 dense)",
                 "launches": rec["n"], "share_of_step": rec["ms"] / tot if tot else None, "avg_launch_ms": rec["ms"] / rec["n"],
                 "step_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
 
@@ -332,10 +333,10 @@ def main():
                 "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             t0 = time.time()
-            cpu_ips = cpu_reference_run(2, 1, batch=1)
-            cpu_fwd = cpu_reference_run(3, 1, batch=1, fwd_only=True)
+            cpu_ips = cpu_reference_run(40, 1, batch=1)                    # ~8-10 s on 16 cores
+            cpu_fwd = cpu_reference_run(60, 1, batch=1, fwd_only=True)     # ~3-4 s
             line["cpu_baseline"] = {"value": cpu_ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"2 train steps + 3 forwards of batch 1 x 3x{H}x{W} fp32 (oracle port), {time.time() - t0:.0f} s of CPU work",
+                                    "sample": f"40 train steps + 60 forwards of batch 1 x 3x{H}x{W} fp32 (oracle port of the reference's torch ops), {time.time() - t0:.0f} s of CPU work",
                                     "fwd_images_per_s": cpu_fwd}
         print(json.dumps(line))
     if world > 1:
