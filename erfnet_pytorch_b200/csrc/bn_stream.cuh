@@ -114,6 +114,7 @@ constexpr int UNR = 2;   // pixels in flight per thread
 template <typename T, bool SQ, typename OUT>
 __global__ void __launch_bounds__(BS_THREADS, 2) channel_reduce_v2_kernel(const T* __restrict__ x, int ld, int C, long long n_px, int px_per_block,
                                                                           OUT* __restrict__ out) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_dyn[];
   const PxRange r = px_range(C, n_px, px_per_block);
   float acc[SQ ? 2 : 1][8];
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(BS_THREADS, 2) bn_bwd_reduce_v2_kernel(const T
                                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                          long long HW, int C, long long n_px, int px_per_block,
                                                                          double* __restrict__ sums) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_dyn[];
   float* s_coef = s_dyn;
   float* s_part = s_dyn + 2 * C;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(BS_THREADS, 2) bn_bwd_apply_v2_kernel(const T*
                                                                         long long HW, int C, long long n_px, int px_per_block, T* __restrict__ dy,
                                                                         int dy_ld, float* dgamma, float* dbeta, T* __restrict__ gmasked,
                                                                         int gmasked_ld) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_dyn[];   // [4C]: k1, k2, k3, mu
   // dy = gamma*is*(gb - s1/M - xhat*s2/M),  xhat = (y - mu)*is   ==>   dy = k1*gb + k2*(y - mu) + k3
   const float inv_m = 1.f / (float)n_px;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(BS_THREADS, 2) affine_act_v2_kernel(const T* _
                                                                       const float* __restrict__ shift, int per_sample, const T* __restrict__ res,
                                                                       int res_ld, T* __restrict__ out, int out_ld, long long HW, int C, long long n_px,
                                                                       int px_per_block, int relu) {
+  pdl_enter();
   const PxRange r = px_range(C, n_px, px_per_block);
   float sc[8], sh[8];
   long long cur_n = -1;
@@ -335,6 +339,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_v2_kernel(const T* __restrict__ in, int H, int W, int C, int in_ld, T* __restrict__ out, int out_ld,
                                                              int out_coff, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                                              unsigned total8) {
+  pdl_enter();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const unsigned c8 = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
@@ -363,6 +368,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_v2_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_v2_kernel(const T* __restrict__ in, int H, int W, int C, int in_ld, const T* __restrict__ dout,
                                                              int out_ld, int out_coff, T* __restrict__ dx, int dx_ld, unsigned total8) {
+  pdl_enter();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const unsigned c8 = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;

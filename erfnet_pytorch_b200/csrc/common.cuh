@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/erfnet_b200.h"
 
@@ -88,6 +89,37 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
+// A training step is ~600 kernels of 5-40 us: the 2-3 us between the end of one grid and the start of the next (grid launch latency,
+// plus barrier / TMEM / descriptor set-up for the tcgen05 kernels) is ~20 % of the step.  Every hot-path kernel is launched with the
+// programmatic-stream-serialization attribute and begins with pdl_trigger() (dependents may be scheduled) ... pdl_wait() (the
+// producer grid has completed and its memory is visible): whatever precedes pdl_wait() overlaps the previous kernel's tail.
+// RULE: a kernel launched through launch_pdl() must execute pdl_wait() in every thread before it reads or writes global memory that an
+// earlier kernel of the stream may have written or read.  ERF_PDL=0 in the environment falls back to ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+static inline bool pdl_enabled() {
+  static const bool on = !(getenv("ERF_PDL") && atoi(getenv("ERF_PDL")) == 0);
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

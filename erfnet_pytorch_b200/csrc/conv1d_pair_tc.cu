@@ -40,6 +40,7 @@ __device__ __forceinline__ void pair_bulk_g2s(void* smem_dst, const void* gsrc, 
 template <int C>
 __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                                         const __grid_constant__ CUtensorMap tmap_res, const PairParams p) {
+  pdl_trigger();
   constexpr int RB = C * 2;                      // bytes per pixel row (one k-chunk: C <= 64)
   constexpr int KSTEPS = C / 16;
   constexpr int CPR = RB / 16;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
   const int cnt = (int)blockIdx.x < p.rows ? (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // rows of this CTA
 
   if (warp == 0) {
@@ -382,10 +384,10 @@ extern "C" int erf_conv1d_pair_tc(const void* in, const void* w1_img, const floa
   cudaError_t e;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_pair_tc_kernel<16><<<grid, kPairThreads, smem, st>>>(tin, tout, tres, p);
+    if (e == cudaSuccess) launch_pdl(conv1d_pair_tc_kernel<16>, dim3(grid), dim3(kPairThreads), smem, (cudaStream_t)(st), tin, tout, tres, p);
   } else {
     e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_pair_tc_kernel<64><<<grid, kPairThreads, smem, st>>>(tin, tout, tres, p);
+    if (e == cudaSuccess) launch_pdl(conv1d_pair_tc_kernel<64>, dim3(grid), dim3(kPairThreads), smem, (cudaStream_t)(st), tin, tout, tres, p);
   }
   if (e != cudaSuccess) {
     set_error("erf_conv1d_pair_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

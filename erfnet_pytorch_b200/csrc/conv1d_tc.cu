@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   __shared__ float s_bias[C];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();   // the set-up below overlaps the previous kernel's tail; nothing before pdl_wait() touches tensors an earlier kernel writes
   for (int i = tid; i < C; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   const bool want_red = RED && (p.stats != nullptr || p.colsum != nullptr);
   if (want_red) {
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int segs = p.W / 128;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer: whole warp in uniform control flow, one elected lane issues =================
@@ -528,13 +530,13 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<16><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<16>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<64><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<64>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
   } else {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv1d_tc_kernel<128><<<grid, kThreads, smem, st>>>(tin, tout, taux, p);
+    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<128>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
   }
   if (e != cudaSuccess) {
     set_error("erf_conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

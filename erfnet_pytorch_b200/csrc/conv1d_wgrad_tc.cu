@@ -35,6 +35,7 @@ constexpr int PX = 64;  // pixels (K) per unit
 template <int C>
 __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                                                                  const WgradTcParams p) {
+  pdl_trigger();
   constexpr int CH = C < 64 ? C : 64;      // channels per chunk = one swizzle row of RB bytes
   constexpr int RB = CH * 2;
   constexpr int KC = C / CH;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int segs = p.W / PX;
+  pdl_wait();
   const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
 // slabs serially is latency-bound), four independent partial sums per thread keep loads in flight, one atomic per split.
 template <int C>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int grid_ctas, float* __restrict__ dw) {
+  pdl_enter();
   constexpr int ACCS = C == 128 ? 3 : (C == 64 ? 2 : 1);
   constexpr size_t SLAB = (size_t)ACCS * 128 * C;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // linear index into a slab [acc][col/4][row][4]: coalesced reads
@@ -272,20 +275,20 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      conv1d_wgrad_tc_kernel<16><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<16><<<dim3((1 * 128 * 16 + 255) / 256, 37), 256, 0, s>>>(p.ws, grid, dw);
+      launch_pdl(conv1d_wgrad_tc_kernel<16>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
+      launch_pdl(wgrad_reduce_kernel<16>, dim3(dim3((1 * 128 * 16 + 255) / 256, 37)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      conv1d_wgrad_tc_kernel<64><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<64><<<dim3((2 * 128 * 64 + 255) / 256, 12), 256, 0, s>>>(p.ws, grid, dw);
+      launch_pdl(conv1d_wgrad_tc_kernel<64>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
+      launch_pdl(wgrad_reduce_kernel<64>, dim3(dim3((2 * 128 * 64 + 255) / 256, 12)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      conv1d_wgrad_tc_kernel<128><<<grid, 192, smem, s>>>(mx, mdy, p);
-      wgrad_reduce_kernel<128><<<dim3((3 * 128 * 128 + 255) / 256, 6), 256, 0, s>>>(p.ws, grid, dw);
+      launch_pdl(conv1d_wgrad_tc_kernel<128>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
+      launch_pdl(wgrad_reduce_kernel<128>, dim3(dim3((3 * 128 * 128 + 255) / 256, 6)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   }
   if (e != cudaSuccess) {

@@ -450,9 +450,9 @@ extern "C" int erf_channel_sum(const void* x, int ld, int coff, int C, long long
   if (bs_reduce_ok(C) && (ld % 8) == 0 && (coff % 8) == 0 && ((uintptr_t)x % 16) == 0) {   // vectorised slice [coff, coff + C) of each pixel row
     const BsLaunch l = bs_launch(C, n_px, 2);
     if (dtype == ERF_F32)
-      channel_reduce_v2_kernel<float, false, float><<<l.grid, BS_THREADS, l.smem(C, 1), (cudaStream_t)stream>>>((const float*)x + coff, ld, C, n_px, l.px_per_block, out);
+      launch_pdl(channel_reduce_v2_kernel<float, false, float>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 1), (cudaStream_t)((cudaStream_t)stream), (const float*)x + coff, ld, C, n_px, l.px_per_block, out);
     else
-      channel_reduce_v2_kernel<__nv_bfloat16, false, float><<<l.grid, BS_THREADS, l.smem(C, 1), (cudaStream_t)stream>>>((const __nv_bfloat16*)x + coff, ld, C, n_px, l.px_per_block, out);
+      launch_pdl(channel_reduce_v2_kernel<__nv_bfloat16, false, float>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 1), (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)x + coff, ld, C, n_px, l.px_per_block, out);
     ERF_CHECK_LAUNCH("erf_channel_sum");
     return ERF_OK;
   }

@@ -40,6 +40,7 @@ __device__ __forceinline__ void bulk_g2s_im(void* smem_dst, const void* gsrc, ui
 template <int NP>
 __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf_im2col_desc p, const int slots, const int slot_bytes,
                                                                        const int w_bytes) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
 
   if (warp < 4) {
     // ================= loaders: 128 threads gather one tap tile per ring slot =================
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
 // for n < n_src, k < k_src (zero otherwise).
 __global__ void pack_im2col_weights_kernel(const float* __restrict__ w, long long stride_n, long long stride_k, int n0, int n_src, int k_src,
                                            erf_im2col_taps taps, int Cin, int NP, __nv_bfloat16* __restrict__ img) {
+  pdl_enter();
   const int CH = (Cin % 64) == 0 ? 64 : 16, CPR = CH / 8, KC = Cin / CH;
   const int total = taps.ntaps * KC * NP * CPR;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,7 +298,7 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   cudaError_t e = cudaSuccess;
 #define IM_LAUNCH(NP_)                                                                                                  \
   e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-  if (e == cudaSuccess) conv_im2col_tc_kernel<NP_><<<grid, kImThreads, smem, st>>>(p, slots, slot_bytes, w_bytes);
+  if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), p, slots, slot_bytes, w_bytes);
   if (d->NP == 16) { IM_LAUNCH(16) }
   else if (d->NP == 32) { IM_LAUNCH(32) }
   else if (d->NP == 64) { IM_LAUNCH(64) }
@@ -314,7 +317,7 @@ extern "C" int erf_pack_im2col_weights(const float* w, long long stride_n, long 
   ERF_CHECK_ARG(w && taps && img && taps->ntaps >= 1 && taps->ntaps <= 9 && (Cin % 16) == 0 && Cin <= 128, "erf_pack_im2col_weights: bad arguments");
   const int CH = (Cin % 64) == 0 ? 64 : 16;
   const int total = taps->ntaps * (Cin / CH) * NP * (CH / 8);
-  pack_im2col_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, stride_n, stride_k, n0, n_src, k_src, *taps, Cin, NP,
+  launch_pdl(pack_im2col_weights_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), w, stride_n, stride_k, n0, n_src, k_src, *taps, Cin, NP,
                                                                                    (__nv_bfloat16*)img);
   ERF_CHECK_LAUNCH("erf_pack_im2col_weights");
   return ERF_OK;

@@ -34,6 +34,7 @@ __device__ __forceinline__ void wi_cp_async(void* smem_dst, const void* gsrc, in
 // smem stage layout: [gathered: ntaps*gsubs sub-tiles of 64 px x CHg][dense: dsubs sub-tiles of 64 px x CHd]
 __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(const erf_wgrad_im2col_desc p, const int stages, const int stage_bytes,
                                                                              const int dense_off, const int groups, float* __restrict__ ws) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[kWiMaxStages], empty_bar[kWiMaxStages], done_bar;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
 
   if (warp < 4) {
     // ================= loaders =================
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
 
 // dw[((n0 + col) * Cg + cg) * KHW + tap_off[tap]] += sum over CTAs; (group, row) -> atom = group*(128/CHg) + row/CHg -> (tap, sub)
 __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int ctas, int groups, erf_wgrad_im2col_desc p, float* __restrict__ dw) {
+  pdl_enter();
   const int CHg = (p.CgP % 64) == 0 ? 64 : 16, gsubs = p.CgP / CHg;
   const int per_cta = groups * 128 * p.NP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,11 +276,11 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
     set_error("erf_conv_wgrad_im2col_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return ERF_ERR_CUDA;
   }
-  conv_wgrad_im2col_tc_kernel<<<grid, kWiThreads, smem, st>>>(p, stages, stage_bytes, g_bytes, groups, (float*)workspace);
+  launch_pdl(conv_wgrad_im2col_tc_kernel, dim3(grid), dim3(kWiThreads), smem, (cudaStream_t)(st), p, stages, stage_bytes, g_bytes, groups, (float*)workspace);
   const int per_cta = groups * 128 * d->NP;
   const int rblocks = (per_cta + 255) / 256;
   const int rsplit = rblocks >= 148 ? 4 : (rblocks >= 32 ? 12 : 37);
-  wgrad_im2col_reduce_kernel<<<dim3(rblocks, rsplit), 256, 0, st>>>((const float*)workspace, grid, groups, p, dw);
+  launch_pdl(wgrad_im2col_reduce_kernel, dim3(dim3(rblocks, rsplit)), dim3(256), 0, (cudaStream_t)(st), (const float*)workspace, grid, groups, p, dw);
   ERF_CHECK_LAUNCH("erf_conv_wgrad_im2col_tc");
   return ERF_OK;
 }

@@ -9,6 +9,7 @@ namespace erfk {
 // ------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, long long HW, long long total_px, T* __restrict__ out, int ld) {
+  pdl_enter();
   // one thread per pixel: reads are coalesced per channel plane, the (small) pixel vector is written contiguously
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_px) return;
@@ -20,6 +21,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, long lo
 
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int ld, int C, long long HW, long long total_px, float* __restrict__ out) {
+  pdl_enter();
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total_px) return;
   long long n = p / HW, hw = p % HW;
@@ -173,6 +175,7 @@ __global__ void relu_bwd_kernel(const T* __restrict__ g, int g_ld, const T* __re
 // ------------------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(double* stats, double count, const float* gamma, const float* beta, float* rm, float* rv, float momentum,
                                    float eps, const float* drop, int N, int C, float* mean, float* invstd, float* scale, float* shift) {
+  pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = stats[c], sq = stats[C + c];
@@ -320,6 +323,7 @@ __global__ void pack_conv1d_tc_kernel(const float* __restrict__ w, int C, __nv_b
 
 // every 3-tap conv of the net in ONE launch (blockIdx.y = table entry): the per-step weight re-pack of a training step
 __global__ void pack_conv1d_tc_batched_kernel(const erf_pack1d_entry* __restrict__ table) {
+  pdl_enter();
   const erf_pack1d_entry e = table[blockIdx.y];
   pack_conv1d_tc_body(e.w, e.C, (__nv_bfloat16*)e.img_fwd, (__nv_bfloat16*)e.img_dgrad, blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -328,6 +332,7 @@ __global__ void pack_conv1d_tc_batched_kernel(const erf_pack1d_entry* __restrict
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                             float lr_over_bc1, float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale,
                             const int* __restrict__ step_dev, float lr) {
+  pdl_enter();
   if (step_dev) {  // CUDA-graph friendly: the step count lives on the device (incremented by adam_step_inc_kernel)
     const double st = (double)*step_dev;
     lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, st)));
@@ -344,7 +349,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pv - lr_over_bc1 * mv / (sqrtf(vv) * inv_sqrt_bc2 + eps);
 }
 
-__global__ void adam_step_inc_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void adam_step_inc_kernel(int* step_dev) {
+  pdl_enter(); *step_dev += 1; }
 
 }  // namespace erfk
 
@@ -361,8 +367,8 @@ extern "C" int erf_nchw_f32_to_nhwc(const float* in, int N, int C, int H, int W,
   ERF_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && out_ld >= C, "erf_nchw_f32_to_nhwc: bad arguments");
   long long HW = (long long)H * W, total = HW * N;
   unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == ERF_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, HW, total, (float*)out, out_ld);
-  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, HW, total, (__nv_bfloat16*)out, out_ld);
+  if (dtype == ERF_F32) launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), in, C, HW, total, (float*)out, out_ld);
+  else launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), in, C, HW, total, (__nv_bfloat16*)out, out_ld);
   ERF_CHECK_LAUNCH("erf_nchw_f32_to_nhwc");
   return ERF_OK;
 }
@@ -372,8 +378,8 @@ extern "C" int erf_nhwc_to_nchw_f32(const void* in, int in_ld, int N, int C, int
   ERF_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && in_ld >= C, "erf_nhwc_to_nchw_f32: bad arguments");
   long long HW = (long long)H * W, total = HW * N;
   unsigned grid = (unsigned)((total + 255) / 256);
-  if (dtype == ERF_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)in, in_ld, C, HW, total, out);
-  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, in_ld, C, HW, total, out);
+  if (dtype == ERF_F32) launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const float*)in, in_ld, C, HW, total, out);
+  else launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)in, in_ld, C, HW, total, out);
   ERF_CHECK_LAUNCH("erf_nhwc_to_nchw_f32");
   return ERF_OK;
 }
@@ -392,9 +398,9 @@ extern "C" int erf_maxpool2x2_fwd(const void* in, int N, int H, int W, int C, in
         ((uintptr_t)out % 16) == 0) {
       const unsigned g8 = (unsigned)((total8 + 255) / 256);
       if (dtype == ERF_F32)
-        maxpool_fwd_v2_kernel<float><<<g8, 256, 0, (cudaStream_t)stream>>>((const float*)in, H, W, C, in_ld, (float*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
+        launch_pdl(maxpool_fwd_v2_kernel<float>, dim3(g8), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const float*)in, H, W, C, in_ld, (float*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
       else
-        maxpool_fwd_v2_kernel<__nv_bfloat16><<<g8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, H, W, C, in_ld, (__nv_bfloat16*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
+        launch_pdl(maxpool_fwd_v2_kernel<__nv_bfloat16>, dim3(g8), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)in, H, W, C, in_ld, (__nv_bfloat16*)out, out_ld, out_coff, scale, shift, relu, (unsigned)total8);
       ERF_CHECK_LAUNCH("erf_maxpool2x2_fwd");
       return ERF_OK;
     }
@@ -417,9 +423,9 @@ extern "C" int erf_maxpool2x2_bwd(const void* in, int N, int H, int W, int C, in
         ((uintptr_t)in % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dx % 16) == 0) {
       const unsigned g8 = (unsigned)((total8 + 255) / 256);
       if (dtype == ERF_F32)
-        maxpool_bwd_v2_kernel<float><<<g8, 256, 0, (cudaStream_t)stream>>>((const float*)in, H, W, C, in_ld, (const float*)dout, out_ld, out_coff, (float*)dx, dx_ld, (unsigned)total8);
+        launch_pdl(maxpool_bwd_v2_kernel<float>, dim3(g8), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const float*)in, H, W, C, in_ld, (const float*)dout, out_ld, out_coff, (float*)dx, dx_ld, (unsigned)total8);
       else
-        maxpool_bwd_v2_kernel<__nv_bfloat16><<<g8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, H, W, C, in_ld, (const __nv_bfloat16*)dout, out_ld, out_coff, (__nv_bfloat16*)dx, dx_ld, (unsigned)total8);
+        launch_pdl(maxpool_bwd_v2_kernel<__nv_bfloat16>, dim3(g8), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)in, H, W, C, in_ld, (const __nv_bfloat16*)dout, out_ld, out_coff, (__nv_bfloat16*)dx, dx_ld, (unsigned)total8);
       ERF_CHECK_LAUNCH("erf_maxpool2x2_bwd");
       return ERF_OK;
     }
@@ -445,9 +451,9 @@ extern "C" int erf_affine_act(const void* x, int x_ld, const float* scale, const
     const long long n_px = (long long)N * HW;
     const BsLaunch l = bs_launch(C, n_px, 4);
     if (dtype == ERF_F32)
-      affine_act_v2_kernel<float><<<l.grid, BS_THREADS, 0, (cudaStream_t)stream>>>((const float*)x, x_ld, scale, shift, sc_per_sample, (const float*)res, res_ld, (float*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
+      launch_pdl(affine_act_v2_kernel<float>, dim3(l.grid), dim3(BS_THREADS), 0, (cudaStream_t)((cudaStream_t)stream), (const float*)x, x_ld, scale, shift, sc_per_sample, (const float*)res, res_ld, (float*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
     else
-      affine_act_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, x_ld, scale, shift, sc_per_sample, (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
+      launch_pdl(affine_act_v2_kernel<__nv_bfloat16>, dim3(l.grid), dim3(BS_THREADS), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)x, x_ld, scale, shift, sc_per_sample, (const __nv_bfloat16*)res, res_ld, (__nv_bfloat16*)out, out_ld, HW, C, n_px, l.px_per_block, relu);
     ERF_CHECK_LAUNCH("erf_affine_act");
     return ERF_OK;
   }
@@ -467,9 +473,9 @@ extern "C" int erf_channel_stats(const void* x, int ld, int C, long long n_px, d
   if (bs_fast_ok(C) && ((uintptr_t)x % 16) == 0) {
     const BsLaunch l = bs_launch(C, n_px, 2);
     if (dtype == ERF_F32)
-      channel_reduce_v2_kernel<float, true, double><<<l.grid, BS_THREADS, l.smem(C, 2), (cudaStream_t)stream>>>((const float*)x, ld, C, n_px, l.px_per_block, stats);
+      launch_pdl(channel_reduce_v2_kernel<float, true, double>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 2), (cudaStream_t)((cudaStream_t)stream), (const float*)x, ld, C, n_px, l.px_per_block, stats);
     else
-      channel_reduce_v2_kernel<__nv_bfloat16, true, double><<<l.grid, BS_THREADS, l.smem(C, 2), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, C, n_px, l.px_per_block, stats);
+      launch_pdl(channel_reduce_v2_kernel<__nv_bfloat16, true, double>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 2), (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)x, ld, C, n_px, l.px_per_block, stats);
     ERF_CHECK_LAUNCH("erf_channel_stats");
     return ERF_OK;
   }
@@ -506,7 +512,7 @@ extern "C" int erf_bn_finalize(double* stats, double count, const float* gamma, 
                                erf_stream_t stream) {
   ERF_CHECK_ARG(stats && gamma && beta && mean && invstd && scale && shift && C > 0 && count > 0, "erf_bn_finalize: bad arguments");
   ERF_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "erf_bn_finalize: running_mean/var must be given together");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, running_mean, running_var, momentum, eps, drop, N, C, mean,
+  launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), stats, count, gamma, beta, running_mean, running_var, momentum, eps, drop, N, C, mean,
                                                                         invstd, scale, shift);
   ERF_CHECK_LAUNCH("erf_bn_finalize");
   return ERF_OK;
@@ -530,9 +536,9 @@ extern "C" int erf_bn_bwd_reduce(const void* g, int g_ld, const void* y, int y_l
   if (bs_fast_ok(C) && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)mask % 16) == 0) {
     const BsLaunch l = bs_launch(C, n_px, 2);
     if (dtype == ERF_F32)
-      bn_bwd_reduce_v2_kernel<float><<<l.grid, BS_THREADS, l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
+      launch_pdl(bn_bwd_reduce_v2_kernel<float>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)((cudaStream_t)stream), (const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
     else
-      bn_bwd_reduce_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
+      launch_pdl(bn_bwd_reduce_v2_kernel<__nv_bfloat16>, dim3(l.grid), dim3(BS_THREADS), l.smem(C, 2) + 2 * C * sizeof(float), (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, mean, invstd, HW, C, n_px, l.px_per_block, sums);
     ERF_CHECK_LAUNCH("erf_bn_bwd_reduce");
     return ERF_OK;
   }
@@ -563,9 +569,9 @@ extern "C" int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld
       ((uintptr_t)gmasked % 16) == 0) {
     const BsLaunch l = bs_launch(C, n_px, 4);
     if (dtype == ERF_F32)
-      bn_bwd_apply_v2_kernel<float><<<l.grid, BS_THREADS, 4 * C * sizeof(float), (cudaStream_t)stream>>>((const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (float*)dy, dy_ld, dgamma, dbeta, (float*)gmasked, gmasked_ld);
+      launch_pdl(bn_bwd_apply_v2_kernel<float>, dim3(l.grid), dim3(BS_THREADS), 4 * C * sizeof(float), (cudaStream_t)((cudaStream_t)stream), (const float*)g, g_ld, (const float*)y, y_ld, (const float*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (float*)dy, dy_ld, dgamma, dbeta, (float*)gmasked, gmasked_ld);
     else
-      bn_bwd_apply_v2_kernel<__nv_bfloat16><<<l.grid, BS_THREADS, 4 * C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta, (__nv_bfloat16*)gmasked, gmasked_ld);
+      launch_pdl(bn_bwd_apply_v2_kernel<__nv_bfloat16>, dim3(l.grid), dim3(BS_THREADS), 4 * C * sizeof(float), (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)y, y_ld, (const __nv_bfloat16*)mask, mask_ld, drop, gamma, mean, invstd, sums, HW, C, n_px, l.px_per_block, (__nv_bfloat16*)dy, dy_ld, dgamma, dbeta, (__nv_bfloat16*)gmasked, gmasked_ld);
     ERF_CHECK_LAUNCH("erf_bn_bwd_apply");
     return ERF_OK;
   }
@@ -585,7 +591,7 @@ extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long 
   ERF_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "erf_adam_step: bad arguments");
   double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   unsigned grid = (unsigned)((n + 255) / 256);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale,
+  launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale,
                                                       nullptr, lr);
   ERF_CHECK_LAUNCH("erf_adam_step");
   return ERF_OK;
@@ -595,8 +601,8 @@ extern "C" int erf_adam_step_dev(float* p, const float* g, float* m, float* v, l
                                  float weight_decay, int* step_dev, float grad_scale, erf_stream_t stream) {
   ERF_CHECK_ARG(p && g && m && v && n > 0 && step_dev, "erf_adam_step_dev: bad arguments");
   unsigned grid = (unsigned)((n + 255) / 256);
-  adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr);
+  launch_pdl(adam_step_inc_kernel, dim3(1), dim3(1), 0, (cudaStream_t)((cudaStream_t)stream), step_dev);
+  launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr);
   ERF_CHECK_LAUNCH("erf_adam_step_dev");
   return ERF_OK;
 }
@@ -605,7 +611,7 @@ extern "C" int erf_pack_conv1d_tc_batched(const erf_pack1d_entry* table_dev, int
   ERF_CHECK_ARG(table_dev && n_entries > 0 && n_entries <= 65535 && (max_C == 16 || max_C == 64 || max_C == 128),
                 "erf_pack_conv1d_tc_batched: bad arguments (n=%d, max_C=%d)", n_entries, max_C);
   int total = 2 * 3 * max_C * (max_C / 8);
-  pack_conv1d_tc_batched_kernel<<<dim3((total + 255) / 256, n_entries), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  launch_pdl(pack_conv1d_tc_batched_kernel, dim3(dim3((total + 255) / 256, n_entries)), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), table_dev);
   ERF_CHECK_LAUNCH("erf_pack_conv1d_tc_batched");
   return ERF_OK;
 }

@@ -7,6 +7,7 @@ namespace erfk {
 
 __global__ void ce_weight_sum_kernel(const int64_t* __restrict__ target, long long n_px, const float* __restrict__ weight, int C, int ignore,
                                      float* __restrict__ wsum) {
+  pdl_enter();
   float a = 0.f;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += (long long)gridDim.x * blockDim.x) {
     long long t = target[p];
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(128) ce_fwd_bwd_nhwc_bf16_kernel(const __nv_bf
                                                                    long long n_px, const float* __restrict__ weight, int C, int ignore,
                                                                    const float* __restrict__ wsum, float* __restrict__ loss_sum,
                                                                    __nv_bfloat16* __restrict__ dlogits) {
+  pdl_enter();
   float lsum = 0.f;
   const float inv_w = 1.f / *wsum;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += (long long)gridDim.x * blockDim.x) {
@@ -201,7 +203,7 @@ extern "C" int erf_ce_weight_sum(const int64_t* target, long long n_px, const fl
   ERF_CHECK_ARG(target && wsum && n_px > 0 && C > 0, "erf_ce_weight_sum: bad arguments");
   long long blocks = (n_px + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  ce_weight_sum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(target, n_px, weight, C, ignore_index, wsum);
+  launch_pdl(ce_weight_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), target, n_px, weight, C, ignore_index, wsum);
   ERF_CHECK_LAUNCH("erf_ce_weight_sum");
   return ERF_OK;
 }
@@ -217,9 +219,9 @@ extern "C" int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int
   if (dtype == ERF_BF16 && nchw_hw == 0 && (ld == 24 || ld == 32) &&
       ((uintptr_t)logits % 16) == 0 && (!dlogits || ((uintptr_t)dlogits % 16) == 0)) {
     if (ld == 24)
-      ce_fwd_bwd_nhwc_bf16_kernel<3><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<3>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
     else
-      ce_fwd_bwd_nhwc_bf16_kernel<4><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<4>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
     ERF_CHECK_LAUNCH("erf_ce_fwd_bwd");
     return ERF_OK;
   }

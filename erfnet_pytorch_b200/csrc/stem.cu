@@ -31,6 +31,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu, T* __restrict__ y, double* __restrict__ stats) {
+  pdl_enter();
   __shared__ __align__(16) float s_w[9 * STEM_CI * STEM_C];   // [tap][ci][co padded to 16]
   __shared__ float s_b[STEM_C], s_sc[STEM_C], s_sh[STEM_C];
   __shared__ float s_red[8][2 * STEM_C];
@@ -126,6 +127,7 @@ constexpr int SW_LANES = 7, SW_GROUP = 36;   // 36 threads = 9 taps x 4 output-c
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int N, int H, int W,
                                                          float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t s_raw[];
   const int Ho = H / 2, Wo = W / 2;
   T* s_x = reinterpret_cast<T*>(s_raw);                               // [3 rows][W][4]
@@ -210,9 +212,9 @@ extern "C" int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, 
   if (blocks > 148 * 6) blocks = 148 * 6;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == ERF_F32)
-    stem_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, N, H, W, w, bias, scale, shift, relu, (float*)y, stats);
+    launch_pdl(stem_fwd_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)(s), (const float*)x, N, H, W, w, bias, scale, shift, relu, (float*)y, stats);
   else
-    stem_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, N, H, W, w, bias, scale, shift, relu, (__nv_bfloat16*)y, stats);
+    launch_pdl(stem_fwd_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)(s), (const __nv_bfloat16*)x, N, H, W, w, bias, scale, shift, relu, (__nv_bfloat16*)y, stats);
   ERF_CHECK_LAUNCH("erf_stem_fwd");
   return ERF_OK;
 }
@@ -230,10 +232,10 @@ extern "C" int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W
   cudaError_t e;
   if (dtype == ERF_F32) {
     e = cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) stem_wgrad_kernel<float><<<grid, 256, smem, s>>>((const float*)x, (const float*)dy, N, H, W, dw, db);
+    if (e == cudaSuccess) launch_pdl(stem_wgrad_kernel<float>, dim3(grid), dim3(256), smem, (cudaStream_t)(s), (const float*)x, (const float*)dy, N, H, W, dw, db);
   } else {
     e = cudaFuncSetAttribute(stem_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) stem_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
+    if (e == cudaSuccess) launch_pdl(stem_wgrad_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, (cudaStream_t)(s), (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
   }
   if (e != cudaSuccess) {
     set_error("erf_stem_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
