@@ -709,16 +709,42 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
 _BN_SUMS = {}  # (device, C) -> fp64 [2C] scratch for the BN-backward reductions
 
 
+class ScratchArena:
+    """Pre-zeroed fp64 scratch for one training step: reset() is ONE memset, take(n) hands out consecutive zeroed slices.  Used by
+    FlatAdamTrainer so that the 39 BN-backward reductions of a step do not each launch their own fill kernel (which is also a full
+    serialisation point between programmatically dependent kernels)."""
+
+    def __init__(self, device, n=32768):
+        self.buf = torch.zeros(n, device=device, dtype=torch.float64)
+        self.cursor = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.cursor = 0
+
+    def take(self, n):
+        if self.cursor + n > self.buf.numel():
+            return None
+        out = self.buf[self.cursor:self.cursor + n]
+        self.cursor += n
+        return out
+
+
+ARENA = None   # set by the trainer for the duration of a step
+
+
 def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False):
     """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c].
     dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step).
     want_masked: also return g*(mask>0) as a 4th value (written by the apply pass, saves a separate relu_bwd)."""
     n, h, w, c = y.shape
-    sums = _BN_SUMS.get((y.device, c))
+    sums = ARENA.take(2 * c) if (ARENA is not None and ARENA.buf.device == y.device) else None
     if sums is None:
-        sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
-    else:
-        sums.zero_()
+        sums = _BN_SUMS.get((y.device, c))
+        if sums is None:
+            sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
+        else:
+            sums.zero_()
     L = _lib.lib()
     check(L.erf_bn_bwd_reduce(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(mean), _p(invstd),
                               n, h * w, c, _p(sums), dt(y), _stream(y)))

@@ -177,10 +177,16 @@ class FlatAdamTrainer:
 
     def _backward(self, logits, dlog):
         _erfnet._GRAD_SINK = self
+        if self.cuda and not ops.EMULATED:
+            if getattr(self, "_arena", None) is None:
+                self._arena = ops.ScratchArena(self.flat_p.device)
+            self._arena.reset()          # one memset for all BN-backward reductions of the step
+            ops.ARENA = self._arena
         try:
             logits.backward(dlog)
         finally:
             _erfnet._GRAD_SINK = None
+            ops.ARENA = None
 
     def optimizer_step(self):
         self.step_count += 1
