@@ -203,11 +203,13 @@ class FlatAdamTrainer:
             self._g_images.copy_(images, non_blocking=True)
             self._g_labels.copy_(labels, non_blocking=True)
             if isinstance(self._graph, tuple):
-                # N > 1: three graph segments with the (tiny) NCCL collectives launched eagerly between them
-                g1, g2, g3 = self._graph
-                g1.replay()                                                    # zero grads, forward, valid-pixel weight sum
+                # N > 1: two graph segments with the NCCL collectives launched eagerly around them.  The global valid-pixel weight sum
+                # depends on the labels only, so it is reduced BEFORE the step and forward + loss + backward stay one graph.
+                g12, g3 = self._graph
+                self._g_acc.zero_()
+                ops.ce_weight_sum(self._g_labels, self.criterion.weight, self.num_classes, self.criterion.ignore_index, self._g_acc[0:1])
                 dist.all_reduce(self._g_acc[0:1], op=dist.ReduceOp.SUM, group=self.pg)
-                g2.replay()                                                    # CE fwd+bwd, backward
+                g12.replay()                                                   # zero grads, forward, CE fwd+bwd, backward
                 dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
                 dist.all_reduce(self._g_acc[1:2], op=dist.ReduceOp.SUM, group=self.pg)
                 g3.replay()                                                    # Adam, loss = lsum / wsum
@@ -290,22 +292,26 @@ class FlatAdamTrainer:
             self._hooks_enabled = False
             c, w = self.num_classes, self.criterion.weight
             self._g_acc = torch.zeros(2, device=dev, dtype=torch.float32)
-            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
+            g12, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            ops.ce_weight_sum(self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1])   # any non-zero denominator for the capture
+            with torch.cuda.graph(g12):
                 self.flat_g.zero_()
                 self.flat_nbt.add_(1)
-                self._g_acc.zero_()
                 self.model.train()
-                logits = self.model.forward_nhwc(self._g_images)
-                ops.ce_weight_sum(self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1])
-            with torch.cuda.graph(g2, pool=g1.pool()):
+                if self._pack_table is not None:
+                    self._pack_table.run()
+                    _erfnet._PREPACKED_FRESH = True
+                try:
+                    logits = self.model.forward_nhwc(self._g_images)
+                finally:
+                    _erfnet._PREPACKED_FRESH = False
                 dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
                 self._backward(logits, dlog)
-            with torch.cuda.graph(g3, pool=g1.pool()):
+            with torch.cuda.graph(g3, pool=g12.pool()):
                 self.optimizer_step()
                 loss = (self._g_acc[1:2] / self._g_acc[0:1]).reshape(())
             self._hooks_enabled = True
-            graph = (g1, g2, g3)
+            graph = (g12, g3)
         else:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
