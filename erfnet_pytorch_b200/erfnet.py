@@ -42,6 +42,7 @@ class _Ctx:
         self.dtype = _act_dtype(precision)
         self.training = training
         self.drop_scales = drop_scales  # optional {id(module) or name: [N,C] fp32} (tests inject fixed masks)
+        self.drawn = None               # {module: [N,C] fp32} Dropout2d multipliers drawn up front by draw_dropout()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -159,6 +160,25 @@ def fixed_dropout(scales):
         yield
     finally:
         _FIXED_DROPOUT = prev
+
+
+def draw_dropout(model, n, device):
+    """All Dropout2d multipliers of one training forward in ONE bernoulli call per distinct p (instead of four small kernels per block,
+    each a serialisation point between programmatically dependent kernels): {block: [N, C] fp32 in {0, 1/(1-p)}}.  Same distribution as
+    nn.Dropout2d (one draw per (sample, channel)); the order in which the generator is consumed differs from the reference's."""
+    groups = {}
+    for m in model.modules():
+        if isinstance(m, non_bottleneck_1d) and m.use_dropout and m.dropout.p != 0:
+            groups.setdefault(float(m.dropout.p), []).append(m)
+    drawn = {}
+    for p, mods in groups.items():
+        total = sum(n * m.chann for m in mods)
+        flat = F.dropout(torch.ones(total, device=device), p, True)
+        off = 0
+        for m in mods:
+            drawn[m] = flat[off:off + n * m.chann].view(n, m.chann)
+            off += n * m.chann
+    return drawn
 
 
 _WEIGHTS_EPOCH = 0  # bumped by code that updates parameters through aliases torch's version counters cannot see
@@ -434,6 +454,8 @@ class non_bottleneck_1d(_B200Module):
         fixed = ctx.drop_scales if ctx.drop_scales is not None else _FIXED_DROPOUT
         if fixed is not None and self in fixed:
             return fixed[self].to(x.device, torch.float32).reshape(x.shape[0], self.chann).contiguous()
+        if ctx.drawn is not None and self in ctx.drawn:      # drawn for the whole net in one call (draw_dropout)
+            return ctx.drawn[self]
         ones = torch.ones(x.shape[0], self.chann, 1, 1, device=x.device)
         return F.dropout2d(ones, p, True).reshape(x.shape[0], self.chann).contiguous()
 
@@ -778,6 +800,8 @@ class ERFNet(_B200Module):
         """NCHW fp32 in, internal NHWC logits out ([N,H,W,round8(C)], activation dtype) -- what the fused loss /
         argmax / histogram kernels consume without the NCHW fp32 round trip."""
         ctx = _Ctx(self._precision(), self.training, drop_scales)
+        if self.training and drop_scales is None and _FIXED_DROPOUT is None and input.is_cuda and not ops.EMULATED:
+            ctx.drawn = draw_dropout(self, input.shape[0], input.device)
         x = _ToNHWC.apply(input, 4, ctx.dtype)
         if only_encode:
             return self.encoder._nhwc(x, ctx, predict=True)

@@ -29,3 +29,22 @@ def test_argument_errors_do_not_need_a_gpu():
     e = _lib.ConvEpilogue()
     rc = L.erf_conv_fwd(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.byref(g), ctypes.byref(e), 1, None)
     assert rc == -1 and b"multiples of 4" in L.erf_last_error_string()
+
+
+def test_every_pdl_launched_kernel_waits_for_its_producer():
+    """Static audit of the programmatic-dependent-launch rule (csrc/common.cuh): a kernel launched through launch_pdl() may start
+    before the previous kernel of the stream has finished, so its body must execute pdl_wait() (directly or via pdl_enter())."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "erfnet_pytorch_b200", "csrc")
+    src = "".join(open(f).read() for f in sorted(glob.glob(os.path.join(root, "*.cu*"))))
+    names = sorted(set(re.findall(r"launch_pdl\(([A-Za-z_][A-Za-z_0-9]*)", src)) - {"void"})
+    assert len(names) >= 20
+    for n in names:
+        m = re.search(r"__global__[^;{]*?\b" + n + r"\s*\(", src, re.S)
+        assert m, f"definition of {n} not found"
+        i = src.index("{", m.end())
+        j = src.find("__global__", i)
+        body = src[i:j if j > 0 else len(src)]
+        assert "pdl_enter();" in body[:400] or "pdl_wait();" in body, f"{n} is launched with PDL but never waits for its producer grid"
