@@ -65,6 +65,8 @@ _SIGNATURES = {
     "erf_argmax": [_vp, _i, _i, _ll, _i, _vp, _i, _i, _vp],
     "erf_masked_loss_fwd": [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _f, _vp, _vp],
     "erf_masked_loss_bwd": [_i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "erf_softmax_nhwc_fwd": [_vp, _i, _vp, _i, _ll, _i, _vp, _i, _vp],
+    "erf_softmax_nhwc_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp, _i, _i, _vp],
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "erf_adam_step_dev": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],

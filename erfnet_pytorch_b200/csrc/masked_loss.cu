@@ -219,3 +219,74 @@ extern "C" int erf_masked_loss_bwd(int kind, const float* a, const float* b, con
   ERF_CHECK_LAUNCH("erf_masked_loss_bwd");
   return ERF_OK;
 }
+
+// ---- SoftMaxConv tail (train/erfnet_blocks.py:92-110): Dropout2d multiplier + softmax over the channels -----------------------------
+// forward: prob[n][c][p] (NCHW fp32) = softmax_c(logits[n][p][c] * drop[n][c]) from NHWC logits with row pitch ld;
+// backward: dlogits[n][p][c] = drop[n][c] * prob_c * (dprob_c - sum_k dprob_k prob_k), pad channels (c >= C) zeroed.
+namespace erfk {
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_nhwc_fwd_kernel(const T* __restrict__ logits, int ld, const float* __restrict__ drop, long long hw,
+                                                               long long n_px, int C, float* __restrict__ prob) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_px) return;
+  const long long n = p / hw, q = p - n * hw;
+  float v[ML_MAXC];
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    v[c] = to_f(logits[(size_t)p * ld + c]) * (drop ? drop[n * C + c] : 1.f);
+    mx = fmaxf(mx, v[c]);
+  }
+  float se = 0.f;
+  for (int c = 0; c < C; ++c) { v[c] = __expf(v[c] - mx); se += v[c]; }
+  const float inv = 1.f / se;
+  for (int c = 0; c < C; ++c) prob[((size_t)n * C + c) * hw + q] = v[c] * inv;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_nhwc_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob,
+                                                               const float* __restrict__ drop, long long hw, long long n_px, int C,
+                                                               T* __restrict__ dlogits, int ld) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_px) return;
+  const long long n = p / hw, q = p - n * hw;
+  float pr[ML_MAXC], dp[ML_MAXC];
+  float dot = 0.f;
+  for (int c = 0; c < C; ++c) {
+    pr[c] = prob[((size_t)n * C + c) * hw + q];
+    dp[c] = dprob[((size_t)n * C + c) * hw + q];
+    dot += pr[c] * dp[c];
+  }
+  for (int c = 0; c < ld; ++c)
+    dlogits[(size_t)p * ld + c] = from_f<T>(c < C ? (drop ? drop[n * C + c] : 1.f) * pr[c] * (dp[c] - dot) : 0.f);
+}
+
+}  // namespace erfk
+
+extern "C" int erf_softmax_nhwc_fwd(const void* logits, int ld, const float* drop, int N, long long hw, int C, float* prob, int dtype,
+                                    erf_stream_t stream) {
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_softmax_nhwc_fwd: bad dtype %d", dtype);
+  ERF_CHECK_ARG(logits && prob && N > 0 && hw > 0 && C > 0 && C <= ML_MAXC && ld >= C, "erf_softmax_nhwc_fwd: bad arguments (C=%d, ld=%d)", C, ld);
+  const long long n_px = (long long)N * hw;
+  const unsigned grid = (unsigned)((n_px + 255) / 256);
+  if (dtype == ERF_F32)
+    softmax_nhwc_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, ld, drop, hw, n_px, C, prob);
+  else
+    softmax_nhwc_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, ld, drop, hw, n_px, C, prob);
+  ERF_CHECK_LAUNCH("erf_softmax_nhwc_fwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_softmax_nhwc_bwd(const float* prob, const float* dprob, const float* drop, int N, long long hw, int C, void* dlogits, int ld,
+                                    int dtype, erf_stream_t stream) {
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_softmax_nhwc_bwd: bad dtype %d", dtype);
+  ERF_CHECK_ARG(prob && dprob && dlogits && N > 0 && hw > 0 && C > 0 && C <= ML_MAXC && ld >= C, "erf_softmax_nhwc_bwd: bad arguments (C=%d, ld=%d)", C, ld);
+  const long long n_px = (long long)N * hw;
+  const unsigned grid = (unsigned)((n_px + 255) / 256);
+  if (dtype == ERF_F32)
+    softmax_nhwc_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(prob, dprob, drop, hw, n_px, C, (float*)dlogits, ld);
+  else
+    softmax_nhwc_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(prob, dprob, drop, hw, n_px, C, (__nv_bfloat16*)dlogits, ld);
+  ERF_CHECK_LAUNCH("erf_softmax_nhwc_bwd");
+  return ERF_OK;
+}

@@ -3,12 +3,15 @@ with the FORK's defaults -- BatchNorm off, dropout off unless ``use_dropout`` --
 in the fork's net_*.py files resolves to these.  The BatchNorm modules are still constructed (their parameters and
 buffers are part of the fork's checkpoints) but take no part in the arithmetic when ``use_batchnorm`` is False.
 
-Built: DownsamplerBlock, non_bottleneck_1d, UpsamplerBlock, DecoderBlockSmall, DecoderBlock, LadderBlock (train + eval, all
-on the same kernels as erfnet.py).  SoftMaxConv is a SURVEY section 8(f) "next" item."""
+Built: DownsamplerBlock, non_bottleneck_1d, UpsamplerBlock, DecoderBlockSmall, DecoderBlock, LadderBlock, SoftMaxConv (train +
+eval, all on the same kernels as erfnet.py)."""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
 
 from .ops import ConvSpec
 
@@ -85,3 +88,51 @@ class LadderBlock(_E._B200Module):
         x = _E._ToNHWC.apply(input, input.shape[1], ctx.dtype)
         l = _E._ToNHWC.apply(input_ladder, input_ladder.shape[1], ctx.dtype)
         return _E._ToNCHW.apply(self._nhwc2(x, l, ctx), self.noutput)
+
+
+class _SoftmaxFn(torch.autograd.Function):
+    """NHWC logits -> NCHW fp32 class probabilities (Dropout2d multiplier folded in); backward writes NHWC logit gradients."""
+
+    @staticmethod
+    def forward(ctx, logits, c, drop):
+        prob = ops.softmax_nhwc_fwd(logits.detach(), c, drop)
+        ctx.save_for_backward(prob, drop)
+        ctx.ld, ctx.dtype = logits.shape[-1], logits.dtype
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        prob, drop = ctx.saved_tensors
+        return ops.softmax_nhwc_bwd(prob, dprob, drop, ctx.ld, ctx.dtype), None, None
+
+
+class SoftMaxConv(_E._B200Module):
+    """train/erfnet_blocks.py:92-110: ConvTranspose2d(in, classes, 2, stride 2) -> Dropout2d (if use_dropout) -> softmax(dim=1).
+    Output: NCHW fp32 probabilities.  The transposed conv runs on the tensor cores (row-parity form), dropout and softmax are one kernel."""
+
+    def __init__(self, in_channels, softmax_classes, late_dropout_prob, use_dropout):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.convolution = nn.ConvTranspose2d(in_channels, softmax_classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+        self.dropout = nn.Dropout2d(p=late_dropout_prob)
+        self.in_channels, self.softmax_classes = in_channels, softmax_classes
+
+    def _prob(self, x, ctx):
+        conv = _E._PlainConv(self.convolution, ConvSpec(self.in_channels, self.softmax_classes, 2, 2, 2, transposed=True))
+        logits = _E._run(conv, x, ctx)
+        drop = None
+        if self.use_dropout and self.training and self.dropout.p != 0:
+            fixed = _E._FIXED_DROPOUT
+            if fixed is not None and self in fixed:
+                drop = fixed[self].to(x.device, torch.float32).reshape(x.shape[0], self.softmax_classes).contiguous()
+            else:
+                ones = torch.ones(x.shape[0], self.softmax_classes, 1, 1, device=x.device)
+                drop = F.dropout2d(ones, self.dropout.p, True).reshape(x.shape[0], self.softmax_classes).contiguous()
+        if ctx.training:
+            return _SoftmaxFn.apply(logits, self.softmax_classes, drop)
+        with torch.no_grad():
+            return ops.softmax_nhwc_fwd(logits, self.softmax_classes, None)
+
+    def forward(self, input):
+        ctx = _E._Ctx(self._precision(), self.training)
+        return self._prob(_E._ToNHWC.apply(input, input.shape[1], ctx.dtype), ctx)

@@ -825,6 +825,23 @@ def argmax(logits: torch.Tensor, c: int, nchw: bool, out_dtype=torch.int64) -> t
     return out
 
 
+def softmax_nhwc_fwd(logits, c, drop=None):
+    """NHWC logits [N,H,W,ld] -> NCHW fp32 probabilities [N,c,H,W] = softmax_c(logits * drop[n,c])."""
+    n, h, w, ld = logits.shape
+    prob = torch.empty(n, c, h, w, device=logits.device, dtype=torch.float32)
+    check(_lib.lib().erf_softmax_nhwc_fwd(_p(logits), ld, _p(drop), n, h * w, c, _p(prob), dt(logits), _stream(logits)))
+    _count()
+    return prob
+
+
+def softmax_nhwc_bwd(prob, dprob, drop, ld, dtype):
+    n, c, h, w = prob.shape
+    dlog = torch.empty(n, h, w, ld, device=prob.device, dtype=dtype)
+    check(_lib.lib().erf_softmax_nhwc_bwd(_p(prob), _p(dprob.contiguous().float()), _p(drop), n, h * w, c, _p(dlog), ld, dt(dlog), _stream(prob)))
+    _count()
+    return dlog
+
+
 LOSS_L1, LOSS_LOGLIK, LOSS_L1_CLASSPROB, LOSS_LOGLIK_CLASSPROB, LOSS_MSE_WEIGHTED = range(5)
 
 

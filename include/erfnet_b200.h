@@ -182,6 +182,14 @@ int erf_masked_loss_bwd(int kind, const float* a, const float* b, const float* p
                         long long n_px, long long hw, int C, float eps, float scale, const double* acc,
                         const float* go, float* d_a, float* d_b, float* d_prob, double* dclass, erf_stream_t stream);
 
+/* ---- SoftMaxConv tail (train/erfnet_blocks.py:104-110): Dropout2d multiplier + softmax over channels -------------------------- */
+/* prob (NCHW fp32) = softmax_c(logits[n,p,c] * drop[n,c]); logits NHWC with row pitch ld >= C (C <= 32); drop [N,C] or NULL. */
+int erf_softmax_nhwc_fwd(const void* logits, int ld, const float* drop, int N, long long hw, int C, float* prob, int dtype,
+                         erf_stream_t stream);
+/* dlogits[n,p,c] = drop[n,c] * prob_c * (dprob_c - sum_k dprob_k prob_k); channels [C, ld) are written as zeros. */
+int erf_softmax_nhwc_bwd(const float* prob, const float* dprob, const float* drop, int N, long long hw, int C, void* dlogits,
+                         int ld, int dtype, erf_stream_t stream);
+
 /* ---- Adam as configured by train/main.py:43-46,213 (L2 in the gradient), over one flat fp32 buffer ------- */
 int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, erf_stream_t stream);

@@ -284,6 +284,38 @@ def ladder_net(path):
                   "decoder.ladder_block_2.layer.conv1x3_1.bias", "decoder.scalar_output_conv.weight", "decoder.scalar_decoder_2.layers.0.conv.bias"):
             mod, attr = k.rsplit(".", 1)
             res[f"{name}_g_{k}"] = getattr(m.get_submodule(mod), attr).grad.numpy()
+    # class-probability variant (softmax_classes = 6): SoftMaxConv head + class_power parameters + L1LossClassProbMasked / the likelihood
+    # version.  Dropout is forced off (p = 0 everywhere) so that train mode is deterministic.
+    with contextlib.redirect_stdout(io.StringIO()):
+        cls = {"cls": ref_net.Net(softmax_classes=6, spread_class_power=True, late_dropout_prob=0.0),
+               "clslik": ref_net.Net(softmax_classes=6, likelihood_loss=True, spread_class_power=True, late_dropout_prob=0.0)}
+    for name, m in cls.items():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout2d):
+                mod.p = 0.0
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        sd = O.make_state_dict(shapes, seed=33)
+        sd["class_power"] = torch.linspace(0.0, 2.0, 6).view(1, 6, 1, 1)
+        if "class_power_var" in sd:
+            sd["class_power_var"] = torch.linspace(0.3, 0.8, 6).view(1, 6, 1, 1)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        out = m(x)
+        if name == "cls":
+            prob, power = out
+            loss = ref_ev.L1LossClassProbMasked()(prob, power, tgt)
+        else:
+            prob, power, var = out
+            loss = ref_ev.LogLikelihoodLossClassProbMasked(opt_eps=0.05)(prob, power, var, tgt)
+        loss.backward()
+        res[name + "_prob"], res[name + "_loss"] = prob.detach().numpy(), np.float64(loss.item())
+        for k in ("class_power", "decoder.scalar_output_conv.convolution.weight", "decoder.ladder_block_1.conv.weight", "encoder.block1.3.conv1x3_1.weight") + (("class_power_var",) if name == "clslik" else ()):
+            if "." in k:
+                mod, attr = k.rsplit(".", 1)
+                gten = getattr(m.get_submodule(mod), attr).grad
+            else:
+                gten = getattr(m, k).grad
+            res[f"{name}_g_{k}"] = gten.numpy()
     np.savez_compressed(path, **res)
 
 

@@ -290,8 +290,25 @@ def masked_loss_bwd(kind, a, b, prob, target, eps, scale, acc, go):
     return (leaves[2].grad * g).detach(), dclass
 
 
+def softmax_nhwc_fwd(logits, c, drop=None):
+    v = logits[..., :c].float()
+    if drop is not None:
+        v = v * drop[:, None, None, :]
+    return torch.softmax(v, dim=-1).permute(0, 3, 1, 2).contiguous()
+
+
+def softmax_nhwc_bwd(prob, dprob, drop, ld, dtype):
+    p, dp = prob.permute(0, 2, 3, 1), dprob.float().permute(0, 2, 3, 1)
+    g = p * (dp - (p * dp).sum(-1, keepdim=True))
+    if drop is not None:
+        g = g * drop[:, None, None, :]
+    out = torch.zeros(*g.shape[:3], ld, dtype=dtype)
+    out[..., :g.shape[-1]] = g.to(dtype)
+    return out
+
+
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "channel_sum_slice", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd"]
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd", "softmax_nhwc_fwd", "softmax_nhwc_bwd"]
 
 
 @contextlib.contextmanager

@@ -57,3 +57,46 @@ def check_ladder_net(golden_dir, device, precision="fp32", out_tol=1e-4, grad_to
         m.eval()
         with torch.no_grad():
             assert_rel(m(x.to(device)).cpu().numpy(), g[name + "_out"], out_tol, name + " eval output")
+
+
+def check_ladder_net_classes(golden_dir, device, precision="fp32", out_tol=1e-4, grad_tol=2e-3):
+    """softmax_classes = 6: SoftMaxConv head, class_power parameters, class-probability losses (dropout forced off as in the golden run)."""
+    g = np.load(os.path.join(golden_dir, "ladder_net.npz"))
+    x, tgt = ladder_inputs()
+    for name in ("cls", "clslik"):
+        m = NL.Net(softmax_classes=6, likelihood_loss=(name == "clslik"), spread_class_power=True, late_dropout_prob=0.0)
+        m.precision = precision
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout2d):
+                mod.p = 0.0
+        sd = O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=33)
+        sd["class_power"] = torch.linspace(0.0, 2.0, 6).view(1, 6, 1, 1)
+        if "class_power_var" in sd:
+            sd["class_power_var"] = torch.linspace(0.3, 0.8, 6).view(1, 6, 1, 1)
+        m.load_state_dict(sd, strict=True)
+        m.to(device).train()
+        out = m(x.to(device))
+        if name == "cls":
+            prob, power = out
+            loss = EV.L1LossClassProbMasked()(prob, power, tgt.to(device))
+        else:
+            prob, power, var = out
+            loss = EV.LogLikelihoodLossClassProbMasked(opt_eps=0.05)(prob, power, var, tgt.to(device))
+        assert_rel(prob.detach().cpu().numpy(), g[name + "_prob"], out_tol, name + " probabilities")
+        np.testing.assert_allclose(prob.detach().sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+        loss.backward()
+        assert abs(loss.item() - g[name + "_loss"]) <= max(out_tol * 10, 1e-4) * abs(g[name + "_loss"]), (loss.item(), g[name + "_loss"])
+        keys = ["class_power", "decoder.scalar_output_conv.convolution.weight", "decoder.ladder_block_1.conv.weight", "encoder.block1.3.conv1x3_1.weight"]
+        if name == "clslik":
+            keys.append("class_power_var")
+        for k in keys:
+            if "." in k:
+                mod, attr = k.rsplit(".", 1)
+                got = getattr(m.get_submodule(mod), attr).grad
+            else:
+                got = getattr(m, k).grad
+            assert got is not None, k
+            assert_rel(got.cpu().numpy(), g[f"{name}_g_{k}"], grad_tol * 5, f"{name} grad {k}")
+        m.eval()
+        with torch.no_grad():
+            assert_rel(m(x.to(device))[0].cpu().numpy(), g[name + "_prob"], out_tol, name + " eval probabilities")

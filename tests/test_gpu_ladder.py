@@ -8,7 +8,7 @@ import torch
 from erfnet_pytorch_b200 import evaluation_functions as EV
 from oracle import erfnet_oracle as O
 from oracle.make_golden import golden_input
-from tests.ladder_cases import check_ladder_net, make_net
+from tests.ladder_cases import check_ladder_net, check_ladder_net_classes, make_net
 from tests.test_host_logic import assert_rel
 
 pytestmark = pytest.mark.gpu
@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
 
 def test_ladder_net_fp32_golden(golden_dir):
     check_ladder_net(golden_dir, "cuda", "fp32", out_tol=1e-4, grad_tol=2e-3)
+
+
+def test_ladder_net_softmax_classes_fp32_golden(golden_dir):
+    check_ladder_net_classes(golden_dir, "cuda", "fp32", out_tol=1e-4, grad_tol=2e-3)
 
 
 def test_ladder_net_bf16_tensor_cores():

@@ -211,9 +211,10 @@ def test_fork_losses_host_logic(golden_dir):
 def test_ladder_net_host_logic(golden_dir):
     """train/net_regression_ladder.Net: module wiring (three-scale encoder, ladder concat, conv+ReLU block, 1/2-channel heads),
     autograd through it and the masked losses, kernels emulated."""
-    from tests.ladder_cases import check_ladder_net
+    from tests.ladder_cases import check_ladder_net, check_ladder_net_classes
     with emulated_kernels():
         check_ladder_net(golden_dir, "cpu", "fp32", out_tol=1e-4, grad_tol=2e-3)
+        check_ladder_net_classes(golden_dir, "cpu", "fp32", out_tol=1e-4, grad_tol=2e-3)
 
 
 def test_no_cpu_fallback():
