@@ -187,6 +187,7 @@ def main():
     fork_losses(os.path.join(OUT, "fork_losses.npz"))
     blocks_nobn(os.path.join(OUT, "blocks_nobn.npz"))
     ladder_net(os.path.join(OUT, "ladder_net.npz"))
+    fork_nets(os.path.join(OUT, "fork_nets.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -319,6 +320,73 @@ def ladder_net(path):
     np.savez_compressed(path, **res)
 
 
+FORK_NETS = {   # name -> (reference module, Net kwargs, head kind)
+    "regression": ("net_regression", dict(), "reg"),
+    "regression_lik": ("net_regression", dict(likelihood_loss=True), "lik"),
+    "regression_small": ("net_regression_small", dict(), "reg"),
+    "regression_small_cls": ("net_regression_small", dict(softmax_classes=4, spread_class_power=True, late_dropout_prob=0.0), "prob"),
+    "regression_ladder_small": ("net_regression_ladder_small", dict(likelihood_loss=True), "lik"),
+    "classification": ("net_classification", dict(softmax_classes=6, spread_class_power=True), "logits"),
+    "classification_ladder": ("net_classification_ladder", dict(softmax_classes=5), "logits"),
+}
+FORK_NET_GRADS = ("encoder.initial_block.conv.weight", "decoder.scalar_decoder_1.layers.0.conv.bias", "decoder.scalar_decoder_2.layers.1.conv1x3_2.weight")
+
+
+def fork_net_inputs():
+    x = golden_input((1, 3, 64, 128), 91)
+    tgt = golden_input((1, 64, 128), 92) * 2.0
+    tgt[golden_input((1, 64, 128), 93) < 0.6] = -1.0
+    return x, tgt, golden_labels((1, 64, 128), 94, n_classes=5)
+
+
+def fork_net_loss(ev, kind, out, tgt, labels):
+    """The criterion train/main.py:174-186 pairs with each head."""
+    if kind == "reg":
+        return ev.L1LossMasked()(out, tgt)
+    if kind == "lik":
+        return ev.LogLikelihoodLossMasked(opt_eps=0.05)(out[:, 0], out[:, 1].pow(2), tgt)
+    if kind == "prob":
+        return ev.L1LossClassProbMasked()(out[0], out[1], tgt)
+    return ev.CrossEntropyLoss2d()(out[0], labels)
+
+
+def fork_nets(path):
+    """The five remaining train/net_*.py graphs (net_regression, _small, _ladder_small, net_classification, _ladder): state_dict layout,
+    train-mode output, loss of the matching criterion and a few gradients at 1 x 3 x 64 x 128 (dropout p forced to 0: deterministic)."""
+    import contextlib
+    import importlib
+    import io
+    import warnings
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(REF, "train"))
+    res = {}
+    x, tgt, labels = fork_net_inputs()
+    for name, (modname, kw, kind) in FORK_NETS.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_ev = importlib.import_module("evaluation_functions")
+            m = importlib.import_module(modname).Net(**kw)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout2d):
+                mod.p = 0.0
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        res[name + "_keys"] = np.array([f"{k} {sh}" for k, sh in shapes.items()])
+        sd = O.make_state_dict(shapes, seed=41)
+        if "class_power" in sd:
+            sd["class_power"] = torch.linspace(0.2, 1.8, sd["class_power"].numel()).view_as(sd["class_power"])
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        out = m(x)
+        first = out[0] if isinstance(out, tuple) else out
+        res[name + "_out"] = first.detach().numpy()
+        loss = fork_net_loss(ref_ev, kind, out, tgt, labels)
+        loss.backward()
+        res[name + "_loss"] = np.float64(loss.item())
+        for k in FORK_NET_GRADS + (("class_power",) if kind == "prob" else ()):
+            gten = m.get_parameter(k).grad
+            res[f"{name}_g_{k}"] = gten.numpy()
+    np.savez_compressed(path, **res)
+
+
 def fork_loss_inputs():
     """Deterministic operands of the fork-loss KATs (regenerated by the tests, not stored)."""
     b, c, h, w = 2, 6, 12, 20
@@ -362,4 +430,8 @@ def fork_losses(path):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:      # regenerate single fixtures: python oracle/make_golden.py fork_nets ...
+        for fn in sys.argv[1:]:
+            globals()[fn](os.path.join(OUT, fn + ".npz"))
+    else:
+        main()

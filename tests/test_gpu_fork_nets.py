@@ -1,0 +1,28 @@
+"""GPU: the fork's remaining five net_*.py graphs through the C ABI against the reference's golden outputs / losses / gradients (fp32
+check mode), and one of them in bf16 at a tensor-core-eligible size against the fp32 run of the same kernels' check mode."""
+import pytest
+import torch
+
+from oracle.make_golden import golden_input
+from tests.forknet_cases import build_fork_net, check_fork_nets
+from tests.test_host_logic import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fork_nets_fp32_golden(golden_dir):
+    check_fork_nets(golden_dir, "cuda", "fp32", out_tol=1e-4, grad_tol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["regression_small", "classification_ladder"])
+def test_fork_net_bf16_tensor_cores(name):
+    """1 x 3 x 128 x 1024: every 64/128-channel block, the ladder convs and the head run on tcgen05; compared with the fp32 check mode."""
+    x = golden_input((1, 3, 128, 1024), 95).cuda()
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        m, _ = build_fork_net(name, "cuda", precision)
+        m.eval()
+        with torch.no_grad():
+            o = m(x)
+        outs[precision] = (o[0] if isinstance(o, tuple) else o).float().cpu().numpy()
+    assert_rel(outs["bf16"], outs["fp32"], 3e-2, name + " bf16 vs fp32")

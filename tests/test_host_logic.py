@@ -227,3 +227,19 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 32, 64))
     with pytest.raises(RuntimeError):
         iouEval(20).addBatch(torch.zeros(1, 1, 4, 4).long(), torch.zeros(1, 1, 4, 4).long())
+
+
+def test_fork_nets_host_logic(golden_dir):
+    """The five remaining train/net_*.py graphs: module wiring, checkpoint layout, heads and criteria, kernels emulated."""
+    from tests.forknet_cases import check_fork_nets
+    with emulated_kernels():
+        check_fork_nets(golden_dir, "cpu", "fp32", out_tol=1e-4, grad_tol=2e-3)
+
+
+def test_classification_net_argument_errors():
+    from erfnet_pytorch_b200 import net_classification
+    with pytest.raises(RuntimeError):
+        net_classification.Net()            # softmax_classes = 0: ConvTranspose2d(16, 0) in the reference (train/main.py:835-836 asserts > 0)
+    m = net_classification.Net(softmax_classes=3, spread_class_power=True, fix_class_power=True)
+    assert "class_power" not in m.state_dict() and "class_power" not in dict(m.named_parameters())
+    np.testing.assert_allclose(m.class_power.flatten().cpu().numpy(), np.linspace(0.7, 2.0, 3), rtol=1e-6)
