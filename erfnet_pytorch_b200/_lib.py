@@ -82,6 +82,17 @@ _SIGNATURES = {
     "erf_pack_im2col_weights": [_vp, _ll, _ll, _i, _i, _i, C.POINTER(Im2colTaps), _i, _i, _vp, _vp],
     "erf_conv_wgrad_im2col_tc_workspace": [],
     "erf_conv_wgrad_im2col_tc": [C.POINTER(WgradIm2colDesc), _vp, _vp, C.c_size_t, _vp],
+    "erf_avgpool_fwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "erf_avgpool_bwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "erf_linear_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "erf_linear_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "erf_ce_rows_fwd": [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp],
+    "erf_ce_rows_bwd": [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp],
+    "erf_sgd_step": [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _f, _vp],
+    "erf_ema_update": [_vp, _vp, _ll, _f, _vp],
+    "erf_ingest_u8": [_vp, _ll, _i, _vp, _vp, _vp, _i, _vp],
+    "erf_label_lut": [_vp, _i, _ll, _vp, _i, _vp, _vp],
+    "erf_colorize": [_vp, _i, _ll, _ll, _vp, _i, _vp, _vp],
     "erf_umma_probe": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp],
 }
 

@@ -85,6 +85,15 @@ class _ToNCHW(torch.autograd.Function):
         return ops.nchw_to_nhwc(dy, ctx.ld, ctx.dtype), None
 
 
+def input_to_nhwc(input, ld, dtype, mean=None, std=None):
+    """Public-boundary input -> internal NHWC activations.  NCHW fp32 (the reference API) goes through the layout kernel; a uint8
+    [N,H,W,3] image batch (HWC, what PIL / a camera delivers; train/dataset.py:113-114 applies ToTensor to it) goes through the ingest
+    kernel, which fuses ToTensor (/255) [+ Normalize] with the layout change."""
+    if input.dtype == torch.uint8:
+        return ops.ingest_u8(input, ld, dtype, mean, std)
+    return _ToNHWC.apply(input, ld, dtype)
+
+
 class _B200Module(nn.Module):
     """Common plumbing: NCHW<->NHWC at the public boundary, packed-weight cache for eval mode."""
     precision: Optional[str] = None
@@ -802,7 +811,7 @@ class ERFNet(_B200Module):
         ctx = _Ctx(self._precision(), self.training, drop_scales)
         if self.training and drop_scales is None and _FIXED_DROPOUT is None and input.is_cuda and not ops.EMULATED:
             ctx.drawn = draw_dropout(self, input.shape[0], input.device)
-        x = _ToNHWC.apply(input, 4, ctx.dtype)
+        x = input_to_nhwc(input, 4, ctx.dtype)
         if only_encode:
             return self.encoder._nhwc(x, ctx, predict=True)
         return self.decoder._nhwc(self.encoder._nhwc(x, ctx), ctx)

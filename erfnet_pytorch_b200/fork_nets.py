@@ -158,7 +158,7 @@ class ForkNet(_E._B200Module):
     LADDER = False
 
     def _features(self, input, ctx):
-        x = _E._ToNHWC.apply(input, 4, ctx.dtype)
+        x = _E.input_to_nhwc(input, 4, ctx.dtype)
         if self.LADDER:
             return self.decoder._nhwc3(*self.encoder._nhwc3(x, ctx), ctx)
         return self.decoder._nhwc(self.encoder._nhwc(x, ctx), ctx)

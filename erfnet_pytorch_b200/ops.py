@@ -896,6 +896,111 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, gra
     _count(2)
 
 
+# ---- ImageNet tail, mean teacher, I/O side (csrc/tail_io.cu) -------------------------------------------------------------------
+def avgpool_fwd(x: torch.Tensor, c: int, k: int) -> torch.Tensor:
+    """nn.AvgPool2d(k, 1, 0) over NHWC x [N,H,W,ld] -> fp32 NHWC [N,H-k+1,W-k+1,c]."""
+    n, h, w, ld = x.shape
+    if h < k or w < k:
+        raise RuntimeError(f"AvgPool2d({k}): input {h}x{w} is smaller than the window")
+    out = torch.empty(n, h - k + 1, w - k + 1, c, device=x.device, dtype=torch.float32)
+    check(_lib.lib().erf_avgpool_fwd(_p(x), n, h, w, ld, c, k, _p(out), dt(x), _stream(x)))
+    _count()
+    return out
+
+
+def avgpool_bwd(dout: torch.Tensor, h: int, w: int, ld: int, k: int, dtype) -> torch.Tensor:
+    n, _, _, c = dout.shape
+    dx = torch.empty(n, h, w, ld, device=dout.device, dtype=dtype)
+    check(_lib.lib().erf_avgpool_bwd(_p(dout.contiguous()), n, h, w, ld, c, k, _p(dx), dt(dx), _stream(dout)))
+    _count()
+    return dx
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    m, k = x.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=x.device, dtype=torch.float32)
+    check(_lib.lib().erf_linear_fwd(_p(x), _p(w), _p(bias), _p(out), m, n, k, _stream(x)))
+    _count()
+    return out
+
+
+def linear_bwd(x, w, dout, need_dx=True, dw_out=None, db_out=None, want_bias=True):
+    """-> (dx or None, dw, db): dw / db are ACCUMULATED into dw_out / db_out (e.g. .grad views) or into fresh zero tensors."""
+    m, k = x.shape
+    n = w.shape[0]
+    dx = torch.empty(m, k, device=x.device, dtype=torch.float32) if need_dx else None
+    dw = torch.zeros(n, k, device=x.device, dtype=torch.float32) if dw_out is None else dw_out
+    db = (torch.zeros(n, device=x.device, dtype=torch.float32) if db_out is None else db_out) if want_bias else None
+    check(_lib.lib().erf_linear_bwd(_p(x), _p(w), _p(dout.contiguous()), _p(dx), _p(dw), _p(db), m, n, k, _stream(x)))
+    _count(2 + int(need_dx))
+    return dx, dw, db
+
+
+def ce_rows_fwd(logits: torch.Tensor, target: torch.Tensor, ignore_index: int):
+    """-> (acc fp32 [2] = (sum nll, #valid rows), lse fp32 [N], rank int32 [N])."""
+    n, c = logits.shape
+    acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+    lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+    rank = torch.empty(n, device=logits.device, dtype=torch.int32)
+    check(_lib.lib().erf_ce_rows_fwd(_p(logits), _p(target), n, c, ignore_index, _p(lse), _p(rank), _p(acc), _stream(logits)))
+    _count()
+    return acc, lse, rank
+
+
+def ce_rows_bwd(logits, target, ignore_index, lse, acc, go):
+    n, c = logits.shape
+    dlog = torch.empty_like(logits)
+    check(_lib.lib().erf_ce_rows_bwd(_p(logits), _p(target), n, c, ignore_index, _p(lse), _p(acc), _p(go), _p(dlog), _stream(logits)))
+    _count()
+    return dlog
+
+
+def sgd_step(p, g, buf, lr, momentum, weight_decay, first_step, grad_scale=1.0):
+    check(_lib.lib().erf_sgd_step(_p(p), _p(g), _p(buf), p.numel(), lr, momentum, weight_decay, int(first_step), grad_scale, _stream(p)))
+    _count()
+
+
+def ema_update(teacher, student, rate):
+    check(_lib.lib().erf_ema_update(_p(teacher), _p(student), teacher.numel(), rate, _stream(teacher)))
+    _count()
+
+
+def ingest_u8(img: torch.Tensor, ld: int, dtype, mean=None, std=None) -> torch.Tensor:
+    """uint8 [N,H,W,3] (HWC, as PIL / a camera delivers it) -> NHWC activations [N,H,W,ld] = ToTensor [+ Normalize] + layout, one pass."""
+    if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
+        raise RuntimeError(f"ingest_u8: expected a uint8 [N,H,W,3] tensor, got {img.dtype} {tuple(img.shape)}")
+    img = img.contiguous()
+    n, h, w, _ = img.shape
+    out = torch.empty(n, h, w, ld, device=img.device, dtype=dtype)
+    check(_lib.lib().erf_ingest_u8(_p(img), n * h * w, ld, _p(mean), _p(std), _p(out), dt(out), _stream(img)))
+    _count()
+    return out
+
+
+def label_lut(labels: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    if labels.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError("label_lut: labels must be uint8 or int64")
+    labels = labels.contiguous()
+    out = torch.empty(labels.shape, device=labels.device, dtype=torch.int64)
+    if labels.numel():
+        check(_lib.lib().erf_label_lut(_p(labels), labels.element_size(), labels.numel(), _p(lut), lut.numel(), _p(out), _stream(labels)))
+        _count()
+    return out
+
+
+def colorize(labels: torch.Tensor, cmap: torch.Tensor) -> torch.Tensor:
+    """labels uint8 / int64 [N,H,W] -> uint8 [N,3,H,W]; cmap uint8 [n_colors,3]."""
+    if labels.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError("colorize: labels must be uint8 or int64")
+    labels = labels.contiguous()
+    n, h, w = labels.shape
+    out = torch.empty(n, 3, h, w, device=labels.device, dtype=torch.uint8)
+    check(_lib.lib().erf_colorize(_p(labels), labels.element_size(), n, h * w, _p(cmap), cmap.shape[0], _p(out), _stream(labels)))
+    _count()
+    return out
+
+
 def umma_probe(a: torch.Tensor, b: torch.Tensor, row_shift: int, layout: int, iters: int = 1):
     """a [rows,K] bf16, b [N,K] bf16 -> (D [128,N] fp32, cycles)."""
     rows, k = a.shape
@@ -919,5 +1024,6 @@ def _wrap_timed(name):
 
 for _n in ("channel_stats", "channel_sum", "channel_sum_slice", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
            "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
-           "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair"):
+           "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair", "avgpool_fwd", "avgpool_bwd", "linear_fwd", "linear_bwd", "ce_rows_fwd", "ce_rows_bwd",
+           "sgd_step", "ema_update", "ingest_u8", "label_lut", "colorize"):
     _wrap_timed(_n)

@@ -284,6 +284,42 @@ typedef struct {
 size_t erf_conv_wgrad_im2col_tc_workspace(void);
 int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* dw, void* workspace, size_t ws_bytes, erf_stream_t stream);
 
+/* ---- ImageNet classification tail (imagenet/erfnet_imagenet.py:89-110, imagenet/main.py:80-85, 168-189, 288-301) ------------------- */
+/* nn.AvgPool2d(k, stride 1, padding 0) over NHWC activations: out fp32 [N, H-k+1, W-k+1, C]; bwd writes every channel of dx (pitch ld,
+ * channels >= C as zeros). */
+int erf_avgpool_fwd(const void* in, int N, int H, int W, int ld, int C, int k, float* out, int dtype, erf_stream_t stream);
+int erf_avgpool_bwd(const float* dout, int N, int H, int W, int ld, int C, int k, void* dx, int dtype, erf_stream_t stream);
+/* nn.Linear: out[M,N] = x[M,K] w[N,K]^T + bias[N] (fp32); bwd: dx[M,K] = dout w (NULL: skipped), dw[N,K] += dout^T x, db[N] += column sums. */
+int erf_linear_fwd(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, erf_stream_t stream);
+int erf_linear_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, float* db, int M, int N, int K,
+                   erf_stream_t stream);
+/* nn.CrossEntropyLoss() over logits [N,C] fp32 and int64 targets: acc[0] += sum of -log_softmax[target], acc[1] += #rows whose target is
+ * not ignore_index (caller-zeroed; loss = acc[0] / acc[1]); lse[N] = log-sum-exp per row; rank[N] = position of the target logit in the
+ * descending order of its row (ties: lower class first; -1 for ignored rows): top-k precision = #(rank < k) / N (imagenet/main.py:288-301). */
+int erf_ce_rows_fwd(const float* logits, const long long* target, int N, int C, long long ignore_index, float* lse, int* rank, float* acc,
+                    erf_stream_t stream);
+/* dlogits = go[0] * (softmax - onehot) / acc[1] for valid rows, 0 for ignored rows (go NULL: 1). */
+int erf_ce_rows_bwd(const float* logits, const long long* target, int N, int C, long long ignore_index, const float* lse,
+                    const float* acc, const float* go, float* dlogits, erf_stream_t stream);
+/* torch.optim.SGD(lr, momentum, weight_decay) over one flat fp32 buffer: d = grad_scale * g + wd * p; buf = first_step ? d : momentum * buf + d;
+ * p -= lr * buf (momentum == 0: p -= lr * d, buf unused). */
+int erf_sgd_step(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay, int first_step,
+                 float grad_scale, erf_stream_t stream);
+
+/* ---- mean teacher (train/main.py:140-142, 384-390): teacher = teacher * (1 - rate) + rate * student over flat fp32 buffers ----------- */
+int erf_ema_update(float* teacher, const float* student, long long n, float rate, erf_stream_t stream);
+
+/* ---- I/O side ----------------------------------------------------------------------------------------------------------------- */
+/* uint8 HWC pixels [n_px, 3] -> NHWC activations [n_px, ld] (channels >= 3 zero): v = u8 / 255 (torchvision ToTensor, train/dataset.py:113-114),
+ * then (v - mean[c]) / std[c] when mean / std (device fp32 [3]) are given.  Replaces ToTensor + the NCHW fp32 -> NHWC conversion. */
+int erf_ingest_u8(const void* in, long long n_px, int ld, const float* mean, const float* stdv, void* out, int dtype, erf_stream_t stream);
+/* out[i] = lut[in[i]] for 0 <= in[i] < lut_n, else in[i]; in uint8 or int64, out int64: ToLabel + Relabel (eval/transform.py:55-70), and the
+ * trainId -> id table of eval/eval_cityscapes_server.py:39-63. */
+int erf_label_lut(const void* in, int elem_bytes, long long n, const long long* lut, int lut_n, long long* out, erf_stream_t stream);
+/* Colorize (eval/transform.py:73-93): out uint8 [n_img, 3, hw], out[:, ch, p] = cmap[label][ch] for label < n_colors (cmap uint8 [n_colors,3]), else 0. */
+int erf_colorize(const void* labels, int elem_bytes, long long n_img, long long hw, const unsigned char* cmap, int n_colors,
+                 unsigned char* out, erf_stream_t stream);
+
 /* ---- tcgen05 / TMEM / TMA building blocks (sm_100a) ------------------------------------------------------ */
 /* Probe used by the GPU tests to pin the UMMA shared-memory descriptor semantics the fused kernels rely on:
  * D[128 x N] = A[rows row_shift .. row_shift+127] (K-major, K = 16*ksteps) * B[N x K]^T, layout: 0 = no swizzle

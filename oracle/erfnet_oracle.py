@@ -113,6 +113,8 @@ def make_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, gain: flo
         else:
             if "decoder" in key and ".conv." in key or key.startswith("decoder.output_conv"):
                 fan_in = shape[0] * shape[2] * shape[3] / 4.0  # ConvTranspose, stride 2: ~1/4 of the taps hit
+            elif len(shape) == 2:       # nn.Linear [out, in]
+                fan_in = shape[1]
             else:
                 fan_in = shape[1] * shape[2] * shape[3]
             bound = gain * math.sqrt(3.0 / fan_in)

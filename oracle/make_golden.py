@@ -188,6 +188,7 @@ def main():
     blocks_nobn(os.path.join(OUT, "blocks_nobn.npz"))
     ladder_net(os.path.join(OUT, "ladder_net.npz"))
     fork_nets(os.path.join(OUT, "fork_nets.npz"))
+    imagenet_net(os.path.join(OUT, "imagenet_net.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -385,6 +386,80 @@ def fork_nets(path):
             gten = m.get_parameter(k).grad
             res[f"{name}_g_{k}"] = gten.numpy()
     np.savez_compressed(path, **res)
+
+
+IMAGENET_GRADS = ("features.encoder.initial_block.conv.weight", "features.encoder.layers.10.bn2.weight", "classifier.linear.bias")
+
+
+def imagenet_inputs(classes=1000):
+    g = torch.Generator().manual_seed(3000)
+    x = torch.randn(2, 3, 224, 224, generator=g)            # normalised-image-like
+    y = torch.tensor([3, classes - 5])
+    return x, y
+
+
+def imagenet_net(path):
+    """imagenet/erfnet_imagenet.ERFNet(1000) (BASELINE config 3): state_dict layout, train-mode logits (BatchNorm batch statistics,
+    dropout p forced to 0), nn.CrossEntropyLoss, accuracy() top-1/top-5 of imagenet/main.py:288-301 (restated with reshape: its
+    ``.view(-1)`` on the transposed prediction no longer runs on current torch), a few gradients, and parameters after two
+    SGD(0.002, momentum 0.9, weight decay 1e-4) steps; plus the eval-mode logits after those steps."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "imagenet"))
+    ref = importlib.import_module("erfnet_imagenet")
+    m = ref.ERFNet(1000)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    res = {"keys": np.array([f"{k} {sh}" for k, sh in shapes.items()])}
+    m.load_state_dict(O.make_state_dict(shapes, seed=51), strict=True)
+    x, y = imagenet_inputs()
+    opt = torch.optim.SGD(m.parameters(), 0.002, momentum=0.9, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss()
+    m.train()
+    for step in range(2):
+        out = m(x)
+        loss = crit(out, y)
+        opt.zero_grad()
+        loss.backward()
+        if step == 0:
+            res["logits"], res["loss"] = out.detach().numpy(), np.float64(loss.item())
+            _, pred = out.detach().topk(5, 1, True, True)
+            correct = pred.t().eq(y.view(1, -1).expand_as(pred.t()))
+            res["top1"] = np.float64(correct[:1].reshape(-1).float().sum(0) * 100.0 / 2)
+            res["top5"] = np.float64(correct[:5].reshape(-1).float().sum(0) * 100.0 / 2)
+            for k in IMAGENET_GRADS:
+                res["g_" + k] = m.get_parameter(k).grad.numpy().copy()
+        opt.step()
+    res["loss2"] = np.float64(loss.item())
+    for k in IMAGENET_GRADS:
+        res["p2_" + k] = m.get_parameter(k).detach().numpy().copy()
+    res["rm2"] = m.features.encoder.layers[10].bn2.running_mean.numpy().copy()
+    m.eval()
+    with torch.no_grad():
+        res["eval_logits"] = m(x).numpy()
+    # accuracy() / CrossEntropyLoss KAT on a logits matrix with a spread of target ranks (and an ignored row for the loss)
+    lg, tg = topk_kat_inputs()
+    _, pred = lg.topk(5, 1, True, True)
+    correct = pred.t().eq(tg.view(1, -1).expand_as(pred.t()))
+    res["kat_topk"] = np.array([float(correct[:k].reshape(-1).float().sum(0) * 100.0 / tg.numel()) for k in (1, 3, 5)])
+    lg2 = lg.clone().requires_grad_(True)
+    tg2 = tg.clone()
+    tg2[4] = -100
+    l2 = torch.nn.CrossEntropyLoss()(lg2, tg2)
+    l2.backward()
+    res["kat_loss"], res["kat_dlogits"] = np.float64(l2.item()), lg2.grad.numpy()
+    np.savez_compressed(path, **res)
+
+
+def topk_kat_inputs():
+    lg = (golden_input((64, 37), 55) - 0.5) * 6.0
+    g = torch.Generator().manual_seed(56)
+    tg = torch.randint(0, 37, (64,), generator=g)
+    order = lg.argsort(1, descending=True)
+    for i in range(0, 64, 3):          # every third row: make the target one of the top-6 classes
+        tg[i] = order[i, (i // 3) % 6]
+    return lg, tg
 
 
 def fork_loss_inputs():

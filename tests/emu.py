@@ -307,8 +307,97 @@ def softmax_nhwc_bwd(prob, dprob, drop, ld, dtype):
     return out
 
 
+def avgpool_fwd(x, c, k):
+    return F.avg_pool2d(x[..., :c].float().permute(0, 3, 1, 2), k, 1, 0).permute(0, 2, 3, 1).contiguous()
+
+
+@torch.enable_grad()
+def avgpool_bwd(dout, h, w, ld, k, dtype):
+    n, _, _, c = dout.shape
+    xi = torch.zeros(n, c, h, w, requires_grad=True)
+    (g,) = torch.autograd.grad(F.avg_pool2d(xi, k, 1, 0), xi, dout.permute(0, 3, 1, 2))
+    dx = torch.zeros(n, h, w, ld, dtype=dtype)
+    dx[..., :c] = g.permute(0, 2, 3, 1).to(dtype)
+    return dx
+
+
+def linear_fwd(x, w, bias):
+    return F.linear(x, w, bias)
+
+
+def linear_bwd(x, w, dout, need_dx=True, dw_out=None, db_out=None, want_bias=True):
+    dx = dout @ w if need_dx else None
+    dw = dout.t() @ x
+    dw = dw if dw_out is None else dw_out.add_(dw)
+    db = None
+    if want_bias:
+        db = dout.sum(0) if db_out is None else db_out.add_(dout.sum(0))
+    return dx, dw, db
+
+
+def ce_rows_fwd(logits, target, ignore_index):
+    n, c = logits.shape
+    valid = (target != ignore_index) & (target >= 0) & (target < c)
+    lse = torch.logsumexp(logits, 1)
+    t = target.clamp(0, c - 1)
+    lt = logits.gather(1, t[:, None])[:, 0]
+    nll = (lse - lt)[valid]
+    idx = torch.arange(c)[None, :]
+    rank = ((logits > lt[:, None]) | ((logits == lt[:, None]) & (idx < t[:, None]))).sum(1).int()
+    rank[~valid] = -1
+    return torch.stack([nll.sum(), valid.sum().float()]), lse, rank
+
+
+def ce_rows_bwd(logits, target, ignore_index, lse, acc, go):
+    n, c = logits.shape
+    valid = (target != ignore_index) & (target >= 0) & (target < c)
+    g = torch.exp(logits - lse[:, None])
+    g[valid, target[valid]] -= 1.0
+    g[~valid] = 0.0
+    return g * ((go if go is not None else 1.0) / acc[1].clamp_min(1.0))
+
+
+def sgd_step(p, g, buf, lr, momentum, weight_decay, first_step, grad_scale=1.0):
+    d = g * grad_scale + weight_decay * p
+    if momentum != 0:
+        if first_step:
+            buf.copy_(d)
+        else:
+            buf.mul_(momentum).add_(d)
+        d = buf
+    p.sub_(lr * d)
+
+
+def ema_update(teacher, student, rate):
+    teacher.mul_(1.0 - rate).add_(rate * student)
+
+
+def ingest_u8(img, ld, dtype, mean=None, std=None):
+    n, h, w, _ = img.shape
+    v = img.float() / 255.0
+    if mean is not None or std is not None:
+        v = (v - (mean if mean is not None else 0.0)) / (std if std is not None else 1.0)
+    out = torch.zeros(n, h, w, ld, dtype=dtype)
+    out[..., :3] = v.to(dtype)
+    return out
+
+
+def label_lut(labels, lut):
+    v = labels.long()
+    inside = (v >= 0) & (v < lut.numel())
+    return torch.where(inside, lut[v.clamp(0, lut.numel() - 1)], v)
+
+
+def colorize(labels, cmap):
+    v = labels.long()
+    inside = (v >= 0) & (v < cmap.shape[0])
+    col = cmap[v.clamp(0, cmap.shape[0] - 1)] * inside[..., None].to(torch.uint8)
+    return col.permute(0, 3, 1, 2).contiguous()
+
+
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "channel_sum_slice", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd", "softmax_nhwc_fwd", "softmax_nhwc_bwd"]
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd", "softmax_nhwc_fwd", "softmax_nhwc_bwd",
+          "avgpool_fwd", "avgpool_bwd", "linear_fwd", "linear_bwd", "ce_rows_fwd", "ce_rows_bwd", "sgd_step", "ema_update", "ingest_u8", "label_lut", "colorize"]
 
 
 @contextlib.contextmanager

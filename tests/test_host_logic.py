@@ -243,3 +243,22 @@ def test_classification_net_argument_errors():
     m = net_classification.Net(softmax_classes=3, spread_class_power=True, fix_class_power=True)
     assert "class_power" not in m.state_dict() and "class_power" not in dict(m.named_parameters())
     np.testing.assert_allclose(m.class_power.flatten().cpu().numpy(), np.linspace(0.7, 2.0, 3), rtol=1e-6)
+
+
+def test_imagenet_net_host_logic(golden_dir):
+    """imagenet/erfnet_imagenet.ERFNet(1000) + the SGD step of imagenet/main.py: wiring of the pooling / Linear tail, row-wise CE,
+    top-k, FlatSGD (momentum, weight decay, flat views), kernels emulated."""
+    from tests.imagenet_cases import check_ce_topk, check_imagenet_net, check_lr_schedule
+    with emulated_kernels():
+        check_imagenet_net(golden_dir, "cpu")
+        check_ce_topk(golden_dir, "cpu")
+    check_lr_schedule()
+
+
+def test_io_side_and_mean_teacher_host_logic():
+    from tests.io_cases import check_ingest, check_labels, check_mean_teacher, check_model_accepts_uint8
+    with emulated_kernels():
+        check_ingest("cpu")
+        check_model_accepts_uint8("cpu")
+        check_labels("cpu")
+        check_mean_teacher("cpu")
