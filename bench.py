@@ -206,6 +206,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(3, args.warmup)
+    pk0 = peaks()
     B = args.batch
 
     model = E.ERFNet(NC)
@@ -290,6 +291,50 @@ def main():
 
     fwd_ms, _ = timed(fwd, K, Wm)
 
+    # ---- inference at a batch that fills the 148 SMs (the 128-channel layers of a batch of 6 are only 2.6 waves of 128-pixel tiles), and
+    # BASELINE configs[4]: batch 8 at 1024 x 2048 -> fused argmax -> iouEval confusion histogram (what eval_iou.py does per batch)
+    extra = {}
+    if os.environ.get("ERF_BENCH_EXTRA", "1") == "1":
+        from erfnet_pytorch_b200.iouEval import iouEval
+        gi = None
+        torch.cuda.empty_cache()
+        BB = 32
+        xb = torch.cat([pool_dev[i % len(pool_dev)][0] for i in range((BB + B - 1) // B)])[:BB].contiguous()
+        xs = [xb, xb.flip(0).contiguous()]          # 2 x 403 MB of input: never L2-resident
+        gb = GraphedInference(model, xs[0]) if use_graph else None
+
+        def fwd_big(i):
+            if gb is not None:
+                gb(xs[i % 2])
+            else:
+                with torch.no_grad():
+                    model(xs[i % 2])
+
+        big_ms, _ = timed(fwd_big, max(3, K // 2), 3)
+        extra["fwd_b32"] = {"images_per_s": BB * world / (big_ms * 1e-3), "ms_per_step": big_ms, "batch": BB,
+                            "tc_frac": BB / (big_ms * 1e-3) * GFLOP_FWD_PER_IMG / 1e3 / pk0["tc_sustained"]}
+        del gb, xs, xb
+        torch.cuda.empty_cache()
+        HF, WF, BF = 1024, 2048, 8
+        gen = torch.Generator(device=dev).manual_seed(7 + rank)
+        xf = [torch.rand(BF, 3, HF, WF, device=dev, generator=gen) for _ in range(2)]
+        lab = torch.randint(0, NC, (BF, HF, WF), device=dev, generator=gen, dtype=torch.int64).to(torch.uint8)   # 19 = ignore (eval_iou.py:37)
+        ev = iouEval(NC)
+
+        def eval_full(i):
+            with torch.no_grad():
+                logits = model.forward_nhwc(xf[i % 2])
+                pred = ops.argmax(logits, NC, False, torch.uint8)
+                ev.addBatch(pred.unsqueeze(1), lab.unsqueeze(1))
+
+        full_ms, _ = timed(eval_full, max(3, K // 2), 3)
+        miou = float(ev.getIoU()[0])
+        extra["eval_fullres"] = {"workload": f"configs[4]: batch {BF} x 3x{HF}x{WF} forward + argmax + iouEval.addBatch, eager launches",
+                                 "frames_per_s": BF * world / (full_ms * 1e-3), "ms_per_batch": full_ms, "mean_iou_random_labels": miou,
+                                 "tc_frac": BF / (full_ms * 1e-3) * 4 * GFLOP_FWD_PER_IMG / 1e3 / pk0["tc_sustained"]}
+        del xf, lab
+        torch.cuda.empty_cache()
+
     # ---- dominant kernel: per-launch CUDA events on one extra (untimed, eager) training step.  The GPU is first parked on
     # a 40 ms spin so that the whole step is already queued when it starts: event intervals then measure kernels, not the
     # CPU launch path.
@@ -331,6 +376,7 @@ def main():
                         "tc_frac": B * world / (fwd_ms * 1e-3) * GFLOP_FWD_PER_IMG / 1e3 / (pk["tc_sustained"] * world)},
                 "train_tc_frac": ips * GFLOP_TRAIN_PER_IMG / 1e3 / (pk["tc_sustained"] * world),
                 "roofline": roof}
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
             t0 = time.time()
             cpu_ips = cpu_reference_run(40, 1, batch=1)                    # ~8-10 s on 16 cores

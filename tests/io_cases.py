@@ -85,3 +85,18 @@ def check_mean_teacher(device):
     mt.update(1.0)
     for t, b in zip(teacher.parameters(), s0):
         np.testing.assert_allclose(t.detach().cpu().numpy(), (b + 1.0).cpu().numpy(), rtol=1e-6)
+
+
+def check_iou_one_hot(device):
+    """eval/iouEval.py:37-46: [B,C,H,W] one-hot predictions / targets give the same counts as the label maps."""
+    from erfnet_pytorch_b200.iouEval import iouEval
+    g = torch.Generator().manual_seed(8)
+    p = torch.randint(0, 20, (2, 1, 12, 16), generator=g)
+    t = torch.randint(0, 20, (2, 1, 12, 16), generator=g)
+    a, b = iouEval(20), iouEval(20)
+    a.addBatch(p.to(device), t.to(device))
+    hot = lambda v: torch.zeros(2, 20, 12, 16).scatter_(1, v, 1)
+    b.addBatch(hot(p).to(device), hot(t).to(device))
+    assert torch.equal(a.getIoU()[1], b.getIoU()[1]) and torch.equal(a.tp, b.tp) and torch.equal(a.fp, b.fp) and torch.equal(a.fn, b.fn)
+    tp, fp, fn = O.iou_counts(p.numpy(), t.numpy(), 20, 19)
+    assert np.array_equal(b.tp.numpy().astype(np.int64), tp) and np.array_equal(b.fn.numpy().astype(np.int64), fn)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from tests.imagenet_cases import build_imagenet, check_ce_topk, check_imagenet_net
-from tests.io_cases import check_ingest, check_labels, check_mean_teacher, check_model_accepts_uint8
+from tests.io_cases import check_ingest, check_iou_one_hot, check_labels, check_mean_teacher, check_model_accepts_uint8
 from tests.test_host_logic import assert_rel
 
 pytestmark = pytest.mark.gpu
@@ -35,6 +35,10 @@ def test_ingest_labels_colorize():
     check_labels("cuda")
     check_model_accepts_uint8("cuda", "fp32")
     check_model_accepts_uint8("cuda", "bf16")
+
+
+def test_iou_one_hot_inputs():
+    check_iou_one_hot("cuda")
 
 
 def test_mean_teacher():

@@ -256,8 +256,9 @@ def test_imagenet_net_host_logic(golden_dir):
 
 
 def test_io_side_and_mean_teacher_host_logic():
-    from tests.io_cases import check_ingest, check_labels, check_mean_teacher, check_model_accepts_uint8
+    from tests.io_cases import check_ingest, check_iou_one_hot, check_labels, check_mean_teacher, check_model_accepts_uint8
     with emulated_kernels():
+        check_iou_one_hot("cpu")
         check_ingest("cpu")
         check_model_accepts_uint8("cpu")
         check_labels("cpu")
