@@ -97,38 +97,66 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
     const int lag = slots > 2 ? 2 : 1;
     int pend[2] = {-1, -1};
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(p.in);
-    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      // decode this thread's rows once per unit
-      int ry[8], rx[8], rn[8];
+    // Everything that does not depend on the tap is hoisted out of the tap loop: with ONE loader warp per scheduler the gather is bound
+    // by the instruction latency of its address arithmetic (ncu: ~120 SASS instructions per cp.async before this), not by memory.
+    uint32_t dst_off[8];   // shared-memory offset of this thread's chunk of row i inside a ring slot (swizzled), loop invariant
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < iters) {
-          // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod here was the kernel's critical path
-          const unsigned q = (unsigned)u * 128u + (unsigned)(i * rows_per_iter + r0);
-          if (q < (unsigned)total) {
-            const unsigned t2 = q / (unsigned)p.EW;
-            rx[i] = (int)(q - t2 * (unsigned)p.EW);
-            rn[i] = (int)(t2 / (unsigned)p.EH);
-            ry[i] = (int)(t2 - (unsigned)rn[i] * (unsigned)p.EH);
-          } else {
-            rn[i] = -1; ry[i] = rx[i] = 0;
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * rows_per_iter + r0;
+      const int key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
+      dst_off[i] = (uint32_t)(row * RB + ((j ^ key) * 16));
+    }
+    const uint32_t s_a_addr = smem_u32(s_a);
+    const uint32_t kc_stride = 128u * RB;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      // decode this thread's rows once per unit: one division pair for the first row, the others by stepping (rows_per_iter pixels apart)
+      int y0[8], x0[8];                  // input coordinates of tap (0,0); y0 very negative = row outside the enumerated grid
+      const __nv_bfloat16* src0[8];      // address of that pixel's chunk j
+      {
+        // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod here was the kernel's critical path
+        unsigned q = (unsigned)u * 128u + (unsigned)r0;
+        const unsigned t2 = q / (unsigned)p.EW;
+        int x = (int)(q - t2 * (unsigned)p.EW);
+        int n = (int)(t2 / (unsigned)p.EH);
+        int y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < iters) {
+            const bool inside = q < (unsigned)total;
+            y0[i] = inside ? p.in_step * y : -(1 << 28);
+            x0[i] = in_step_x * x;
+            src0[i] = in + (((size_t)n * p.H + (inside ? y0[i] : 0)) * p.W + x0[i]) * p.in_ld + j * 8;
+            q += (unsigned)rows_per_iter;
+            x += rows_per_iter;
+            while (x >= p.EW) {
+              x -= p.EW;
+              if (++y == p.EH) { y = 0; ++n; }
+            }
           }
         }
       }
       for (int t = 0; t < p.ntaps; ++t) {
         mbar_wait(&empty_bar[slot], phase ^ 1);
-        uint8_t* base = s_a + (size_t)slot * slot_bytes;
+        const uint32_t base = s_a_addr + (uint32_t)slot * (uint32_t)slot_bytes;
         const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+        const long long toff = ((long long)dy * p.W + dx) * p.in_ld;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (i < iters) {
-            const int row = i * rows_per_iter + r0;
-            const int iy = p.in_step * ry[i] + dy, ix = in_step_x * rx[i] + dx;
-            const bool ok = rn[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-            const __nv_bfloat16* src = ok ? in + (((size_t)rn[i] * p.H + iy) * p.W + ix) * p.in_ld + j * 8 : in;
-            const int key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
-            uint8_t* dst = base + row * RB + ((j ^ key) * 16);
-            for (int kc = 0; kc < KC; ++kc) cp_async16(dst + kc * (128 * RB), src + (ok ? kc * CH : 0), ok ? 16u : 0u);
+            const bool ok = (unsigned)(y0[i] + dy) < (unsigned)p.H && (unsigned)(x0[i] + dx) < (unsigned)p.W;
+            const __nv_bfloat16* src = ok ? src0[i] + toff : in;
+            const uint32_t nb = ok ? 16u : 0u;
+            uint32_t dst = base + dst_off[i];
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nb) : "memory");
+            if (KC > 1) {
+              const int cstep = ok ? CH : 0;
+#pragma unroll 1
+              for (int kc = 1; kc < KC; ++kc) {
+                dst += kc_stride;
+                src += cstep;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nb) : "memory");
+              }
+            }
           }
         }
         cp_async_commit();
