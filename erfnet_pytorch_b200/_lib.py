@@ -26,7 +26,8 @@ class Im2colDesc(C.Structure):
     _fields_ = ([("in_", C.c_void_p)] + [(n, C.c_int) for n in ("H", "W", "in_ld", "Cin", "EN", "EH", "EW", "in_step", "ntaps")] +
                 [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p)] +
                 [(n, C.c_int) for n in ("Ho", "Wo", "out_ld", "out_c0", "out_step", "out_oy", "out_ox", "NP", "n_valid", "relu", "units",
-                                        "in_step_x", "out_step_x", "bias_period")])
+                                        "in_step_x", "out_step_x", "bias_period")] +
+                [("nchw_out", C.c_void_p), ("nchw_C", C.c_int)])
 
 
 class WgradIm2colDesc(C.Structure):

@@ -37,7 +37,7 @@ __device__ __forceinline__ void bulk_g2s_im(void* smem_dst, const void* gsrc, ui
                : "memory");
 }
 
-template <int NP>
+template <int NP, bool NCHW = false>
 __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf_im2col_desc p, const int slots, const int slot_bytes,
                                                                        const int w_bytes) {
   pdl_trigger();
@@ -227,6 +227,41 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * NP + ((uint32_t)(quad * 32) << 16);
+      if constexpr (NCHW) {
+        // NCHW fp32 output of a row-parity class (N index = b * NP/2 + c): lane = input column x, so the float2 (b = 0, 1) of one channel is
+        // 8 contiguous bytes per lane and 256 contiguous bytes per warp -- the logits never take the NHWC bf16 round trip
+        float* o = nullptr;
+        const size_t plane = (size_t)p.Ho * (size_t)(2 * p.Wo);
+        if (q < (unsigned)total) {
+          const unsigned t2 = q / (unsigned)p.EW;
+          const int x = (int)(q - t2 * (unsigned)p.EW);
+          const int n = (int)(t2 / (unsigned)p.EH), y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
+          o = p.nchw_out + ((size_t)n * p.nchw_C * p.Ho + (size_t)(p.out_step * y + p.out_oy)) * (size_t)(2 * p.Wo) + 2 * x;
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < NP / 2; c0 += 16) {   // 16 channels at a time: columns c0.. of parity 0 and NP/2 + c0.. of parity 1
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr + c0, r0);
+          tmem_ld16(taddr + NP / 2 + c0, r1);
+          tmem_ld_wait();
+          if (o != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (c0 + e < p.nchw_C) {
+                float v0 = __uint_as_float(r0[e]) + s_bias[c0 + e], v1 = __uint_as_float(r1[e]) + s_bias[NP / 2 + c0 + e];
+                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                *reinterpret_cast<float2*>(o + (size_t)(c0 + e) * plane) = make_float2(v0, v1);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll
       for (int c0 = 0; c0 < NP; c0 += 16) {
         uint32_t r[16];
@@ -297,6 +332,9 @@ using namespace erfk;
 
 extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream) {
   ERF_CHECK_ARG(d && d->in && d->out && d->w_img, "erf_conv_im2col_tc: null pointer");
+  ERF_CHECK_ARG(d->nchw_out == nullptr || ((d->NP == 32 || d->NP == 64) && d->out_step == 2 && d->out_step_x == 1 && d->bias_period == d->NP / 2 && d->nchw_C > 0 &&
+                                            d->nchw_C <= d->NP / 2 && d->n_valid == d->NP),
+                "erf_conv_im2col_tc: NCHW output needs the row-parity form with n_split = NP/2 <= 32 and nchw_C <= NP/2");
   ERF_CHECK_ARG(d->Cin >= 16 && d->Cin <= 128 && (d->Cin % 16) == 0 && (d->in_ld % 8) == 0 && d->in_ld >= d->Cin,
                 "erf_conv_im2col_tc: Cin=%d must be a multiple of 16 in [16,128] and in_ld=%d a multiple of 8", d->Cin, d->in_ld);
   ERF_CHECK_ARG(d->NP == 16 || d->NP == 32 || d->NP == 64 || d->NP == 128, "erf_conv_im2col_tc: padded N=%d must be 16, 32, 64 or 128", d->NP);
@@ -324,13 +362,16 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   int grid = p.units < 148 * per_sm ? p.units : 148 * per_sm;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-#define IM_LAUNCH(NP_)                                                                                                  \
-  e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-  if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), p, slots, slot_bytes, w_bytes);
-  if (d->NP == 16) { IM_LAUNCH(16) }
-  else if (d->NP == 32) { IM_LAUNCH(32) }
-  else if (d->NP == 64) { IM_LAUNCH(64) }
-  else { IM_LAUNCH(128) }
+#define IM_LAUNCH(NP_, NCHW_)                                                                                                  \
+  e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_, NCHW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_, NCHW_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), p, slots, slot_bytes, w_bytes);
+  if (d->nchw_out != nullptr) {
+    if (d->NP == 32) { IM_LAUNCH(32, true) } else { IM_LAUNCH(64, true) }
+  }
+  else if (d->NP == 16) { IM_LAUNCH(16, false) }
+  else if (d->NP == 32) { IM_LAUNCH(32, false) }
+  else if (d->NP == 64) { IM_LAUNCH(64, false) }
+  else { IM_LAUNCH(128, false) }
 #undef IM_LAUNCH
   if (e != cudaSuccess) {
     set_error("erf_conv_im2col_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

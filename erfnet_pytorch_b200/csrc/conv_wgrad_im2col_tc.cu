@@ -79,9 +79,40 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
     int stage = 0;
     uint32_t phase = 0;
     int pend = -1;
+    // Loop-invariant part of this thread's copy items, hoisted (same reasoning as conv_im2col_tc.cu: with one loader warp per scheduler the
+    // gather is bound by the instruction latency of its index arithmetic).  Items (tap, row, chunk) are dealt round-robin to the 128 loader
+    // threads; when one tap's items (64 * g_chunks) are a multiple of 128, a thread owns the SAME (row, chunk) pairs in every tap and unit.
+    const int per_tap = kWiPX * g_chunks;
+    const bool fast_g = (per_tap % 128) == 0 && per_tap / 128 <= 8;
+    const int gm = fast_g ? per_tap / 128 : 0;
+    int g_row[8];
+    uint32_t g_dst[8], g_srcoff[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int w = tid + 128 * m, ch = w % g_chunks, row = (w / g_chunks) % kWiPX;
+      const int byte0 = ch * g_chunk, c16 = byte0 / 16, sub = c16 / (CHg / 8), cj = c16 % (CHg / 8);
+      const int key = RBg == 128 ? (row & 7) : ((row >> 2) & 1);
+      g_row[m] = row;
+      g_dst[m] = (uint32_t)(sub * g_sub_bytes + row * RBg + ((cj ^ key) * 16) + (byte0 & 15));
+      g_srcoff[m] = (uint32_t)byte0;
+    }
+    const int dm = d_chunks / 2;                            // dense items per thread: 64 * d_chunks / 128 (d_chunks = 2, 4, 8 or 16)
+    int d_row[8];
+    uint32_t d_dst[8], d_srcoff[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int w = tid + 128 * m, c16 = w % d_chunks, row = (w / d_chunks) % kWiPX;
+      const int sub = c16 / (CHd / 8), cj = c16 % (CHd / 8);
+      const int key = RBd == 128 ? (row & 7) : ((row >> 2) & 1);
+      d_row[m] = row;
+      d_dst[m] = (uint32_t)(dense_off + sub * d_sub_bytes + row * RBd + ((cj ^ key) * 16));
+      d_srcoff[m] = (uint32_t)(c16 * 16);
+    }
+    const uint32_t tap_pitch = (uint32_t)(gsubs * g_sub_bytes);
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* base = smem + (size_t)stage * stage_bytes;
+      const uint32_t base_addr = smem_u32(base);
       // per-unit pixel table (64 rows); the loader group syncs on named barrier 1
       if (tid < kWiPX) {
         const unsigned q = (unsigned)u * (unsigned)kWiPX + (unsigned)tid;   // 32-bit index arithmetic (host-checked range)
@@ -95,31 +126,59 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      // gathered operand: items (tap, row, chunk)
-      const int g_items = p.ntaps * kWiPX * g_chunks;
-      for (int it = tid; it < g_items; it += 128) {
-        const int ch = it % g_chunks, row = (it / g_chunks) % kWiPX, t = it / (g_chunks * kWiPX);
-        const int n = s_row[stage][row][0];
-        const int gy = p.g_step * s_row[stage][row][1] + p.tap_dy[t], gx = p.g_step * s_row[stage][row][2] + p.tap_dx[t];
-        const bool ok = n >= 0 && gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
-        const uint8_t* src = ok ? G + ((((size_t)n * p.GH + gy) * p.GW + gx) * p.g_ld) * 2 + ch * g_chunk : G;
-        // destination: 16-byte chunk index c16 of the pixel row -> sub-tile c16 / (CHg/8), chunk within the sub-tile row
-        const int byte0 = ch * g_chunk, c16 = byte0 / 16, sub = c16 / (CHg / 8), cj = c16 % (CHg / 8);
-        const int key = RBg == 128 ? (row & 7) : ((row >> 2) & 1);
-        uint8_t* dst = base + (t * gsubs + sub) * g_sub_bytes + row * RBg + ((cj ^ key) * 16) + (byte0 & 15);
-        wi_cp_async(dst, src, g_chunk, ok ? (uint32_t)g_chunk : 0u);
+      if (fast_g) {
+        int gy0[8], gx0[8];
+        const uint8_t* gsrc[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          if (m < gm) {
+            const int n = s_row[stage][g_row[m]][0];
+            gy0[m] = n >= 0 ? p.g_step * s_row[stage][g_row[m]][1] : -(1 << 28);
+            gx0[m] = p.g_step * s_row[stage][g_row[m]][2];
+            gsrc[m] = G + ((((size_t)(n >= 0 ? n : 0) * p.GH + (n >= 0 ? gy0[m] : 0)) * p.GW + gx0[m]) * p.g_ld) * 2 + g_srcoff[m];
+          }
+        }
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+          const long long toff = ((long long)dy * p.GW + dx) * p.g_ld * 2;
+          const uint32_t tbase = base_addr + (uint32_t)t * tap_pitch;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            if (m < gm) {
+              const bool ok = (unsigned)(gy0[m] + dy) < (unsigned)p.GH && (unsigned)(gx0[m] + dx) < (unsigned)p.GW;
+              const uint8_t* src = ok ? gsrc[m] + toff : G;
+              if (g_chunk == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tbase + g_dst[m]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+              else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tbase + g_dst[m]), "l"(src), "r"(ok ? 8u : 0u) : "memory");
+            }
+          }
+        }
+      } else {
+        // gathered operand, general form: items (tap, row, chunk)
+        const int g_items = p.ntaps * kWiPX * g_chunks;
+        for (int it = tid; it < g_items; it += 128) {
+          const int ch = it % g_chunks, row = (it / g_chunks) % kWiPX, t = it / (g_chunks * kWiPX);
+          const int n = s_row[stage][row][0];
+          const int gy = p.g_step * s_row[stage][row][1] + p.tap_dy[t], gx = p.g_step * s_row[stage][row][2] + p.tap_dx[t];
+          const bool ok = n >= 0 && gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
+          const uint8_t* src = ok ? G + ((((size_t)n * p.GH + gy) * p.GW + gx) * p.g_ld) * 2 + ch * g_chunk : G;
+          // destination: 16-byte chunk index c16 of the pixel row -> sub-tile c16 / (CHg/8), chunk within the sub-tile row
+          const int byte0 = ch * g_chunk, c16 = byte0 / 16, sub = c16 / (CHg / 8), cj = c16 % (CHg / 8);
+          const int key = RBg == 128 ? (row & 7) : ((row >> 2) & 1);
+          uint8_t* dst = base + (t * gsubs + sub) * g_sub_bytes + row * RBg + ((cj ^ key) * 16) + (byte0 & 15);
+          wi_cp_async(dst, src, g_chunk, ok ? (uint32_t)g_chunk : 0u);
+        }
       }
-      // dense operand: items (row, chunk)
-      const int d_items = kWiPX * d_chunks;
-      for (int it = tid; it < d_items; it += 128) {
-        const int c16 = it % d_chunks, row = it / d_chunks;
-        const int n = s_row[stage][row][0];
-        const bool ok = n >= 0;
-        const uint8_t* src = ok ? D + ((((size_t)n * p.EH + s_row[stage][row][1]) * p.EW + s_row[stage][row][2]) * p.d_ld + p.d_c0) * 2 + c16 * 16 : D;
-        const int sub = c16 / (CHd / 8), cj = c16 % (CHd / 8);
-        const int key = RBd == 128 ? (row & 7) : ((row >> 2) & 1);
-        uint8_t* dst = base + dense_off + sub * d_sub_bytes + row * RBd + ((cj ^ key) * 16);
-        wi_cp_async(dst, src, 16, ok ? 16u : 0u);
+      // dense operand: items (row, chunk), the same (row, chunk) pairs for a thread in every unit
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        if (m < dm) {
+          const int n = s_row[stage][d_row[m]][0];
+          const bool ok = n >= 0;
+          const uint8_t* src = ok ? D + ((((size_t)n * p.EH + s_row[stage][d_row[m]][1]) * p.EW + s_row[stage][d_row[m]][2]) * p.d_ld + p.d_c0) * 2 + d_srcoff[m] : D;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base_addr + d_dst[m]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (pend >= 0) {

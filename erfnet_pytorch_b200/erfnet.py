@@ -232,6 +232,17 @@ class _TcConv:
     def forward(self, x, imgs, bias, relu=False, out=None, out_coff=0):
         return ops.conv_im2col_tc(x, imgs, self.plans()[0], self.spec, bias, relu=relu, out=out, out_coff=out_coff)
 
+    def nchw_ok(self, dtype):
+        return ops.USE_TC and ops.FUSE_NCHW_HEAD and ops.im2col_nchw_supported(self.spec, dtype)
+
+    def nchw_plan(self):
+        if self.__dict__.get("_nchw_plan") is None:
+            self._nchw_plan = ops.im2col_plan_nchw(self.spec)
+        return self._nchw_plan
+
+    def forward_nchw(self, x, imgs, bias, relu=False):
+        return ops.conv_im2col_tc_nchw(x, imgs, self.nchw_plan(), self.spec, bias, relu=relu)
+
     def dgrad(self, dy, w, out_hw):
         plan = self.plans()[1]
         return ops.conv_im2col_tc(dy, ops.im2col_pack(w, self.spec, True, plan), plan, self.dspec, out_hw=out_hw)
@@ -701,6 +712,16 @@ class _PlainConv:
             return self._tc.forward(x, tc, b, relu=self.relu, out=self._out(x, tc=True))
         return ops.conv_fwd(x, w, self.spec, b, relu=self.relu, out=self._out(x))
 
+    def _fwd_eval_nchw(self, x, ctx):
+        """Eval-mode forward whose epilogue writes the NCHW fp32 result directly (caller checked self._tc.nchw_ok)."""
+        sig = (ctx.dtype,) + _sig(self._conv)
+        c = self._conv.__dict__.get("_packed_nchw")
+        if c is None or c[0] != sig:
+            c = (sig, (ops.im2col_pack(self._conv.weight, self.spec, False, self._tc.nchw_plan()), self._conv.bias.detach().float().contiguous()))
+            self._conv.__dict__["_packed_nchw"] = c
+        imgs, b = c[1]
+        return self._tc.forward_nchw(x, imgs, b, relu=self.relu)
+
     def _train_params(self):
         return (self._conv.weight, self._conv.bias)
 
@@ -817,6 +838,16 @@ class ERFNet(_B200Module):
         return self.decoder._nhwc(self.encoder._nhwc(x, ctx), ctx)
 
     def forward(self, input, only_encode=False):
+        if not self.training and not only_encode:
+            # inference: the head's epilogue writes the NCHW fp32 logits itself when it runs on the tensor cores
+            ctx = _Ctx(self._precision(), False)
+            head = _PlainConv(self.decoder.output_conv, ConvSpec(16, self.num_classes, 2, 2, 2, transposed=True))
+            if head._tc.nchw_ok(ctx.dtype) and input.is_cuda:
+                with torch.no_grad():
+                    y = self.encoder._nhwc(input_to_nhwc(input, 4, ctx.dtype), ctx)
+                    for layer in self.decoder.layers:
+                        y = _run(layer, y, ctx)
+                    return head._fwd_eval_nchw(y, ctx)
         y = self.forward_nhwc(input, only_encode)
         return _ToNCHW.apply(y, self.num_classes)
 

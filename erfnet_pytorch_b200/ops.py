@@ -227,6 +227,7 @@ def conv1d_pair_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
 
 
 USE_PAIR = True   # fused 3x1 -> ReLU -> 1x3 pairs in eval mode (C = 16 / 64)
+FUSE_NCHW_HEAD = True   # inference: the decoder head writes the NCHW fp32 logits from its epilogue (no NHWC logits, no layout pass)
 
 
 def conv1d_pair_tc(x, w1_img, b1, w2_img, b2, dil, relu=True, res=None):
@@ -340,11 +341,12 @@ def im2col_plan(spec_g: ConvSpec, row_parity: Optional[bool] = None):
     return plan
 
 
-def _im2col_plan_row_parity(spec_g: ConvSpec):
+def _im2col_plan_row_parity(spec_g: ConvSpec, split: Optional[int] = None):
     """Stride-2 transposed gather in row-parity form: one class per output row parity a; its N axis is (b, c) = (column parity,
     channel), so pixel (y, x) of the input grid writes the 2*cout8 contiguous values of output row 2y+a at columns 2x, 2x+1.
-    A tap is an input offset (dy, dx) plus, per column parity, the kernel element that multiplies it (None = no contribution)."""
-    c8 = round_up(spec_g.cout, 8)
+    A tap is an input offset (dy, dx) plus, per column parity, the kernel element that multiplies it (None = no contribution).
+    split: N offset of column parity 1 (default round8(cout); the NCHW epilogue wants a power of two = NP / 2)."""
+    c8 = round_up(spec_g.cout, 8) if split is None else split
     plan = []
     for a in range(2):
         taps = {}
@@ -444,6 +446,46 @@ def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional
                 d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo, out.shape[-1], out_coff + e["n0"]
                 d.out_step, d.out_oy, d.out_ox = e["out_step"], e["oy"], e["ox"]
             d.NP, d.n_valid, d.relu = e["NP"], e["n_valid"], int(relu)
+            check(L.erf_conv_im2col_tc(C.byref(d), _stream(x)))
+            _count()
+    return out
+
+
+def im2col_nchw_supported(spec_g: ConvSpec, dtype) -> bool:
+    """The fused NCHW fp32 epilogue: stride-2 transposed convs in row-parity form whose two column parities fit N <= 64."""
+    return (im2col_supported(spec_g, dtype) and spec_g.transposed and spec_g.stride == 2 and spec_g.cout <= 32
+            and len(_im2col_plan_row_parity(spec_g, split=32 if spec_g.cout > 16 else 16)) == 2)
+
+
+def im2col_plan_nchw(spec_g: ConvSpec):
+    return _im2col_plan_row_parity(spec_g, split=32 if spec_g.cout > 16 else 16)
+
+
+def conv_im2col_tc_nchw(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional[torch.Tensor] = None, relu=False) -> torch.Tensor:
+    """Like conv_im2col_tc for a plan of im2col_plan_nchw, but the epilogue writes the reference's NCHW fp32 tensor [N,cout,Ho,Wo] directly
+    (no NHWC bf16 logits, no layout pass): what eval/erfnet.py:132 returns."""
+    n, h, w, ld = x.shape
+    ho, wo = spec_g.out_hw(h, w)
+    out = torch.empty(n, spec_g.cout, ho, wo, device=x.device, dtype=torch.float32)
+    split = plan[0]["merged"]
+    if bias is not None:
+        bias = torch.nn.functional.pad(bias.float()[:spec_g.cout], (0, split - spec_g.cout)).contiguous()
+    L = _lib.lib()
+    with _timed("conv_im2col_tc_kernel", conv_flops(spec_g, n, ho, wo)):
+        for e, img in zip(plan, imgs):
+            d = _lib.Im2colDesc()
+            d.in_, d.H, d.W, d.in_ld, d.Cin = x.data_ptr(), h, w, ld, round_up(spec_g.cin, 16)
+            d.EN, d.EH, d.EW, d.in_step = n, ho // 2, wo // 2, 1
+            d.ntaps = len(e["taps"])
+            for i, (_, _, dy, dx) in enumerate(e["taps"]):
+                d.tap_dy[i], d.tap_dx[i] = dy, dx
+            d.w_img = img.data_ptr()
+            d.bias = None if bias is None else bias.data_ptr()
+            d.bias_period = split
+            d.out, d.Ho, d.Wo, d.out_ld, d.out_c0 = out.data_ptr(), ho, wo // 2, 2 * split, 0
+            d.out_step, d.out_step_x, d.out_oy, d.out_ox = 2, 1, e["oy"], 0
+            d.NP, d.n_valid, d.relu = e["NP"], e["NP"], int(relu)
+            d.nchw_out, d.nchw_C = out.data_ptr(), spec_g.cout
             check(L.erf_conv_im2col_tc(C.byref(d), _stream(x)))
             _count()
     return out

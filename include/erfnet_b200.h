@@ -259,6 +259,9 @@ typedef struct {
   int units;                                        /* filled in by the library */
   int in_step_x, out_step_x;                        /* 0: same as in_step / out_step; else the column step differs from the row step */
   int bias_period;                                  /* 0: bias[n]; else bias[(out_c0 + n) % bias_period] (column-folded outputs) */
+  float* nchw_out; int nchw_C;                      /* non-NULL (row-parity form with n_split = NP/2 <= 32 only): the epilogue writes the reference's
+                                                     * NCHW fp32 tensor [EN][nchw_C][Ho][2*Wo] directly -- value pairs (b = 0, 1) of channel c as one
+                                                     * float2 at columns 2x, 2x+1 -- instead of the NHWC tensor `out` (eval/erfnet.py:132 returns NCHW) */
 } erf_im2col_desc;
 /* Row-parity form of a stride-2 transposed conv: the two column parities b of an output row are folded into N (n = b*n_split + c),
  * the output is addressed as [N][Ho][Wo/2][2*ld] with out_step = 2 (rows) and out_step_x = 1, so each launch writes whole rows.

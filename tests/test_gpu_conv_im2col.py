@@ -115,3 +115,36 @@ def test_channel_sum_padded_24():
     out = torch.zeros(24, device="cuda")
     ops.channel_sum_slice(x, 24, out)
     np.testing.assert_allclose(out.cpu().numpy(), x.float().sum((0, 1, 2)).cpu().numpy(), rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 256), (1, 3, 40, 72), (3, 3, 8, 8)])
+def test_fused_nchw_head_matches_the_two_pass_form(shape):
+    """Inference: the decoder head writes the NCHW fp32 logits from its epilogue.  Against the NHWC bf16 head + layout kernel it differs only by
+    the bf16 rounding of the logits it no longer performs; against the fp32 check mode it is within the bf16 gate."""
+    from erfnet_pytorch_b200 import erfnet as E
+    from oracle import erfnet_oracle as O
+    m = E.ERFNet(20)
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 3))
+    m = m.cuda().eval()
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(12)).cuda()
+    l0 = ops.LAUNCHES
+    with torch.no_grad():
+        fused = m(x)
+    n_fused = ops.LAUNCHES - l0
+    ops.FUSE_NCHW_HEAD = False
+    try:
+        l0 = ops.LAUNCHES
+        with torch.no_grad():
+            two_pass = m(x)
+        n_two = ops.LAUNCHES - l0
+    finally:
+        ops.FUSE_NCHW_HEAD = True
+    assert fused.shape == two_pass.shape == (shape[0], 20, shape[2], shape[3]) and fused.dtype == torch.float32
+    assert n_fused == n_two - 1                                            # the layout pass is gone
+    scale = two_pass.abs().max().item()
+    assert (fused - two_pass).abs().max().item() <= 2.0 ** -8 * scale      # one bf16 rounding of the logits
+    assert (fused - two_pass).abs().max().item() > 0                       # ... and it really is a different (more exact) path
+    m.precision = "fp32"
+    with torch.no_grad():
+        ref = m(x)
+    assert (fused - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
