@@ -47,6 +47,7 @@ _SIGNATURES = {
     "erf_conv_wgrad": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _vp],
     "erf_conv_wgrad_torch": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _i, _vp],
     "erf_stem_fwd": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
+    "erf_stem_fwd_nchw": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
     "erf_stem_wgrad": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "erf_maxpool2x2_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp],
     "erf_maxpool2x2_bwd": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp],

@@ -27,8 +27,13 @@ template <> struct Px4<float> {
   }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+// Two adjacent output pixels (A = 2j, B = 2j+1 of an output row) per thread: their 3x3 stride-2 windows share input column 4j+1, the
+// weights are fetched from shared memory once for both, and the 13 conv channels are accumulated as 6 packed fp32 pairs (FFMA2) + 1 scalar
+// per pixel -- the kernel is FMA-issue bound, not bandwidth bound (27 x 13 MACs for 32 output bytes).  The accumulation order per channel
+// is bias, then (ky, kx, ci) ascending, as in a plain loop.
+// NCHW_IN: x is the caller's NCHW fp32 tensor [N][3][H][W] (inference: no separate layout pass); otherwise NHWC [N][H][W][4] of type T.
+template <typename T, bool NCHW_IN, bool STATS>
+__global__ void __launch_bounds__(256, 2) stem_fwd_kernel(const void* __restrict__ xin, int N, int H, int W, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu, T* __restrict__ y, double* __restrict__ stats) {
   pdl_enter();
@@ -45,64 +50,111 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, 
     s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
   }
   __syncthreads();
-  const int Ho = H / 2, Wo = W / 2;
-  const unsigned total = (unsigned)N * (unsigned)Ho * (unsigned)Wo;   // host-checked < 2^31: 32-bit index arithmetic
+  const int Ho = H / 2, Wp = W / 4;                                   // Wp = output pixel pairs per row
+  const unsigned total = (unsigned)N * (unsigned)Ho * (unsigned)Wp;   // host-checked < 2^31: 32-bit index arithmetic
   float st_sum[STEM_C], st_sq[STEM_C];
 #pragma unroll
   for (int c = 0; c < STEM_C; ++c) st_sum[c] = st_sq[c] = 0.f;
   for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
-    const unsigned t2 = p / (unsigned)Wo;
-    const int ox = (int)(p - t2 * (unsigned)Wo);
+    const unsigned t2 = p / (unsigned)Wp;
+    const int j = (int)(p - t2 * (unsigned)Wp);
     const int n = (int)(t2 / (unsigned)Ho), oy = (int)(t2 - (unsigned)n * (unsigned)Ho);
-    float acc[STEM_C];
+    float2 accA[6], accB[6];
 #pragma unroll
-    for (int c = 0; c < STEM_C; ++c) acc[c] = s_b[c];
-    float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
+    for (int q = 0; q < 6; ++q) accA[q] = accB[q] = make_float2(s_b[2 * q], s_b[2 * q + 1]);
+    float a12 = s_b[12], b12 = s_b[12];
+    float mxA[3] = {-INFINITY, -INFINITY, -INFINITY}, mxB[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1   // one input row at a time: keeps the 27 x 13 weights out of the register file (they stream from shared memory)
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy - 1 + ky;
+      const bool row_ok = iy >= 0;                 // with even H, W and padding 1 only the top row and the left column fall outside
+      float v[5][3];                               // input columns 4j-1 .. 4j+3, channels 0..2
+      if (NCHW_IN) {
+        const float* x = reinterpret_cast<const float*>(xin);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* r = x + (((size_t)n * 3 + c) * H + (row_ok ? iy : 0)) * W + 4 * j;
+          float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float l = 0.f;
+          if (row_ok) {
+            q4 = *reinterpret_cast<const float4*>(r);
+            if (j > 0) l = r[-1];
+          }
+          v[0][c] = l; v[1][c] = q4.x; v[2][c] = q4.y; v[3][c] = q4.z; v[4][c] = q4.w;
+        }
+      } else {
+        const T* r = reinterpret_cast<const T*>(xin) + (((size_t)n * H + (row_ok ? iy : 0)) * W + 4 * j) * 4;
+#pragma unroll
+        for (int col = 0; col < 5; ++col) {
+          float f[4] = {0.f, 0.f, 0.f, 0.f};
+          if (row_ok && (col > 0 || j > 0)) Px4<T>::load(r + (col - 1) * 4, f);
+          v[col][0] = f[0]; v[col][1] = f[1]; v[col][2] = f[2];
+        }
+      }
+      if (ky >= 1) {   // the 2x2 pooling windows: A = columns 4j, 4j+1 (v[1], v[2]); B = columns 4j+2, 4j+3 (v[3], v[4]); always inside
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          mxA[c] = fmaxf(mxA[c], fmaxf(v[1][c], v[2][c]));
+          mxB[c] = fmaxf(mxB[c], fmaxf(v[3][c], v[4][c]));
+        }
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox - 1 + kx;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) Px4<T>::load(x + (((size_t)n * H + iy) * W + ix) * 4, v);
-        if (ky >= 1 && kx >= 1) {   // the 2x2 pooling window = taps (1..2, 1..2), always inside the image
+        const float* wt = s_w + (ky * 3 + kx) * STEM_CI * STEM_C;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) mx[c] = fmaxf(mx[c], v[c]);
-        }
-        const float4* wt = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * STEM_CI * STEM_C);
+        for (int ci = 0; ci < STEM_CI; ++ci) {
+          const float va = v[kx][ci], vb = v[kx + 2][ci];     // A reads column 4j-1+kx, B column 4j+1+kx
+          const float2 va2 = make_float2(va, va), vb2 = make_float2(vb, vb);
+          const float4* w4p = reinterpret_cast<const float4*>(wt + ci * STEM_C);
 #pragma unroll
-        for (int ci = 0; ci < STEM_CI; ++ci)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 w4 = wt[ci * 4 + q];
-            acc[4 * q] += v[ci] * w4.x; acc[4 * q + 1] += v[ci] * w4.y; acc[4 * q + 2] += v[ci] * w4.z; acc[4 * q + 3] += v[ci] * w4.w;
+          for (int q = 0; q < 3; ++q) {
+            const float4 w4 = w4p[q];
+            accA[2 * q] = __ffma2_rn(va2, make_float2(w4.x, w4.y), accA[2 * q]);
+            accA[2 * q + 1] = __ffma2_rn(va2, make_float2(w4.z, w4.w), accA[2 * q + 1]);
+            accB[2 * q] = __ffma2_rn(vb2, make_float2(w4.x, w4.y), accB[2 * q]);
+            accB[2 * q + 1] = __ffma2_rn(vb2, make_float2(w4.z, w4.w), accB[2 * q + 1]);
           }
+          const float w12 = wt[ci * STEM_C + 12];
+          a12 = fmaf(va, w12, a12);
+          b12 = fmaf(vb, w12, b12);
+        }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) acc[STEM_CO + c] = mx[c];
     // round to the storage type first: statistics and the affine epilogue see the values as stored
-    __align__(16) T o[STEM_C];
 #pragma unroll
-    for (int c = 0; c < STEM_C; ++c) {
-      float f = acc[c] * s_sc[c] + s_sh[c];
-      if (relu) f = fmaxf(f, 0.f);
-      o[c] = from_f<T>(f);
-      const float r = to_f(o[c]);
-      st_sum[c] += r;
-      st_sq[c] += r * r;
-    }
-    T* dst = y + (size_t)p * STEM_C;
-    if (sizeof(T) == 2) {
-      reinterpret_cast<uint4*>(dst)[0] = *reinterpret_cast<const uint4*>(&o[0]);
-      reinterpret_cast<uint4*>(dst)[1] = *reinterpret_cast<const uint4*>(&o[8]);
-    } else {
+    for (int px = 0; px < 2; ++px) {
+      float acc[STEM_C];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(&o[4 * q]);
+      for (int q = 0; q < 6; ++q) {
+        acc[2 * q] = px ? accB[q].x : accA[q].x;
+        acc[2 * q + 1] = px ? accB[q].y : accA[q].y;
+      }
+      acc[12] = px ? b12 : a12;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[STEM_CO + c] = px ? mxB[c] : mxA[c];
+      __align__(16) T o[STEM_C];
+#pragma unroll
+      for (int c = 0; c < STEM_C; ++c) {
+        float f = acc[c] * s_sc[c] + s_sh[c];
+        if (relu) f = fmaxf(f, 0.f);
+        o[c] = from_f<T>(f);
+        if (STATS) {
+          const float r = to_f(o[c]);
+          st_sum[c] += r;
+          st_sq[c] += r * r;
+        }
+      }
+      T* dst = y + ((size_t)p * 2 + px) * STEM_C;      // output pixel index = (n*Ho + oy)*Wo + 2j + px = 2p + px
+      if (sizeof(T) == 2) {
+        reinterpret_cast<uint4*>(dst)[0] = *reinterpret_cast<const uint4*>(&o[0]);
+        reinterpret_cast<uint4*>(dst)[1] = *reinterpret_cast<const uint4*>(&o[8]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(&o[4 * q]);
+      }
     }
   }
-  if (stats) {
+  if (STATS) {
 #pragma unroll
     for (int c = 0; c < STEM_C; ++c) {
       st_sum[c] = warp_sum(st_sum[c]);
@@ -200,22 +252,41 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x
 
 using namespace erfk;
 
+static int stem_fwd_launch(const void* x, bool nchw_in, int N, int H, int W, const float* w, const float* bias, const float* scale,
+                           const float* shift, int relu, void* y, double* stats, int dtype, erf_stream_t stream, const char* name) {
+  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "%s: bad dtype %d", name, dtype);
+  ERF_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 4) == 0, "%s: bad arguments (H must be even, W a multiple of 4)", name);
+  ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "%s: scale and shift must be given together", name);
+  ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "%s: tensors must be 16-byte aligned", name);
+  const long long total = (long long)N * (H / 2) * (W / 4);
+  ERF_CHECK_ARG(total * 2 < 0x7fffffffLL, "%s: %lld output pixels exceed the 32-bit index range", name, total * 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  const dim3 g((unsigned)blocks), b(256);
+#define STEM_LAUNCH(T_, IN_, ST_) launch_pdl(stem_fwd_kernel<T_, IN_, ST_>, g, b, 0, s, x, N, H, W, w, bias, scale, shift, relu, (T_*)y, stats)
+#define STEM_DISPATCH(T_)                                                    \
+  if (nchw_in) { if (stats) STEM_LAUNCH(T_, true, true); else STEM_LAUNCH(T_, true, false); } \
+  else { if (stats) STEM_LAUNCH(T_, false, true); else STEM_LAUNCH(T_, false, false); }
+  if (dtype == ERF_F32) { STEM_DISPATCH(float) } else { STEM_DISPATCH(__nv_bfloat16) }
+#undef STEM_DISPATCH
+#undef STEM_LAUNCH
+  return ERF_OK;
+}
+
 extern "C" int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
                             int relu, void* y, double* stats, int dtype, erf_stream_t stream) {
-  ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_stem_fwd: bad dtype %d", dtype);
-  ERF_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0, "erf_stem_fwd: bad arguments (H, W must be even)");
-  ERF_CHECK_ARG((scale == nullptr) == (shift == nullptr), "erf_stem_fwd: scale and shift must be given together");
-  ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "erf_stem_fwd: tensors must be 16-byte aligned");
-  const long long total = (long long)N * (H / 2) * (W / 2);
-  ERF_CHECK_ARG(total < 0x7fffffffLL, "erf_stem_fwd: %lld output pixels exceed the 32-bit index range", total);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 6) blocks = 148 * 6;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == ERF_F32)
-    launch_pdl(stem_fwd_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)(s), (const float*)x, N, H, W, w, bias, scale, shift, relu, (float*)y, stats);
-  else
-    launch_pdl(stem_fwd_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)(s), (const __nv_bfloat16*)x, N, H, W, w, bias, scale, shift, relu, (__nv_bfloat16*)y, stats);
+  const int rc = stem_fwd_launch(x, false, N, H, W, w, bias, scale, shift, relu, y, stats, dtype, stream, "erf_stem_fwd");
+  if (rc != ERF_OK) return rc;
   ERF_CHECK_LAUNCH("erf_stem_fwd");
+  return ERF_OK;
+}
+
+extern "C" int erf_stem_fwd_nchw(const float* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
+                                 int relu, void* y, double* stats, int dtype, erf_stream_t stream) {
+  const int rc = stem_fwd_launch(x, true, N, H, W, w, bias, scale, shift, relu, y, stats, dtype, stream, "erf_stem_fwd_nchw");
+  if (rc != ERF_OK) return rc;
+  ERF_CHECK_LAUNCH("erf_stem_fwd_nchw");
   return ERF_OK;
 }
 

@@ -335,6 +335,11 @@ class DownsamplerBlock(_B200Module):
         ops.maxpool_fwd(x, self.ninput, y, self.noutput - self.ninput, pk["ps"], pk["psh"], relu=True)
         return y
 
+    def _fwd_eval_nchw(self, input, ctx):
+        """Eval-mode stem straight from the NCHW fp32 image (caller checked ops.stem_nchw_supported and that this is the 3 -> 16 block)."""
+        pk = self._cache(ctx.dtype)
+        return ops.stem_fwd_nchw(input, pk["stem_w"], pk["b"], pk.get("stem_sc"), pk.get("stem_sh"), True, ctx.dtype)
+
     def _train_params(self):
         return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
 
@@ -774,20 +779,34 @@ class Encoder(_B200Module):
         self.num_classes = num_classes
         self._in_ld = 4
 
-    def _nhwc(self, x, ctx, predict=False):
-        if x.shape[1] % 8 or x.shape[2] % 8:
-            raise RuntimeError(f"ERFNet: H and W must be multiples of 8, got {x.shape[1]}x{x.shape[2]} (SURVEY D8)")
-        y = _run(self.initial_block, x, ctx)
+    def _nhwc(self, x, ctx, predict=False, skip_stem=False):
+        if not skip_stem:
+            if x.shape[1] % 8 or x.shape[2] % 8:
+                raise RuntimeError(f"ERFNet: H and W must be multiples of 8, got {x.shape[1]}x{x.shape[2]} (SURVEY D8)")
+            y = _run(self.initial_block, x, ctx)
+        else:
+            y = x
         for layer in self.layers:
             y = _run(layer, y, ctx)
         if predict:
             y = _run(_PlainConv(self.output_conv, ConvSpec(128, self.num_classes, 1, 1)), y, ctx)
         return y
 
+    def _from_input(self, input, ctx, predict=False):
+        """Public-boundary input (NCHW fp32, or uint8 HWC) -> encoder output (NHWC).  In inference the stem reads an NCHW fp32 image itself."""
+        ib = self.initial_block
+        if (not ctx.training and input.dtype == torch.float32 and ops.stem_nchw_supported(input) and ib.ninput == 3 and ib.noutput == 16
+                and input.shape[3] <= 4096):
+            if input.shape[2] % 8 or input.shape[3] % 8:
+                raise RuntimeError(f"ERFNet: H and W must be multiples of 8, got {input.shape[2]}x{input.shape[3]} (SURVEY D8)")
+            with torch.no_grad():
+                y = ib._fwd_eval_nchw(input, ctx)
+            return self._nhwc(y, ctx, predict, skip_stem=True)
+        return self._nhwc(input_to_nhwc(input, 4, ctx.dtype), ctx, predict)
+
     def forward(self, input, predict=False):
         ctx = _Ctx(self._precision(), self.training)
-        x = _ToNHWC.apply(input, 4, ctx.dtype)
-        y = self._nhwc(x, ctx, predict)
+        y = self._from_input(input, ctx, predict)
         return _ToNCHW.apply(y, self.num_classes if predict else 128)
 
 
@@ -832,10 +851,18 @@ class ERFNet(_B200Module):
         ctx = _Ctx(self._precision(), self.training, drop_scales)
         if self.training and drop_scales is None and _FIXED_DROPOUT is None and input.is_cuda and not ops.EMULATED:
             ctx.drawn = draw_dropout(self, input.shape[0], input.device)
-        x = input_to_nhwc(input, 4, ctx.dtype)
         if only_encode:
-            return self.encoder._nhwc(x, ctx, predict=True)
-        return self.decoder._nhwc(self.encoder._nhwc(x, ctx), ctx)
+            return self._encode(input, ctx, predict=True)
+        return self.decoder._nhwc(self._encode(input, ctx), ctx)
+
+    def _encode(self, input, ctx, predict=False):
+        """Encoder pass from the public-boundary input; also serves a foreign encoder handed to the constructor, e.g. the ImageNet
+        pre-trained ``features.encoder`` (train/main.py:857-867), which has no prediction conv."""
+        enc = self.encoder
+        if hasattr(enc, "_from_input"):
+            return enc._from_input(input, ctx, predict)
+        x = input_to_nhwc(input, 4, ctx.dtype)
+        return enc._nhwc(x, ctx, True) if predict else enc._nhwc(x, ctx)
 
     def forward(self, input, only_encode=False):
         if not self.training and not only_encode:
@@ -844,7 +871,7 @@ class ERFNet(_B200Module):
             head = _PlainConv(self.decoder.output_conv, ConvSpec(16, self.num_classes, 2, 2, 2, transposed=True))
             if head._tc.nchw_ok(ctx.dtype) and input.is_cuda:
                 with torch.no_grad():
-                    y = self.encoder._nhwc(input_to_nhwc(input, 4, ctx.dtype), ctx)
+                    y = self._encode(input, ctx)
                     for layer in self.decoder.layers:
                         y = _run(layer, y, ctx)
                     return head._fwd_eval_nchw(y, ctx)

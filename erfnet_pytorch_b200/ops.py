@@ -642,6 +642,25 @@ def stem_fwd(x, w, bias, scale=None, shift=None, relu=False, stats=None):
     return y
 
 
+STEM_NCHW = True   # inference: the stem reads the caller's NCHW fp32 image directly (no layout pass)
+
+
+def stem_nchw_supported(x: torch.Tensor) -> bool:
+    return (STEM_NCHW and not EMULATED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 2 == 0
+            and x.shape[3] % 4 == 0)
+
+
+def stem_fwd_nchw(x, w, bias, scale, shift, relu, dtype):
+    """DownsamplerBlock(3, 16) forward straight from the NCHW fp32 image x [N,3,H,W] -> NHWC y [N,H/2,W/2,16] of `dtype`."""
+    n, _, h, wd = x.shape
+    x = x.contiguous()
+    y = torch.empty(n, h // 2, wd // 2, 16, device=x.device, dtype=dtype)
+    with _timed("stem_fwd", 2.0 * n * (h // 2) * (wd // 2) * 13 * 27):
+        check(_lib.lib().erf_stem_fwd_nchw(_p(x), n, h, wd, _p(w), _p(bias), _p(scale), _p(shift), int(relu), _p(y), None, dt(y), _stream(x)))
+    _count()
+    return y
+
+
 def stem_wgrad(x, dy, dw_out=None, db_out=None, want_bias=True):
     """(dw [13,3,3,3], db [13] or None), ACCUMULATED into dw_out / db_out when given."""
     n, h, wd, _ = x.shape

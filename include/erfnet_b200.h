@@ -86,6 +86,9 @@ int erf_conv_wgrad_torch(const void* in, const void* dout, float* dw, float* db,
  * w: torch layout [13][3][3][3] fp32.  CUDA-core kernels: K = 27 fits no tensor-core shape and the block is bandwidth-bound. */
 int erf_stem_fwd(const void* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
                  int relu, void* y, double* stats, int dtype, erf_stream_t stream);
+/* The same block reading the caller's NCHW fp32 image [N][3][H][W] directly (inference: no separate layout pass); y has element type dtype. */
+int erf_stem_fwd_nchw(const float* x, int N, int H, int W, const float* w, const float* bias, const float* scale, const float* shift,
+                      int relu, void* y, double* stats, int dtype, erf_stream_t stream);
 /* dw[13][3][3][3] += conv weight gradient from x and dy (the 16-channel gradient of y; channels 13..15 are ignored);
  * db[13] += per-channel sum of dy (NULL to skip). */
 int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W, float* dw, float* db, int dtype, erf_stream_t stream);

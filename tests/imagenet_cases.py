@@ -79,3 +79,16 @@ def check_lr_schedule():
     assert o.param_groups[0] == {"lr": 0.1, "weight_decay": 1e-4}
     EI.adjust_learning_rate(o, 20, 0.1)
     assert abs(o.param_groups[0]["lr"] - 0.1 * 0.95 ** 5) < 1e-12 and o.param_groups[0]["weight_decay"] == 0
+
+
+def check_pretrained_encoder_handoff(device):
+    """train/main.py:857-867: the ImageNet net's ``features.encoder`` becomes the encoder of the segmentation net."""
+    from erfnet_pytorch_b200 import erfnet as E
+    im = build_imagenet(device)
+    seg = E.ERFNet(20, encoder=im.features.encoder).to(device)
+    seg.precision = "fp32"
+    assert seg.encoder is im.features.encoder
+    seg.eval()
+    with torch.no_grad():
+        y = seg(torch.rand(1, 3, 32, 64, generator=torch.Generator().manual_seed(2)).to(device))
+    assert y.shape == (1, 20, 32, 64) and bool(torch.isfinite(y).all())

@@ -336,3 +336,24 @@ def test_full_resolution_forward_and_iou_config5():
     np.testing.assert_array_equal(ev.tp.cpu().numpy().astype(np.int64), tp)
     np.testing.assert_array_equal(ev.fp.cpu().numpy().astype(np.int64), fp)
     np.testing.assert_array_equal(ev.fn.cpu().numpy().astype(np.int64), fn)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 3, 8, 8), (1, 3, 40, 24)])
+def test_stem_from_nchw_matches_the_layout_pass(shape):
+    """Inference: the stem reads the NCHW fp32 image itself.  In fp32 check mode the result is bit-identical to layout pass + NHWC stem
+    (same arithmetic order); in bf16 it skips the bf16 rounding of the input pixels, so it is compared within the bf16 gate."""
+    m = E.ERFNet(20)
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 4))
+    m = m.cuda().eval()
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(13)).cuda()
+    for precision in ("fp32", "bf16"):
+        m.precision = precision
+        ctx = E._Ctx(precision, False)
+        with torch.no_grad():
+            a = m.encoder.initial_block._fwd_eval_nchw(x, ctx)
+            b = m.encoder.initial_block._fwd_eval(E.input_to_nhwc(x, 4, ctx.dtype), ctx)
+        assert a.shape == b.shape == (shape[0], shape[2] // 2, shape[3] // 2, 16) and a.dtype == b.dtype
+        if precision == "fp32":
+            assert torch.equal(a, b)
+        else:
+            assert (a.float() - b.float()).abs().max().item() <= 2e-2 * b.float().abs().max().item()

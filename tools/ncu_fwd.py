@@ -12,7 +12,8 @@ from oracle import erfnet_oracle as O  # noqa: E402
 model = E.ERFNet(NC)
 model.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), 0))
 model = model.cuda().eval()
-x, _ = synth_batch(torch, 0, 6)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+x, _ = synth_batch(torch, 0, B)
 x = x.cuda()
 for _ in range(3):
     with torch.no_grad():
