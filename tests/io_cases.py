@@ -27,7 +27,8 @@ def check_ingest(device):
 
 
 def check_model_accepts_uint8(device, precision="fp32"):
-    """model(uint8 HWC batch) == model(ToTensor(batch)) bit for bit."""
+    """model(uint8 HWC batch) == model(ToTensor(batch)): bit for bit in fp32 check mode; in bf16 the float path's stem reads the fp32
+    pixels while the ingest kernel stores bf16 pixels, so the two agree within the bf16 gate."""
     m = E.ERFNet(20)
     m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 0))
     m.precision = precision
@@ -36,7 +37,10 @@ def check_model_accepts_uint8(device, precision="fp32"):
     with torch.no_grad():
         a = m(img.to(device))
         b = m(img.permute(0, 3, 1, 2).float().div(255).to(device))
-    assert torch.equal(a, b)
+    if precision == "fp32":
+        assert torch.equal(a, b)
+    else:
+        assert (a - b).abs().max().item() <= 2e-2 * b.abs().max().item()
 
 
 def check_labels(device):
