@@ -347,6 +347,13 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   const int slot_bytes = KC * 128 * RB;
   int slots = (200 * 1024 - w_pad) / slot_bytes;
   if (slots > kImMaxSlots) slots = kImMaxSlots;
+  {
+    // two CTAs per SM (twice the gathers in flight, epilogue of one unit under the gather of another) whenever a ring of >= 3 slots fits in
+    // half of the shared memory; ERF_IM2COL_2CTA=0 keeps the deep single-CTA ring
+    static const bool two = !(getenv("ERF_IM2COL_2CTA") && atoi(getenv("ERF_IM2COL_2CTA")) == 0);
+    const int half = (100 * 1024 - 1024 - w_pad) / slot_bytes;
+    if (two && 2 * d->NP <= 128 && half >= 3 && half < slots) slots = half;
+  }
   if (slots < 2) {
     set_error("erf_conv_im2col_tc: %d taps x N=%d x Cin=%d of weights do not fit in shared memory; split the class", d->ntaps, d->NP, d->Cin);
     return ERF_ERR_UNSUPPORTED;
