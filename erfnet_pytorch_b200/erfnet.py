@@ -59,7 +59,10 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         dx, grads = ctx.block._bwd(dy.contiguous(), ctx.saved, ctx.needs_input_grad[2])
-        ctx.saved = None
+        if _GRAD_SINK is not None:
+            ctx.saved = None      # the flat trainer runs exactly one backward per forward: release the activations block by block.  Plain
+                                  # autograd use keeps them until the graph dies, so backward(retain_graph=True) + a second backward
+                                  # (train/main.py:375-379, mean teacher) works
         return (None, None, dx) + tuple(grads)
 
 

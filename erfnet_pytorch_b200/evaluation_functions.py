@@ -17,8 +17,7 @@ class _CEFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, go):
-        d = ctx.dlog
-        ctx.dlog = None
+        d = ctx.dlog          # kept on the node: a second backward through a retained graph reuses it
         return d * go.to(d.dtype), None, None, None, None, None
 
 

@@ -189,6 +189,7 @@ def main():
     ladder_net(os.path.join(OUT, "ladder_net.npz"))
     fork_nets(os.path.join(OUT, "fork_nets.npz"))
     imagenet_net(os.path.join(OUT, "imagenet_net.npz"))
+    mean_teacher(os.path.join(OUT, "mean_teacher.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -460,6 +461,65 @@ def topk_kat_inputs():
     for i in range(0, 64, 3):          # every third row: make the target one of the top-6 classes
         tg[i] = order[i, (i // 3) % 6]
     return lg, tg
+
+
+def mean_teacher_inputs():
+    x1 = golden_input((1, 3, 64, 128), 101)
+    x2 = (x1 + 0.05 * (golden_input((1, 3, 64, 128), 102) - 0.5)).clamp(0, 1)     # the second augmentation of the same frame
+    tgt = golden_input((1, 64, 128), 103) * 2.0
+    tgt[golden_input((1, 64, 128), 104) < 0.6] = -1.0
+    return x1, x2, tgt
+
+
+def mean_teacher_step(student, teacher, ev, opt, x1, x2, tgt, consistency_weight, update_teacher):
+    """One iteration of train/main.py:297-392 with --mean-teacher on a regression net (l.350-381): student on images1, teacher on images2,
+    L1LossMasked on both, MSELossWeighted consistency, consistency.backward(retain_graph) + prediction.backward, optimizer.step, teacher update."""
+    out_s = student(x1)
+    opt.zero_grad()
+    out_t = teacher(x2)
+    loss_c = ev.MSELossWeighted(3.0)(out_s, out_t, consistency_weight)
+    loss_s = ev.L1LossMasked()(out_s, tgt)
+    loss_t = ev.L1LossMasked()(out_t, tgt)
+    loss_c.backward(retain_graph=True)
+    loss_s.backward()
+    opt.step()
+    update_teacher(0.01)                                    # DISCOUNT_RATE_START, train/main.py:48
+    return float(loss_s.detach()), float(loss_t.detach()), float(loss_c.detach())
+
+
+def mean_teacher(path):
+    """Three mean-teacher iterations of the reference's net_regression_small.Net pair (student seed 41, teacher seed 43) with
+    Adam(1e-4, (.9,.999), eps 1e-4, wd 1e-6) on the student (train/main.py:43-46, 212-213): the three losses per step and teacher / student
+    parameter samples afterwards."""
+    import contextlib
+    import importlib
+    import io
+    import warnings
+    warnings.simplefilter("ignore")
+    sys.path.insert(0, os.path.join(REF, "train"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        ev = importlib.import_module("evaluation_functions")
+        mod = importlib.import_module("net_regression_small")
+        student, teacher = mod.Net(), mod.Net()
+    shapes = {k: tuple(v.shape) for k, v in student.state_dict().items()}
+    student.load_state_dict(O.make_state_dict(shapes, seed=41))
+    teacher.load_state_dict(O.make_state_dict(shapes, seed=43))
+    for target in teacher.parameters():                    # what copyWeightsToModelNoGrad effectively does (train/main.py:130-135)
+        target.requires_grad = False
+    x1, x2, tgt = mean_teacher_inputs()
+    opt = torch.optim.Adam([p for p in student.parameters()], 1e-4, (0.9, 0.999), eps=1e-4, weight_decay=1e-6)
+
+    def update(rate):                                      # copyWeightsToModelWithDiscount (train/main.py:137-139)
+        for source, target in zip(student.parameters(), teacher.parameters()):
+            target.data = target.data * (1 - rate) + rate * source.data
+
+    student.train(), teacher.train()
+    losses = [mean_teacher_step(student, teacher, ev, opt, x1, x2, tgt, 0.5, update) for _ in range(3)]
+    res = {"losses": np.array(losses)}
+    for k in ("decoder.scalar_output_conv.weight", "encoder.initial_block.conv.bias"):
+        res["student_" + k] = student.get_parameter(k).detach().numpy().copy()
+        res["teacher_" + k] = teacher.get_parameter(k).detach().numpy().copy()
+    np.savez_compressed(path, **res)
 
 
 def fork_loss_inputs():

@@ -47,3 +47,8 @@ def test_iou_one_hot_inputs():
 
 def test_mean_teacher():
     check_mean_teacher("cuda")
+
+
+def test_mean_teacher_training_vs_reference(golden_dir):
+    from tests.mean_teacher_cases import check_mean_teacher_training
+    check_mean_teacher_training(golden_dir, "cuda", "fp32")

@@ -264,3 +264,10 @@ def test_io_side_and_mean_teacher_host_logic():
         check_model_accepts_uint8("cpu")
         check_labels("cpu")
         check_mean_teacher("cpu")
+
+
+def test_mean_teacher_training_host_logic(golden_dir):
+    """Student / teacher pair of the fork's small regression net through three mean-teacher iterations, kernels emulated."""
+    from tests.mean_teacher_cases import check_mean_teacher_training
+    with emulated_kernels():
+        check_mean_teacher_training(golden_dir, "cpu")
