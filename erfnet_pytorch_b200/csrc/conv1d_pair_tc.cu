@@ -26,6 +26,7 @@ struct PairParams {
   const float* bias1;
   const float* bias2;
   int N, H, W, dil, relu, has_res;
+  int w_static;   // weight images not written by any kernel in flight (inference): copy them before pdl_wait()
   int rows, NT, slots, t_rows, t_bytes;
 };
 
@@ -89,6 +90,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
     for (int a = 0; a < NSTG; ++a) mbar_init(&aux_bar[a], 1);
     mbar_init(&w_bar, 1);
     fence_barrier_init();
+    if (p.w_static) {   // static weights: fetch them while the previous kernel's last CTAs are still running
+      mbar_arrive_expect_tx(&w_bar, 2 * W_BYTES);
+      pair_bulk_g2s(s_w1, p.w1_img, W_BYTES, &w_bar);
+      pair_bulk_g2s(s_w2, p.w2_img, W_BYTES, &w_bar);
+    }
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_out);
     if (p.has_res) tma_prefetch_desc(&tmap_res);
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
   if (warp == 0) {
     // ================= TMA producer =================
     {   // whole warp in uniform control flow, one elected lane issues
-      if (elect_one()) {
+      if (!p.w_static && elect_one()) {
         mbar_arrive_expect_tx(&w_bar, 2 * W_BYTES);
         pair_bulk_g2s(s_w1, p.w1_img, W_BYTES, &w_bar);
         pair_bulk_g2s(s_w2, p.w2_img, W_BYTES, &w_bar);
@@ -361,7 +367,7 @@ extern "C" int erf_conv1d_pair_tc(const void* in, const void* w1_img, const floa
   p.w1_img = (const __nv_bfloat16*)w1_img;
   p.w2_img = (const __nv_bfloat16*)w2_img;
   p.bias1 = bias1; p.bias2 = bias2;
-  p.N = N; p.H = H; p.W = W; p.dil = dil; p.relu = relu; p.has_res = res != nullptr;
+  p.N = N; p.H = H; p.W = W; p.dil = dil; p.relu = relu & 1; p.w_static = (relu >> 1) & 1; p.has_res = res != nullptr;
   p.rows = N * H;
   p.NT = W / 128;
   p.t_rows = ((W + 2 * dil + 7) / 8) * 8 + 8;          // + one swizzle group of slack behind the last halo pixel

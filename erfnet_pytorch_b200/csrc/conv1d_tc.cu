@@ -34,6 +34,7 @@ struct Conv1dTcParams {
   int horizontal;               // 0: taps along H (3x1), 1: taps along W (1x3)
   int dil;
   int relu;
+  int w_static;                 // the weight image is not written by any kernel still in flight (inference): its copy starts before pdl_wait()
   int aux_mode;                 // 0 none, 1 add (residual / gradient accumulation), 2 relu-backward mask
   int units;                    // N * H * (W / 128)
   int slots;                    // A ring depth
@@ -114,6 +115,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     }
     mbar_init(&sfinal_bar, 1);
     fence_barrier_init();
+    if (p.w_static) {   // static weights: fetch them while the previous kernel's last CTAs are still running
+      mbar_arrive_expect_tx(&w_bar, W_BYTES);
+      for (int off = 0; off < W_BYTES; off += 32768) {
+        const int n = W_BYTES - off < 32768 ? W_BYTES - off : 32768;
+        bulk_g2s(s_w + off, reinterpret_cast<const uint8_t*>(p.w_img) + off, n, &w_bar);
+      }
+    }
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_out);
     if (p.aux_mode) tma_prefetch_desc(&tmap_aux);
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     // ================= TMA producer: whole warp in uniform control flow, one elected lane issues =================
     {
       // weights: one bulk copy per <= 32 KB piece, completing on w_bar
-      if (elect_one()) {
+      if (!p.w_static && elect_one()) {
         mbar_arrive_expect_tx(&w_bar, W_BYTES);
         for (int off = 0; off < W_BYTES; off += 32768) {
           const int n = W_BYTES - off < 32768 ? W_BYTES - off : 32768;
@@ -497,7 +505,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.w_img = (const __nv_bfloat16*)w_img;
   p.bias = bias;
   p.N = N; p.H = H; p.W = W;
-  p.horizontal = horizontal; p.dil = dil; p.relu = relu;
+  p.horizontal = horizontal; p.dil = dil; p.relu = relu & 1; p.w_static = (relu >> 1) & 1;   // relu: bit 0 = ReLU, bit 1 = static weights
   p.aux_mode = res ? 1 : (mask ? 2 : 0);
   p.stats = stats;
   p.colsum = colsum;

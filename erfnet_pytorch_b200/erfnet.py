@@ -113,6 +113,9 @@ class _B200Module(nn.Module):
         if c is None or c[0] != sig:
             c = (sig, self._pack_eval(dtype))
             self.__dict__["_packed"] = c
+            self.__dict__["_packed_fresh"] = True     # written by kernels that may still be in flight
+        else:
+            self.__dict__["_packed_fresh"] = False    # written during an earlier forward: static for every kernel launched from now on
         return c[1]
 
     def _nhwc(self, x, ctx):
@@ -458,13 +461,14 @@ class non_bottleneck_1d(_B200Module):
         d = self.dilated
         if "tc" in pk and ops.conv1d_tc_supported(self.chann, x.shape[2], d, x.dtype) and ops.USE_TC:
             tc = pk["tc"]
+            st = ops.STATIC_WEIGHT_PREFETCH and not self.__dict__.get("_packed_fresh", True)   # cached images: their copy may start before pdl_wait()
             if ops.conv1d_pair_tc_supported(self.chann, x.shape[2], d, x.dtype) and ops.conv1d_pair_tc_supported(self.chann, x.shape[2], 1, x.dtype):
-                t = ops.conv1d_pair_tc(x, tc[0], b[0], tc[1], b[1], 1, relu=True)            # 3x1 -> ReLU -> 1x3 (+BN1 folded) -> ReLU
-                return ops.conv1d_pair_tc(t, tc[2], b[2], tc[3], b[3], d, relu=True, res=x)  # dilated pair (+BN2 folded) + x -> ReLU
-            t = ops.conv1d_tc(x, tc[0], b[0], False, 1, relu=True)
-            t = ops.conv1d_tc(t, tc[1], b[1], True, 1, relu=True)
-            t = ops.conv1d_tc(t, tc[2], b[2], False, d, relu=True)
-            return ops.conv1d_tc(t, tc[3], b[3], True, d, relu=True, res=x)
+                t = ops.conv1d_pair_tc(x, tc[0], b[0], tc[1], b[1], 1, relu=True, static_w=st)            # 3x1 -> ReLU -> 1x3 (+BN1 folded) -> ReLU
+                return ops.conv1d_pair_tc(t, tc[2], b[2], tc[3], b[3], d, relu=True, res=x, static_w=st)  # dilated pair (+BN2 folded) + x -> ReLU
+            t = ops.conv1d_tc(x, tc[0], b[0], False, 1, relu=True, static_w=st)
+            t = ops.conv1d_tc(t, tc[1], b[1], True, 1, relu=True, static_w=st)
+            t = ops.conv1d_tc(t, tc[2], b[2], False, d, relu=True, static_w=st)
+            return ops.conv1d_tc(t, tc[3], b[3], True, d, relu=True, res=x, static_w=st)
         t = ops.conv_fwd(x, w[0], s[0], b[0], relu=True)
         t = ops.conv_fwd(t, w[1], s[1], b[1], relu=True)
         t = ops.conv_fwd(t, w[2], s[2], b[2], relu=True)

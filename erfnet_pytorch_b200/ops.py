@@ -230,12 +230,17 @@ USE_PAIR = True   # fused 3x1 -> ReLU -> 1x3 pairs in eval mode (C = 16 / 64)
 FUSE_NCHW_HEAD = True   # inference: the decoder head writes the NCHW fp32 logits from its epilogue (no NHWC logits, no layout pass)
 
 
-def conv1d_pair_tc(x, w1_img, b1, w2_img, b2, dil, relu=True, res=None):
-    """act(conv1x3_d(relu(conv3x1_d(x) + b1)) + b2 [+ res]) in one launch; bit-identical to two conv1d_tc calls."""
+STATIC_WEIGHT_PREFETCH = True   # inference: cached weight images are fetched before the PDL wait (bit 1 of the kernels' relu argument)
+
+
+def conv1d_pair_tc(x, w1_img, b1, w2_img, b2, dil, relu=True, res=None, static_w=False):
+    """act(conv1x3_d(relu(conv3x1_d(x) + b1)) + b2 [+ res]) in one launch; bit-identical to two conv1d_tc calls.
+    static_w: no kernel in flight writes the weight images (cached eval-mode images), so their copy may overlap the previous kernel's tail."""
     n, h, w, c = x.shape
     out = torch.empty_like(x)
     with _timed("conv1d_pair_tc_kernel", 2.0 * 2.0 * n * h * w * c * c * 3):
-        check(_lib.lib().erf_conv1d_pair_tc(_p(x), _p(w1_img), _p(b1), _p(w2_img), _p(b2), _p(out), _p(res), n, h, w, c, dil, int(relu), _stream(x)))
+        check(_lib.lib().erf_conv1d_pair_tc(_p(x), _p(w1_img), _p(b1), _p(w2_img), _p(b2), _p(out), _p(res), n, h, w, c, dil,
+                                            int(relu) | (2 if static_w else 0), _stream(x)))
     _count()
     return out
 
@@ -272,13 +277,14 @@ class Conv1dPackTable:
 
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
               res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated by the kernel itself (Gram / ones MMAs over the staged output tile)."""
+              colsum: Optional[torch.Tensor] = None, static_w: bool = False) -> torch.Tensor:
+    """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated by the kernel itself (Gram / ones MMAs over the staged output tile).
+    static_w: see conv1d_pair_tc."""
     n, h, w, c = x.shape
     out = torch.empty_like(x)
     fused = True
     with _timed("conv1d_tc_kernel", 2.0 * n * h * w * c * c * 3):
-        check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu),
+        check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu) | (2 if static_w else 0),
                                        _p(stats) if fused else None, _p(colsum) if fused else None, _stream(x)))
     _count()
     if not fused:

@@ -209,6 +209,8 @@ int erf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
  * with the 16-byte chunks of row n XOR-swizzled by (n & 7) (erfnet_pytorch_b200.ops.pack_conv1d_tc).
  * stats  (fp64 [2C]): += per-channel sum and sum of squares of the stored (bf16) output -- the BN batch statistics;
  * colsum (fp32 [C]): += per-channel sum of the stored output -- the bias gradient when this call is a data gradient.
+ * relu: bit 0 = ReLU in the epilogue; bit 1 = "static weights": no kernel in flight on the stream writes w_img (cached inference images), so
+ * the kernel may copy it to shared memory before the programmatic-dependent-launch wait, under the previous kernel's tail (same for the pair kernel).
  * Returns ERF_ERR_UNSUPPORTED unless erf_conv1d_tc_supported(C, W, dil). */
 int erf_conv1d_tc_supported(int C, int W, int dil);
 int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask,
