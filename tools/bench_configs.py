@@ -1,0 +1,85 @@
+"""Throughput of the other BASELINE configs (parity-test cases, not bench lines): config 3 (ImageNet encoder pre-training step, 224 x 224) and
+config 4 (fork ladder regression net, 512 x 1024, masked L1), one GPU, eager launches, CUDA events.  For DESIGN.md section 7."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from erfnet_pytorch_b200 import erfnet_imagenet as EI  # noqa: E402
+from erfnet_pytorch_b200 import evaluation_functions as EV  # noqa: E402
+from erfnet_pytorch_b200 import net_regression_ladder as NL  # noqa: E402
+from erfnet_pytorch_b200.optim import FlatSGD  # noqa: E402
+from oracle import erfnet_oracle as O  # noqa: E402
+
+
+def timed(fn, steps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+res = {}
+# ---- config 3: erfnet_imagenet.ERFNet(1000), CE, SGD(0.1, 0.9, 1e-4)
+B = int(os.environ.get("IMAGENET_BATCH", "64"))
+m = EI.ERFNet(1000)
+m.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=51))
+m = m.cuda().train()
+opt = FlatSGD(m.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
+crit = EI.CrossEntropyLoss()
+x = torch.randn(B, 3, 224, 224, device="cuda")
+y = torch.randint(0, 1000, (B,), device="cuda")
+
+
+def step3():
+    loss = crit(m(x), y)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+
+
+ms = timed(step3)
+res["config3_imagenet_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "224x224: W < 128 at every encoder stage, so the convs run on the CUDA-core kernels"}
+m.eval()
+with torch.no_grad():
+    ms = timed(lambda: m(x))
+res["config3_imagenet_eval"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3}
+del m, opt, x, y
+torch.cuda.empty_cache()
+
+# ---- config 4: net_regression_ladder.Net(), L1LossMasked, Adam as train/main.py:43-46
+B = 6
+net = NL.Net()
+net.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=31))
+net = net.cuda().train()
+opt = torch.optim.Adam(net.parameters(), 1e-4, (0.9, 0.999), eps=1e-4, weight_decay=1e-6)
+crit = EV.L1LossMasked()
+x = torch.rand(B, 3, 512, 1024, device="cuda")
+tgt = torch.rand(B, 512, 1024, device="cuda") * 2
+tgt[torch.rand(B, 512, 1024, device="cuda") < 0.7] = -1.0
+
+
+def step4():
+    loss = crit(net(x), tgt)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+
+
+ms = timed(step4)
+res["config4_ladder_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 225.2 / 1e3 / 1427.3,
+                               "note": "eager launches through autograd + torch.optim.Adam (no flat trainer / CUDA graph for the fork nets)"}
+net.eval()
+with torch.no_grad():
+    ms = timed(lambda: net(x))
+res["config4_ladder_eval"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 75.05 / 1e3 / 1427.3}
+print(json.dumps(res))
