@@ -36,9 +36,13 @@ class FlatAdamTrainer:
     """Fused training step: forward (NHWC logits) -> CE fwd+bwd kernel -> backward -> bucketed all-reduce -> flat Adam."""
 
     def __init__(self, model, weight=None, ignore_index=-1, lr=1e-4, betas=(0.9, 0.999), eps=1e-4, weight_decay=1e-6,
-                 process_group=None, num_classes=None):
+                 process_group=None, num_classes=None, loss_fn=None):
+        """loss_fn: None = the fused Cityscapes path (ERFNet.forward_nhwc + weighted CE kernel).  Otherwise any of the nets with any
+        criterion: ``loss_fn(model(images), *targets)`` -> scalar loss (e.g. ``lambda out, t: L1LossMasked()(out, t)`` for the fork's
+        regression nets, train/main.py:174-184); the loss is then the mean over the RANK's batch and gradients are averaged over ranks."""
         self.model = model
-        self.num_classes = num_classes or model.num_classes
+        self.loss_fn = loss_fn
+        self.num_classes = num_classes or getattr(model, "num_classes", None)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
@@ -145,16 +149,36 @@ class FlatAdamTrainer:
         self._seen = set()
 
     # ---- one step ---------------------------------------------------------------------------------------------
+    def _generic_loss_and_backward(self, images, targets):
+        """Any net + any criterion: public forward, autograd through the criterion, kernels accumulate into the flat gradient views."""
+        try:
+            out = self.model(images)
+        finally:
+            _erfnet._PREPACKED_FRESH = False
+        loss = self.loss_fn(out, *targets)
+        self._backward(loss, None)
+        self._finish_buckets()
+        loss = loss.detach()
+        if self.world > 1:
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
+            loss /= self.world
+        return loss
+
     def loss_and_backward(self, images, labels, drop_scales=None):
-        """images NCHW fp32, labels int64 [B,H,W] on the model's device.  Returns the GLOBAL-batch loss (0-dim tensor)."""
+        """images NCHW fp32, labels int64 [B,H,W] on the model's device.  Returns the GLOBAL-batch loss (0-dim tensor).
+        With a ``loss_fn``: labels is the target tensor (or a tuple of them) that follows the net output in the criterion call."""
         self.flat_g.zero_()
-        self.flat_nbt.add_(1)
+        if self.flat_nbt.numel():
+            self.flat_nbt.add_(1)
         self.model.train()
         if self._pack_table is not None:
             if not self._pack_table.valid():
                 raise RuntimeError("FlatAdamTrainer: a conv weight was re-allocated after the trainer took ownership of the parameters")
             self._pack_table.run()
             _erfnet._PREPACKED_FRESH = True
+        if self.loss_fn is not None:
+            return self._generic_loss_and_backward(images, labels if isinstance(labels, (tuple, list)) else (labels,))
         try:
             logits = self.model.forward_nhwc(images, drop_scales=drop_scales)
         finally:
@@ -183,19 +207,23 @@ class FlatAdamTrainer:
             self._arena.reset()          # one memset for all BN-backward reductions of the step
             ops.ARENA = self._arena
         try:
-            logits.backward(dlog)
+            if dlog is None:
+                logits.backward()          # generic path: `logits` is the scalar loss
+            else:
+                logits.backward(dlog)
         finally:
             _erfnet._GRAD_SINK = None
             ops.ARENA = None
 
     def optimizer_step(self):
         self.step_count += 1
+        gs = 1.0 / self.world if self.loss_fn is not None else 1.0   # generic path: ranks' mean losses are averaged (the CE path is pre-normalised)
         if self._step_dev is not None:  # CUDA-graph mode: the step counter lives on the device
             ops.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                              self._step_dev)
+                              self._step_dev, gs)
         else:
             ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                          self.step_count)
+                          self.step_count, gs)
         _erfnet.bump_weights_epoch()  # flat_p aliases the parameters; invalidate eval-mode packed weights
 
     def train_step(self, images, labels, drop_scales=None):
@@ -269,12 +297,15 @@ class FlatAdamTrainer:
             nxt, k = nxt2, k ^ 1
 
     # ---- CUDA graph of the whole step (forward, loss, backward, all-reduce, Adam): ~700 launches -> one replay ---------
-    def capture_cuda_graph(self, images_shape, labels_shape, warmup=2):
+    def capture_cuda_graph(self, images_shape, labels_shape, warmup=2, labels_dtype=torch.int64):
         """Capture one full training step for fixed shapes.  State touched by the warm-up steps is restored, so training
-        semantics are unchanged; afterwards train_step() copies the batch into static buffers and replays the graph."""
+        semantics are unchanged; afterwards train_step() copies the batch into static buffers and replays the graph.
+        labels_dtype: torch.float32 for the fork's regression targets."""
         dev = self.flat_p.device
+        if self.loss_fn is not None and self.world > 1:
+            raise RuntimeError("FlatAdamTrainer: graph capture of the generic (loss_fn) step is built for one GPU; run it eagerly at N > 1")
         self._g_images = torch.zeros(images_shape, device=dev, dtype=torch.float32)
-        self._g_labels = torch.zeros(labels_shape, device=dev, dtype=torch.int64)
+        self._g_labels = torch.zeros(labels_shape, device=dev, dtype=labels_dtype)
         self._step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int32)
         snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self._step_dev)]
         bufs = [b.clone() for b in self.model.buffers()]

@@ -26,3 +26,11 @@ def test_fork_net_bf16_tensor_cores(name):
             o = m(x)
         outs[precision] = (o[0] if isinstance(o, tuple) else o).float().cpu().numpy()
     assert_rel(outs["bf16"], outs["fp32"], 3e-2, name + " bf16 vs fp32")
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_flat_trainer_generic_loss(graph):
+    """The flat trainer (gradient sink, one Adam kernel, optional CUDA graph) on a fork net + masked L1 == autograd + torch.optim.Adam."""
+    from tests.flat_generic_cases import check_flat_generic
+    check_flat_generic("cuda", "fp32", graph=graph, tol=2e-4)
+    check_flat_generic("cuda", "bf16", shape=(1, 3, 128, 1024), graph=graph, tol=5e-2)

@@ -271,3 +271,10 @@ def test_mean_teacher_training_host_logic(golden_dir):
     from tests.mean_teacher_cases import check_mean_teacher_training
     with emulated_kernels():
         check_mean_teacher_training(golden_dir, "cpu")
+
+
+def test_flat_trainer_generic_loss_host_logic():
+    """FlatAdamTrainer(loss_fn=...) on a fork net == autograd + torch.optim.Adam, kernels emulated."""
+    from tests.flat_generic_cases import check_flat_generic
+    with emulated_kernels():
+        check_flat_generic("cpu")

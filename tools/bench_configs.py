@@ -78,6 +78,15 @@ def step4():
 ms = timed(step4)
 res["config4_ladder_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 225.2 / 1e3 / 1427.3,
                                "note": "eager launches through autograd + torch.optim.Adam (no flat trainer / CUDA graph for the fork nets)"}
+del opt
+from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
+tr = FlatAdamTrainer(net, loss_fn=lambda out, t: crit(out, t))
+ms = timed(lambda: tr.train_step(x, tgt))
+res["config4_ladder_train_flat"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "FlatAdamTrainer(loss_fn=...): gradient sink + one Adam kernel, eager"}
+tr.capture_cuda_graph(tuple(x.shape), tuple(tgt.shape), labels_dtype=torch.float32)
+ms = timed(lambda: tr.train_step(x, tgt))
+res["config4_ladder_train_flat_graph"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 225.2 / 1e3 / 1427.3,
+                                          "note": "the same step replayed from one CUDA graph"}
 net.eval()
 with torch.no_grad():
     ms = timed(lambda: net(x))
