@@ -48,6 +48,17 @@ class FlatAdamTrainer:
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.criterion = CrossEntropyLoss2d(weight, ignore_index)
         self.step_count = 0
+        # The trainer takes ownership of the parameters: every nn.Parameter is replaced by a FRESH one (a view of the flat buffer below).
+        # A grad-enabled forward that ran before this point leaves AccumulateGrad nodes bound to the stream it ran on (normally the legacy
+        # default stream); the autograd engine would then synchronise that stream with the capturing stream at the end of a captured
+        # backward ("dependency created on uncaptured work in another stream").  Fresh parameters have no such history.
+        fresh = {}
+        for mod in model.modules():
+            for pname, par in list(mod._parameters.items()):
+                if par is not None:
+                    if id(par) not in fresh:
+                        fresh[id(par)] = torch.nn.Parameter(par.detach(), requires_grad=par.requires_grad)
+                    mod._parameters[pname] = fresh[id(par)]
         named = list(model.named_parameters())
         # flat layout ordered by bucket so that each bucket is one contiguous slice
         order = sorted(range(len(named)), key=lambda i: (_bucket_of(named[i][0]), i))

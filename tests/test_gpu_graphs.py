@@ -77,3 +77,25 @@ def test_train_stream_matches_sequential_steps():
     np.testing.assert_allclose(got[0], seq[0], rtol=1e-5)
     np.testing.assert_allclose(got, seq, rtol=1e-2)
     assert float((t1.flat_p - t2.flat_p).abs().mean()) < 1e-4   # Adam's sign-like first steps amplify rounding noise on ~zero gradients: mean, not max
+
+
+def test_capture_after_an_earlier_autograd_forward():
+    """A grad-enabled forward (and backward) on the default stream BEFORE the trainer exists used to poison a later capture (stale
+    AccumulateGrad nodes bound to the legacy stream); the trainer now re-creates the parameters it takes ownership of."""
+    import torch
+    from erfnet_pytorch_b200 import erfnet as E
+    from erfnet_pytorch_b200.parallel import FlatAdamTrainer
+    from oracle import erfnet_oracle as O
+    m = E.ERFNet(20)
+    m.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(20), 0))
+    m = m.cuda().train()
+    x = torch.rand(1, 3, 64, 128, device="cuda")
+    lab = torch.randint(0, 19, (1, 64, 128), device="cuda")
+    y = m(x)                       # graph kept alive on purpose
+    y.sum().backward()
+    tr = FlatAdamTrainer(m)
+    tr.capture_cuda_graph(tuple(x.shape), tuple(lab.shape))
+    l0 = float(tr.train_step(x, lab))
+    l1 = float(tr.train_step(x, lab))
+    assert l0 == l0 and l1 < l0 + 1.0
+    assert all(p.grad is not None for n, p in m.named_parameters() if "encoder.output_conv" not in n)
