@@ -36,12 +36,14 @@ class FlatAdamTrainer:
     """Fused training step: forward (NHWC logits) -> CE fwd+bwd kernel -> backward -> bucketed all-reduce -> flat Adam."""
 
     def __init__(self, model, weight=None, ignore_index=-1, lr=1e-4, betas=(0.9, 0.999), eps=1e-4, weight_decay=1e-6,
-                 process_group=None, num_classes=None, loss_fn=None):
+                 process_group=None, num_classes=None, loss_fn=None, sgd_momentum=None):
         """loss_fn: None = the fused Cityscapes path (ERFNet.forward_nhwc + weighted CE kernel).  Otherwise any of the nets with any
         criterion: ``loss_fn(model(images), *targets)`` -> scalar loss (e.g. ``lambda out, t: L1LossMasked()(out, t)`` for the fork's
         regression nets, train/main.py:174-184); the loss is then the mean over the RANK's batch and gradients are averaged over ranks."""
         self.model = model
         self.loss_fn = loss_fn
+        self.sgd_momentum = sgd_momentum   # not None: torch.optim.SGD(lr, momentum, weight_decay) semantics (imagenet/main.py:83-85) instead of Adam;
+                                           # lr / weight_decay are read from self.lr / self.wd at every eager step (re-capture a graph after changing them)
         self.num_classes = num_classes or getattr(model, "num_classes", None)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -229,6 +231,11 @@ class FlatAdamTrainer:
     def optimizer_step(self):
         self.step_count += 1
         gs = 1.0 / self.world if self.loss_fn is not None else 1.0   # generic path: ranks' mean losses are averaged (the CE path is pre-normalised)
+        if self.sgd_momentum is not None:
+            # the momentum buffer starts at zero, so momentum * buf + d on the first step equals torch's "buf = d" initialisation
+            ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr, self.sgd_momentum, self.wd, False, gs)
+            _erfnet.bump_weights_epoch()
+            return
         if self._step_dev is not None:  # CUDA-graph mode: the step counter lives on the device
             ops.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                               self._step_dev, gs)

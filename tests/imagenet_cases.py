@@ -92,3 +92,18 @@ def check_pretrained_encoder_handoff(device):
     with torch.no_grad():
         y = seg(torch.rand(1, 3, 32, 64, generator=torch.Generator().manual_seed(2)).to(device))
     assert y.shape == (1, 20, 32, 64) and bool(torch.isfinite(y).all())
+
+
+def check_imagenet_flat_trainer(golden_dir, device):
+    """The same two SGD steps through FlatAdamTrainer(loss_fn=CE, sgd_momentum=0.9): gradient sink + one SGD kernel."""
+    from erfnet_pytorch_b200.parallel import FlatAdamTrainer
+    g = np.load(os.path.join(golden_dir, "imagenet_net.npz"))
+    m = build_imagenet(device)
+    x, y = imagenet_inputs()
+    x, y = x.to(device), y.to(device)
+    crit = EI.CrossEntropyLoss()
+    tr = FlatAdamTrainer(m, lr=0.002, weight_decay=1e-4, loss_fn=lambda out, t: crit(out, t), sgd_momentum=0.9)
+    losses = [float(tr.train_step(x, y)) for _ in range(2)]
+    assert abs(losses[0] - g["loss"]) <= 1e-4 * abs(g["loss"]) and abs(losses[1] - g["loss2"]) <= 5e-3 * abs(g["loss2"]), losses
+    for k, tol in zip(IMAGENET_GRADS, (4e-2, 1e-3, 1e-3)):      # conditioning: see check_imagenet_net
+        assert_rel(m.get_parameter(k).detach().cpu().numpy(), g["p2_" + k], tol, "flat trainer: parameter after 2 SGD steps " + k)

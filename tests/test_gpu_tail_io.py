@@ -3,7 +3,7 @@ kernels (uint8 ingest, label tables, colouring) through the C ABI."""
 import pytest
 import torch
 
-from tests.imagenet_cases import build_imagenet, check_ce_topk, check_imagenet_net, check_pretrained_encoder_handoff
+from tests.imagenet_cases import build_imagenet, check_ce_topk, check_imagenet_flat_trainer, check_imagenet_net, check_pretrained_encoder_handoff
 from tests.io_cases import check_ingest, check_iou_one_hot, check_labels, check_mean_teacher, check_model_accepts_uint8
 from tests.test_host_logic import assert_rel
 
@@ -12,6 +12,10 @@ pytestmark = pytest.mark.gpu
 
 def test_imagenet_net_fp32_golden(golden_dir):
     check_imagenet_net(golden_dir, "cuda")
+
+
+def test_imagenet_flat_trainer(golden_dir):
+    check_imagenet_flat_trainer(golden_dir, "cuda")
 
 
 def test_pretrained_encoder_handoff():

@@ -248,8 +248,9 @@ def test_classification_net_argument_errors():
 def test_imagenet_net_host_logic(golden_dir):
     """imagenet/erfnet_imagenet.ERFNet(1000) + the SGD step of imagenet/main.py: wiring of the pooling / Linear tail, row-wise CE,
     top-k, FlatSGD (momentum, weight decay, flat views), kernels emulated."""
-    from tests.imagenet_cases import check_ce_topk, check_imagenet_net, check_lr_schedule, check_pretrained_encoder_handoff
+    from tests.imagenet_cases import check_ce_topk, check_imagenet_flat_trainer, check_imagenet_net, check_lr_schedule, check_pretrained_encoder_handoff
     with emulated_kernels():
+        check_imagenet_flat_trainer(golden_dir, "cpu")
         check_pretrained_encoder_handoff("cpu")
         check_imagenet_net(golden_dir, "cpu")
         check_ce_topk(golden_dir, "cpu")

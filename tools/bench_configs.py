@@ -49,6 +49,15 @@ def step3():
 
 ms = timed(step3)
 res["config3_imagenet_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "224x224: W < 128 at every encoder stage, so the convs run on the CUDA-core kernels"}
+del opt
+from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
+tr3 = FlatAdamTrainer(m, lr=0.1, weight_decay=1e-4, loss_fn=lambda out, t: crit(out, t), sgd_momentum=0.9)
+ms = timed(lambda: tr3.train_step(x, y))
+res["config3_imagenet_train_flat"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "FlatAdamTrainer(loss_fn=CE, sgd_momentum=0.9), eager"}
+tr3.capture_cuda_graph(tuple(x.shape), tuple(y.shape))
+ms = timed(lambda: tr3.train_step(x, y))
+res["config3_imagenet_train_flat_graph"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "the same step replayed from one CUDA graph"}
+del tr3
 m.eval()
 with torch.no_grad():
     ms = timed(lambda: m(x))
