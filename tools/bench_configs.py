@@ -62,7 +62,7 @@ m.eval()
 with torch.no_grad():
     ms = timed(lambda: m(x))
 res["config3_imagenet_eval"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3}
-del m, opt, x, y
+del m, x, y
 torch.cuda.empty_cache()
 
 # ---- config 4: net_regression_ladder.Net(), L1LossMasked, Adam as train/main.py:43-46
