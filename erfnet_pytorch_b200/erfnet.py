@@ -66,6 +66,13 @@ class _BlockFn(torch.autograd.Function):
         return (None, None, dx) + tuple(grads)
 
 
+class _Holder:
+    """(weight, bias) of a derived conv: quacks like the nn.Conv2d the block code reads them from."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
 class _ToNHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ld, dtype):
@@ -133,13 +140,14 @@ _GRAD_SINK = None   # set by parallel.FlatAdamTrainer while it runs backward: gr
 
 
 def _sink(p):
-    return p.grad if (_GRAD_SINK is not None and p.grad is not None) else None
+    # non-leaf "parameters" (the folded weights of a 32-channel block) get their gradient through autograd, never through the sink
+    return p.grad if (_GRAD_SINK is not None and p.is_leaf and p.grad is not None) else None
 
 
 def _sunk(*params):
     if _GRAD_SINK is not None:
         for p in params:
-            if p.grad is not None:
+            if p.is_leaf and p.grad is not None:
                 _GRAD_SINK.ready(p)
 
 
@@ -437,10 +445,69 @@ class non_bottleneck_1d(_B200Module):
         self._out_c = chann
 
     def _convs(self):
-        return (self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)
+        ov = self.__dict__.get("_conv_override")   # the 64-channel twin of a folded 32-channel block: (weight, bias) holders derived per step
+        return ov if ov is not None else (self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)
 
     def _nhwc(self, x, ctx):
+        if self.chann == 32 and self._fold_ok(x, ctx):
+            return self._nhwc_folded(x, ctx)
         return _run(self, x, ctx)
+
+    # ---- 32-channel blocks (the fork's LadderBlock(16), train/erfnet_blocks.py:144) on the 64-channel tcgen05 kernels -----------------
+    # [N,H,W,32] is the same memory as [N,H,W/2,64]: a "folded" pixel holds two neighbours (sub-pixel 0 = even column, 1 = odd column).
+    # A 3x1 conv of the block is then a 3x1 conv over folded pixels with block-diagonal weights diag(W_t, W_t); a 1x3 conv (dilation 1) is
+    # a 1x3 conv over folded pixels whose taps are  [-1]: out.sub0 <- in.sub1 * W_0;  [0]: [[W_1, W_2], [W_0, W_1]];  [+1]: out.sub1 <- in.sub0 * W_2.
+    # Half of those MMAs multiply zeros, which is free next to running the block on the CUDA cores.  The folded weights are built with
+    # differentiable torch ops, so autograd maps the 64-channel weight gradients back onto the 32-channel parameters.
+    def _fold_ok(self, x, ctx):
+        if self.use_batchnorm or self.dilated != 1 or not ops.USE_TC or not ops.FOLD_32 or x.shape[2] % 2:
+            return False
+        if ctx.training and self.use_dropout and self.dropout.p != 0:
+            return False                      # Dropout2d masks are per original channel; not folded
+        return ops.conv1d_tc_supported(64, x.shape[2] // 2, 1, x.dtype)
+
+    def _folded_weights(self):
+        out = []
+        for i, conv in enumerate((self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)):
+            w = conv.weight
+            z = w.new_zeros(32, 32)
+            blk = lambda a, b, c, d: torch.cat([torch.cat([a, b], 1), torch.cat([c, d], 1)], 0)     # [[a, b], [c, d]]: rows = out, cols = in
+            if i % 2 == 0:
+                w64 = torch.stack([blk(w[:, :, t, 0], z, z, w[:, :, t, 0]) for t in range(3)], 2).unsqueeze(3)          # [64,64,3,1]
+            else:
+                w0, w1, w2 = w[:, :, 0, 0], w[:, :, 0, 1], w[:, :, 0, 2]
+                w64 = torch.stack([blk(z, w0, z, z), blk(w1, w2, w0, w1), blk(z, z, w2, z)], 2).unsqueeze(2)            # [64,64,1,3]
+            out.append((w64.contiguous(), torch.cat([conv.bias, conv.bias])))
+        return out
+
+    def _twin(self, device):
+        tw = self.__dict__.get("_twin64")
+        if tw is None or tw.conv3x1_1.weight.device != device:
+            tw = non_bottleneck_1d(64, 0.0, 1, use_dropout=False, use_batchnorm=False).to(device)
+            tw.precision = None
+            self.__dict__["_twin64"] = tw     # not a registered sub-module: state_dict() / parameters() stay the reference's
+        return tw
+
+    def _nhwc_folded(self, x, ctx):
+        n, h, w, _ = x.shape
+        tw = self._twin(x.device)
+        xf = x.view(n, h, w // 2, 64)
+        if ctx.training:
+            fw = self._folded_weights()
+            tw.__dict__["_conv_override"] = [_Holder(a, b) for a, b in fw]
+            yf = _BlockFn.apply(tw, ctx, xf, *tw._train_params())
+        else:
+            sig = _sig(self)
+            if self.__dict__.get("_twin_sig") != sig:
+                with torch.no_grad():
+                    for conv, (a, b) in zip((tw.conv3x1_1, tw.conv1x3_1, tw.conv3x1_2, tw.conv1x3_2), self._folded_weights()):
+                        conv.weight.copy_(a)
+                        conv.bias.copy_(b)
+                self.__dict__["_twin_sig"] = sig
+            tw.__dict__["_conv_override"] = None
+            with torch.no_grad():
+                yf = tw._fwd_eval(xf, ctx)
+        return yf.view(n, h, w, 32)
 
     def _pack_eval(self, dtype):
         ws = [c.weight.detach().float() for c in self._convs()]
@@ -475,8 +542,9 @@ class non_bottleneck_1d(_B200Module):
         return ops.conv_fwd(t, w[3], s[3], b[3], relu=True, add=x)
 
     def _train_params(self):
-        return (self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias, self.bn1.weight, self.bn1.bias,
-                self.conv3x1_2.weight, self.conv3x1_2.bias, self.conv1x3_2.weight, self.conv1x3_2.bias, self.bn2.weight, self.bn2.bias)
+        c = self._convs()
+        return (c[0].weight, c[0].bias, c[1].weight, c[1].bias, self.bn1.weight, self.bn1.bias,
+                c[2].weight, c[2].bias, c[3].weight, c[3].bias, self.bn2.weight, self.bn2.bias)
 
     def _drop_scale(self, x, ctx):
         """Dropout2d multiplier [N,C] (0 or 1/(1-p)): same RNG consumption as nn.Dropout2d on [N,C,H,W] (noise [N,C,1,1])."""

@@ -227,6 +227,7 @@ def conv1d_pair_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
 
 
 USE_PAIR = True   # fused 3x1 -> ReLU -> 1x3 pairs in eval mode (C = 16 / 64)
+FOLD_32 = True          # 32-channel BN-free blocks run as [W/2, 64]-folded views on the 64-channel tcgen05 kernels
 FUSE_NCHW_HEAD = True   # inference: the decoder head writes the NCHW fp32 logits from its epilogue (no NHWC logits, no layout pass)
 
 

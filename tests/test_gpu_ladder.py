@@ -46,3 +46,41 @@ def test_ladder_net_bf16_tensor_cores():
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     assert m.encoder.output_conv.weight.grad is None          # unused in this graph, as in the reference
+
+
+def test_32_channel_block_folded_onto_the_64_channel_kernels():
+    """LadderBlock(16): its non_bottleneck_1d(32) runs as a [W/2, 64]-folded view on conv1d_tc<64> (block-structured weights).  Against the
+    same block on the generic kernels (ops.FOLD_32 = False, same bf16 storage): eval output, training output, input and parameter gradients."""
+    from erfnet_pytorch_b200 import erfnet_blocks as EB
+    from erfnet_pytorch_b200 import ops
+    torch.manual_seed(0)
+    blk = EB.LadderBlock(16).cuda()
+    blk.precision = "bf16"
+    sd = O.make_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=61)
+    blk.load_state_dict(sd)
+    x = (golden_input((2, 16, 8, 512), 121) - 0.3).cuda()
+    lad = (golden_input((2, 16, 8, 512), 122) - 0.3).cuda()
+    gout = (golden_input((2, 16, 8, 512), 123) - 0.5).cuda()
+    res = {}
+    for fold in (True, False):
+        ops.FOLD_32 = fold
+        try:
+            l0 = ops.LAUNCHES
+            blk.eval()
+            with torch.no_grad():
+                ye = blk(x, lad)
+            blk.train()
+            for p in blk.parameters():
+                p.grad = None
+            xi, li = x.clone().requires_grad_(True), lad.clone().requires_grad_(True)
+            yt = blk(xi, li)
+            yt.backward(gout)
+            res[fold] = dict(ye=ye, yt=yt.detach(), dx=xi.grad, dl=li.grad, dw=blk.layer.conv1x3_1.weight.grad.clone(), dw3=blk.layer.conv3x1_2.weight.grad.clone(),
+                             db=blk.layer.conv1x3_2.bias.grad.clone(), dwc=blk.conv.weight.grad.clone())
+        finally:
+            ops.FOLD_32 = True
+    for k in res[True]:
+        a, b = res[True][k].float(), res[False][k].float()
+        assert a.shape == b.shape
+        assert_rel(a.cpu().numpy(), b.cpu().numpy(), 3e-2, "folded vs generic: " + k)
+    assert float((res[True]["ye"] - res[False]["ye"]).abs().max()) > 0      # really a different kernel path
