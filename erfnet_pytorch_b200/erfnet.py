@@ -494,8 +494,11 @@ class non_bottleneck_1d(_B200Module):
         xf = x.view(n, h, w // 2, 64)
         if ctx.training:
             fw = self._folded_weights()
-            tw.__dict__["_conv_override"] = [_Holder(a, b) for a, b in fw]
-            yf = _BlockFn.apply(tw, ctx, xf, *tw._train_params())
+            # the block code reads DETACHED copies (holding the tracked tensors on the module would keep this step's autograd graph -- and the
+            # parameters' AccumulateGrad nodes with the stream they were created on -- alive into the next step / a later graph capture)
+            tw.__dict__["_conv_override"] = [_Holder(a.detach(), b.detach()) for a, b in fw]
+            tracked = (fw[0][0], fw[0][1], fw[1][0], fw[1][1], tw.bn1.weight, tw.bn1.bias, fw[2][0], fw[2][1], fw[3][0], fw[3][1], tw.bn2.weight, tw.bn2.bias)
+            yf = _BlockFn.apply(tw, ctx, xf, *tracked)      # same order as _train_params()
         else:
             sig = _sig(self)
             if self.__dict__.get("_twin_sig") != sig:
