@@ -73,6 +73,36 @@ class _Holder:
         self.weight, self.bias = weight, bias
 
 
+class _FoldAdapter:
+    """Presents a folded 32-channel block to _BlockFn: the forward / backward kernels run on its 64-channel twin with folded weights, the
+    parameter gradients are mapped back (and accumulated into the gradient sink when one is active), all without native autograd nodes."""
+
+    def __init__(self, block, twin):
+        self.block, self.twin = block, twin
+
+    def _train_params(self):
+        return self.block._train_params()
+
+    def _fwd_train(self, x, ctx):
+        self.twin.__dict__["_conv_override"] = [_Holder(a, b) for a, b in self.block._folded_weights()]
+        return self.twin._fwd_train(x, ctx)
+
+    def _bwd(self, dy, saved, need_dx):
+        dx, g64 = self.twin._bwd(dy, saved, need_dx)                  # twin order: w1,b1,w2,b2,g1,be1,w3,b3,w4,b4,g2,be2 (all returned: no sink on holders)
+        P = self.block._train_params()
+        grads = [None] * 12
+        for i, (wi, bi) in enumerate(((0, 1), (2, 3), (6, 7), (8, 9))):
+            dw, db = self.block._unfold_grads(i, g64[wi], g64[bi])
+            for idx, g in ((wi, dw), (bi, db)):
+                dst = _sink(P[idx])
+                if dst is not None:
+                    dst.add_(g)
+                else:
+                    grads[idx] = g
+        _sunk(*P)
+        return dx, tuple(grads)
+
+
 class _ToNHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ld, dtype):
@@ -467,18 +497,31 @@ class non_bottleneck_1d(_B200Module):
         return ops.conv1d_tc_supported(64, x.shape[2] // 2, 1, x.dtype)
 
     def _folded_weights(self):
+        """[(w64, b64)] x 4 from the 32-channel parameters (no autograd: _FoldAdapter maps the gradients back)."""
         out = []
-        for i, conv in enumerate((self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)):
-            w = conv.weight
-            z = w.new_zeros(32, 32)
-            blk = lambda a, b, c, d: torch.cat([torch.cat([a, b], 1), torch.cat([c, d], 1)], 0)     # [[a, b], [c, d]]: rows = out, cols = in
-            if i % 2 == 0:
-                w64 = torch.stack([blk(w[:, :, t, 0], z, z, w[:, :, t, 0]) for t in range(3)], 2).unsqueeze(3)          # [64,64,3,1]
-            else:
-                w0, w1, w2 = w[:, :, 0, 0], w[:, :, 0, 1], w[:, :, 0, 2]
-                w64 = torch.stack([blk(z, w0, z, z), blk(w1, w2, w0, w1), blk(z, z, w2, z)], 2).unsqueeze(2)            # [64,64,1,3]
-            out.append((w64.contiguous(), torch.cat([conv.bias, conv.bias])))
+        with torch.no_grad():
+            for i, conv in enumerate((self.conv3x1_1, self.conv1x3_1, self.conv3x1_2, self.conv1x3_2)):
+                w = conv.weight.detach()
+                z = w.new_zeros(32, 32)
+                blk = lambda a, b, c, d: torch.cat([torch.cat([a, b], 1), torch.cat([c, d], 1)], 0)     # [[a, b], [c, d]]: rows = out, cols = in
+                if i % 2 == 0:
+                    w64 = torch.stack([blk(w[:, :, t, 0], z, z, w[:, :, t, 0]) for t in range(3)], 2).unsqueeze(3)          # [64,64,3,1]
+                else:
+                    w0, w1, w2 = w[:, :, 0, 0], w[:, :, 0, 1], w[:, :, 0, 2]
+                    w64 = torch.stack([blk(z, w0, z, z), blk(w1, w2, w0, w1), blk(z, z, w2, z)], 2).unsqueeze(2)            # [64,64,1,3]
+                out.append((w64.contiguous(), torch.cat([conv.bias.detach(), conv.bias.detach()])))
         return out
+
+    @staticmethod
+    def _unfold_grads(i, dw64, db64):
+        """Transpose of the folding map: gradients of the 64-channel twin -> gradients of conv i of the 32-channel block."""
+        a, b = slice(0, 32), slice(32, 64)
+        if i % 2 == 0:
+            dw = (dw64[a, a] + dw64[b, b])                                                        # [32,32,3,1]
+        else:
+            g = dw64[:, :, 0, :]                                                                  # [64,64,3]
+            dw = torch.stack([g[a, b, 0] + g[b, a, 1], g[a, a, 1] + g[b, b, 1], g[a, b, 1] + g[b, a, 2]], 2).unsqueeze(2)   # [32,32,1,3]
+        return dw, db64[a] + db64[b]
 
     def _twin(self, device):
         tw = self.__dict__.get("_twin64")
@@ -493,12 +536,7 @@ class non_bottleneck_1d(_B200Module):
         tw = self._twin(x.device)
         xf = x.view(n, h, w // 2, 64)
         if ctx.training:
-            fw = self._folded_weights()
-            # the block code reads DETACHED copies (holding the tracked tensors on the module would keep this step's autograd graph -- and the
-            # parameters' AccumulateGrad nodes with the stream they were created on -- alive into the next step / a later graph capture)
-            tw.__dict__["_conv_override"] = [_Holder(a.detach(), b.detach()) for a, b in fw]
-            tracked = (fw[0][0], fw[0][1], fw[1][0], fw[1][1], tw.bn1.weight, tw.bn1.bias, fw[2][0], fw[2][1], fw[3][0], fw[3][1], tw.bn2.weight, tw.bn2.bias)
-            yf = _BlockFn.apply(tw, ctx, xf, *tracked)      # same order as _train_params()
+            yf = _BlockFn.apply(_FoldAdapter(self, tw), ctx, xf, *self._train_params())
         else:
             sig = _sig(self)
             if self.__dict__.get("_twin_sig") != sig:

@@ -335,6 +335,12 @@ class FlatAdamTrainer:
                 self.loss_and_backward(self._g_images, self._g_labels)
                 self.optimizer_step()
         torch.cuda.current_stream(dev).wait_stream(side)
+        # Parameters that receive their gradient through autograd (class_power, the folded 32-channel weights) own AccumulateGrad nodes that
+        # remember the stream they were created on; a dead-but-uncollected graph from the steps above would hand those stale nodes to the
+        # captured forward and make the engine synchronise an uncaptured stream with the capturing one.  Collect them now.
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(dev)
         if self.world > 1:
             # NCCL collectives stay outside the graphs (8.27 MB of gradients + two scalars per step): capture the three
             # compute segments between them, sharing one memory pool so that activations saved by segment 1 stay alive
