@@ -89,7 +89,9 @@ class FlatAdamTrainer:
             self._param_bucket[p] = b
             off += n
         # all BatchNorm step counters in one int64 tensor: one increment per step instead of 39
-        bns = [mod for mod in model.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+        unused = {c for mod in model.modules() if getattr(mod, "use_batchnorm", True) is False for c in mod.children()
+                  if isinstance(c, torch.nn.BatchNorm2d)}      # the fork's BN-free blocks keep (and never step) their BatchNorm modules
+        bns = [mod for mod in model.modules() if isinstance(mod, torch.nn.BatchNorm2d) and mod not in unused]
         self.flat_nbt = torch.zeros(len(bns), device=dev, dtype=torch.int64)
         for i, bn in enumerate(bns):
             self.flat_nbt[i] = bn.num_batches_tracked

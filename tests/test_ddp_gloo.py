@@ -92,3 +92,65 @@ def test_two_ranks_match_global_batch():
     np.testing.assert_allclose(l0[0], losses[0], rtol=2e-5)
     # north_star gate: loss curve within 1 % (Adam's +-lr first step amplifies gradient sign noise of zero-gradient biases)
     np.testing.assert_allclose(l0[1], losses[1], rtol=1e-2)
+
+
+def _worker_generic(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from erfnet_pytorch_b200 import evaluation_functions as EV
+    from erfnet_pytorch_b200 import net_regression_small
+    from erfnet_pytorch_b200.parallel import FlatAdamTrainer
+    from oracle import erfnet_oracle as O
+    from oracle.make_golden import golden_input
+    from tests.emu import emulated_kernels
+
+    m = net_regression_small.Net()
+    m.precision = "fp32"
+    m.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=41 + rank))   # rank 0's weights win
+    x = golden_input((2, 3, 32, 64), 131)
+    t = golden_input((2, 32, 64), 132) * 2.0          # every pixel labelled: the mean of the ranks' means is the global mean
+    crit = EV.L1LossMasked()
+    with emulated_kernels():
+        tr = FlatAdamTrainer(m, loss_fn=lambda out, tgt: crit(out, tgt))
+        losses = [float(tr.train_step(x[rank:rank + 1], t[rank:rank + 1])) for _ in range(2)]
+    ret[rank] = (losses, {k: v.detach().clone() for k, v in m.state_dict().items()})
+    dist.destroy_process_group()
+
+
+def test_generic_loss_two_ranks_match_one_process():
+    """FlatAdamTrainer(loss_fn=...) at world_size 2 (bucketed SUM all-reduce, gradients scaled by 1/world in the optimiser kernel) ==
+    one process on the concatenated batch (autograd + torch.optim.Adam, train/main.py:213)."""
+    mp.set_start_method("spawn", force=True)
+    ret = mp.Manager().dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker_generic, args=(2, port, ret), nprocs=2, join=True)
+    (l0, sd0), (l1, sd1) = ret[0], ret[1]
+    assert l0 == l1
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k
+    from erfnet_pytorch_b200 import evaluation_functions as EV
+    from erfnet_pytorch_b200 import net_regression_small
+    from oracle import erfnet_oracle as O
+    from oracle.make_golden import golden_input
+    from tests.emu import emulated_kernels
+    m = net_regression_small.Net()
+    m.precision = "fp32"
+    m.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=41))
+    m.train()
+    x = golden_input((2, 3, 32, 64), 131)
+    t = golden_input((2, 32, 64), 132) * 2.0
+    opt = torch.optim.Adam(m.parameters(), 1e-4, (0.9, 0.999), eps=1e-4, weight_decay=1e-6)
+    ref = []
+    with emulated_kernels():
+        for _ in range(2):
+            opt.zero_grad()
+            loss = EV.L1LossMasked()(m(x), t)
+            loss.backward()
+            opt.step()
+            ref.append(float(loss))
+    np.testing.assert_allclose(l0, ref, rtol=1e-5)
+    for k, v in m.state_dict().items():
+        np.testing.assert_allclose(sd0[k].numpy(), v.detach().numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
