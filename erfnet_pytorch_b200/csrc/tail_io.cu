@@ -225,13 +225,21 @@ __global__ void ingest_u8_kernel(const uint8_t* __restrict__ in, long long n_px,
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       T* dst = out + (size_t)(gi * 4 + px) * ld;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float v = __fdiv_rn((float)b[px * 3 + c], 255.f);
-        if (mean || stdv) v = __fdiv_rn(v - m[c], s[c]);
-        dst[c] = from_f<T>(v);
+        v[c] = __fdiv_rn((float)b[px * 3 + c], 255.f);
+        if (mean || stdv) v[c] = __fdiv_rn(v[c] - m[c], s[c]);
       }
-      for (int c = 3; c < ld; ++c) dst[c] = from_f<T>(0.f);
+      if (ld == 4) {   // the models' input pitch: one 8-byte (bf16) / 16-byte (fp32) store per pixel, contiguous across the thread's 4 pixels
+        Vec<T, 4> o;
+        o.v[0] = v[0]; o.v[1] = v[1]; o.v[2] = v[2]; o.v[3] = 0.f;
+        o.store(dst);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c] = from_f<T>(v[c]);
+        for (int c = 3; c < ld; ++c) dst[c] = from_f<T>(0.f);
+      }
     }
   }
   // tail pixels (n_px % 4)

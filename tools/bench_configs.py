@@ -100,4 +100,10 @@ net.eval()
 with torch.no_grad():
     ms = timed(lambda: net(x))
 res["config4_ladder_eval"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 75.05 / 1e3 / 1427.3}
+# ---- I/O side: uint8 HWC ingest (ToTensor + layout) at the bench shape, 3 B in + 8 B out per pixel
+from erfnet_pytorch_b200 import ops  # noqa: E402
+img = torch.randint(0, 256, (24, 512, 1024, 3), device="cuda", dtype=torch.uint8)
+ms = timed(lambda: ops.ingest_u8(img, 4, torch.bfloat16), steps=20)
+res["ingest_u8_bf16"] = {"batch": 24, "ms_per_step": ms, "images_per_s": 24 / ms * 1e3, "gbytes_per_s": img.numel() / 3 * 11 / ms / 1e6,
+                         "note": "algorithmic 11 B/pixel (3 in + 8 out); measured HBM peak 6445 GB/s"}
 print(json.dumps(res))
