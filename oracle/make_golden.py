@@ -190,6 +190,7 @@ def main():
     fork_nets(os.path.join(OUT, "fork_nets.npz"))
     imagenet_net(os.path.join(OUT, "imagenet_net.npz"))
     mean_teacher(os.path.join(OUT, "mean_teacher.npz"))
+    erfnet_nobn(os.path.join(OUT, "erfnet_nobn.npz"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -520,6 +521,22 @@ def mean_teacher(path):
         res["student_" + k] = student.get_parameter(k).detach().numpy().copy()
         res["teacher_" + k] = teacher.get_parameter(k).detach().numpy().copy()
     np.savez_compressed(path, **res)
+
+
+def erfnet_nobn(path):
+    """eval/erfnet_nobn.ERFNet(20) (the net eval_forwardTime.py times): state_dict layout and eval logits at 1 x 3 x 64 x 128."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "eval"))
+    ref = importlib.import_module("erfnet_nobn")
+    m = ref.ERFNet(20)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(O.make_state_dict(shapes, seed=71), strict=True)
+    m.eval()
+    x = golden_input((1, 3, 64, 128), 141)
+    with torch.no_grad():
+        y = m(x)
+        ye = m(x, only_encode=True)
+    np.savez_compressed(path, keys=np.array([f"{k} {sh}" for k, sh in shapes.items()]), logits=y.numpy(), enc_logits=ye.numpy())
 
 
 def fork_loss_inputs():

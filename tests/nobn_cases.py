@@ -81,3 +81,20 @@ def check_blocks_nobn(golden_dir, device, precision="fp32", tol=1e-3, names=None
         assert_rel(x.grad.cpu().numpy(), g[name + "_dx"], tol, name + " dx")
         assert_rel(blk.layers[0].conv.weight.grad.cpu().numpy(), g[name + "_dw_up"], tol, name + " dw_up")
         assert_rel(blk.layers[-1].conv1x3_2.bias.grad.cpu().numpy(), g[name + "_db_last"], tol, name + " db_last")
+
+
+def check_erfnet_nobn(golden_dir, device, precision="fp32", tol=1e-4):
+    """eval/erfnet_nobn.ERFNet(20): checkpoint layout and eval logits (full net and only_encode) vs the reference's own module."""
+    import os
+    from erfnet_pytorch_b200 import erfnet_nobn
+    from oracle.make_golden import golden_input
+    g = np.load(os.path.join(golden_dir, "erfnet_nobn.npz"))
+    m = erfnet_nobn.ERFNet(20)
+    assert [f"{k} {tuple(v.shape)}" for k, v in m.state_dict().items()] == list(g["keys"])
+    m.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=71), strict=True)
+    m.precision = precision
+    m = m.to(device).eval()
+    x = golden_input((1, 3, 64, 128), 141).to(device)
+    with torch.no_grad():
+        _assert_rel_max(m(x).cpu().numpy(), g["logits"], tol, "erfnet_nobn logits")
+        _assert_rel_max(m(x, only_encode=True).cpu().numpy(), g["enc_logits"], tol, "erfnet_nobn encoder logits")

@@ -61,3 +61,10 @@ def test_nb1d_nobn_tc_vs_oracle(c, d, p):
     for lab, a, b, r in zip(labels, res["tc"], res["generic"], ref):
         assert_rel_l2(a.numpy(), b.numpy(), 2e-2, f"tc vs generic {lab}")
         assert_rel_l2(a.numpy(), r.numpy(), 0.15, f"tc vs oracle {lab}")  # bf16 mask-flip noise, DESIGN.md section 2
+
+
+def test_erfnet_nobn_net(golden_dir):
+    """eval/erfnet_nobn.ERFNet(20) (the net eval_forwardTime.py times): fp32 check mode vs the reference's logits, bf16 within the gate."""
+    from tests.nobn_cases import check_erfnet_nobn
+    check_erfnet_nobn(golden_dir, "cuda", "fp32", tol=1e-4)
+    check_erfnet_nobn(golden_dir, "cuda", "bf16", tol=2e-2)

@@ -196,9 +196,10 @@ def test_iou_eval_kat(golden_dir):
 
 def test_blocks_without_batchnorm(golden_dir):
     """Fork default (use_batchnorm=False): train-mode forward/backward wiring of all three blocks, kernels emulated."""
-    from tests.nobn_cases import check_blocks_nobn
+    from tests.nobn_cases import check_blocks_nobn, check_erfnet_nobn
     with emulated_kernels():
         check_blocks_nobn(golden_dir, "cpu")
+        check_erfnet_nobn(golden_dir, "cpu")
 
 
 def test_fork_losses_host_logic(golden_dir):
