@@ -8,6 +8,8 @@
            max over ranks.  `fwd` carries the inference (eval-mode, BN folded) images/s of the same net.
 `e2e`    = the same training step through the public API with HOST buffers: pinned H2D copy of the step's images
            and labels and a D2H read of the loss inside the timed region.
+`fwd_b1` / `fwd_b32` / `eval_fullres` (ERF_BENCH_EXTRA=0 skips them) = inference at batch 1 (BASELINE configs[0], the eval_forwardTime.py
+           shape: latency), at batch 32 (enough work to fill the 148 SMs) and configs[4] (batch 8 x 1024x2048 forward + argmax + iouEval.addBatch).
 `--impl reference` times the reference's CPU path (the oracle port of its torch arithmetic; the reference is pure
 Python and /root/reference does not exist on the GPU box) on the host cores, bounded sample.
 """
@@ -314,6 +316,21 @@ def main():
         extra["fwd_b32"] = {"images_per_s": BB * world / (big_ms * 1e-3), "ms_per_step": big_ms, "batch": BB,
                             "tc_frac": BB / (big_ms * 1e-3) * GFLOP_FWD_PER_IMG / 1e3 / pk0["tc_sustained"]}
         del gb, xs, xb
+        torch.cuda.empty_cache()
+        # BASELINE configs[0] / eval/eval_forwardTime.py:31-55: batch 1 x 3 x 512 x 1024 forward latency (graph replay; inputs alternate)
+        x1 = [pool_dev[i][0][:1].contiguous() for i in range(2)]
+        g1 = GraphedInference(model, x1[0]) if use_graph else None
+
+        def fwd_one(i):
+            if g1 is not None:
+                g1(x1[i % 2])
+            else:
+                with torch.no_grad():
+                    model(x1[i % 2])
+
+        one_ms, _ = timed(fwd_one, max(10, K), 3)
+        extra["fwd_b1"] = {"workload": "configs[0] shape: 1 x 3 x 512 x 1024 (eval_forwardTime.py), bf16", "ms_per_image": one_ms, "images_per_s": world / (one_ms * 1e-3)}
+        del g1, x1
         torch.cuda.empty_cache()
         HF, WF, BF = 1024, 2048, 8
         gen = torch.Generator(device=dev).manual_seed(7 + rank)
