@@ -173,7 +173,9 @@ def run_reference(args):
     sample = f"{steps} train steps (fwd+weighted CE+bwd+Adam) of batch 1 x 3x{H}x{W} fp32 after {warmup} warm-up, oracle port of the reference's torch ops, {cores} threads"
     line = {"impl": "reference", "metric": "train_images_per_s", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ERFNet({NC}) train step {H}x{W} (config[1]); CPU sample at batch 1"},
+            "config": {"workload": f"ERFNet({NC}) encoder+decoder training, batch {BATCH}/GPU at {H}x{W}, weighted CrossEntropy2d, Adam (BASELINE configs[1])",
+                       "global_batch": BATCH * args.gpus, "parallelism": f"dp{args.gpus}",
+                       "sample": "each CPU step is a bounded sample of that workload: batch 1 (images/s is per image, so the metric is comparable)"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
