@@ -7,8 +7,9 @@ import torch
 
 
 class GraphedInference:
-    """Eval-mode forward of a model for one fixed input shape.  ``__call__(x)`` copies x into a static buffer, replays
-    the captured graph and returns the static output tensor (valid until the next call)."""
+    """Eval-mode forward of a model for one fixed input shape and the weights it had at capture time (the graph holds the packed,
+    BN-folded weight images: build a new GraphedInference after load_state_dict() / an optimiser step).  ``__call__(x)`` copies x into a
+    static buffer, replays the captured graph and returns the static output tensor (valid until the next call)."""
 
     def __init__(self, model, example: torch.Tensor, warmup: int = 2, **fwd_kwargs):
         model.eval()
