@@ -282,8 +282,9 @@ class FlatAdamTrainer:
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_used = [False, False]
         buf = self._stage_buf[k]
-        if buf is None or buf[0].shape != images.shape or buf[1].shape != labels.shape:
-            buf = self._stage_buf[k] = (torch.empty(images.shape, device=dev, dtype=torch.float32), torch.empty(labels.shape, device=dev, dtype=torch.int64))
+        if buf is None or buf[0].shape != images.shape or buf[1].shape != labels.shape or buf[1].dtype != labels.dtype or buf[0].dtype != images.dtype:
+            # labels keep their dtype (int64 class maps, float regression targets of the fork nets); images may be fp32 NCHW or uint8 HWC
+            buf = self._stage_buf[k] = (torch.empty(images.shape, device=dev, dtype=images.dtype), torch.empty(labels.shape, device=dev, dtype=labels.dtype))
             self._stage_used[k] = False
         with torch.cuda.stream(self._h2d_stream):
             if self._stage_used[k]:
