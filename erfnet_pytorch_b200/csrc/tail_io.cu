@@ -222,22 +222,41 @@ __global__ void ingest_u8_kernel(const uint8_t* __restrict__ in, long long n_px,
     const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
     const uint32_t b[12] = {w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, w0 >> 24, w1 & 255, (w1 >> 8) & 255, (w1 >> 16) & 255, w1 >> 24,
                             w2 & 255, (w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24};
+    float v[4][4];
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
-      T* dst = out + (size_t)(gi * 4 + px) * ld;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        v[c] = __fdiv_rn((float)b[px * 3 + c], 255.f);
-        if (mean || stdv) v[c] = __fdiv_rn(v[c] - m[c], s[c]);
+        v[px][c] = __fdiv_rn((float)b[px * 3 + c], 255.f);
+        if (mean || stdv) v[px][c] = __fdiv_rn(v[px][c] - m[c], s[c]);
       }
-      if (ld == 4) {   // the models' input pitch: one 8-byte (bf16) / 16-byte (fp32) store per pixel, contiguous across the thread's 4 pixels
-        Vec<T, 4> o;
-        o.v[0] = v[0]; o.v[1] = v[1]; o.v[2] = v[2]; o.v[3] = 0.f;
-        o.store(dst);
+      v[px][3] = 0.f;
+    }
+    if (ld == 4) {   // the models' input pitch: the thread's 4 pixels are 32 (bf16) / 64 (fp32) contiguous bytes -> 16-byte stores
+      T* dst = out + (size_t)gi * 16;
+      if (sizeof(T) == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          Vec<T, 8> o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] = v[2 * h + (e >> 2)][e & 3];
+          o.store(dst + 8 * h);
+        }
       } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dst[c] = from_f<T>(v[c]);
+        for (int px = 0; px < 4; ++px) {
+          Vec<T, 4> o;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o.v[e] = v[px][e];
+          o.store(dst + 4 * px);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        T* dst = out + (size_t)(gi * 4 + px) * ld;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c] = from_f<T>(v[px][c]);
         for (int c = 3; c < ld; ++c) dst[c] = from_f<T>(0.f);
       }
     }
@@ -369,7 +388,7 @@ extern "C" int erf_ema_update(float* teacher, const float* student, long long n,
 extern "C" int erf_ingest_u8(const void* in, long long n_px, int ld, const float* mean, const float* stdv, void* out, int dtype,
                              erf_stream_t stream) {
   ERF_CHECK_ARG(in && out && n_px > 0 && ld >= 3, "erf_ingest_u8: bad arguments n_px=%lld ld=%d", n_px, ld);
-  ERF_CHECK_ARG(((uintptr_t)in & 3) == 0, "erf_ingest_u8: the uint8 image must be 4-byte aligned");
+  ERF_CHECK_ARG(((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0, "erf_ingest_u8: the uint8 image must be 4-byte aligned and the output 16-byte aligned");
   const int g = grid_for((n_px + 3) / 4, 256);
   if (dtype == ERF_F32) ingest_u8_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, n_px, ld, mean, stdv, (float*)out);
   else if (dtype == ERF_BF16) ingest_u8_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, n_px, ld, mean, stdv, (__nv_bfloat16*)out);
