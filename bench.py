@@ -200,7 +200,7 @@ def main():
     from erfnet_pytorch_b200 import erfnet as E
     from erfnet_pytorch_b200 import ops
     from erfnet_pytorch_b200.parallel import FlatAdamTrainer
-    from oracle import erfnet_oracle as O  # weights generator only (deterministic "trained-like" init)
+    from erfnet_pytorch_b200.synthetic import synthetic_state_dict   # deterministic "trained-like" init (the GPU arm never touches oracle/)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,7 +214,7 @@ def main():
     B = args.batch
 
     model = E.ERFNet(NC)
-    model.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), 0))
+    model.load_state_dict(synthetic_state_dict(model, 0))
     model.precision = args.precision
     model = model.to(dev)
     trainer = FlatAdamTrainer(model, weight=torch.linspace(0.5, 1.5, NC))

@@ -280,3 +280,18 @@ def test_flat_trainer_generic_loss_host_logic():
     from tests.flat_generic_cases import check_flat_generic
     with emulated_kernels():
         check_flat_generic("cpu")
+
+
+def test_synthetic_weights_match_the_oracle_generator():
+    """bench.py / tools use erfnet_pytorch_b200.synthetic (the GPU arm must not touch oracle/); it must stay identical to the oracle's copy
+    that the golden fixtures were generated with."""
+    from erfnet_pytorch_b200 import erfnet_imagenet, synthetic
+    shapes = O.erfnet_param_shapes(20)
+    a, b = synthetic.make_state_dict(shapes, 3), O.make_state_dict(shapes, 3)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    m = erfnet_imagenet.ERFNet(10)
+    c = synthetic.synthetic_state_dict(m, 5)
+    d = O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 5)
+    assert all(torch.equal(c[k], d[k]) for k in d)
+    main_body = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read().split("def main()")[1]
+    assert "from oracle" not in main_body and "import oracle" not in main_body       # only cpu_reference_run() (the CPU baseline leg) imports it

@@ -12,7 +12,7 @@ from erfnet_pytorch_b200 import erfnet_imagenet as EI  # noqa: E402
 from erfnet_pytorch_b200 import evaluation_functions as EV  # noqa: E402
 from erfnet_pytorch_b200 import net_regression_ladder as NL  # noqa: E402
 from erfnet_pytorch_b200.optim import FlatSGD  # noqa: E402
-from oracle import erfnet_oracle as O  # noqa: E402
+from erfnet_pytorch_b200 import synthetic as O  # noqa: E402
 
 
 def timed(fn, steps=10, warm=3):

@@ -8,11 +8,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import NC, synth_batch  # noqa: E402
 from erfnet_pytorch_b200 import erfnet as E  # noqa: E402
 from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
-from oracle import erfnet_oracle as O  # noqa: E402
+from erfnet_pytorch_b200 import synthetic as O  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 model = E.ERFNet(NC)
-model.load_state_dict(O.make_state_dict(O.erfnet_param_shapes(NC), 0))
+model.load_state_dict(O.synthetic_state_dict(model, 0))
 model = model.cuda()
 x, y = synth_batch(torch, 0, B)
 x, y = x.cuda(), y.cuda()
