@@ -295,3 +295,30 @@ def test_synthetic_weights_match_the_oracle_generator():
     assert all(torch.equal(c[k], d[k]) for k in d)
     main_body = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read().split("def main()")[1]
     assert "from oracle" not in main_body and "import oracle" not in main_body       # only cpu_reference_run() (the CPU baseline leg) imports it
+
+
+def test_32_channel_folding_map_and_its_transpose():
+    """The [W/2, 64]-folded view of a 32-channel block (erfnet.non_bottleneck_1d._folded_weights): a 3x1 / 1x3 conv with the folded
+    weights on the folded tensor equals the original conv, and _unfold_grads is the exact transpose of the folding map."""
+    import torch.nn.functional as F
+    from erfnet_pytorch_b200 import erfnet_blocks as EB
+    torch.manual_seed(0)
+    blk = EB.non_bottleneck_1d(32, 0.0, 1)
+    for p in blk.parameters():
+        torch.nn.init.uniform_(p, -0.5, 0.5)
+    n, h, w = 2, 6, 10
+    x = torch.randn(n, 32, h, w)
+    xf = x.permute(0, 2, 3, 1).reshape(n, h, w // 2, 64).permute(0, 3, 1, 2)          # folded pixel = (even column, odd column)
+    convs = (blk.conv3x1_1, blk.conv1x3_1, blk.conv3x1_2, blk.conv1x3_2)
+    for i, ((w64, b64), conv) in enumerate(zip(blk._folded_weights(), convs)):
+        ref = conv(x)
+        pad = (1, 0) if i % 2 == 0 else (0, 1)
+        got = F.conv2d(xf, w64, b64, padding=pad)
+        got = got.permute(0, 2, 3, 1).reshape(n, h, w, 32).permute(0, 3, 1, 2)
+        np.testing.assert_allclose(got.detach().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+        # transpose: <fold(w), g> == <w, unfold(g)> for arbitrary g
+        g64, gb = torch.randn_like(w64), torch.randn(64)
+        dw, db = blk._unfold_grads(i, g64, gb)
+        assert dw.shape == conv.weight.shape and db.shape == conv.bias.shape
+        np.testing.assert_allclose(float((w64 * g64).sum()), float((conv.weight.detach() * dw).sum()), rtol=1e-4)
+        np.testing.assert_allclose(float((b64 * gb).sum()), float((conv.bias.detach() * db).sum()), rtol=1e-4)
