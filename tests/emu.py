@@ -400,15 +400,89 @@ _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc"
           "avgpool_fwd", "avgpool_bwd", "linear_fwd", "linear_bwd", "ce_rows_fwd", "ce_rows_bwd", "sgd_step", "ema_update", "ingest_u8", "label_lut", "colorize"]
 
 
+# ---- optional: contracts of the tcgen05 3-tap conv entry points, so that the HOST wiring of the tensor-core path (operand images for forward and
+# data gradient, epilogue options, statistics / column sums, weight-gradient accumulation, the folded 32-channel block) runs on the CPU too.
+# An "image" here is simply Wt[t][co][ci] in fp32 (the real one is the same matrix in bf16, swizzled for shared memory).
+def _tc_image(w, dgrad=False):
+    co, ci = w.shape[:2]
+    wt = w.detach().float().reshape(co, ci, 3).permute(2, 0, 1)      # [t][co][ci]
+    if dgrad:
+        wt = wt.flip(0).transpose(1, 2)                              # taps mirrored, channels transposed
+    return wt.contiguous()
+
+
+def tc_conv1d_tc_supported(c, w, dil, dtype):
+    return c in (16, 64, 128) and w >= 128 and w % 128 == 0 and 1 <= dil <= 32
+
+
+def tc_pack_conv1d_tc(w, dgrad=False):
+    return _tc_image(w, dgrad)
+
+
+def tc_pack_conv1d_tc_pair(w):
+    return _tc_image(w, False), _tc_image(w, True)
+
+
+def tc_conv1d_tc(x, w_img, bias, horizontal, dil, relu=False, res=None, mask=None, stats=None, colsum=None, static_w=False):
+    assert not (res is not None and mask is not None)
+    c = x.shape[-1]
+    xi = x.float().permute(0, 3, 1, 2)
+    wt = w_img.permute(1, 2, 0)                                       # [co][ci][t]
+    wt = wt.unsqueeze(2) if horizontal else wt.unsqueeze(3)           # [co,ci,1,3] / [co,ci,3,1]
+    y = F.conv2d(xi, wt, None, 1, (0, dil) if horizontal else (dil, 0), (1, dil) if horizontal else (dil, 1)).permute(0, 2, 3, 1)
+    if bias is not None:
+        y = y + bias
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = y.relu()
+    if mask is not None:
+        y = y * (mask.float() > 0)
+    out = y.to(x.dtype)
+    if stats is not None:      # statistics of the STORED output
+        stats[:c] += out.double().sum((0, 1, 2))
+        stats[c:] += (out.double() ** 2).sum((0, 1, 2))
+    if colsum is not None:
+        colsum += out.float().sum((0, 1, 2))
+    return out
+
+
+def tc_conv1d_wgrad_tc_supported(c, w, dil, dtype):
+    return c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
+
+
+@torch.enable_grad()
+def tc_conv1d_wgrad_tc(x, dy, horizontal, dil, dw_out=None, db_out=None, want_bias=True):
+    c = x.shape[-1]
+    xi = x.detach().float().permute(0, 3, 1, 2)
+    wt = torch.zeros((c, c, 1, 3) if horizontal else (c, c, 3, 1), requires_grad=True)
+    y = F.conv2d(xi, wt, None, 1, (0, dil) if horizontal else (dil, 0), (1, dil) if horizontal else (dil, 1))
+    (g,) = torch.autograd.grad(y, wt, dy.detach().float().permute(0, 3, 1, 2))
+    dw = g if dw_out is None else dw_out.add_(g)
+    db = None
+    if want_bias:
+        s = dy.float().sum((0, 1, 2))
+        db = s if db_out is None else db_out.add_(s)
+    return dw, db
+
+
+_TC_NAMES = ["conv1d_tc_supported", "pack_conv1d_tc", "pack_conv1d_tc_pair", "conv1d_tc", "conv1d_wgrad_tc_supported", "conv1d_wgrad_tc"]
+
+
 @contextlib.contextmanager
-def emulated_kernels():
-    """Swap erfnet_pytorch_b200.ops kernels for the CPU emulations above (tests only)."""
-    saved = {n: getattr(ops, n) for n in _NAMES}
+def emulated_kernels(tc=False):
+    """Swap erfnet_pytorch_b200.ops kernels for the CPU emulations above (tests only).  tc=True also emulates the tcgen05 3-tap conv entry
+    points, so blocks take their tensor-core code path (at widths that are multiples of 128) instead of the generic one."""
+    names = _NAMES + (_TC_NAMES if tc else [])
+    saved = {n: getattr(ops, n) for n in names}
     saved["EMULATED"] = ops.EMULATED
     try:
         ops.EMULATED = True
         for n in _NAMES:
             setattr(ops, n, globals()[n])
+        if tc:
+            for n in _TC_NAMES:
+                setattr(ops, n, globals()["tc_" + n])
         yield
     finally:
         for n, f in saved.items():

@@ -322,3 +322,72 @@ def test_32_channel_folding_map_and_its_transpose():
         assert dw.shape == conv.weight.shape and db.shape == conv.bias.shape
         np.testing.assert_allclose(float((w64 * g64).sum()), float((conv.weight.detach() * dw).sum()), rtol=1e-4)
         np.testing.assert_allclose(float((b64 * gb).sum()), float((conv.bias.detach() * db).sum()), rtol=1e-4)
+
+
+@pytest.mark.parametrize("c,d,p", [(64, 1, 0.3), (128, 4, 0.0), (16, 1, 0.0), (32, 1, 0.0)])
+def test_tensor_core_code_path_host_wiring(c, d, p):
+    """The blocks' tensor-core code path on the CPU (tcgen05 entry points emulated by their contracts): forward / data-gradient operand images,
+    epilogue options, bias-gradient column sums, weight-gradient accumulation -- and for C = 32 the [W/2, 64]-folded twin with its gradient
+    adapter -- against the fp32 oracle of the BN-free block (train/erfnet_blocks.py:33-73)."""
+    from erfnet_pytorch_b200 import erfnet as E
+    from erfnet_pytorch_b200 import erfnet_blocks as EB
+    torch.manual_seed(3)
+    n, h, w = 1, 5, 256
+    blk = EB.non_bottleneck_1d(c, p, d, use_dropout=True)
+    sd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=21)
+    blk.load_state_dict({k[4:]: v for k, v in sd.items()})
+    blk.precision = "fp32"
+    blk.train()
+    x0 = torch.rand(n, c, h, w) - 0.3
+    gy = torch.rand(n, c, h, w) - 0.5
+    drop = torch.nn.functional.dropout2d(torch.ones(n, c, 1, 1), p, True).reshape(n, c) if p else None
+    calls = []
+    with emulated_kernels(tc=True):
+        real = ops.conv1d_tc
+        ops.conv1d_tc = lambda x, *a, **k: (calls.append(x.shape[-1]), real(x, *a, **k))[1]
+        x = x0.clone().requires_grad_(True)
+        with E.fixed_dropout({blk: drop} if drop is not None else {}):
+            y = blk(x)
+        y.backward(gy)
+    assert calls and all(ch == (64 if c == 32 else c) for ch in calls)          # the tensor-core entry point ran (on the folded view for C = 32)
+    xo = x0.clone().requires_grad_(True)
+    sdo = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    yo = O.non_bottleneck_1d(xo, sdo, "blk", d, dropprob=p, training=True, drop_scale=None if drop is None else drop.view(n, c, 1, 1),
+                             use_batchnorm=False)
+    yo.backward(gy)
+    assert_rel(y.detach().numpy(), yo.detach().numpy(), 1e-5, "y")
+    assert_rel(x.grad.numpy(), xo.grad.numpy(), 1e-4, "dx")
+    for cn in ("conv3x1_1", "conv1x3_1", "conv3x1_2", "conv1x3_2"):
+        assert_rel(getattr(blk, cn).weight.grad.numpy(), sdo[f"blk.{cn}.weight"].grad.numpy(), 1e-4, cn + " dw")
+        assert_rel(getattr(blk, cn).bias.grad.numpy(), sdo[f"blk.{cn}.bias"].grad.numpy(), 1e-4, cn + " db")
+
+
+@pytest.mark.parametrize("c,d", [(64, 1), (128, 8), (16, 1)])
+def test_tensor_core_code_path_with_batchnorm(c, d):
+    """The same for the Cityscapes block with train-mode BatchNorm (eval/erfnet.py:26-61): batch statistics taken in the conv epilogue,
+    BN backward, running statistics -- tensor-core entry points emulated, against the fp32 oracle."""
+    from erfnet_pytorch_b200 import erfnet as E
+    torch.manual_seed(4)
+    n, h, w = 2, 3, 128
+    blk = E.non_bottleneck_1d(c, 0.0, d)
+    sd = O.make_state_dict({"blk." + k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=22)
+    blk.load_state_dict({k[4:]: v for k, v in sd.items()})
+    blk.precision = "fp32"
+    blk.train()
+    x0 = torch.rand(n, c, h, w) - 0.3
+    gy = torch.rand(n, c, h, w) - 0.5
+    with emulated_kernels(tc=True):
+        x = x0.clone().requires_grad_(True)
+        y = blk(x)
+        y.backward(gy)
+    xo = x0.clone().requires_grad_(True)
+    sdo = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    yo = O.non_bottleneck_1d(xo, sdo, "blk", d, dropprob=0.0, training=True)
+    yo.backward(gy)
+    assert_rel(y.detach().numpy(), yo.detach().numpy(), 1e-4, "y")
+    assert_rel(x.grad.numpy(), xo.grad.numpy(), 1e-3, "dx")
+    for name in ("conv3x1_1.weight", "conv1x3_2.weight", "bn1.weight", "bn2.bias", "conv3x1_2.bias"):
+        mod, attr = name.split(".")
+        assert_rel(getattr(getattr(blk, mod), attr).grad.numpy(), sdo["blk." + name].grad.numpy(), 1e-3, name)
+    assert_rel(blk.bn2.running_var.numpy(), sdo["blk.bn2.running_var"].detach().numpy(), 1e-4, "running_var")
+    assert int(blk.bn1.num_batches_tracked) == int(sdo["blk.bn1.num_batches_tracked"])
