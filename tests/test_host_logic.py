@@ -391,3 +391,34 @@ def test_tensor_core_code_path_with_batchnorm(c, d):
         assert_rel(getattr(getattr(blk, mod), attr).grad.numpy(), sdo["blk." + name].grad.numpy(), 1e-3, name)
     assert_rel(blk.bn2.running_var.numpy(), sdo["blk.bn2.running_var"].detach().numpy(), 1e-4, "running_var")
     assert int(blk.bn1.num_batches_tracked) == int(sdo["blk.bn1.num_batches_tracked"])
+
+
+def test_whole_net_on_the_tensor_core_code_path():
+    """ERFNet(20) training forward + loss + backward at a tensor-core-eligible size (16 x 1024: every 3-tap conv takes the emulated tcgen05 entry
+    points, statistics fused in their epilogues) against the fp32 oracle: logits, loss, and the decoder-side gradients."""
+    from erfnet_pytorch_b200.evaluation_functions import CrossEntropyLoss2d
+    from oracle.make_golden import golden_labels
+    m, sd = _model()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    x = golden_input((1, 3, 16, 1024), 181)
+    y = golden_labels((1, 16, 1024), 182)
+    calls = []
+    with emulated_kernels(tc=True):
+        real = ops.conv1d_tc
+        ops.conv1d_tc = lambda t, *a, **k: (calls.append(t.shape[-1]), real(t, *a, **k))[1]
+        logits = m(x)
+        loss = CrossEntropyLoss2d()(logits, y)
+        loss.backward()
+    assert sorted(set(calls)) == [16, 64, 128] and len(calls) == 2 * 68     # 68 convs forward + 68 data gradients = the 136 launches bench.py's roofline leg reports
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    ref = O.erfnet_forward(x, sdo, training=True, dropprob=0.0)
+    lref = O.cross_entropy_2d(ref, y)
+    lref.backward()
+    # train-mode BatchNorm over 2 x 128 samples per channel at 1/8 resolution amplifies fp32 summation-order differences a little above the 1e-4 gate
+    assert_rel(logits.detach().numpy(), ref.detach().numpy(), 5e-4, "logits")
+    assert abs(float(loss.detach()) - float(lref.detach())) <= 1e-4 * abs(float(lref.detach()))
+    for k in ("decoder.output_conv.weight", "decoder.layers.5.conv1x3_2.weight", "decoder.layers.1.bn2.weight"):
+        assert_rel(m.get_parameter(k).grad.numpy(), sdo[k].grad.numpy(), WHOLE_NET_GRAD_TOL, k)
