@@ -155,6 +155,7 @@ class _CERowsFn(torch.autograd.Function):
     def forward(ctx, logits, target, ignore_index):
         logits = logits.contiguous()
         acc, lse, rank = ops.ce_rows_fwd(logits, target.contiguous(), ignore_index)
+        ops.loss_global_reduce(acc)              # data-parallel training: (sum of -log p, #rows) over the global batch
         ctx.save_for_backward(logits, target, lse, acc)
         ctx.ignore_index = ignore_index
         ctx.mark_non_differentiable(rank)

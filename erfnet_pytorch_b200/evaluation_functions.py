@@ -52,6 +52,7 @@ class _MaskedLossFn(torch.autograd.Function):
             raise RuntimeError("masked loss: empty target")
         acc = torch.zeros(2, device=tf.device, dtype=torch.float64)
         ops.masked_loss_fwd(kind, af, bf, pf, tf, eps, acc)
+        ops.loss_global_reduce(acc)              # data-parallel training: (sum, #labelled pixels) over the global batch
         ctx.kind, ctx.eps, ctx.scale = kind, eps, scale
         ctx.shapes = (a.shape, None if b is None else b.shape)
         ctx.save_for_backward(af, bf, pf, tf, acc)

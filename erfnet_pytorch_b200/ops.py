@@ -850,6 +850,22 @@ def ce_fwd_bwd(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torc
     return dlog
 
 
+# ---- global-batch loss normalisation (data-parallel training through a criterion, parallel.FlatAdamTrainer(loss_fn=...)) --------------------
+# The reference computes its criterion on the outputs nn.DataParallel GATHERED from all replicas (train/main.py:869-874), i.e. the mean runs over the
+# global batch.  While LOSS_REDUCE is set (a callable that sum-all-reduces a tensor in place), every criterion of this package reduces its
+# (sum, count) accumulators across ranks before dividing, so its value is the global mean and its gradient kernels divide by the global count:
+# SUM-all-reduced parameter gradients are then exactly the reference's.  LOSS_REDUCED records that a criterion did so.
+LOSS_REDUCE = None
+LOSS_REDUCED = False
+
+
+def loss_global_reduce(t: torch.Tensor):
+    global LOSS_REDUCED
+    if LOSS_REDUCE is not None:
+        LOSS_REDUCE(t)
+        LOSS_REDUCED = True
+
+
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, c: int,
                   nchw: bool, want_grad: bool):
     """Returns (loss_sum fp32[1], wsum fp32[1], dlogits or None); loss = loss_sum / wsum."""
@@ -857,7 +873,9 @@ def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[t
     acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
     wsum, lsum = acc[0:1], acc[1:2]
     ce_weight_sum(target, weight, c, ignore_index, wsum)
+    loss_global_reduce(wsum)                       # the gradient is normalised by the global valid-pixel weight
     dlog = ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw, want_grad)
+    loss_global_reduce(lsum)
     return lsum, wsum, dlog
 
 

@@ -39,7 +39,9 @@ class FlatAdamTrainer:
                  process_group=None, num_classes=None, loss_fn=None, sgd_momentum=None):
         """loss_fn: None = the fused Cityscapes path (ERFNet.forward_nhwc + weighted CE kernel).  Otherwise any of the nets with any
         criterion: ``loss_fn(model(images), *targets)`` -> scalar loss (e.g. ``lambda out, t: L1LossMasked()(out, t)`` for the fork's
-        regression nets, train/main.py:174-184); the loss is then the mean over the RANK's batch and gradients are averaged over ranks."""
+        regression nets, train/main.py:174-184).  At world_size > 1 this package's criteria normalise by the GLOBAL batch (their (sum, count)
+        accumulators are all-reduced, ops.LOSS_REDUCE), which with SUM-all-reduced gradients is exactly the reference's loss over the outputs
+        gathered by nn.DataParallel; a foreign criterion's per-rank means are averaged instead."""
         self.model = model
         self.loss_fn = loss_fn
         self.sgd_momentum = sgd_momentum   # not None: torch.optim.SGD(lr, momentum, weight_decay) semantics (imagenet/main.py:83-85) instead of Adam;
@@ -170,11 +172,19 @@ class FlatAdamTrainer:
             out = self.model(images)
         finally:
             _erfnet._PREPACKED_FRESH = False
-        loss = self.loss_fn(out, *targets)
+        if self.world > 1:      # this package's criteria then normalise by the GLOBAL batch (see ops.LOSS_REDUCE), like the reference under DataParallel
+            ops.LOSS_REDUCE = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+            ops.LOSS_REDUCED = False
+        try:
+            loss = self.loss_fn(out, *targets)
+        finally:
+            ops.LOSS_REDUCE = None
+        # a foreign criterion (plain torch ops) yields the rank's own mean: average those instead
+        self._grad_scale = 1.0 if (self.world == 1 or ops.LOSS_REDUCED) else 1.0 / self.world
         self._backward(loss, None)
         self._finish_buckets()
         loss = loss.detach()
-        if self.world > 1:
+        if self.world > 1 and not ops.LOSS_REDUCED:
             loss = loss.clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.pg)
             loss /= self.world
@@ -232,7 +242,7 @@ class FlatAdamTrainer:
 
     def optimizer_step(self):
         self.step_count += 1
-        gs = 1.0 / self.world if self.loss_fn is not None else 1.0   # generic path: ranks' mean losses are averaged (the CE path is pre-normalised)
+        gs = getattr(self, "_grad_scale", 1.0) if self.loss_fn is not None else 1.0   # 1 when the loss was normalised by the global batch
         if self.sgd_momentum is not None:
             # the momentum buffer starts at zero, so momentum * buf + d on the first step equals torch's "buf = d" initialisation
             ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr, self.sgd_momentum, self.wd, False, gs)

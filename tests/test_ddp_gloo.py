@@ -111,7 +111,8 @@ def _worker_generic(rank, world, port, ret):
     m.precision = "fp32"
     m.load_state_dict(O.make_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=41 + rank))   # rank 0's weights win
     x = golden_input((2, 3, 32, 64), 131)
-    t = golden_input((2, 32, 64), 132) * 2.0          # every pixel labelled: the mean of the ranks' means is the global mean
+    t = golden_input((2, 32, 64), 132) * 2.0
+    t[0, :20] = -1.0                                  # rank 0 has far fewer labelled pixels: only a global-batch normalisation reproduces one process
     crit = EV.L1LossMasked()
     with emulated_kernels():
         tr = FlatAdamTrainer(m, loss_fn=lambda out, tgt: crit(out, tgt))
@@ -121,8 +122,9 @@ def _worker_generic(rank, world, port, ret):
 
 
 def test_generic_loss_two_ranks_match_one_process():
-    """FlatAdamTrainer(loss_fn=...) at world_size 2 (bucketed SUM all-reduce, gradients scaled by 1/world in the optimiser kernel) ==
-    one process on the concatenated batch (autograd + torch.optim.Adam, train/main.py:213)."""
+    """FlatAdamTrainer(loss_fn=...) at world_size 2 (criterion normalised by the all-reduced global labelled-pixel count, bucketed SUM
+    all-reduce of the gradients) == one process on the concatenated batch (autograd + torch.optim.Adam, train/main.py:213), with very
+    different labelled-pixel counts on the two ranks."""
     mp.set_start_method("spawn", force=True)
     ret = mp.Manager().dict()
     port = 31500 + os.getpid() % 2000
@@ -142,6 +144,7 @@ def test_generic_loss_two_ranks_match_one_process():
     m.train()
     x = golden_input((2, 3, 32, 64), 131)
     t = golden_input((2, 32, 64), 132) * 2.0
+    t[0, :20] = -1.0
     opt = torch.optim.Adam(m.parameters(), 1e-4, (0.9, 0.999), eps=1e-4, weight_decay=1e-6)
     ref = []
     with emulated_kernels():
