@@ -71,6 +71,7 @@ _SIGNATURES = {
     "erf_softmax_nhwc_bwd": [_vp, _vp, _vp, _i, _ll, _i, _vp, _i, _i, _vp],
     "erf_adam_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp],
     "erf_adam_step_dev": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
+    "erf_adam_step_graph": [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _vp, _f, _vp],
     "erf_conv1d_tc_supported": [_i, _i, _i],
     "erf_conv1d_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "erf_conv1d_pair_tc_supported": [_i, _i, _i],
@@ -91,6 +92,7 @@ _SIGNATURES = {
     "erf_ce_rows_fwd": [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp],
     "erf_ce_rows_bwd": [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp],
     "erf_sgd_step": [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _f, _vp],
+    "erf_sgd_step_graph": [_vp, _vp, _vp, _ll, _vp, _f, _f, _vp],
     "erf_ema_update": [_vp, _vp, _ll, _f, _vp],
     "erf_ingest_u8": [_vp, _ll, _i, _vp, _vp, _vp, _i, _vp],
     "erf_label_lut": [_vp, _i, _ll, _vp, _i, _vp, _vp],

@@ -331,8 +331,12 @@ __global__ void pack_conv1d_tc_batched_kernel(const erf_pack1d_entry* __restrict
 // ------------------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                             float lr_over_bc1, float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2, float grad_scale,
-                            const int* __restrict__ step_dev, float lr) {
+                            const int* __restrict__ step_dev, float lr, const float* __restrict__ hyper_dev) {
   pdl_enter();
+  if (hyper_dev) {  // CUDA-graph friendly: learning rate and weight decay live on the device (a captured launch bakes by-value arguments in)
+    lr = hyper_dev[0];
+    wd = hyper_dev[1];
+  }
   if (step_dev) {  // CUDA-graph friendly: the step count lives on the device (incremented by adam_step_inc_kernel)
     const double st = (double)*step_dev;
     lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, st)));
@@ -592,7 +596,7 @@ extern "C" int erf_adam_step(float* p, const float* g, float* m, float* v, long 
   double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   unsigned grid = (unsigned)((n + 255) / 256);
   launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), grad_scale,
-                                                      nullptr, lr);
+                                                      nullptr, lr, nullptr);
   ERF_CHECK_LAUNCH("erf_adam_step");
   return ERF_OK;
 }
@@ -602,8 +606,20 @@ extern "C" int erf_adam_step_dev(float* p, const float* g, float* m, float* v, l
   ERF_CHECK_ARG(p && g && m && v && n > 0 && step_dev, "erf_adam_step_dev: bad arguments");
   unsigned grid = (unsigned)((n + 255) / 256);
   launch_pdl(adam_step_inc_kernel, dim3(1), dim3(1), 0, (cudaStream_t)((cudaStream_t)stream), step_dev);
-  launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr);
+  launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 0.f, grad_scale, step_dev, lr,
+             nullptr);
   ERF_CHECK_LAUNCH("erf_adam_step_dev");
+  return ERF_OK;
+}
+
+extern "C" int erf_adam_step_graph(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, float beta1, float beta2, float eps,
+                                   int* step_dev, float grad_scale, erf_stream_t stream) {
+  ERF_CHECK_ARG(p && g && m && v && n > 0 && step_dev && hyper_dev, "erf_adam_step_graph: bad arguments");
+  unsigned grid = (unsigned)((n + 255) / 256);
+  launch_pdl(adam_step_inc_kernel, dim3(1), dim3(1), 0, (cudaStream_t)((cudaStream_t)stream), step_dev);
+  launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)((cudaStream_t)stream), p, g, m, v, n, 0.f, beta1, beta2, eps, 0.f, 0.f, grad_scale, step_dev, 0.f,
+             hyper_dev);
+  ERF_CHECK_LAUNCH("erf_adam_step_graph");
   return ERF_OK;
 }
 

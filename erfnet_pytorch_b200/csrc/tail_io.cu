@@ -189,7 +189,11 @@ __global__ void ce_rows_bwd_kernel(const float* __restrict__ logits, const int64
 
 // ---- torch.optim.SGD(lr, momentum, weight_decay) (imagenet/main.py:83-85) over one flat fp32 buffer ---------------------------------
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n, float lr,
-                                float momentum, float wd, int first, float grad_scale) {
+                                float momentum, float wd, int first, float grad_scale, const float* __restrict__ hyper_dev) {
+  if (hyper_dev) {   // CUDA-graph replay: lr / weight decay are read from device memory (see erf_sgd_step_graph)
+    lr = hyper_dev[0];
+    wd = hyper_dev[1];
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float w = p[i];
     float d = fmaf(wd, w, g[i] * grad_scale);
@@ -373,8 +377,16 @@ extern "C" int erf_ce_rows_bwd(const float* logits, const long long* target, int
 extern "C" int erf_sgd_step(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay, int first_step,
                             float grad_scale, erf_stream_t stream) {
   ERF_CHECK_ARG(p && g && n > 0 && (momentum == 0.f || buf), "erf_sgd_step: bad arguments");
-  sgd_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, grad_scale);
+  sgd_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, grad_scale, nullptr);
   ERF_CHECK_LAUNCH("erf_sgd_step");
+  return ERF_OK;
+}
+
+extern "C" int erf_sgd_step_graph(float* p, const float* g, float* buf, long long n, const float* hyper_dev, float momentum, float grad_scale,
+                                  erf_stream_t stream) {
+  ERF_CHECK_ARG(p && g && n > 0 && hyper_dev && (momentum == 0.f || buf), "erf_sgd_step_graph: bad arguments");
+  sgd_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n, 0.f, momentum, 0.f, 0, grad_scale, hyper_dev);
+  ERF_CHECK_LAUNCH("erf_sgd_step_graph");
   return ERF_OK;
 }
 

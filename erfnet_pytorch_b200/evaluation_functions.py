@@ -26,13 +26,28 @@ class CrossEntropyLoss2d(torch.nn.Module):
     ``outputs``: NCHW fp32 logits (the reference API) -- or the model's internal NHWC logits
     (``ERFNet.forward_nhwc``) with ``nhwc_classes=C``, which skips the NCHW fp32 round trip."""
 
-    def __init__(self, weight=None, ignore_index=-1):
+    def __init__(self, weight=None, ignore_index=-1, strict_labels=False):
+        """strict_labels: the kernels skip EVERY label outside [0, C) (that is how ignore_index is honoured), whereas torch's
+        nn.CrossEntropyLoss asserts on an out-of-range label that is not ignore_index (an un-relabelled 255, an off-by-one class id).
+        strict_labels=True restores that behaviour with a host check of target.min() / max() (one device synchronisation per call:
+        meant for the first steps of a run / debugging a data pipeline, not for the steady state)."""
         super().__init__()
         self.register_buffer("weight", None if weight is None else torch.as_tensor(weight, dtype=torch.float32))
         self.ignore_index = ignore_index
+        self.strict_labels = strict_labels
+
+    def _check_labels(self, targets, c):
+        if targets.numel() == 0:
+            return
+        bad = (targets != self.ignore_index) & ((targets < 0) | (targets >= c))
+        if bool(bad.any()):
+            v = int(targets[bad][0])
+            raise RuntimeError(f"CrossEntropyLoss2d: target {v} is out of bounds for {c} classes (ignore_index = {self.ignore_index})")
 
     def forward(self, outputs, targets, nhwc_classes=None):
         w = None if self.weight is None else self.weight.to(outputs.device)
+        if self.strict_labels:
+            self._check_labels(targets, nhwc_classes if nhwc_classes is not None else outputs.shape[1])
         if nhwc_classes is not None:
             return _CEFn.apply(outputs, targets, w, self.ignore_index, nhwc_classes, False)
         return _CEFn.apply(outputs.contiguous(), targets, w, self.ignore_index, outputs.shape[1], True)
@@ -50,6 +65,7 @@ class _MaskedLossFn(torch.autograd.Function):
         tf = ops._f32c(target, "target")
         if tf.numel() == 0:
             raise RuntimeError("masked loss: empty target")
+        ops.check_masked_loss_shapes(kind, af, bf, pf, tf)
         acc = torch.zeros(2, device=tf.device, dtype=torch.float64)
         ops.masked_loss_fwd(kind, af, bf, pf, tf, eps, acc)
         ops.loss_global_reduce(acc)              # data-parallel training: (sum, #labelled pixels) over the global batch

@@ -826,10 +826,64 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbe
     return (dy, dgamma, dbeta, gm) if want_masked else (dy, dgamma, dbeta)
 
 
+def _same_device(what: str, ref: torch.Tensor, **tensors):
+    """The kernels take raw pointers: a tensor on another device (or on the host) would be dereferenced on `ref`'s GPU."""
+    if not EMULATED and not ref.is_cuda:
+        raise RuntimeError(f"{what}: erfnet_pytorch_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    for name, t in tensors.items():
+        if t is not None and t.device != ref.device:
+            raise RuntimeError(f"{what}: {name} is on {t.device}, expected {ref.device}")
+
+
+def check_ce_shapes(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], c: int, nchw: bool):
+    """Host-side contract of the CE kernels (they loop over target.numel() pixels and read / WRITE c values per pixel of the logits):
+    NCHW logits [N,c,H,W] or NHWC logits [N,H,W,ld >= c] against a target [N,H,W] on the same device.  The reference's
+    nn.CrossEntropyLoss raises the same kind of size-mismatch error (train/evaluation_functions.py:11-14)."""
+    _same_device("CrossEntropyLoss2d", logits, target=target, weight=weight)
+    if logits.dim() != 4:
+        raise RuntimeError(f"CrossEntropyLoss2d: expected 4-D logits, got shape {tuple(logits.shape)}")
+    if nchw:
+        n, ch, h, w = logits.shape
+        if ch != c:
+            raise RuntimeError(f"CrossEntropyLoss2d: logits have {ch} channels, expected {c}")
+    else:
+        n, h, w, ld = logits.shape
+        if ld < c:
+            raise RuntimeError(f"CrossEntropyLoss2d: NHWC logits pitch {ld} is smaller than the {c} classes")
+    if tuple(target.shape) != (n, h, w):
+        raise RuntimeError(f"CrossEntropyLoss2d: size mismatch, target {tuple(target.shape)} vs logits of {n} x {h} x {w} pixels "
+                           f"(expected target shape {(n, h, w)})")
+    if weight is not None and weight.numel() != c:
+        raise RuntimeError(f"CrossEntropyLoss2d: weight has {weight.numel()} entries, expected {c}")
+    if not logits.is_contiguous():
+        raise RuntimeError("CrossEntropyLoss2d: logits must be contiguous")
+
+
+def check_masked_loss_shapes(kind: int, a, b, prob, target):
+    """Host-side contract of the masked-loss kernels (they loop over target.numel() pixels): per-pixel kinds need prediction / variance
+    with exactly one value per target pixel; class-probability kinds need prob [B,C,*target.shape[1:]] and C per-class values."""
+    _same_device("masked loss", target, prediction=a, variance=b, prob=prob)
+    if prob is None:
+        for name, t in (("prediction", a), ("variance", b)):
+            if t is not None and t.numel() != target.numel():
+                raise RuntimeError(f"masked loss: size mismatch, {name} {tuple(t.shape)} vs target {tuple(target.shape)}")
+    else:
+        want = (target.shape[0], prob.shape[1]) + tuple(target.shape[1:]) if prob.dim() >= 2 else None
+        if prob.dim() != 4 or tuple(prob.shape) != want:
+            raise RuntimeError(f"masked loss: size mismatch, class probabilities {tuple(prob.shape)} vs target {tuple(target.shape)} "
+                               f"(expected {want})")
+        for name, t in (("per-class cost", a), ("per-class variance", b)):
+            if t is not None and t.numel() != prob.shape[1]:
+                raise RuntimeError(f"masked loss: {name} has {t.numel()} values, expected {prob.shape[1]}")
+
+
 def ce_weight_sum(target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int, wsum: torch.Tensor):
     """wsum[0] += sum over valid pixels of weight[target] (1 when weight is None)."""
     if target.dtype != torch.int64:
         raise RuntimeError("CrossEntropyLoss2d: target must be int64")
+    _same_device("CrossEntropyLoss2d", target, weight=weight, wsum=wsum)
+    if weight is not None and weight.numel() != c:
+        raise RuntimeError(f"CrossEntropyLoss2d: weight has {weight.numel()} entries, expected {c}")
     check(_lib.lib().erf_ce_weight_sum(_p(target), target.numel(), _p(weight), c, ignore_index, _p(wsum), _stream(target)))
     _count()
 
@@ -837,6 +891,8 @@ def ce_weight_sum(target: torch.Tensor, weight: Optional[torch.Tensor], c: int, 
 def ce_fwd_bwd(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int,
                wsum: torch.Tensor, lsum: torch.Tensor, nchw: bool = False, want_grad: bool = True):
     """lsum[0] += sum_valid w[y]*nll; returns dlogits = w[y]*(softmax-onehot)/wsum (same layout/dtype as logits) or None."""
+    check_ce_shapes(logits, target, weight, c, nchw)
+    _same_device("CrossEntropyLoss2d", logits, wsum=wsum, lsum=lsum)
     dlog = torch.empty_like(logits) if want_grad else None
     if nchw:
         hw, ld = logits.shape[2] * logits.shape[3], 0
@@ -869,6 +925,7 @@ def loss_global_reduce(t: torch.Tensor):
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], ignore_index: int, c: int,
                   nchw: bool, want_grad: bool):
     """Returns (loss_sum fp32[1], wsum fp32[1], dlogits or None); loss = loss_sum / wsum."""
+    check_ce_shapes(logits, target, weight, c, nchw)     # before any kernel touches a pointer (also under the CPU emulation of the tests)
     target = target.contiguous()
     acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
     wsum, lsum = acc[0:1], acc[1:2]
@@ -980,6 +1037,18 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, gra
     check(_lib.lib().erf_adam_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, _p(step_dev), grad_scale,
                                        _stream(p)))
     _count(2)
+
+
+def adam_step_graph(p, g, m, v, hyper_dev, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    """Adam with step counter, learning rate and weight decay in device memory (hyper_dev fp32 [2] = {lr, weight_decay}): the captured
+    launch follows later changes of the learning rate."""
+    check(_lib.lib().erf_adam_step_graph(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper_dev), beta1, beta2, eps, _p(step_dev), grad_scale, _stream(p)))
+    _count(2)
+
+
+def sgd_step_graph(p, g, buf, hyper_dev, momentum, grad_scale=1.0):
+    check(_lib.lib().erf_sgd_step_graph(_p(p), _p(g), _p(buf), p.numel(), _p(hyper_dev), momentum, grad_scale, _stream(p)))
+    _count()
 
 
 # ---- ImageNet tail, mean teacher, I/O side (csrc/tail_io.cu) -------------------------------------------------------------------

@@ -44,6 +44,18 @@ def flatten_parameters(params, like=None):
     return flat
 
 
+def _check_views(params, flat, who):
+    """Every parameter must still be a view INTO `flat` (same storage, inside its range): Module.to() / a trainer that takes ownership of
+    the parameters afterwards re-allocates them, and a kernel over the old flat buffer would silently update orphaned memory."""
+    base = flat.untyped_storage().data_ptr()
+    lo, hi = flat.storage_offset(), flat.storage_offset() + flat.numel()
+    for p in params:
+        d = p.data
+        if d.untyped_storage().data_ptr() != base or not (lo <= d.storage_offset() and d.storage_offset() + d.numel() <= hi):
+            raise RuntimeError(f"{who}: a parameter no longer aliases the flat buffer captured at construction (the model was moved, or another "
+                               "trainer took ownership of its parameters afterwards) -- build this object last")
+
+
 class FlatSGD:
     """Drop-in for ``torch.optim.SGD(model.parameters(), lr, momentum=..., weight_decay=...)`` (no dampening, no Nesterov -- what
     imagenet/main.py:83-85 uses): ``zero_grad()``, ``step()``, ``param_groups`` (lr / weight_decay are read at every step, so
@@ -65,20 +77,52 @@ class FlatSGD:
         self.flat_g.zero_()          # the .grad views stay in place: autograd / the gradient sink accumulate into them
 
     def step(self):
+        self._check_alias()
         g = self.param_groups[0]
         ops.sgd_step(self.flat_p, self.flat_g, self.flat_buf, float(g["lr"]), float(g["momentum"]), float(g["weight_decay"]), self.steps == 0)
         self.steps += 1
         _E.bump_weights_epoch()      # the parameters changed in place: invalidate eval-mode packed weights
 
+    def _check_alias(self):
+        _check_views(self.params, self.flat_p, "FlatSGD")
+
     def state_dict(self):
+        """torch.optim.SGD's layout ({"state": {i: {"momentum_buffer"}}, "param_groups": [{..., "params": [0..n-1]}]}), which is what
+        imagenet/main.py:89-97, 146-152 saves and resumes; "steps" is an extra key torch ignores."""
         g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
-        return {"param_groups": [g], "steps": self.steps, "momentum_buffer": None if self.flat_buf is None else self.flat_buf.clone()}
+        g.update(dampening=0, nesterov=False, params=list(range(len(self.params))))
+        state = {}
+        if self.flat_buf is not None and self.steps > 0:
+            lo = min(p.data.storage_offset() for p in self.params)
+            for i, p in enumerate(self.params):
+                o = p.data.storage_offset() - lo
+                state[i] = {"momentum_buffer": self.flat_buf[o:o + p.numel()].view_as(p).clone()}
+        return {"state": state, "param_groups": [g], "steps": self.steps}
 
     def load_state_dict(self, sd):
-        self.param_groups[0].update(sd["param_groups"][0])
-        self.steps = sd["steps"]
-        if self.flat_buf is not None and sd.get("momentum_buffer") is not None:
-            self.flat_buf.copy_(sd["momentum_buffer"])
+        g = {k: v for k, v in sd["param_groups"][0].items() if k in ("lr", "momentum", "weight_decay")}
+        self.param_groups[0].update(g)
+        if "momentum_buffer" in sd:      # this class's round-1 format: one flat buffer
+            self.steps = sd["steps"]
+            if self.flat_buf is not None and sd.get("momentum_buffer") is not None:
+                self.flat_buf.copy_(sd["momentum_buffer"])
+            return
+        state = sd.get("state", {})
+        ids = list(sd["param_groups"][0].get("params", range(len(self.params))))
+        if len(ids) != len(self.params):
+            raise ValueError(f"FlatSGD.load_state_dict: {len(ids)} parameters in the checkpoint, {len(self.params)} in the model")
+        seen = False
+        if self.flat_buf is not None:
+            self.flat_buf.zero_()
+            lo = min(p.data.storage_offset() for p in self.params)
+            for pos, i in enumerate(ids):
+                st = state.get(i, state.get(str(i)))
+                if st and st.get("momentum_buffer") is not None:
+                    p = self.params[pos]
+                    o = p.data.storage_offset() - lo
+                    self.flat_buf[o:o + p.numel()].copy_(st["momentum_buffer"].reshape(-1))
+                    seen = True
+        self.steps = int(sd.get("steps", 1 if seen else 0))
 
 
 class MeanTeacher:
@@ -92,9 +136,14 @@ class MeanTeacher:
             raise RuntimeError("MeanTeacher: student and teacher must have the same parameters")
         self.flat_student = flatten_parameters(sp)
         self.flat_teacher = flatten_parameters(tp, like=sp)
+        self._student, self._teacher = model_student, model_teacher
         for target in tp:
             target.requires_grad = False
 
     def update(self, discount_factor):
+        # Construction order matters: a FlatAdamTrainer built AFTER this object re-creates the student's parameters in its own
+        # flat buffer, and Module.to() / .cuda() re-allocates storage; the buffers captured here would then be orphans averaged in silence.
+        _check_views(self._student.parameters(), self.flat_student, "MeanTeacher (student)")     # the models' CURRENT parameters
+        _check_views(self._teacher.parameters(), self.flat_teacher, "MeanTeacher (teacher)")
         ops.ema_update(self.flat_teacher, self.flat_student, float(discount_factor))
         _E.bump_weights_epoch()

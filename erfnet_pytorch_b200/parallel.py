@@ -44,12 +44,13 @@ class FlatAdamTrainer:
         gathered by nn.DataParallel; a foreign criterion's per-rank means are averaged instead."""
         self.model = model
         self.loss_fn = loss_fn
-        self.sgd_momentum = sgd_momentum   # not None: torch.optim.SGD(lr, momentum, weight_decay) semantics (imagenet/main.py:83-85) instead of Adam;
-                                           # lr / weight_decay are read from self.lr / self.wd at every eager step (re-capture a graph after changing them)
+        self.sgd_momentum = sgd_momentum   # not None: torch.optim.SGD(lr, momentum, weight_decay) semantics (imagenet/main.py:83-85) instead of Adam
         self.num_classes = num_classes or getattr(model, "num_classes", None)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self._hyper_dev = None      # fp32 [2] = {lr, weight_decay} on the device once a CUDA graph holds the optimiser launch (set_lr keeps it current)
+        self._lr, self._wd = float(lr), float(weight_decay)
+        self.betas, self.eps = betas, eps
         self.criterion = CrossEntropyLoss2d(weight, ignore_index)
         self.step_count = 0
         # The trainer takes ownership of the parameters: every nn.Parameter is replaced by a FRESH one (a view of the flat buffer below).
@@ -90,6 +91,11 @@ class FlatAdamTrainer:
             self._bucket_params[b] += 1
             self._param_bucket[p] = b
             off += n
+        self._params = [p for _, p in named]                         # model.parameters() order = torch.optim's parameter indices
+        self._offsets = {}
+        for i in order:
+            p = named[i][1]
+            self._offsets[p] = p.data.storage_offset() - self.flat_p.storage_offset()
         # all BatchNorm step counters in one int64 tensor: one increment per step instead of 39
         unused = {c for mod in model.modules() if getattr(mod, "use_batchnorm", True) is False for c in mod.children()
                   if isinstance(c, torch.nn.BatchNorm2d)}      # the fork's BN-free blocks keep (and never step) their BatchNorm modules
@@ -122,6 +128,95 @@ class FlatAdamTrainer:
             dist.broadcast(self.flat_p, 0, group=self.pg)
             for b in model.buffers():
                 dist.broadcast(b, 0, group=self.pg)
+
+    # ---- hyper-parameters: the reference steps a LambdaLR every epoch (train/main.py:238-239) and the ImageNet schedule decays lr every 30
+    # epochs (imagenet/main.py:276-286).  A captured graph cannot see host-side floats, so once a graph exists lr / weight decay live in a
+    # two-float device tensor that the Adam / SGD kernels read; assigning trainer.lr (or set_lr) updates it, also between replays.
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self._lr = float(value)
+        self._sync_hyper()
+
+    @property
+    def wd(self):
+        return self._wd
+
+    @wd.setter
+    def wd(self, value):
+        self._wd = float(value)
+        self._sync_hyper()
+
+    def set_lr(self, lr):
+        """scheduler.step() of the reference: takes effect at the next step, graph replay included."""
+        self.lr = lr
+
+    def _sync_hyper(self):
+        if self._hyper_dev is not None:
+            self._hyper_dev.copy_(torch.tensor([self._lr, self._wd], dtype=torch.float32), non_blocking=False)
+
+    @property
+    def param_groups(self):
+        """Read-only view in torch.optim's vocabulary (what `for g in optimizer.param_groups: g['lr']` loops expect to read); assign
+        through ``trainer.lr`` / ``set_lr``."""
+        g = {"params": self._params, "lr": self._lr, "weight_decay": self._wd}
+        if self.sgd_momentum is not None:
+            g.update(momentum=self.sgd_momentum, dampening=0, nesterov=False)
+        else:
+            g.update(betas=tuple(self.betas), eps=self.eps, amsgrad=False)
+        return [g]
+
+    # ---- checkpoints: the layout torch.optim.Adam / SGD produce for optimizer.state_dict() (train/main.py:229, 783 save and resume
+    # checkpoint['optimizer']), so a reference checkpoint resumes here and vice versa -------------------------------------------------
+    def state_dict(self):
+        state = {}
+        if self.step_count > 0:
+            for i, p in enumerate(self._params):
+                o, n = self._offsets[p], p.numel()
+                if self.sgd_momentum is not None:
+                    state[i] = {"momentum_buffer": self.flat_m[o:o + n].view_as(p).clone()}
+                else:
+                    state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.flat_m[o:o + n].view_as(p).clone(),
+                                "exp_avg_sq": self.flat_v[o:o + n].view_as(p).clone()}
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        g["params"] = list(range(len(self._params)))
+        return {"state": state, "param_groups": [g]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self._params):
+            raise ValueError(f"FlatAdamTrainer.load_state_dict: {len(ids)} parameters in the checkpoint, {len(self._params)} in the model")
+        g0 = groups[0]
+        if "betas" in g0 and self.sgd_momentum is None:
+            self.betas, self.eps = tuple(g0["betas"]), g0["eps"]
+        self._lr, self._wd = float(g0["lr"]), float(g0.get("weight_decay", self._wd))
+        state = sd.get("state", {})
+        step = 0
+        with torch.no_grad():
+            self.flat_m.zero_()
+            self.flat_v.zero_()
+            for pos, i in enumerate(ids):
+                st = state.get(i, state.get(str(i)))
+                if not st:
+                    continue
+                p = self._params[pos]
+                o, n = self._offsets[p], p.numel()
+                if self.sgd_momentum is not None:
+                    if st.get("momentum_buffer") is not None:
+                        self.flat_m[o:o + n].copy_(st["momentum_buffer"].reshape(-1))
+                        step = max(step, 1)
+                else:
+                    self.flat_m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self.flat_v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = max(step, int(float(st["step"])))
+        self.step_count = int(sd.get("step_count", step))
+        if self._step_dev is not None:
+            self._step_dev.fill_(self.step_count)
+        self._sync_hyper()
 
     # ---- gradient buckets ---------------------------------------------------------------------------------
     def _launch_bucket(self, b):
@@ -211,6 +306,7 @@ class FlatAdamTrainer:
         c = self.num_classes
         w = self.criterion.weight
         labels = labels.contiguous()
+        ops.check_ce_shapes(logits, labels, w, c, False)
         # pass 1: valid-pixel weight sum, all-reduced so that every rank normalises by the global denominator
         acc = torch.zeros(2, device=logits.device, dtype=torch.float32)
         wsum, lsum = acc[0:1], acc[1:2]
@@ -245,12 +341,15 @@ class FlatAdamTrainer:
         gs = getattr(self, "_grad_scale", 1.0) if self.loss_fn is not None else 1.0   # 1 when the loss was normalised by the global batch
         if self.sgd_momentum is not None:
             # the momentum buffer starts at zero, so momentum * buf + d on the first step equals torch's "buf = d" initialisation
-            ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr, self.sgd_momentum, self.wd, False, gs)
+            if self._hyper_dev is not None:
+                ops.sgd_step_graph(self.flat_p, self.flat_g, self.flat_m, self._hyper_dev, self.sgd_momentum, gs)
+            else:
+                ops.sgd_step(self.flat_p, self.flat_g, self.flat_m, self.lr, self.sgd_momentum, self.wd, False, gs)
             _erfnet.bump_weights_epoch()
             return
-        if self._step_dev is not None:  # CUDA-graph mode: the step counter lives on the device
-            ops.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                              self._step_dev, gs)
+        if self._step_dev is not None:  # CUDA-graph mode: step counter, learning rate and weight decay live on the device
+            ops.adam_step_graph(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev, self.betas[0], self.betas[1], self.eps,
+                                self._step_dev, gs)
         else:
             ops.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                           self.step_count, gs)
@@ -338,6 +437,7 @@ class FlatAdamTrainer:
         self._g_images = torch.zeros(images_shape, device=dev, dtype=torch.float32)
         self._g_labels = torch.zeros(labels_shape, device=dev, dtype=labels_dtype)
         self._step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int32)
+        self._hyper_dev = torch.tensor([self._lr, self._wd], device=dev, dtype=torch.float32)
         snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self._step_dev)]
         bufs = [b.clone() for b in self.model.buffers()]
         count = self.step_count

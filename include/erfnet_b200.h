@@ -202,6 +202,12 @@ int erf_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int erf_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int* step_dev, float grad_scale, erf_stream_t stream);
 
+/* Same, with the learning rate and the weight decay ALSO in device memory (hyper_dev = fp32 [2] = {lr, weight_decay}): a launch captured
+ * in a CUDA graph bakes by-value arguments in, whereas the reference steps a LambdaLR every epoch (train/main.py:238-239) -- the host
+ * updates hyper_dev between replays (FlatAdamTrainer.set_lr) and the replayed kernel sees the new values. */
+int erf_adam_step_graph(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, float beta1,
+                        float beta2, float eps, int* step_dev, float grad_scale, erf_stream_t stream);
+
 /* ---- tcgen05 implicit-GEMM 3x1 / 1x3 (dilated) convolution, C = 64 or 128, NHWC bf16 ----------
  * out[p,co] = epilogue(sum_t sum_ci in[p + (t-1)*dil along H (horizontal=0) or W (horizontal=1), ci] * Wt[t][co][ci]),
  * epilogue as erf_conv_fwd (bias -> + res -> relu -> * (mask>0)).  TMA-staged 128B-swizzled activation tiles (zero-filled
@@ -313,6 +319,10 @@ int erf_ce_rows_bwd(const float* logits, const long long* target, int N, int C, 
  * p -= lr * buf (momentum == 0: p -= lr * d, buf unused). */
 int erf_sgd_step(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay, int first_step,
                  float grad_scale, erf_stream_t stream);
+/* Same for CUDA-graph replay: hyper_dev = fp32 [2] = {lr, weight_decay} in device memory (imagenet/main.py:276-286 changes lr every 30
+ * epochs); buf must start zeroed (momentum * 0 + d = torch's first-step initialisation). */
+int erf_sgd_step_graph(float* p, const float* g, float* buf, long long n, const float* hyper_dev, float momentum, float grad_scale,
+                       erf_stream_t stream);
 
 /* ---- mean teacher (train/main.py:140-142, 384-390): teacher = teacher * (1 - rate) + rate * student over flat fp32 buffers ----------- */
 int erf_ema_update(float* teacher, const float* student, long long n, float rate, erf_stream_t stream);

@@ -185,7 +185,7 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbe
 
 
 def ce_weight_sum(target, weight, c, ignore_index, wsum):
-    valid = target != ignore_index
+    valid = (target != ignore_index) & (target >= 0) & (target < c)    # the kernels skip EVERY label outside [0, C) (csrc/loss_metric.cu)
     t = torch.where(valid, target, torch.zeros_like(target))
     w = torch.ones(c) if weight is None else weight
     wsum += (w[t] * valid).sum()
@@ -195,7 +195,7 @@ def ce_weight_sum(target, weight, c, ignore_index, wsum):
 def ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw=False, want_grad=True):
     lg = logits.detach().float() if nchw else logits.detach()[..., :c].float().permute(0, 3, 1, 2)
     lg = lg.requires_grad_(True)
-    valid = target != ignore_index
+    valid = (target != ignore_index) & (target >= 0) & (target < c)
     t = torch.where(valid, target, torch.zeros_like(target))
     w = torch.ones(c) if weight is None else weight
     wpx = w[t] * valid
@@ -241,6 +241,15 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
 def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale=1.0):
     step_dev += 1
     adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, int(step_dev), grad_scale)
+
+
+def adam_step_graph(p, g, m, v, hyper_dev, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    step_dev += 1
+    adam_step(p, g, m, v, float(hyper_dev[0]), beta1, beta2, eps, float(hyper_dev[1]), int(step_dev), grad_scale)
+
+
+def sgd_step_graph(p, g, buf, hyper_dev, momentum, grad_scale=1.0):
+    sgd_step(p, g, buf, float(hyper_dev[0]), momentum, float(hyper_dev[1]), False, grad_scale)
 
 
 def _ml_per_px(kind, a, b, prob, target, eps):
@@ -396,7 +405,7 @@ def colorize(labels, cmap):
 
 
 _NAMES = ["conv_fwd", "conv_wgrad", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "channel_stats", "channel_sum", "channel_sum_slice", "relu_bwd", "bn_finalize",
-          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "masked_loss_fwd", "masked_loss_bwd", "softmax_nhwc_fwd", "softmax_nhwc_bwd",
+          "bn_eval_affine", "bn_bwd", "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "adam_step_dev", "adam_step_graph", "sgd_step_graph", "masked_loss_fwd", "masked_loss_bwd", "softmax_nhwc_fwd", "softmax_nhwc_bwd",
           "avgpool_fwd", "avgpool_bwd", "linear_fwd", "linear_bwd", "ce_rows_fwd", "ce_rows_bwd", "sgd_step", "ema_update", "ingest_u8", "label_lut", "colorize"]
 
 
