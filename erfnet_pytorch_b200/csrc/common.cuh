@@ -122,6 +122,28 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- grid-wide barrier for kernels whose WHOLE grid is co-resident (the launcher checks grid <= SMs x occupancy) ------------------------
+// `counter` is a zeroed 32-bit word in global memory used by exactly one barrier of one launch (the trainer hands out slots of a scratch
+// arena it zeroes with one memset per step).  Pattern of cooperative groups' grid.sync(): block barrier, one thread publishes the block's
+// global writes (fence) and arrives, spins with acquire loads, block barrier.  Data written by other blocks before the barrier must be
+// read with L1-bypassing loads afterwards (__ldcg) -- the lines may sit stale in this SM's L1.
+// Deadlock freedom with programmatic dependent launch: a dependent grid is only scheduled once every block of this grid has executed
+// pdl_trigger(), i.e. is resident, and the preceding grid never waits for this one.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= expected) break;
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace erfk

@@ -181,17 +181,27 @@ def _sunk(*params):
                 _GRAD_SINK.ready(p)
 
 
+def _side(fn, keep, *params):
+    """Run fn() (weight-gradient launches that accumulate into the sinks of `params`) on the trainer's side stream when there is one and every
+    parameter has a sink -- nothing is then returned to autograd, so nothing downstream waits for these kernels except the optimiser."""
+    q = ops.SIDE
+    if q is None or any(_sink(p) is None for p in params):
+        return fn()
+    return q.run(fn, keep)
+
+
 def _ret(p, g):
     """What autograd gets for parameter p: nothing if the kernel already accumulated into p.grad."""
     return None if _sink(p) is not None else g
 
 
-def _stats_buf(bn, device):
-    """Persistent zeroed fp64 [2C] statistics accumulator of a BatchNorm (erf_bn_finalize resets it after use)."""
-    b = bn.__dict__.get("_erf_stats")
-    if b is None or b.device != device:
-        b = bn.__dict__["_erf_stats"] = torch.zeros(2 * bn.num_features, device=device, dtype=torch.float64)
-    return b
+def _bn_apply(bn, y_raw, stats, count, drop=None, res=None):
+    """Train-mode BatchNorm (+ Dropout2d multiplier, + residual) + ReLU of y_raw from the fp64 batch sums its producer accumulated:
+    (out, mean, invstd); updates bn's running statistics and step counter like nn.BatchNorm2d.forward."""
+    out, mean, invstd = ops.bn_apply(y_raw, stats, count, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
+                                     drop=drop, res=res, relu=True)
+    _tick(bn)
+    return out, mean, invstd
 
 
 def _tick(bn):
@@ -294,6 +304,9 @@ class _TcConv:
     def wgrad(self, x, dy, wparam, bparam, bias_is_zero):
         """(dw, db) for autograd, accumulated in place when a gradient sink is active.  bias_is_zero: the conv feeds a
         train-mode BatchNorm, so its bias gradient is exactly zero (see non_bottleneck_1d._bwd)."""
+        return _side(lambda: self._wgrad_now(x, dy, wparam, bparam, bias_is_zero), (x, dy), wparam, bparam)
+
+    def _wgrad_now(self, x, dy, wparam, bparam, bias_is_zero):
         if ops.wgrad_im2col_supported(self.spec, x.dtype):
             dw = ops.conv_wgrad_im2col_tc(x, dy, self.spec, dw_out=_sink(wparam))
             bdst = _sink(bparam)
@@ -396,12 +409,9 @@ class DownsamplerBlock(_B200Module):
             y = ops.stem_fwd(x, self.conv.weight.detach(), self.conv.bias.detach(), relu=True)
             return y, (x, None, y, None, None)
         if stem:
-            stats = _stats_buf(self.bn, x.device)
+            stats = ops.bn_stats_buf(self.noutput, x.device)
             y_raw = ops.stem_fwd(x, self.conv.weight.detach(), self.conv.bias.detach(), stats=stats)
-            mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
-                                                         self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
-            _tick(self.bn)
-            y = ops.affine_act(y_raw, scale, shift, relu=True)
+            y, mean, invstd = _bn_apply(self.bn, y_raw, stats, n * (h // 2) * (w // 2))
             return y, (x, y_raw, y, mean, invstd)
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
         if not self.use_batchnorm:  # train/erfnet_blocks.py:24-29: relu(cat(conv, pool)), both ReLUs in the producing kernels
@@ -412,7 +422,7 @@ class DownsamplerBlock(_B200Module):
                              relu=True, out=y_raw)
             ops.maxpool_fwd(x, self.ninput, y_raw, cc, relu=True)
             return y_raw, (x, None, y_raw, None, None)
-        stats = _stats_buf(self.bn, x.device)
+        stats = ops.bn_stats_buf(self.noutput, x.device)
         if self._tc.fwd_ok(x.dtype):
             self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), out=y_raw)
             ops.maxpool_fwd(x, self.ninput, y_raw, cc)
@@ -421,21 +431,18 @@ class DownsamplerBlock(_B200Module):
             ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                          out=y_raw, stats=stats)
             ops.maxpool_fwd(x, self.ninput, y_raw, cc, stats=stats)
-        mean, invstd, scale, shift = ops.bn_finalize(stats, n * (h // 2) * (w // 2), self.bn.weight.detach(), self.bn.bias.detach(),
-                                                     self.bn.running_mean, self.bn.running_var, BN_MOMENTUM, BN_EPS)
-        _tick(self.bn)
-        y = ops.affine_act(y_raw, scale, shift, relu=True)
+        y, mean, invstd = _bn_apply(self.bn, y_raw, stats, n * (h // 2) * (w // 2))
         return y, (x, y_raw, y, mean, invstd)
 
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
         if self.use_batchnorm:
-            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb), beta_for_mask=gb.detach())
         else:
             dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
         if self.ninput == 3 and self.noutput == 16 and ops.stem_supported(x):
-            dw, db = ops.stem_wgrad(x, dyr, dw_out=_sink(cw), db_out=_sink(cb), want_bias=not self.use_batchnorm)
+            dw, db = _side(lambda: ops.stem_wgrad(x, dyr, dw_out=_sink(cw), db_out=_sink(cb), want_bias=not self.use_batchnorm), (x, dyr), cw, cb)
             if db is None and _sink(cb) is None:   # conv bias feeding a train-mode BN: gradient exactly zero
                 db = torch.zeros(self.noutput - self.ninput, device=x.device, dtype=torch.float32)
         else:
@@ -604,13 +611,13 @@ class non_bottleneck_1d(_B200Module):
         return (self.chann in (16, 64, 128) and ops.USE_TC and ops.conv1d_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
                 and ops.conv1d_tc_supported(self.chann, x.shape[2], 1, x.dtype))
 
-    def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None, colsum=None):
+    def _conv(self, i, x, w, bias, tc, relu=False, stats=None, mask=None, add=None, spec=None, colsum=None, static_w=False):
         """conv i (0..3) of the block (or its data gradient when spec is a dgrad spec) on the tcgen05 or the generic kernel.
         colsum: fp32 [C] that receives the per-channel sum of the result (= bias gradient of the conv that produced the
         tensor this gradient belongs to)."""
         if tc:
             return ops.conv1d_tc(x, w, bias, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, relu=relu, res=add, mask=mask,
-                                 stats=stats, colsum=colsum)
+                                 stats=stats, colsum=colsum, static_w=static_w and ops.STATIC_WEIGHT_PREFETCH)
         y = ops.conv_fwd(x, w, spec or self.specs[i], bias, relu=relu, stats=stats, mask=mask, add=add, out_hw=x.shape[1:3])
         if colsum is not None:
             ops.channel_sum(y, colsum)
@@ -623,43 +630,40 @@ class non_bottleneck_1d(_B200Module):
         tc = self._use_tc(x)
         if tc:
             # forward + data-gradient images: pre-packed for this step by the trainer's batched launch, else one launch per conv
-            pairs = (self.__dict__.get("_prepacked") if _PREPACKED_FRESH else None) or [ops.pack_conv1d_tc_pair(m.weight) for m in cv]
+            pairs = self.__dict__.get("_prepacked") if (_PREPACKED_FRESH and self.__dict__.get("_conv_override") is None) else None
+            sw = pairs is not None     # the trainer's images: complete before any kernel of this step starts (FlatAdamTrainer._begin_step)
+            if pairs is None:
+                pairs = [ops.pack_conv1d_tc_pair(m.weight) for m in cv]
             wp = [pr[0] for pr in pairs]
         else:
-            pairs = None
+            pairs, sw = None, False
             wp = [ops.pack_weight_fwd(m.weight.detach(), sp, dtp) for m, sp in zip(cv, s)]
         bs = [m.bias.detach().float() for m in cv]
         if not self.use_batchnorm:
             # train/erfnet_blocks.py:55-73 without the BNs: conv+bias+ReLU chain, everything in the conv epilogues
-            t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
-            a2 = self._conv(1, t1, wp[1], bs[1], tc, relu=True)
-            t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True)
+            t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True, static_w=sw)
+            a2 = self._conv(1, t1, wp[1], bs[1], tc, relu=True, static_w=sw)
+            t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True, static_w=sw)
             drop = self._drop_scale(x, ctx)
             if drop is None:
-                out = self._conv(3, t3, wp[3], bs[3], tc, relu=True, add=x)
+                out = self._conv(3, t3, wp[3], bs[3], tc, relu=True, add=x, static_w=sw)
             else:
-                y4 = self._conv(3, t3, wp[3], bs[3], tc)
+                y4 = self._conv(3, t3, wp[3], bs[3], tc, static_w=sw)
                 out = ops.affine_act(y4, drop, torch.zeros_like(drop), res=x, relu=True)
-            return out, (x, t1, None, a2, t3, None, out, None, None, None, None, drop, pairs)
+            return out, (x, t1, None, a2, t3, None, out, None, None, None, None, drop, (pairs, sw))
         count = n * h * w
-        st = (_stats_buf(self.bn1, x.device), _stats_buf(self.bn2, x.device))
-        t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True)
-        y2 = self._conv(1, t1, wp[1], bs[1], tc, stats=st[0])
-        mean1, invstd1, sc1, sh1 = ops.bn_finalize(st[0], count, self.bn1.weight.detach(), self.bn1.bias.detach(), self.bn1.running_mean,
-                                                   self.bn1.running_var, BN_MOMENTUM, BN_EPS)
-        _tick(self.bn1)
-        a2 = ops.affine_act(y2, sc1, sh1, relu=True)
-        t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True)
-        y4 = self._conv(3, t3, wp[3], bs[3], tc, stats=st[1])
+        st = (ops.bn_stats_buf(c, x.device), ops.bn_stats_buf(c, x.device))
+        t1 = self._conv(0, x, wp[0], bs[0], tc, relu=True, static_w=sw)
+        y2 = self._conv(1, t1, wp[1], bs[1], tc, stats=st[0], static_w=sw)
+        a2, mean1, invstd1 = _bn_apply(self.bn1, y2, st[0], count)
+        t3 = self._conv(2, a2, wp[2], bs[2], tc, relu=True, static_w=sw)
+        y4 = self._conv(3, t3, wp[3], bs[3], tc, stats=st[1], static_w=sw)
         drop = self._drop_scale(x, ctx)
-        mean2, invstd2, sc2, sh2 = ops.bn_finalize(st[1], count, self.bn2.weight.detach(), self.bn2.bias.detach(), self.bn2.running_mean,
-                                                   self.bn2.running_var, BN_MOMENTUM, BN_EPS, drop=drop)
-        _tick(self.bn2)
-        out = ops.affine_act(y4, sc2, sh2, res=x, relu=True)
-        return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, pairs)
+        out, mean2, invstd2 = _bn_apply(self.bn2, y4, st[1], count, drop=drop, res=x)
+        return out, (x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, (pairs, sw))
 
     def _bwd(self, dout, saved, need_dx):
-        x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, pairs = saved
+        x, t1, y2, a2, t3, y4, out, mean1, invstd1, mean2, invstd2, drop, (pairs, sw) = saved
         s, dtp = self.specs, x.dtype
         cv = self._convs()
         tc = self._use_tc(x)
@@ -678,27 +682,28 @@ class non_bottleneck_1d(_B200Module):
         # The biases of conv1x3_1 / conv1x3_2 feed a train-mode BatchNorm: their gradient sum_p dy is EXACTLY zero
         # (sum_p xhat = 0), the reference only ever sees its rounding noise (~1e-9, far below Adam's eps = 1e-4) -> no kernel.
         if not self.use_batchnorm:
-            return self._bwd_nobn(dout, saved, need_dx, tc, wd, ds, P, bias_dst)
+            return self._bwd_nobn(dout, saved, need_dx, tc, wd, ds, P, bias_dst, sw)
         db2 = db4 = None if (_sink(P[3]) is not None) else torch.zeros(self.chann, device=dev, dtype=torch.float32)
         db1, db3 = bias_dst(P[1]), bias_dst(P[7])
         dy4, dg2, dbe2, gres = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]),
                                           dbeta_out=_sink(P[11]), want_masked=True)  # gres = dout * (out > 0): the residual path's gradient
         dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
-        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3)     # grad wrt conv3x1_2's output
+        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3, static_w=sw)     # grad wrt conv3x1_2's output
         dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
-        da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2])
-        dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, P[4].detach(), mean1, invstd1, mask=a2, dgamma_out=_sink(P[4]), dbeta_out=_sink(P[5]))
+        da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2], static_w=sw)
+        dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, P[4].detach(), mean1, invstd1, mask=a2, dgamma_out=_sink(P[4]), dbeta_out=_sink(P[5]),
+                                     beta_for_mask=P[5].detach())
         dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
-        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1)     # grad wrt conv3x1_1's output
+        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1, static_w=sw)     # grad wrt conv3x1_1's output
         dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
         dx = None
         if need_dx:
-            dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0])
+            dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0], static_w=sw)
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)))
         _sunk(*P)
         return dx, grads
 
-    def _bwd_nobn(self, dout, saved, need_dx, tc, wd, ds, P, bias_dst):
+    def _bwd_nobn(self, dout, saved, need_dx, tc, wd, ds, P, bias_dst, sw=False):
         """Backward of the BN-free block: every ReLU mask and bias-gradient column sum rides in a data-gradient epilogue;
         the BN parameters get no gradient (they are unused, as in the reference)."""
         x, t1, _, a2, t3, _, out, _, _, _, _, drop, _ = saved
@@ -707,19 +712,22 @@ class non_bottleneck_1d(_B200Module):
         dy4 = gres if drop is None else ops.affine_act(gres, drop, torch.zeros_like(drop), relu=False)
         ops.channel_sum(dy4, db4)
         dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
-        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3)
+        dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3, static_w=sw)
         dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
-        dy2 = self._conv(2, dt3, wd[2], None, tc, mask=a2, spec=ds[2], colsum=db2)
+        dy2 = self._conv(2, dt3, wd[2], None, tc, mask=a2, spec=ds[2], colsum=db2, static_w=sw)
         dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
-        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1)
+        dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1, static_w=sw)
         dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
-        dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0]) if need_dx else None
+        dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0], static_w=sw) if need_dx else None
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, None, None, dw3, db3, dw4, db4, None, None)))
         _sunk(*P)  # the unused BN parameters count as done (their gradient stays zero)
         return dx, grads
 
     def _wgrad(self, i, x, dy, tc, wparam):
         """Weight gradient only (the bias gradients come from the data-gradient epilogues, see _bwd)."""
+        return _side(lambda: self._wgrad_now(i, x, dy, tc, wparam), (x, dy), wparam)
+
+    def _wgrad_now(self, i, x, dy, tc, wparam):
         if tc and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype):
             return ops.conv1d_wgrad_tc(x, dy, horizontal=bool(i & 1), dil=1 if i < 2 else self.dilated, dw_out=_sink(wparam), want_bias=False)
         return ops.conv_wgrad(x, dy, self.specs[i], dw_out=_sink(wparam), want_bias=False)
@@ -769,7 +777,7 @@ class UpsamplerBlock(_B200Module):
                 y = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                                  relu=True)
             return y, (x, None, y, None, None)
-        stats = _stats_buf(self.bn, x.device)
+        stats = ops.bn_stats_buf(self.bn.num_features, x.device)
         if self._tc.fwd_ok(x.dtype):
             y_raw = self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float())
             ops.channel_stats(y_raw, stats)
@@ -777,17 +785,14 @@ class UpsamplerBlock(_B200Module):
             y_raw = ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                                  stats=stats)
         count = y_raw.shape[0] * y_raw.shape[1] * y_raw.shape[2]
-        mean, invstd, scale, shift = ops.bn_finalize(stats, count, self.bn.weight.detach(), self.bn.bias.detach(), self.bn.running_mean,
-                                                     self.bn.running_var, BN_MOMENTUM, BN_EPS)
-        _tick(self.bn)
-        y = ops.affine_act(y_raw, scale, shift, relu=True)
+        y, mean, invstd = _bn_apply(self.bn, y_raw, stats, count)
         return y, (x, y_raw, y, mean, invstd)
 
     def _bwd(self, dy, saved, need_dx):
         x, y_raw, y, mean, invstd = saved
         cw, cb, gw, gb = self._train_params()
         if self.use_batchnorm:
-            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb))
+            dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb), beta_for_mask=gb.detach())
         else:
             dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
         dw, db = self._tc.wgrad(x, dyr, cw, cb, bias_is_zero=self.use_batchnorm)

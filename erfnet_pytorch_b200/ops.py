@@ -4,6 +4,7 @@ arithmetic op below is a kernel in liberfnet_b200.so.  Internal activations are 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -284,7 +285,9 @@ def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor]
     n, h, w, c = x.shape
     out = torch.empty_like(x)
     fused = True
-    with _timed("conv1d_tc_kernel", 2.0 * n * h * w * c * c * 3):
+    name = (f"conv1d_tc[C={c} {'H' if horizontal else 'V'} d={dil}{' +res' if res is not None else ''}{' +mask' if mask is not None else ''}"
+            f"{' +stats' if stats is not None else ''}{' +colsum' if colsum is not None else ''}]") if DETAIL else "conv1d_tc_kernel"
+    with _timed(name, 2.0 * n * h * w * c * c * 3):
         check(_lib.lib().erf_conv1d_tc(_p(x), _p(w_img), _p(bias), _p(out), _p(res), _p(mask), n, h, w, c, int(horizontal), dil, int(relu) | (2 if static_w else 0),
                                        _p(stats) if fused else None, _p(colsum) if fused else None, _stream(x)))
     _count()
@@ -625,7 +628,7 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
         ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     if dw_out is None:
         dw_out = torch.zeros((c, c, 1, 3) if horizontal else (c, c, 3, 1), device=x.device, dtype=torch.float32)
-    with _timed("conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
+    with _timed(f"conv1d_wgrad_tc[C={c} {'H' if horizontal else 'V'}]" if DETAIL else "conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
         check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
     _count(2)
     if want_bias:
@@ -774,6 +777,39 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
     return scale, shift
 
 
+BN_FUSED = True   # one launch per train-mode BatchNorm and direction (csrc/bn_fused.cu); False = the round-1 kernels (finalize + apply, reduce + apply)
+
+
+def bn_fused_supported(c: int) -> bool:
+    return BN_FUSED and not EMULATED and bool(_lib.lib().erf_bn_fused_supported(c))
+
+
+def bn_stats_buf(c: int, device) -> torch.Tensor:
+    """Zeroed fp64 [2C] accumulator for the batch sums (sum, sum of squares) of one train-mode BatchNorm: a slice of the step's scratch arena
+    (one memset per step) when a trainer provides one, else a fresh tensor."""
+    b = ARENA.take(2 * c) if (ARENA is not None and ARENA.buf.device == torch.device(device)) else None
+    return b if b is not None else torch.zeros(2 * c, device=device, dtype=torch.float64)
+
+
+def bn_apply(x, stats, count, gamma, beta, rm, rv, momentum, eps, drop=None, res=None, relu=True):
+    """nn.BatchNorm2d.forward in training mode on the pre-BN activation x, from the fp64 batch sums `stats` its producer accumulated:
+    out = relu?(((x - mean) * invstd * gamma + beta) * drop[n,c] (+ res)); running statistics updated (momentum, unbiased variance).
+    Returns (out, mean, invstd).  One launch (every CTA derives scale / shift itself) when the layout allows, else finalize + apply."""
+    n, h, w, c = x.shape
+    if bn_fused_supported(c):
+        out = torch.empty_like(x)
+        mean = torch.empty(c, device=x.device, dtype=torch.float32)
+        invstd = torch.empty(c, device=x.device, dtype=torch.float32)
+        with _timed(f"bn_apply[C={c}{' +drop' if drop is not None else ''}{' +res' if res is not None else ''}]" if DETAIL else "bn_apply"):
+            check(_lib.lib().erf_bn_fwd_apply(_p(x), c, _p(stats), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), float(momentum), float(eps), _p(drop),
+                                              _p(res), 0 if res is None else res.shape[-1], _p(out), c, n, h * w, c, int(relu), _p(mean), _p(invstd), dt(x),
+                                              _stream(x)))
+        _count()
+        return out, mean, invstd
+    mean, invstd, scale, shift = bn_finalize(stats, count, gamma, beta, rm, rv, momentum, eps, drop=drop)
+    return affine_act(x, scale, shift, res=res, relu=relu), mean, invstd
+
+
 _BN_SUMS = {}  # (device, C) -> fp64 [2C] scratch for the BN-backward reductions
 
 
@@ -801,27 +837,83 @@ class ScratchArena:
 ARENA = None   # set by the trainer for the duration of a step
 
 
-def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False):
+class SideQueue:
+    """Weight-gradient launches off the critical path.  In the backward pass only the data gradients feed the next layer; the weight gradients
+    are needed by the optimiser alone.  Every hot kernel here is sized one CTA per SM, so two of them never share an SM -- but at batch 6 each
+    launch leaves SMs idle while its last CTAs finish (384 units over 148 SMs) and during the next launch's ramp-up.  Weight-gradient
+    kernels enqueued on a second stream fill those gaps.  run(fn, keep): fn's launches are ordered after everything enqueued so far on the
+    current stream; `keep` holds the tensors they read until join(), so the caching allocator cannot hand their memory to a later
+    main-stream allocation while the side stream still reads it (also true inside a CUDA-graph capture, where the two streams become two
+    branches of the graph).  Never put a kernel that contains a grid barrier on this stream: two barrier kernels on two streams can each
+    hold part of the SMs and wait for the rest forever."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep = []
+        self.used = False
+
+    def run(self, fn, keep=()):
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        self.keep.extend(keep)
+        self.used = True
+        return out
+
+    def join(self):
+        if self.used:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.keep.clear()
+        self.used = False
+
+
+SIDE = None        # a SideQueue while a trainer runs backward with WGRAD_SIDE_STREAM
+WGRAD_SIDE_STREAM = os.environ.get("ERF_WGRAD_SIDE", "0") != "0"   # ERF_WGRAD_SIDE=1: weight gradients on a second stream (measured neutral at the bench workload: the SMs are busy, see DESIGN.md)
+
+
+MASK_FROM_Y = True   # BN -> ReLU without dropout / residual: the backward kernel recomputes the ReLU mask from y (one tensor read less)
+
+
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False, beta_for_mask=None):
     """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c].
     dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step).
-    want_masked: also return g*(mask>0) as a 4th value (written by the apply pass, saves a separate relu_bwd)."""
+    want_masked: also return g*(mask>0) as a 4th value (written by the apply pass, saves a separate relu_bwd).
+    beta_for_mask: this BN's beta, given when mask == relu(BN(y)) exactly (no dropout, no residual): the bf16 kernel may then recompute
+    the mask from y instead of reading the mask tensor."""
     n, h, w, c = y.shape
-    sums = ARENA.take(2 * c) if (ARENA is not None and ARENA.buf.device == y.device) else None
+    sums = ARENA.take(2 * c + 1) if (ARENA is not None and ARENA.buf.device == y.device) else None     # [2C] sums + the grid-barrier counter
     if sums is None:
         sums = _BN_SUMS.get((y.device, c))
         if sums is None:
-            sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c, device=y.device, dtype=torch.float64)
+            sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c + 1, device=y.device, dtype=torch.float64)
         else:
             sums.zero_()
     L = _lib.lib()
-    check(L.erf_bn_bwd_reduce(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(mean), _p(invstd),
-                              n, h * w, c, _p(sums), dt(y), _stream(y)))
+    if bn_fused_supported(c):
+        dy = torch.empty_like(y)
+        dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
+        dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
+        gm = torch.empty_like(y) if want_masked else None
+        bfm = beta_for_mask if (MASK_FROM_Y and mask is not None and drop is None) else None
+        with _timed(f"bn_bwd[C={c}{' +drop' if drop is not None else ''}{' +gm' if want_masked else ''}{' y-mask' if bfm is not None else ''}]" if DETAIL else "bn_bwd"):
+            check(L.erf_bn_bwd_fused(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(bfm), _p(drop), _p(gamma), _p(mean),
+                                     _p(invstd), _p(sums), C.c_void_p(sums.data_ptr() + 16 * c), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), _p(gm), c,
+                                     dt(y), _stream(y)))
+        _count()
+        return (dy, dgamma, dbeta, gm) if want_masked else (dy, dgamma, dbeta)
     dy = torch.empty_like(y)
     dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
     dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, device=y.device, dtype=torch.float32)
     gm = torch.empty_like(y) if want_masked else None
-    check(L.erf_bn_bwd_apply(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(gamma), _p(mean),
-                             _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), _p(gm), c, dt(y), _stream(y)))
+    with _timed("bn_bwd"):
+        check(L.erf_bn_bwd_reduce(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(mean), _p(invstd),
+                                  n, h * w, c, _p(sums), dt(y), _stream(y)))
+        check(L.erf_bn_bwd_apply(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(drop), _p(gamma), _p(mean),
+                                 _p(invstd), _p(sums), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), _p(gm), c, dt(y), _stream(y)))
     _count(2)
     return (dy, dgamma, dbeta, gm) if want_masked else (dy, dgamma, dbeta)
 
@@ -1177,7 +1269,7 @@ def _wrap_timed(name):
     globals()[name] = wrapper
 
 
-for _n in ("channel_stats", "channel_sum", "channel_sum_slice", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine", "bn_bwd",
+for _n in ("channel_stats", "channel_sum", "channel_sum_slice", "maxpool_fwd", "maxpool_bwd", "nchw_to_nhwc", "nhwc_to_nchw", "affine_act", "relu_bwd", "bn_finalize", "bn_eval_affine",
            "ce_weight_sum", "ce_fwd_bwd", "confusion_hist", "iou_counts", "argmax", "adam_step", "pack_weight_fwd", "pack_weight_dgrad",
            "unpack_wgrad", "pack_conv1d_tc", "pack_conv1d_tc_pair", "avgpool_fwd", "avgpool_bwd", "linear_fwd", "linear_bwd", "ce_rows_fwd", "ce_rows_bwd",
            "sgd_step", "ema_update", "ingest_u8", "label_lut", "colorize"):

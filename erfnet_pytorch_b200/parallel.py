@@ -229,6 +229,8 @@ class FlatAdamTrainer:
         buf = self.flat_g[lo:hi]
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            if ops.SIDE is not None and ops.SIDE.used:
+                self.comm_stream.wait_stream(ops.SIDE.stream)      # this bucket's weight gradients were accumulated on the side stream
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
         else:
@@ -288,15 +290,38 @@ class FlatAdamTrainer:
     def loss_and_backward(self, images, labels, drop_scales=None):
         """images NCHW fp32, labels int64 [B,H,W] on the model's device.  Returns the GLOBAL-batch loss (0-dim tensor).
         With a ``loss_fn``: labels is the target tensor (or a tuple of them) that follows the net output in the criterion call."""
-        self.flat_g.zero_()
-        if self.flat_nbt.numel():
-            self.flat_nbt.add_(1)
-        self.model.train()
+        self._begin_step()
+        try:
+            return self._loss_and_backward(images, labels, drop_scales)
+        finally:
+            self._end_step()
+
+    def _begin_step(self):
+        """Zero the flat gradient buffer and the step's scratch arena (BN batch sums of forward and backward, grid-barrier counters: ONE
+        memset), step the BatchNorm counters, re-pack the tensor-core weight images."""
+        # The weight re-pack comes FIRST and the memsets after it: a memset is a full serialisation point of the stream, so every kernel
+        # launched later -- including the part of a programmatically dependent kernel that runs before its pdl_wait() -- starts after the
+        # packed images are complete.  That is what lets the training convs fetch their weights before pdl_wait() (static_w).
         if self._pack_table is not None:
             if not self._pack_table.valid():
                 raise RuntimeError("FlatAdamTrainer: a conv weight was re-allocated after the trainer took ownership of the parameters")
             self._pack_table.run()
             _erfnet._PREPACKED_FRESH = True
+        self.flat_g.zero_()
+        if self.flat_nbt.numel():
+            self.flat_nbt.add_(1)
+        self.model.train()
+        if self.cuda and not ops.EMULATED:
+            if getattr(self, "_arena", None) is None:
+                self._arena = ops.ScratchArena(self.flat_p.device)
+            self._arena.reset()
+            ops.ARENA = self._arena
+
+    def _end_step(self):
+        _erfnet._PREPACKED_FRESH = False
+        ops.ARENA = None
+
+    def _loss_and_backward(self, images, labels, drop_scales=None):
         if self.loss_fn is not None:
             return self._generic_loss_and_backward(images, labels if isinstance(labels, (tuple, list)) else (labels,))
         try:
@@ -322,11 +347,10 @@ class FlatAdamTrainer:
 
     def _backward(self, logits, dlog):
         _erfnet._GRAD_SINK = self
-        if self.cuda and not ops.EMULATED:
-            if getattr(self, "_arena", None) is None:
-                self._arena = ops.ScratchArena(self.flat_p.device)
-            self._arena.reset()          # one memset for all BN-backward reductions of the step
-            ops.ARENA = self._arena
+        if self.cuda and not ops.EMULATED and ops.WGRAD_SIDE_STREAM:
+            if getattr(self, "_side", None) is None:
+                self._side = ops.SideQueue(self.flat_p.device)
+            ops.SIDE = self._side
         try:
             if dlog is None:
                 logits.backward()          # generic path: `logits` is the scalar loss
@@ -334,7 +358,9 @@ class FlatAdamTrainer:
                 logits.backward(dlog)
         finally:
             _erfnet._GRAD_SINK = None
-            ops.ARENA = None
+            if ops.SIDE is not None:
+                ops.SIDE.join()            # the optimiser (and the gradient all-reduce) wait for the weight gradients
+                ops.SIDE = None
 
     def optimizer_step(self):
         self.step_count += 1
@@ -463,18 +489,16 @@ class FlatAdamTrainer:
             g12, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             ops.ce_weight_sum(self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1])   # any non-zero denominator for the capture
             with torch.cuda.graph(g12):
-                self.flat_g.zero_()
-                self.flat_nbt.add_(1)
-                self.model.train()
-                if self._pack_table is not None:
-                    self._pack_table.run()
-                    _erfnet._PREPACKED_FRESH = True
+                self._begin_step()
                 try:
-                    logits = self.model.forward_nhwc(self._g_images)
+                    try:
+                        logits = self.model.forward_nhwc(self._g_images)
+                    finally:
+                        _erfnet._PREPACKED_FRESH = False
+                    dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
+                    self._backward(logits, dlog)
                 finally:
-                    _erfnet._PREPACKED_FRESH = False
-                dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
-                self._backward(logits, dlog)
+                    self._end_step()
             with torch.cuda.graph(g3, pool=g12.pool()):
                 self.optimizer_step()
                 loss = (self._g_acc[1:2] / self._g_acc[0:1]).reshape(())

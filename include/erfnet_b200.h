@@ -144,6 +144,28 @@ int erf_bn_bwd_apply(const void* g, int g_ld, const void* y, int y_ld, const voi
                      const double* sums, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta,
                      void* gmasked, int gmasked_ld, int dtype, erf_stream_t stream);
 
+/* ---- train-mode nn.BatchNorm2d in ONE launch per direction (csrc/bn_fused.cu; eval/erfnet.py:19,37,55,105 in training mode) ----------
+ * erf_bn_fused_supported: 1 when C takes the single-launch kernels (C % 8 == 0, C/8 divides 32, C <= 256). */
+int erf_bn_fused_supported(int C);
+/* Forward: stats = fp64 [2C] batch sums (sum x, sum x^2) of x accumulated by its producer (read only; the caller re-zeroes them for the next
+ * step).  mean = stats[c]/count, var (biased) = stats[C+c]/count - mean^2, invstd = 1/sqrt(var + eps);
+ * out = relu?(((x - mean) * invstd * gamma + beta) * drop[n,c] (+ res)); mean / invstd (fp32 [C]) are written for the backward pass and the
+ * running statistics updated with `momentum` and the UNBIASED variance (torch semantics) -- replaces erf_bn_finalize + erf_affine_act. */
+int erf_bn_fwd_apply(const void* x, int x_ld, const double* stats, double count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, const float* drop, const void* res,
+                     int res_ld, void* out, int out_ld, int N, int HW, int C, int relu, float* mean, float* invstd, int dtype,
+                     erf_stream_t stream);
+/* Backward: erf_bn_bwd_reduce + erf_bn_bwd_apply as one kernel with a grid barrier between the two phases; what a thread read in phase 1
+ * stays in registers / shared memory for phase 2.  sums (fp64 [2C]) and counter (one 32-bit word) must be ZERO on entry.  Falls back to the
+ * two launches when the grid would not be co-resident or the layout is unsupported (same arithmetic).
+ * beta_for_mask (optional, bf16 path): the BN's beta, given when `mask` is exactly relu(BN(y)) of THIS BatchNorm with no dropout and no
+ * residual (BN1 of a block, the samplers' BN): the kernel then recomputes the mask as fma(y, gamma*invstd, beta - mean*gamma*invstd) > 0, the
+ * forward pass's own expression, instead of reading the mask tensor (one tensor read less). */
+int erf_bn_bwd_fused(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* beta_for_mask,
+                     const float* drop, const float* gamma, const float* mean, const float* invstd, double* sums, unsigned* counter,
+                     int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked, int gmasked_ld,
+                     int dtype, erf_stream_t stream);
+
 /* ---- CrossEntropyLoss2d (train/evaluation_functions.py:6-14) ------------------------------------------- */
 /* logits element (p, c): NHWC -> logits[p*ld + c]; NCHW (nchw_hw > 0) -> logits[(p/hw)*C*hw + c*hw + p%hw].
  * pass 1: wsum += sum_valid w[y];  pass 2: loss_sum += sum_valid w[y]*nll, dlogits = w[y]*(softmax-onehot)/wsum. */

@@ -163,7 +163,8 @@ def bn_eval_affine(gamma, beta, rm, rv, eps):
     return sc, beta - rm * sc
 
 
-def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False):
+def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False, beta_for_mask=None):
+    # beta_for_mask: permission to recompute the mask from y (bf16 GPU kernel only); the mask tensor stays authoritative here
     if want_masked:
         gm = (g.float() * (mask.float() > 0) if mask is not None else g.float()).to(y.dtype)
         return bn_bwd(g, y, gamma, mean, invstd, mask, drop, dgamma_out, dbeta_out) + (gm,)

@@ -107,19 +107,22 @@ def test_learning_rate_change_reaches_the_captured_optimiser_and_checkpoint_resu
     (torch.optim.Adam layout) restores moments and the device-side step counter."""
     x = [golden_input((2, 3, 64, 256), 10 + i).cuda() for i in range(4)]
     y = [golden_labels((2, 64, 256), 10 + i).cuda() for i in range(4)]
-    a, b = _trainer("fp32"), _trainer("fp32")
+    a, b, keep = _trainer("fp32"), _trainer("fp32"), _trainer("fp32")
     b.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
+    keep.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
     for i in range(4):
         if i == 2:
             a.set_lr(3e-3)
             b.set_lr(3e-3)
         a.train_step(x[i], y[i])
         b.train_step(x[i], y[i])
+        keep.train_step(x[i], y[i])          # never changes its learning rate
     torch.cuda.synchronize()
-    # lr 1e-4 -> 3e-3 moves the weights 30x further per step: were the captured launch still at 1e-4 the two runs would differ by ~1e-2
-    delta = float((a.flat_p - b.flat_p).abs().max())
-    moved = float((a.flat_p - _trainer("fp32").flat_p).abs().max())
-    assert moved > 5e-3 and delta < 0.05 * moved, (delta, moved)
+    # lr 1e-4 -> 3e-3 moves the weights 30x further per step.  Adam's sign-like steps amplify rounding noise on ~zero gradients, so the
+    # comparison uses the MEAN distance: the replayed run must sit on the eager run with the new lr, far from the run that kept the old one
+    same = float((a.flat_p - b.flat_p).abs().mean())
+    apart = float((keep.flat_p - b.flat_p).abs().mean())
+    assert apart > 1e-3 and same < 0.1 * apart, (same, apart)
     c = _trainer("fp32")
     c.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
     c.model.load_state_dict(b.model.state_dict())
@@ -127,4 +130,4 @@ def test_learning_rate_change_reaches_the_captured_optimiser_and_checkpoint_resu
     assert c.step_count == 4 and int(c._step_dev) == 4 and c.lr == 3e-3 and abs(float(c._hyper_dev[0]) - 3e-3) < 1e-9
     lb, lc = float(b.train_step(x[0], y[0])), float(c.train_step(x[0], y[0]))
     np.testing.assert_allclose(lc, lb, rtol=1e-3)
-    assert float((b.flat_p - c.flat_p).abs().max()) < 0.05 * moved
+    assert float((b.flat_p - c.flat_p).abs().mean()) < 0.1 * apart

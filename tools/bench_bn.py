@@ -1,4 +1,5 @@
-"""Isolated timing of the BatchNorm backward kernels (reduce + apply) and affine_act at the bench shapes."""
+"""Isolated timing of the train-mode BatchNorm kernels at the bench shapes: backward as one launch (csrc/bn_fused.cu) against the round-1
+reduce + apply pair, forward apply as one launch against finalize + affine_act; cold (tensor sets rotating over > L2) and hot (one set)."""
 import os
 import sys
 
@@ -8,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from erfnet_pytorch_b200 import ops  # noqa: E402
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=24):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -22,49 +23,46 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) * 1e3 / n
 
 
+arena = ops.ScratchArena(torch.device("cuda"), n=1 << 20)
+ops.ARENA = arena
 for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
     b = 6
-    # rotate over 6 tensor sets so that the working set (6 x 4 x T) exceeds L2 like in the real step
     sets = [[torch.randn(b, h, w, c, device="cuda").bfloat16() for _ in range(3)] for _ in range(6)]
-    gamma, mean, invstd = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.rand(c, device="cuda")
+    mean, invstd = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
     drop = (torch.rand(b, c, device="cuda") > 0.1).float() / 0.9
+    stats = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
+    ops.channel_stats(sets[0][0], stats)
     it = [0]
-
-    def run(masked):
-        g, y, m = sets[it[0] % 6]
-        it[0] += 1
-        ops.bn_bwd(g, y, gamma, mean, invstd, mask=m, drop=drop, want_masked=masked)
-
     t_bytes = b * h * w * c * 2
-    from erfnet_pytorch_b200 import _lib
-    L = _lib.lib()
-    sums = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
-    dy = torch.empty_like(sets[0][0])
-    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
-    st = ops._stream(dy)
+    for hot in (False, True):
+        def pick():
+            s = sets[0] if hot else sets[it[0] % 6]
+            it[0] += 1
+            return s
 
-    def red():
-        g, y, m = sets[it[0] % 6]
-        it[0] += 1
-        ops.check(L.erf_bn_bwd_reduce(ops._p(g), c, ops._p(y), c, ops._p(m), c, ops._p(drop), ops._p(mean), ops._p(invstd), b, h * w, c, ops._p(sums), 1, st))
+        def bwd(masked, from_y=False):
+            g, y, m = pick()
+            if arena.cursor + 2 * c + 1 > arena.buf.numel():
+                arena.cursor = 0      # (the slots are only ever incremented by the barrier: reuse is fine for timing as long as they were re-zeroed)
+                arena.buf.zero_()
+            ops.bn_bwd(g, y, gamma, mean, invstd, mask=m, drop=drop if masked else None, want_masked=masked, beta_for_mask=beta if from_y else None)
 
-    def app():
-        g, y, m = sets[it[0] % 6]
-        it[0] += 1
-        ops.check(L.erf_bn_bwd_apply(ops._p(g), c, ops._p(y), c, ops._p(m), c, ops._p(drop), ops._p(gamma), ops._p(mean), ops._p(invstd), ops._p(sums), b, h * w, c,
-                                     ops._p(dy), c, ops._p(dg), ops._p(db), None, c, 1, st))
+        def fwd(res):
+            g, y, m = pick()
+            ops.bn_apply(g, stats, b * h * w, gamma, beta, rm, rv, 0.1, 1e-3, drop=drop if res else None, res=y if res else None, relu=True)
 
-    ur, ua = timeit(red), timeit(app)
-    print(f"C={c:3d}: reduce {ur:6.1f} us ({3 * t_bytes / ur / 1e6:5.2f} TB/s)   apply {ua:6.1f} us ({4 * t_bytes / ua / 1e6:5.2f} TB/s)")
-    us = timeit(lambda: run(False))
-    us2 = timeit(lambda: run(True))
-    sc, sh = torch.rand(c, device="cuda"), torch.rand(c, device="cuda")
-
-    def aff():
-        g, y, m = sets[it[0] % 6]
-        it[0] += 1
-        ops.affine_act(g, sc, sh, res=y, relu=True, out=m)
-
-    us3 = timeit(aff)
-    print(f"C={c:3d} {h}x{w}: bn_bwd {us:6.1f} us ({7 * t_bytes / us / 1e6:5.2f} TB/s)  +gmasked {us2:6.1f} us ({8 * t_bytes / us2 / 1e6:5.2f} TB/s)  "
-          f"affine_act(res) {us3:6.1f} us ({3 * t_bytes / us3 / 1e6:5.2f} TB/s)")
+        row = []
+        for fused in (True, False):
+            ops.BN_FUSED = fused
+            arena.reset()
+            row += [timeit(lambda: bwd(False)), timeit(lambda: bwd(True)), timeit(lambda: fwd(False)), timeit(lambda: fwd(True))]
+        ops.BN_FUSED = True
+        arena.reset()
+        fy = timeit(lambda: bwd(False, True))
+        f = row[:4]
+        u = row[4:]
+        print(f"C={c:3d} {h}x{w} {'hot ' if hot else 'cold'}: bn_bwd fused {f[0]:6.1f} us ({4 * t_bytes / f[0] / 1e6:5.2f} TB/s algorithmic), mask from y {fy:6.1f} us / two launches {u[0]:6.1f} us;  "
+              f"+drop+gmasked {f[1]:6.1f} / {u[1]:6.1f} us;  bn_apply fused {f[2]:6.1f} / finalize+affine {u[2]:6.1f} us;  +drop+res {f[3]:6.1f} / {u[3]:6.1f} us")
+ops.ARENA = None

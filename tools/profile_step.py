@@ -26,19 +26,23 @@ def table(title, kt):
     print(f"--- {title}: {tot:.3f} ms in timed kernels")
     for k, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"]):
         tf = f"{v['flops'] / (v['ms'] * 1e-3) / 1e12:8.1f} TF/s" if v["flops"] else ""
-        print(f"{k:24s} n={v['n']:4d} {v['ms']:9.3f} ms {100 * v['ms'] / tot:5.1f}% {tf}")
+        print(f"{k:52s} n={v['n']:4d} {v['ms']:9.3f} ms {100 * v['ms'] / tot:5.1f}% {tf}")
 
 
 model.eval()
 for _ in range(2):
     with torch.no_grad():
         model(x)
+torch.cuda.synchronize()
+torch.cuda._sleep(int(0.02 * 1.9e9))
 ops.start_kernel_timing()
 with torch.no_grad():
     model(x)
 table(f"forward eval bf16 batch {B}", ops.stop_kernel_timing())
 for _ in range(2):
     tr.train_step(x, y)
+torch.cuda.synchronize()
+torch.cuda._sleep(int(0.06 * 1.9e9))     # park the GPU so that the whole step is queued: the event intervals then measure kernels, not the CPU launch path
 ops.start_kernel_timing()
 tr.train_step(x, y)
 table(f"train step bf16 batch {B}", ops.stop_kernel_timing())
