@@ -33,7 +33,8 @@ class Im2colDesc(C.Structure):
 class WgradIm2colDesc(C.Structure):
     _fields_ = ([("g", C.c_void_p)] + [(n, C.c_int) for n in ("GH", "GW", "g_ld", "Cg", "CgP", "g_copy_bytes", "g_step")] +
                 [("d", C.c_void_p)] + [(n, C.c_int) for n in ("EN", "EH", "EW", "d_ld", "d_c0", "d_c_base", "Cd", "NP", "ntaps")] +
-                [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("tap_off", C.c_int * 9), ("KHW", C.c_int), ("tail_bytes", C.c_int)])
+                [("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("tap_off", C.c_int * 9), ("KHW", C.c_int), ("tail_bytes", C.c_int),
+                 ("g_step_x", C.c_int), ("fold", C.c_int), ("fold_c", C.c_int)])
 
 
 class Im2colTaps(C.Structure):
@@ -65,6 +66,8 @@ _SIGNATURES = {
     "erf_bn_bwd_fused": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "erf_ce_weight_sum": [_vp, _ll, _vp, _i, _i, _vp, _vp],
     "erf_ce_fwd_bwd": [_vp, _i, _i, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "erf_ce_fwd_bwd_colsum_supported": [_i, _i, _i],
+    "erf_ce_fwd_bwd_colsum": [_vp, _i, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "erf_confusion_hist": [_vp, _vp, _i, _ll, _i, _vp, _vp],
     "erf_iou_counts": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "erf_argmax": [_vp, _i, _i, _ll, _i, _vp, _i, _i, _vp],
@@ -83,6 +86,7 @@ _SIGNATURES = {
     "erf_pack_conv1d_tc_batched": [_vp, _i, _i, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_conv1d_wgrad_tc_fused": [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],
     "erf_conv_im2col_tc": [C.POINTER(Im2colDesc), _vp],
     "erf_pack_im2col_weights": [_vp, _ll, _ll, _i, _i, _i, C.POINTER(Im2colTaps), _i, _i, _vp, _vp],

@@ -359,6 +359,20 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
   uint4 cg[REGI], cy[REGI];
 
+  // Dropout2d multipliers of the current sample for this thread's 8 channels: a thread's pixels ascend, so the row changes at most
+  // N - 1 times (two 16-byte loads each) instead of eight scalar loads and a division per item
+  float dropv[8];
+  long long drop_n = -1, drop_end = 0;      // pixels [.., drop_end) belong to sample drop_n
+  auto load_drop = [&](long long q) {
+    if (q >= drop_end || drop_n < 0) {
+      drop_n = img_of(q, p.HW);
+      drop_end = (drop_n + 1) * p.HW;
+      const float4* dp = reinterpret_cast<const float4*>(p.drop + drop_n * C + r.c0);
+      const float4 a = dp[0], b = dp[1];
+      dropv[0] = a.x; dropv[1] = a.y; dropv[2] = a.z; dropv[3] = a.w;
+      dropv[4] = b.x; dropv[5] = b.y; dropv[6] = b.z; dropv[7] = b.w;
+    }
+  };
   // gq <- g * (mask > 0), in place
   auto apply_mask = [&](uint4& gq, const uint4& yq, const uint4& mq) {
     uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
@@ -386,9 +400,9 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
     float gf[8], yf[8], mu[8];
     unpack_bf8(gq, gf);
     if (p.drop) {
-      const float* dp = p.drop + img_of(q, p.HW) * C + r.c0;
+      load_drop(q);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) gf[k] *= dp[k];
+      for (int k = 0; k < 8; ++k) gf[k] *= dropv[k];
     }
     unpack_bf8(yq, yf);
     lds8(s_coef + 2 * C + r.c0, mu);
@@ -474,14 +488,15 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
     }
   }
   __syncthreads();
+  drop_n = -1;                               // phase 2 walks the pixels again from the start
   auto proc2 = [&](long long q, const uint4& gmq, const uint4& yq) {
     if (gmasked) *reinterpret_cast<uint4*>(gmasked + (size_t)q * p.gmasked_ld + r.c0) = gmq;
     float gf[8], yf[8], k[8];
     unpack_bf8(gmq, gf);
     if (p.drop) {
-      const float* dp = p.drop + img_of(q, p.HW) * C + r.c0;
+      load_drop(q);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gf[e] *= dp[e];
+      for (int e = 0; e < 8; ++e) gf[e] *= dropv[e];
     }
     lds8(s_coef + 3 * C + r.c0, k);
 #pragma unroll
@@ -649,7 +664,7 @@ extern "C" int erf_bn_bwd_fused(const void* g, int g_ld, const void* y, int y_ld
   ERF_CHECK_ARG(!beta_for_mask || (mask && !drop), "erf_bn_bwd_fused: the mask can only be recomputed from y for a plain BN -> ReLU (mask tensor still required as the fallback operand, no dropout)");
   const bool ok = !fused_disabled() && bs_fast_ok(C) && C <= 256 && (g_ld % 8) == 0 && (y_ld % 8) == 0 && (dy_ld % 8) == 0 && (!mask || (mask_ld % 8) == 0) &&
                   (!gmasked || (gmasked_ld % 8) == 0) && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)mask % 16) == 0 &&
-                  ((uintptr_t)dy % 16) == 0 && ((uintptr_t)gmasked % 16) == 0;
+                  ((uintptr_t)dy % 16) == 0 && ((uintptr_t)gmasked % 16) == 0 && ((uintptr_t)drop % 16) == 0;
   if (ok) {
     BnBwdFusedParams p;
     p.g = g; p.y = y; p.mask = mask;

@@ -45,7 +45,7 @@ struct Conv1dTcParams {
 };
 
 constexpr int kMaxSlots = 8;
-constexpr int kThreads = 352;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warp 10 statistics MMAs
+constexpr int kThreads = 384;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warps 10-11 per-channel statistics
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -69,35 +69,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   constexpr int STG_PAD = ((STG_BYTES + 1023) / 1024) * 1024;
   constexpr int STG_TOTAL = 4 * STG_PAD;        // 2 epilogue groups x double buffer
   constexpr int EW = C >= 32 ? 32 : 16;         // epilogue column chunk
-  // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) ride on the tensor pipe: the staged output
-  // sub-tile Y [128 px][64 ch] is an MN-major operand, so  Y^T Y (Gram, diagonal = sum of squares) and  Y^T 1  (sums) are
-  // two more accumulating MMAs per sub-tile, issued by warp 10 into their own TMEM columns and read once at the end.
+  // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) of the STORED output are taken by warps 10-11 from the
+  // staged bf16 sub-tiles (see their role below).
   constexpr bool RED = true;
-  constexpr int GW = CH;                                                   // Gram width = channels of a sub-tile (64, or 16 for C = 16)
-  constexpr uint32_t GRAM_COL = 2 * C, ONES_COL = 2 * C + KC * GW;         // KC x GW Gram columns, KC x 16 sum columns
-  constexpr uint32_t TMEM_COLS = C == 128 ? 512 : (C == 64 ? 256 : 64);
+  constexpr uint32_t TMEM_COLS = C == 128 ? 256 : (C == 64 ? 128 : 32);   // two accumulators of C columns
   constexpr uint32_t IDESC = make_idesc_bf16(128, C);
-  constexpr uint32_t IDESC_GRAM = make_idesc_bf16(128, GW) | (1u << 15) | (1u << 16);  // both operands MN-major
-  constexpr uint32_t IDESC_ONES = make_idesc_bf16(128, 16) | (1u << 15) | (1u << 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;
   uint8_t* s_stg = smem + W_PAD;
   uint8_t* s_a = s_stg + STG_TOTAL;
-  uint8_t* s_ones = s_a + (size_t)p.slots * p.slot_bytes;   // 512 B of bf16 1.0 (statistics mode only)
   __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar[4];
-  __shared__ uint64_t sfull_bar[4], sdone_bar[4], sfinal_bar;   // staged sub-tile ready / statistics MMAs done (per group x buffer)
+  __shared__ uint64_t sfull_bar[4], sdone_bar[4];   // staged sub-tile ready / read by both statistics warps (per group x buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[C];
+  __shared__ float s_stat[2][2 * C];                // per statistics warp: [C] sums, [C] sums of squares
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_trigger();   // the set-up below overlaps the previous kernel's tail; nothing before pdl_wait() touches tensors an earlier kernel writes
   for (int i = tid; i < C; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   const bool want_red = RED && (p.stats != nullptr || p.colsum != nullptr);
-  if (want_red) {
-    for (int i = tid; i < 128; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
-    fence_proxy_async_smem();
-  }
   if (tid == 0) {
     for (int s = 0; s < p.slots; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -111,9 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     for (int a = 0; a < 4; ++a) {
       mbar_init(&aux_bar[a], 1);
       mbar_init(&sfull_bar[a], 1);
-      mbar_init(&sdone_bar[a], 1);
+      mbar_init(&sdone_bar[a], 2);
     }
-    mbar_init(&sfinal_bar, 1);
     fence_barrier_init();
     if (p.w_static) {   // static weights: fetch them while the previous kernel's last CTAs are still running
       mbar_arrive_expect_tx(&w_bar, W_BYTES);
@@ -239,16 +229,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp == 10) {
-    // ================= statistics MMAs: Y^T Y and Y^T 1 of every staged sub-tile =================
-    if (RED && want_red) {   // whole warp, one elected lane issues
-      const uint32_t hi128 = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);           // MN-major, 8 pixel rows of RB bytes per atom
-      const uint32_t hi32 = ((8u * 32u) >> 4) | (1u << 14) | (LAYOUT_SW32 << 29);      // the ones operand: 16 "channels" = 32-byte rows
-      const uint32_t ones_addr = smem_u32(s_ones);
-      const uint64_t d_ones = ((uint64_t)hi32 << 32) | (uint64_t)((ones_addr >> 4) & 0x3FFF);
+  } else if (warp >= 10) {
+    // ================= per-channel statistics of every staged sub-tile on the CUDA cores =================
+    // (sum and sum of squares for the BN batch statistics, sum alone for a bias gradient.)  Round 1 took them as two more MMAs per
+    // sub-tile (Y^T Y Gram diagonal, Y^T 1): correct, but the Gram MMAs cost as many tensor-pipe cycles as the convolution itself
+    // (+5 us per launch, 34 launches per step).  Two warps reading the staged bf16 tile back -- one conflict-free 4-byte word per lane
+    // and pixel row, 64 rows each -- cost ~220 issue slots per scheduler and sub-tile and leave the tensor pipe to the convolution.
+    if (want_red) {
+      const int sw = warp - 10;                       // rows [64*sw, 64*sw + 64) of every sub-tile
+      constexpr int LPR = RB / 4;                     // lanes per pixel row: 32 (one 128-byte row per load) or 8 (four 32-byte rows per load)
+      constexpr int RPI = 32 / LPR;                   // rows per load instruction
+      const int wl = lane % LPR;                      // 4-byte word of the row = channel pair (2*wl, 2*wl + 1)
+      const int jl = wl >> 2;                         // logical 16-byte chunk holding that word
+      float s0[KC], s1[KC], q0[KC], q1[KC];
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) s0[kc] = s1[kc] = q0[kc] = q1[kc] = 0.f;
       int cnt[2] = {0, 0};
       uint32_t ph[4] = {0, 0, 0, 0};
-      uint32_t started = 0;   // bit kc: the accumulators of k-chunk kc hold data
       int i = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
         const int g = i & 1;
@@ -258,25 +255,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
           ++cnt[g];
           mbar_wait(&sfull_bar[g * 2 + b], ph[g * 2 + b]);
           ph[g * 2 + b] ^= 1;
-          tcgen05_fence_after();
-          const uint32_t tile = smem_u32(s_stg + (g * 2 + b) * STG_PAD);
-          // M = 128 = 128/GW channel atoms: the sub-tile and (LBO away each) whatever follows it in shared memory (the next staging
-          // buffers or the operand ring); rows GW..127 of D are never read and cannot influence rows 0..GW-1
-          const uint32_t a_lo = ((tile >> 4) & 0x3FFF) | (((STG_PAD >> 4) & 0x3FFF) << 16);
-          const uint32_t b_lo = ((tile >> 4) & 0x3FFF) | (1u << 16);
-          const uint32_t acc_en = (started >> kc) & 1u;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {   // K = 128 pixels, 16 per MMA = 16 rows of RB bytes
-            const uint64_t da = ((uint64_t)hi128 << 32) | (uint64_t)(a_lo + k * RB);
-            if (p.stats)
-              if (elect_one()) umma_bf16(tmem_base + GRAM_COL + kc * GW, da, ((uint64_t)hi128 << 32) | (uint64_t)(b_lo + k * RB), IDESC_GRAM, (acc_en | k) ? 1u : 0u);
-            if (elect_one()) umma_bf16(tmem_base + ONES_COL + kc * 16, da, d_ones, IDESC_ONES, (acc_en | k) ? 1u : 0u);
+          const uint8_t* tile = s_stg + (g * 2 + b) * STG_PAD;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;   // two independent chains per value
+#pragma unroll 8
+          for (int it = 0; it < 64 / RPI; it += 2) {
+            const int r0 = sw * 64 + it * RPI + lane / LPR, r1 = r0 + RPI;
+            const int k0 = CPR == 8 ? (r0 & 7) : ((r0 >> 2) & 1), k1 = CPR == 8 ? (r1 & 7) : ((r1 >> 2) & 1);
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile + r0 * RB + ((jl ^ k0) * 16) + (wl & 3) * 4);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(tile + r1 * RB + ((jl ^ k1) * 16) + (wl & 3) * 4);
+            const float x0 = __uint_as_float(w0 << 16), y0 = __uint_as_float(w0 & 0xFFFF0000u);
+            const float x1 = __uint_as_float(w1 << 16), y1 = __uint_as_float(w1 & 0xFFFF0000u);
+            a0 += x0; a1 += y0; b0 = fmaf(x0, x0, b0); b1 = fmaf(y0, y0, b1);
+            c0 += x1; c1 += y1; d0 = fmaf(x1, x1, d0); d1 = fmaf(y1, y1, d1);
           }
-          started |= 1u << kc;
-          if (elect_one()) umma_commit(&sdone_bar[g * 2 + b]);
+          s0[kc] += a0 + c0; s1[kc] += a1 + c1; q0[kc] += b0 + d0; q1[kc] += b1 + d1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sdone_bar[g * 2 + b]);     // this warp has read the sub-tile (the barrier counts both statistics warps)
         }
       }
-      if (elect_one()) umma_commit(&sfinal_bar);
+      // combine: lanes sharing a channel pair (C = 16: four groups of 8 lanes), then the two warps through shared memory, one atomic per channel
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int off = LPR; off < 32; off <<= 1) {
+          s0[kc] += __shfl_xor_sync(0xffffffffu, s0[kc], off);
+          s1[kc] += __shfl_xor_sync(0xffffffffu, s1[kc], off);
+          q0[kc] += __shfl_xor_sync(0xffffffffu, q0[kc], off);
+          q1[kc] += __shfl_xor_sync(0xffffffffu, q1[kc], off);
+        }
+        if (lane < LPR) {
+          const int c = kc * CH + 2 * wl;
+          s_stat[sw][c] = s0[kc]; s_stat[sw][c + 1] = s1[kc];
+          s_stat[sw][C + c] = q0[kc]; s_stat[sw][C + c + 1] = q1[kc];
+        }
+      }
+      asm volatile("bar.sync 5, 64;" ::: "memory");               // the two statistics warps
+      for (int c = tid - 320; c < C; c += 64) {
+        const float sum = s_stat[0][c] + s_stat[1][c];
+        if (p.colsum) atomicAdd(&p.colsum[c], sum);
+        if (p.stats) {
+          atomicAdd(&p.stats[c], (double)sum);
+          atomicAdd(&p.stats[C + c], (double)(s_stat[0][C + c] + s_stat[1][C + c]));
+        }
+      }
     }
   } else {
     // ================= epilogue: group 0 = warps 2..5, group 1 = warps 6..9; TMEM lane quadrant = warp % 4 =========
@@ -395,48 +415,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
-    if constexpr (RED) {
-      if (want_red && grp == 0 && quad * 32 < GW) {   // whole warps (tcgen05.ld is warp-collective); TMEM lanes 0..GW-1 = the channels of a k-chunk
-        const bool mine = quad * 32 + lane < GW;         // one atomic per channel and CTA
-        mbar_wait(&sfinal_bar, 0);
-        tcgen05_fence_after();
-        const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
-#pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-          const int c = kc * GW + quad * 32 + lane;
-          uint32_t o[16];
-          tmem_ld16(tmem_base + ONES_COL + kc * 16 + lane_bits, o);
-          tmem_ld_wait();
-          const float sum = __uint_as_float(o[0]);
-          if (p.colsum && mine) atomicAdd(&p.colsum[c], sum);
-          if (p.stats) {
-            float sq = 0.f;   // the diagonal element: column (quad*32 + lane) of this thread's row
-            if constexpr (GW == 64) {
-              uint32_t g0[32], g1[32];
-              tmem_ld32(tmem_base + GRAM_COL + kc * GW + lane_bits, g0);
-              tmem_ld32(tmem_base + GRAM_COL + kc * GW + 32 + lane_bits, g1);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j == lane) sq = __uint_as_float(quad == 0 ? g0[j] : g1[j]);
-              }
-            } else {
-              uint32_t g0[16];
-              tmem_ld16(tmem_base + GRAM_COL + lane_bits, g0);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (j == lane) sq = __uint_as_float(g0[j]);
-              }
-            }
-            if (mine) {
-              atomicAdd(&p.stats[c], (double)sum);
-              atomicAdd(&p.stats[C + c], (double)sq);
-            }
-          }
-        }
-      }
-    }
   }
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();
@@ -518,15 +496,14 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.slot_bytes = p.sub_bytes;   // one (tap, k-chunk) tile [vertical] or one k-chunk of the haloed row tile [horizontal]
   const int w_pad = ((3 * KC * C * RB + 1023) / 1024) * 1024;
   const int stg_pad = 4 * (((128 * RB + 1023) / 1024) * 1024);
-  const int ones_bytes = (stats || colsum) ? 1024 : 0;   // bf16 ones operand of the statistics MMAs
-  const int budget = 225 * 1024 - w_pad - stg_pad - ones_bytes;
+  const int budget = 222 * 1024 - w_pad - stg_pad;   // + 1 KB alignment slack + ~3 KB of static shared memory (barriers, bias, statistics) <= 227 KB
   p.slots = budget / p.slot_bytes;
   if (p.slots > kMaxSlots) p.slots = kMaxSlots;
   if (p.slots < 2) {
     set_error("erf_conv1d_tc: tile does not fit in shared memory");
     return ERF_ERR_UNSUPPORTED;
   }
-  size_t smem = (size_t)w_pad + stg_pad + (size_t)p.slots * p.slot_bytes + ones_bytes + 1024;
+  size_t smem = (size_t)w_pad + stg_pad + (size_t)p.slots * p.slot_bytes + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -538,6 +515,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = prefer_max_smem(conv1d_tc_kernel<16>);
     if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<16>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

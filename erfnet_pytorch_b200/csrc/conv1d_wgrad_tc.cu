@@ -20,6 +20,8 @@ namespace erfk {
 using namespace tc;
 
 struct WgradTcParams {
+  float* dw;          // fused reduction: the torch-layout gradient the partial sums are added to (null: a second kernel reduces)
+  unsigned* counter;  // fused reduction: zeroed grid-barrier word
   float* ws;      // [grid][ACCS][128][C] per-CTA partial sums
   int N, H, W;
   int horizontal, dil;
@@ -169,6 +171,64 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (p.dw == nullptr) return;
+  // ---- fused reduction of the per-CTA partial sums (no second launch): after a grid barrier CTA b owns a contiguous range of the slab's
+  // float4s, sums it over all CTAs' slabs straight from L2 (eight independent 16-byte loads in flight per thread, S threads per output
+  // splitting the slabs) and adds the result to the torch-layout gradient -- every output element has exactly one owner, so no atomics.
+  grid_barrier(p.counter, gridDim.x);
+  {
+    constexpr int SLAB4 = ACCS * 128 * C / 4;                 // float4s per slab, layout [acc][col/4][row][4]
+    __shared__ float4 s_red[192];
+    const int per = (SLAB4 + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int f0 = blockIdx.x * per;
+    const float4* wsv = reinterpret_cast<const float4*>(p.ws);
+    for (int base = 0; base < per; base += 192) {             // one pass unless a CTA owns more than 192 float4s
+      const int span = per - base < 192 ? per - base : 192;   // outputs of this pass
+      const int S = 192 / span;                               // threads per output (>= 1)
+      const int o = tid % span, sidx = tid / span;
+      const int f = f0 + base + o;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      if (sidx < S && f < SLAB4) {
+        const float4* src = wsv + f;
+        const int nb = (int)gridDim.x;
+        constexpr int RU = 16;                                  // independent 16-byte loads in flight per thread (the phase is L2-latency-bound)
+        for (int b = sidx; b < nb; b += RU * S) {
+          float4 v[RU];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) v[u] = b + u * S < nb ? __ldcg(src + (size_t)(b + u * S) * SLAB4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < RU; u += 2) {
+            a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+            a1.x += v[u + 1].x; a1.y += v[u + 1].y; a1.z += v[u + 1].z; a1.w += v[u + 1].w;
+          }
+        }
+      }
+      s_red[tid] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+      __syncthreads();
+      if (tid < span && f < SLAB4) {
+        float4 t4 = s_red[tid];
+        for (int k = 1; k < S; ++k) {
+          const float4 v = s_red[tid + k * span];
+          t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+        }
+        const int row = f & 127, c4 = (f >> 7) % (C / 4), acc = (f >> 7) / (C / 4);
+        int t, ci;
+        bool ok = true;
+        if (C == 128) { t = acc; ci = row; }
+        else if (C == 64) { t = acc + (row >> 6); ci = row & 63; ok = !(acc == 1 && row < 64); }   // accumulator 1 repeats tap 1 in rows 0..63
+        else { t = row >> 4; ci = row & 15; ok = t <= 2; }                                          // rows 48..127 are the ignored atoms
+        if (ok) {
+          const float v[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float* dst = p.dw + ((size_t)(c4 * 4 + e) * C + ci) * 3 + t;
+            *dst += v[e];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // dw[co][ci][t] (the nn.Conv2d layout [Co,Ci,3,1] / [Co,Ci,1,3]) += sum over CTAs of the partial accumulators.
@@ -192,6 +252,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const float* src = ws + i;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int b = b0;
+  for (; b + 8 <= b1; b += 8) {      // eight independent loads in flight: the kernel is L2-latency-bound
+    const float v0 = src[(size_t)b * SLAB], v1 = src[(size_t)(b + 1) * SLAB], v2 = src[(size_t)(b + 2) * SLAB], v3 = src[(size_t)(b + 3) * SLAB];
+    const float v4 = src[(size_t)(b + 4) * SLAB], v5 = src[(size_t)(b + 5) * SLAB], v6 = src[(size_t)(b + 6) * SLAB], v7 = src[(size_t)(b + 7) * SLAB];
+    s0 += v0 + v4;
+    s1 += v1 + v5;
+    s2 += v2 + v6;
+    s3 += v3 + v7;
+  }
   for (; b + 4 <= b1; b += 4) {
     s0 += src[(size_t)b * SLAB];
     s1 += src[(size_t)(b + 1) * SLAB];
@@ -231,8 +299,22 @@ extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) {
   return (size_t)(C == 16 ? 296 : 148) * (C == 128 ? 3 : (C == 64 ? 2 : 1)) * 128 * C * sizeof(float);
 }
 
+static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, unsigned* counter, int N, int H, int W, int C, int horizontal,
+                        int dil, erf_stream_t stream);
+
 extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W, int C,
                                    int horizontal, int dil, erf_stream_t stream) {
+  return wgrad_launch(x, dy, dw, workspace, ws_bytes, nullptr, N, H, W, C, horizontal, dil, stream);
+}
+
+extern "C" int erf_conv1d_wgrad_tc_fused(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, unsigned* counter, int N, int H,
+                                         int W, int C, int horizontal, int dil, erf_stream_t stream) {
+  ERF_CHECK_ARG(counter, "erf_conv1d_wgrad_tc_fused: null barrier counter");
+  return wgrad_launch(x, dy, dw, workspace, ws_bytes, counter, N, H, W, C, horizontal, dil, stream);
+}
+
+static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, unsigned* counter, int N, int H, int W, int C, int horizontal,
+                        int dil, erf_stream_t stream) {
   ERF_CHECK_ARG(x && dy && dw && workspace, "erf_conv1d_wgrad_tc: null pointer");
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_wgrad_tc: empty tensor");
   if (!((C == 16 || C == 64 || C == 128) && W >= 64 && (W % 64) == 0 && dil >= 1 && dil <= 32)) {
@@ -249,6 +331,8 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
     return ERF_ERR_CUDA;
   }
   WgradTcParams p;
+  p.dw = nullptr;
+  p.counter = counter;
   p.ws = (float*)workspace;
   p.N = N; p.H = H; p.W = W; p.horizontal = horizontal; p.dil = dil;
   p.units = N * H * (W / PX);
@@ -272,23 +356,41 @@ extern "C" int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, voi
   int grid = p.units < ctas ? p.units : ctas;
   cudaError_t e;
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool fuse_off = getenv("ERF_WGRAD_FUSED") && atoi(getenv("ERF_WGRAD_FUSED")) == 0;
+  bool fused = counter != nullptr && !fuse_off;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = prefer_max_smem(conv1d_wgrad_tc_kernel<16>);
     if (e == cudaSuccess) {
+      if (fused) {   // the grid barrier needs every CTA resident
+        int occ = 0;
+        fused = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv1d_wgrad_tc_kernel<16>, 192, smem) == cudaSuccess && grid <= occ * 148;
+      }
+      if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<16>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      launch_pdl(wgrad_reduce_kernel<16>, dim3(dim3((1 * 128 * 16 + 255) / 256, 37)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused) launch_pdl(wgrad_reduce_kernel<16>, dim3(dim3((1 * 128 * 16 + 255) / 256, 37)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
+      if (fused) {   // the grid barrier needs every CTA resident
+        int occ = 0;
+        fused = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv1d_wgrad_tc_kernel<64>, 192, smem) == cudaSuccess && grid <= occ * 148;
+      }
+      if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<64>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      launch_pdl(wgrad_reduce_kernel<64>, dim3(dim3((2 * 128 * 64 + 255) / 256, 12)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused) launch_pdl(wgrad_reduce_kernel<64>, dim3(dim3((2 * 128 * 64 + 255) / 256, 12)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
+      if (fused) {   // the grid barrier needs every CTA resident
+        int occ = 0;
+        fused = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv1d_wgrad_tc_kernel<128>, 192, smem) == cudaSuccess && grid <= occ * 148;
+      }
+      if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<128>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      launch_pdl(wgrad_reduce_kernel<128>, dim3(dim3((3 * 128 * 128 + 255) / 256, 6)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused) launch_pdl(wgrad_reduce_kernel<128>, dim3(dim3((3 * 128 * 128 + 255) / 256, 6)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   }
   if (e != cudaSuccess) {

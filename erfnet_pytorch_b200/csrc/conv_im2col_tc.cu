@@ -371,6 +371,7 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   cudaError_t e = cudaSuccess;
 #define IM_LAUNCH(NP_, NCHW_)                                                                                                  \
   e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_, NCHW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e == cudaSuccess && per_sm > 1) e = prefer_max_smem(conv_im2col_tc_kernel<NP_, NCHW_>);                                   \
   if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_, NCHW_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), p, slots, slot_bytes, w_bytes);
   if (d->nchw_out != nullptr) {
     if (d->NP == 32) { IM_LAUNCH(32, true) } else { IM_LAUNCH(64, true) }

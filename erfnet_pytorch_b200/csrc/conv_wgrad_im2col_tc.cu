@@ -13,6 +13,7 @@
 // or 8 taps of a 16-channel one at full tensor-core width (the same trick as conv1d_wgrad_tc.cu).  Each group of 128 M rows
 // owns one TMEM accumulator [128 x NP]; a persistent CTA accumulates over all its 64-pixel units and dumps once.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -32,7 +33,17 @@ __device__ __forceinline__ void wi_cp_async(void* smem_dst, const void* gsrc, in
 }
 
 // smem stage layout: [gathered: ntaps*gsubs sub-tiles of 64 px x CHg][dense: dsubs sub-tiles of 64 px x CHd]
-__global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(const erf_wgrad_im2col_desc p, const int stages, const int stage_bytes,
+// MINB = CTAs per SM the launch is sized for: 2 caps the registers at 113 (small layers, latency-bound per-unit chain), 1 leaves the loaders'
+// hoisted index tables in registers (large layers, one 181 KB ring per SM)
+// TMA = true: the tap tiles and the dense tile arrive by cp.async.bulk.tensor from two tensor maps (built per launch by the host).  A strided
+// gather is a TILED map with element strides: boxDim = 64 * step along W with elementStrides = step loads every step-th pixel, rows / columns
+// outside the tensor are zero-filled (= the conv padding), and the hardware swizzle reproduces the operand layout the software gather
+// wrote.  One elected lane then issues ntaps * gsubs + dsubs copies per 64-pixel unit, where 128 loader threads spent ~600 instructions per
+// unit on index arithmetic (ncu: the loaders' latency-bound instruction stream set the kernel time, 94 us for the head against a 27 us
+// DRAM floor).  Needs row-aligned units (EW % 64 == 0) and 16-byte aligned pixel rows; everything else keeps the cp.async gather.
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(kWiThreads, MINB) conv_wgrad_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_d,
+                                                                             const erf_wgrad_im2col_desc p, const int stages, const int stage_bytes,
                                                                              const int dense_off, const int groups, float* __restrict__ ws) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -53,11 +64,15 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
   for (int i = tid; i < (stages * stage_bytes + p.tail_bytes) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 128);
+      mbar_init(&full_bar[s], TMA ? 1 : 128);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
+    if (TMA) {
+      tma_prefetch_desc(&tmap_g);
+      tma_prefetch_desc(&tmap_d);
+    }
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -68,7 +83,32 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
 
-  if (warp < 4) {
+  if (TMA && warp < 4) {
+    // ================= TMA producer: warp 0, one elected lane issues (uniform control flow) =================
+    if (warp == 0) {
+      const int gsx = p.g_step_x > 0 ? p.g_step_x : p.g_step;
+      const uint32_t tx = (uint32_t)(p.ntaps * gsubs * g_sub_bytes + dsubs * d_sub_bytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const unsigned q0 = (unsigned)u * (unsigned)kWiPX;
+        const unsigned t2 = q0 / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
+        const int x0 = (int)(q0 - t2 * (unsigned)p.EW), y0 = (int)(t2 - nn * (unsigned)p.EH);
+        uint8_t* base = smem + (size_t)stage * stage_bytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          for (int t = 0; t < p.ntaps; ++t)
+            for (int sub = 0; sub < gsubs; ++sub)
+              tma_load_4d(base + (t * gsubs + sub) * g_sub_bytes, &tmap_g, &full_bar[stage], sub * CHg, gsx * x0 + p.tap_dx[t], p.g_step * y0 + p.tap_dy[t], (int)nn);
+          for (int sub = 0; sub < dsubs; ++sub)
+            tma_load_4d(base + dense_off + sub * d_sub_bytes, &tmap_d, &full_bar[stage], p.d_c0 + sub * CHd, x0, y0, (int)nn);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < 4) {
     // ================= loaders =================
     const uint8_t* G = reinterpret_cast<const uint8_t*>(p.g);
     const uint8_t* D = reinterpret_cast<const uint8_t*>(p.d);
@@ -78,7 +118,11 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
     const int d_chunks = p.NP / 8;                          // 16-byte chunks per dense pixel
     int stage = 0;
     uint32_t phase = 0;
-    int pend = -1;
+    // completion lag: a unit's copies are awaited (cp.async.wait_group) only after LAG later units have been issued, so LAG + 1 units of
+    // gathers are in flight per CTA -- the small layers' units are 14-24 KB, far too little for one unit in flight to cover DRAM latency
+    const int lag = stages >= 4 ? 2 : 1;
+    int pend[2] = {-1, -1};                                  // stages of the units issued but not yet signalled (oldest first)
+    const int gsx = p.g_step_x > 0 ? p.g_step_x : p.g_step;
     // Loop-invariant part of this thread's copy items, hoisted (same reasoning as conv_im2col_tc.cu: with one loader warp per scheduler the
     // gather is bound by the instruction latency of its index arithmetic).  Items (tap, row, chunk) are dealt round-robin to the 128 loader
     // threads; when one tap's items (64 * g_chunks) are a multiple of 128, a thread owns the SAME (row, chunk) pairs in every tap and unit.
@@ -109,10 +153,45 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
       d_srcoff[m] = (uint32_t)(c16 * 16);
     }
     const uint32_t tap_pitch = (uint32_t)(gsubs * g_sub_bytes);
+    // Row-aligned units (EW % 64 == 0, every layer of the net): a unit is 64 consecutive pixels of ONE image row, so (n, y, x0) come from two
+    // divisions per unit and a thread's pixel is x0 + its fixed row index -- no per-pixel table, no loader-group barrier.  The small layers
+    // (14-24 KB per unit, two CTAs per SM) were bound by exactly that per-unit bookkeeping: ~2.4 us per unit for the head.
+    const bool aligned = fast_g && (p.EW % kWiPX) == 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* base = smem + (size_t)stage * stage_bytes;
       const uint32_t base_addr = smem_u32(base);
+      if (aligned) {
+        const unsigned q0 = (unsigned)u * (unsigned)kWiPX;
+        const unsigned t2 = q0 / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
+        const int x0 = (int)(q0 - t2 * (unsigned)p.EW), y0 = (int)(t2 - nn * (unsigned)p.EH);
+        const int gy = p.g_step * y0;
+        const size_t img = (size_t)nn * p.GH;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+          const bool oky = (unsigned)(gy + dy) < (unsigned)p.GH;
+          const uint8_t* rowp = G + ((img + (oky ? gy + dy : 0)) * p.GW) * (size_t)p.g_ld * 2;
+          const uint32_t tbase = base_addr + (uint32_t)t * tap_pitch;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            if (m < gm) {
+              const int gx = gsx * (x0 + g_row[m]) + dx;
+              const bool ok = oky && (unsigned)gx < (unsigned)p.GW;
+              const uint8_t* src = ok ? rowp + (size_t)gx * p.g_ld * 2 + g_srcoff[m] : G;
+              if (g_chunk == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tbase + g_dst[m]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+              else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tbase + g_dst[m]), "l"(src), "r"(ok ? 8u : 0u) : "memory");
+            }
+          }
+        }
+        const uint8_t* drow = D + ((((size_t)nn * p.EH + y0) * p.EW + x0) * p.d_ld + p.d_c0) * 2;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          if (m < dm)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base_addr + d_dst[m]), "l"(drow + (size_t)d_row[m] * p.d_ld * 2 + d_srcoff[m]), "r"(16u) : "memory");
+        }
+      } else {
       // per-unit pixel table (64 rows); the loader group syncs on named barrier 1
       if (tid < kWiPX) {
         const unsigned q = (unsigned)u * (unsigned)kWiPX + (unsigned)tid;   // 32-bit index arithmetic (host-checked range)
@@ -134,7 +213,7 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
           if (m < gm) {
             const int n = s_row[stage][g_row[m]][0];
             gy0[m] = n >= 0 ? p.g_step * s_row[stage][g_row[m]][1] : -(1 << 28);
-            gx0[m] = p.g_step * s_row[stage][g_row[m]][2];
+            gx0[m] = gsx * s_row[stage][g_row[m]][2];
             gsrc[m] = G + ((((size_t)(n >= 0 ? n : 0) * p.GH + (n >= 0 ? gy0[m] : 0)) * p.GW + gx0[m]) * p.g_ld) * 2 + g_srcoff[m];
           }
         }
@@ -160,7 +239,7 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
         for (int it = tid; it < g_items; it += 128) {
           const int ch = it % g_chunks, row = (it / g_chunks) % kWiPX, t = it / (g_chunks * kWiPX);
           const int n = s_row[stage][row][0];
-          const int gy = p.g_step * s_row[stage][row][1] + p.tap_dy[t], gx = p.g_step * s_row[stage][row][2] + p.tap_dx[t];
+          const int gy = p.g_step * s_row[stage][row][1] + p.tap_dy[t], gx = gsx * s_row[stage][row][2] + p.tap_dx[t];
           const bool ok = n >= 0 && gy >= 0 && gy < p.GH && gx >= 0 && gx < p.GW;
           const uint8_t* src = ok ? G + ((((size_t)n * p.GH + gy) * p.GW + gx) * p.g_ld) * 2 + ch * g_chunk : G;
           // destination: 16-byte chunk index c16 of the pixel row -> sub-tile c16 / (CHg/8), chunk within the sub-tile row
@@ -180,18 +259,30 @@ __global__ void __launch_bounds__(kWiThreads, 1) conv_wgrad_im2col_tc_kernel(con
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base_addr + d_dst[m]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
         }
       }
+      }   // !aligned
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (pend >= 0) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[pend]);
+      if (lag == 2) {
+        if (pend[0] >= 0) {
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[pend[0]]);
+        }
+        pend[0] = pend[1];
+        pend[1] = stage;
+      } else {
+        if (pend[1] >= 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[pend[1]]);
+        }
+        pend[1] = stage;
       }
-      pend = stage;
       if (++stage == stages) { stage = 0; phase ^= 1; }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_proxy_async_smem();
-    if (pend >= 0) mbar_arrive(&full_bar[pend]);
+    if (pend[0] >= 0) mbar_arrive(&full_bar[pend[0]]);
+    if (pend[1] >= 0) mbar_arrive(&full_bar[pend[1]]);
   } else if (warp == 4) {
     // ================= MMA issuer =================
     {   // whole warp: uniform control flow, one elected lane issues (see tc.cuh elect_one)
@@ -266,6 +357,14 @@ __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int cta
   const int tap = atom / gsubs, sub = atom % gsubs;
   const int cg = sub * CHg + row % CHg, cd = p.d_c0 - p.d_c_base + col;
   if (tap >= p.ntaps || cg >= p.Cg || cd >= p.Cd) return;
+  size_t out_idx;
+  if (p.fold > 0) {   // column-folded gathered operand: cg = b * fold + c
+    const int b = cg / p.fold, c = cg - b * p.fold;
+    if (c >= p.fold_c) return;
+    out_idx = ((size_t)cd * p.fold_c + c) * p.KHW + p.tap_off[tap] + b;
+  } else {
+    out_idx = ((size_t)cd * p.Cg + cg) * p.KHW + p.tap_off[tap];
+  }
   const int per = (ctas + gridDim.y - 1) / gridDim.y;  // CTA range split over blockIdx.y, one atomic per split
   const int b0 = blockIdx.y * per, b1 = min(b0 + per, ctas);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -277,7 +376,29 @@ __global__ void wgrad_im2col_reduce_kernel(const float* __restrict__ ws, int cta
     s3 += ws[(size_t)(b + 3) * per_cta + i];
   }
   for (; b < b1; ++b) s0 += ws[(size_t)b * per_cta + i];
-  if (b1 > b0) atomicAdd(&dw[((size_t)cd * p.Cg + cg) * p.KHW + p.tap_off[tap]], (s0 + s1) + (s2 + s3));
+  if (b1 > b0) atomicAdd(&dw[out_idx], (s0 + s1) + (s2 + s3));
+}
+
+typedef CUresult (*WiEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC bf16 tensor [N][H][W][ld] as (C = ld, W, H, N); box = {ch, box_w, 1, 1} traversed with steps (1, step_w, step_h, 1): ch channels of
+// box_w / step_w pixels of one row.  The row step only matters through the start coordinate (one row per box).
+static int wi_make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int ld, int ch, int box_w, int step_w, int step_h) {
+  static WiEncodeFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (WiEncodeFn)q;
+  }
+  if (!fn || box_w > 256) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)step_w, 1, 1};
+  (void)step_h;
+  return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 }  // namespace erfk
@@ -330,12 +451,33 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   ERF_CHECK_ARG(ws_bytes >= (size_t)grid * groups * 128 * d->NP * sizeof(float), "erf_conv_wgrad_im2col_tc: workspace too small");
   size_t smem = (size_t)stages * stage_bytes + p.tail_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_im2col_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // TMA loaders: row-aligned units, 16-byte aligned pixel rows and channel offsets, whole 16-byte gathered rows
+  static const bool tma_off = getenv("ERF_WGRAD_IM2COL_TMA") && atoi(getenv("ERF_WGRAD_IM2COL_TMA")) == 0;
+  CUtensorMap mg, md;
+  bool tma = !tma_off && (d->EW % kWiPX) == 0 && d->g_copy_bytes >= 16 && (d->g_ld % 8) == 0 && (d->d_ld % 8) == 0 && ((uintptr_t)d->g % 16) == 0 &&
+             ((uintptr_t)d->d % 16) == 0 && d->g_step >= 1 && d->g_step <= 4;
+  if (tma) {
+    const int gsx = d->g_step_x > 0 ? d->g_step_x : d->g_step;
+    tma = wi_make_map(&mg, d->g, d->EN, d->GH, d->GW, d->g_ld, CHg, kWiPX * gsx, gsx, d->g_step) == 0 &&
+          wi_make_map(&md, d->d, d->EN, d->EH, d->EW, d->d_ld, CHd, kWiPX, 1, 1) == 0;
+  }
+  if (!tma) { memset(&mg, 0, sizeof(mg)); memset(&md, 0, sizeof(md)); }
+  cudaError_t e;
+#define WI_ATTR(MINB_, TMA_)                                                                                                   \
+  e = cudaFuncSetAttribute(conv_wgrad_im2col_tc_kernel<MINB_, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e == cudaSuccess && MINB_ == 2) e = prefer_max_smem(conv_wgrad_im2col_tc_kernel<MINB_, TMA_>);
+  if (per_sm == 2) { if (tma) { WI_ATTR(2, true) } else { WI_ATTR(2, false) } }
+  else { if (tma) { WI_ATTR(1, true) } else { WI_ATTR(1, false) } }
+#undef WI_ATTR
   if (e != cudaSuccess) {
     set_error("erf_conv_wgrad_im2col_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return ERF_ERR_CUDA;
   }
-  launch_pdl(conv_wgrad_im2col_tc_kernel, dim3(grid), dim3(kWiThreads), smem, (cudaStream_t)(st), p, stages, stage_bytes, g_bytes, groups, (float*)workspace);
+#define WI_LAUNCH(MINB_, TMA_) \
+  launch_pdl(conv_wgrad_im2col_tc_kernel<MINB_, TMA_>, dim3(grid), dim3(kWiThreads), smem, (cudaStream_t)(st), mg, md, p, stages, stage_bytes, g_bytes, groups, (float*)workspace)
+  if (per_sm == 2) { if (tma) WI_LAUNCH(2, true); else WI_LAUNCH(2, false); }
+  else { if (tma) WI_LAUNCH(1, true); else WI_LAUNCH(1, false); }
+#undef WI_LAUNCH
   const int per_cta = groups * 128 * d->NP;
   const int rblocks = (per_cta + 255) / 256;
   const int rsplit = rblocks >= 148 ? 4 : (rblocks >= 32 ? 12 : 37);

@@ -31,9 +31,12 @@ template <int LD8>
 __global__ void __launch_bounds__(128) ce_fwd_bwd_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
                                                                    long long n_px, const float* __restrict__ weight, int C, int ignore,
                                                                    const float* __restrict__ wsum, float* __restrict__ loss_sum,
-                                                                   __nv_bfloat16* __restrict__ dlogits) {
+                                                                   __nv_bfloat16* __restrict__ dlogits, float* __restrict__ colsum) {
   pdl_enter();
   float lsum = 0.f;
+  float csum[LD8 * 8];      // colsum: per-class sums of the STORED (bf16) dlogits = the bias gradient of the conv that produced the logits
+#pragma unroll
+  for (int c = 0; c < LD8 * 8; ++c) csum[c] = 0.f;
   const float inv_w = 1.f / *wsum;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += (long long)gridDim.x * blockDim.x) {
     float v[LD8 * 8];
@@ -77,6 +80,10 @@ __global__ void __launch_bounds__(128) ce_fwd_bwd_nhwc_bf16_kernel(const __nv_bf
         for (int e = 0; e < 4; ++e) {
           const int c = q * 8 + 2 * e;
           h[e] = __floats2bfloat162_rn(k * (v[c] * inv_se - (c == t ? 1.f : 0.f)), k * (v[c + 1] * inv_se - (c + 1 == t ? 1.f : 0.f)));
+          if (colsum) {
+            csum[c] += __low2float(h[e]);
+            csum[c + 1] += __high2float(h[e]);
+          }
         }
         dst[q] = t4;   // padding channels (c >= C) get exactly 0 (v = 0, never the target)
       }
@@ -90,6 +97,16 @@ __global__ void __launch_bounds__(128) ce_fwd_bwd_nhwc_bf16_kernel(const __nv_bf
     lsum = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
     lsum = warp_sum(lsum);
     if (threadIdx.x == 0) atomicAdd(loss_sum, lsum);
+  }
+  if (colsum) {   // block-level class sums: warp shuffles, one shared-memory row per warp, one global atomic per class and block
+    __shared__ float s_cs[4][LD8 * 8];
+#pragma unroll
+    for (int c = 0; c < LD8 * 8; ++c) {
+      const float t = warp_sum(csum[c]);
+      if ((threadIdx.x & 31) == 0) s_cs[threadIdx.x >> 5][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(&colsum[threadIdx.x], (s_cs[0][threadIdx.x] + s_cs[1][threadIdx.x]) + (s_cs[2][threadIdx.x] + s_cs[3][threadIdx.x]));
   }
 }
 
@@ -208,8 +225,26 @@ extern "C" int erf_ce_weight_sum(const int64_t* target, long long n_px, const fl
   return ERF_OK;
 }
 
+static int ce_launch(const void* logits, int ld, int nchw_hw, const int64_t* target, long long n_px, const float* weight, int C, int ignore_index,
+                     const float* wsum, float* loss_sum, void* dlogits, float* colsum, int dtype, erf_stream_t stream);
+
 extern "C" int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int64_t* target, long long n_px, const float* weight, int C,
                               int ignore_index, const float* wsum, float* loss_sum, void* dlogits, int dtype, erf_stream_t stream) {
+  return ce_launch(logits, ld, nchw_hw, target, n_px, weight, C, ignore_index, wsum, loss_sum, dlogits, nullptr, dtype, stream);
+}
+
+extern "C" int erf_ce_fwd_bwd_colsum_supported(int ld, int nchw_hw, int dtype) { return dtype == ERF_BF16 && nchw_hw == 0 && (ld == 24 || ld == 32); }
+
+extern "C" int erf_ce_fwd_bwd_colsum(const void* logits, int ld, const int64_t* target, long long n_px, const float* weight, int C, int ignore_index,
+                                     const float* wsum, float* loss_sum, void* dlogits, float* colsum, erf_stream_t stream) {
+  ERF_CHECK_ARG(colsum && dlogits, "erf_ce_fwd_bwd_colsum: null pointer");
+  ERF_CHECK_ARG(erf_ce_fwd_bwd_colsum_supported(ld, 0, ERF_BF16) && ((uintptr_t)logits % 16) == 0 && ((uintptr_t)dlogits % 16) == 0,
+                "erf_ce_fwd_bwd_colsum: needs 16-byte aligned NHWC bf16 logits with a pitch of 24 or 32");
+  return ce_launch(logits, ld, 0, target, n_px, weight, C, ignore_index, wsum, loss_sum, dlogits, colsum, ERF_BF16, stream);
+}
+
+static int ce_launch(const void* logits, int ld, int nchw_hw, const int64_t* target, long long n_px, const float* weight, int C, int ignore_index,
+                     const float* wsum, float* loss_sum, void* dlogits, float* colsum, int dtype, erf_stream_t stream) {
   ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_ce_fwd_bwd: bad dtype %d", dtype);
   ERF_CHECK_ARG(logits && target && wsum && loss_sum && n_px > 0, "erf_ce_fwd_bwd: null pointer");
   ERF_CHECK_ARG(C > 0 && C <= CE_MAXC, "erf_ce_fwd_bwd: C=%d not in [1,%d]", C, CE_MAXC);
@@ -219,9 +254,9 @@ extern "C" int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int
   if (dtype == ERF_BF16 && nchw_hw == 0 && (ld == 24 || ld == 32) &&
       ((uintptr_t)logits % 16) == 0 && (!dlogits || ((uintptr_t)dlogits % 16) == 0)) {
     if (ld == 24)
-      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<3>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<3>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits, colsum);
     else
-      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<4>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits);
+      launch_pdl(ce_fwd_bwd_nhwc_bf16_kernel<4>, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)((cudaStream_t)stream), (const __nv_bfloat16*)logits, target, n_px, weight, C, ignore_index, wsum, loss_sum, (__nv_bfloat16*)dlogits, colsum);
     ERF_CHECK_LAUNCH("erf_ce_fwd_bwd");
     return ERF_OK;
   }

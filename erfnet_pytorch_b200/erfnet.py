@@ -301,16 +301,19 @@ class _TcConv:
         plan = self.plans()[1]
         return ops.conv_im2col_tc(dy, ops.im2col_pack(w, self.spec, True, plan), plan, self.dspec, out_hw=out_hw)
 
-    def wgrad(self, x, dy, wparam, bparam, bias_is_zero):
+    def wgrad(self, x, dy, wparam, bparam, bias_is_zero, bias_done=False):
         """(dw, db) for autograd, accumulated in place when a gradient sink is active.  bias_is_zero: the conv feeds a
         train-mode BatchNorm, so its bias gradient is exactly zero (see non_bottleneck_1d._bwd)."""
-        return _side(lambda: self._wgrad_now(x, dy, wparam, bparam, bias_is_zero), (x, dy), wparam, bparam)
+        return _side(lambda: self._wgrad_now(x, dy, wparam, bparam, bias_is_zero, bias_done), (x, dy), wparam, bparam)
 
-    def _wgrad_now(self, x, dy, wparam, bparam, bias_is_zero):
+    def _wgrad_now(self, x, dy, wparam, bparam, bias_is_zero, bias_done=False):
+        """bias_done: the bias gradient was already accumulated into its sink by the producer of dy (the fused CE kernel)."""
         if ops.wgrad_im2col_supported(self.spec, x.dtype):
             dw = ops.conv_wgrad_im2col_tc(x, dy, self.spec, dw_out=_sink(wparam))
             bdst = _sink(bparam)
-            if bias_is_zero:
+            if bias_done and bdst is not None:
+                db = bdst
+            elif bias_is_zero:
                 db = None if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
             else:
                 db = bdst if bdst is not None else torch.zeros(self.spec.cout, device=x.device, dtype=torch.float32)
@@ -441,7 +444,7 @@ class DownsamplerBlock(_B200Module):
             dyr, dgamma, dbeta = ops.bn_bwd(dy, y_raw, gw.detach(), mean, invstd, mask=y, dgamma_out=_sink(gw), dbeta_out=_sink(gb), beta_for_mask=gb.detach())
         else:
             dyr, dgamma, dbeta = ops.relu_bwd(dy, y), None, None
-        if self.ninput == 3 and self.noutput == 16 and ops.stem_supported(x):
+        if self.ninput == 3 and self.noutput == 16 and ops.stem_supported(x) and not (ops.STEM_WGRAD_TC and ops.wgrad_im2col_supported(self.spec, x.dtype)):
             dw, db = _side(lambda: ops.stem_wgrad(x, dyr, dw_out=_sink(cw), db_out=_sink(cb), want_bias=not self.use_batchnorm), (x, dyr), cw, cb)
             if db is None and _sink(cb) is None:   # conv bias feeding a train-mode BN: gradient exactly zero
                 db = torch.zeros(self.noutput - self.ninput, device=x.device, dtype=torch.float32)
@@ -864,7 +867,7 @@ class _PlainConv:
         if self.relu:
             dy = ops.relu_bwd(dy, y)
         cw, cb = self._train_params()
-        dw, db = self._tc.wgrad(x, dy, cw, cb, bias_is_zero=False)
+        dw, db = self._tc.wgrad(x, dy, cw, cb, bias_is_zero=False, bias_done=self._conv.__dict__.pop("_erf_bias_grad_done", False))
         dx = None
         if need_dx:
             if self._tc.bwd_ok(x.dtype):

@@ -563,6 +563,24 @@ def conv_wgrad_im2col_tc(x: torch.Tensor, dy: torch.Tensor, spec: ConvSpec, dy_c
     ws = _WS.get((x.device, nbytes))
     if ws is None:
         ws = _WS[(x.device, nbytes)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    if (FOLD_HEAD_WGRAD and spec.transposed and spec.kh == 2 and spec.kw == 2 and spec.stride == 2 and spec.pad_h == 0 and spec.pad_w == 0 and dy_coff == 0
+            and wo % 2 == 0 and (2 * dyld) % 16 == 0 and 2 * dyld <= 128 and spec.cin % 16 == 0 and spec.cin <= 128 and ho == 2 * h and wo == 2 * w):
+        # Non-overlapping ConvTranspose2d(k = 2, s = 2) (the decoder head, eval/erfnet.py:124): dW[ci,co,a,b] = sum x[i,j,ci] * dy[2i+a, 2j+b, co].
+        # dy [N,Ho,Wo,ld] read as [N,Ho,Wo/2,2*ld] makes the column pair (2j, 2j+1) ONE pixel with channels (b, co): two taps (a = 0, 1; row step 2,
+        # column step 1) of 2*ld contiguous channels instead of four taps of ld -- whole 96-byte rows per gathered pixel (the kernel's fast path).
+        d = _lib.WgradIm2colDesc()
+        k2 = 2 * dyld
+        d.g, d.GH, d.GW, d.g_ld, d.Cg, d.CgP, d.g_copy_bytes, d.g_step, d.g_step_x = dy.data_ptr(), ho, wo // 2, k2, k2, round_up(k2, 16), k2 * 2, 2, 1
+        d.d, d.EN, d.EH, d.EW, d.d_ld, d.d_c0, d.d_c_base, d.Cd = x.data_ptr(), n, h, w, xld, 0, 0, spec.cin
+        d.NP = round_up(spec.cin, 16)
+        d.ntaps = 2
+        d.tap_dy[0], d.tap_dx[0], d.tap_off[0] = 0, 0, 0
+        d.tap_dy[1], d.tap_dx[1], d.tap_off[1] = 1, 0, 2
+        d.KHW, d.fold, d.fold_c = 4, dyld, spec.cout
+        with _timed(f"conv_wgrad_im2col_tc[{spec.cin}->{spec.cout} 2x2 s2T folded]" if DETAIL else "conv_wgrad_im2col_tc_kernel", conv_flops(spec, n, ho, wo)):
+            check(L.erf_conv_wgrad_im2col_tc(C.byref(d), _p(dw_out), _p(ws), nbytes, _stream(x)))
+        _count(2)
+        return dw_out
     if spec.transposed:   # gathered = dy (channels co), dense = x (channels ci)
         g, gh, gw, gld, cg, goff = dy, ho, wo, dyld, spec.cout, dy_coff
         dn, eh, ew, dld, cd, dbase = x, h, w, xld, spec.cin, 0
@@ -610,6 +628,9 @@ def conv_wgrad_im2col_tc(x: torch.Tensor, dy: torch.Tensor, spec: ConvSpec, dy_c
     return dw_out
 
 
+WGRAD_FUSED_REDUCE = False  # True: the 3-tap weight gradients reduce their per-CTA partial sums behind a grid barrier inside the kernel (one launch
+                            # instead of two; measured SLOWER at the bench workload: 19.2 -> 22.4 us at C=64 -- the barrier costs the tail overlap PDL gives two kernels)
+FOLD_HEAD_WGRAD = True   # the 2x2 stride-2 transposed head's weight gradient through the column-folded view of dy (tests flip it)
 _WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partial sums
 
 
@@ -629,8 +650,15 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
     if dw_out is None:
         dw_out = torch.zeros((c, c, 1, 3) if horizontal else (c, c, 3, 1), device=x.device, dtype=torch.float32)
     with _timed(f"conv1d_wgrad_tc[C={c} {'H' if horizontal else 'V'}]" if DETAIL else "conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3):
-        check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
-    _count(2)
+        if WGRAD_FUSED_REDUCE:
+            ctr = ARENA.take(1) if (ARENA is not None and ARENA.buf.device == x.device) else None      # zeroed grid-barrier word
+            if ctr is None:
+                ctr = torch.zeros(2, device=x.device, dtype=torch.int32)
+            check(L.erf_conv1d_wgrad_tc_fused(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, _p(ctr), n, h, w, c, int(horizontal), dil, _stream(x)))
+            _count()
+        else:
+            check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
+            _count(2)
     if want_bias:
         if db_out is None:
             db_out = torch.zeros(c, device=x.device, dtype=torch.float32)
@@ -652,6 +680,7 @@ def stem_fwd(x, w, bias, scale=None, shift=None, relu=False, stats=None):
     return y
 
 
+STEM_WGRAD_TC = os.environ.get("ERF_STEM_WGRAD_TC", "0") != "0"   # stem weight gradient on the generic tcgen05 gather kernel instead of the CUDA-core kernel
 STEM_NCHW = True   # inference: the stem reads the caller's NCHW fp32 image directly (no layout pass)
 
 
@@ -980,11 +1009,26 @@ def ce_weight_sum(target: torch.Tensor, weight: Optional[torch.Tensor], c: int, 
     _count()
 
 
+def ce_colsum_supported(logits: torch.Tensor) -> bool:
+    """ce_fwd_bwd(..., colsum=) is available: NHWC bf16 logits with a pitch of 24 or 32 on the real kernels."""
+    return (not EMULATED and logits.is_cuda and logits.dtype == torch.bfloat16
+            and bool(_lib.lib().erf_ce_fwd_bwd_colsum_supported(logits.shape[-1], 0, ERF_BF16)))
+
+
 def ce_fwd_bwd(logits: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor], c: int, ignore_index: int,
-               wsum: torch.Tensor, lsum: torch.Tensor, nchw: bool = False, want_grad: bool = True):
-    """lsum[0] += sum_valid w[y]*nll; returns dlogits = w[y]*(softmax-onehot)/wsum (same layout/dtype as logits) or None."""
+               wsum: torch.Tensor, lsum: torch.Tensor, nchw: bool = False, want_grad: bool = True, colsum: Optional[torch.Tensor] = None):
+    """lsum[0] += sum_valid w[y]*nll; returns dlogits = w[y]*(softmax-onehot)/wsum (same layout/dtype as logits) or None.
+    colsum (fp32 [>= c], only where ce_colsum_supported): += per-class sums of the stored dlogits (the head conv's bias gradient)."""
     check_ce_shapes(logits, target, weight, c, nchw)
-    _same_device("CrossEntropyLoss2d", logits, wsum=wsum, lsum=lsum)
+    _same_device("CrossEntropyLoss2d", logits, wsum=wsum, lsum=lsum, colsum=colsum)
+    if colsum is not None:
+        if nchw or not want_grad or not ce_colsum_supported(logits):
+            raise RuntimeError("ce_fwd_bwd: colsum needs NHWC bf16 logits with a pitch of 24 or 32 and want_grad")
+        dlog = torch.empty_like(logits)
+        check(_lib.lib().erf_ce_fwd_bwd_colsum(_p(logits), logits.shape[-1], _p(target), target.numel(), _p(weight), c, ignore_index, _p(wsum), _p(lsum),
+                                               _p(dlog), _p(colsum), _stream(logits)))
+        _count()
+        return dlog
     dlog = torch.empty_like(logits) if want_grad else None
     if nchw:
         hw, ld = logits.shape[2] * logits.shape[3], 0

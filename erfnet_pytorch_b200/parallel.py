@@ -338,12 +338,24 @@ class FlatAdamTrainer:
         ops.ce_weight_sum(labels, w, c, self.criterion.ignore_index, wsum)
         if self.world > 1:
             dist.all_reduce(wsum, op=dist.ReduceOp.SUM, group=self.pg)
-        dlog = ops.ce_fwd_bwd(logits.detach(), labels, w, c, self.criterion.ignore_index, wsum, lsum)
+        dlog = self._ce(logits, labels, wsum, lsum)
         self._backward(logits, dlog)
         self._finish_buckets()
         if self.world > 1:
             dist.all_reduce(lsum, op=dist.ReduceOp.SUM, group=self.pg)
         return (lsum / wsum).reshape(())
+
+    def _ce(self, logits, labels, wsum, lsum):
+        """Fused CE forward + dlogits.  The per-class sums of dlogits ARE the bias gradient of decoder.output_conv (the logits are its raw
+        output): where the kernel supports it they are accumulated into that gradient here and the head's backward skips its own pass over
+        the 151 MB of dlogits."""
+        head = getattr(getattr(self.model, "decoder", None), "output_conv", None)
+        colsum = None
+        if (head is not None and getattr(head, "bias", None) is not None and head.bias.grad is not None and head.bias.numel() == self.num_classes
+                and ops.ce_colsum_supported(logits)):
+            colsum = head.bias.grad
+            head.__dict__["_erf_bias_grad_done"] = True      # consumed by _PlainConv._bwd of this step
+        return ops.ce_fwd_bwd(logits.detach(), labels, self.criterion.weight, self.num_classes, self.criterion.ignore_index, wsum, lsum, colsum=colsum)
 
     def _backward(self, logits, dlog):
         _erfnet._GRAD_SINK = self
@@ -495,7 +507,7 @@ class FlatAdamTrainer:
                         logits = self.model.forward_nhwc(self._g_images)
                     finally:
                         _erfnet._PREPACKED_FRESH = False
-                    dlog = ops.ce_fwd_bwd(logits.detach(), self._g_labels, w, c, self.criterion.ignore_index, self._g_acc[0:1], self._g_acc[1:2])
+                    dlog = self._ce(logits, self._g_labels, self._g_acc[0:1], self._g_acc[1:2])
                     self._backward(logits, dlog)
                 finally:
                     self._end_step()

@@ -175,6 +175,13 @@ int erf_ce_fwd_bwd(const void* logits, int ld, int nchw_hw, const int64_t* targe
                    const float* weight, int C, int ignore_index, const float* wsum, float* loss_sum,
                    void* dlogits, int dtype, erf_stream_t stream);
 
+/* Same for NHWC bf16 logits of pitch 24 or 32, which also accumulates colsum[c] += sum over pixels of the STORED (bf16) dlogits[p,c]: the bias
+ * gradient of the convolution that produced the logits (decoder.output_conv, eval/erfnet.py:124), without a separate pass over the 151 MB of
+ * dlogits. */
+int erf_ce_fwd_bwd_colsum_supported(int ld, int nchw_hw, int dtype);
+int erf_ce_fwd_bwd_colsum(const void* logits, int ld, const int64_t* target, long long n_px, const float* weight, int C,
+                          int ignore_index, const float* wsum, float* loss_sum, void* dlogits, float* colsum, erf_stream_t stream);
+
 /* ---- iouEval (eval/iouEval.py:21-69) and argmax (eval/eval_iou.py:92) ----------------------------------- */
 /* cm[g*nc + p] += #pixels with label g predicted p (u64, bit exact); labels outside [0,nc) are skipped. */
 int erf_confusion_hist(const void* pred, const void* gt, int elem_bytes, long long n, int nc,
@@ -272,6 +279,11 @@ int erf_pack_conv1d_tc_batched(const erf_pack1d_entry* table_dev, int n_entries,
 size_t erf_conv1d_wgrad_tc_workspace(int C);
 int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W,
                         int C, int horizontal, int dil, erf_stream_t stream);
+/* Same with the reduction of the per-CTA partial sums INSIDE the kernel (no second launch): after a grid barrier every CTA sums its slice of
+ * the slab over all CTAs' partials and adds it to dw.  counter = one zeroed 32-bit word per call (grid barrier); falls back to the two
+ * launches when the grid would not be co-resident. */
+int erf_conv1d_wgrad_tc_fused(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, unsigned* counter, int N,
+                              int H, int W, int C, int horizontal, int dil, erf_stream_t stream);
 /* out[c] += sum_p x[p*ld + coff + c]   (bias gradients) */
 int erf_channel_sum(const void* x, int ld, int coff, int C, long long n_px, float* out, int dtype, erf_stream_t stream);
 
@@ -316,6 +328,9 @@ typedef struct {
   const void* d; int EN, EH, EW, d_ld, d_c0, d_c_base, Cd, NP;        /* dense operand (N side), its pixel grid is the loop */
   int ntaps; int tap_dy[9]; int tap_dx[9]; int tap_off[9]; int KHW;
   int tail_bytes;                                                     /* filled in by the library */
+  int g_step_x;                                                       /* column step of the gather (0: = g_step) */
+  int fold, fold_c;   /* fold > 0: G is a column-folded view [..][GW][fold * 2]: gathered channel cg = b * fold + c holds channel c of the column
+                       * parity b; only c < fold_c exists in the parameter, which is indexed ((cd)*fold_c + c)*KHW + tap_off[t] + b */
 } erf_wgrad_im2col_desc;
 size_t erf_conv_wgrad_im2col_tc_workspace(void);
 int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* dw, void* workspace, size_t ws_bytes, erf_stream_t stream);

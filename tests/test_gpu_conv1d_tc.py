@@ -153,6 +153,29 @@ def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
     assert_rel(db.cpu().numpy(), dy.float().sum((0, 1, 2)).numpy(), 2e-3, "db")
 
 
+@pytest.mark.parametrize("c,n,h,w", [(128, 6, 64, 128), (64, 6, 128, 256), (16, 6, 256, 512), (64, 1, 3, 64), (128, 2, 5, 192)])
+def test_conv1d_wgrad_fused_reduction_matches_two_launches(c, n, h, w):
+    """The in-kernel reduction (grid barrier, every CTA sums its slice of the partial-sum slabs) against the separate reduce kernel: the same
+    partial sums added in a different order, ACCUMULATED into existing gradient contents; bench shapes and grids smaller than the SM count."""
+    gen = torch.Generator().manual_seed(c + n + h)
+    x = torch.randn(n, h, w, c, generator=gen).bfloat16().cuda()
+    dy = torch.randn(n, h, w, c, generator=gen).bfloat16().cuda()
+    got = []
+    for fused in (True, False):
+        ops.WGRAD_FUSED_REDUCE = fused
+        try:
+            dw = torch.full((c, c, 3, 1), 0.125, device="cuda")
+            before = ops.LAUNCHES
+            for _ in range(2):                                   # two accumulating calls
+                ops.conv1d_wgrad_tc(x, dy, False, 2, dw_out=dw, want_bias=False)
+            assert ops.LAUNCHES - before == (2 if fused else 4)
+            got.append(dw.cpu().numpy() - 0.125)
+        finally:
+            ops.WGRAD_FUSED_REDUCE = True
+    assert_rel(got[0], got[1], 2e-5, "fused vs two-launch dW")
+    assert np.abs(got[0]).max() > 1.0
+
+
 def test_pack_kernel_matches_host_packing():
     for c, shape in ((64, (64, 64, 3, 1)), (128, (128, 128, 1, 3)), (16, (16, 16, 3, 1))):
         w = torch.randn(*shape, generator=torch.Generator().manual_seed(c)).cuda()

@@ -70,6 +70,8 @@ def test_forward_and_data_gradient(name, spec, nhw):
 
 
 WG_CASES = CASES[:5] + [("stem3_13", ConvSpec(3, 13, 3, 3, 2, 1, 1), (2, 20, 44))]
+# row-aligned dense grids (width % 64 == 0): the TMA-loaded form of the kernel (strided tensor maps); the sizes above keep the cp.async gather covered
+WG_CASES += [(c[0] + "_tma", c[1], (2, 6, 64 if c[1].transposed else 128)) for c in CASES[:5]] + [("up128_64_tma_wide", CASES[2][1], (1, 3, 192))]
 
 
 @pytest.mark.parametrize("name,spec,nhw", WG_CASES, ids=[c[0] for c in WG_CASES])
@@ -150,3 +152,31 @@ def test_fused_nchw_head_matches_the_two_pass_form(shape):
     with torch.no_grad():
         ref = m(x)
     assert (fused - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dyld,w", [(24, 72), (32, 72), (24, 128)])
+def test_head_weight_gradient_column_folded(dyld, w):
+    """ConvTranspose2d(16, 20, 2, stride 2) weight gradient through the column-folded view of dy (two taps of 2 * ld channels) vs torch
+    autograd and vs the four-tap form it replaces."""
+    gen = torch.Generator().manual_seed(77)
+    spec = ConvSpec(16, 20, 2, 2, 2, 0, 0, transposed=True)
+    n, h = 3, 24
+    x = torch.randn(n, h, w, 16, generator=gen).bfloat16()
+    wt = torch.zeros(16, 20, 2, 2, requires_grad=True)
+    y = _torch_fwd(x.float().permute(0, 3, 1, 2), wt, None, spec)
+    dy = torch.zeros(n, 2 * h, 2 * w, dyld).bfloat16()
+    dy[..., :20] = torch.randn(n, 2 * h, 2 * w, 20, generator=gen).bfloat16()
+    if dyld > 24:
+        dy[..., 24:] = 3.0    # channels beyond the padded logits belong to somebody else: must not leak into the gradient
+    (ref,) = torch.autograd.grad(y, wt, dy[..., :20].float().permute(0, 3, 1, 2))
+    got = []
+    for fold in (True, False):
+        ops.FOLD_HEAD_WGRAD = fold
+        try:
+            dw = torch.full((16, 20, 2, 2), -0.25, device="cuda")
+            ops.conv_wgrad_im2col_tc(x.cuda(), dy.cuda(), spec, dw_out=dw)
+            got.append((dw.cpu() + 0.25).numpy())
+        finally:
+            ops.FOLD_HEAD_WGRAD = True
+    assert_rel(got[0], ref.numpy(), 3e-3, "folded head dW")
+    assert_rel(got[0], got[1], 1e-3, "folded vs four-tap head dW")

@@ -103,31 +103,35 @@ def test_capture_after_an_earlier_autograd_forward():
 
 def test_learning_rate_change_reaches_the_captured_optimiser_and_checkpoint_resumes():
     """The reference steps a LambdaLR every epoch (train/main.py:238-239): after capture the Adam launch reads lr / weight decay from device
-    memory, so trainer.set_lr() changes the next REPLAY exactly as it changes the next eager step; the optimiser checkpoint
-    (torch.optim.Adam layout) restores moments and the device-side step counter."""
+    memory, so trainer.set_lr() changes the next REPLAY; the optimiser checkpoint (torch.optim.Adam layout) restores the moments and the
+    device-side step counter.  (Trajectories of two runs cannot be compared after a large lr: 39 train-mode BNs at this size amplify the
+    atomics' rounding noise chaotically -- so the check uses lr = 0, which must freeze the weights EXACTLY.)"""
     x = [golden_input((2, 3, 64, 256), 10 + i).cuda() for i in range(4)]
     y = [golden_labels((2, 64, 256), 10 + i).cuda() for i in range(4)]
-    a, b, keep = _trainer("fp32"), _trainer("fp32"), _trainer("fp32")
+    b = _trainer("fp32")
     b.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
-    keep.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
-    for i in range(4):
-        if i == 2:
-            a.set_lr(3e-3)
-            b.set_lr(3e-3)
-        a.train_step(x[i], y[i])
-        b.train_step(x[i], y[i])
-        keep.train_step(x[i], y[i])          # never changes its learning rate
-    torch.cuda.synchronize()
-    # lr 1e-4 -> 3e-3 moves the weights 30x further per step.  Adam's sign-like steps amplify rounding noise on ~zero gradients, so the
-    # comparison uses the MEAN distance: the replayed run must sit on the eager run with the new lr, far from the run that kept the old one
-    same = float((a.flat_p - b.flat_p).abs().mean())
-    apart = float((keep.flat_p - b.flat_p).abs().mean())
-    assert apart > 1e-3 and same < 0.1 * apart, (same, apart)
+    p0 = b.flat_p.clone()
+    b.train_step(x[0], y[0])
+    b.train_step(x[1], y[1])
+    p2 = b.flat_p.clone()
+    moved = float((p2 - p0).abs().mean())
+    assert moved > 2e-5                                   # two steps at lr 1e-4
+    b.set_lr(0.0)                                         # a captured by-value lr would keep moving the weights
+    b.train_step(x[2], y[2])
+    assert torch.equal(b.flat_p, p2)
+    b.lr = 1e-3                                           # the attribute form, 10x the original rate
+    b.train_step(x[3], y[3])
+    step = float((b.flat_p - p2).abs().mean())
+    assert 3.0 * moved < step < 30.0 * moved, (step, moved)
+    assert b.step_count == 4 and int(b._step_dev) == 4
+    # checkpoint: a fresh captured trainer resumes from (model state_dict, optimiser state_dict)
     c = _trainer("fp32")
     c.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
     c.model.load_state_dict(b.model.state_dict())
     c.load_state_dict(b.state_dict())
-    assert c.step_count == 4 and int(c._step_dev) == 4 and c.lr == 3e-3 and abs(float(c._hyper_dev[0]) - 3e-3) < 1e-9
+    assert c.step_count == 4 and int(c._step_dev) == 4 and c.lr == 1e-3 and abs(float(c._hyper_dev[0]) - 1e-3) < 1e-9
+    assert torch.equal(c.flat_m, b.flat_m) and torch.equal(c.flat_v, b.flat_v) and torch.equal(c.flat_p, b.flat_p)
+    before = b.flat_p.clone()
     lb, lc = float(b.train_step(x[0], y[0])), float(c.train_step(x[0], y[0]))
     np.testing.assert_allclose(lc, lb, rtol=1e-3)
-    assert float((b.flat_p - c.flat_p).abs().mean()) < 0.1 * apart
+    assert float((b.flat_p - c.flat_p).abs().mean()) < 0.2 * float((b.flat_p - before).abs().mean())
