@@ -37,6 +37,10 @@ class WgradIm2colDesc(C.Structure):
                  ("g_step_x", C.c_int), ("fold", C.c_int), ("fold_c", C.c_int)])
 
 
+class WgradJob(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("horizontal", C.c_int), ("dil", C.c_int)]
+
+
 class Im2colTaps(C.Structure):
     _fields_ = [("ntaps", C.c_int), ("off", C.c_longlong * 9), ("n_split", C.c_int), ("off2", C.c_longlong * 9)]
 
@@ -86,6 +90,8 @@ _SIGNATURES = {
     "erf_pack_conv1d_tc_batched": [_vp, _i, _i, _vp],
     "erf_conv1d_wgrad_tc_workspace": [_i],
     "erf_conv1d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
+    "erf_conv1d_wgrad_group_tc_workspace": [_i],
+    "erf_conv1d_wgrad_group_tc": [C.POINTER(WgradJob), _i, _vp, C.c_size_t, _i, _i, _i, _i, _vp],
     "erf_conv1d_wgrad_tc_fused": [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "erf_channel_sum": [_vp, _i, _i, _i, _ll, _vp, _i, _vp],
     "erf_conv_im2col_tc": [C.POINTER(Im2colDesc), _vp],

@@ -16,6 +16,7 @@
 //     epilogue (bias, ReLU, bf16, per-pixel 16-byte stores into the NHWC output slice).
 // These layers are 6 % of the network's FLOPs; the point of this kernel is to get them off the CUDA cores, not peak MMA rate.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -37,9 +38,13 @@ __device__ __forceinline__ void bulk_g2s_im(void* smem_dst, const void* gsrc, ui
                : "memory");
 }
 
-template <int NP, bool NCHW = false>
-__global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf_im2col_desc p, const int slots, const int slot_bytes,
-                                                                       const int w_bytes) {
+// TMA = true: a tap tile (128 enumerated pixels of ONE input row, every in_step_x-th pixel) is a strided box of a tiled tensor map -- one
+// cp.async.bulk.tensor per (tap, k-chunk) issued by an elected lane of warp 0, zero fill outside the image = padding, hardware swizzle =
+// the K-major operand layout -- instead of 128 threads computing addresses for 16-byte cp.async pieces.  Needs EW % 128 == 0 (a unit never
+// straddles rows) and 16-byte aligned pixel rows; other shapes keep the software gather below.
+template <int NP, bool NCHW = false, bool TMA = false>
+__global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const erf_im2col_desc p, const int slots,
+                                                                       const int slot_bytes, const int w_bytes) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
   const int in_step_x = p.in_step_x > 0 ? p.in_step_x : p.in_step, out_step_x = p.out_step_x > 0 ? p.out_step_x : p.out_step;
   if (tid == 0) {
     for (int s = 0; s < slots; ++s) {
-      mbar_init(&full_bar[s], 128);   // one arrival per loader thread
+      mbar_init(&full_bar[s], TMA ? 1 : 128);   // one arrival per loader thread, or the TMA producer's expect_tx
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
     }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
+    if (TMA) tma_prefetch_desc(&tmap_in);
   }
   __syncthreads();
   if (warp == 4) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -79,7 +85,38 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const erf
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
 
-  if (warp < 4) {
+  if (TMA && warp < 4) {
+    // ================= TMA producer (warp 0; uniform control flow, one elected lane issues) =================
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w_bar, w_bytes);
+        for (int off = 0; off < w_bytes; off += 32768) {
+          const int nb = w_bytes - off < 32768 ? w_bytes - off : 32768;
+          bulk_g2s_im(s_w + off, reinterpret_cast<const uint8_t*>(p.w_img) + off, nb, &w_bar);
+        }
+      }
+      __syncwarp();
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(KC * 128 * RB);
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const unsigned q0 = (unsigned)u * 128u;
+        const unsigned t2 = q0 / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
+        const int x0 = in_step_x * (int)(q0 - t2 * (unsigned)p.EW), y0 = p.in_step * (int)(t2 - nn * (unsigned)p.EH);
+        for (int t = 0; t < p.ntaps; ++t) {
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* base = s_a + (size_t)slot * slot_bytes;
+            mbar_arrive_expect_tx(&full_bar[slot], tx);
+            for (int kc = 0; kc < KC; ++kc)
+              tma_load_4d(base + kc * (128 * RB), &tmap_in, &full_bar[slot], kc * CH, x0 + p.tap_dx[t], y0 + p.tap_dy[t], (int)nn);
+          }
+          __syncwarp();
+          if (++slot == slots) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4) {
     // ================= loaders: 128 threads gather one tap tile per ring slot =================
     if (tid == 0) {
       mbar_arrive_expect_tx(&w_bar, w_bytes);
@@ -326,6 +363,26 @@ __global__ void pack_im2col_weights_kernel(const float* __restrict__ w, long lon
   v.store(img + (size_t)i * 8);
 }
 
+typedef CUresult (*ImEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC bf16 input [N][H][W][ld] as (C, W, H, N); box = {ch, box_w, 1, 1} traversed with column step step_w: box_w / step_w pixels of one row
+static int im_make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int ld, int ch, int box_w, int step_w) {
+  static ImEncodeFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (ImEncodeFn)q;
+  }
+  if (!fn || box_w > 256 || (ld % 8) != 0) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)step_w, 1, 1};
+  return (int)fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 }  // namespace erfk
 
 using namespace erfk;
@@ -369,10 +426,18 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   int grid = p.units < 148 * per_sm ? p.units : 148 * per_sm;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-#define IM_LAUNCH(NP_, NCHW_)                                                                                                  \
-  e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_, NCHW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-  if (e == cudaSuccess && per_sm > 1) e = prefer_max_smem(conv_im2col_tc_kernel<NP_, NCHW_>);                                   \
-  if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_, NCHW_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), p, slots, slot_bytes, w_bytes);
+  // TMA-loaded tap tiles: units of 128 pixels inside one row, 16-byte aligned rows
+  static const bool tma_off = getenv("ERF_IM2COL_TMA") && atoi(getenv("ERF_IM2COL_TMA")) == 0;
+  const int isx = d->in_step_x > 0 ? d->in_step_x : d->in_step;
+  CUtensorMap tm;
+  bool tma = !tma_off && (d->EW % 128) == 0 && (total % 128) == 0 && ((uintptr_t)d->in % 16) == 0 && isx >= 1 && isx <= 2 && d->in_step >= 1;
+  if (tma) tma = im_make_map(&tm, d->in, d->EN, d->H, d->W, d->in_ld, CH, 128 * isx, isx) == 0;
+  if (!tma) memset(&tm, 0, sizeof(tm));
+#define IM_LAUNCH2(NP_, NCHW_, TMA_)                                                                                                 \
+  e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_, NCHW_, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e == cudaSuccess && per_sm > 1) e = prefer_max_smem(conv_im2col_tc_kernel<NP_, NCHW_, TMA_>);                                   \
+  if (e == cudaSuccess) launch_pdl(conv_im2col_tc_kernel<NP_, NCHW_, TMA_>, dim3(grid), dim3(kImThreads), smem, (cudaStream_t)(st), tm, p, slots, slot_bytes, w_bytes);
+#define IM_LAUNCH(NP_, NCHW_) if (tma) { IM_LAUNCH2(NP_, NCHW_, true) } else { IM_LAUNCH2(NP_, NCHW_, false) }
   if (d->nchw_out != nullptr) {
     if (d->NP == 32) { IM_LAUNCH(32, true) } else { IM_LAUNCH(64, true) }
   }
@@ -381,6 +446,7 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   else if (d->NP == 64) { IM_LAUNCH(64, false) }
   else { IM_LAUNCH(128, false) }
 #undef IM_LAUNCH
+#undef IM_LAUNCH2
   if (e != cudaSuccess) {
     set_error("erf_conv_im2col_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return ERF_ERR_CUDA;

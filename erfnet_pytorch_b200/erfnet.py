@@ -690,18 +690,21 @@ class non_bottleneck_1d(_B200Module):
         db1, db3 = bias_dst(P[1]), bias_dst(P[7])
         dy4, dg2, dbe2, gres = ops.bn_bwd(dout, y4, P[10].detach(), mean2, invstd2, mask=out, drop=drop, dgamma_out=_sink(P[10]),
                                           dbeta_out=_sink(P[11]), want_masked=True)  # gres = dout * (out > 0): the residual path's gradient
-        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
+        grp = self._wgrad_group(x, tc, P)
+        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8], grp)
         dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3, static_w=sw)     # grad wrt conv3x1_2's output
-        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
+        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6], grp)
         da2 = self._conv(2, dt3, wd[2], None, tc, spec=ds[2], static_w=sw)
         dy2, dg1, dbe1 = ops.bn_bwd(da2, y2, P[4].detach(), mean1, invstd1, mask=a2, dgamma_out=_sink(P[4]), dbeta_out=_sink(P[5]),
                                      beta_for_mask=P[5].detach())
-        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
+        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2], grp)
         dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1, static_w=sw)     # grad wrt conv3x1_1's output
-        dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
+        dw1, _ = self._wgrad(0, x, dt1, tc, P[0], grp)
         dx = None
         if need_dx:
             dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0], static_w=sw)
+        if grp:
+            ops.conv1d_wgrad_tc_group(grp)
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2)))
         _sunk(*P)
         return dx, grads
@@ -714,21 +717,35 @@ class non_bottleneck_1d(_B200Module):
         gres = ops.relu_bwd(dout, out)                                                  # grad wrt (branch + x)
         dy4 = gres if drop is None else ops.affine_act(gres, drop, torch.zeros_like(drop), relu=False)
         ops.channel_sum(dy4, db4)
-        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8])
+        grp = self._wgrad_group(x, tc, P)
+        dw4, _ = self._wgrad(3, t3, dy4, tc, P[8], grp)
         dt3 = self._conv(3, dy4, wd[3], None, tc, mask=t3, spec=ds[3], colsum=db3, static_w=sw)
-        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6])
+        dw3, _ = self._wgrad(2, a2, dt3, tc, P[6], grp)
         dy2 = self._conv(2, dt3, wd[2], None, tc, mask=a2, spec=ds[2], colsum=db2, static_w=sw)
-        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2])
+        dw2, _ = self._wgrad(1, t1, dy2, tc, P[2], grp)
         dt1 = self._conv(1, dy2, wd[1], None, tc, mask=t1, spec=ds[1], colsum=db1, static_w=sw)
-        dw1, _ = self._wgrad(0, x, dt1, tc, P[0])
+        dw1, _ = self._wgrad(0, x, dt1, tc, P[0], grp)
         dx = self._conv(0, dt1, wd[0], None, tc, add=gres, spec=ds[0], static_w=sw) if need_dx else None
+        if grp:
+            ops.conv1d_wgrad_tc_group(grp)
         grads = tuple(_ret(p, g) for p, g in zip(P, (dw1, db1, dw2, db2, None, None, dw3, db3, dw4, db4, None, None)))
         _sunk(*P)  # the unused BN parameters count as done (their gradient stays zero)
         return dx, grads
 
-    def _wgrad(self, i, x, dy, tc, wparam):
-        """Weight gradient only (the bias gradients come from the data-gradient epilogues, see _bwd)."""
+    def _wgrad(self, i, x, dy, tc, wparam, group=None):
+        """Weight gradient only (the bias gradients come from the data-gradient epilogues, see _bwd).  group: a list that collects the block's
+        weight-gradient jobs for ONE grouped launch at the end of its backward (only the optimiser waits for a weight gradient)."""
+        if group is not None:
+            group.append((x, dy, bool(i & 1), 1 if i < 2 else self.dilated, _sink(wparam)))
+            return _sink(wparam), None
         return _side(lambda: self._wgrad_now(i, x, dy, tc, wparam), (x, dy), wparam)
+
+    def _wgrad_group(self, x, tc, P):
+        """[] when this block's four weight gradients can go out as one grouped launch (tensor-core path, every weight has a gradient sink), else
+        None (one launch per conv, results returned to autograd)."""
+        ok = (tc and ops.WGRAD_GROUP and not ops.EMULATED and ops.SIDE is None and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype)
+              and all(_sink(P[i]) is not None for i in (0, 2, 6, 8)))
+        return [] if ok else None
 
     def _wgrad_now(self, i, x, dy, tc, wparam):
         if tc and ops.conv1d_wgrad_tc_supported(self.chann, x.shape[2], self.dilated, x.dtype):

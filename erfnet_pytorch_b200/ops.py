@@ -666,6 +666,31 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
     return dw_out, db_out
 
 
+WGRAD_GROUP = os.environ.get("ERF_WGRAD_GROUP", "0") != "0"   # the four 3-tap weight gradients of a block in ONE launch (+ one reduce launch).  Measured: the
+# eager step gains (89 -> 72 us per 128-channel block: six launch gaps less) but the graph-replayed step LOSES (5.33 -> 5.42 ms): programmatic
+# dependent launch already hides those gaps, and deferring the weight gradients to the end of the block costs the L2 residency of x / dy
+
+
+def conv1d_wgrad_tc_group(jobs):
+    """jobs: [(x, dy, horizontal, dil, dw_out)] (1..4) over tensors of ONE shape [N,H,W,C]: dw_out_j += weight gradient of job j, all in one
+    kernel launch plus one reduce launch (csrc/conv1d_wgrad_group_tc.cu)."""
+    x0 = jobs[0][0]
+    n, h, w, c = x0.shape
+    L = _lib.lib()
+    nbytes = L.erf_conv1d_wgrad_group_tc_workspace(c)
+    ws = _WS.get((x0.device, nbytes))
+    if ws is None:
+        ws = _WS[(x0.device, nbytes)] = torch.empty(nbytes, device=x0.device, dtype=torch.uint8)
+    arr = (_lib.WgradJob * len(jobs))()
+    for i, (x, dy, horizontal, dil, dw) in enumerate(jobs):
+        if x.shape != x0.shape or dy.shape != x0.shape or x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16:
+            raise RuntimeError("conv1d_wgrad_tc_group: all jobs must share one bf16 [N,H,W,C] shape")
+        arr[i].x, arr[i].dy, arr[i].dw, arr[i].horizontal, arr[i].dil = x.data_ptr(), dy.data_ptr(), dw.data_ptr(), int(horizontal), int(dil)
+    with _timed(f"conv1d_wgrad_group[C={c} x{len(jobs)}]" if DETAIL else "conv1d_wgrad_tc_kernel", 2.0 * n * h * w * c * c * 3 * len(jobs)):
+        check(L.erf_conv1d_wgrad_group_tc(arr, len(jobs), _p(ws), nbytes, n, h, w, c, _stream(x0)))
+    _count(2)
+
+
 def stem_supported(x: torch.Tensor) -> bool:
     return not EMULATED and x.shape[-1] == 4 and x.shape[1] % 2 == 0 and x.shape[2] % 4 == 0 and x.shape[2] <= 4096
 

@@ -279,6 +279,12 @@ int erf_pack_conv1d_tc_batched(const erf_pack1d_entry* table_dev, int n_entries,
 size_t erf_conv1d_wgrad_tc_workspace(int C);
 int erf_conv1d_wgrad_tc(const void* x, const void* dy, float* dw, void* workspace, size_t ws_bytes, int N, int H, int W,
                         int C, int horizontal, int dil, erf_stream_t stream);
+/* The weight gradients of up to four 3-tap convolutions that share (N, H, W, C) -- the four convs of one non_bottleneck_1d block -- in ONE
+ * launch plus one reduce launch: persistent CTAs walk the jobs in order (csrc/conv1d_wgrad_group_tc.cu).  dw_j += as erf_conv1d_wgrad_tc. */
+typedef struct { const void* x; const void* dy; float* dw; int horizontal, dil; } erf_wgrad_job;
+size_t erf_conv1d_wgrad_group_tc_workspace(int C);
+int erf_conv1d_wgrad_group_tc(const erf_wgrad_job* jobs, int njobs, void* workspace, size_t ws_bytes, int N, int H, int W, int C,
+                              erf_stream_t stream);
 /* Same with the reduction of the per-CTA partial sums INSIDE the kernel (no second launch): after a grid barrier every CTA sums its slice of
  * the slab over all CTAs' partials and adds it to dw.  counter = one zeroed 32-bit word per call (grid barrier); falls back to the two
  * launches when the grid would not be co-resident. */

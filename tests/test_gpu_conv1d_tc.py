@@ -176,6 +176,31 @@ def test_conv1d_wgrad_fused_reduction_matches_two_launches(c, n, h, w):
     assert np.abs(got[0]).max() > 1.0
 
 
+@pytest.mark.parametrize("c,n,h,w,dil", [(128, 6, 64, 128, 8), (64, 6, 128, 256, 1), (16, 6, 256, 512, 1), (64, 1, 3, 64, 2), (128, 2, 5, 192, 16)])
+def test_conv1d_wgrad_group_matches_single_launches(c, n, h, w, dil):
+    """The grouped weight-gradient kernel (four jobs of one block in one launch: 3x1, 1x3, dilated 3x1, dilated 1x3, each with its own x / dy)
+    against four single launches: identical partial sums, ACCUMULATED into existing gradient contents."""
+    gen = torch.Generator().manual_seed(c + n + h + dil)
+    xs = [torch.randn(n, h, w, c, generator=gen).bfloat16().cuda() for _ in range(4)]
+    dys = [torch.randn(n, h, w, c, generator=gen).bfloat16().cuda() for _ in range(4)]
+    geo = [(False, 1), (True, 1), (False, dil), (True, dil)]
+    ref = []
+    for (hz, d), x, dy in zip(geo, xs, dys):
+        dw = torch.full((c, c, 1, 3) if hz else (c, c, 3, 1), 0.25, device="cuda")
+        ops.conv1d_wgrad_tc(x, dy, hz, d, dw_out=dw, want_bias=False)
+        ref.append(dw)
+    got = [torch.full_like(r, 0.25) for r in ref]
+    before = ops.LAUNCHES
+    ops.conv1d_wgrad_tc_group([(x, dy, hz, d, dw) for (hz, d), x, dy, dw in zip(geo, xs, dys, got)])
+    assert ops.LAUNCHES - before == 2
+    for a, b, (hz, d) in zip(got, ref, geo):
+        assert_rel((a - 0.25).cpu().numpy(), (b - 0.25).cpu().numpy(), 2e-5, f"group vs single, horizontal={hz} dil={d}")
+    # a shorter job list (the kernel takes 1..4)
+    one = torch.zeros_like(ref[2])
+    ops.conv1d_wgrad_tc_group([(xs[2], dys[2], False, dil, one)])
+    assert_rel(one.cpu().numpy(), (ref[2] - 0.25).cpu().numpy(), 2e-5, "single-job group")
+
+
 def test_pack_kernel_matches_host_packing():
     for c, shape in ((64, (64, 64, 3, 1)), (128, (128, 128, 1, 3)), (16, (16, 16, 3, 1))):
         w = torch.randn(*shape, generator=torch.Generator().manual_seed(c)).cuda()

@@ -21,6 +21,10 @@ CASES = [
 ]
 
 
+# row-aligned enumeration grids (width % 128 == 0): the TMA-loaded form of the kernel; the small sizes above keep the cp.async gather covered
+CASES += [(c[0] + "_tma", c[1], (2, 4, 128 if c[1].transposed else 256)) for c in CASES[:5]] + [("enc_head_1x1_tma", CASES[5][1], (1, 3, 256))]
+
+
 def _torch_fwd(x_nchw, w, b, spec):
     if spec.transposed:
         return F.conv_transpose2d(x_nchw, w, b, stride=spec.stride, padding=(spec.pad_h, spec.pad_w), output_padding=spec.out_pad)
