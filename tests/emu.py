@@ -193,7 +193,8 @@ def ce_weight_sum(target, weight, c, ignore_index, wsum):
 
 
 @torch.enable_grad()
-def ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw=False, want_grad=True):
+def ce_fwd_bwd(logits, target, weight, c, ignore_index, wsum, lsum, nchw=False, want_grad=True, colsum=None):
+    assert colsum is None    # only the bf16 GPU kernel offers it (ops.ce_colsum_supported is False under emulation)
     lg = logits.detach().float() if nchw else logits.detach()[..., :c].float().permute(0, 3, 1, 2)
     lg = lg.requires_grad_(True)
     valid = (target != ignore_index) & (target >= 0) & (target < c)
