@@ -44,6 +44,12 @@ struct Conv1dTcParams {
   float* colsum;                // [C]  += per-channel sum of the stored output (bias gradient of the producing conv), or null
 };
 
+// Timeline instrumentation (tools/timeline_conv1d.py): when a buffer is registered every CTA records SM-clock stamps of its phases.
+__device__ unsigned long long* g_conv1d_dbg = nullptr;
+__device__ __forceinline__ void dbg_stamp(int k) {
+  if (g_conv1d_dbg) g_conv1d_dbg[(size_t)blockIdx.x * 8 + k] = (unsigned long long)clock64();
+}
+
 constexpr int kMaxSlots = 8;
 constexpr int kThreads = 384;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warps 10-11 per-channel statistics
 
@@ -86,6 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   __shared__ float s_stat[2][2 * C];                // per statistics warp: [C] sums, [C] sums of squares
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) dbg_stamp(0);
   pdl_trigger();   // the set-up below overlaps the previous kernel's tail; nothing before pdl_wait() touches tensors an earlier kernel writes
   for (int i = tid; i < C; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   const bool want_red = RED && (p.stats != nullptr || p.colsum != nullptr);
@@ -124,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_s;
   const int segs = p.W / 128;
   pdl_wait();
+  if (tid == 0) dbg_stamp(1);
 
   if (warp == 0) {
     // ================= TMA producer: whole warp in uniform control flow, one elected lane issues =================
@@ -177,6 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t desc_hi = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);  // SBO = 8 rows, version 1, swizzle mode
       mbar_wait(&w_bar, 0);
+      if (lane == 0) dbg_stamp(2);
+      bool first_unit = true;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         const uint32_t d_tmem = tmem_base + acc * C;
@@ -225,6 +235,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
         }
         if (elect_one()) umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
         __syncwarp();
+        if (first_unit && lane == 0) dbg_stamp(3);
+        first_unit = false;
+        if (lane == 0) dbg_stamp(4);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -415,10 +428,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
       }
     }
     if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
+    if (leader) dbg_stamp(5 + grp);
   }
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) dbg_stamp(7);
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -456,6 +471,10 @@ static int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 }  // namespace erfk
 
 using namespace erfk;
+
+extern "C" int erf_conv1d_tc_set_debug(unsigned long long* buf) {   // tools only: [grid][8] clock stamps per launch (nullptr switches it off)
+  return cudaMemcpyToSymbol(g_conv1d_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
+}
 
 extern "C" int erf_conv1d_tc_supported(int C, int W, int dil) {
   return (C == 16 || C == 64 || C == 128) && W >= 128 && (W % 128) == 0 && dil >= 1 && dil <= 32;
