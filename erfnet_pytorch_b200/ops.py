@@ -277,12 +277,17 @@ class Conv1dPackTable:
         _count()
 
 
+CONV1D_CALL_LOG = None   # bench.py: a list that receives the arguments of every conv1d_tc call (to re-issue the step's launches back to back)
+
+
 def conv1d_tc(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], horizontal: bool, dil: int, relu=False,
               res: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
               colsum: Optional[torch.Tensor] = None, static_w: bool = False) -> torch.Tensor:
     """stats (fp64 [2C]) / colsum (fp32 [C]) are accumulated by the kernel itself (Gram / ones MMAs over the staged output tile).
     static_w: see conv1d_pair_tc."""
     n, h, w, c = x.shape
+    if CONV1D_CALL_LOG is not None:
+        CONV1D_CALL_LOG.append((x, w_img, bias, horizontal, dil, relu, res, mask, stats, colsum, static_w))
     out = torch.empty_like(x)
     fused = True
     name = (f"conv1d_tc[C={c} {'H' if horizontal else 'V'} d={dil}{' +res' if res is not None else ''}{' +mask' if mask is not None else ''}"
