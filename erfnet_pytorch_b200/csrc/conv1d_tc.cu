@@ -36,7 +36,7 @@ struct Conv1dTcParams {
   int relu;
   int w_static;                 // the weight image is not written by any kernel still in flight (inference): its copy starts before pdl_wait()
   int aux_mode;                 // 0 none, 1 add (residual / gradient accumulation), 2 relu-backward mask
-  int units;                    // N * H * (W / 128)
+  int units;                    // N * H * ceil(W / 128): the last segment of a row may be ragged (TMA zero-fills its loads and clips its stores)
   int slots;                    // A ring depth
   int slot_bytes;               // bytes per ring slot (multiple of 1024)
   int sub_bytes;                // pitch of one k-chunk sub-tile inside a slot
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int segs = p.W / 128;
+  const int segs = (p.W + 127) / 128;
   pdl_wait();
   if (tid == 0) dbg_stamp(1);
 
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
           mbar_wait(&sfull_bar[g * 2 + b], ph[g * 2 + b]);
           ph[g * 2 + b] ^= 1;
           const uint8_t* tile = s_stg + (g * 2 + b) * STG_PAD;
+          const int vrows = min(128, p.W - (u % segs) * 128);      // pixel rows of this unit inside the image (ragged last segment)
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;   // two independent chains per value
 #pragma unroll 8
           for (int it = 0; it < 64 / RPI; it += 2) {
@@ -276,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
             const int k0 = CPR == 8 ? (r0 & 7) : ((r0 >> 2) & 1), k1 = CPR == 8 ? (r1 & 7) : ((r1 >> 2) & 1);
             const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile + r0 * RB + ((jl ^ k0) * 16) + (wl & 3) * 4);
             const uint32_t w1 = *reinterpret_cast<const uint32_t*>(tile + r1 * RB + ((jl ^ k1) * 16) + (wl & 3) * 4);
-            const float x0 = __uint_as_float(w0 << 16), y0 = __uint_as_float(w0 & 0xFFFF0000u);
-            const float x1 = __uint_as_float(w1 << 16), y1 = __uint_as_float(w1 & 0xFFFF0000u);
+            const float x0 = r0 < vrows ? __uint_as_float(w0 << 16) : 0.f, y0 = r0 < vrows ? __uint_as_float(w0 & 0xFFFF0000u) : 0.f;
+            const float x1 = r1 < vrows ? __uint_as_float(w1 << 16) : 0.f, y1 = r1 < vrows ? __uint_as_float(w1 & 0xFFFF0000u) : 0.f;
             a0 += x0; a1 += y0; b0 = fmaf(x0, x0, b0); b1 = fmaf(y0, y0, b1);
             c0 += x1; c1 += y1; d0 = fmaf(x1, x1, d0); d1 = fmaf(y1, y1, d1);
           }
@@ -477,7 +478,9 @@ extern "C" int erf_conv1d_tc_set_debug(unsigned long long* buf) {   // tools onl
 }
 
 extern "C" int erf_conv1d_tc_supported(int C, int W, int dil) {
-  return (C == 16 || C == 64 || C == 128) && W >= 128 && (W % 128) == 0 && dil >= 1 && dil <= 32;
+  // any width from 16 pixels: rows are cut into 128-pixel units, the last one may be ragged (round 1 required W % 128 == 0, which left the
+  // reference fork's own 640 x 480 frames -- widths 320 / 160 / 80 -- and the 224 x 224 ImageNet net on the CUDA-core kernels)
+  return (C == 16 || C == 64 || C == 128) && W >= 16 && dil >= 1 && dil <= 32;
 }
 
 extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bias, void* out, const void* res, const void* mask, int N, int H, int W,
@@ -486,7 +489,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_tc: empty tensor");
   ERF_CHECK_ARG(!(res && mask), "erf_conv1d_tc: res and mask are mutually exclusive");
   if (!erf_conv1d_tc_supported(C, W, dil)) {
-    set_error("erf_conv1d_tc: unsupported shape C=%d W=%d dil=%d (need C in {16,64,128}, W %% 128 == 0, dil <= 32)", C, W, dil);
+    set_error("erf_conv1d_tc: unsupported shape C=%d W=%d dil=%d (need C in {16,64,128}, W >= 16, dil <= 32)", C, W, dil);
     return ERF_ERR_UNSUPPORTED;
   }
   const int CH = C < 64 ? C : 64, RB = CH * 2, KC = C / CH;
@@ -506,7 +509,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.aux_mode = res ? 1 : (mask ? 2 : 0);
   p.stats = stats;
   p.colsum = colsum;
-  p.units = N * H * (W / 128);
+  p.units = N * H * ((W + 127) / 128);
   if (horizontal) {
     p.sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;
   } else {

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_group_tc_kernel(const __g
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int segs = p.W / GPX;
+  const int segs = (p.W + GPX - 1) / GPX;
   pdl_wait();
   const int my_units = (int)blockIdx.x < p.units ? (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -241,7 +241,7 @@ extern "C" int erf_conv1d_wgrad_group_tc(const erf_wgrad_job* jobs, int njobs, v
                                          erf_stream_t stream) {
   ERF_CHECK_ARG(jobs && workspace && njobs >= 1 && njobs <= kWgMaxJobs, "erf_conv1d_wgrad_group_tc: 1..%d jobs", kWgMaxJobs);
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_wgrad_group_tc: empty tensor");
-  if (!((C == 16 || C == 64 || C == 128) && W >= 64 && (W % 64) == 0)) {
+  if (!((C == 16 || C == 64 || C == 128) && W >= 16)) {
     set_error("erf_conv1d_wgrad_group_tc: unsupported shape C=%d W=%d", C, W);
     return ERF_ERR_UNSUPPORTED;
   }
@@ -256,7 +256,7 @@ extern "C" int erf_conv1d_wgrad_group_tc(const erf_wgrad_job* jobs, int njobs, v
   p.ws = (float*)workspace;
   p.njobs = njobs;
   p.N = N; p.H = H; p.W = W;
-  p.units = N * H * (W / GPX);
+  p.units = N * H * ((W + GPX - 1) / GPX);
   int stage_bytes = 0;
   for (int j = 0; j < njobs; ++j) {
     const erf_wgrad_job& jb = jobs[j];

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int segs = p.W / PX;
+  const int segs = (p.W + PX - 1) / PX;   // the last 64-pixel unit of a row may be ragged: TMA zero-fills x and dy beyond the row, zero products
   pdl_wait();
   const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -317,7 +317,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
                         int dil, erf_stream_t stream) {
   ERF_CHECK_ARG(x && dy && dw && workspace, "erf_conv1d_wgrad_tc: null pointer");
   ERF_CHECK_ARG(N > 0 && H > 0, "erf_conv1d_wgrad_tc: empty tensor");
-  if (!((C == 16 || C == 64 || C == 128) && W >= 64 && (W % 64) == 0 && dil >= 1 && dil <= 32)) {
+  if (!((C == 16 || C == 64 || C == 128) && W >= 16 && dil >= 1 && dil <= 32)) {
     set_error("erf_conv1d_wgrad_tc: unsupported shape C=%d W=%d dil=%d", C, W, dil);
     return ERF_ERR_UNSUPPORTED;
   }
@@ -335,7 +335,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
   p.counter = counter;
   p.ws = (float*)workspace;
   p.N = N; p.H = H; p.W = W; p.horizontal = horizontal; p.dil = dil;
-  p.units = N * H * (W / PX);
+  p.units = N * H * ((W + PX - 1) / PX);
   int x_bytes;
   if (horizontal) {
     p.x_sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;

@@ -640,7 +640,7 @@ _WS = {}  # (device, bytes) -> workspace tensor for the tensor-core wgrad partia
 
 
 def conv1d_wgrad_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
-    return dtype == torch.bfloat16 and not EMULATED and c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
+    return dtype == torch.bfloat16 and not EMULATED and c in (16, 64, 128) and w >= 16 and 1 <= dil <= 32
 
 
 def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: int, dw_out=None, db_out=None, want_bias=True):

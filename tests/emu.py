@@ -423,7 +423,7 @@ def _tc_image(w, dgrad=False):
 
 
 def tc_conv1d_tc_supported(c, w, dil, dtype):
-    return c in (16, 64, 128) and w >= 128 and w % 128 == 0 and 1 <= dil <= 32
+    return c in (16, 64, 128) and w >= 16 and 1 <= dil <= 32
 
 
 def tc_pack_conv1d_tc(w, dgrad=False):
@@ -459,7 +459,7 @@ def tc_conv1d_tc(x, w_img, bias, horizontal, dil, relu=False, res=None, mask=Non
 
 
 def tc_conv1d_wgrad_tc_supported(c, w, dil, dtype):
-    return c in (16, 64, 128) and w % 64 == 0 and 1 <= dil <= 32
+    return c in (16, 64, 128) and w >= 16 and 1 <= dil <= 32
 
 
 @torch.enable_grad()

@@ -14,7 +14,8 @@ from tests.test_host_logic import assert_rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 128), (128, 384), (16, 512), (16, 128)])
+# widths: multiples of 128 (whole units) and ragged ones -- the reference fork's own 640 x 480 frames give 320 / 160 / 80, the 224 x 224 ImageNet net 56 / 28
+@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 128), (128, 384), (16, 512), (16, 128), (64, 160), (128, 80), (16, 320), (128, 28), (64, 56), (16, 200)])
 @pytest.mark.parametrize("horizontal", [False, True])
 @pytest.mark.parametrize("dil", [1, 2, 16])
 def test_conv1d_tc_matches_fp32_conv(c, w, horizontal, dil):
@@ -135,7 +136,7 @@ def test_block_train_fwd_bwd_on_tensor_cores(c, d, hw):
         assert l2(runs[True][k], ref[k]) < 0.2, (k, l2(runs[True][k], ref[k]))
 
 
-@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 64), (128, 192), (16, 512), (16, 64)])
+@pytest.mark.parametrize("c,w", [(64, 256), (128, 128), (64, 64), (128, 192), (16, 512), (16, 64), (64, 160), (128, 80), (16, 320), (128, 28), (64, 56), (16, 200)])
 @pytest.mark.parametrize("horizontal", [False, True])
 @pytest.mark.parametrize("dil", [1, 2, 16])
 def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):

@@ -48,7 +48,7 @@ def step3():
 
 
 ms = timed(step3)
-res["config3_imagenet_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "224x224: W < 128 at every encoder stage, so the convs run on the CUDA-core kernels"}
+res["config3_imagenet_train"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "note": "224x224: widths 56 / 28 in the encoder: ragged 128-pixel units on the tcgen05 kernels since round 2 (CUDA-core kernels in round 1)"}
 del opt
 from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
 tr3 = FlatAdamTrainer(m, lr=0.1, weight_decay=1e-4, loss_fn=lambda out, t: crit(out, t), sgd_momentum=0.9)
@@ -100,6 +100,21 @@ net.eval()
 with torch.no_grad():
     ms = timed(lambda: net(x))
 res["config4_ladder_eval"] = {"batch": B, "ms_per_step": ms, "images_per_s": B / ms * 1e3, "tc_frac": B / ms * 1e3 * 75.05 / 1e3 / 1427.3}
+# ---- the fork's own frame size: 640 x 480: widths 320 / 160 / 80 are not multiples of 128 -- ragged last units since round 2
+del tr
+net.train()
+B2 = 6
+x2 = torch.rand(B2, 3, 480, 640, device="cuda")
+tgt2 = torch.rand(B2, 480, 640, device="cuda") * 2
+tgt2[torch.rand(B2, 480, 640, device="cuda") < 0.7] = -1.0
+tr2 = FlatAdamTrainer(net, loss_fn=lambda out, t: crit(out, t))
+tr2.capture_cuda_graph(tuple(x2.shape), tuple(tgt2.shape), labels_dtype=torch.float32)
+ms = timed(lambda: tr2.train_step(x2, tgt2))
+res["config4_ladder_train_480x640_graph"] = {"batch": B2, "ms_per_step": ms, "images_per_s": B2 / ms * 1e3, "note": "the reference fork's frame size (train/main.py crops to 640x480)"}
+net.eval()
+with torch.no_grad():
+    ms = timed(lambda: net(x2))
+res["config4_ladder_eval_480x640"] = {"batch": B2, "ms_per_step": ms, "images_per_s": B2 / ms * 1e3}
 # ---- I/O side: uint8 HWC ingest (ToTensor + layout) at the bench shape, 3 B in + 8 B out per pixel
 from erfnet_pytorch_b200 import ops  # noqa: E402
 img = torch.randint(0, 256, (24, 512, 1024, 3), device="cuda", dtype=torch.uint8)
