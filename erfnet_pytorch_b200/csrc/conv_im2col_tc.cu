@@ -59,6 +59,25 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const __g
   const int RB = CH * 2, KC = p.Cin / CH, KSTEPS = CH / 16, CPR = RB / 16;
   const uint32_t layout = RB == 128 ? LAYOUT_SW128 : LAYOUT_SW32;
   const long long total = (long long)p.EN * p.EH * p.EW;
+  // TMA loaders walk ROW units (ceil(EW / 128) per enumerated row, the last one possibly ragged: zero-filled loads, skipped stores); the
+  // software gather walks the enumerated pixels linearly.  p.units is set accordingly by the host.
+  const int row_segs = (p.EW + 127) / 128;
+  auto decode = [&](int u, int row, int& n, int& y, int& x) -> bool {   // enumerated pixel of (unit, tile row); false = outside the grid
+    if (TMA) {
+      const unsigned t2 = (unsigned)u / (unsigned)row_segs;
+      x = (int)((unsigned)u - t2 * (unsigned)row_segs) * 128 + row;
+      n = (int)(t2 / (unsigned)p.EH);
+      y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
+      return x < p.EW;
+    }
+    const unsigned q = (unsigned)u * 128u + (unsigned)row;
+    if (q >= (unsigned)total) return false;
+    const unsigned t2 = q / (unsigned)p.EW;
+    x = (int)(q - t2 * (unsigned)p.EW);
+    n = (int)(t2 / (unsigned)p.EH);
+    y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
+    return true;
+  };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < NP; i += blockDim.x)
@@ -100,9 +119,8 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const __g
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(KC * 128 * RB);
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const unsigned q0 = (unsigned)u * 128u;
-        const unsigned t2 = q0 / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
-        const int x0 = in_step_x * (int)(q0 - t2 * (unsigned)p.EW), y0 = p.in_step * (int)(t2 - nn * (unsigned)p.EH);
+        const unsigned t2 = (unsigned)u / (unsigned)row_segs, nn = t2 / (unsigned)p.EH;
+        const int x0 = in_step_x * (int)((unsigned)u - t2 * (unsigned)row_segs) * 128, y0 = p.in_step * (int)(t2 - nn * (unsigned)p.EH);
         for (int t = 0; t < p.ntaps; ++t) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
           if (elect_one()) {
@@ -253,14 +271,10 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const __g
     uint32_t acc = 0, acc_phase = 0;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
     for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
-      const unsigned q = (unsigned)u * 128u + (unsigned)row;
       __nv_bfloat16* dst = nullptr;
-      if (q < (unsigned)total) {
-        const unsigned t2 = q / (unsigned)p.EW;
-        const int x = (int)(q - t2 * (unsigned)p.EW);
-        const int n = (int)(t2 / (unsigned)p.EH), y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
-        dst = outp + (((size_t)n * p.Ho + (p.out_step * y + p.out_oy)) * p.Wo + (out_step_x * x + p.out_ox)) * p.out_ld + p.out_c0;
-      }
+      int pn = 0, py = 0, px = 0;
+      const bool inside = decode(u, row, pn, py, px);
+      if (inside) dst = outp + (((size_t)pn * p.Ho + (p.out_step * py + p.out_oy)) * p.Wo + (out_step_x * px + p.out_ox)) * p.out_ld + p.out_c0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * NP + ((uint32_t)(quad * 32) << 16);
@@ -269,12 +283,7 @@ __global__ void __launch_bounds__(kImThreads, 1) conv_im2col_tc_kernel(const __g
         // 8 contiguous bytes per lane and 256 contiguous bytes per warp -- the logits never take the NHWC bf16 round trip
         float* o = nullptr;
         const size_t plane = (size_t)p.Ho * (size_t)(2 * p.Wo);
-        if (q < (unsigned)total) {
-          const unsigned t2 = q / (unsigned)p.EW;
-          const int x = (int)(q - t2 * (unsigned)p.EW);
-          const int n = (int)(t2 / (unsigned)p.EH), y = (int)(t2 - (unsigned)n * (unsigned)p.EH);
-          o = p.nchw_out + ((size_t)n * p.nchw_C * p.Ho + (size_t)(p.out_step * y + p.out_oy)) * (size_t)(2 * p.Wo) + 2 * x;
-        }
+        if (inside) o = p.nchw_out + ((size_t)pn * p.nchw_C * p.Ho + (size_t)(p.out_step * py + p.out_oy)) * (size_t)(2 * p.Wo) + 2 * px;
 #pragma unroll
         for (int c0 = 0; c0 < NP / 2; c0 += 16) {   // 16 channels at a time: columns c0.. of parity 0 and NP/2 + c0.. of parity 1
           uint32_t r0[16], r1[16];
@@ -430,9 +439,15 @@ extern "C" int erf_conv_im2col_tc(const erf_im2col_desc* d, erf_stream_t stream)
   static const bool tma_off = getenv("ERF_IM2COL_TMA") && atoi(getenv("ERF_IM2COL_TMA")) == 0;
   const int isx = d->in_step_x > 0 ? d->in_step_x : d->in_step;
   CUtensorMap tm;
-  bool tma = !tma_off && (d->EW % 128) == 0 && (total % 128) == 0 && ((uintptr_t)d->in % 16) == 0 && isx >= 1 && isx <= 2 && d->in_step >= 1;
+  bool tma = !tma_off && d->EW >= 16 && ((uintptr_t)d->in % 16) == 0 && isx >= 1 && isx <= 2 && d->in_step >= 1;
   if (tma) tma = im_make_map(&tm, d->in, d->EN, d->H, d->W, d->in_ld, CH, 128 * isx, isx) == 0;
   if (!tma) memset(&tm, 0, sizeof(tm));
+  if (tma) {   // row units: ceil(EW / 128) per enumerated row
+    const long long ru = (long long)d->EN * d->EH * ((d->EW + 127) / 128);
+    ERF_CHECK_ARG(ru < 0x7fffffffLL, "erf_conv_im2col_tc: too many row units");
+    p.units = (int)ru;
+    grid = p.units < 148 * per_sm ? p.units : 148 * per_sm;
+  }
 #define IM_LAUNCH2(NP_, NCHW_, TMA_)                                                                                                 \
   e = cudaFuncSetAttribute(conv_im2col_tc_kernel<NP_, NCHW_, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
   if (e == cudaSuccess && per_sm > 1) e = prefer_max_smem(conv_im2col_tc_kernel<NP_, NCHW_, TMA_>);                                   \

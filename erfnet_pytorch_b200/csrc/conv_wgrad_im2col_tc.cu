@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(kWiThreads, MINB) conv_wgrad_im2col_tc_kernel(
   const int CHd = (p.NP % 64) == 0 ? 64 : 16, RBd = CHd * 2, dsubs = p.NP / CHd;
   const int g_sub_bytes = kWiPX * RBg, d_sub_bytes = kWiPX * RBd;
   const long long total = (long long)p.EN * p.EH * p.EW;
-  const int units = (int)((total + kWiPX - 1) / kWiPX);
+  // TMA loaders walk ROW units: ceil(EW / 64) per image row, the last one possibly ragged (zero-filled dense rows contribute nothing);
+  // the software gather walks the pixels linearly
+  const int row_segs = (p.EW + kWiPX - 1) / kWiPX;
+  const int units = TMA ? p.EN * p.EH * row_segs : (int)((total + kWiPX - 1) / kWiPX);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < groups * p.NP) tmem_cols <<= 1;
@@ -92,9 +95,8 @@ __global__ void __launch_bounds__(kWiThreads, MINB) conv_wgrad_im2col_tc_kernel(
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        const unsigned q0 = (unsigned)u * (unsigned)kWiPX;
-        const unsigned t2 = q0 / (unsigned)p.EW, nn = t2 / (unsigned)p.EH;
-        const int x0 = (int)(q0 - t2 * (unsigned)p.EW), y0 = (int)(t2 - nn * (unsigned)p.EH);
+        const unsigned t2 = (unsigned)u / (unsigned)row_segs, nn = t2 / (unsigned)p.EH;
+        const int x0 = (int)((unsigned)u - t2 * (unsigned)row_segs) * kWiPX, y0 = (int)(t2 - nn * (unsigned)p.EH);
         uint8_t* base = smem + (size_t)stage * stage_bytes;
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -439,7 +441,7 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   p.tail_bytes = atoms_per_m * kWiPX * RBg;
   const long long total = (long long)d->EN * d->EH * d->EW;
   ERF_CHECK_ARG(total + kWiPX < 0x7fffffffLL, "erf_conv_wgrad_im2col_tc: %lld pixels exceed the 32-bit index range", total);
-  const int units = (int)((total + kWiPX - 1) / kWiPX);
+  int units = (int)((total + kWiPX - 1) / kWiPX);
   // two CTAs per SM when two rings of >= 2 stages and two accumulator sets fit (latency-bound per-unit chain)
   int per_sm = 1;
   if (groups * d->NP <= 256 && (104 * 1024 - p.tail_bytes) / stage_bytes >= 2 && units > 148) {
@@ -454,7 +456,7 @@ extern "C" int erf_conv_wgrad_im2col_tc(const erf_wgrad_im2col_desc* d, float* d
   // TMA loaders: row-aligned units, 16-byte aligned pixel rows and channel offsets, whole 16-byte gathered rows
   static const bool tma_off = getenv("ERF_WGRAD_IM2COL_TMA") && atoi(getenv("ERF_WGRAD_IM2COL_TMA")) == 0;
   CUtensorMap mg, md;
-  bool tma = !tma_off && (d->EW % kWiPX) == 0 && d->g_copy_bytes >= 16 && (d->g_ld % 8) == 0 && (d->d_ld % 8) == 0 && ((uintptr_t)d->g % 16) == 0 &&
+  bool tma = !tma_off && d->EW >= 16 && d->g_copy_bytes >= 16 && (d->g_ld % 8) == 0 && (d->d_ld % 8) == 0 && ((uintptr_t)d->g % 16) == 0 &&
              ((uintptr_t)d->d % 16) == 0 && d->g_step >= 1 && d->g_step <= 4;
   if (tma) {
     const int gsx = d->g_step_x > 0 ? d->g_step_x : d->g_step;

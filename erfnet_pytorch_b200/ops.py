@@ -444,7 +444,11 @@ def conv_im2col_tc(x: torch.Tensor, imgs, plan, spec_g: ConvSpec, bias: Optional
         for e, img in zip(plan, imgs):
             d = _lib.Im2colDesc()
             d.in_, d.H, d.W, d.in_ld, d.Cin = x.data_ptr(), h, w, ld, round_up(spec_g.cin, 16)
-            d.EN, d.EH, d.EW, d.in_step = n, ho // e["div"], wo // e["div"], e["in_step"]
+            # a parity class (oy, ox) of a stride-2 transposed gather owns ceil((ho - oy) / 2) x ceil((wo - ox) / 2) output pixels (odd sizes: the
+            # data gradient of a stride-2 conv over an odd-sized input)
+            d.EN, d.EH, d.EW, d.in_step = n, (ho - e["oy"] + e["div"] - 1) // e["div"], (wo - e["ox"] + e["div"] - 1) // e["div"], e["in_step"]
+            if d.EH <= 0 or d.EW <= 0:
+                continue
             d.ntaps = len(e["taps"])
             for i, (_, _, dy, dx) in enumerate(e["taps"]):
                 d.tap_dy[i], d.tap_dx[i] = dy, dx

@@ -25,6 +25,12 @@ CASES = [
 CASES += [(c[0] + "_tma", c[1], (2, 4, 128 if c[1].transposed else 256)) for c in CASES[:5]] + [("enc_head_1x1_tma", CASES[5][1], (1, 3, 256))]
 
 
+# ragged rows (round 2): any enumerated width >= 16 runs on the TMA loaders as ceil(EW / 128) row units, the last one zero-filled / clipped;
+# narrower grids (EW < 16) keep the cp.async gather covered
+CASES += [(c[0] + "_ragged", c[1], (2, 5, 100 if c[1].transposed else 200)) for c in CASES[:5]] + [("enc_head_1x1_ragged", CASES[5][1], (2, 3, 160))]
+CASES += [(c[0] + "_gather", c[1], (2, 9, 12 if c[1].transposed else 24)) for c in CASES[:5]] + [("enc_head_1x1_gather", CASES[5][1], (3, 7, 12))]
+
+
 def _torch_fwd(x_nchw, w, b, spec):
     if spec.transposed:
         return F.conv_transpose2d(x_nchw, w, b, stride=spec.stride, padding=(spec.pad_h, spec.pad_w), output_padding=spec.out_pad)
@@ -76,6 +82,11 @@ def test_forward_and_data_gradient(name, spec, nhw):
 WG_CASES = CASES[:5] + [("stem3_13", ConvSpec(3, 13, 3, 3, 2, 1, 1), (2, 20, 44))]
 # row-aligned dense grids (width % 64 == 0): the TMA-loaded form of the kernel (strided tensor maps); the sizes above keep the cp.async gather covered
 WG_CASES += [(c[0] + "_tma", c[1], (2, 6, 64 if c[1].transposed else 128)) for c in CASES[:5]] + [("up128_64_tma_wide", CASES[2][1], (1, 3, 192))]
+
+
+# ragged rows: ceil(EW / 64) units per row, the last one zero-filled; EW < 16 keeps the cp.async gather covered
+WG_CASES += [(c[0] + "_ragged", c[1], (2, 5, 100 if c[1].transposed else 200)) for c in CASES[:5]]
+WG_CASES += [(c[0] + "_gather", c[1], (2, 9, 12 if c[1].transposed else 24)) for c in CASES[:5]]
 
 
 @pytest.mark.parametrize("name,spec,nhw", WG_CASES, ids=[c[0] for c in WG_CASES])
