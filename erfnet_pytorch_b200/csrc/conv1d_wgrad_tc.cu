@@ -22,6 +22,7 @@ using namespace tc;
 struct WgradTcParams {
   float* dw;          // fused reduction: the torch-layout gradient the partial sums are added to (null: a second kernel reduces)
   unsigned* counter;  // fused reduction: zeroed grid-barrier word
+  float* dw_bulk; // bulk reduction: every CTA adds its accumulators to the torch-layout gradient with cp.reduce.async.bulk (no workspace, no second kernel)
   float* ws;      // [grid][ACCS][128][C] per-CTA partial sums
   int N, H, W;
   int horizontal, dil;
@@ -136,6 +137,78 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
       }
       if (elect_one()) umma_commit(&done_bar);
     }
+  } else if (p.dw_bulk != nullptr) {
+    // epilogue (once), bulk-reduction form: the accumulators are transposed through shared memory into the gradient's own layout
+    // dw[co][ci][t] (the ring is idle once done_bar has fired) and ADDED to it by the TMA unit -- cp.reduce.async.bulk .add.f32, the L2
+    // performs the additions -- so there is no per-CTA partial slab, no workspace traffic and no reduction launch.  C = 128 goes in four
+    // chunks of 32 output channels through three staging regions; CTAs start at different chunks so they do not all hit the same lines.
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int etid = tid - 64;
+    constexpr int NCH = C == 128 ? 4 : 1;
+    constexpr int CO_CH = C == 128 ? 32 : C;
+    constexpr int CHUNK_FLOATS = CO_CH * C * 3;
+    constexpr int R = C == 128 ? 3 : 1;
+    if (my_units > 0) {
+      mbar_wait(&done_bar, 0);
+      tcgen05_fence_after();
+      float* stg = reinterpret_cast<float*>(smem);
+      const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+#pragma unroll 1
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = (i + (int)blockIdx.x) % NCH;
+        float* s = stg + (size_t)(i % R) * CHUNK_FLOATS;
+        if (i >= R) {   // the region's previous reduction must have read it
+          if (etid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(R - 1) : "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (C == 128) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + a * C + ch * 32 + lane_sel, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[(j * 128 + row) * 3 + a] = __uint_as_float(r[j]);   // lanes 3 words apart: conflict-free
+          }
+        } else if (C == 64) {
+          // accumulator 0: rows 0..63 = tap 0, rows 64..127 = tap 1; accumulator 1: rows 64..127 = tap 2 (rows 0..63 repeat tap 1)
+          const int ci = row & 63, t0 = row >> 6;
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + c0 + lane_sel, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[((c0 + j) * 64 + ci) * 3 + t0] = __uint_as_float(r[j]);
+            tmem_ld32(tmem_base + C + c0 + lane_sel, r);
+            tmem_ld_wait();
+            if (t0 == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s[((c0 + j) * 64 + ci) * 3 + 2] = __uint_as_float(r[j]);
+            }
+          }
+        } else {
+          // one accumulator: row = tap * 16 + ci for rows 0..47, the other rows are the ignored atoms
+          uint32_t r[16];
+          tmem_ld16(tmem_base + lane_sel, r);
+          tmem_ld_wait();
+          if (row < 48) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s[(j * 16 + (row & 15)) * 3 + (row >> 4)] = __uint_as_float(r[j]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (etid == 0) {
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                       ::"l"(p.dw_bulk + (size_t)ch * CHUNK_FLOATS), "r"(smem_u32(s)), "r"((uint32_t)(CHUNK_FLOATS * 4))
+                       : "memory");
+          tma_store_commit();
+        }
+      }
+      if (etid == 0) tma_store_wait0();
+    }
   } else {
     // epilogue (once): dump the accumulators of this CTA
     const int quad = warp & 3;
@@ -171,7 +244,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (p.dw == nullptr) return;
+  if (p.dw == nullptr || p.dw_bulk != nullptr) return;
   // ---- fused reduction of the per-CTA partial sums (no second launch): after a grid barrier CTA b owns a contiguous range of the slab's
   // float4s, sums it over all CTAs' slabs straight from L2 (eight independent 16-byte loads in flight per thread, S threads per output
   // splitting the slabs) and adds the result to the torch-layout gradient -- every output element has exactly one owner, so no atomics.
@@ -332,6 +405,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
   }
   WgradTcParams p;
   p.dw = nullptr;
+  p.dw_bulk = nullptr;
   p.counter = counter;
   p.ws = (float*)workspace;
   p.N = N; p.H = H; p.W = W; p.horizontal = horizontal; p.dil = dil;
@@ -358,6 +432,12 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
   cudaStream_t s = (cudaStream_t)stream;
   static const bool fuse_off = getenv("ERF_WGRAD_FUSED") && atoi(getenv("ERF_WGRAD_FUSED")) == 0;
   bool fused = counter != nullptr && !fuse_off;
+  // bulk-reduction epilogue (default): needs a 16-byte aligned gradient and the staging regions inside the ring
+  const char* bulk_env = getenv("ERF_WGRAD_BULK");   // read per call: the tests switch forms inside one process
+  const bool bulk_off = bulk_env && atoi(bulk_env) == 0;
+  const size_t stage_need = C == 128 ? (size_t)3 * 32 * 128 * 3 * 4 : (size_t)C * C * 3 * 4;
+  const bool bulk = !bulk_off && !fused && ((uintptr_t)dw % 16) == 0 && (size_t)p.stages * p.stage_bytes >= stage_need;
+  if (bulk) p.dw_bulk = dw;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = prefer_max_smem(conv1d_wgrad_tc_kernel<16>);
@@ -368,7 +448,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
       }
       if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<16>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      if (!fused) launch_pdl(wgrad_reduce_kernel<16>, dim3(dim3((1 * 128 * 16 + 255) / 256, 37)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused && !bulk) launch_pdl(wgrad_reduce_kernel<16>, dim3(dim3((1 * 128 * 16 + 255) / 256, 37)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else if (C == 64) {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -379,7 +459,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
       }
       if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<64>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      if (!fused) launch_pdl(wgrad_reduce_kernel<64>, dim3(dim3((2 * 128 * 64 + 255) / 256, 12)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused && !bulk) launch_pdl(wgrad_reduce_kernel<64>, dim3(dim3((2 * 128 * 64 + 255) / 256, 12)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   } else {
     e = cudaFuncSetAttribute(conv1d_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -390,7 +470,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
       }
       if (fused) p.dw = dw;
       launch_pdl(conv1d_wgrad_tc_kernel<128>, dim3(grid), dim3(192), smem, (cudaStream_t)(s), mx, mdy, p);
-      if (!fused) launch_pdl(wgrad_reduce_kernel<128>, dim3(dim3((3 * 128 * 128 + 255) / 256, 6)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
+      if (!fused && !bulk) launch_pdl(wgrad_reduce_kernel<128>, dim3(dim3((3 * 128 * 128 + 255) / 256, 6)), dim3(256), 0, (cudaStream_t)(s), p.ws, grid, dw);
     }
   }
   if (e != cudaSuccess) {

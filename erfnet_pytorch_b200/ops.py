@@ -667,12 +667,23 @@ def conv1d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, horizontal: bool, dil: in
             _count()
         else:
             check(L.erf_conv1d_wgrad_tc(_p(x), _p(dy), _p(dw_out), _p(ws), nbytes, n, h, w, c, int(horizontal), dil, _stream(x)))
-            _count(2)
+            _count(1 if (WGRAD_BULK and dw_out.data_ptr() % 16 == 0) else 2)   # bulk-reduction epilogue: no reduce launch (csrc/conv1d_wgrad_tc.cu)
     if want_bias:
         if db_out is None:
             db_out = torch.zeros(c, device=x.device, dtype=torch.float32)
         channel_sum(dy, db_out)
     return dw_out, db_out
+
+
+WGRAD_BULK = os.environ.get("ERF_WGRAD_BULK", "1") != "0"     # mirrors the library's switch (launch counting only)
+
+
+def set_wgrad_bulk(flag: bool) -> None:
+    """Reduction form of conv1d_wgrad_tc: True (default) = every CTA adds its accumulators to the gradient with cp.reduce.async.bulk (one launch);
+    False = per-CTA partial slabs + reduce kernel (two launches).  The library reads ERF_WGRAD_BULK on every call."""
+    global WGRAD_BULK
+    WGRAD_BULK = bool(flag)
+    os.environ["ERF_WGRAD_BULK"] = "1" if flag else "0"
 
 
 WGRAD_GROUP = os.environ.get("ERF_WGRAD_GROUP", "0") != "0"   # the four 3-tap weight gradients of a block in ONE launch (+ one reduce launch).  Measured: the

@@ -67,10 +67,12 @@ class FlatAdamTrainer:
         named = list(model.named_parameters())
         # flat layout ordered by bucket so that each bucket is one contiguous slice
         order = sorted(range(len(named)), key=lambda i: (_bucket_of(named[i][0]), i))
-        total = sum(p.numel() for _, p in named)
+        # every parameter starts on a 16-byte boundary of the flat buffers (the weight-gradient kernels add into their slice with TMA bulk reductions,
+        # the optimiser kernels use 16-byte accesses); the few padding values stay zero
+        total = sum((p.numel() + 3) // 4 * 4 for _, p in named)
         dev = named[0][1].device
         self.criterion = self.criterion.to(dev)
-        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -90,7 +92,7 @@ class FlatAdamTrainer:
             sl[1] = off + n
             self._bucket_params[b] += 1
             self._param_bucket[p] = b
-            off += n
+            off += (n + 3) // 4 * 4
         self._params = [p for _, p in named]                         # model.parameters() order = torch.optim's parameter indices
         self._offsets = {}
         for i in order:

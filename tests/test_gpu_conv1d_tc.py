@@ -155,26 +155,46 @@ def test_conv1d_wgrad_tc_matches_autograd(c, w, horizontal, dil):
 
 
 @pytest.mark.parametrize("c,n,h,w", [(128, 6, 64, 128), (64, 6, 128, 256), (16, 6, 256, 512), (64, 1, 3, 64), (128, 2, 5, 192)])
-def test_conv1d_wgrad_fused_reduction_matches_two_launches(c, n, h, w):
-    """The in-kernel reduction (grid barrier, every CTA sums its slice of the partial-sum slabs) against the separate reduce kernel: the same
-    partial sums added in a different order, ACCUMULATED into existing gradient contents; bench shapes and grids smaller than the SM count."""
+def test_conv1d_wgrad_reduction_forms_agree(c, n, h, w):
+    """The three reduction forms of the weight gradient -- bulk (default: every CTA adds its accumulators to the gradient with cp.reduce.async.bulk,
+    one launch), in-kernel (grid barrier, every CTA sums its slice of the partial-sum slabs) and the separate reduce kernel -- add the same partial
+    sums in different orders, ACCUMULATED into existing gradient contents; bench shapes and grids smaller than the SM count."""
     gen = torch.Generator().manual_seed(c + n + h)
     x = torch.randn(n, h, w, c, generator=gen).bfloat16().cuda()
     dy = torch.randn(n, h, w, c, generator=gen).bfloat16().cuda()
     got = []
-    for fused in (True, False):
-        ops.WGRAD_FUSED_REDUCE = fused
-        try:
+    try:
+        for bulk, fused, launches in ((True, False, 2), (False, True, 2), (False, False, 4)):
+            ops.set_wgrad_bulk(bulk)
+            ops.WGRAD_FUSED_REDUCE = fused
             dw = torch.full((c, c, 3, 1), 0.125, device="cuda")
             before = ops.LAUNCHES
             for _ in range(2):                                   # two accumulating calls
                 ops.conv1d_wgrad_tc(x, dy, False, 2, dw_out=dw, want_bias=False)
-            assert ops.LAUNCHES - before == (2 if fused else 4)
+            assert ops.LAUNCHES - before == launches
             got.append(dw.cpu().numpy() - 0.125)
-        finally:
-            ops.WGRAD_FUSED_REDUCE = True
-    assert_rel(got[0], got[1], 2e-5, "fused vs two-launch dW")
+    finally:
+        ops.WGRAD_FUSED_REDUCE = False
+        ops.set_wgrad_bulk(True)
+    assert_rel(got[0], got[2], 2e-5, "bulk vs two-launch dW")
+    assert_rel(got[1], got[2], 2e-5, "fused vs two-launch dW")
     assert np.abs(got[0]).max() > 1.0
+
+
+def test_conv1d_wgrad_bulk_needs_aligned_gradient():
+    """A gradient view that is not 16-byte aligned cannot be the target of a bulk reduction: the library falls back to the reduce kernel."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 8, 128, 64, generator=gen).bfloat16().cuda()
+    dy = torch.randn(2, 8, 128, 64, generator=gen).bfloat16().cuda()
+    ref, _ = ops.conv1d_wgrad_tc(x, dy, True, 1, want_bias=False)
+    buf = torch.zeros(64 * 64 * 3 + 4, device="cuda")
+    dw = buf[1:1 + 64 * 64 * 3].view(64, 64, 1, 3)
+    assert dw.data_ptr() % 16 != 0
+    before = ops.LAUNCHES
+    ops.conv1d_wgrad_tc(x, dy, True, 1, dw_out=dw, want_bias=False)
+    assert ops.LAUNCHES - before == 2
+    assert_rel(dw.cpu().numpy(), ref.cpu().numpy(), 2e-5, "unaligned dW")
+    assert float(buf[0]) == 0.0 and float(buf[-1]) == 0.0
 
 
 @pytest.mark.parametrize("c,n,h,w,dil", [(128, 6, 64, 128, 8), (64, 6, 128, 256, 1), (16, 6, 256, 512, 1), (64, 1, 3, 64, 2), (128, 2, 5, 192, 16)])
