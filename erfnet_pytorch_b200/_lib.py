@@ -68,6 +68,7 @@ _SIGNATURES = {
     "erf_bn_fused_supported": [_i],
     "erf_bn_fwd_apply": [_vp, _i, _vp, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "erf_bn_bwd_fused": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "erf_bn_bwd_fused_spread": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "erf_ce_weight_sum": [_vp, _ll, _vp, _i, _i, _vp, _vp],
     "erf_ce_fwd_bwd": [_vp, _i, _i, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "erf_ce_fwd_bwd_colsum_supported": [_i, _i, _i],

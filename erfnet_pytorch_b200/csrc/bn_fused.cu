@@ -101,7 +101,8 @@ struct BnBwdFusedParams {
   long long HW, n_px;
   int C, px_per_block, smem_items;
   int ring_gy, ring_m;   // bf16 kernel: first slot of the (g, y) ring of items beyond the cache, first slot of the mask ring
-  double* sums;        // [2C], zeroed by the caller
+  double* sums;        // [sum_copies][2C], zeroed by the caller
+  int sum_copies;      // lean kernel: CTA b adds into copy b % sum_copies (148 same-address fp64 atomics serialise in the L2: ~3 us at the end of phase 1)
   unsigned* counter;   // zeroed by the caller
   void* dy;
   int dy_ld;
@@ -327,9 +328,21 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Timeline instrumentation (tools/timeline_bn.py): when a buffer is registered every CTA records globaltimer stamps (ns) of its phases.
+__device__ unsigned long long* g_bn_dbg = nullptr;
+__device__ __forceinline__ void bn_stamp(int k) {
+  if (g_bn_dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bn_dbg[(size_t)blockIdx.x * 8 + k] = t;
+  }
+}
+
 template <int MODE, int REGI>
 __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const BnBwdFusedParams p) {
+  bn_stamp(0);
   pdl_enter();
+  bn_stamp(1);
   extern __shared__ __align__(16) float s_dyn[];
   const int C = p.C, tid = threadIdx.x;
   float* s_coef = s_dyn;                                   // [6C]: sc, sh (mask from y), mean | after the barrier also k1, k2, k3
@@ -464,9 +477,12 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
     if (MODE != BN_MASK_NONE && j < p.smem_items) s_slot[(size_t)gs * BS_THREADS + tid] = gq;   // keep the masked gradient
   }
   cp_async_wait<0>();
+  bn_stamp(2);
   block_channel_reduce<2>(acc, C, r.c0, s_part, [&](int i, float t) { atomicAdd(&p.sums[i], (double)t); });
+  bn_stamp(3);
 
   grid_barrier(p.counter, gridDim.x);
+  bn_stamp(4);
 
   // ---- phase 2 ----
   const int first_uncached = p.smem_items;                    // streamed items [first_uncached, ns) are read again
@@ -488,6 +504,7 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
     }
   }
   __syncthreads();
+  bn_stamp(5);
   drop_n = -1;                               // phase 2 walks the pixels again from the start
   auto proc2 = [&](long long q, const uint4& gmq, const uint4& yq) {
     if (gmasked) *reinterpret_cast<uint4*>(gmasked + (size_t)q * p.gmasked_ld + r.c0) = gmq;
@@ -541,6 +558,360 @@ __global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_fused_bf16_kernel(const 
     proc2(q, gq, yq);
   }
   cp_async_wait<0>();
+  bn_stamp(6);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// bf16 fast path, third generation.  The per-CTA timeline of the kernel above (tools/timeline_bn.py) showed both phases bound by
+// INSTRUCTION ISSUE, not by memory: ~200 SASS instructions per 16-byte item in phase 1 and ~110 in phase 2 (64-bit index arithmetic and
+// a bounds check per item, coefficient vectors re-fetched from shared memory, scalar fp32 math) -- 15 + 12 us at C = 64 for 92 MB.
+// Same two-phase structure and the same on-chip cache, but a short instruction stream:
+//   * addresses are running pointers with one per-thread stride; a thread knows its item count up front (no per-item bounds checks);
+//   * per-channel coefficients stay in registers, the math is packed fp32x2 (FFMA2 / FADD2 / FMUL2: bit-identical to the scalar forms);
+//   * Dropout2d: a CTA's pixel range crosses at most one sample boundary (checked by the launcher), so the multipliers are reloaded
+//     once at a precomputed item index instead of dividing per item;
+//   * with a mask TENSOR the masked gradient gm is written in phase 1 (it is an output anyway), so phase 2 re-reads only (gm, y) for
+//     the items beyond the cache and never touches the mask again.
+// Modes served: BN_MASK_AFFINE (plain BN -> ReLU, mask recomputed from y; no dropout, no gm output) and BN_MASK_TENSOR with the gm
+// output (BN2 of a block), with or without Dropout2d.  Everything else stays on the kernel above.
+constexpr int BL_D = 4;   // cp.async prefetch depth (items)
+
+__device__ __forceinline__ void unpack_bf8_2(const uint4& q, float2 (&f)[4]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+}
+__device__ __forceinline__ void ld8_as_f2(const float* __restrict__ src, float2 (&f)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w); f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+}
+
+template <int MODE, bool DROP, int REGI>
+__global__ void __launch_bounds__(BS_THREADS, 1) bn_bwd_lean_kernel(const BnBwdFusedParams p) {
+  bn_stamp(0);
+  pdl_enter();
+  bn_stamp(1);
+  static_assert(MODE == BN_MASK_AFFINE || MODE == BN_MASK_TENSOR, "modes of the lean kernel");
+  extern __shared__ __align__(16) float s_dyn[];
+  const int C = p.C, tid = threadIdx.x;
+  float* s_coef = s_dyn;                                   // [5C]: sc, sh (mask from y) | k1, k2, k3 (after the barrier)
+  float* s_part = s_dyn + 5 * C;                           // [warps][2C]
+  char* s_mine = reinterpret_cast<char*>(s_part + (BS_THREADS / 32) * 2 * C) + tid * 16;   // this thread's 16 bytes of every slot
+  constexpr int SLOT = BS_THREADS * 16;                    // bytes between slots
+  const int c8 = C >> 3, c0 = (tid % c8) * 8, lanes = BS_THREADS / c8;
+  const long long p0 = (long long)blockIdx.x * p.px_per_block;
+  const long long p1 = p0 + p.px_per_block < p.n_px ? p0 + p.px_per_block : p.n_px;
+  const long long q0 = p0 + tid / c8;
+  const int cnt = q0 < p1 ? (int)((p1 - q0 + lanes - 1) / lanes) : 0;   // items of this thread (pixels q0 + k * lanes)
+  const int ns = cnt > REGI ? cnt - REGI : 0;                            // streamed items
+  const int nc = p.smem_items;                                           // streamed items [0, nc) have their own (g, y) slots
+
+  if (MODE == BN_MASK_AFFINE) {
+    for (int i = tid; i < C; i += blockDim.x) {   // the forward pass's scale / shift (bn_fwd_apply_kernel / bn_finalize_kernel), same expressions
+      const float sc = p.gamma[i] * p.invstd[i];
+      s_coef[i] = sc;
+      s_coef[C + i] = p.beta[i] - p.mean[i] * sc;
+    }
+    __syncthreads();
+  }
+  float2 nmu[4];
+  {
+    ld8_as_f2(p.mean + c0, nmu);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nmu[i] = make_float2(-nmu[i].x, -nmu[i].y);
+  }
+  // running pointers (bytes) and per-item strides
+  const char* gp = reinterpret_cast<const char*>(p.g) + ((size_t)q0 * p.g_ld + c0) * 2;
+  const char* yp = reinterpret_cast<const char*>(p.y) + ((size_t)q0 * p.y_ld + c0) * 2;
+  const char* mp = reinterpret_cast<const char*>(p.mask) + ((size_t)q0 * p.mask_ld + c0) * 2;
+  char* dyp = reinterpret_cast<char*>(p.dy) + ((size_t)q0 * p.dy_ld + c0) * 2;
+  char* gmp = reinterpret_cast<char*>(p.gmasked) + ((size_t)q0 * p.gmasked_ld + c0) * 2;
+  const size_t gs = (size_t)lanes * p.g_ld * 2, ys = (size_t)lanes * p.y_ld * 2, ms = (size_t)lanes * p.mask_ld * 2;
+  const size_t dys = (size_t)lanes * p.dy_ld * 2, gms = (size_t)lanes * p.gmasked_ld * 2;
+  // Dropout2d: items [0, kb) belong to sample n0, items [kb, cnt) to sample n0 + 1 (px_per_block <= HW)
+  float2 dv[4];
+  int kb = 0x7fffffff;
+  const float* drop_next = nullptr;
+  if (DROP) {
+    const long long n0 = img_of(q0 < p.n_px ? q0 : 0, p.HW);
+    const long long edge = (n0 + 1) * p.HW;
+    kb = (int)((edge - q0 + lanes - 1) / lanes);
+    ld8_as_f2(p.drop + n0 * C + c0, dv);
+    drop_next = p.drop + (n0 + 1) * C + c0;
+  }
+  float2 acc0[4], acc1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
+  uint4 cg[REGI], cy[REGI];
+
+  // gq <- g * (mask > 0) in place (exact in bf16); sums += (gb, gb * (y - mean)), gb = gq * drop
+  auto proc1 = [&](uint4& gq, const uint4& yq, const uint4& mq) {
+    float2 yf[4], gf[4];
+    unpack_bf8_2(yq, yf);
+    uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
+    if (MODE == BN_MASK_TENSOR) {
+      const uint32_t* mw = reinterpret_cast<const uint32_t*>(&mq);
+      const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gw[i] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mw[i]), zero);
+    } else {
+      float2 sc[4], sh[4];
+      ld8_as_f2(s_coef + c0, sc);
+      ld8_as_f2(s_coef + C + c0, sh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 z = __ffma2_rn(yf[i], sc[i], sh[i]);
+        const uint32_t lo = z.x > 0.f ? 0x0000FFFFu : 0u, hi = z.y > 0.f ? 0xFFFF0000u : 0u;
+        gw[i] &= lo | hi;
+      }
+    }
+    unpack_bf8_2(gq, gf);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (DROP) gf[i] = __fmul2_rn(gf[i], dv[i]);
+      acc0[i] = __fadd2_rn(acc0[i], gf[i]);
+      acc1[i] = __ffma2_rn(gf[i], __fadd2_rn(yf[i], nmu[i]), acc1[i]);
+    }
+  };
+  auto next_sample = [&]() { if (DROP) ld8_as_f2(drop_next, dv); };
+
+  // streamed item j: slots of its g / y (own slots below nc, a ring of BL_D pairs beyond) and, with a mask tensor, a ring of BL_D mask slots
+  int iss = 0, iss_r = 0, iss_m = 0;                       // issue side: next item, ring positions
+  const char* ig = gp + (size_t)REGI * gs;
+  const char* iy = yp + (size_t)REGI * ys;
+  const char* im = mp + (size_t)REGI * ms;
+  auto issue1 = [&]() {
+    if (iss < ns) {
+      const int gsl = iss < nc ? 2 * iss : p.ring_gy + 2 * iss_r;
+      cp_async16(s_mine + (size_t)gsl * SLOT, ig);
+      cp_async16(s_mine + (size_t)(gsl + 1) * SLOT, iy);
+      if (MODE == BN_MASK_TENSOR) cp_async16(s_mine + (size_t)(p.ring_m + iss_m) * SLOT, im);
+      if (iss >= nc) iss_r = iss_r + 1 == BL_D ? 0 : iss_r + 1;
+      iss_m = iss_m + 1 == BL_D ? 0 : iss_m + 1;
+      ig += gs; iy += ys; im += ms;
+    }
+    ++iss;
+    cp_async_commit();
+  };
+
+  // ---- phase 1 ----
+#pragma unroll
+  for (int j = 0; j < BL_D - 1; ++j) issue1();
+  {
+    uint4 mv[REGI];
+#pragma unroll
+    for (int k = 0; k < REGI; ++k) {
+      if (k < cnt) {
+        cg[k] = *reinterpret_cast<const uint4*>(gp + (size_t)k * gs);
+        cy[k] = *reinterpret_cast<const uint4*>(yp + (size_t)k * ys);
+        if (MODE == BN_MASK_TENSOR) mv[k] = *reinterpret_cast<const uint4*>(mp + (size_t)k * ms);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < REGI; ++k) {
+      if (k < cnt) {
+        if (DROP && k == kb) next_sample();
+        proc1(cg[k], cy[k], mv[k]);
+        if (MODE == BN_MASK_TENSOR) *reinterpret_cast<uint4*>(gmp + (size_t)k * gms) = cg[k];
+      }
+    }
+  }
+  {
+    int con_r = 0, con_m = 0;                              // consume side ring positions
+    char* og = gmp + (size_t)REGI * gms;
+    for (int j = 0; j < ns; ++j) {
+      issue1();
+      cp_async_wait<BL_D - 1>();
+      const int gsl = j < nc ? 2 * j : p.ring_gy + 2 * con_r;
+      uint4 gq = *reinterpret_cast<const uint4*>(s_mine + (size_t)gsl * SLOT);
+      const uint4 yq = *reinterpret_cast<const uint4*>(s_mine + (size_t)(gsl + 1) * SLOT);
+      uint4 mq = make_uint4(0u, 0u, 0u, 0u);
+      if (MODE == BN_MASK_TENSOR) mq = *reinterpret_cast<const uint4*>(s_mine + (size_t)(p.ring_m + con_m) * SLOT);
+      if (DROP && REGI + j == kb) next_sample();
+      proc1(gq, yq, mq);
+      if (j < nc) *reinterpret_cast<uint4*>(s_mine + (size_t)gsl * SLOT) = gq;   // keep the masked gradient
+      else con_r = con_r + 1 == BL_D ? 0 : con_r + 1;
+      con_m = con_m + 1 == BL_D ? 0 : con_m + 1;
+      if (MODE == BN_MASK_TENSOR) { *reinterpret_cast<uint4*>(og) = gq; og += gms; }
+    }
+  }
+  cp_async_wait<0>();
+  bn_stamp(2);
+  {
+    float acc[2][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[0][2 * i] = acc0[i].x; acc[0][2 * i + 1] = acc0[i].y;
+      acc[1][2 * i] = acc1[i].x; acc[1][2 * i + 1] = acc1[i].y;
+    }
+    double* my_sums = p.sums + (size_t)(blockIdx.x % (unsigned)p.sum_copies) * 2 * C;
+    block_channel_reduce<2>(acc, C, c0, s_part, [&](int i, float t) { atomicAdd(&my_sums[i], (double)t); });
+  }
+  bn_stamp(3);
+
+  grid_barrier(p.counter, gridDim.x);
+  bn_stamp(4);
+
+  // ---- phase 2: dy = k1 * gb + k2 * y + k3 ----
+  // items beyond the cache are read again: (gm, y) when gm was written in phase 1, (g, y) + the recomputed mask otherwise
+  const char* rg = MODE == BN_MASK_TENSOR ? gmp : gp;
+  const size_t rgs = MODE == BN_MASK_TENSOR ? gms : gs;
+  int iss2 = nc, iss2_r = 0;
+  const char* ig2 = rg + (size_t)(REGI + nc) * rgs;
+  const char* iy2 = yp + (size_t)(REGI + nc) * ys;
+  auto issue2 = [&]() {
+    if (iss2 < ns) {
+      const int gsl = p.ring_gy + 2 * iss2_r;
+      cp_async16(s_mine + (size_t)gsl * SLOT, ig2);
+      cp_async16(s_mine + (size_t)(gsl + 1) * SLOT, iy2);
+      iss2_r = iss2_r + 1 == BL_D ? 0 : iss2_r + 1;
+      ig2 += rgs; iy2 += ys;
+    }
+    ++iss2;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int j = 0; j < BL_D - 1; ++j) issue2();   // in flight while the cached items are processed
+  {
+    const double inv_m = 1.0 / (double)p.n_px;
+    for (int i = tid; i < C; i += blockDim.x) {
+      const double is = p.invstd[i], ga = p.gamma[i], mu = p.mean[i];
+      double s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < p.sum_copies; ++k) {
+        s1 += __ldcg(&p.sums[(size_t)k * 2 * C + i]);
+        s2 += __ldcg(&p.sums[(size_t)k * 2 * C + C + i]);
+      }
+      s2 *= is;                                                 // sum gb * xhat
+      const double k2 = -ga * is * is * s2 * inv_m;
+      s_coef[2 * C + i] = (float)(ga * is);
+      s_coef[3 * C + i] = (float)k2;
+      s_coef[4 * C + i] = (float)(-ga * is * s1 * inv_m - k2 * mu);
+      if (blockIdx.x == 0) {
+        if (p.dbeta) p.dbeta[i] = (float)s1;
+        if (p.dgamma) p.dgamma[i] = (float)s2;
+      }
+    }
+  }
+  __syncthreads();
+  bn_stamp(5);
+  float2 k1[4], k2[4], k3[4], k1d[4];
+  ld8_as_f2(s_coef + 2 * C + c0, k1);
+  ld8_as_f2(s_coef + 3 * C + c0, k2);
+  ld8_as_f2(s_coef + 4 * C + c0, k3);
+  if (DROP) {
+    ld8_as_f2(drop_next - C, dv);              // back to the first sample
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k1d[i] = __fmul2_rn(k1[i], dv[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k1d[i] = k1[i];
+  }
+  auto next_sample2 = [&]() {
+    if (DROP) {
+      ld8_as_f2(drop_next, dv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) k1d[i] = __fmul2_rn(k1[i], dv[i]);
+    }
+  };
+  auto proc2 = [&](char* dst, const uint4& gmq, const uint4& yq) {
+    float2 gf[4], yf[4];
+    unpack_bf8_2(gmq, gf);
+    unpack_bf8_2(yq, yf);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 r2 = __ffma2_rn(gf[i], k1d[i], __ffma2_rn(yf[i], k2[i], k3[i]));
+      ow[i] = pack_bf2(r2.x, r2.y);
+    }
+    *reinterpret_cast<uint4*>(dst) = o;
+  };
+#pragma unroll
+  for (int k = 0; k < REGI; ++k) {
+    if (k < cnt) {
+      if (DROP && k == kb) next_sample2();
+      proc2(dyp + (size_t)k * dys, cg[k], cy[k]);
+    }
+  }
+  char* od = dyp + (size_t)REGI * dys;
+  {
+    const int ncc = ns < nc ? ns : nc;
+    for (int j = 0; j < ncc; ++j) {
+      if (DROP && REGI + j == kb) next_sample2();
+      proc2(od, *reinterpret_cast<const uint4*>(s_mine + (size_t)(2 * j) * SLOT), *reinterpret_cast<const uint4*>(s_mine + (size_t)(2 * j + 1) * SLOT));
+      od += dys;
+    }
+  }
+  {
+    int con_r = 0;
+    for (int j = nc; j < ns; ++j) {
+      issue2();
+      cp_async_wait<BL_D - 1>();
+      const int gsl = p.ring_gy + 2 * con_r;
+      uint4 gq = *reinterpret_cast<const uint4*>(s_mine + (size_t)gsl * SLOT);
+      const uint4 yq = *reinterpret_cast<const uint4*>(s_mine + (size_t)(gsl + 1) * SLOT);
+      con_r = con_r + 1 == BL_D ? 0 : con_r + 1;
+      if (MODE == BN_MASK_AFFINE) {            // redo the mask
+        float2 yf[4], sc[4], sh[4];
+        unpack_bf8_2(yq, yf);
+        ld8_as_f2(s_coef + c0, sc);
+        ld8_as_f2(s_coef + C + c0, sh);
+        uint32_t* gw = reinterpret_cast<uint32_t*>(&gq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 z = __ffma2_rn(yf[i], sc[i], sh[i]);
+          const uint32_t lo = z.x > 0.f ? 0x0000FFFFu : 0u, hi = z.y > 0.f ? 0xFFFF0000u : 0u;
+          gw[i] &= lo | hi;
+        }
+      }
+      if (DROP && REGI + j == kb) next_sample2();
+      proc2(od, gq, yq);
+      od += dys;
+    }
+  }
+  cp_async_wait<0>();
+  bn_stamp(6);
+}
+
+template <int MODE, bool DROP>
+static int launch_bn_bwd_lean(BnBwdFusedParams p, cudaStream_t stream) {
+  constexpr int REGI = 6;
+  const BsLaunch l = bs_launch(p.C, p.n_px, 1);
+  if (DROP && l.px_per_block > p.HW) return 1;      // a thread's items must cross at most one sample boundary
+  const int lanes = BS_THREADS / (p.C / 8);
+  const int items = l.px_per_block / lanes;
+  const int ns = items > REGI ? items - REGI : 0;
+  const size_t fixed = (size_t)(5 * p.C + (BS_THREADS / 32) * 2 * p.C) * sizeof(float);
+  const size_t slot_bytes = (size_t)BS_THREADS * 16;
+  const size_t budget = 220 * 1024;
+  const int slots = (int)((budget - fixed) / slot_bytes);
+  const int mask_slots = MODE == BN_MASK_TENSOR ? BL_D : 0;
+  int cache_items = ns;
+  if (2 * cache_items + mask_slots > slots) {       // not everything fits: the rest goes through a (g, y) ring and is read again in phase 2
+    cache_items = (slots - mask_slots - 2 * BL_D) / 2;
+    if (cache_items < 0) return 1;
+  }
+  const bool ring = cache_items < ns;
+  p.smem_items = cache_items;
+  p.ring_gy = 2 * cache_items;
+  p.ring_m = 2 * cache_items + (ring ? 2 * BL_D : 0);
+  const int used = p.ring_m + mask_slots;
+  const size_t smem = fixed + (size_t)used * slot_bytes;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  auto kern = bn_bwd_lean_kernel<MODE, DROP, REGI>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) return -1;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BS_THREADS, smem) != cudaSuccess) return -1;
+  if (occ < 1 || (long long)l.grid > (long long)occ * sms) return 1;
+  p.px_per_block = l.px_per_block;
+  launch_pdl(bn_bwd_lean_kernel<MODE, DROP, REGI>, dim3(l.grid), dim3(BS_THREADS), smem, stream, p);
+  return 0;
 }
 
 constexpr int BF_REGI = 6;
@@ -620,6 +991,10 @@ static int launch_bn_bwd_fused(BnBwdFusedParams p, cudaStream_t stream) {
 
 using namespace erfk;
 
+extern "C" int erf_bn_set_debug(unsigned long long* buf) {   // tools only: [grid][8] globaltimer stamps per launch (nullptr switches it off)
+  return cudaMemcpyToSymbol(g_bn_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
+}
+
 static bool fused_disabled() {
   static const bool off = getenv("ERF_BN_FUSED") && atoi(getenv("ERF_BN_FUSED")) == 0;
   return off;
@@ -659,6 +1034,15 @@ extern "C" int erf_bn_bwd_fused(const void* g, int g_ld, const void* y, int y_ld
                                 const float* drop, const float* gamma, const float* mean, const float* invstd, double* sums, unsigned* counter, int N,
                                 int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked, int gmasked_ld, int dtype,
                                 erf_stream_t stream) {
+  return erf_bn_bwd_fused_spread(g, g_ld, y, y_ld, mask, mask_ld, beta_for_mask, drop, gamma, mean, invstd, sums, 1, counter, N, HW, C, dy, dy_ld, dgamma, dbeta,
+                                 gmasked, gmasked_ld, dtype, stream);
+}
+
+extern "C" int erf_bn_bwd_fused_spread(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* beta_for_mask,
+                                       const float* drop, const float* gamma, const float* mean, const float* invstd, double* sums, int sum_copies,
+                                       unsigned* counter, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked,
+                                       int gmasked_ld, int dtype, erf_stream_t stream) {
+  ERF_CHECK_ARG(sum_copies >= 1 && sum_copies <= 64, "erf_bn_bwd_fused: sum_copies=%d must be in [1, 64]", sum_copies);
   ERF_CHECK_ARG(dtype == ERF_F32 || dtype == ERF_BF16, "erf_bn_bwd_fused: bad dtype %d", dtype);
   ERF_CHECK_ARG(g && y && gamma && mean && invstd && sums && counter && dy && N > 0 && HW > 0, "erf_bn_bwd_fused: bad arguments");
   ERF_CHECK_ARG(!beta_for_mask || (mask && !drop), "erf_bn_bwd_fused: the mask can only be recomputed from y for a plain BN -> ReLU (mask tensor still required as the fallback operand, no dropout)");
@@ -673,20 +1057,31 @@ extern "C" int erf_bn_bwd_fused(const void* g, int g_ld, const void* y, int y_ld
     p.ring_gy = p.ring_m = 0;
     p.HW = HW; p.n_px = (long long)N * HW;
     p.C = C; p.px_per_block = 0; p.smem_items = 0;
-    p.sums = sums; p.counter = counter;
+    p.sums = sums; p.sum_copies = sum_copies; p.counter = counter;   // only the lean kernel spreads; the others use copy 0
     p.dy = dy; p.dy_ld = dy_ld; p.dgamma = dgamma; p.dbeta = dbeta; p.gmasked = gmasked; p.gmasked_ld = gmasked_ld;
     static const int v1 = getenv("ERF_BN_V1") ? atoi(getenv("ERF_BN_V1")) : 0;   // 1: the register / LDG kernel also for bf16 (experiments)
+    const char* lean_env = getenv("ERF_BN_LEAN");   // read per call: tests and tools switch kernels inside one process
+    const bool lean_ok = !(lean_env && atoi(lean_env) == 0) && ((uintptr_t)mean % 16) == 0 && ((uintptr_t)drop % 16) == 0 && (C % 8) == 0;
     int rc;
     if (dtype == ERF_F32)
       rc = launch_bn_bwd_fused<float, 2>(p, (cudaStream_t)stream);
     else if (v1)
       rc = launch_bn_bwd_fused<__nv_bfloat16, 2>(p, (cudaStream_t)stream);
-    else if (!mask)
-      rc = launch_bn_bwd_fused_bf16<BN_MASK_NONE>(p, (cudaStream_t)stream);
-    else if (beta_for_mask)
-      rc = launch_bn_bwd_fused_bf16<BN_MASK_AFFINE>(p, (cudaStream_t)stream);
-    else
-      rc = launch_bn_bwd_fused_bf16<BN_MASK_TENSOR>(p, (cudaStream_t)stream);
+    else {
+      rc = 1;   // 1 = this kernel does not take the case, try the next one
+      if (lean_ok && mask && beta_for_mask && !gmasked && !drop)
+        rc = launch_bn_bwd_lean<BN_MASK_AFFINE, false>(p, (cudaStream_t)stream);
+      else if (lean_ok && mask && !beta_for_mask && gmasked)
+        rc = drop ? launch_bn_bwd_lean<BN_MASK_TENSOR, true>(p, (cudaStream_t)stream) : launch_bn_bwd_lean<BN_MASK_TENSOR, false>(p, (cudaStream_t)stream);
+      if (rc == 1) {
+        if (!mask)
+          rc = launch_bn_bwd_fused_bf16<BN_MASK_NONE>(p, (cudaStream_t)stream);
+        else if (beta_for_mask)
+          rc = launch_bn_bwd_fused_bf16<BN_MASK_AFFINE>(p, (cudaStream_t)stream);
+        else
+          rc = launch_bn_bwd_fused_bf16<BN_MASK_TENSOR>(p, (cudaStream_t)stream);
+      }
+    }
     if (rc == 0) {
       ERF_CHECK_LAUNCH("erf_bn_bwd_fused");
       return ERF_OK;

@@ -892,7 +892,7 @@ class ScratchArena:
     FlatAdamTrainer so that the 39 BN-backward reductions of a step do not each launch their own fill kernel (which is also a full
     serialisation point between programmatically dependent kernels)."""
 
-    def __init__(self, device, n=32768):
+    def __init__(self, device, n=131072):
         self.buf = torch.zeros(n, device=device, dtype=torch.float64)
         self.cursor = 0
 
@@ -952,6 +952,9 @@ WGRAD_SIDE_STREAM = os.environ.get("ERF_WGRAD_SIDE", "0") != "0"   # ERF_WGRAD_S
 MASK_FROM_Y = True   # BN -> ReLU without dropout / residual: the backward kernel recomputes the ReLU mask from y (one tensor read less)
 
 
+BN_SUM_COPIES = int(os.environ.get("ERF_BN_SUM_COPIES", "8"))   # zeroed copies of the BN-backward sums: CTA b adds into copy b % K (spreads same-address atomics)
+
+
 def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbeta_out=None, want_masked=False, beta_for_mask=None):
     """Returns (dy, dgamma, dbeta) for y_bn = gamma*(y-mean)*invstd+beta, upstream grad g*(mask>0)*drop[n,c].
     dgamma/dbeta are WRITTEN into dgamma_out/dbeta_out when given (one BN contributes once per step).
@@ -959,11 +962,12 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbe
     beta_for_mask: this BN's beta, given when mask == relu(BN(y)) exactly (no dropout, no residual): the bf16 kernel may then recompute
     the mask from y instead of reading the mask tensor."""
     n, h, w, c = y.shape
-    sums = ARENA.take(2 * c + 1) if (ARENA is not None and ARENA.buf.device == y.device) else None     # [2C] sums + the grid-barrier counter
+    K = BN_SUM_COPIES
+    sums = ARENA.take(K * 2 * c + 1) if (ARENA is not None and ARENA.buf.device == y.device) else None     # [K][2C] sums + the grid-barrier counter
     if sums is None:
-        sums = _BN_SUMS.get((y.device, c))
+        sums = _BN_SUMS.get((y.device, c, K))
         if sums is None:
-            sums = _BN_SUMS[(y.device, c)] = torch.zeros(2 * c + 1, device=y.device, dtype=torch.float64)
+            sums = _BN_SUMS[(y.device, c, K)] = torch.zeros(K * 2 * c + 1, device=y.device, dtype=torch.float64)
         else:
             sums.zero_()
     L = _lib.lib()
@@ -974,9 +978,9 @@ def bn_bwd(g, y, gamma, mean, invstd, mask=None, drop=None, dgamma_out=None, dbe
         gm = torch.empty_like(y) if want_masked else None
         bfm = beta_for_mask if (MASK_FROM_Y and mask is not None and drop is None) else None
         with _timed(f"bn_bwd[C={c}{' +drop' if drop is not None else ''}{' +gm' if want_masked else ''}{' y-mask' if bfm is not None else ''}]" if DETAIL else "bn_bwd"):
-            check(L.erf_bn_bwd_fused(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(bfm), _p(drop), _p(gamma), _p(mean),
-                                     _p(invstd), _p(sums), C.c_void_p(sums.data_ptr() + 16 * c), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta), _p(gm), c,
-                                     dt(y), _stream(y)))
+            check(L.erf_bn_bwd_fused_spread(_p(g), g.shape[-1], _p(y), c, _p(mask), 0 if mask is None else mask.shape[-1], _p(bfm), _p(drop), _p(gamma), _p(mean),
+                                            _p(invstd), _p(sums), K, C.c_void_p(sums.data_ptr() + 16 * c * K), n, h * w, c, _p(dy), c, _p(dgamma), _p(dbeta),
+                                            _p(gm), c, dt(y), _stream(y)))
         _count()
         return (dy, dgamma, dbeta, gm) if want_masked else (dy, dgamma, dbeta)
     dy = torch.empty_like(y)

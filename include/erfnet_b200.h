@@ -165,6 +165,12 @@ int erf_bn_bwd_fused(const void* g, int g_ld, const void* y, int y_ld, const voi
                      const float* drop, const float* gamma, const float* mean, const float* invstd, double* sums, unsigned* counter,
                      int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked, int gmasked_ld,
                      int dtype, erf_stream_t stream);
+/* The same with `sum_copies` >= 1 zeroed copies of the sums (fp64 [sum_copies][2C]): CTA b accumulates into copy b % sum_copies and phase 2 adds the
+ * copies up -- 148 fp64 atomics on one address serialise in the L2 (~3 us at the end of phase 1, tools/timeline_bn.py); 8 copies hide that. */
+int erf_bn_bwd_fused_spread(const void* g, int g_ld, const void* y, int y_ld, const void* mask, int mask_ld, const float* beta_for_mask,
+                            const float* drop, const float* gamma, const float* mean, const float* invstd, double* sums, int sum_copies,
+                            unsigned* counter, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked,
+                            int gmasked_ld, int dtype, erf_stream_t stream);
 
 /* ---- CrossEntropyLoss2d (train/evaluation_functions.py:6-14) ------------------------------------------- */
 /* logits element (p, c): NHWC -> logits[p*ld + c]; NCHW (nchw_hw > 0) -> logits[(p/hw)*C*hw + c*hw + p%hw].

@@ -36,7 +36,7 @@ def _ref_forward(x, gamma, beta, drop, res, relu):
 
 # sizes: the bench tensors' channel counts at small extents, a ragged pixel count, and one large enough that a thread owns more items
 # than the backward kernel can keep on chip (the re-read path)
-CASES = [(2, 8, 16, 128), (1, 7, 9, 64), (3, 16, 32, 16), (2, 64, 128, 64), (6, 128, 256, 64)]
+CASES = [(2, 8, 16, 128), (1, 7, 9, 64), (3, 16, 32, 16), (2, 64, 128, 64), (6, 128, 256, 64), (5, 40, 100, 64), (3, 50, 60, 16)]
 
 
 @pytest.mark.parametrize("shape", CASES)
@@ -79,7 +79,7 @@ def test_bn_forward_single_launch(shape, dtype, with_drop, with_res):
 
 @pytest.mark.parametrize("shape", CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("with_drop,want_masked", [(False, False), (True, True)])
+@pytest.mark.parametrize("with_drop,want_masked", [(False, False), (True, True), (False, True)])
 def test_bn_backward_single_launch(shape, dtype, with_drop, want_masked):
     n, h, w, c = shape
     y = _rand(shape, 11, dtype)                       # pre-BN activation
