@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liberfnet_b200.so")
+# ERF_TIMELINE=1 (tools/timeline_*.py, tools/trace_step_conv1d.py) loads the build whose kernels carry the per-CTA phase stamps; the
+# product library has them compiled out (measured: the stamps' loads of the table pointer cost ~2 % of a training step, ~3 % of a forward)
+LIB_PATH = os.path.join(_HERE, "lib", "liberfnet_b200_trace.so" if os.environ.get("ERF_TIMELINE", "0") == "1" else "liberfnet_b200.so")
 
 ERF_F32, ERF_BF16 = 0, 1
 

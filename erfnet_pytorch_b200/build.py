@@ -28,18 +28,36 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+TRACE_LIB_PATH = os.path.join(LIB_DIR, "liberfnet_b200_trace.so")
+TRACED = ("conv1d_tc.cu", "bn_fused.cu")   # sources with per-CTA timeline stamps (compiled in only for the trace library)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """liberfnet_b200.so (timeline stamps compiled out: ERF_NO_TIMELINE) and liberfnet_b200_trace.so (the same objects except the
+    instrumented kernels, for the tools under ERF_TIMELINE=1)."""
     os.makedirs(LIB_DIR, exist_ok=True)
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "erfnet_b200.h")]
-    objs, jobs = [], []
+    # a change of the compile flags (or of this recipe) rebuilds everything
+    stamp = os.path.join(build_dir, "flags.txt")
+    recipe = " ".join(FLAGS) + " | main: -DERF_NO_TIMELINE | trace: " + " ".join(TRACED)
+    if not os.path.exists(stamp) or open(stamp).read() != recipe:
+        force = True
+    objs, trace_objs, jobs = [], [], []
     for s in srcs:
         o = os.path.join(build_dir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([NVCC] + FLAGS + ["-c", s, "-o", o])
+            jobs.append([NVCC] + FLAGS + ["-DERF_NO_TIMELINE", "-c", s, "-o", o])
+        if os.path.basename(s) in TRACED:
+            ot = o[:-2] + "_trace.o"
+            trace_objs.append(ot)
+            if force or _stale(ot, [s] + hdrs):
+                jobs.append([NVCC] + FLAGS + ["-c", s, "-o", ot])
+        else:
+            trace_objs.append(o)
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,12 +72,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     raise RuntimeError(f"nvcc failed for {cmd[-3]}")
                 with open(cmd[-1][:-2] + ".ptxas.log", "w") as f:
                     f.write(r.stderr)
-    if jobs or force or _stale(LIB_PATH, objs):
-        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("link failed")
+    with open(stamp, "w") as f:
+        f.write(recipe)
+    for path, members in ((LIB_PATH, objs), (TRACE_LIB_PATH, trace_objs)):
+        if jobs or force or _stale(path, members):
+            cmd = [NVCC, "-shared", "-o", path] + members + ["-gencode", "arch=compute_100a,code=sm_100a"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("link failed")
     return LIB_PATH
 
 

@@ -331,11 +331,13 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
 // Timeline instrumentation (tools/timeline_bn.py): when a buffer is registered every CTA records globaltimer stamps (ns) of its phases.
 __device__ unsigned long long* g_bn_dbg = nullptr;
 __device__ __forceinline__ void bn_stamp(int k) {
+#ifndef ERF_NO_TIMELINE
   if (g_bn_dbg && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     g_bn_dbg[(size_t)blockIdx.x * 8 + k] = t;
   }
+#endif
 }
 
 template <int MODE, int REGI>

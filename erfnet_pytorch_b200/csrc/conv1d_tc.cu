@@ -42,13 +42,31 @@ struct Conv1dTcParams {
   int sub_bytes;                // pitch of one k-chunk sub-tile inside a slot
   double* stats;                // [2C] += per-channel sum / sum of squares of the stored output (BN batch statistics), or null
   float* colsum;                // [C]  += per-channel sum of the stored output (bias gradient of the producing conv), or null
+  int dbg_launch;               // timeline instrumentation: row block of this launch in the debug table
 };
 
-// Timeline instrumentation (tools/timeline_conv1d.py): when a buffer is registered every CTA records SM-clock stamps of its phases.
+// Timeline instrumentation (tools/timeline_conv1d.py, tools/trace_step_conv1d.py): when a buffer is registered every CTA records SM-clock stamps
+// of its phases into row [launch][blockIdx.x] of a [launches][kDbgRows][kDbgCols] table (columns 0-7 clock64, 8 / 9 = globaltimer at entry /
+// exit, comparable across CTAs and launches; row kDbgRows - 1 = the launch's shape).  The launch index is handed out by the host per call.
+constexpr int kDbgRows = 300, kDbgCols = 10;
 __device__ unsigned long long* g_conv1d_dbg = nullptr;
-__device__ __forceinline__ void dbg_stamp(int k) {
-  if (g_conv1d_dbg) g_conv1d_dbg[(size_t)blockIdx.x * 8 + k] = (unsigned long long)clock64();
+static bool h_conv1d_dbg = false;
+static int h_conv1d_dbg_launches = 1, h_conv1d_dbg_next = 0;
+__device__ __forceinline__ unsigned long long dbg_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
+// (nothing is evaluated unless a table is registered: reading %globaltimer takes a sizeable fraction of a microsecond)
+#ifdef ERF_NO_TIMELINE
+#define dbg_stamp(k) do { } while (0)
+#else
+#define dbg_stamp(k)                                                                                                                 \
+  do {                                                                                                                                \
+    unsigned long long* dbg_ = g_conv1d_dbg;                                                                                          \
+    if (dbg_) dbg_[((size_t)p.dbg_launch * kDbgRows + blockIdx.x) * kDbgCols + (k)] = (k) >= 8 ? dbg_globaltimer() : (unsigned long long)clock64(); \
+  } while (0)
+#endif
 
 constexpr int kMaxSlots = 8;
 constexpr int kThreads = 384;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warps 10-11 per-channel statistics
@@ -60,8 +78,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
-template <int C>
-__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+template <int C, bool RED>
+__global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                            const __grid_constant__ CUtensorMap tmap_aux, const Conv1dTcParams p) {
   constexpr int CH = C < 64 ? C : 64;           // channels per K chunk (one swizzle row)
   constexpr int RB = CH * 2;                    // bytes per pixel row of a chunk: 128 (128B swizzle) or 32 (32B swizzle, C = 16)
@@ -77,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   constexpr int EW = C >= 32 ? 32 : 16;         // epilogue column chunk
   // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) of the STORED output are taken by warps 10-11 from the
   // staged bf16 sub-tiles (see their role below).
-  constexpr bool RED = true;
+  // RED = false (no statistics requested: inference, the plain convs of a training step) compiles that role out.
   constexpr uint32_t TMEM_COLS = C == 128 ? 256 : (C == 64 ? 128 : 32);   // two accumulators of C columns
   constexpr uint32_t IDESC = make_idesc_bf16(128, C);
   extern __shared__ uint8_t smem_raw[];
@@ -92,7 +110,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   __shared__ float s_stat[2][2 * C];                // per statistics warp: [C] sums, [C] sums of squares
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) dbg_stamp(0);
+  if (tid == 0) {
+    dbg_stamp(0);
+    dbg_stamp(8);
+    if (g_conv1d_dbg && blockIdx.x == 0) {
+      unsigned long long* m = g_conv1d_dbg + ((size_t)p.dbg_launch * kDbgRows + (kDbgRows - 1)) * kDbgCols;
+      m[0] = C; m[1] = p.horizontal; m[2] = p.dil; m[3] = p.aux_mode; m[4] = (p.stats ? 1 : 0) | (p.colsum ? 2 : 0); m[5] = p.units; m[6] = gridDim.x;
+    }
+  }
   pdl_trigger();   // the set-up below overlaps the previous kernel's tail; nothing before pdl_wait() touches tensors an earlier kernel writes
   for (int i = tid; i < C; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   const bool want_red = RED && (p.stats != nullptr || p.colsum != nullptr);
@@ -249,14 +274,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
     // (+5 us per launch, 34 launches per step).  Two warps reading the staged bf16 tile back -- one conflict-free 4-byte word per lane
     // and pixel row, 64 rows each -- cost ~220 issue slots per scheduler and sub-tile and leave the tensor pipe to the convolution.
     if (want_red) {
+      // 16-byte loads: a lane owns ONE logical 16-byte chunk (8 channels) and reads it from 32 / CPR consecutive rows per instruction -- the
+      // lanes of a row cover the whole (swizzled) row, so the access is conflict-free -- and accumulates in packed fp32x2.  (The first version
+      // read one 4-byte word per lane and row: ~800 instructions per warp and sub-tile; the in-situ timeline, tools/trace_step_conv1d.py,
+      // showed the statistics warps setting the pace of every launch that had them and ~4 us of extra tail.)
       const int sw = warp - 10;                       // rows [64*sw, 64*sw + 64) of every sub-tile
-      constexpr int LPR = RB / 4;                     // lanes per pixel row: 32 (one 128-byte row per load) or 8 (four 32-byte rows per load)
-      constexpr int RPI = 32 / LPR;                   // rows per load instruction
-      const int wl = lane % LPR;                      // 4-byte word of the row = channel pair (2*wl, 2*wl + 1)
-      const int jl = wl >> 2;                         // logical 16-byte chunk holding that word
-      float s0[KC], s1[KC], q0[KC], q1[KC];
+      constexpr int RPI = 32 / CPR;                   // rows per load instruction: 4 (128-byte rows) or 16 (32-byte rows)
+      const int jl = lane % CPR;                      // logical 16-byte chunk = channels 8*jl .. 8*jl + 7 of the k-chunk
+      const int rl = lane / CPR;
+      float2 sa[KC][4], qa[KC][4];
 #pragma unroll
-      for (int kc = 0; kc < KC; ++kc) s0[kc] = s1[kc] = q0[kc] = q1[kc] = 0.f;
+      for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sa[kc][e] = qa[kc][e] = make_float2(0.f, 0.f);
       int cnt[2] = {0, 0};
       uint32_t ph[4] = {0, 0, 0, 0};
       int i = 0;
@@ -270,36 +300,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
           ph[g * 2 + b] ^= 1;
           const uint8_t* tile = s_stg + (g * 2 + b) * STG_PAD;
           const int vrows = min(128, p.W - (u % segs) * 128);      // pixel rows of this unit inside the image (ragged last segment)
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;   // two independent chains per value
-#pragma unroll 8
-          for (int it = 0; it < 64 / RPI; it += 2) {
-            const int r0 = sw * 64 + it * RPI + lane / LPR, r1 = r0 + RPI;
-            const int k0 = CPR == 8 ? (r0 & 7) : ((r0 >> 2) & 1), k1 = CPR == 8 ? (r1 & 7) : ((r1 >> 2) & 1);
-            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile + r0 * RB + ((jl ^ k0) * 16) + (wl & 3) * 4);
-            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(tile + r1 * RB + ((jl ^ k1) * 16) + (wl & 3) * 4);
-            const float x0 = r0 < vrows ? __uint_as_float(w0 << 16) : 0.f, y0 = r0 < vrows ? __uint_as_float(w0 & 0xFFFF0000u) : 0.f;
-            const float x1 = r1 < vrows ? __uint_as_float(w1 << 16) : 0.f, y1 = r1 < vrows ? __uint_as_float(w1 & 0xFFFF0000u) : 0.f;
-            a0 += x0; a1 += y0; b0 = fmaf(x0, x0, b0); b1 = fmaf(y0, y0, b1);
-            c0 += x1; c1 += y1; d0 = fmaf(x1, x1, d0); d1 = fmaf(y1, y1, d1);
+          float2 s2[4], q2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s2[e] = q2[e] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 64 / RPI; ++it) {
+            const int r = sw * 64 + it * RPI + rl;
+            const int key = CPR == 8 ? (r & 7) : ((r >> 2) & 1);
+            uint4 w4 = *reinterpret_cast<const uint4*>(tile + r * RB + ((jl ^ key) * 16));
+            if (r >= vrows) w4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 v = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xFFFF0000u));
+              s2[e] = __fadd2_rn(s2[e], v);
+              q2[e] = __ffma2_rn(v, v, q2[e]);
+            }
           }
-          s0[kc] += a0 + c0; s1[kc] += a1 + c1; q0[kc] += b0 + d0; q1[kc] += b1 + d1;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            sa[kc][e] = __fadd2_rn(sa[kc][e], s2[e]);
+            qa[kc][e] = __fadd2_rn(qa[kc][e], q2[e]);
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&sdone_bar[g * 2 + b]);     // this warp has read the sub-tile (the barrier counts both statistics warps)
         }
       }
-      // combine: lanes sharing a channel pair (C = 16: four groups of 8 lanes), then the two warps through shared memory, one atomic per channel
+      // combine: lanes sharing a chunk (same lane % CPR), then the two warps through shared memory, one atomic per channel
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
-        for (int off = LPR; off < 32; off <<= 1) {
-          s0[kc] += __shfl_xor_sync(0xffffffffu, s0[kc], off);
-          s1[kc] += __shfl_xor_sync(0xffffffffu, s1[kc], off);
-          q0[kc] += __shfl_xor_sync(0xffffffffu, q0[kc], off);
-          q1[kc] += __shfl_xor_sync(0xffffffffu, q1[kc], off);
-        }
-        if (lane < LPR) {
-          const int c = kc * CH + 2 * wl;
-          s_stat[sw][c] = s0[kc]; s_stat[sw][c + 1] = s1[kc];
-          s_stat[sw][C + c] = q0[kc]; s_stat[sw][C + c + 1] = q1[kc];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          for (int off = CPR; off < 32; off <<= 1) {
+            sa[kc][e].x += __shfl_xor_sync(0xffffffffu, sa[kc][e].x, off);
+            sa[kc][e].y += __shfl_xor_sync(0xffffffffu, sa[kc][e].y, off);
+            qa[kc][e].x += __shfl_xor_sync(0xffffffffu, qa[kc][e].x, off);
+            qa[kc][e].y += __shfl_xor_sync(0xffffffffu, qa[kc][e].y, off);
+          }
+          if (lane < CPR) {
+            const int c = kc * CH + 8 * jl + 2 * e;
+            s_stat[sw][c] = sa[kc][e].x; s_stat[sw][c + 1] = sa[kc][e].y;
+            s_stat[sw][C + c] = qa[kc][e].x; s_stat[sw][C + c + 1] = qa[kc][e].y;
+          }
         }
       }
       asm volatile("bar.sync 5, 64;" ::: "memory");               // the two statistics warps
@@ -434,7 +476,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(const __grid_con
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();
   __syncthreads();
-  if (tid == 0) dbg_stamp(7);
+  if (tid == 0) {
+    dbg_stamp(7);
+    dbg_stamp(9);
+  }
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -473,7 +518,11 @@ static int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 
 using namespace erfk;
 
-extern "C" int erf_conv1d_tc_set_debug(unsigned long long* buf) {   // tools only: [grid][8] clock stamps per launch (nullptr switches it off)
+// tools only: buf = [launches][300][10] u64 (nullptr switches it off); launch k of the calls that follow writes row block k % launches
+extern "C" int erf_conv1d_tc_set_debug(unsigned long long* buf, int launches) {
+  h_conv1d_dbg = buf != nullptr;
+  h_conv1d_dbg_launches = launches > 0 ? launches : 1;
+  h_conv1d_dbg_next = 0;
   return cudaMemcpyToSymbol(g_conv1d_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
 }
 
@@ -509,6 +558,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   p.aux_mode = res ? 1 : (mask ? 2 : 0);
   p.stats = stats;
   p.colsum = colsum;
+  p.dbg_launch = h_conv1d_dbg ? (h_conv1d_dbg_next++ % h_conv1d_dbg_launches) : 0;
   p.units = N * H * ((W + 127) / 128);
   if (horizontal) {
     p.sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;
@@ -535,17 +585,19 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   int grid = p.units < sms * per_sm ? p.units : sms * per_sm;
   cudaError_t e;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool red = stats != nullptr || colsum != nullptr;
+#define CONV1D_LAUNCH(C_, RED_)                                                                                                       \
+  e = cudaFuncSetAttribute(conv1d_tc_kernel<C_, RED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+  if (e == cudaSuccess && C_ == 16) e = prefer_max_smem(conv1d_tc_kernel<C_, RED_>);                                                  \
+  if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<C_, RED_>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
   if (C == 16) {
-    e = cudaFuncSetAttribute(conv1d_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = prefer_max_smem(conv1d_tc_kernel<16>);
-    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<16>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+    if (red) { CONV1D_LAUNCH(16, true) } else { CONV1D_LAUNCH(16, false) }
   } else if (C == 64) {
-    e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<64>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+    if (red) { CONV1D_LAUNCH(64, true) } else { CONV1D_LAUNCH(64, false) }
   } else {
-    e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<128>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+    if (red) { CONV1D_LAUNCH(128, true) } else { CONV1D_LAUNCH(128, false) }
   }
+#undef CONV1D_LAUNCH
   if (e != cudaSuccess) {
     set_error("erf_conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return ERF_ERR_CUDA;

@@ -7,6 +7,8 @@ import sys
 
 import torch
 
+os.environ["ERF_TIMELINE"] = "1"   # the instrumented build of the library (erfnet_pytorch_b200/_lib.py)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from erfnet_pytorch_b200 import _lib, ops  # noqa: E402
 

@@ -7,13 +7,15 @@ import sys
 
 import torch
 
+os.environ["ERF_TIMELINE"] = "1"   # the instrumented build of the library (erfnet_pytorch_b200/_lib.py)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from erfnet_pytorch_b200 import _lib, ops  # noqa: E402
 
 L = _lib.lib()
-L.erf_conv1d_tc_set_debug.argtypes = [C.c_void_p]
+L.erf_conv1d_tc_set_debug.argtypes = [C.c_void_p, C.c_int]
 L.erf_conv1d_tc_set_debug.restype = C.c_int
-buf = torch.zeros(296 * 8, device="cuda", dtype=torch.int64)
+buf = torch.zeros(300 * 10, device="cuda", dtype=torch.int64)
 for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
     for horizontal in (False, True):
         for aux in ("none", "res", "mask", "stats"):
@@ -28,14 +30,14 @@ for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
                 ops.conv1d_tc(x, img, bias, horizontal, 1, relu=True, **kw)
             torch.cuda.synchronize()
             buf.zero_()
-            L.erf_conv1d_tc_set_debug(C.c_void_p(buf.data_ptr()))
+            L.erf_conv1d_tc_set_debug(C.c_void_p(buf.data_ptr()), 1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             ops.conv1d_tc(x, img, bias, horizontal, 1, relu=True, **kw)
             e1.record()
             torch.cuda.synchronize()
-            L.erf_conv1d_tc_set_debug(None)
-            t = buf.view(296, 8).cpu().double()
+            L.erf_conv1d_tc_set_debug(None, 1)
+            t = buf.view(300, 10)[:299, :8].cpu().double()
             t = t[t[:, 0] > 0]
             ghz = 1.92
             d = lambda a, b: ((t[:, b] - t[:, a]) / ghz / 1e3)       # us
