@@ -29,7 +29,7 @@ def _stale(target, deps):
 
 
 TRACE_LIB_PATH = os.path.join(LIB_DIR, "liberfnet_b200_trace.so")
-TRACED = ("conv1d_tc.cu", "bn_fused.cu")   # sources with per-CTA timeline stamps (compiled in only for the trace library)
+TRACED = ("conv1d_tc.cu", "conv1d_pair_tc.cu", "conv1d_wgrad_tc.cu", "bn_fused.cu")   # sources with per-CTA timeline stamps (compiled in only for the trace library)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -10,8 +10,8 @@
 // stage 1 of row i+1 overlap stage 2 of row i.  Versus two conv1d_tc launches: half the launches (6 us of fixed cost each at batch 6),
 // no write + re-read of the intermediate, and the same arithmetic in the same order (bit-identical results).
 //
-// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 stage-1 epilogue (TMEM -> row buffer),
-// warps 6-9 stage-2 epilogue (TMEM -> staging -> TMA store, residual tile TMA-prefetched into the staging buffer).
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups that each run both stages for
+// their own tiles of a row (stage 1: TMEM -> row buffer; stage 2: TMEM -> staging -> TMA store, residual tile TMA-prefetched into staging).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,9 +28,25 @@ struct PairParams {
   int N, H, W, dil, relu, has_res;
   int w_static;   // weight images not written by any kernel in flight (inference): copy them before pdl_wait()
   int rows, NT, slots, t_rows, t_bytes;
+  int spg;        // staging tiles per epilogue group: 2 with a residual (its tile is prefetched into the other buffer), else 1 -- the 32 KB go to the
+                  // operand ring: the timeline showed the kernel bound by bytes in flight (4 slots x 16 KB per SM / ~1.5 us = the observed 42 B/ns/SM)
 };
 
-constexpr int kPairThreads = 352, kPairMaxSlots = 8, NSTG = 4;
+constexpr int kPairThreads = 352, kPairMaxSlots = 12, NSTG = 4;   // NSTG: most staging tiles (two per epilogue group)
+
+// Timeline instrumentation (tools/timeline_pair.py; compiled in only for liberfnet_b200_trace.so): per-CTA clock64 stamps [grid][8]:
+// 0 entry, 1 after griddepcontrol.wait, 2 weights arrived, 3 first row's stage-1 MMAs issued, 4 last MMAs issued, 5 / 6 epilogue group 0 / 1
+// done, 7 exit.
+__device__ unsigned long long* g_pair_dbg = nullptr;
+#ifdef ERF_NO_TIMELINE
+#define pair_stamp(k) do { } while (0)
+#else
+#define pair_stamp(k)                                                                                  \
+  do {                                                                                                  \
+    unsigned long long* dbg_ = g_pair_dbg;                                                              \
+    if (dbg_) dbg_[(size_t)blockIdx.x * 8 + (k)] = (unsigned long long)clock64();                       \
+  } while (0)
+#endif
 
 __device__ __forceinline__ void pair_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -41,6 +57,7 @@ __device__ __forceinline__ void pair_bulk_g2s(void* smem_dst, const void* gsrc, 
 template <int C>
 __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                                         const __grid_constant__ CUtensorMap tmap_res, const PairParams p) {
+  if (threadIdx.x == 0) pair_stamp(0);
   pdl_trigger();
   constexpr int RB = C * 2;                      // bytes per pixel row (one k-chunk: C <= 64)
   constexpr int KSTEPS = C / 16;
@@ -58,7 +75,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
   uint8_t* s_w2 = s_w1 + W_PAD;
   uint8_t* s_t = s_w2 + W_PAD;                   // TB row buffers
   uint8_t* s_stg = s_t + TB * p.t_bytes;         // NSTG staging tiles
-  uint8_t* s_a = s_stg + NSTG * TILE_PAD;        // operand ring
+  uint8_t* s_a = s_stg + 2 * p.spg * TILE_PAD;   // operand ring
   __shared__ uint64_t full_bar[kPairMaxSlots], empty_bar[kPairMaxSlots], w_bar;
   __shared__ uint64_t d1_full[2], d1_empty[2], t_full[2], t_empty[2], d2_full[2], d2_empty[2], aux_bar[NSTG];
   __shared__ uint32_t tmem_base_s;
@@ -81,11 +98,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&d1_full[a], 1);
-      mbar_init(&d1_empty[a], 1);
-      mbar_init(&t_full[a], 1);
+      mbar_init(&d1_empty[a], 2);     // one arrival per epilogue group
+      mbar_init(&t_full[a], 2);
       mbar_init(&t_empty[a], 1);
       mbar_init(&d2_full[a], 1);
-      mbar_init(&d2_empty[a], 4);
+      mbar_init(&d2_empty[a], 8);     // one arrival per epilogue warp
     }
     for (int a = 0; a < NSTG; ++a) mbar_init(&aux_bar[a], 1);
     mbar_init(&w_bar, 1);
@@ -106,6 +123,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
+  if (tid == 0) pair_stamp(1);
   const int cnt = (int)blockIdx.x < p.rows ? (p.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;   // rows of this CTA
 
   if (warp == 0) {
@@ -143,7 +161,9 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
       const uint32_t w1_addr = smem_u32(s_w1), w2_addr = smem_u32(s_w2), t_addr = smem_u32(s_t);
       const uint32_t desc_hi = ((8u * RB) >> 4) | (1u << 14) | (LAYOUT << 29);
       mbar_wait(&w_bar, 0);
+      if (lane == 0) pair_stamp(2);
       for (int i = 0; i <= cnt; ++i) {
+        if (i == 1 && lane == 0) pair_stamp(3);
         if (i < cnt) {
           const int par = i & 1;
           mbar_wait(&d1_empty[par], ((i >> 1) & 1) ^ 1);
@@ -156,11 +176,14 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
               tcgen05_fence_after();
               const uint32_t a_lo = ((smem_u32(s_a + (size_t)slot * TILE_PAD) >> 4) & 0x3FFF) | (1u << 16);
               const uint32_t b_lo = (((w1_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+              if (elect_one()) {       // ONE elected region per tile: an elect per MMA cost ~25 cycles each (94 vs 70 cycles per MMA, tools/timeline_pair.py)
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                if (elect_one()) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
-                          (t | k) != 0 ? 1u : 0u);
-              if (elect_one()) umma_commit(&empty_bar[slot]);
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                            (t | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[slot]);
+              }
+              __syncwarp();
               if (++slot == p.slots) { slot = 0; phase ^= 1; }
             }
           }
@@ -173,146 +196,164 @@ __global__ void __launch_bounds__(kPairThreads, 1) conv1d_pair_tc_kernel(const _
           mbar_wait(&d2_empty[par], ((j >> 1) & 1) ^ 1);
           tcgen05_fence_after();
           const uint32_t tb = t_addr + tbi * p.t_bytes;
-          for (int m = 0; m < NT; ++m) {
-            const uint32_t d_tmem = tmem_base + ((2 + par) * NT + m) * C;
+          if (elect_one()) {
+            for (int m = 0; m < NT; ++m) {
+              const uint32_t d_tmem = tmem_base + ((2 + par) * NT + m) * C;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              // pixel q - d + t*d of the row = row buffer index q + t*d (d halo pixels in front)
-              const uint32_t a_lo = (((tb + (128 * m + t * p.dil) * RB) >> 4) & 0x3FFF) | (1u << 16);
-              const uint32_t b_lo = (((w2_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
+              for (int t = 0; t < 3; ++t) {
+                // pixel q - d + t*d of the row = row buffer index q + t*d (d halo pixels in front)
+                const uint32_t a_lo = (((tb + (128 * m + t * p.dil) * RB) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t b_lo = (((w2_addr + t * (C * RB)) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                if (elect_one()) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
-                          (t | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + k * 2), ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + k * 2), IDESC,
+                            (t | k) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(&t_empty[tbi]);
+            umma_commit(&d2_full[par]);
           }
-          if (elect_one()) umma_commit(&t_empty[tbi]);
-          if (elect_one()) umma_commit(&d2_full[par]);
+          __syncwarp();
         }
       }
+      if (lane == 0) pair_stamp(4);
     }
-  } else if (warp >= 2 && warp < 6) {
-    // ================= stage-1 epilogue: TMEM -> (+b1, ReLU, bf16) -> row buffer =================
+  } else if (warp >= 2 && warp < 10) {
+    // ================= epilogue groups: g = 0 (warps 2-5) and g = 1 (warps 6-9), TMEM lane quadrant = warp % 4 =================
+    // Both groups do BOTH stages, each for its own tiles of a row (m = g, g + 2, ...): stage 1 of row i (TMEM -> +b1, ReLU, bf16 -> row
+    // buffer), then stage 2 of row i-1 (TMEM -> +b2, +res, ReLU, bf16 -> staging -> TMA store).  The first version gave stage 1 to one group
+    // and stage 2 to the other: the per-CTA timeline (tools/timeline_pair.py) showed a row paced by max(stage-1 MMAs, stage-1 epilogue) +
+    // stage-2 MMAs with ONE group's epilogue of the whole row on the critical path (2.2 us per row against 1.7 us of MMA issue), and the
+    // residual form paced by the stage-2 group alone (2.8 us per row while the stage-1 group idled half the time).
+    const int g = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
-    for (int i = 0; i < cnt; ++i) {
-      const int par = i & 1;
-      const int tbi = i % TB;
-      mbar_wait(&d1_full[par], (i >> 1) & 1);
-      mbar_wait(&t_empty[tbi], ((i / TB) & 1) ^ 1);     // stage 2 of row i-TB has read this row buffer
-      tcgen05_fence_after();
-      uint8_t* tb = s_t + tbi * p.t_bytes;
-      for (int m = 0; m < NT; ++m) {
-        const uint32_t taddr = tmem_base + (par * NT + m) * C + ((uint32_t)(quad * 32) << 16);
-        uint32_t r[C];
-        if (C == 64) { tmem_ld32(taddr, r); tmem_ld32(taddr + 32, r + 32); }
-        else tmem_ld16(taddr, r);
-        tmem_ld_wait();
-        const int rr = p.dil + 128 * m + row;             // row-buffer index of this pixel
-        const int key = CPR == 8 ? (rr & 7) : ((rr >> 2) & 1);
-        uint8_t* my_row = tb + (size_t)rr * RB;
-#pragma unroll
-        for (int q = 0; q < CPR; ++q) {
-          uint4 t4;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + s_b1[q * 8 + 2 * e], 0.f);
-            const float b = fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + s_b1[q * 8 + 2 * e + 1], 0.f);
-            h[e] = __floats2bfloat162_rn(a, b);
-          }
-          *reinterpret_cast<uint4*>(my_row + ((q ^ key) * 16)) = t4;
-        }
-      }
-      tcgen05_fence_before();
-      fence_proxy_async_smem();                          // row-buffer writes -> visible to the UMMA (async proxy)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (leader) {
-        mbar_arrive(&t_full[tbi]);
-        mbar_arrive(&d1_empty[par]);
-      }
-    }
-  } else if (warp >= 6 && warp < 10) {
-    // ================= stage-2 epilogue: TMEM -> (+b2, +res, ReLU, bf16) -> staging -> TMA store =================
-    // One group works through every tile, so nothing else hides a TMA round trip: NSTG staging buffers let the store of step s-1
-    // still be reading while step s is staged (wait_group.read 1) and let the residual tile of step s+2 be prefetched two steps ahead.
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const bool leader = (warp == 6 && lane == 0);
+    const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
     const int sw_key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
-    uint32_t aux_phase = 0;                               // bit b: phase of aux_bar[b]
-    const int total_steps = cnt * NT;
-    auto prefetch_res = [&](int s) {                      // residual tile of step s -> staging buffer s % NSTG
-      if (s >= total_steps) return;
-      const int ii = s / NT, mm = s - ii * NT, rr = blockIdx.x + ii * gridDim.x, bb = s % NSTG;
-      mbar_arrive_expect_tx(&aux_bar[bb], (uint32_t)TILE);
-      tma_load_4d(s_stg + bb * TILE_PAD, &tmap_res, &aux_bar[bb], 0, 128 * mm, rr % p.H, rr / p.H);
+    const int tpg = (NT - g + 1) / 2;                     // tiles of a row owned by this group
+    uint8_t* stg_g = s_stg + g * p.spg * TILE_PAD;        // one or two staging tiles per group
+    uint64_t* aux_g = &aux_bar[g * 2];
+    uint32_t aux_phase = 0;                               // bit b: phase of aux_g[b]
+    const int total_steps = cnt * tpg;
+    auto prefetch_res = [&](int st) {                     // residual tile of this group's step st -> its staging buffer st & 1
+      if (st >= total_steps) return;
+      const int ii = st / tpg, mm = g + 2 * (st - ii * tpg), rr = blockIdx.x + ii * gridDim.x, bb = st & (p.spg - 1);
+      mbar_arrive_expect_tx(&aux_g[bb], (uint32_t)TILE);
+      tma_load_4d(stg_g + bb * TILE_PAD, &tmap_res, &aux_g[bb], 0, 128 * mm, rr % p.H, rr / p.H);
     };
-    if (leader && p.has_res) {
-      prefetch_res(0);
-      prefetch_res(1);
-    }
+    if (leader && p.has_res) prefetch_res(0);
     int step = 0;
-    for (int i = 0; i < cnt; ++i) {
-      const int par = i & 1;
-      const int r = blockIdx.x + i * gridDim.x, n = r / p.H, y = r % p.H;
-      mbar_wait(&d2_full[par], (i >> 1) & 1);
-      tcgen05_fence_after();
-      for (int m = 0; m < NT; ++m, ++step) {
-        const int b = step % NSTG;
-        uint8_t* my_row = s_stg + b * TILE_PAD + row * RB;
-        const uint32_t taddr = tmem_base + ((2 + par) * NT + m) * C + ((uint32_t)(quad * 32) << 16);
-        uint32_t rg[C];
-        if (C == 64) { tmem_ld32(taddr, rg); tmem_ld32(taddr + 32, rg + 32); }
-        else tmem_ld16(taddr, rg);
-        if (p.has_res) {
-          mbar_wait(&aux_bar[b], (aux_phase >> b) & 1u);
-          aux_phase ^= 1u << b;
+    for (int i = 0; i <= cnt; ++i) {
+      if (i < cnt) {
+        // ---- stage 1 of row i ----
+        const int par = i & 1;
+        const int tbi = i % TB;
+        mbar_wait(&d1_full[par], (i >> 1) & 1);
+        mbar_wait(&t_empty[tbi], ((i / TB) & 1) ^ 1);     // stage 2 of row i-TB has read this row buffer
+        tcgen05_fence_after();
+        uint8_t* tb = s_t + tbi * p.t_bytes;
+        for (int m = g; m < NT; m += 2) {
+          const uint32_t taddr = tmem_base + (par * NT + m) * C + ((uint32_t)(quad * 32) << 16);
+          uint32_t r[C];
+          if (C == 64) { tmem_ld32(taddr, r); tmem_ld32(taddr + 32, r + 32); }
+          else tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          const int rr = p.dil + 128 * m + row;             // row-buffer index of this pixel
+          const int key = CPR == 8 ? (rr & 7) : ((rr >> 2) & 1);
+          uint8_t* my_row = tb + (size_t)rr * RB;
+#pragma unroll
+          for (int q = 0; q < CPR; ++q) {
+            uint4 t4;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + s_b1[q * 8 + 2 * e], 0.f);
+              const float b = fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + s_b1[q * 8 + 2 * e + 1], 0.f);
+              h[e] = __floats2bfloat162_rn(a, b);
+            }
+            *reinterpret_cast<uint4*>(my_row + ((q ^ key) * 16)) = t4;
+          }
         }
-        tmem_ld_wait();
-        if (m == NT - 1) {                                // all TMEM reads of this row are done
+        tcgen05_fence_before();
+        fence_proxy_async_smem();                          // row-buffer writes -> visible to the UMMA (async proxy)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (leader) {
+          mbar_arrive(&t_full[tbi]);                       // both groups arrive (count 2)
+          mbar_arrive(&d1_empty[par]);
+        }
+      }
+      if (i >= 1) {
+        // ---- stage 2 of row i-1 ----
+        const int j = i - 1, par = j & 1;
+        const int r = blockIdx.x + j * gridDim.x, n = r / p.H, y = r % p.H;
+        mbar_wait(&d2_full[par], (j >> 1) & 1);
+        tcgen05_fence_after();
+        if (tpg == 0) {                                    // a group without tiles (W = 128) still releases the accumulators
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d2_empty[par]);
         }
-#pragma unroll
-        for (int q = 0; q < CPR; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rg[q * 8 + e]) + s_b2[q * 8 + e];
-          uint8_t* cptr = my_row + ((q ^ sw_key) * 16);
+        for (int m = g; m < NT; m += 2, ++step) {
+          const int b = step & (p.spg - 1);
+          uint8_t* my_row = stg_g + b * TILE_PAD + row * RB;
+          const uint32_t taddr = tmem_base + ((2 + par) * NT + m) * C + ((uint32_t)(quad * 32) << 16);
+          uint32_t rg[C];
+          if (C == 64) { tmem_ld32(taddr, rg); tmem_ld32(taddr + 32, rg + 32); }
+          else tmem_ld16(taddr, rg);
           if (p.has_res) {
-            const uint4 a4 = *reinterpret_cast<const uint4*>(cptr);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(h[e]); v[2 * e + 1] += __high2float(h[e]); }
+            mbar_wait(&aux_g[b], (aux_phase >> b) & 1u);
+            aux_phase ^= 1u << b;
           }
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          tmem_ld_wait();
+          if (p.spg == 1) {                                // single staging tile: its previous store must have read it before anyone writes
+            if (leader) tma_store_wait_read0();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           }
-          uint4 t4;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+          if (m + 2 >= NT) {                               // this group's TMEM reads of the row are done
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d2_empty[par]);
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          *reinterpret_cast<uint4*>(cptr) = t4;
-        }
-        fence_proxy_async_smem();
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // stores up to step-2 have finished reading
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (leader) {
-          tma_store_4d(&tmap_out, s_stg + b * TILE_PAD, 0, 128 * m, y, n);
-          tma_store_commit();
-          if (p.has_res) prefetch_res(step + 2);          // into the buffer whose store (step-2) is known to be done
+          for (int q = 0; q < CPR; ++q) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(rg[q * 8 + e]) + s_b2[q * 8 + e];
+            uint8_t* cptr = my_row + ((q ^ sw_key) * 16);
+            if (p.has_res) {
+              const uint4 a4 = *reinterpret_cast<const uint4*>(cptr);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(h[e]); v[2 * e + 1] += __high2float(h[e]); }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            uint4 t4;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(cptr) = t4;
+          }
+          fence_proxy_async_smem();
+          if (leader && p.spg == 2) tma_store_wait_read0();   // the store of step-1 (other buffer) has finished reading its tile
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          if (leader) {
+            tma_store_4d(&tmap_out, stg_g + b * TILE_PAD, 0, 128 * m, y, n);
+            tma_store_commit();
+            if (p.has_res) prefetch_res(step + 1);         // into the other buffer, whose store is known to be done
+          }
         }
       }
     }
     if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
+    if (leader) pair_stamp(5 + g);
   }
   // ---- teardown ----------------------------------------------------------------------------------------------------
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) pair_stamp(7);
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -343,6 +384,10 @@ static int pair_make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, i
 }  // namespace erfk
 
 using namespace erfk;
+
+extern "C" int erf_conv1d_pair_tc_set_debug(unsigned long long* buf) {   // tools only: [grid][8] clock stamps (nullptr switches it off)
+  return cudaMemcpyToSymbol(g_pair_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
+}
 
 extern "C" int erf_conv1d_pair_tc_supported(int C, int W, int dil) {
   if (!((C == 16 || C == 64) && W >= 128 && (W % 128) == 0 && dil >= 1 && dil <= 16)) return 0;
@@ -375,14 +420,16 @@ extern "C" int erf_conv1d_pair_tc(const void* in, const void* w1_img, const floa
   const int w_pad = ((3 * C * RB + 1023) / 1024) * 1024;
   const int tile_pad = ((128 * RB + 1023) / 1024) * 1024;
   const int tbufs = C == 64 ? 1 : 2;
-  const int budget = 224 * 1024 - 2 * w_pad - tbufs * p.t_bytes - NSTG * tile_pad;
+  p.spg = p.has_res ? 2 : 1;
+  // C = 16 runs two CTAs per SM: 88 KB per CTA is the largest footprint the occupancy calculator still grants two (95 KB gave one: measured)
+  const int budget = (C == 16 ? 87 : 224) * 1024 - 2 * w_pad - tbufs * p.t_bytes - 2 * p.spg * tile_pad;
   p.slots = budget / tile_pad;
   if (p.slots > kPairMaxSlots) p.slots = kPairMaxSlots;
   if (p.slots < 3) {
     set_error("erf_conv1d_pair_tc: row of %d pixels x %d channels does not fit in shared memory", W, C);
     return ERF_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)2 * w_pad + tbufs * p.t_bytes + NSTG * tile_pad + (size_t)p.slots * tile_pad + 1024;
+  const size_t smem = (size_t)2 * w_pad + tbufs * p.t_bytes + 2 * p.spg * tile_pad + (size_t)p.slots * tile_pad + 1024;
   // C = 16: ~80 KB of shared memory, 68 registers, <= 256 TMEM columns -> two CTAs per SM hide the per-row latency chain
   const int ctas = (C == 16 && smem <= 100 * 1024 && 4 * p.NT * C <= 256) ? 296 : 148;
   const int grid = p.rows < ctas ? p.rows : ctas;
@@ -390,6 +437,7 @@ extern "C" int erf_conv1d_pair_tc(const void* in, const void* w1_img, const floa
   cudaError_t e;
   if (C == 16) {
     e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && ctas == 296) e = prefer_max_smem(conv1d_pair_tc_kernel<16>);   // two CTAs per SM need the full shared-memory carveout
     if (e == cudaSuccess) launch_pdl(conv1d_pair_tc_kernel<16>, dim3(grid), dim3(kPairThreads), smem, (cudaStream_t)(st), tin, tout, tres, p);
   } else {
     e = cudaFuncSetAttribute(conv1d_pair_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

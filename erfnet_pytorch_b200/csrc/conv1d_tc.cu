@@ -20,6 +20,7 @@
 //   * the A ring works at (tap, k-chunk) granularity for vertical convs and k-chunk granularity for horizontal ones, so
 //     at C = 128 (96 KB of weights) there are still 3-4 loads in flight.
 #include <cuda.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -48,7 +49,7 @@ struct Conv1dTcParams {
 // Timeline instrumentation (tools/timeline_conv1d.py, tools/trace_step_conv1d.py): when a buffer is registered every CTA records SM-clock stamps
 // of its phases into row [launch][blockIdx.x] of a [launches][kDbgRows][kDbgCols] table (columns 0-7 clock64, 8 / 9 = globaltimer at entry /
 // exit, comparable across CTAs and launches; row kDbgRows - 1 = the launch's shape).  The launch index is handed out by the host per call.
-constexpr int kDbgRows = 300, kDbgCols = 10;
+constexpr int kDbgRows = 300, kDbgCols = 12;   // columns 10 / 11: statistics warp 10 finished its sub-tiles / issued its atomics
 __device__ unsigned long long* g_conv1d_dbg = nullptr;
 static bool h_conv1d_dbg = false;
 static int h_conv1d_dbg_launches = 1, h_conv1d_dbg_next = 0;
@@ -64,7 +65,7 @@ __device__ __forceinline__ unsigned long long dbg_globaltimer() {
 #define dbg_stamp(k)                                                                                                                 \
   do {                                                                                                                                \
     unsigned long long* dbg_ = g_conv1d_dbg;                                                                                          \
-    if (dbg_) dbg_[((size_t)p.dbg_launch * kDbgRows + blockIdx.x) * kDbgCols + (k)] = (k) >= 8 ? dbg_globaltimer() : (unsigned long long)clock64(); \
+    if (dbg_) dbg_[((size_t)p.dbg_launch * kDbgRows + blockIdx.x) * kDbgCols + (k)] = ((k) == 8 || (k) == 9) ? dbg_globaltimer() : (unsigned long long)clock64(); \
   } while (0)
 #endif
 
@@ -303,20 +304,23 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
           float2 s2[4], q2[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) s2[e] = q2[e] = make_float2(0.f, 0.f);
+          auto accumulate = [&](auto with_squares) {      // a bias gradient (colsum alone) needs no squares: one branch per sub-tile
 #pragma unroll
-          for (int it = 0; it < 64 / RPI; ++it) {
-            const int r = sw * 64 + it * RPI + rl;
-            const int key = CPR == 8 ? (r & 7) : ((r >> 2) & 1);
-            uint4 w4 = *reinterpret_cast<const uint4*>(tile + r * RB + ((jl ^ key) * 16));
-            if (r >= vrows) w4 = make_uint4(0u, 0u, 0u, 0u);
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            for (int it = 0; it < 64 / RPI; ++it) {
+              const int r = sw * 64 + it * RPI + rl;
+              const int key = CPR == 8 ? (r & 7) : ((r >> 2) & 1);
+              uint4 w4 = *reinterpret_cast<const uint4*>(tile + r * RB + ((jl ^ key) * 16));
+              if (r >= vrows) w4 = make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 v = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xFFFF0000u));
-              s2[e] = __fadd2_rn(s2[e], v);
-              q2[e] = __ffma2_rn(v, v, q2[e]);
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xFFFF0000u));
+                s2[e] = __fadd2_rn(s2[e], v);
+                if (decltype(with_squares)::value) q2[e] = __ffma2_rn(v, v, q2[e]);
+              }
             }
-          }
+          };
+          if (p.stats) accumulate(std::true_type{}); else accumulate(std::false_type{});
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             sa[kc][e] = __fadd2_rn(sa[kc][e], s2[e]);
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
           if (lane == 0) mbar_arrive(&sdone_bar[g * 2 + b]);     // this warp has read the sub-tile (the barrier counts both statistics warps)
         }
       }
+      if (warp == 10 && lane == 0) dbg_stamp(10);
       // combine: lanes sharing a chunk (same lane % CPR), then the two warps through shared memory, one atomic per channel
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc) {
@@ -353,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
           atomicAdd(&p.stats[C + c], (double)(s_stat[0][C + c] + s_stat[1][C + c]));
         }
       }
+      if (warp == 10 && lane == 0) dbg_stamp(11);
     }
   } else {
     // ================= epilogue: group 0 = warps 2..5, group 1 = warps 6..9; TMEM lane quadrant = warp % 4 =========

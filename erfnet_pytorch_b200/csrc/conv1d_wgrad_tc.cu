@@ -30,14 +30,47 @@ struct WgradTcParams {
   int stages, stage_bytes;
   int x_sub_bytes;   // pitch of one (tap, k-chunk) x sub-tile (vertical) / one k-chunk sub-tile (horizontal)
   int dy_off;        // offset of the dy tile inside a stage
+  int dbg_launch;    // timeline instrumentation: row block of this launch
 };
 
 constexpr int kWgStages = 8;
 constexpr int PX = 64;  // pixels (K) per unit
 
+// Timeline instrumentation (tools/trace_step_wgrad.py; compiled in only for liberfnet_b200_trace.so): per-CTA stamps into row
+// [launch][blockIdx.x] of a [launches][300][10] table -- columns 0-7 clock64 (0 entry, 1 after griddepcontrol.wait, 2 first unit's MMAs issued,
+// 3 last unit's MMAs issued, 4 accumulators complete, 5 last bulk reduction issued, 6 reductions complete, 7 exit), 8 / 9 globaltimer at entry /
+// exit; row 299 = the launch's shape.
+constexpr int kWgDbgRows = 300, kWgDbgCols = 10;
+__device__ unsigned long long* g_wgrad_dbg = nullptr;
+static bool h_wgrad_dbg = false;
+static int h_wgrad_dbg_launches = 1, h_wgrad_dbg_next = 0;
+#ifdef ERF_NO_TIMELINE
+#define wg_stamp(k) do { } while (0)
+#else
+#define wg_stamp(k)                                                                                                                   \
+  do {                                                                                                                                 \
+    unsigned long long* dbg_ = g_wgrad_dbg;                                                                                            \
+    if (dbg_) {                                                                                                                        \
+      unsigned long long t_;                                                                                                           \
+      if ((k) >= 8) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); else t_ = (unsigned long long)clock64();                    \
+      dbg_[((size_t)p.dbg_launch * kWgDbgRows + blockIdx.x) * kWgDbgCols + (k)] = t_;                                                  \
+    }                                                                                                                                  \
+  } while (0)
+#endif
+
 template <int C>
 __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                                                                  const WgradTcParams p) {
+  if (threadIdx.x == 0) {
+    wg_stamp(0);
+    wg_stamp(8);
+#ifndef ERF_NO_TIMELINE
+    if (g_wgrad_dbg && blockIdx.x == 0) {
+      unsigned long long* m = g_wgrad_dbg + ((size_t)p.dbg_launch * kWgDbgRows + (kWgDbgRows - 1)) * kWgDbgCols;
+      m[0] = C; m[1] = p.horizontal; m[2] = p.dil; m[3] = p.dw_bulk != nullptr; m[4] = 0; m[5] = p.units; m[6] = gridDim.x;
+    }
+#endif
+  }
   pdl_trigger();
   constexpr int CH = C < 64 ? C : 64;      // channels per chunk = one swizzle row of RB bytes
   constexpr int RB = CH * 2;
@@ -72,6 +105,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_s;
   const int segs = (p.W + PX - 1) / PX;   // the last 64-pixel unit of a row may be ragged: TMA zero-fills x and dy beyond the row, zero products
   pdl_wait();
+  if (tid == 0) wg_stamp(1);
   const int my_units = blockIdx.x < p.units ? (p.units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
@@ -131,10 +165,12 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
             if (elect_one()) umma_bf16(tmem_base + a * C, da, db, IDESC, (first && k == 0) ? 0u : 1u);
           }
         }
+        if (first && lane == 0) wg_stamp(2);
         first = false;
         if (elect_one()) umma_commit(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) wg_stamp(3);
       if (elect_one()) umma_commit(&done_bar);
     }
   } else if (p.dw_bulk != nullptr) {
@@ -152,6 +188,7 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
     if (my_units > 0) {
       mbar_wait(&done_bar, 0);
       tcgen05_fence_after();
+      if (etid == 0) wg_stamp(4);
       float* stg = reinterpret_cast<float*>(smem);
       const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
 #pragma unroll 1
@@ -207,7 +244,11 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
           tma_store_commit();
         }
       }
-      if (etid == 0) tma_store_wait0();
+      if (etid == 0) {
+        wg_stamp(5);
+        tma_store_wait0();
+        wg_stamp(6);
+      }
     }
   } else {
     // epilogue (once): dump the accumulators of this CTA
@@ -240,6 +281,10 @@ __global__ void __launch_bounds__(192, 1) conv1d_wgrad_tc_kernel(const __grid_co
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    wg_stamp(7);
+    wg_stamp(9);
+  }
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -368,6 +413,14 @@ static int make_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C,
 
 using namespace erfk;
 
+// tools only: buf = [launches][300][10] u64 (nullptr switches it off); launch k of the calls that follow writes row block k % launches
+extern "C" int erf_conv1d_wgrad_tc_set_debug(unsigned long long* buf, int launches) {
+  h_wgrad_dbg = buf != nullptr;
+  h_wgrad_dbg_launches = launches > 0 ? launches : 1;
+  h_wgrad_dbg_next = 0;
+  return cudaMemcpyToSymbol(g_wgrad_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
+}
+
 extern "C" size_t erf_conv1d_wgrad_tc_workspace(int C) {
   return (size_t)(C == 16 ? 296 : 148) * (C == 128 ? 3 : (C == 64 ? 2 : 1)) * 128 * C * sizeof(float);
 }
@@ -410,6 +463,7 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
   p.ws = (float*)workspace;
   p.N = N; p.H = H; p.W = W; p.horizontal = horizontal; p.dil = dil;
   p.units = N * H * ((W + PX - 1) / PX);
+  p.dbg_launch = h_wgrad_dbg ? (h_wgrad_dbg_next++ % h_wgrad_dbg_launches) : 0;
   int x_bytes;
   if (horizontal) {
     p.x_sub_bytes = ((((box_w + 7) / 8) * 8 * RB + 1023) / 1024) * 1024;

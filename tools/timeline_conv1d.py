@@ -15,7 +15,7 @@ from erfnet_pytorch_b200 import _lib, ops  # noqa: E402
 L = _lib.lib()
 L.erf_conv1d_tc_set_debug.argtypes = [C.c_void_p, C.c_int]
 L.erf_conv1d_tc_set_debug.restype = C.c_int
-buf = torch.zeros(300 * 10, device="cuda", dtype=torch.int64)
+buf = torch.zeros(300 * 12, device="cuda", dtype=torch.int64)
 for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
     for horizontal in (False, True):
         for aux in ("none", "res", "mask", "stats"):
@@ -37,7 +37,7 @@ for c, h, w in [(64, 128, 256), (128, 64, 128), (16, 256, 512)]:
             e1.record()
             torch.cuda.synchronize()
             L.erf_conv1d_tc_set_debug(None, 1)
-            t = buf.view(300, 10)[:299, :8].cpu().double()
+            t = buf.view(300, 12)[:299, :8].cpu().double()
             t = t[t[:, 0] > 0]
             ghz = 1.92
             d = lambda a, b: ((t[:, b] - t[:, a]) / ghz / 1e3)       # us

@@ -17,7 +17,7 @@ from erfnet_pytorch_b200 import erfnet as E  # noqa: E402
 from erfnet_pytorch_b200 import synthetic as O  # noqa: E402
 from erfnet_pytorch_b200.parallel import FlatAdamTrainer  # noqa: E402
 
-B, LAUNCHES, ROWS, COLS = 6, 136, 300, 10
+B, LAUNCHES, ROWS, COLS = 6, 136, 300, 12
 L = _lib.lib()
 L.erf_conv1d_tc_set_debug.argtypes = [C.c_void_p, C.c_int]
 L.erf_conv1d_tc_set_debug.restype = C.c_int
@@ -60,12 +60,13 @@ for k in range(LAUNCHES):
     epi_end = torch.maximum(s[:, 5], s[:, 6])
     rows.append(dict(k=k, c=c, hor=hor, dil=dil, aux=aux, red=red, upc=units / grid, start=(start - t_first) / 1e3, dur=(end - start) / 1e3,
                      gap=(start - prev_end) / 1e3 if prev_end is not None else 0.0, setup=d(0, 1), wts=d(1, 2), first=d(2, 3), loop=d(3, 4),
-                     tail=float(((epi_end - s[:, 4]) / ghz / 1e3).mean()), cta=d(0, 7), spread=float((s[:, 8].max() - s[:, 8].min()) / 1e3)))
+                     tail=float(((epi_end - s[:, 4]) / ghz / 1e3).mean()), cta=d(0, 7),
+                     st_loop=float(((s[:, 10] - s[:, 4]) / ghz / 1e3).mean()) if red else 0.0, st_atom=d(10, 11) if red else 0.0, spread=float((s[:, 8].max() - s[:, 8].min()) / 1e3)))
     prev_end = end
-print("  k   C  dir dil aux red units/CTA  start(us)  dur(us) since-prev-end | setup->wait  +weights  +firstMMA  loop   tail | CTA mean | entry spread")
+print("  k   C  dir dil aux red units/CTA  start(us)  dur(us) since-prev-end | setup->wait  +weights  +firstMMA  loop   tail | CTA mean | entry spread | stats: lastMMA->loop end, +atomics")
 for r in rows:
     print(f"{r['k']:3d} {r['c']:3d}  {'H' if r['hor'] else 'V'}  {r['dil']:3d}  {r['aux']}   {r['red']}   {r['upc']:6.1f}  {r['start']:9.1f} {r['dur']:8.1f} {r['gap']:8.1f}       | "
-          f"{r['setup']:8.2f} {r['wts']:9.2f} {r['first']:9.2f} {r['loop']:6.2f} {r['tail']:6.2f} | {r['cta']:7.2f} | {r['spread']:6.2f}")
+          f"{r['setup']:8.2f} {r['wts']:9.2f} {r['first']:9.2f} {r['loop']:6.2f} {r['tail']:6.2f} | {r['cta']:7.2f} | {r['spread']:6.2f} | {r['st_loop']:6.2f} {r['st_atom']:6.2f}")
 for c in (64, 128, 16):
     sel = [r for r in rows if r["c"] == c]
     if sel:
