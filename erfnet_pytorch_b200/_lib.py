@@ -50,6 +50,7 @@ class Im2colTaps(C.Structure):
 _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _SIGNATURES = {
     "erf_abi_version": [],
+    "erf_set_launch_cap": [_i, _i],
     "erf_conv_fwd": [_vp, _vp, _vp, C.POINTER(ConvGeom), C.POINTER(ConvEpilogue), _i, _vp],
     "erf_conv_wgrad": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _vp],
     "erf_conv_wgrad_torch": [_vp, _vp, _vp, _vp, C.POINTER(ConvGeom), _i, _i, _vp],
@@ -124,6 +125,9 @@ def exported_symbols():
     return ["erf_last_error_string"] + list(_SIGNATURES)
 
 
+_TOOLING = {"erf_set_launch_cap"}   # entry points only experiments use: an A/B against an older build may lack them
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -134,6 +138,8 @@ def lib():
         L.erf_last_error_string.restype = C.c_char_p
         L.erf_last_error_string.argtypes = []
         for name, args in _SIGNATURES.items():
+            if name in _TOOLING and not hasattr(L, name):
+                continue                       # an older build of the library under tools/ab_libs.sh
             fn = getattr(L, name)
             fn.restype = C.c_size_t if name.endswith("_workspace") else C.c_int
             fn.argtypes = args

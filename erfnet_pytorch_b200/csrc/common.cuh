@@ -151,6 +151,11 @@ static inline cudaError_t prefer_max_smem(K kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// Launch cap (erf_set_launch_cap): while weight gradients run on a second stream next to the data gradients, both kinds of kernel take only
+// part of the SMs so that they really run side by side (persistent kernels sized one CTA per SM would just queue behind each other).
+int launch_cap_main();   // CTAs per SM-slot for kernels on the main chain (0 = no cap)
+int launch_cap_side();   // ... for the weight-gradient kernels
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace erfk

@@ -44,6 +44,8 @@ struct Conv1dTcParams {
   double* stats;                // [2C] += per-channel sum / sum of squares of the stored output (BN batch statistics), or null
   float* colsum;                // [C]  += per-channel sum of the stored output (bias gradient of the producing conv), or null
   int dbg_launch;               // timeline instrumentation: row block of this launch in the debug table
+  int nb;                       // staging sub-tiles per epilogue group: 2, or 3 with a residual / mask operand (C <= 64): its tile is then prefetched TWO
+                                // steps ahead (one step = ~0.6 us is less than the L2 / DRAM round trip: the in-situ trace showed those launches 2-3 us longer)
 };
 
 // Timeline instrumentation (tools/timeline_conv1d.py, tools/trace_step_conv1d.py): when a buffer is registered every CTA records SM-clock stamps
@@ -79,7 +81,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
-template <int C, bool RED>
+template <int C, bool RED, int NB>
 __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                            const __grid_constant__ CUtensorMap tmap_aux, const Conv1dTcParams p) {
   constexpr int CH = C < 64 ? C : 64;           // channels per K chunk (one swizzle row)
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
   constexpr int W_PAD = ((W_BYTES + 1023) / 1024) * 1024;
   constexpr int STG_BYTES = 128 * RB;           // one staging sub-tile: 128 px x one k-chunk
   constexpr int STG_PAD = ((STG_BYTES + 1023) / 1024) * 1024;
-  constexpr int STG_TOTAL = 4 * STG_PAD;        // 2 epilogue groups x double buffer
+  // NB = staging sub-tiles per epilogue group: 2, or 3 with a residual / mask operand (see Conv1dTcParams::nb)
+  constexpr int STG_TOTAL = 2 * NB * STG_PAD;
   constexpr int EW = C >= 32 ? 32 : 16;         // epilogue column chunk
   // Per-channel statistics (BN sum / sum of squares, bias-gradient column sums) of the STORED output are taken by warps 10-11 from the
   // staged bf16 sub-tiles (see their role below).
@@ -104,8 +107,8 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
   uint8_t* s_w = smem;
   uint8_t* s_stg = smem + W_PAD;
   uint8_t* s_a = s_stg + STG_TOTAL;
-  __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar[4];
-  __shared__ uint64_t sfull_bar[4], sdone_bar[4];   // staged sub-tile ready / read by both statistics warps (per group x buffer)
+  __shared__ uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots], tfull_bar[2], tempty_bar[2], w_bar, aux_bar[6];
+  __shared__ uint64_t sfull_bar[6], sdone_bar[6];   // staged sub-tile ready / read by both statistics warps (per group x buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[C];
   __shared__ float s_stat[2][2 * C];                // per statistics warp: [C] sums, [C] sums of squares
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
       mbar_init(&tempty_bar[a], 4);
     }
     mbar_init(&w_bar, 1);
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 6; ++a) {
       mbar_init(&aux_bar[a], 1);
       mbar_init(&sfull_bar[a], 1);
       mbar_init(&sdone_bar[a], 2);
@@ -288,18 +291,18 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
       for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
         for (int e = 0; e < 4; ++e) sa[kc][e] = qa[kc][e] = make_float2(0.f, 0.f);
-      int cnt[2] = {0, 0};
-      uint32_t ph[4] = {0, 0, 0, 0};
+      int cnt[2] = {0, 0};                            // buffer of the next sub-tile of group g (rotates over NB)
+      uint32_t ph = 0;                                // bit (g * 3 + b): phase of sfull_bar[g * NB + b]
       int i = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++i) {
         const int g = i & 1;
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
-          const int b = cnt[g] & 1;
-          ++cnt[g];
-          mbar_wait(&sfull_bar[g * 2 + b], ph[g * 2 + b]);
-          ph[g * 2 + b] ^= 1;
-          const uint8_t* tile = s_stg + (g * 2 + b) * STG_PAD;
+          const int b = cnt[g];
+          cnt[g] = b + 1 == NB ? 0 : b + 1;
+          mbar_wait(&sfull_bar[g * NB + b], (ph >> (g * 3 + b)) & 1u);
+          ph ^= 1u << (g * 3 + b);
+          const uint8_t* tile = s_stg + (g * NB + b) * STG_PAD;
           const int vrows = min(128, p.W - (u % segs) * 128);      // pixel rows of this unit inside the image (ragged last segment)
           float2 s2[4], q2[4];
 #pragma unroll
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
             qa[kc][e] = __fadd2_rn(qa[kc][e], q2[e]);
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sdone_bar[g * 2 + b]);     // this warp has read the sub-tile (the barrier counts both statistics warps)
+          if (lane == 0) mbar_arrive(&sdone_bar[g * NB + b]);     // this warp has read the sub-tile (the barrier counts both statistics warps)
         }
       }
       if (warp == 10 && lane == 0) dbg_stamp(10);
@@ -368,18 +371,26 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
     const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
     // swizzled position of logical 16-byte chunk j of this row inside a staging sub-tile
     const int sw_key = CPR == 8 ? (row & 7) : ((row >> 2) & 1);
-    uint8_t* stg_g = s_stg + grp * 2 * STG_PAD;
-    uint64_t* aux_g = &aux_bar[grp * 2];
+    uint8_t* stg_g = s_stg + grp * NB * STG_PAD;
+    uint64_t* aux_g = &aux_bar[grp * NB];
     const uint32_t acc = grp;                  // accumulator owned by this group
-    uint32_t acc_phase = 0, aux_phase[2] = {0, 0};
+    uint32_t acc_phase = 0, aux_phase = 0;     // aux_phase / sdone_phase: bit b = phase of buffer b
     int step = 0;                              // staging steps (unit, k-chunk) done by this group
-    uint32_t sdone_phase[2] = {0, 0};
+    uint32_t sdone_phase = 0;
+    int b = 0, bprev = NB - 1;                 // staging buffer of this step / of the previous step
     // units of this CTA alternate between the two groups
     const int u_first = blockIdx.x + grp * gridDim.x, u_stride = 2 * gridDim.x;
-    if (leader && p.aux_mode && u_first < p.units) {   // aux prefetch for the very first step
-      const int xs = u_first % segs, y = (u_first / segs) % p.H, n = u_first / (segs * p.H);
-      mbar_arrive_expect_tx(&aux_g[0], STG_BYTES);
-      tma_load_4d(stg_g, &tmap_aux, &aux_g[0], 0, xs * 128, y, n);
+    // aux sub-tile (residual / mask operand) of this group's step st -> staging buffer st % NB
+    auto prefetch_aux = [&](int st) {
+      const int uu = u_first + (st / KC) * u_stride, kk = st % KC;
+      if (uu >= p.units) return;
+      const int bb = st % NB;
+      const int xs2 = uu % segs, y2 = (uu / segs) % p.H, n2 = uu / (segs * p.H);
+      mbar_arrive_expect_tx(&aux_g[bb], STG_BYTES);
+      tma_load_4d(stg_g + bb * STG_PAD, &tmap_aux, &aux_g[bb], kk * CH, xs2 * 128, y2, n2);
+    };
+    if (leader && p.aux_mode) {                // the first NB - 1 steps' operands
+      for (int st = 0; st < NB - 1; ++st) prefetch_aux(st);
     }
     for (int u = u_first; u < p.units; u += u_stride) {
       const int xs = u % segs, y = (u / segs) % p.H, n = u / (segs * p.H);
@@ -389,15 +400,14 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
       const uint32_t taddr = tmem_base + acc * C + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
       for (int kc = 0; kc < KC; ++kc, ++step) {
-        const int b = step & 1;
         uint8_t* my_row = stg_g + b * STG_PAD + row * RB;
         // both 32-column TMEM loads of this k-chunk are in flight before the first wait
         uint32_t r[CH];
         if (CH == 64) { tmem_ld32(taddr + kc * CH, r); tmem_ld32(taddr + kc * CH + 32, r + 32); }
         else tmem_ld16(taddr, r);
         if (p.aux_mode) {
-          mbar_wait(&aux_g[b], aux_phase[b]);
-          aux_phase[b] ^= 1;
+          mbar_wait(&aux_g[b], (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
         }
         tmem_ld_wait();
         if (kc == KC - 1) {                      // all TMEM reads of this unit are done: release the accumulator early
@@ -457,23 +467,16 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
         if (leader) {
           tma_store_4d(&tmap_out, stg_g + b * STG_PAD, kc * CH, xs * 128, y, n);
           tma_store_commit();
-          if (want_red) mbar_arrive(&sfull_bar[grp * 2 + b]);   // statistics are taken over the values as STORED (bf16)
+          if (want_red) mbar_arrive(&sfull_bar[grp * NB + b]);   // statistics are taken over the values as STORED (bf16)
         }
         if (want_red && step >= 1) {           // the statistics MMAs of the previous step have read the other buffer
-          mbar_wait(&sdone_bar[grp * 2 + (b ^ 1)], sdone_phase[b ^ 1]);
-          sdone_phase[b ^ 1] ^= 1;
+          mbar_wait(&sdone_bar[grp * NB + bprev], (sdone_phase >> bprev) & 1u);
+          sdone_phase ^= 1u << bprev;
         }
-        if (leader) {
-          if (p.aux_mode) {                    // prefetch the aux sub-tile of the NEXT step into the other buffer
-            int nkc = kc + 1, nu = u;
-            if (nkc == KC) { nkc = 0; nu = u + u_stride; }
-            if (nu < p.units) {
-              const int nxs = nu % segs, ny = (nu / segs) % p.H, nn = nu / (segs * p.H);
-              mbar_arrive_expect_tx(&aux_g[b ^ 1], STG_BYTES);
-              tma_load_4d(stg_g + (b ^ 1) * STG_PAD, &tmap_aux, &aux_g[b ^ 1], nkc * CH, nxs * 128, ny, nn);
-            }
-          }
-        }
+        // the operand of step + NB - 1 goes into the buffer of step - 1: its store has been read (wait above) and, with statistics, so have they
+        if (leader && p.aux_mode) prefetch_aux(step + NB - 1);
+        bprev = b;
+        b = b + 1 == NB ? 0 : b + 1;
       }
     }
     if (leader) tma_store_wait_read0();   // the CTA may exit once the stores have READ shared memory; the writes complete with the grid
@@ -532,6 +535,17 @@ extern "C" int erf_conv1d_tc_set_debug(unsigned long long* buf, int launches) {
   return cudaMemcpyToSymbol(g_conv1d_dbg, &buf, sizeof(buf)) == cudaSuccess ? ERF_OK : ERF_ERR_CUDA;
 }
 
+static int g_cap_main = 0, g_cap_side = 0;
+int erfk::launch_cap_main() { return g_cap_main; }
+int erfk::launch_cap_side() { return g_cap_side; }
+// SMs a 3-tap conv / data-gradient launch (main) and a weight-gradient launch (side) may take; 0 = all.  Host-side state read at launch (or
+// graph-capture) time: the trainer sets it around a backward pass whose weight gradients run on a second stream.
+extern "C" int erf_set_launch_cap(int main_sms, int side_sms) {
+  g_cap_main = main_sms > 0 ? main_sms : 0;
+  g_cap_side = side_sms > 0 ? side_sms : 0;
+  return ERF_OK;
+}
+
 extern "C" int erf_conv1d_tc_supported(int C, int W, int dil) {
   // any width from 16 pixels: rows are cut into 128-pixel units, the last one may be ragged (round 1 required W % 128 == 0, which left the
   // reference fork's own 640 x 480 frames -- widths 320 / 160 / 80 -- and the 224 x 224 ImageNet net on the CUDA-core kernels)
@@ -573,7 +587,12 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   }
   p.slot_bytes = p.sub_bytes;   // one (tap, k-chunk) tile [vertical] or one k-chunk of the haloed row tile [horizontal]
   const int w_pad = ((3 * KC * C * RB + 1023) / 1024) * 1024;
-  const int stg_pad = 4 * (((128 * RB + 1023) / 1024) * 1024);
+  p.nb = (p.aux_mode && C <= 64) ? 3 : 2;
+  {
+    const char* nb_env = getenv("ERF_CONV1D_NB");   // experiments: 2 = the two-buffer scheme everywhere
+    if (nb_env && atoi(nb_env) == 2) p.nb = 2;
+  }
+  const int stg_pad = 2 * p.nb * (((128 * RB + 1023) / 1024) * 1024);
   const int budget = 222 * 1024 - w_pad - stg_pad;   // + 1 KB alignment slack + ~3 KB of static shared memory (barriers, bias, statistics) <= 227 KB
   p.slots = budget / p.slot_bytes;
   if (p.slots > kMaxSlots) p.slots = kMaxSlots;
@@ -588,21 +607,24 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
   // C = 16 tiles are 4 KB: the per-unit TMA -> MMA -> epilogue -> store chain is latency-bound, and the kernel's footprint (~60 KB of
   // shared memory, 72 registers, 32 TMEM columns) lets two CTAs share an SM
   const int per_sm = C == 16 ? 2 : 1;   // measured: 35 -> 23 us (vertical), 21 -> 15 us (horizontal) at batch 6; 3 per SM is slower
+  if (launch_cap_main() > 0 && launch_cap_main() < sms) sms = launch_cap_main();
   int grid = p.units < sms * per_sm ? p.units : sms * per_sm;
   cudaError_t e;
   cudaStream_t st = (cudaStream_t)stream;
   const bool red = stats != nullptr || colsum != nullptr;
-#define CONV1D_LAUNCH(C_, RED_)                                                                                                       \
-  e = cudaFuncSetAttribute(conv1d_tc_kernel<C_, RED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
-  if (e == cudaSuccess && C_ == 16) e = prefer_max_smem(conv1d_tc_kernel<C_, RED_>);                                                  \
-  if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<C_, RED_>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+#define CONV1D_LAUNCH3(C_, RED_, NB_)                                                                                                 \
+  e = cudaFuncSetAttribute(conv1d_tc_kernel<C_, RED_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
+  if (e == cudaSuccess && C_ == 16) e = prefer_max_smem(conv1d_tc_kernel<C_, RED_, NB_>);                                             \
+  if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<C_, RED_, NB_>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+#define CONV1D_LAUNCH(C_, RED_) if (p.nb == 3) { CONV1D_LAUNCH3(C_, RED_, 3) } else { CONV1D_LAUNCH3(C_, RED_, 2) }
   if (C == 16) {
     if (red) { CONV1D_LAUNCH(16, true) } else { CONV1D_LAUNCH(16, false) }
   } else if (C == 64) {
     if (red) { CONV1D_LAUNCH(64, true) } else { CONV1D_LAUNCH(64, false) }
   } else {
-    if (red) { CONV1D_LAUNCH(128, true) } else { CONV1D_LAUNCH(128, false) }
+    if (red) { CONV1D_LAUNCH3(128, true, 2) } else { CONV1D_LAUNCH3(128, false, 2) }
   }
+#undef CONV1D_LAUNCH3
 #undef CONV1D_LAUNCH
   if (e != cudaSuccess) {
     set_error("erf_conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -480,7 +480,8 @@ static int wgrad_launch(const void* x, const void* dy, float* dw, void* workspac
   const bool two_per_sm = C == 16;   // ~60 KB of shared memory, 32 TMEM columns: two CTAs per SM hide the per-unit latency (C = 64: measured neutral)
   // C = 16: the five unused M atoms of the x operand read up to 7 tap pitches past the tile -- keep that inside the allocation
   size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (C == 16 ? 16 * 1024 : 0);
-  const int ctas = two_per_sm ? 296 : 148;
+  int ctas = two_per_sm ? 296 : 148;
+  if (launch_cap_side() > 0 && launch_cap_side() < 148) ctas = launch_cap_side() * (two_per_sm ? 2 : 1);
   int grid = p.units < ctas ? p.units : ctas;
   cudaError_t e;
   cudaStream_t s = (cudaStream_t)stream;

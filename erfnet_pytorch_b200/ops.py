@@ -949,6 +949,14 @@ SIDE = None        # a SideQueue while a trainer runs backward with WGRAD_SIDE_S
 WGRAD_SIDE_STREAM = os.environ.get("ERF_WGRAD_SIDE", "0") != "0"   # ERF_WGRAD_SIDE=1: weight gradients on a second stream (measured neutral at the bench workload: the SMs are busy)
 
 
+SIDE_CAP = [int(v) for v in os.environ.get("ERF_SIDE_CAP", "0,0").split(",")]   # (main, side) SMs while the weight gradients run on the side stream
+
+
+def set_launch_cap(main_sms: int, side_sms: int) -> None:
+    if not EMULATED and hasattr(_lib.lib(), "erf_set_launch_cap"):
+        check(_lib.lib().erf_set_launch_cap(int(main_sms), int(side_sms)))
+
+
 MASK_FROM_Y = True   # BN -> ReLU without dropout / residual: the backward kernel recomputes the ReLU mask from y (one tensor read less)
 
 

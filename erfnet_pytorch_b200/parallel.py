@@ -365,6 +365,8 @@ class FlatAdamTrainer:
             if getattr(self, "_side", None) is None:
                 self._side = ops.SideQueue(self.flat_p.device)
             ops.SIDE = self._side
+            if ops.SIDE_CAP[0] or ops.SIDE_CAP[1]:
+                ops.set_launch_cap(*ops.SIDE_CAP)
         try:
             if dlog is None:
                 logits.backward()          # generic path: `logits` is the scalar loss
@@ -375,6 +377,7 @@ class FlatAdamTrainer:
             if ops.SIDE is not None:
                 ops.SIDE.join()            # the optimiser (and the gradient all-reduce) wait for the weight gradients
                 ops.SIDE = None
+                ops.set_launch_cap(0, 0)
 
     def optimizer_step(self):
         self.step_count += 1

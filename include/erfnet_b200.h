@@ -172,6 +172,11 @@ int erf_bn_bwd_fused_spread(const void* g, int g_ld, const void* y, int y_ld, co
                             unsigned* counter, int N, int HW, int C, void* dy, int dy_ld, float* dgamma, float* dbeta, void* gmasked,
                             int gmasked_ld, int dtype, erf_stream_t stream);
 
+/* SMs a 3-tap conv / data-gradient launch (main_sms) and a 3-tap weight-gradient launch (side_sms) may take from now on; 0 = all.  Host-side
+ * state read at launch / graph-capture time: parallel.FlatAdamTrainer sets it around a backward pass whose weight gradients run on a second
+ * stream (ERF_WGRAD_SIDE=1), so that the two kinds of persistent kernels really run side by side. */
+int erf_set_launch_cap(int main_sms, int side_sms);
+
 /* ---- CrossEntropyLoss2d (train/evaluation_functions.py:6-14) ------------------------------------------- */
 /* logits element (p, c): NHWC -> logits[p*ld + c]; NCHW (nchw_hw > 0) -> logits[(p/hw)*C*hw + c*hw + p%hw].
  * pass 1: wsum += sum_valid w[y];  pass 2: loss_sum += sum_valid w[y]*nll, dlogits = w[y]*(softmax-onehot)/wsum. */
