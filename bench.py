@@ -275,8 +275,8 @@ def main():
     # The public call is FlatAdamTrainer.train_stream(host batches): every step copies ITS batch from pinned host memory (on a side
     # stream, overlapping the previous step's compute) and the loop reads every step's loss back to the host.
     def e2e_run(steps):
-        for loss in trainer.train_stream(pool_pin[i % len(pool_pin)] for i in range(steps)):
-            last["loss"] = float(loss)
+        for loss in trainer.train_stream((pool_pin[i % len(pool_pin)] for i in range(steps)), host_losses=True):
+            last["loss"] = loss       # a Python float: every step's loss is read back on the host (one step behind the launches)
 
     e2e_run(2)
     barrier()

@@ -453,21 +453,43 @@ class FlatAdamTrainer:
         self._stage_used[k] = True
         return loss
 
-    def train_stream(self, batches):
+    def train_stream(self, batches, host_losses=False):
         """Generator over an iterable of HOST batches (images fp32 NCHW, labels int64; pinned memory for asynchronous copies): yields
-        the loss tensor of each step.  The copy of the next batch runs on a side stream while the current step computes, so a
-        training loop that reads the loss every step (train/main.py:392) still keeps the GPU busy."""
+        the loss of each step, in order, one per batch.  The copy of the next batch runs on a side stream while the current step computes.
+
+        host_losses=False: yields the step's loss TENSOR right after the step was enqueued; a loop that calls float() on it every step
+        (train/main.py:392) waits for the step and leaves the GPU idle while the next one is being launched.
+        host_losses=True: yields Python floats.  Every step's loss is copied to pinned host memory by an asynchronous device->host copy behind
+        the step, and the value of step i is handed out after step i+1 has been ENQUEUED (the last one after the loop): the same values in the
+        same order, every one read on the host, without that bubble."""
         it = iter(batches)
         nxt = next(it, None)
         k = 0
         if nxt is not None:
             self._stage(nxt, k)
+        pending = None          # (pinned host slot, event) of the previous step's loss
+        if host_losses and getattr(self, "_loss_host", None) is None:
+            self._loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
         while nxt is not None:
             nxt2 = next(it, None)
             if nxt2 is not None:
                 self._stage(nxt2, k ^ 1)
-            yield self._step_from_stage(k)
+            loss = self._step_from_stage(k)
+            if host_losses:
+                slot, ev = self._loss_host[k], self._loss_evt[k]
+                slot.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+                ev.record(torch.cuda.current_stream(self.flat_p.device))
+                if pending is not None:
+                    pending[1].synchronize()
+                    yield float(pending[0][0])
+                pending = (slot, ev)
+            else:
+                yield loss
             nxt, k = nxt2, k ^ 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield float(pending[0][0])
 
     # ---- CUDA graph of the whole step (forward, loss, backward, all-reduce, Adam): ~700 launches -> one replay ---------
     def capture_cuda_graph(self, images_shape, labels_shape, warmup=2, labels_dtype=torch.int64):

@@ -77,6 +77,14 @@ def test_train_stream_matches_sequential_steps():
     np.testing.assert_allclose(got[0], seq[0], rtol=1e-5)
     np.testing.assert_allclose(got, seq, rtol=1e-2)
     assert float((t1.flat_p - t2.flat_p).abs().mean()) < 1e-4   # Adam's sign-like first steps amplify rounding noise on ~zero gradients: mean, not max
+    # host_losses=True: Python floats, one per batch and in order, each handed out one step behind the launches
+    t3 = make()
+    t3.capture_cuda_graph(batches[0][0].shape, batches[0][1].shape)
+    lag = list(t3.train_stream(iter(pinned), host_losses=True))
+    assert len(lag) == len(seq) and all(isinstance(v, float) for v in lag)
+    np.testing.assert_allclose(lag[0], seq[0], rtol=1e-5)
+    np.testing.assert_allclose(lag, seq, rtol=1e-2)
+    assert list(t3.train_stream(iter([]), host_losses=True)) == []
 
 
 def test_capture_after_an_earlier_autograd_forward():
