@@ -73,6 +73,9 @@ __device__ __forceinline__ unsigned long long dbg_globaltimer() {
 
 constexpr int kMaxSlots = 8;
 constexpr int kThreads = 384;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups, warps 10-11 per-channel statistics
+// Statistics warps: 2, or 4 in the C = 128 statistics instantiation (448 threads) -- a 128-channel launch is 2.6 units = 5 sub-tiles per CTA, the two
+// warps' serial pass over them (~0.45 us each) trailed the MMAs by 2 us (in-situ trace: tail 3.0-3.5 us against 1.3 us without statistics)
+template <int C, bool RED> struct StatWarps { static constexpr int value = (RED && C == 128) ? 4 : 2; };
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -82,7 +85,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 template <int C, bool RED, int NB>
-__global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+__global__ void __launch_bounds__(320 + 32 * StatWarps<C, RED>::value, C == 16 ? 2 : 1) conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                                                            const __grid_constant__ CUtensorMap tmap_aux, const Conv1dTcParams p) {
   constexpr int CH = C < 64 ? C : 64;           // channels per K chunk (one swizzle row)
   constexpr int RB = CH * 2;                    // bytes per pixel row of a chunk: 128 (128B swizzle) or 32 (32B swizzle, C = 16)
@@ -111,7 +114,8 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
   __shared__ uint64_t sfull_bar[6], sdone_bar[6];   // staged sub-tile ready / read by both statistics warps (per group x buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[C];
-  __shared__ float s_stat[2][2 * C];                // per statistics warp: [C] sums, [C] sums of squares
+  constexpr int SW = StatWarps<C, RED>::value;      // statistics warps, each takes 128 / SW rows of every sub-tile
+  __shared__ float s_stat[SW][2 * C];               // per statistics warp: [C] sums, [C] sums of squares
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
     for (int a = 0; a < 6; ++a) {
       mbar_init(&aux_bar[a], 1);
       mbar_init(&sfull_bar[a], 1);
-      mbar_init(&sdone_bar[a], 2);
+      mbar_init(&sdone_bar[a], SW);
     }
     fence_barrier_init();
     if (p.w_static) {   // static weights: fetch them while the previous kernel's last CTAs are still running
@@ -282,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
       // lanes of a row cover the whole (swizzled) row, so the access is conflict-free -- and accumulates in packed fp32x2.  (The first version
       // read one 4-byte word per lane and row: ~800 instructions per warp and sub-tile; the in-situ timeline, tools/trace_step_conv1d.py,
       // showed the statistics warps setting the pace of every launch that had them and ~4 us of extra tail.)
-      const int sw = warp - 10;                       // rows [64*sw, 64*sw + 64) of every sub-tile
+      const int sw = warp - 10;                       // rows [RPW*sw, RPW*sw + RPW) of every sub-tile
+      constexpr int RPW = 128 / SW;
       constexpr int RPI = 32 / CPR;                   // rows per load instruction: 4 (128-byte rows) or 16 (32-byte rows)
       const int jl = lane % CPR;                      // logical 16-byte chunk = channels 8*jl .. 8*jl + 7 of the k-chunk
       const int rl = lane / CPR;
@@ -309,8 +314,8 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
           for (int e = 0; e < 4; ++e) s2[e] = q2[e] = make_float2(0.f, 0.f);
           auto accumulate = [&](auto with_squares) {      // a bias gradient (colsum alone) needs no squares: one branch per sub-tile
 #pragma unroll
-            for (int it = 0; it < 64 / RPI; ++it) {
-              const int r = sw * 64 + it * RPI + rl;
+            for (int it = 0; it < RPW / RPI; ++it) {
+              const int r = sw * RPW + it * RPI + rl;
               const int key = CPR == 8 ? (r & 7) : ((r >> 2) & 1);
               uint4 w4 = *reinterpret_cast<const uint4*>(tile + r * RB + ((jl ^ key) * 16));
               if (r >= vrows) w4 = make_uint4(0u, 0u, 0u, 0u);
@@ -352,13 +357,15 @@ __global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1) conv1d_tc_kernel(co
           }
         }
       }
-      asm volatile("bar.sync 5, 64;" ::: "memory");               // the two statistics warps
-      for (int c = tid - 320; c < C; c += 64) {
-        const float sum = s_stat[0][c] + s_stat[1][c];
+      asm volatile("bar.sync 5, %0;" ::"n"(32 * SW) : "memory");   // the statistics warps
+      for (int c = tid - 320; c < C; c += 32 * SW) {
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int w = 0; w < SW; ++w) { sum += s_stat[w][c]; sq += s_stat[w][C + c]; }
         if (p.colsum) atomicAdd(&p.colsum[c], sum);
         if (p.stats) {
           atomicAdd(&p.stats[c], (double)sum);
-          atomicAdd(&p.stats[C + c], (double)(s_stat[0][C + c] + s_stat[1][C + c]));
+          atomicAdd(&p.stats[C + c], (double)sq);
         }
       }
       if (warp == 10 && lane == 0) dbg_stamp(11);
@@ -615,7 +622,7 @@ extern "C" int erf_conv1d_tc(const void* in, const void* w_img, const float* bia
 #define CONV1D_LAUNCH3(C_, RED_, NB_)                                                                                                 \
   e = cudaFuncSetAttribute(conv1d_tc_kernel<C_, RED_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
   if (e == cudaSuccess && C_ == 16) e = prefer_max_smem(conv1d_tc_kernel<C_, RED_, NB_>);                                             \
-  if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<C_, RED_, NB_>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)(st), tin, tout, taux, p);
+  if (e == cudaSuccess) launch_pdl(conv1d_tc_kernel<C_, RED_, NB_>, dim3(grid), dim3(320 + 32 * StatWarps<C_, RED_>::value), smem, (cudaStream_t)(st), tin, tout, taux, p);
 #define CONV1D_LAUNCH(C_, RED_) if (p.nb == 3) { CONV1D_LAUNCH3(C_, RED_, 3) } else { CONV1D_LAUNCH3(C_, RED_, 2) }
   if (C == 16) {
     if (red) { CONV1D_LAUNCH(16, true) } else { CONV1D_LAUNCH(16, false) }
