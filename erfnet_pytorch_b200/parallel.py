@@ -119,6 +119,7 @@ class FlatAdamTrainer:
         self._launched = [False, False, False]
         self._works = []
         self._graph, self._step_dev = None, None
+        self._coalesce = None       # N > 1 under graphs: gradient + loss all-reduce as one NCCL group (decided at first use)
         self._hooks_enabled = True
         self._seen = set()
         self.cuda = dev.type == "cuda"
@@ -410,8 +411,7 @@ class FlatAdamTrainer:
                 ops.ce_weight_sum(self._g_labels, self.criterion.weight, self.num_classes, self.criterion.ignore_index, self._g_acc[0:1])
                 dist.all_reduce(self._g_acc[0:1], op=dist.ReduceOp.SUM, group=self.pg)
                 g12.replay()                                                   # zero grads, forward, CE fwd+bwd, backward
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-                dist.all_reduce(self._g_acc[1:2], op=dist.ReduceOp.SUM, group=self.pg)
+                self._allreduce_grads_and_loss()
                 g3.replay()                                                    # Adam, loss = lsum / wsum
             else:
                 self._graph.replay()
@@ -421,6 +421,21 @@ class FlatAdamTrainer:
         loss = self.loss_and_backward(images, labels, drop_scales)
         self.optimizer_step()
         return loss
+
+    def _allreduce_grads_and_loss(self):
+        """Gradient buffer and loss sum between the two graph segments: one NCCL group (one launch) where the backend coalesces."""
+        if self._coalesce is None:
+            self._coalesce = dist.get_backend(self.pg) == "nccl" and hasattr(dist, "_coalescing_manager")
+        if self._coalesce:
+            try:
+                with dist._coalescing_manager(group=self.pg, device=self.flat_p.device):
+                    dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                    dist.all_reduce(self._g_acc[1:2], op=dist.ReduceOp.SUM, group=self.pg)
+                return
+            except Exception:      # private API of torch.distributed: fall back to two launches for good
+                self._coalesce = False
+        dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(self._g_acc[1:2], op=dist.ReduceOp.SUM, group=self.pg)
 
     # ---- host-fed training: H2D of batch i+1 overlaps the step on batch i ------------------------------------------------
     def _stage(self, batch, k):
