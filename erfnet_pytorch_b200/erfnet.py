@@ -185,7 +185,7 @@ def _side(fn, keep, *params):
     """Run fn() (weight-gradient launches that accumulate into the sinks of `params`) on the trainer's side stream when there is one and every
     parameter has a sink -- nothing is then returned to autograd, so nothing downstream waits for these kernels except the optimiser."""
     q = ops.SIDE
-    if q is None or any(_sink(p) is None for p in params):
+    if q is None or ops.WGRAD_FUSED_REDUCE or any(_sink(p) is None for p in params):   # (a grid-barrier kernel must never leave the main stream)
         return fn()
     return q.run(fn, keep)
 

@@ -946,7 +946,10 @@ class SideQueue:
 
 
 SIDE = None        # a SideQueue while a trainer runs backward with WGRAD_SIDE_STREAM
-WGRAD_SIDE_STREAM = os.environ.get("ERF_WGRAD_SIDE", "0") != "0"   # ERF_WGRAD_SIDE=1: weight gradients on a second stream (measured neutral at the bench workload: the SMs are busy)
+# Weight gradients of backward on a second stream, joined before the optimiser.  "auto" (default): while a CUDA graph is being captured -- the
+# replayed step gains ~1 % (4.712 -> 4.666 ms; configs 3 / 4: +7 %) because the weight-gradient kernels fill the ramp-up / tail gaps of the
+# data-gradient chain; eagerly the extra events only cost CPU time (config 4 eager: 10.0 -> 11.8 ms), so it stays off there.  ERF_WGRAD_SIDE=1 / 0 force it.
+WGRAD_SIDE_STREAM = {"1": True, "0": False}.get(os.environ.get("ERF_WGRAD_SIDE", "auto"), "auto")
 
 
 SIDE_CAP = [int(v) for v in os.environ.get("ERF_SIDE_CAP", "0,0").split(",")]   # (main, side) SMs while the weight gradients run on the side stream

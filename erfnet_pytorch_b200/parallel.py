@@ -362,7 +362,10 @@ class FlatAdamTrainer:
 
     def _backward(self, logits, dlog):
         _erfnet._GRAD_SINK = self
-        if self.cuda and not ops.EMULATED and ops.WGRAD_SIDE_STREAM:
+        side = ops.WGRAD_SIDE_STREAM
+        if side == "auto":
+            side = self.cuda and torch.cuda.is_current_stream_capturing()
+        if self.cuda and not ops.EMULATED and side:
             if getattr(self, "_side", None) is None:
                 self._side = ops.SideQueue(self.flat_p.device)
             ops.SIDE = self._side

@@ -143,3 +143,28 @@ def test_learning_rate_change_reaches_the_captured_optimiser_and_checkpoint_resu
     lb, lc = float(b.train_step(x[0], y[0])), float(c.train_step(x[0], y[0]))
     np.testing.assert_allclose(lc, lb, rtol=1e-3)
     assert float((b.flat_p - c.flat_p).abs().mean()) < 0.2 * float((b.flat_p - before).abs().mean())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_side_stream_weight_gradients_match_main_stream(graph):
+    """ops.WGRAD_SIDE_STREAM: the weight-gradient launches of backward run on a second stream (optionally with SM caps, erf_set_launch_cap) and are
+    joined before the optimiser; three steps must give the losses and parameters of the single-stream run (eagerly and captured in a CUDA graph)."""
+    from erfnet_pytorch_b200 import ops
+    x = [golden_input((2, 3, 64, 256), i).cuda() for i in range(3)]
+    y = [golden_labels((2, 64, 256), i).cuda() for i in range(3)]
+    ref = _trainer("fp32")
+    lr = [float(ref.train_step(x[i], y[i])) for i in range(3)]
+    old_side, old_cap = ops.WGRAD_SIDE_STREAM, list(ops.SIDE_CAP)
+    try:
+        ops.WGRAD_SIDE_STREAM = True
+        ops.SIDE_CAP[:] = [100, 48]
+        t = _trainer("fp32")
+        if graph:
+            t.capture_cuda_graph((2, 3, 64, 256), (2, 64, 256))
+        ls = [float(t.train_step(x[i], y[i])) for i in range(3)]
+    finally:
+        ops.WGRAD_SIDE_STREAM = old_side
+        ops.SIDE_CAP[:] = old_cap
+        ops.set_launch_cap(0, 0)
+    np.testing.assert_allclose(ls, lr, rtol=2e-3)
+    assert float((t.flat_p - ref.flat_p).abs().mean()) < 1e-4
