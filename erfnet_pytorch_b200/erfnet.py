@@ -388,11 +388,12 @@ class DownsamplerBlock(_B200Module):
         if "stem_w" in pk and ops.stem_supported(x):
             return ops.stem_fwd(x, pk["stem_w"], pk["b"], pk.get("stem_sc"), pk.get("stem_sh"), relu=True)
         y = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
-        if "tc" in pk and ops.USE_TC:
-            self._tc.forward(x, pk["tc"], pk["b"], relu=True, out=y)
+        pool = lambda: ops.maxpool_fwd(x, self.ninput, y, self.noutput - self.ninput, pk["ps"], pk["psh"], relu=True)
+        if "tc" in pk and ops.USE_TC:   # the two halves write disjoint channel slices: side by side under graph replay
+            ops.fork_join(pool, lambda: self._tc.forward(x, pk["tc"], pk["b"], relu=True, out=y))
         else:
             ops.conv_fwd(x, pk["w"], self.spec, pk["b"], relu=True, out=y)
-        ops.maxpool_fwd(x, self.ninput, y, self.noutput - self.ninput, pk["ps"], pk["psh"], relu=True)
+            pool()
         return y
 
     def _fwd_eval_nchw(self, input, ctx):
@@ -419,16 +420,17 @@ class DownsamplerBlock(_B200Module):
         y_raw = torch.empty(n, h // 2, w // 2, self.noutput, device=x.device, dtype=x.dtype)
         if not self.use_batchnorm:  # train/erfnet_blocks.py:24-29: relu(cat(conv, pool)), both ReLUs in the producing kernels
             if self._tc.fwd_ok(x.dtype):
-                self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), relu=True, out=y_raw)
+                img, bias = self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float()
+                ops.fork_join(lambda: ops.maxpool_fwd(x, self.ninput, y_raw, cc, relu=True), lambda: self._tc.forward(x, img, bias, relu=True, out=y_raw))
             else:
                 ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),
                              relu=True, out=y_raw)
-            ops.maxpool_fwd(x, self.ninput, y_raw, cc, relu=True)
+                ops.maxpool_fwd(x, self.ninput, y_raw, cc, relu=True)
             return y_raw, (x, None, y_raw, None, None)
         stats = ops.bn_stats_buf(self.noutput, x.device)
         if self._tc.fwd_ok(x.dtype):
-            self._tc.forward(x, self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float(), out=y_raw)
-            ops.maxpool_fwd(x, self.ninput, y_raw, cc)
+            img, bias = self._tc.pack_fwd(self.conv.weight), self.conv.bias.detach().float()
+            ops.fork_join(lambda: ops.maxpool_fwd(x, self.ninput, y_raw, cc), lambda: self._tc.forward(x, img, bias, out=y_raw))
             ops.channel_stats(y_raw, stats)
         else:
             ops.conv_fwd(x, ops.pack_weight_fwd(self.conv.weight.detach(), self.spec, x.dtype), self.spec, self.conv.bias.detach().float(),

@@ -227,6 +227,29 @@ def conv1d_pair_tc_supported(c: int, w: int, dil: int, dtype) -> bool:
     return dtype == torch.bfloat16 and not EMULATED and USE_TC and USE_PAIR and bool(_lib.lib().erf_conv1d_pair_tc_supported(c, w, dil))
 
 
+FORK_JOIN = os.environ.get("ERF_FORK_JOIN", "1") != "0"
+_FORK_STREAMS = {}
+
+
+def fork_join(side_fn, main_fn):
+    """main_fn() and side_fn() launch kernels that are independent of each other (they write disjoint memory).  While a CUDA graph is being captured
+    side_fn's launches go to a second stream, forked from and joined to the capturing stream, so that the replayed graph runs them side by side (the
+    max-pool half of a downsampler next to its convolution half: two kernels that fit on an SM together).  Eagerly the two simply run in order."""
+    if not FORK_JOIN or EMULATED or not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
+        main_fn()
+        side_fn()
+        return
+    main = torch.cuda.current_stream()
+    s = _FORK_STREAMS.get(main.device)
+    if s is None:
+        s = _FORK_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+    s.wait_stream(main)
+    with torch.cuda.stream(s):
+        side_fn()
+    main_fn()
+    main.wait_stream(s)
+
+
 USE_PAIR = True   # fused 3x1 -> ReLU -> 1x3 pairs in eval mode (C = 16 / 64)
 FOLD_32 = True          # 32-channel BN-free blocks run as [W/2, 64]-folded views on the 64-channel tcgen05 kernels
 FUSE_NCHW_HEAD = True   # inference: the decoder head writes the NCHW fp32 logits from its epilogue (no NHWC logits, no layout pass)
