@@ -261,6 +261,30 @@ def _bn_fold(bn: nn.BatchNorm2d):
     return ops.bn_eval_affine(bn.weight.detach().float(), bn.bias.detach().float(), bn.running_mean, bn.running_var, bn.eps)
 
 
+# Weight images of the im2col convs packed AHEAD of the layers, on a second stream, at the start of a captured training step (the ~17 pack
+# launches of a step are tiny but sat on the critical path, the data-gradient ones in the middle of backward).  `epoch` ties the images to ONE step:
+# prepack_end() bumps it, so nothing (an eval forward, the next step) can pick up images packed from older weights.
+_PREPACK = {"epoch": 0, "stream": None, "joined": True}
+
+
+def prepack_begin(convs, dtype):
+    """convs: [(_TcConv, weight)].  Call while a CUDA graph is being captured, after the optimiser's weights are final for this step."""
+    main = torch.cuda.current_stream()
+    s = ops.side_stream(main.device)
+    s.wait_stream(main)
+    with torch.cuda.stream(s):
+        for tc, w in convs:
+            tc.prepack(w, dtype, _PREPACK["epoch"])
+    _PREPACK["stream"], _PREPACK["joined"] = s, False
+
+
+def prepack_end():
+    if not _PREPACK["joined"] and _PREPACK["stream"] is not None:      # nobody used an image: still join the fork
+        torch.cuda.current_stream().wait_stream(_PREPACK["stream"])
+    _PREPACK["joined"] = True
+    _PREPACK["epoch"] += 1
+
+
 class _TcConv:
     """tcgen05 (software-im2col) execution of one conv layer: forward and data gradient, with cached plans."""
 
@@ -268,6 +292,21 @@ class _TcConv:
         self.spec = spec
         self.dspec = ops.dgrad_spec(spec)
         self._plans = None
+        self._pre = None    # (epoch, weight pointer, forward images, data-gradient images) of prepack()
+
+    def prepack(self, w, dtype, epoch):
+        fwd = ops.im2col_pack(w, self.spec, False, self.plans()[0]) if self.fwd_ok(dtype) else None
+        bwd = ops.im2col_pack(w, self.spec, True, self.plans()[1]) if self.bwd_ok(dtype) else None
+        self._pre = (epoch, w.data_ptr(), fwd, bwd)
+
+    def _prepacked(self, w, idx):
+        pre = self._pre
+        if pre is None or pre[0] != _PREPACK["epoch"] or pre[1] != w.data_ptr() or pre[idx] is None or _PREPACK["stream"] is None:
+            return None
+        if not _PREPACK["joined"]:      # first consumer of the step: the capturing stream waits for the packing stream once
+            torch.cuda.current_stream().wait_stream(_PREPACK["stream"])
+            _PREPACK["joined"] = True
+        return pre[idx]
 
     def plans(self):
         if self._plans is None:
@@ -281,7 +320,8 @@ class _TcConv:
         return ops.im2col_supported(self.dspec, dtype)
 
     def pack_fwd(self, w):
-        return ops.im2col_pack(w, self.spec, False, self.plans()[0])
+        pre = self._prepacked(w, 2)
+        return pre if pre is not None else ops.im2col_pack(w, self.spec, False, self.plans()[0])
 
     def forward(self, x, imgs, bias, relu=False, out=None, out_coff=0):
         return ops.conv_im2col_tc(x, imgs, self.plans()[0], self.spec, bias, relu=relu, out=out, out_coff=out_coff)
@@ -299,7 +339,10 @@ class _TcConv:
 
     def dgrad(self, dy, w, out_hw):
         plan = self.plans()[1]
-        return ops.conv_im2col_tc(dy, ops.im2col_pack(w, self.spec, True, plan), plan, self.dspec, out_hw=out_hw)
+        imgs = self._prepacked(w, 3)
+        if imgs is None:
+            imgs = ops.im2col_pack(w, self.spec, True, plan)
+        return ops.conv_im2col_tc(dy, imgs, plan, self.dspec, out_hw=out_hw)
 
     def wgrad(self, x, dy, wparam, bparam, bias_is_zero, bias_done=False):
         """(dw, db) for autograd, accumulated in place when a gradient sink is active.  bias_is_zero: the conv feeds a

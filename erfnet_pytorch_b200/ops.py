@@ -231,6 +231,13 @@ FORK_JOIN = os.environ.get("ERF_FORK_JOIN", "1") != "0"
 _FORK_STREAMS = {}
 
 
+def side_stream(device):
+    s = _FORK_STREAMS.get(device)
+    if s is None:
+        s = _FORK_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def fork_join(side_fn, main_fn):
     """main_fn() and side_fn() launch kernels that are independent of each other (they write disjoint memory).  While a CUDA graph is being captured
     side_fn's launches go to a second stream, forked from and joined to the capturing stream, so that the replayed graph runs them side by side (the
@@ -240,9 +247,7 @@ def fork_join(side_fn, main_fn):
         side_fn()
         return
     main = torch.cuda.current_stream()
-    s = _FORK_STREAMS.get(main.device)
-    if s is None:
-        s = _FORK_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+    s = side_stream(main.device)
     s.wait_stream(main)
     with torch.cuda.stream(s):
         side_fn()

@@ -310,6 +310,19 @@ class FlatAdamTrainer:
                 raise RuntimeError("FlatAdamTrainer: a conv weight was re-allocated after the trainer took ownership of the parameters")
             self._pack_table.run()
             _erfnet._PREPACKED_FRESH = True
+        if self.cuda and not ops.EMULATED and ops.FORK_JOIN and torch.cuda.is_current_stream_capturing():
+            # the im2col convs' weight images (forward and data gradient) for this step, packed on a second stream next to the first layers
+            convs = []
+            for mod in self.model.modules():
+                tc = mod.__dict__.get("_tc")
+                if isinstance(tc, _erfnet._TcConv) and getattr(mod, "conv", None) is not None:
+                    convs.append((tc, mod.conv.weight))
+                for v in mod.__dict__.values():
+                    if isinstance(v, _erfnet._PlainConv):
+                        convs.append((v._tc, v._conv.weight))
+            if convs:
+                prec = self.model._precision() if hasattr(self.model, "_precision") else "bf16"
+                _erfnet.prepack_begin(convs, torch.bfloat16 if prec == "bf16" else torch.float32)
         self.flat_g.zero_()
         if self.flat_nbt.numel():
             self.flat_nbt.add_(1)
@@ -322,6 +335,7 @@ class FlatAdamTrainer:
 
     def _end_step(self):
         _erfnet._PREPACKED_FRESH = False
+        _erfnet.prepack_end()
         ops.ARENA = None
 
     def _loss_and_backward(self, images, labels, drop_scales=None):
