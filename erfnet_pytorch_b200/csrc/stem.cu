@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x
   const int Ho = H / 2, Wo = W / 2;
   T* s_x = reinterpret_cast<T*>(s_raw);                               // [3 rows][W][4]
   T* s_dy = s_x + (size_t)3 * W * 4;                                  // [Wo][16]
-  float* s_acc = reinterpret_cast<float*>(s_dy + (size_t)Wo * STEM_C);  // [SW_LANES][9][16][3] partial sums + [16] bias sums
+  float* s_acc = reinterpret_cast<float*>(s_raw);  // [SW_LANES][9][16][3] partial sums + [16] bias sums: ALIASES the row staging, used only after the last row
   const int tid = threadIdx.x;
   const int lane_px = tid / SW_GROUP, g = tid % SW_GROUP, tap = g / 4, cq = g % 4;
   const int ky = tap / 3, kx = tap % 3;
@@ -295,10 +295,14 @@ extern "C" int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W
   ERF_CHECK_ARG(x && dy && dw && N > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 4) == 0, "erf_stem_wgrad: bad arguments (H even, W % 4 == 0)");
   ERF_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0, "erf_stem_wgrad: tensors must be 16-byte aligned");
   const size_t esz = dtype == ERF_F32 ? 4 : 2;
-  const size_t smem = (size_t)3 * W * 4 * esz + (size_t)(W / 2) * STEM_C * esz + (size_t)SW_LANES * SW_GROUP * 16 * sizeof(float);
+  size_t smem = (size_t)3 * W * 4 * esz + (size_t)(W / 2) * STEM_C * esz;
+  if (smem < (size_t)SW_LANES * SW_GROUP * 16 * sizeof(float)) smem = (size_t)SW_LANES * SW_GROUP * 16 * sizeof(float);
   ERF_CHECK_ARG(smem <= 200 * 1024, "erf_stem_wgrad: image row of %d pixels does not fit in shared memory", W);
   const int rows = N * (H / 2);
-  int grid = rows < 148 * 2 ? rows : 148 * 2;
+  // blocks per SM: the kernel alternates staging and compute behind block-wide barriers, so co-resident blocks are what overlaps the two
+  static const int per_sm_env = getenv("ERF_STEM_WGRAD_BLOCKS") ? atoi(getenv("ERF_STEM_WGRAD_BLOCKS")) : 0;
+  const int per_sm = per_sm_env > 0 ? per_sm_env : 4;   // measured at the bench shape: 122 (2) / 93 (3) / 91 (4) / 96 us (5)
+  int grid = rows < 148 * per_sm ? rows : 148 * per_sm;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e;
   if (dtype == ERF_F32) {
