@@ -357,3 +357,14 @@ def test_stem_from_nchw_matches_the_layout_pass(shape):
             assert torch.equal(a, b)
         else:
             assert (a.float() - b.float()).abs().max().item() <= 2e-2 * b.float().abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (1, 3, 6, 10), (6, 3, 64, 128)])
+def test_image_ingest_nchw3_to_nhwc4_matches_generic(shape):
+    """The vectorised 3-plane fp32 -> NHWC bf16 (4-channel pixels) conversion (four pixels per thread; HW % 4 == 0) against the definition,
+    and the generic kernel for sizes it does not take (HW % 4 != 0)."""
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(7)).cuda()
+    got = ops.nchw_to_nhwc(x, 4, torch.bfloat16)
+    ref = torch.zeros(shape[0], shape[2], shape[3], 4, device="cuda", dtype=torch.bfloat16)
+    ref[..., :3] = x.permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(got, ref)
