@@ -248,6 +248,91 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const T* __restrict__ x
   }
 }
 
+// bf16, second version.  The kernel above is FMA-ISSUE bound (12 MACs for ~35 instructions per pixel and thread) and is the LAST kernel of backward,
+// fully exposed in front of the optimiser.  Here a thread owns ONE tap and ALL 13 output channels x 3 input channels: per pixel one 8-byte load of
+// x, two 16-byte loads of dy, and 21 packed FFMA2 (output channels in pairs -- a bf16x2 word of dy unpacks straight into the float2 operand) = 39
+// MACs for ~50 instructions.  252 threads = 28 pixel lanes x 9 taps; the lanes are combined through shared memory (aliasing the row staging) at the end.
+constexpr int SW2_LANES = 28, SW2_VALS = 44;   // 7 channel pairs x 3 input channels x 2 = 42 sums per thread, padded
+__global__ void __launch_bounds__(256, 3) stem_wgrad_bf16_v2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int N, int H, int W,
+                                                                 float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const int Ho = H / 2, Wo = W / 2;
+  __nv_bfloat16* s_x = reinterpret_cast<__nv_bfloat16*>(s_raw);   // [3 rows][W][4]
+  __nv_bfloat16* s_dy = s_x + (size_t)3 * W * 4;                   // [Wo][16]
+  float* s_acc = reinterpret_cast<float*>(s_raw);                  // [252][SW2_VALS] + [SW2_LANES][14] bias sums: ALIASES the staging, used after the last row
+  const int tid = threadIdx.x;
+  const int lane_px = tid / 9, tap = tid % 9, ky = tap / 3, kx = tap % 3;
+  const bool active = tid < SW2_LANES * 9;
+  float2 acc[7][3], bs[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    bs[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[k][c] = make_float2(0.f, 0.f);
+  }
+  const int rows = N * Ho;
+  const int x_vecs = W * 4 * 2 / 16, dy_vecs = Wo * STEM_C * 2 / 16;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int n = r / Ho, oy = r % Ho;
+    __syncthreads();   // previous row fully consumed
+    for (int i = tid; i < 3 * x_vecs; i += blockDim.x) {
+      const int rr = i / x_vecs, v = i % x_vecs, iy = 2 * oy - 1 + rr;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (iy >= 0 && iy < H) val = reinterpret_cast<const uint4*>(x + ((size_t)n * H + iy) * W * 4)[v];
+      reinterpret_cast<uint4*>(s_x)[i] = val;
+    }
+    for (int i = tid; i < dy_vecs; i += blockDim.x) reinterpret_cast<uint4*>(s_dy)[i] = reinterpret_cast<const uint4*>(dy + (size_t)r * Wo * STEM_C)[i];
+    __syncthreads();
+    if (active) {
+      const __nv_bfloat16* xrow = s_x + (size_t)ky * W * 4;
+      for (int ox = lane_px; ox < Wo; ox += SW2_LANES) {
+        const int ix = 2 * ox - 1 + kx;
+        uint2 xw = make_uint2(0u, 0u);
+        if (ix >= 0 && ix < W) xw = *reinterpret_cast<const uint2*>(xrow + (size_t)ix * 4);
+        const float x0 = __uint_as_float(xw.x << 16), x1 = __uint_as_float(xw.x & 0xFFFF0000u), x2 = __uint_as_float(xw.y << 16);
+        const float2 xs0 = make_float2(x0, x0), xs1 = make_float2(x1, x1), xs2 = make_float2(x2, x2);
+        const uint4 d0 = *reinterpret_cast<const uint4*>(s_dy + (size_t)ox * STEM_C), d1 = *reinterpret_cast<const uint4*>(s_dy + (size_t)ox * STEM_C + 8);
+        const uint32_t dwd[7] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};   // channel pairs (0,1) .. (12,13)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const float2 dv = make_float2(__uint_as_float(dwd[k] << 16), __uint_as_float(dwd[k] & 0xFFFF0000u));
+          acc[k][0] = __ffma2_rn(dv, xs0, acc[k][0]);
+          acc[k][1] = __ffma2_rn(dv, xs1, acc[k][1]);
+          acc[k][2] = __ffma2_rn(dv, xs2, acc[k][2]);
+          if (tap == 4) bs[k] = __fadd2_rn(bs[k], dv);      // every tap sees the same dy: the centre tap takes the bias sums
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+    float* mine = s_acc + (size_t)tid * SW2_VALS;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { mine[(k * 3 + c) * 2] = acc[k][c].x; mine[(k * 3 + c) * 2 + 1] = acc[k][c].y; }
+    if (tap == 4) {
+      float* bm = s_acc + (size_t)SW2_LANES * 9 * SW2_VALS + lane_px * 14;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { bm[2 * k] = bs[k].x; bm[2 * k + 1] = bs[k].y; }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * 42; i += blockDim.x) {       // (tap, value) summed over the pixel lanes, one atomic per weight and block
+    const int tp = i / 42, v = i % 42;
+    float t = 0.f;
+    for (int l = 0; l < SW2_LANES; ++l) t += s_acc[(size_t)(l * 9 + tp) * SW2_VALS + v];
+    const int k = v / 6, c = (v % 6) / 2, co = 2 * k + (v & 1);
+    if (co < STEM_CO) atomicAdd(&dw[(co * STEM_CI + c) * 9 + tp], t);
+  }
+  if (db && tid < STEM_CO) {
+    float t = 0.f;
+    for (int l = 0; l < SW2_LANES; ++l) t += s_acc[(size_t)SW2_LANES * 9 * SW2_VALS + l * 14 + tid];
+    atomicAdd(&db[tid], t);
+  }
+}
+
 }  // namespace erfk
 
 using namespace erfk;
@@ -309,8 +394,17 @@ extern "C" int erf_stem_wgrad(const void* x, const void* dy, int N, int H, int W
     e = cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) launch_pdl(stem_wgrad_kernel<float>, dim3(grid), dim3(256), smem, (cudaStream_t)(s), (const float*)x, (const float*)dy, N, H, W, dw, db);
   } else {
-    e = cudaFuncSetAttribute(stem_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) launch_pdl(stem_wgrad_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, (cudaStream_t)(s), (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
+    static const bool v1 = getenv("ERF_STEM_WGRAD_V1") && atoi(getenv("ERF_STEM_WGRAD_V1")) != 0;
+    if (v1) {
+      e = cudaFuncSetAttribute(stem_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) launch_pdl(stem_wgrad_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, (cudaStream_t)(s), (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
+    } else {
+      size_t smem2 = (size_t)(SW2_LANES * 9 * SW2_VALS + SW2_LANES * 14) * sizeof(float);
+      if (smem2 < smem) smem2 = smem;
+      if (per_sm_env <= 0) grid = rows < 148 * 2 ? rows : 148 * 2;   // measured at the bench shape: 55.7 us (2 per SM) / 60.0 us (3) against 91 us for the first version
+      e = cudaFuncSetAttribute(stem_wgrad_bf16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e == cudaSuccess) launch_pdl(stem_wgrad_bf16_v2_kernel, dim3(grid), dim3(256), smem2, (cudaStream_t)(s), (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, N, H, W, dw, db);
+    }
   }
   if (e != cudaSuccess) {
     set_error("erf_stem_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
