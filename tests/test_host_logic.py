@@ -422,3 +422,35 @@ def test_whole_net_on_the_tensor_core_code_path():
     assert abs(float(loss.detach()) - float(lref.detach())) <= 1e-4 * abs(float(lref.detach()))
     for k in ("decoder.output_conv.weight", "decoder.layers.5.conv1x3_2.weight", "decoder.layers.1.bn2.weight"):
         assert_rel(m.get_parameter(k).grad.numpy(), sdo[k].grad.numpy(), WHOLE_NET_GRAD_TOL, k)
+
+
+def test_fork_join_runs_in_order_without_a_capturing_stream():
+    """ops.fork_join forks to a second stream only while a CUDA graph is being captured; everywhere else (CPU box, eager GPU code) it must simply run
+    the main closure and then the side closure on the caller's stream."""
+    from erfnet_pytorch_b200 import ops
+    order = []
+    ops.fork_join(lambda: order.append("side"), lambda: order.append("main"))
+    assert order == ["main", "side"]
+
+
+def test_prepacked_images_are_tied_to_one_step():
+    """erfnet._TcConv hands out images packed ahead of the layers only for the step (epoch) and the weight they were packed for: after
+    prepack_end() -- i.e. once the optimiser may have changed the weights -- nothing can pick them up again."""
+    import torch
+    from erfnet_pytorch_b200 import erfnet as E
+    from erfnet_pytorch_b200.ops import ConvSpec
+    tc = E._TcConv(ConvSpec(64, 64, 3, 3, 2, 1, 1))
+    w, other = torch.zeros(4), torch.zeros(4)
+    epoch = E._PREPACK["epoch"]
+    tc._pre = (epoch, w.data_ptr(), "fwd-images", "dgrad-images")
+    saved = dict(E._PREPACK)
+    try:
+        E._PREPACK.update(stream=object(), joined=True)
+        assert tc._prepacked(w, 2) == "fwd-images" and tc._prepacked(w, 3) == "dgrad-images"
+        assert tc._prepacked(other, 2) is None                    # another tensor (e.g. BN-folded eval weights)
+        E.prepack_end()
+        assert E._PREPACK["epoch"] == epoch + 1
+        assert tc._prepacked(w, 2) is None and tc._prepacked(w, 3) is None
+    finally:
+        E._PREPACK.update(saved)
+        E._PREPACK["epoch"] = epoch + 1
