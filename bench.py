@@ -6,8 +6,9 @@
 `value`  = training images/s (config[1]: ERFNet(20) encoder+decoder, batch 6/GPU at 512x1024, weighted
            CrossEntropy2d, Adam; data-parallel, weak scaling), inputs resident in HBM, CUDA-event timed,
            max over ranks.  `fwd` carries the inference (eval-mode, BN folded) images/s of the same net.
-`e2e`    = the same training step through the public API with HOST buffers: pinned H2D copy of the step's images
-           and labels and a D2H read of the loss inside the timed region.
+`e2e`    = the same training step through the public API with HOST buffers (FlatAdamTrainer.train_stream(..., host_losses=True)): pinned H2D
+           copy of every step's images and labels and a D2H read of every step's loss inside the timed region (each loss is handed to the
+           host loop one step behind the launches, so reading it does not stall the next launch).
 `fwd_b1` / `fwd_b32` / `eval_fullres` (ERF_BENCH_EXTRA=0 skips them) = inference at batch 1 (BASELINE configs[0], the eval_forwardTime.py
            shape: latency), at batch 32 (enough work to fill the 148 SMs) and configs[4] (batch 8 x 1024x2048 forward + argmax + iouEval.addBatch).
 `--impl reference` times the reference's CPU path (the oracle port of its torch arithmetic; the reference is pure
